@@ -1,0 +1,373 @@
+// HBM-bound passes of the path: feature cast, LayerNorm, the beta-gate pooling
+// and blend.  All are one-warp-per-row kernels with 16-byte vector accesses and
+// fp32 statistics; none needs tensor cores.
+#include "host_common.h"
+#include "sm100_ptx.cuh"
+
+namespace hriemo {
+
+constexpr int ROW_MAX_VEC = 8;  // 8 lanes-iterations x 32 lanes x 8 elements -> d <= 2048
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
+  u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  return u;
+}
+
+// A row of d elements held by one warp: lane l owns elements [(i*32 + l)*8, +8) for i < nv.
+struct RowRegs {
+  float v[ROW_MAX_VEC][8];
+};
+
+template <bool F32>
+__device__ __forceinline__ void load_row(RowRegs& r, const void* row, int d, int lane) {
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < d) {
+      if (F32) {
+        const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(row) + c);
+        const float4 a = __ldg(p), b = __ldg(p + 1);
+        r.v[i][0] = a.x; r.v[i][1] = a.y; r.v[i][2] = a.z; r.v[i][3] = a.w;
+        r.v[i][4] = b.x; r.v[i][5] = b.y; r.v[i][6] = b.z; r.v[i][7] = b.w;
+      } else {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(row) + c));
+        unpack8(u, r.v[i]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r.v[i][k] = 0.0f;
+    }
+  }
+}
+
+// In-place LayerNorm of a warp-held row (two-pass: mean, then biased variance).
+__device__ __forceinline__ void normalize_row(RowRegs& r, int d, int lane, const float* gamma,
+                                              const float* beta, float eps) {
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_VEC; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += r.v[i][k];
+  const float mean = warp_sum(s) / static_cast<float>(d);
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < d) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float t = r.v[i][k] - mean;
+        q += t * t;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(d) + eps);
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < d) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r.v[i][k] = (r.v[i][k] - mean) * rstd * g[k] + bb[k];
+    }
+  }
+}
+
+__device__ __forceinline__ void store_row(const RowRegs& r, __nv_bfloat16* yb, float* yf, int d, int lane) {
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < d) {
+      if (yb) *reinterpret_cast<uint4*>(yb + c) = pack8(r.v[i]);
+      if (yf) {
+        float4* p = reinterpret_cast<float4*>(yf + c);
+        p[0] = make_float4(r.v[i][0], r.v[i][1], r.v[i][2], r.v[i][3]);
+        p[1] = make_float4(r.v[i][4], r.v[i][5], r.v[i][6], r.v[i][7]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ cast
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, int64_t ld_in,
+                                     __nv_bfloat16* __restrict__ out, int64_t ld_out, int64_t rows,
+                                     int cols, int vec_ok) {
+  const int64_t chunks_per_row = ld_out / 8;
+  const int64_t total = rows * chunks_per_row;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = idx / chunks_per_row;
+    const int c = static_cast<int>(idx - row * chunks_per_row) * 8;
+    const float* src = in + row * ld_in + c;
+    float f[8];
+    if (vec_ok && c + 8 <= cols) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = (c + k < cols) ? __ldg(src + k) : 0.0f;
+    }
+    *reinterpret_cast<uint4*>(out + row * ld_out + c) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm
+template <bool F32>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const void* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ yb,
+                 float* __restrict__ yf, int64_t ldy, int64_t rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  RowRegs r;
+  const void* xr = F32 ? static_cast<const void*>(static_cast<const float*>(x) + row * ldx)
+                       : static_cast<const void*>(static_cast<const __nv_bfloat16*>(x) + row * ldx);
+  load_row<F32>(r, xr, d, lane);
+  normalize_row(r, d, lane, gamma, beta, eps);
+  store_row(r, yb ? yb + row * ldy : nullptr, yf ? yf + row * ldy : nullptr, d, lane);
+}
+
+// ------------------------------------------------------------------ gate: LN + masked mean
+// One CTA per utterance; warp w reduces rows t = w, w+8, ... in registers, then the
+// 8 partial sums are combined through shared memory in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float eps, int apply_ln,
+                      const uint8_t* __restrict__ pad, float* __restrict__ pooled, int64_t ld_pooled,
+                      int T, int d) {
+  extern __shared__ float part[];  // [8][d]
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  RowRegs acc;
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_VEC; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc.v[i][k] = 0.0f;
+  int count = 0;
+  for (int t = warp; t < T; t += 8) {
+    const bool valid = pad == nullptr || pad[static_cast<int64_t>(b) * T + t] == 0;
+    if (!valid) continue;  // warp-uniform
+    ++count;
+    RowRegs r;
+    load_row<false>(r, x + (static_cast<int64_t>(b) * T + t) * ldx, d, lane);
+    if (apply_ln) normalize_row(r, d, lane, gamma, beta, eps);
+#pragma unroll
+    for (int i = 0; i < ROW_MAX_VEC; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc.v[i][k] += r.v[i][k];
+  }
+  __shared__ int counts[8];
+  if (lane == 0) counts[warp] = count;
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < d) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) part[warp * d + c + k] = acc.v[i][k];
+    }
+  }
+  __syncthreads();
+  int total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) total += counts[w];
+  // mask None -> plain mean over T; else sum / clamp(count, 1)   (beta_gate_tacfn.py:17-24)
+  const float denom = pad == nullptr ? static_cast<float>(T) : fmaxf(static_cast<float>(total), 1.0f);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[w * d + c];
+    pooled[static_cast<int64_t>(b) * ld_pooled + c] = s / denom;
+  }
+}
+
+__global__ void gate_input_kernel(const float* __restrict__ a, const float* __restrict__ t,
+                                  float* __restrict__ g, int B, int d) {
+  const int64_t total = static_cast<int64_t>(B) * d;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = idx / d;
+    const int c = static_cast<int>(idx - b * d);
+    const float av = a[idx], tv = t[idx];
+    float* gr = g + b * 4 * d;
+    gr[c] = av;
+    gr[d + c] = tv;
+    gr[2 * d + c] = fabsf(av - tv);
+    gr[3 * d + c] = av * tv;
+  }
+}
+
+// ------------------------------------------------------------------ gate: blend
+__global__ void __launch_bounds__(256)
+gate_blend_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int T_a,
+                  const __nv_bfloat16* __restrict__ t, int64_t ldt, const float* __restrict__ ga,
+                  const float* __restrict__ ba, const float* __restrict__ gt, const float* __restrict__ bt,
+                  float eps, int apply_ln, const float* __restrict__ w, int w_is_scalar,
+                  __nv_bfloat16* __restrict__ hb, float* __restrict__ hf, int64_t ldh,
+                  float* __restrict__ beta_out, int B, int L, int d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= static_cast<int64_t>(B) * L) return;
+  const int b = static_cast<int>(row / L);
+  const int tt = static_cast<int>(row - static_cast<int64_t>(b) * L);
+  RowRegs ra, rt;
+  load_row<false>(ra, a + (static_cast<int64_t>(b) * T_a + tt) * lda, d, lane);
+  load_row<false>(rt, t + (static_cast<int64_t>(b) * L + tt) * ldt, d, lane);
+  if (apply_ln) {
+    normalize_row(ra, d, lane, ga, ba, eps);
+    normalize_row(rt, d, lane, gt, bt, eps);
+  }
+  float wsum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < d) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float wv = w_is_scalar ? __ldg(w + b) : __ldg(w + static_cast<int64_t>(b) * d + c + k);
+        wsum += wv;
+        ra.v[i][k] = wv * ra.v[i][k] + (1.0f - wv) * rt.v[i][k];
+      }
+    }
+  }
+  store_row(ra, hb ? hb + row * ldh : nullptr, hf ? hf + row * ldh : nullptr, d, lane);
+  if (tt == 0 && beta_out != nullptr) {
+    wsum = warp_sum(wsum);
+    if (lane == 0) beta_out[b] = w_is_scalar ? __ldg(w + b) : wsum / static_cast<float>(d);
+  }
+}
+
+__global__ void mean_over_time_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int L,
+                                      int d) {
+  const int64_t total = static_cast<int64_t>(B) * d;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = idx / d;
+    const int c = static_cast<int>(idx - b * d);
+    float s = 0.0f;
+    for (int t = 0; t < L; ++t) s += x[(b * L + t) * d + c];
+    out[idx] = s / static_cast<float>(L);
+  }
+}
+
+static unsigned grid_for(int64_t work_items, int block) {
+  int64_t g = (work_items + block - 1) / block;
+  const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
+static bool row_shape_ok(int d) { return d > 0 && d % 8 == 0 && d <= ROW_MAX_VEC * 256; }
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace hriemo
+
+using namespace hriemo;
+
+extern "C" int hriemo_cast_f32_to_bf16(const float* in, int64_t ld_in, void* out, int64_t ld_out,
+                                       int64_t rows, int32_t cols, void* stream) {
+  HRIEMO_REQUIRE(in && out, "cast: null pointer");
+  HRIEMO_REQUIRE(rows >= 0 && cols > 0 && ld_in >= cols && ld_out >= cols && ld_out % 8 == 0,
+                 "cast: bad shape rows=%lld cols=%d ld_in=%lld ld_out=%lld", (long long)rows, cols,
+                 (long long)ld_in, (long long)ld_out);
+  HRIEMO_REQUIRE(aligned16(out), "cast: out misaligned");
+  if (rows == 0) return HRIEMO_OK;
+  const int vec_ok = aligned16(in) && ld_in % 4 == 0;
+  const int64_t total = rows * (ld_out / 8);
+  cast_f32_bf16_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, ld_in, static_cast<__nv_bfloat16*>(out), ld_out, rows, cols, vec_ok);
+  return check_launch("cast_f32_to_bf16");
+}
+
+extern "C" int hriemo_layernorm(const void* x, int32_t x_is_f32, int64_t ldx, const float* gamma,
+                                const float* beta, float eps, void* y_bf16, float* y_f32, int64_t ldy,
+                                int64_t rows, int32_t d, void* stream) {
+  HRIEMO_REQUIRE(x && gamma && beta && (y_bf16 || y_f32), "layernorm: null pointer");
+  HRIEMO_REQUIRE(row_shape_ok(d), "layernorm: d=%d must be a multiple of 8 and <= %d", d, ROW_MAX_VEC * 256);
+  HRIEMO_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(gamma) && aligned16(beta) &&
+                     aligned16(y_bf16) && aligned16(y_f32),
+                 "layernorm: misaligned operand");
+  if (rows <= 0) return HRIEMO_OK;
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (x_is_f32)
+    layernorm_kernel<true><<<grid, 256, 0, s>>>(x, ldx, gamma, beta, eps, static_cast<__nv_bfloat16*>(y_bf16),
+                                                y_f32, ldy, rows, d);
+  else
+    layernorm_kernel<false><<<grid, 256, 0, s>>>(x, ldx, gamma, beta, eps, static_cast<__nv_bfloat16*>(y_bf16),
+                                                 y_f32, ldy, rows, d);
+  return check_launch("layernorm");
+}
+
+extern "C" int hriemo_ln_masked_mean(const void* x, int64_t ldx, const float* gamma, const float* beta,
+                                     float eps, int32_t apply_ln, const uint8_t* pad, float* pooled,
+                                     int64_t ld_pooled, int32_t B, int32_t T, int32_t d, void* stream) {
+  HRIEMO_REQUIRE(x && pooled && (!apply_ln || (gamma && beta)), "ln_masked_mean: null pointer");
+  HRIEMO_REQUIRE(row_shape_ok(d) && B > 0 && T > 0, "ln_masked_mean: bad shape B=%d T=%d d=%d", B, T, d);
+  HRIEMO_REQUIRE(ldx % 8 == 0 && aligned16(x) && aligned16(gamma) && aligned16(beta),
+                 "ln_masked_mean: misaligned operand");
+  const size_t smem = static_cast<size_t>(8) * d * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(ln_masked_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4);
+    attr = true;
+  }
+  ln_masked_mean_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, apply_ln, pad, pooled, ld_pooled, T, d);
+  return check_launch("ln_masked_mean");
+}
+
+extern "C" int hriemo_gate_input(const float* a_pool, const float* t_pool, float* g, int32_t B, int32_t d,
+                                 void* stream) {
+  HRIEMO_REQUIRE(a_pool && t_pool && g && B > 0 && d > 0, "gate_input: bad argument");
+  gate_input_kernel<<<grid_for(static_cast<int64_t>(B) * d, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      a_pool, t_pool, g, B, d);
+  return check_launch("gate_input");
+}
+
+extern "C" int hriemo_gate_blend(const void* a, int64_t lda, int32_t T_a, const void* t, int64_t ldt,
+                                 const float* gamma_a, const float* beta_a, const float* gamma_t,
+                                 const float* beta_t, float eps, int32_t apply_ln, const float* w,
+                                 int32_t w_is_scalar, void* h_bf16, float* h_f32, int64_t ldh,
+                                 float* beta_out, int32_t B, int32_t L, int32_t d, void* stream) {
+  HRIEMO_REQUIRE(a && t && w && (h_bf16 || h_f32), "gate_blend: null pointer");
+  HRIEMO_REQUIRE(!apply_ln || (gamma_a && beta_a && gamma_t && beta_t), "gate_blend: LN params missing");
+  HRIEMO_REQUIRE(row_shape_ok(d) && B > 0 && L > 0 && T_a >= L, "gate_blend: bad shape B=%d L=%d T_a=%d d=%d",
+                 B, L, T_a, d);
+  HRIEMO_REQUIRE(lda % 8 == 0 && ldt % 8 == 0 && ldh % 8 == 0 && aligned16(a) && aligned16(t) &&
+                     aligned16(h_bf16) && aligned16(h_f32),
+                 "gate_blend: misaligned operand");
+  const int64_t rows = static_cast<int64_t>(B) * L;
+  gate_blend_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), lda, T_a, static_cast<const __nv_bfloat16*>(t), ldt, gamma_a,
+      beta_a, gamma_t, beta_t, eps, apply_ln, w, w_is_scalar, static_cast<__nv_bfloat16*>(h_bf16), h_f32,
+      ldh, beta_out, B, L, d);
+  return check_launch("gate_blend");
+}
+
+extern "C" int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d,
+                                     void* stream) {
+  HRIEMO_REQUIRE(x && out && B > 0 && L > 0 && d > 0, "mean_over_time: bad argument");
+  mean_over_time_kernel<<<grid_for(static_cast<int64_t>(B) * d, 256), 256, 0,
+                          static_cast<cudaStream_t>(stream)>>>(x, out, B, L, d);
+  return check_launch("mean_over_time");
+}

@@ -1,0 +1,328 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:
+//   out = epilogue(A[M,K] . W[N,K]^T + bias)
+// TMA (128B-swizzled tiles) -> shared-memory ring -> tcgen05.mma (fp32 accumulators
+// in TMEM, double-buffered) -> epilogue warps (tcgen05.ld, bias/ReLU/residual,
+// bf16 or fp32 stores, optional per-utterance V^T scatter).
+//
+// Replaces the nn.Linear / MHA projection calls of the reference forward
+// (models/cross_modal_block_tacfn.py:24-52,74-119; models/emotion_decoder.py:14-27;
+//  models/mosei_fusion_with_emotion_decoder.py:41-42).
+//
+// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4..7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31, one
+// accumulator row per thread).
+#include "host_common.h"
+#include "sm100_ptx.cuh"
+
+namespace hriemo {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int GEMM_THREADS = 256;
+
+struct GemmKernelParams {
+  int64_t M;
+  int N, K;
+  int epilogue;
+  const float* bias;
+  void* out;
+  int64_t ldo;
+  const void* resid;
+  int64_t ldr;
+  __nv_bfloat16* vt;
+  int T, T_pad, v_col_begin;
+  int num_n_blocks, num_k_blocks;
+  int64_t num_tiles;
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
+  static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
+};
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&f)[32]) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 v;
+    v.x = pack_bf16(f[i * 8 + 0], f[i * 8 + 1]);
+    v.y = pack_bf16(f[i * 8 + 2], f[i * 8 + 3]);
+    v.z = pack_bf16(f[i * 8 + 4], f[i * 8 + 5]);
+    v.w = pack_bf16(f[i * 8 + 6], f[i * 8 + 7]);
+    d4[i] = v;
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const GemmKernelParams p) {
+  using L = GemmSmem<BN, STAGES>;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages (power of two: 256 or 512)
+  constexpr uint32_t STAGE_TX = A_STAGE_BYTES + L::B_STAGE_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base + L::A_OFF;
+  const uint32_t sB = smem_base + L::B_OFF;
+  const uint32_t bar_full = smem_base + L::BAR_OFF;
+  const uint32_t bar_empty = bar_full + STAGES * 8;
+  const uint32_t bar_tfull = bar_empty + STAGES * 8;
+  const uint32_t bar_tempty = bar_tfull + 2 * 8;
+  const uint32_t tmem_slot = bar_tempty + 2 * 8;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + s * 8, 1);
+      mbar_init(bar_empty + s * 8, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + s * 8, 1);
+      mbar_init(bar_tempty + s * 8, 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m0 = static_cast<int>(tile / p.num_n_blocks) * BM;
+        const int n0 = static_cast<int>(tile % p.num_n_blocks) * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(bar_empty + stage * 8, phase ^ 1);
+          mbar_arrive_expect_tx(bar_full + stage * 8, STAGE_TX);
+          tma_load_2d(&tm_a, bar_full + stage * 8, sA + stage * A_STAGE_BYTES, kb * BK, m0);
+          tma_load_2d(&tm_b, bar_full + stage * 8, sB + stage * L::B_STAGE_BYTES, kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      uint32_t stage = 0, phase = 0;
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t as = it & 1u;
+        const uint32_t aphase = (it >> 1) & 1u;
+        mbar_wait(bar_tempty + as * 8, aphase ^ 1);  // epilogue drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(bar_full + stage * 8, phase);
+          tc_fence_after_sync();
+          const uint64_t a_desc = umma_desc_sw128(sA + stage * A_STAGE_BYTES);
+          const uint64_t b_desc = umma_desc_sw128(sB + stage * L::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes (= 16 bf16) along K inside the swizzle atom: +2 in addr>>4 units
+            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(bar_empty + stage * 8);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + as * 8);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it & 1u;
+      const uint32_t aphase = (it >> 1) & 1u;
+      const int64_t m = (tile / p.num_n_blocks) * BM + row_in_tile;
+      const int n0 = static_cast<int>(tile % p.num_n_blocks) * BN;
+      const bool row_ok = m < p.M;
+      int64_t vt_row_base = 0;  // (b * dv) * T_pad + t
+      if (p.epilogue == HRIEMO_EPI_QKV && row_ok) {
+        const int64_t b = m / p.T;
+        const int t = static_cast<int>(m - b * p.T);
+        vt_row_base = b * static_cast<int64_t>(p.N - p.v_col_begin) * p.T_pad + t;
+      }
+      mbar_wait(bar_tfull + as * 8, aphase);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n = n0 + c * 32;
+        if (n >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(t_row + c * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (p.bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = __ldg(bp + i);
+            f[i * 4 + 0] += b4.x; f[i * 4 + 1] += b4.y; f[i * 4 + 2] += b4.z; f[i * 4 + 3] += b4.w;
+          }
+        }
+        if (row_ok) {
+        switch (p.epilogue) {
+          case HRIEMO_EPI_BIAS_RELU:
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+            store_bf16x32(static_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n, f);
+            break;
+          case HRIEMO_EPI_BIAS_RESID: {
+            const uint4* rp = reinterpret_cast<const uint4*>(
+                static_cast<const __nv_bfloat16*>(p.resid) + m * p.ldr + n);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 r4 = __ldg(rp + i);
+              f[i * 8 + 0] += bf16_lo(r4.x); f[i * 8 + 1] += bf16_hi(r4.x);
+              f[i * 8 + 2] += bf16_lo(r4.y); f[i * 8 + 3] += bf16_hi(r4.y);
+              f[i * 8 + 4] += bf16_lo(r4.z); f[i * 8 + 5] += bf16_hi(r4.z);
+              f[i * 8 + 6] += bf16_lo(r4.w); f[i * 8 + 7] += bf16_hi(r4.w);
+            }
+            store_bf16x32(static_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n, f);
+            break;
+          }
+          case HRIEMO_EPI_BIAS_RESID_F32:
+          case HRIEMO_EPI_BIAS_F32: {
+            if (p.epilogue == HRIEMO_EPI_BIAS_RESID_F32) {
+              const float4* rp =
+                  reinterpret_cast<const float4*>(static_cast<const float*>(p.resid) + m * p.ldr + n);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 r4 = __ldg(rp + i);
+                f[i * 4 + 0] += r4.x; f[i * 4 + 1] += r4.y; f[i * 4 + 2] += r4.z; f[i * 4 + 3] += r4.w;
+              }
+            }
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + m * p.ldo + n);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              op[i] = make_float4(f[i * 4 + 0], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
+            break;
+          }
+          case HRIEMO_EPI_QKV:
+            if (n < p.v_col_begin) {
+              store_bf16x32(static_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n, f);
+            } else {
+              // V^T scatter: consecutive lanes hold consecutive t -> coalesced 2-byte stores
+              __nv_bfloat16* vp = p.vt + vt_row_base + static_cast<int64_t>(n - p.v_col_begin) * p.T_pad;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) vp[static_cast<int64_t>(i) * p.T_pad] = __float2bfloat16_rn(f[i]);
+            }
+            break;
+          default:  // HRIEMO_EPI_BIAS
+            store_bf16x32(static_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n, f);
+            break;
+        }
+        }
+        __syncwarp();  // reconverge before the next warp-collective tcgen05.ld
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + as * 8);
+    }
+  }
+
+  // ===================== teardown =====================
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const hriemo_gemm_args& a, cudaStream_t stream) {
+  using L = GemmSmem<BN, STAGES>;
+  static_assert(L::DYN_BYTES <= 227 * 1024, "shared memory budget");
+  CUtensorMap tm_a, tm_b;
+  int rc = make_tmap_bf16_2d(&tm_a, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, BK, BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tm_b, a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldw, BK, BN);
+  if (rc) return rc;
+
+  GemmKernelParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.epilogue = a.epilogue; p.bias = a.bias;
+  p.out = a.out; p.ldo = a.ldo; p.resid = a.resid; p.ldr = a.ldr;
+  p.vt = static_cast<__nv_bfloat16*>(a.vt); p.T = a.T; p.T_pad = a.T_pad; p.v_col_begin = a.v_col_begin;
+  p.num_n_blocks = (a.N + BN - 1) / BN;
+  p.num_k_blocks = (a.K + BK - 1) / BK;
+  const int64_t num_m_blocks = (a.M + BM - 1) / BM;
+  p.num_tiles = num_m_blocks * p.num_n_blocks;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+    if (e != cudaSuccess)
+      return set_error(HRIEMO_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int64_t sms = device_sm_count();
+  const unsigned grid = static_cast<unsigned>(p.num_tiles < sms ? p.num_tiles : sms);
+  gemm_bf16_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tm_a, tm_b, p);
+  return check_launch("gemm_bf16");
+}
+
+}  // namespace hriemo
+
+extern "C" int hriemo_gemm_bf16(const hriemo_gemm_args* a, void* stream) {
+  using namespace hriemo;
+  HRIEMO_REQUIRE(a != nullptr, "gemm: null args");
+  HRIEMO_REQUIRE(a->A && a->W && a->out, "gemm: null operand");
+  HRIEMO_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, "gemm: bad shape M=%lld N=%d K=%d",
+                 (long long)a->M, a->N, a->K);
+  HRIEMO_REQUIRE(a->N % 32 == 0, "gemm: N=%d must be a multiple of 32", a->N);
+  HRIEMO_REQUIRE(a->K % 8 == 0 && a->lda % 8 == 0 && a->ldw % 8 == 0,
+                 "gemm: K=%d, lda=%lld, ldw=%lld must be multiples of 8", a->K, (long long)a->lda,
+                 (long long)a->ldw);
+  HRIEMO_REQUIRE(a->lda >= a->K && a->ldw >= a->K, "gemm: leading dimension smaller than K");
+  HRIEMO_REQUIRE(a->epilogue >= HRIEMO_EPI_BIAS && a->epilogue <= HRIEMO_EPI_BIAS_F32,
+                 "gemm: unknown epilogue %d", a->epilogue);
+  const bool f32_out = a->epilogue == HRIEMO_EPI_BIAS_RESID_F32 || a->epilogue == HRIEMO_EPI_BIAS_F32;
+  HRIEMO_REQUIRE(a->ldo % (f32_out ? 4 : 8) == 0, "gemm: ldo=%lld misaligned", (long long)a->ldo);
+  HRIEMO_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15u) == 0, "gemm: out not 16-byte aligned");
+  if (a->epilogue == HRIEMO_EPI_BIAS_RESID || a->epilogue == HRIEMO_EPI_BIAS_RESID_F32) {
+    HRIEMO_REQUIRE(a->resid != nullptr, "gemm: residual epilogue without resid");
+    HRIEMO_REQUIRE(a->ldr % (f32_out ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(a->resid) & 15u) == 0,
+                   "gemm: resid misaligned");
+  }
+  if (a->epilogue == HRIEMO_EPI_QKV) {
+    HRIEMO_REQUIRE(a->vt != nullptr && a->T > 0 && a->T_pad >= a->T && a->T_pad % 8 == 0,
+                   "gemm: QKV epilogue needs vt, T, T_pad (multiple of 8)");
+    HRIEMO_REQUIRE(a->v_col_begin > 0 && a->v_col_begin < a->N && a->v_col_begin % 32 == 0,
+                   "gemm: bad v_col_begin %d", a->v_col_begin);
+    HRIEMO_REQUIRE(a->M % a->T == 0, "gemm: M must be B*T in QKV mode");
+  }
+  if (a->bias) HRIEMO_REQUIRE((reinterpret_cast<uintptr_t>(a->bias) & 15u) == 0, "gemm: bias misaligned");
+  if (a->M == 0) return HRIEMO_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // Wide tiles for wide outputs; 128-column tiles keep more CTAs busy when N is small.
+  if (a->N >= 256 && a->N % 256 == 0) return launch_gemm<256, 4>(*a, s);
+  return launch_gemm<128, 6>(*a, s);
+}

@@ -1,0 +1,29 @@
+// Host-side helpers shared by the C-ABI entry points: error text, launch
+// counter, TMA tensor-map encoding through the driver entry point (no -lcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hriemo.h"
+
+namespace hriemo {
+
+int set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);
+
+// 2-D bf16 tensor map: dim0 (contiguous) extent `inner`, dim1 extent `outer`,
+// row pitch `pitch_elems`; box = box_inner x box_outer, 128-byte swizzle,
+// out-of-bounds elements read as zero.  Returns 0 or a negative error code.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
+                      uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer);
+
+int device_sm_count();
+
+#define HRIEMO_REQUIRE(cond, ...)                                      \
+  do {                                                                 \
+    if (!(cond)) return ::hriemo::set_error(HRIEMO_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+}  // namespace hriemo

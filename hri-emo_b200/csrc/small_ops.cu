@@ -1,0 +1,234 @@
+// CUDA-core kernels for the small, decision-sensitive parts of the path:
+//  * fp32 GEMM for the beta-gate MLP, the emotion head and the classifier head,
+//  * small-query attention (emotion decoder) and head-averaged attention maps.
+#include <math.h>
+
+#include "host_common.h"
+#include "sm100_ptx.cuh"
+
+namespace hriemo {
+
+// ------------------------------------------------------------------ fp32 GEMM
+// out[M,N] = act(A[M,K] . W[N,K]^T + bias); 64x64 tile, 16-wide K slab, 4x4 per thread.
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
+
+__global__ void __launch_bounds__(256)
+sgemm_f32_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, int64_t ldw,
+                 const float* __restrict__ bias, float* __restrict__ out, int64_t ldo, int64_t M, int N,
+                 int K, int act) {
+  __shared__ float As[SG_BK][SG_BM + 4];
+  __shared__ float Ws[SG_BK][SG_BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.y) * SG_BM;
+  const int n0 = blockIdx.x * SG_BN;
+  float acc[4][4] = {};
+  const int lr = tid >> 2;        // 0..63: row inside the tile
+  const int lk = (tid & 3) * 4;   // 0,4,8,12
+  for (int k0 = 0; k0 < K; k0 += SG_BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + lk + i;
+      const int64_t am = m0 + lr;
+      As[lk + i][lr] = (am < M && k < K) ? __ldg(A + am * lda + k) : 0.0f;
+      const int wn = n0 + lr;
+      Ws[lk + i][lr] = (wn < N && k < K) ? __ldg(W + static_cast<int64_t>(wn) * ldw + k) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = Ws[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.0f);
+      if (act == 1) v = fmaxf(v, 0.0f);
+      else if (act == 2) v = 1.0f / (1.0f + expf(-v));
+      out[m * ldo + n] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ small attention
+// One CTA per (utterance, block of up to 8 query rows); loops over heads.
+// Per head: scores for every key (thread per key), exact softmax per query row
+// (warp per row), optional head-averaged probabilities, then P.V (thread per column).
+constexpr int SA_NQ = 8;
+constexpr int SA_THREADS = 128;
+
+__global__ void __launch_bounds__(SA_THREADS)
+small_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k,
+                       int64_t ldk, const __nv_bfloat16* __restrict__ v, int64_t ldv,
+                       const uint8_t* __restrict__ key_pad, __nv_bfloat16* __restrict__ out, int64_t ldo,
+                       float* __restrict__ probs, int H, int Nq, int Tk, int dh, float scale) {
+  extern __shared__ float sm[];
+  float* qs = sm;                         // [SA_NQ][dh]
+  float* sc = qs + SA_NQ * dh;            // [SA_NQ][Tk]  scores -> probabilities
+  float* pavg = sc + SA_NQ * Tk;          // [SA_NQ][Tk]  (only if probs)
+  const int b = blockIdx.x;
+  const int qb = blockIdx.y * SA_NQ;
+  const int nq = min(SA_NQ, Nq - qb);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float inv_h = 1.0f / static_cast<float>(H);
+  if (probs)
+    for (int i = tid; i < SA_NQ * Tk; i += SA_THREADS) pavg[i] = 0.0f;
+
+  for (int h = 0; h < H; ++h) {
+    __syncthreads();
+    for (int i = tid; i < nq * dh; i += SA_THREADS) {
+      const int qi = i / dh, c = i - qi * dh;
+      qs[qi * dh + c] =
+          __bfloat162float(q[(static_cast<int64_t>(b) * Nq + qb + qi) * ldq + h * dh + c]) * scale;
+    }
+    __syncthreads();
+    // scores
+    for (int j = tid; j < Tk; j += SA_THREADS) {
+      const bool pad = key_pad != nullptr && key_pad[static_cast<int64_t>(b) * Tk + j] != 0;
+      float acc[SA_NQ];
+#pragma unroll
+      for (int qi = 0; qi < SA_NQ; ++qi) acc[qi] = 0.0f;
+      const __nv_bfloat16* kr = k + (static_cast<int64_t>(b) * Tk + j) * ldk + h * dh;
+      for (int c = 0; c < dh; c += 8) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(kr + c));
+        const float kv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                             bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+        for (int qi = 0; qi < SA_NQ; ++qi) {
+          if (qi < nq) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[qi] = fmaf(qs[qi * dh + c + e], kv[e], acc[qi]);
+          }
+        }
+      }
+#pragma unroll
+      for (int qi = 0; qi < SA_NQ; ++qi)
+        if (qi < nq) sc[qi * Tk + j] = pad ? -INFINITY : acc[qi];
+    }
+    __syncthreads();
+    // softmax per query row (a fully masked row gives NaN, like torch.softmax)
+    for (int qi = warp; qi < nq; qi += SA_THREADS / 32) {
+      float m = -INFINITY;
+      for (int j = lane; j < Tk; j += 32) m = fmaxf(m, sc[qi * Tk + j]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float s = 0.0f;
+      for (int j = lane; j < Tk; j += 32) {
+        const float e = expf(sc[qi * Tk + j] - m);
+        sc[qi * Tk + j] = e;
+        s += e;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float inv = 1.0f / s;
+      for (int j = lane; j < Tk; j += 32) {
+        const float pr = sc[qi * Tk + j] * inv;
+        sc[qi * Tk + j] = pr;
+        if (probs) pavg[qi * Tk + j] += pr * inv_h;
+      }
+    }
+    __syncthreads();
+    // P.V
+    if (out != nullptr) {
+      for (int c = tid; c < dh; c += SA_THREADS) {
+        float acc[SA_NQ];
+#pragma unroll
+        for (int qi = 0; qi < SA_NQ; ++qi) acc[qi] = 0.0f;
+        const __nv_bfloat16* vc = v + static_cast<int64_t>(b) * Tk * ldv + h * dh + c;
+        for (int j = 0; j < Tk; ++j) {
+          const float vv = __bfloat162float(vc[static_cast<int64_t>(j) * ldv]);
+#pragma unroll
+          for (int qi = 0; qi < SA_NQ; ++qi)
+            if (qi < nq) acc[qi] = fmaf(sc[qi * Tk + j], vv, acc[qi]);
+        }
+#pragma unroll
+        for (int qi = 0; qi < SA_NQ; ++qi)
+          if (qi < nq)
+            out[(static_cast<int64_t>(b) * Nq + qb + qi) * ldo + h * dh + c] = __float2bfloat16_rn(acc[qi]);
+      }
+    }
+  }
+  if (probs) {
+    __syncthreads();
+    for (int i = tid; i < nq * Tk; i += SA_THREADS) {
+      const int qi = i / Tk, j = i - qi * Tk;
+      probs[(static_cast<int64_t>(b) * Nq + qb + qi) * Tk + j] = pavg[qi * Tk + j];
+    }
+  }
+}
+
+static int launch_small_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                  int64_t ldv, const uint8_t* key_pad, void* out, int64_t ldo, float* probs,
+                                  int B, int H, int Nq, int Tk, int dh, float scale, cudaStream_t s) {
+  const size_t smem = sizeof(float) * (static_cast<size_t>(SA_NQ) * dh + static_cast<size_t>(SA_NQ) * Tk * (probs ? 2 : 1));
+  if (smem > 200 * 1024) return set_error(HRIEMO_ERR_INVALID, "small_attention: Tk=%d too long", Tk);
+  static size_t attr = 48 * 1024;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+    if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "small_attention: %s", cudaGetErrorString(e));
+    attr = 200 * 1024;
+  }
+  dim3 grid(B, (Nq + SA_NQ - 1) / SA_NQ);
+  small_attention_kernel<<<grid, SA_THREADS, smem, s>>>(
+      static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k), ldk,
+      static_cast<const __nv_bfloat16*>(v), ldv, key_pad, static_cast<__nv_bfloat16*>(out), ldo, probs, H, Nq,
+      Tk, dh, scale);
+  return check_launch("small_attention");
+}
+
+}  // namespace hriemo
+
+using namespace hriemo;
+
+extern "C" int hriemo_sgemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                                float* out, int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t act,
+                                void* stream) {
+  HRIEMO_REQUIRE(A && W && out, "sgemm: null pointer");
+  HRIEMO_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ldo >= N, "sgemm: bad shape");
+  HRIEMO_REQUIRE(act >= 0 && act <= 2, "sgemm: unknown activation %d", act);
+  if (M == 0) return HRIEMO_OK;
+  HRIEMO_REQUIRE((M + SG_BM - 1) / SG_BM <= 65535, "sgemm: M too large");
+  dim3 grid((N + SG_BN - 1) / SG_BN, static_cast<unsigned>((M + SG_BM - 1) / SG_BM));
+  sgemm_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, lda, W, ldw, bias, out, ldo, M, N,
+                                                                       K, act);
+  return check_launch("sgemm_f32");
+}
+
+extern "C" int hriemo_small_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                      int64_t ldv, const uint8_t* key_pad, void* out_bf16, int64_t ldo,
+                                      float* probs, int32_t B, int32_t H, int32_t Nq, int32_t Tk, int32_t dh,
+                                      float scale, void* stream) {
+  HRIEMO_REQUIRE(q && k && v && out_bf16, "small_attention: null pointer");
+  HRIEMO_REQUIRE(B > 0 && B <= 2147483647 && H > 0 && Nq > 0 && Tk > 0 && dh > 0 && dh % 8 == 0,
+                 "small_attention: bad shape");
+  HRIEMO_REQUIRE(ldk % 8 == 0 && (reinterpret_cast<uintptr_t>(k) & 15u) == 0, "small_attention: K misaligned");
+  return launch_small_attention(q, ldq, k, ldk, v, ldv, key_pad, out_bf16, ldo, probs, B, H, Nq, Tk, dh, scale,
+                                static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int hriemo_attention_probs(const void* q, int64_t ldq, const void* k, int64_t ldk,
+                                      const uint8_t* key_pad, float* probs, int32_t B, int32_t H, int32_t Tq,
+                                      int32_t Tk, int32_t dh, float scale, void* stream) {
+  HRIEMO_REQUIRE(q && k && probs, "attention_probs: null pointer");
+  HRIEMO_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0 && dh > 0 && dh % 8 == 0, "attention_probs: bad shape");
+  HRIEMO_REQUIRE(ldk % 8 == 0 && (reinterpret_cast<uintptr_t>(k) & 15u) == 0, "attention_probs: K misaligned");
+  HRIEMO_REQUIRE((Tq + SA_NQ - 1) / SA_NQ <= 65535, "attention_probs: Tq too large");
+  return launch_small_attention(q, ldq, k, ldk, nullptr, 0, key_pad, nullptr, 0, probs, B, H, Tq, Tk, dh, scale,
+                                static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,99 @@
+"""ctypes binding of libhriemo_b200.so (C ABI declared in include/hriemo.h).
+
+There is no fallback: if the shared library is missing or a call fails, an
+exception is raised.  PyTorch is only used for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhriemo_b200.so")
+
+EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESID, EPI_BIAS_RESID_F32, EPI_QKV, EPI_BIAS_F32 = range(6)
+ACT_NONE, ACT_RELU, ACT_SIGMOID = range(3)
+
+
+class HriemoError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("lda", C.c_int64),
+        ("W", C.c_void_p), ("ldw", C.c_int64),
+        ("bias", C.c_void_p),
+        ("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32),
+        ("epilogue", C.c_int32), ("reserved0", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("resid", C.c_void_p), ("ldr", C.c_int64),
+        ("vt", C.c_void_p), ("T", C.c_int32), ("T_pad", C.c_int32),
+        ("v_col_begin", C.c_int32), ("reserved1", C.c_int32),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_int64),
+        ("k", C.c_void_p), ("ldk", C.c_int64),
+        ("vt", C.c_void_p), ("Tk_pad", C.c_int32), ("reserved0", C.c_int32),
+        ("key_pad", C.c_void_p),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("B", C.c_int32), ("H", C.c_int32), ("Tq", C.c_int32), ("Tk", C.c_int32), ("dh", C.c_int32),
+        ("scale", C.c_float),
+    ]
+
+
+_P, _I64, _I32, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+
+# name -> (restype, argtypes); must list every symbol include/hriemo.h declares
+SIGNATURES = {
+    "hriemo_version": (C.c_int, []),
+    "hriemo_last_error": (C.c_char_p, []),
+    "hriemo_launch_count": (C.c_int64, []),
+    "hriemo_cast_f32_to_bf16": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _P]),
+    "hriemo_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _P]),
+    "hriemo_attention_bf16": (C.c_int, [C.POINTER(AttnArgs), _P]),
+    "hriemo_attention_probs": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I32, _I32, _I32, _I32, _I32, _F, _P]),
+    "hriemo_small_attention": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P,
+                                          _I32, _I32, _I32, _I32, _I32, _F, _P]),
+    "hriemo_layernorm": (C.c_int, [_P, _I32, _I64, _P, _P, _F, _P, _P, _I64, _I64, _I32, _P]),
+    "hriemo_ln_masked_mean": (C.c_int, [_P, _I64, _P, _P, _F, _I32, _P, _P, _I64, _I32, _I32, _I32, _P]),
+    "hriemo_gate_input": (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
+    "hriemo_sgemm_f32": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I64, _I64, _I32, _I32, _I32, _P]),
+    "hriemo_gate_blend": (C.c_int, [_P, _I64, _I32, _P, _I64, _P, _P, _P, _P, _F, _I32, _P, _I32,
+                                     _P, _P, _I64, _P, _I32, _I32, _I32, _P]),
+    "hriemo_mean_over_time": (C.c_int, [_P, _P, _I32, _I32, _I32, _P]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HriemoError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+            "There is no CPU or PyTorch fallback for the HRI-EMO B200 kernels."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().hriemo_last_error()
+        raise HriemoError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def launch_count() -> int:
+    return int(load().hriemo_launch_count())

@@ -1,0 +1,238 @@
+"""torch.Tensor-level wrappers over the C ABI (one function per kernel).
+
+Every function enqueues on the current CUDA stream and returns freshly
+allocated tensors owned by the caller.  2-D operands may be row-strided views
+(e.g. a column slice of a wider buffer): the row pitch is passed as the leading
+dimension, the last dimension must be contiguous.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import lib as _l
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+LN_EPS = 1e-5
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk2d(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise _l.HriemoError(f"{name}: expected a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise _l.HriemoError(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise _l.HriemoError(f"{name}: expected a 2-D tensor with a contiguous last dim, got {tuple(t.shape)} / {t.stride()}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _mask_u8(mask: Optional[torch.Tensor], B: int, T: int, name: str) -> Optional[torch.Tensor]:
+    if mask is None:
+        return None
+    if tuple(mask.shape) != (B, T):
+        raise _l.HriemoError(f"{name}: mask shape {tuple(mask.shape)} != {(B, T)}")
+    m = mask.contiguous()
+    return m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ------------------------------------------------------------------ cast
+def cast_bf16(x: torch.Tensor, ld_out: Optional[int] = None) -> torch.Tensor:
+    """fp32 [rows, cols] -> bf16 [rows, ld_out] (zero-padded columns)."""
+    _chk2d(x, f32, "cast_bf16")
+    rows, cols = x.shape
+    ld_out = round_up(cols, 8) if ld_out is None else ld_out
+    out = torch.empty((rows, ld_out), dtype=bf16, device=x.device)
+    _l.check(_l.load().hriemo_cast_f32_to_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), ld_out, rows, cols,
+                                                _stream()), "cast_f32_to_bf16")
+    return out
+
+
+# ------------------------------------------------------------------ GEMM
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int = _l.EPI_BIAS,
+         resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = epilogue(a[M,K] @ w[N,K]^T + bias) on tcgen05 tensor cores."""
+    _chk2d(a, bf16, "gemm A")
+    _chk2d(w, bf16, "gemm W")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise _l.HriemoError(f"gemm: K mismatch {a.shape} vs {w.shape}")
+    f32_out = epilogue in (_l.EPI_BIAS_RESID_F32, _l.EPI_BIAS_F32)
+    if out is None:
+        out = torch.empty((M, N), dtype=f32 if f32_out else bf16, device=a.device)
+    _chk2d(out, f32 if f32_out else bf16, "gemm out")
+    args = _l.GemmArgs()
+    args.A, args.lda, args.W, args.ldw = a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0)
+    args.bias = _ptr(bias)
+    args.M, args.N, args.K, args.epilogue = M, N, K, epilogue
+    args.out, args.ldo = out.data_ptr(), out.stride(0)
+    if resid is not None:
+        _chk2d(resid, f32 if f32_out else bf16, "gemm resid")
+        args.resid, args.ldr = resid.data_ptr(), resid.stride(0)
+    _l.check(_l.load().hriemo_gemm_bf16(C.byref(args), _stream()), "gemm_bf16")
+    return out
+
+
+def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], T: int,
+             v_col_begin: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[Q|K|V] projection of a [B*T, K] stream.  Returns (qk [B*T, v_col_begin] bf16 row-major,
+    vt [B, N - v_col_begin, T_pad] bf16 = per-utterance V^T, columns t >= T unspecified)."""
+    _chk2d(a, bf16, "gemm_qkv A")
+    _chk2d(w, bf16, "gemm_qkv W")
+    M, K = a.shape
+    N = w.shape[0]
+    B = M // T
+    T_pad = round_up(T, 8)
+    qk = torch.empty((M, v_col_begin), dtype=bf16, device=a.device)
+    vt = torch.empty((B, N - v_col_begin, T_pad), dtype=bf16, device=a.device)
+    args = _l.GemmArgs()
+    args.A, args.lda, args.W, args.ldw = a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0)
+    args.bias = _ptr(bias)
+    args.M, args.N, args.K, args.epilogue = M, N, K, _l.EPI_QKV
+    args.out, args.ldo = qk.data_ptr(), qk.stride(0)
+    args.vt, args.T, args.T_pad, args.v_col_begin = vt.data_ptr(), T, T_pad, v_col_begin
+    _l.check(_l.load().hriemo_gemm_bf16(C.byref(args), _stream()), "gemm_bf16[qkv]")
+    return qk, vt
+
+
+# ------------------------------------------------------------------ attention
+def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, key_pad: Optional[torch.Tensor],
+              B: int, H: int, Tq: int, Tk: int, dh: int) -> torch.Tensor:
+    """q: [B*Tq, >=H*dh] view, k: [B*Tk, >=H*dh] view, vt: [B, H*dh, Tk_pad].  Returns [B*Tq, H*dh] bf16."""
+    _chk2d(q, bf16, "attention q")
+    _chk2d(k, bf16, "attention k")
+    if vt.dtype != bf16 or vt.dim() != 3 or not vt.is_contiguous() or vt.shape[0] != B or vt.shape[1] != H * dh:
+        raise _l.HriemoError(f"attention: vt must be contiguous bf16 [B, H*dh, Tk_pad], got {tuple(vt.shape)}")
+    out = torch.empty((B * Tq, H * dh), dtype=bf16, device=q.device)
+    m = _mask_u8(key_pad, B, Tk, "attention")
+    args = _l.AttnArgs()
+    args.q, args.ldq, args.k, args.ldk = q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0)
+    args.vt, args.Tk_pad = vt.data_ptr(), vt.shape[2]
+    args.key_pad = _ptr(m)
+    args.out, args.ldo = out.data_ptr(), out.stride(0)
+    args.B, args.H, args.Tq, args.Tk, args.dh = B, H, Tq, Tk, dh
+    args.scale = 1.0 / math.sqrt(dh)
+    _l.check(_l.load().hriemo_attention_bf16(C.byref(args), _stream()), "attention_bf16")
+    return out
+
+
+def attention_probs(q: torch.Tensor, k: torch.Tensor, key_pad: Optional[torch.Tensor], B: int, H: int,
+                    Tq: int, Tk: int, dh: int) -> torch.Tensor:
+    """Head-averaged softmax probabilities [B, Tq, Tk] fp32 (return_attention path)."""
+    _chk2d(q, bf16, "attention_probs q")
+    _chk2d(k, bf16, "attention_probs k")
+    probs = torch.empty((B, Tq, Tk), dtype=f32, device=q.device)
+    m = _mask_u8(key_pad, B, Tk, "attention_probs")
+    _l.check(_l.load().hriemo_attention_probs(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), _ptr(m),
+                                               probs.data_ptr(), B, H, Tq, Tk, dh, 1.0 / math.sqrt(dh),
+                                               _stream()), "attention_probs")
+    return probs
+
+
+def small_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Optional[torch.Tensor],
+                    B: int, H: int, Nq: int, Tk: int, dh: int, want_probs: bool = False):
+    """Decoder attention: q [B*Nq, *], k/v [B*Tk, *] row-major views.  Returns (out bf16, probs|None)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _chk2d(t, bf16, f"small_attention {n}")
+    out = torch.empty((B * Nq, H * dh), dtype=bf16, device=q.device)
+    probs = torch.empty((B, Nq, Tk), dtype=f32, device=q.device) if want_probs else None
+    m = _mask_u8(key_pad, B, Tk, "small_attention")
+    _l.check(_l.load().hriemo_small_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+                                               v.stride(0), _ptr(m), out.data_ptr(), out.stride(0), _ptr(probs),
+                                               B, H, Nq, Tk, dh, 1.0 / math.sqrt(dh), _stream()),
+             "small_attention")
+    return out, probs
+
+
+# ------------------------------------------------------------------ LayerNorm
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, want_bf16: bool = True,
+              want_f32: bool = False, eps: float = LN_EPS):
+    """x: [rows, d] bf16 or f32 (residual already added).  Returns (y_bf16|None, y_f32|None)."""
+    if x.dtype not in (bf16, f32):
+        raise _l.HriemoError(f"layernorm: unsupported dtype {x.dtype}")
+    _chk2d(x, x.dtype, "layernorm x")
+    rows, d = x.shape
+    yb = torch.empty((rows, d), dtype=bf16, device=x.device) if want_bf16 else None
+    yf = torch.empty((rows, d), dtype=f32, device=x.device) if want_f32 else None
+    _l.check(_l.load().hriemo_layernorm(x.data_ptr(), int(x.dtype == f32), x.stride(0), gamma.data_ptr(),
+                                         beta.data_ptr(), eps, _ptr(yb), _ptr(yf), d, rows, d, _stream()),
+             "layernorm")
+    return yb, yf
+
+
+# ------------------------------------------------------------------ gate
+def ln_masked_mean(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
+                   pad: Optional[torch.Tensor], B: int, T: int, apply_ln: bool = True,
+                   eps: float = LN_EPS) -> torch.Tensor:
+    """x: [B*T, d] bf16 -> pooled [B, d] fp32 = masked_mean_t(LN(x))."""
+    _chk2d(x, bf16, "ln_masked_mean x")
+    d = x.shape[1]
+    pooled = torch.empty((B, d), dtype=f32, device=x.device)
+    m = _mask_u8(pad, B, T, "ln_masked_mean")
+    _l.check(_l.load().hriemo_ln_masked_mean(x.data_ptr(), x.stride(0), _ptr(gamma), _ptr(beta), eps,
+                                              int(apply_ln), _ptr(m), pooled.data_ptr(), d, B, T, d, _stream()),
+             "ln_masked_mean")
+    return pooled
+
+
+def gate_input(a_pool: torch.Tensor, t_pool: torch.Tensor) -> torch.Tensor:
+    B, d = a_pool.shape
+    g = torch.empty((B, 4 * d), dtype=f32, device=a_pool.device)
+    _l.check(_l.load().hriemo_gate_input(a_pool.data_ptr(), t_pool.data_ptr(), g.data_ptr(), B, d, _stream()),
+             "gate_input")
+    return g
+
+
+def sgemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = _l.ACT_NONE) -> torch.Tensor:
+    """fp32 CUDA-core GEMM: act(a[M,K] @ w[N,K]^T + bias)."""
+    _chk2d(a, f32, "sgemm A")
+    _chk2d(w, f32, "sgemm W")
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=f32, device=a.device)
+    _l.check(_l.load().hriemo_sgemm_f32(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+                                         out.data_ptr(), N, M, N, K, act, _stream()), "sgemm_f32")
+    return out
+
+
+def gate_blend(a: torch.Tensor, T_a: int, t: torch.Tensor, ln_a, ln_t, w: torch.Tensor, B: int, L: int,
+               apply_ln: bool = True, w_is_scalar: bool = False, want_bf16: bool = True,
+               want_f32: bool = False, eps: float = LN_EPS):
+    """a: [B*T_a, d] bf16, t: [B*L, d] bf16, w: [B, d] (or [B, 1] scalar gate) fp32.
+    Returns (h_bf16|None, h_f32|None, beta [B,1] fp32)."""
+    _chk2d(a, bf16, "gate_blend a")
+    _chk2d(t, bf16, "gate_blend t")
+    d = a.shape[1]
+    hb = torch.empty((B * L, d), dtype=bf16, device=a.device) if want_bf16 else None
+    hf = torch.empty((B * L, d), dtype=f32, device=a.device) if want_f32 else None
+    beta = torch.empty((B, 1), dtype=f32, device=a.device)
+    ga, ba = (ln_a if apply_ln else (None, None))
+    gt, bt = (ln_t if apply_ln else (None, None))
+    _l.check(_l.load().hriemo_gate_blend(a.data_ptr(), a.stride(0), T_a, t.data_ptr(), t.stride(0), _ptr(ga),
+                                          _ptr(ba), _ptr(gt), _ptr(bt), eps, int(apply_ln), w.data_ptr(),
+                                          int(w_is_scalar), _ptr(hb), _ptr(hf), d, beta.data_ptr(), B, L, d,
+                                          _stream()), "gate_blend")
+    return hb, hf, beta
+
+
+def mean_over_time(x: torch.Tensor, B: int, L: int) -> torch.Tensor:
+    _chk2d(x, f32, "mean_over_time")
+    d = x.shape[1]
+    out = torch.empty((B, d), dtype=f32, device=x.device)
+    _l.check(_l.load().hriemo_mean_over_time(x.data_ptr(), out.data_ptr(), B, L, d, _stream()), "mean_over_time")
+    return out

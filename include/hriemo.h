@@ -1,0 +1,189 @@
+/* hriemo.h — C ABI of libhriemo_b200.so: the B200 (sm_100a) kernels behind the
+ * HRI-EMO fusion-and-decode forward path.
+ *
+ * The reference (Makiato1999/HRI-EMO) is pure Python/PyTorch; its "FFI" for this
+ * path is the set of torch.nn calls made by models/*.py.  Each entry point below
+ * names the reference call group it replaces (paths relative to the reference
+ * repository root).  The Python nn.Modules in hri-emo_b200/models/ are the only
+ * intended callers (ctypes binding in hri-emo_b200/hriemo/lib.py; the binding a
+ * reference maintainer would add is shown in INTEGRATION.md).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless stated otherwise; the caller owns
+ *    all buffers; the library never allocates caller-visible memory, never
+ *    synchronises the host, and enqueues on the `stream` handle it is given
+ *    (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *  - "bf16" is a 16-bit bfloat16, "f32" IEEE binary32; matrices are row-major
+ *    with an explicit leading dimension in ELEMENTS;
+ *  - masks are uint8 (torch.bool storage), 1 = PAD (ignored key), like the
+ *    reference's key_padding_mask (models/cross_modal_block_tacfn.py:66-67);
+ *  - return value: 0 = ok, negative = error; hriemo_last_error() gives the text
+ *    of the last error raised on the calling thread.  No C++ exception crosses
+ *    the boundary.
+ */
+#ifndef HRIEMO_H_
+#define HRIEMO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRIEMO_VERSION 100 /* 0.1.0 */
+
+enum {
+  HRIEMO_OK = 0,
+  HRIEMO_ERR_INVALID = -1, /* bad shape / alignment / argument */
+  HRIEMO_ERR_CUDA = -2,    /* a CUDA runtime / driver call failed */
+  HRIEMO_ERR_DEVICE = -3   /* not an sm_100 device */
+};
+
+int hriemo_version(void);
+const char* hriemo_last_error(void);
+/* Number of kernels this library has launched from the calling process so far
+ * (monotonic; bench.py reports the delta over its timed region). */
+int64_t hriemo_launch_count(void);
+
+/* ---------------------------------------------------------------- cast ----
+ * fp32 features -> bf16 operand, zero-padding each row from `cols` to `ld_out`
+ * (TMA needs 16-byte row pitches; MOSEI d_audio=74 / d_text=300 are padded).
+ * Replaces the implicit autocast of models/mosei_fusion_with_emotion_decoder.py:64-66
+ * inputs and the `.float()` feature load (scripts/fusion/train_fusion_seq_level_decoder.py:151).
+ */
+int hriemo_cast_f32_to_bf16(const float* in, int64_t ld_in, void* out_bf16, int64_t ld_out,
+                            int64_t rows, int32_t cols, void* stream);
+
+/* ---------------------------------------------------------------- GEMM ----
+ * out = epilogue(A[M,K] . W[N,K]^T + bias) on tcgen05 tensor cores (TMA-fed,
+ * fp32 accumulation in TMEM).  W is exactly nn.Linear.weight ([out,in]).
+ * Replaces every nn.Linear / MHA in-projection / out-projection on the path:
+ *   models/cross_modal_block_tacfn.py:24-52 (MHA in/out projections, ffn_a, ffn_t),
+ *   models/emotion_decoder.py:14,20,25-27, models/mosei_fusion_with_emotion_decoder.py:41-42.
+ */
+enum {
+  HRIEMO_EPI_BIAS = 0,           /* out bf16 = acc + bias                                   */
+  HRIEMO_EPI_BIAS_RELU = 1,      /* out bf16 = relu(acc + bias)            (FFN first half) */
+  HRIEMO_EPI_BIAS_RESID = 2,     /* out bf16 = acc + bias + resid(bf16)    (pre-LayerNorm)  */
+  HRIEMO_EPI_BIAS_RESID_F32 = 3, /* out f32  = acc + bias + resid(f32)     (decoder stream) */
+  HRIEMO_EPI_QKV = 4,            /* cols [0,v_col_begin) -> out bf16 row-major;
+                                    cols [v_col_begin,N) -> vt[b][c][t] (per-utterance V^T) */
+  HRIEMO_EPI_BIAS_F32 = 5        /* out f32  = acc + bias                                   */
+};
+
+typedef struct hriemo_gemm_args {
+  const void* A;     /* bf16 [M,K]   */
+  int64_t lda;       /* multiple of 8 */
+  const void* W;     /* bf16 [N,K]   */
+  int64_t ldw;       /* multiple of 8 */
+  const float* bias; /* f32 [N] or NULL */
+  int64_t M;
+  int32_t N;         /* multiple of 32 */
+  int32_t K;         /* multiple of 8  */
+  int32_t epilogue;  /* HRIEMO_EPI_*   */
+  int32_t reserved0;
+  void* out;         /* bf16 or f32, see epilogue */
+  int64_t ldo;
+  const void* resid; /* bf16 or f32 [M,N], RESID modes only */
+  int64_t ldr;
+  /* HRIEMO_EPI_QKV only: rows are (b, t) = (m / T, m % T); V^T is
+   * vt[(b * (N - v_col_begin) + c) * T_pad + t] for c = n - v_col_begin. */
+  void* vt;          /* bf16 */
+  int32_t T;
+  int32_t T_pad;     /* multiple of 8, >= T */
+  int32_t v_col_begin;
+  int32_t reserved1;
+} hriemo_gemm_args;
+
+int hriemo_gemm_bf16(const hriemo_gemm_args* args, void* stream);
+
+/* ----------------------------------------------------------- attention ----
+ * O = softmax(Q K^T * scale + key_padding) V per (utterance, head), flash-style
+ * on tcgen05 (S and O accumulate in TMEM, online softmax in registers).
+ * Replaces the scaled_dot_product_attention inside nn.MultiheadAttention at
+ *   models/cross_modal_block_tacfn.py:74-80, 85-91, 98-104, 111-117 and
+ *   models/cross_modal_block.py:56-59, 64-67.
+ * Q rows are (b, t_q) with row pitch ldq, head h at columns [h*dh, (h+1)*dh);
+ * K likewise over t_k; V is given transposed per utterance as written by
+ * HRIEMO_EPI_QKV: vt[(b*d + h*dh + c) * Tk_pad + t_k].
+ * A fully masked key row yields NaN, as torch.softmax does in the reference.
+ */
+typedef struct hriemo_attn_args {
+  const void* q;  int64_t ldq;   /* bf16 */
+  const void* k;  int64_t ldk;   /* bf16 */
+  const void* vt; int32_t Tk_pad; int32_t reserved0;
+  const uint8_t* key_pad;        /* [B, Tk] 1 = PAD, or NULL */
+  void* out;      int64_t ldo;   /* bf16 [B*Tq, H*dh] */
+  int32_t B, H, Tq, Tk, dh;      /* dh in {32, 64, 96, 128} */
+  float scale;                   /* 1/sqrt(dh) */
+} hriemo_attn_args;
+
+int hriemo_attention_bf16(const hriemo_attn_args* args, void* stream);
+
+/* Head-averaged attention probabilities mean_h softmax(...)[B,Tq,Tk] (f32) — the
+ * `need_weights=True` / return_attention=True side output of
+ * models/cross_modal_block_tacfn.py:79,90,103,116 and models/emotion_decoder.py:53.
+ * V is not needed.  Interpretability path; CUDA-core kernel, not tuned. */
+int hriemo_attention_probs(const void* q, int64_t ldq, const void* k, int64_t ldk,
+                           const uint8_t* key_pad, float* probs, int32_t B, int32_t H, int32_t Tq,
+                           int32_t Tk, int32_t dh, float scale, void* stream);
+
+/* Small-query attention for the emotion decoder (N_q learned queries over Tk
+ * keys; models/emotion_decoder.py:42 and :48-54).  K and V are row-major bf16
+ * ([B*Tk, ld], head h at columns h*dh..).  One CTA per utterance, K/V head
+ * slices staged through shared memory.  probs (optional, f32 [B,Nq,Tk]) receives
+ * the head-averaged weights. */
+int hriemo_small_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                           int64_t ldv, const uint8_t* key_pad, void* out_bf16, int64_t ldo,
+                           float* probs, int32_t B, int32_t H, int32_t Nq, int32_t Tk, int32_t dh,
+                           float scale, void* stream);
+
+/* ----------------------------------------------------------- LayerNorm ----
+ * y = LayerNorm(x) over the last dim (biased variance, eps inside the sqrt),
+ * x bf16 or f32 (already holding residual + sub-layer output), y written as
+ * bf16 and/or f32 (either may be NULL).  Replaces nn.LayerNorm at
+ *   models/cross_modal_block_tacfn.py:81,92,105,106,118,119, models/emotion_decoder.py:43,55,59,
+ *   models/fusion_classifier.py:73.
+ */
+int hriemo_layernorm(const void* x, int32_t x_is_f32, int64_t ldx, const float* gamma,
+                     const float* beta, float eps, void* y_bf16, float* y_f32, int64_t ldy,
+                     int64_t rows, int32_t d, void* stream);
+
+/* -------------------------------------------------------------- β-gate ----
+ * models/beta_gate_tacfn.py:79-84 (and models/beta_gate.py:81-82 with
+ * apply_ln = 0): pooled[b,:] = masked_mean_t(LN(x[b,t,:])).  x bf16 [B,T,d].
+ */
+int hriemo_ln_masked_mean(const void* x_bf16, int64_t ldx, const float* gamma, const float* beta,
+                          float eps, int32_t apply_ln, const uint8_t* pad, float* pooled,
+                          int64_t ld_pooled, int32_t B, int32_t T, int32_t d, void* stream);
+
+/* models/beta_gate_tacfn.py:87-89: g = [a, t, |a-t|, a*t]  (f32 [B,4d]). */
+int hriemo_gate_input(const float* a_pool, const float* t_pool, float* g, int32_t B, int32_t d,
+                      void* stream);
+
+/* Small fp32 GEMM on CUDA cores: out = act(A[M,K] . W[N,K]^T + bias), act in
+ * {0 none, 1 relu, 2 sigmoid}.  Used where the reference result feeds a
+ * bit-sensitive decision (gate MLP models/beta_gate_tacfn.py:62-66,92; emotion
+ * head models/emotion_decoder.py:155; classifier models/fusion_classifier.py:74-77). */
+int hriemo_sgemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                     float* out, int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t act,
+                     void* stream);
+
+/* models/beta_gate_tacfn.py:95-116: beta[b] = mean_d w[b,:];
+ * h[b,t,:] = w[b,:]*LN_a(a[b,t,:]) + (1-w[b,:])*LN_t(t[b,t,:]) for t < L.
+ * With apply_ln = 0 and w_is_scalar = 1 it is the legacy scalar gate
+ * (models/beta_gate.py:103-112; beta_out then just copies w).
+ * a is [B,T_a,d] bf16 (row pitch lda; only the first L rows are read), t is [B,L,d]. */
+int hriemo_gate_blend(const void* a_bf16, int64_t lda, int32_t T_a, const void* t_bf16, int64_t ldt,
+                      const float* gamma_a, const float* beta_a, const float* gamma_t,
+                      const float* beta_t, float eps, int32_t apply_ln, const float* w,
+                      int32_t w_is_scalar, void* h_bf16, float* h_f32, int64_t ldh, float* beta_out,
+                      int32_t B, int32_t L, int32_t d, void* stream);
+
+/* Mean over time (UNMASKED) of an f32 [B,L,d] tensor — models/fusion_classifier.py:145. */
+int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRIEMO_H_ */

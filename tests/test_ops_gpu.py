@@ -1,0 +1,320 @@
+"""Per-kernel parity tests (B200 only): each C-ABI kernel against a plain torch
+fp32 computation of the same op on the same bf16-rounded operands.
+
+Tolerances are written next to each check.  bf16 outputs carry one rounding
+(2^-9 relative), accumulations are fp32 in both arms.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def _report(name, got, ref, atol, rtol):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    nan_mismatch = torch.isnan(got) != torch.isnan(ref)
+    bad = (bad & ~torch.isnan(ref)) | nan_mismatch
+    if bad.any():
+        idx = bad.nonzero()
+        first = idx[:8].tolist()
+        rows_bad = idx[:, 0].unique().numel()
+        cols_bad = idx[:, -1].unique().numel()
+        msg = (f"{name}: {int(bad.sum())}/{bad.numel()} elements out of tolerance; max err {float(err[~torch.isnan(err)].max()):.4g}; "
+               f"distinct bad rows {rows_bad}, cols {cols_bad}; first {first}; "
+               f"got {got[tuple(idx[0])].item():.5g} ref {ref[tuple(idx[0])].item():.5g}")
+        raise AssertionError(msg)
+
+
+# ------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [
+    # M, N, K
+    (128, 256, 64),
+    (300, 256, 768),
+    (1000, 768, 3072),
+    (4096, 2304, 768),
+    (777, 384, 768),      # 128-wide tile path
+    (64, 128, 80),        # K tail (MOSEI d_audio padded to 80)
+    (1, 32, 8),
+    (20000, 3072, 768),   # many tiles per CTA (persistent loop, both accumulator stages)
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_bias(M, N, K):
+    from hriemo import lib as L, ops
+
+    a = _rand((M, K), 1, dtype=torch.bfloat16)
+    w = _rand((N, K), 2, 1.0 / math.sqrt(K), dtype=torch.bfloat16)
+    bias = _rand((N,), 3)
+    ref = a.float() @ w.float().t() + bias
+    out = ops.gemm(a, w, bias, L.EPI_BIAS)
+    torch.cuda.synchronize()
+    _report(f"gemm bias {M}x{N}x{K}", out, ref, atol=1e-2, rtol=1e-2)  # one bf16 rounding of O(1) values
+
+
+def test_gemm_epilogues():
+    from hriemo import lib as L, ops
+
+    M, N, K = 1500, 768, 768
+    a = _rand((M, K), 4, dtype=torch.bfloat16)
+    w = _rand((N, K), 5, 1.0 / math.sqrt(K), dtype=torch.bfloat16)
+    bias = _rand((N,), 6)
+    acc = a.float() @ w.float().t() + bias
+    out = ops.gemm(a, w, bias, L.EPI_BIAS_RELU)
+    _report("relu", out, acc.clamp(min=0), 1e-2, 1e-2)
+    out = ops.gemm(a, w, None, L.EPI_BIAS)
+    _report("no-bias", out, a.float() @ w.float().t(), 1e-2, 1e-2)
+    resid = _rand((M, N), 7, dtype=torch.bfloat16)
+    out = ops.gemm(a, w, bias, L.EPI_BIAS_RESID, resid=resid)
+    _report("resid bf16", out, acc + resid.float(), 2e-2, 1e-2)
+    resid32 = _rand((M, N), 8)
+    out = ops.gemm(a, w, bias, L.EPI_BIAS_RESID_F32, resid=resid32)
+    assert out.dtype == torch.float32
+    _report("resid f32", out, acc + resid32, 1e-3, 1e-4)  # fp32 out: only accumulation-order noise
+    out = ops.gemm(a, w, bias, L.EPI_BIAS_F32)
+    _report("bias f32", out, acc, 1e-3, 1e-4)
+
+
+def test_gemm_strided_views():
+    """A as a column slice of a wider buffer, output into a column slice."""
+    from hriemo import lib as L, ops
+
+    M, N, K = 500, 256, 128
+    big = _rand((M, 3 * K), 9, dtype=torch.bfloat16)
+    a = big[:, K:2 * K]
+    w = _rand((N, K), 10, 0.1, dtype=torch.bfloat16)
+    outbig = torch.zeros((M, 2 * N), dtype=torch.bfloat16, device=DEV)
+    ops.gemm(a, w, None, L.EPI_BIAS, out=outbig[:, N:])
+    _report("strided", outbig[:, N:], a.float() @ w.float().t(), 1e-2, 1e-2)
+    assert outbig[:, :N].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("B,T,d", [(3, 50, 192), (5, 300, 768), (2, 64, 256), (7, 13, 128)])
+def test_gemm_qkv_layout(B, T, d):
+    from hriemo import ops
+
+    a = _rand((B * T, d), 11, dtype=torch.bfloat16)
+    w = _rand((3 * d, d), 12, 1.0 / math.sqrt(d), dtype=torch.bfloat16)
+    bias = _rand((3 * d,), 13)
+    ref = a.float() @ w.float().t() + bias
+    qk, vt = ops.gemm_qkv(a, w, bias, T, 2 * d)
+    _report("qk", qk, ref[:, :2 * d], 1e-2, 1e-2)
+    v_ref = ref[:, 2 * d:].view(B, T, d).transpose(1, 2)  # [B, d, T]
+    assert vt.shape == (B, d, (T + 7) // 8 * 8)
+    _report("vt", vt[:, :, :T], v_ref, 1e-2, 1e-2)
+
+
+# ------------------------------------------------------------------ attention
+def _attn_ref(q, k, v, pad, H):
+    B, Tq, d = q.shape
+    Tk = k.shape[1]
+    dh = d // H
+    qh = q.float().view(B, Tq, H, dh).transpose(1, 2)
+    kh = k.float().view(B, Tk, H, dh).transpose(1, 2)
+    vh = v.float().view(B, Tk, H, dh).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(dh)
+    if pad is not None:
+        s = s.masked_fill(pad[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return (p @ vh).transpose(1, 2).reshape(B * Tq, d), p.mean(dim=1)
+
+
+def _ragged(B, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(max(T // 2, 1), T + 1, (B,), generator=g)
+    return (torch.arange(T)[None, :] >= lens[:, None]).to(DEV)
+
+
+ATTN_CASES = [
+    # B, H, Tq, Tk, dh, masked
+    (2, 2, 128, 128, 64, False),
+    (3, 8, 300, 300, 96, False),
+    (3, 8, 300, 300, 96, True),
+    (2, 8, 500, 64, 96, True),    # audio queries text: single KV tile
+    (2, 8, 64, 500, 96, True),    # text queries audio: one short Q tile, 4 KV tiles
+    (2, 4, 300, 128, 64, True),   # MOSEI head dim
+    (2, 2, 50, 50, 32, False),
+    (1, 2, 1000, 1000, 128, True),
+    (4, 8, 1, 1, 96, False),      # utterance-level: softmax over one key
+]
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,dh,masked", ATTN_CASES)
+def test_attention(B, H, Tq, Tk, dh, masked):
+    from hriemo import ops
+
+    d = H * dh
+    q = _rand((B, Tq, d), 21, dtype=torch.bfloat16)
+    k = _rand((B, Tk, d), 22, dtype=torch.bfloat16)
+    v = _rand((B, Tk, d), 23, dtype=torch.bfloat16)
+    pad = _ragged(B, Tk, 24) if masked else None
+    ref, _ = _attn_ref(q, k, v, pad, H)
+    Tk_pad = (Tk + 7) // 8 * 8
+    vt = torch.full((B, d, Tk_pad), float("nan"), dtype=torch.bfloat16, device=DEV)  # padding must never be read
+    vt[:, :, :Tk] = v.transpose(1, 2)
+    out = ops.attention(q.view(B * Tq, d), k.view(B * Tk, d), vt, pad, B, H, Tq, Tk, dh)
+    torch.cuda.synchronize()
+    # P is rounded to bf16 before PV and O to bf16 after: ~2^-8 relative on O(0.1..1) values
+    _report(f"attention {B,H,Tq,Tk,dh,masked}", out, ref, atol=1.5e-2, rtol=2e-2)
+
+
+def test_attention_strided_qk_and_large_scores():
+    """Q/K read as column slices of a packed [Q|K] buffer; large score spread exercises the
+    lazy running-max rescale."""
+    from hriemo import ops
+
+    B, H, T, dh = 2, 4, 400, 64
+    d = H * dh
+    qk = _rand((B * T, 2 * d), 31, 3.0, dtype=torch.bfloat16)  # scores with std ~9*8/8
+    v = _rand((B, T, d), 32, dtype=torch.bfloat16)
+    vt = torch.zeros((B, d, T), dtype=torch.bfloat16, device=DEV)
+    vt[:] = v.transpose(1, 2)
+    ref, _ = _attn_ref(qk[:, :d].reshape(B, T, d), qk[:, d:].reshape(B, T, d), v, None, H)
+    out = ops.attention(qk[:, :d], qk[:, d:], vt, None, B, H, T, T, dh)
+    _report("attention strided/peaky", out, ref, atol=2e-2, rtol=3e-2)
+
+
+def test_attention_fully_masked_row_is_nan():
+    from hriemo import ops
+
+    B, H, T, dh = 2, 2, 40, 64
+    d = H * dh
+    q = _rand((B, T, d), 41, dtype=torch.bfloat16)
+    vt = torch.zeros((B, d, T), dtype=torch.bfloat16, device=DEV)
+    pad = torch.zeros((B, T), dtype=torch.bool, device=DEV)
+    pad[1] = True  # utterance 1: every key is PAD -> torch.softmax gives NaN
+    out = ops.attention(q.view(B * T, d), q.view(B * T, d), vt, pad, B, H, T, T, dh).view(B, T, d)
+    assert torch.isfinite(out[0]).all()
+    assert torch.isnan(out[1]).all()
+
+
+# ------------------------------------------------------------------ elementwise
+@pytest.mark.parametrize("rows,d,f32in", [(1000, 768, False), (33, 256, True), (5, 2048, False), (4096 * 4, 768, True)])
+def test_layernorm(rows, d, f32in):
+    from hriemo import ops
+
+    x = _rand((rows, d), 51, 2.0, dtype=torch.float32 if f32in else torch.bfloat16)
+    g = _rand((d,), 52) + 1.0
+    b = _rand((d,), 53)
+    ref = torch.nn.functional.layer_norm(x.double(), (d,), g.double(), b.double(), 1e-5)
+    yb, yf = ops.layernorm(x, g, b, want_bf16=True, want_f32=True)
+    _report("ln f32", yf, ref, atol=2e-5, rtol=2e-5)       # fp32 arithmetic
+    _report("ln bf16", yb, ref, atol=1e-2, rtol=1e-2)      # bf16 rounding of the output
+
+
+def test_cast_pad():
+    from hriemo import ops
+
+    x = _rand((301, 74), 61)
+    y = ops.cast_bf16(x, 80)
+    assert y.shape == (301, 80)
+    assert torch.equal(y[:, :74], x.to(torch.bfloat16))
+    assert y[:, 74:].abs().max().item() == 0
+    x2 = _rand((64, 768), 62)
+    assert torch.equal(ops.cast_bf16(x2), x2.to(torch.bfloat16))
+    x3 = _rand((10, 300), 63)
+    assert torch.equal(ops.cast_bf16(x3, 304)[:, :300], x3.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("B,T,d,masked,apply_ln", [(4, 300, 768, True, True), (3, 50, 256, False, True), (2, 7, 128, True, False)])
+def test_ln_masked_mean(B, T, d, masked, apply_ln):
+    from hriemo import ops
+
+    x = _rand((B * T, d), 71, dtype=torch.bfloat16)
+    g = _rand((d,), 72) + 1.0
+    b = _rand((d,), 73)
+    pad = _ragged(B, T, 74) if masked else None
+    xr = x.double().view(B, T, d)
+    if apply_ln:
+        xr = torch.nn.functional.layer_norm(xr, (d,), g.double(), b.double(), 1e-5)
+    if pad is None:
+        ref = xr.mean(dim=1)
+    else:
+        valid = (~pad).double()
+        ref = (xr * valid[..., None]).sum(1) / valid.sum(1, keepdim=True).clamp(min=1.0)
+    got = ops.ln_masked_mean(x, g, b, pad, B, T, apply_ln=apply_ln)
+    _report("ln_masked_mean", got, ref, atol=1e-5, rtol=1e-5)
+
+
+def test_ln_masked_mean_all_pad_is_zero():
+    from hriemo import ops
+
+    B, T, d = 2, 9, 64
+    x = _rand((B * T, d), 75, dtype=torch.bfloat16)
+    pad = torch.ones((B, T), dtype=torch.bool, device=DEV)
+    got = ops.ln_masked_mean(x, None, None, pad, B, T, apply_ln=False)
+    assert got.abs().max().item() == 0.0  # sum 0 / clamp(0, min=1)
+
+
+@pytest.mark.parametrize("M,N,K,act", [(4096, 256, 3072, 1), (100, 768, 256, 2), (37, 1, 768, 0), (16, 4, 768, 0)])
+def test_sgemm(M, N, K, act):
+    from hriemo import ops
+
+    a = _rand((M, K), 81)
+    w = _rand((N, K), 82, 1.0 / math.sqrt(K))
+    bias = _rand((N,), 83)
+    ref = a.double() @ w.double().t() + bias.double()
+    if act == 1:
+        ref = ref.clamp(min=0)
+    elif act == 2:
+        ref = torch.sigmoid(ref)
+    got = ops.sgemm(a, w, bias, act)
+    _report("sgemm", got, ref, atol=2e-5, rtol=2e-5)  # fp32 FMA chain of length K
+
+
+def test_gate_blend_and_input():
+    from hriemo import ops
+
+    B, T_a, L, d = 3, 40, 12, 256
+    a = _rand((B * T_a, d), 91, dtype=torch.bfloat16)
+    t = _rand((B * L, d), 92, dtype=torch.bfloat16)
+    ga, ba, gt, bt = _rand((d,), 93) + 1, _rand((d,), 94), _rand((d,), 95) + 1, _rand((d,), 96)
+    w = torch.sigmoid(_rand((B, d), 97))
+    an = torch.nn.functional.layer_norm(a.double().view(B, T_a, d), (d,), ga.double(), ba.double(), 1e-5)[:, :L]
+    tn = torch.nn.functional.layer_norm(t.double().view(B, L, d), (d,), gt.double(), bt.double(), 1e-5)
+    ref = w.double()[:, None] * an + (1 - w.double()[:, None]) * tn
+    hb, hf, beta = ops.gate_blend(a, T_a, t, (ga, ba), (gt, bt), w, B, L, want_bf16=True, want_f32=True)
+    _report("blend f32", hf, ref.view(B * L, d), 2e-5, 2e-5)
+    _report("blend bf16", hb, ref.view(B * L, d), 1e-2, 1e-2)
+    _report("beta", beta, w.double().mean(-1, keepdim=True), 1e-6, 1e-6)
+    # legacy scalar gate, no LayerNorm
+    ws = torch.sigmoid(_rand((B, 1), 98))
+    ref2 = ws.double()[:, None] * a.double().view(B, T_a, d)[:, :L] + (1 - ws.double()[:, None]) * t.double().view(B, L, d)
+    _, hf2, beta2 = ops.gate_blend(a, T_a, t, None, None, ws, B, L, apply_ln=False, w_is_scalar=True,
+                                   want_bf16=False, want_f32=True)
+    _report("blend scalar", hf2, ref2.view(B * L, d), 1e-6, 1e-6)
+    assert torch.equal(beta2, ws)
+    ap, tp = _rand((B, d), 99), _rand((B, d), 100)
+    g = ops.gate_input(ap, tp)
+    assert torch.equal(g, torch.cat([ap, tp, (ap - tp).abs(), ap * tp], dim=-1))
+    x = _rand((B * L, d), 101)
+    _report("mean_over_time", ops.mean_over_time(x, B, L), x.double().view(B, L, d).mean(1), 1e-6, 1e-6)
+
+
+@pytest.mark.parametrize("B,H,Nq,Tk,dh,masked", [(5, 8, 4, 50, 96, True), (3, 4, 6, 128, 64, False), (2, 8, 4, 4, 96, False), (2, 2, 19, 37, 32, True)])
+def test_small_attention(B, H, Nq, Tk, dh, masked):
+    from hriemo import ops
+
+    d = H * dh
+    q = _rand((B, Nq, d), 111, dtype=torch.bfloat16)
+    kv = _rand((B * Tk, 2 * d), 112, dtype=torch.bfloat16)  # packed [K|V] rows, as the decoder produces
+    pad = _ragged(B, Tk, 113) if masked else None
+    ref, pref = _attn_ref(q, kv[:, :d].reshape(B, Tk, d), kv[:, d:].reshape(B, Tk, d), pad, H)
+    out, probs = ops.small_attention(q.view(B * Nq, d), kv[:, :d], kv[:, d:], pad, B, H, Nq, Tk, dh, want_probs=True)
+    _report("small_attention out", out, ref, 1e-2, 1e-2)
+    _report("small_attention probs", probs, pref, 1e-5, 1e-4)
+    p2 = ops.attention_probs(q.view(B * Nq, d), kv[:, :d], pad, B, H, Nq, Tk, dh)
+    _report("attention_probs", p2, pref, 1e-5, 1e-4)

@@ -1,0 +1,57 @@
+"""Micro-benchmarks of the individual kernels against the measured peaks (and cuBLAS / SDPA
+as same-box yardsticks).  Diagnostic tool; bench.py is the contract benchmark."""
+import json, math, os, sys, time
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "hri-emo_b200"))
+from hriemo import lib as L, ops
+
+PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in evs:
+        a.record(); fn(); b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2], ts[0]
+
+def main():
+    dev = "cuda"
+    res = []
+    for (M, N, K, epi) in [(2048000 // 4, 2304, 768, L.EPI_BIAS), (2048000 // 4, 3072, 768, L.EPI_BIAS_RELU), (2048000 // 4, 768, 3072, L.EPI_BIAS),
+                           (2048000 // 4, 768, 768, L.EPI_BIAS), (262144 // 4, 2304, 768, L.EPI_BIAS), (16384, 768, 768, L.EPI_BIAS)]:
+        a = torch.randn(M, K, device=dev).bfloat16(); w = torch.randn(N, K, device=dev).bfloat16(); b = torch.randn(N, device=dev)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        med, best = timeit(lambda: ops.gemm(a, w, b, epi, out=out))
+        medc, bestc = timeit(lambda: torch.nn.functional.linear(a, w, b.bfloat16()))
+        fl = 2.0 * M * N * K
+        res.append(dict(kernel="gemm", M=M, N=N, K=K, ms=med, tflops=fl / med / 1e9, frac_burst=fl / med / 1e9 / PEAKS["bf16_tflops"], cublas_ms=medc, cublas_tflops=fl / medc / 1e9))
+        print(res[-1], flush=True)
+    for (B, H, Tq, Tk, dh) in [(512, 8, 500, 500, 96), (512, 8, 500, 64, 96), (512, 8, 64, 500, 96), (512, 4, 300, 128, 64)]:
+        d = H * dh
+        q = torch.randn(B * Tq, d, device=dev).bfloat16(); k = torch.randn(B * Tk, d, device=dev).bfloat16()
+        v = torch.randn(B, Tk, d, device=dev).bfloat16()
+        vt = torch.zeros(B, d, (Tk + 7) // 8 * 8, device=dev, dtype=torch.bfloat16); vt[:, :, :Tk] = v.transpose(1, 2)
+        med, best = timeit(lambda: ops.attention(q, k, vt, None, B, H, Tq, Tk, dh))
+        qh = q.view(B, Tq, H, dh).transpose(1, 2); kh = k.view(B, Tk, H, dh).transpose(1, 2); vh = v.view(B, Tk, H, dh).transpose(1, 2)
+        meds, _ = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qh, kh, vh))
+        fl = 4.0 * B * H * Tq * Tk * dh
+        res.append(dict(kernel="attention", B=B, H=H, Tq=Tq, Tk=Tk, dh=dh, ms=med, tflops=fl / med / 1e9, frac_burst=fl / med / 1e9 / PEAKS["bf16_tflops"], sdpa_ms=meds))
+        print(res[-1], flush=True)
+    rows, d = 2048000 // 4, 768
+    x = torch.randn(rows, d, device=dev).bfloat16(); g = torch.ones(d, device=dev); bb = torch.zeros(d, device=dev)
+    med, best = timeit(lambda: ops.layernorm(x, g, bb))
+    res.append(dict(kernel="layernorm", rows=rows, d=d, ms=med, gbs=rows * d * 4 / med / 1e6, frac=rows * d * 4 / med / 1e6 / PEAKS["hbm_gbs"]))
+    print(res[-1], flush=True)
+    xf = torch.randn(rows, d, device=dev)
+    med, best = timeit(lambda: ops.cast_bf16(xf))
+    res.append(dict(kernel="cast", rows=rows, d=d, ms=med, gbs=rows * d * 6 / med / 1e6, frac=rows * d * 6 / med / 1e6 / PEAKS["hbm_gbs"]))
+    print(res[-1], flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bench_kernels.json"), "w"), indent=1)
+
+if __name__ == "__main__":
+    main()
