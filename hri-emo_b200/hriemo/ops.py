@@ -20,6 +20,25 @@ f32 = torch.float32
 LN_EPS = 1e-5
 
 
+# When set to a list (bench.py), every tensor-core launch is bracketed by CUDA events on the
+# launching stream and (kind, algorithmic FLOPs, start, end) is appended.
+PROFILE = None
+
+
+def _prof_begin(kind: str, work: float):
+    if PROFILE is None:
+        return None
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    return (kind, work, a, b)
+
+
+def _prof_end(tok) -> None:
+    if tok is not None:
+        tok[3].record()
+        PROFILE.append(tok)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -84,7 +103,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogu
     if resid is not None:
         _chk2d(resid, f32 if f32_out else bf16, "gemm resid")
         args.resid, args.ldr = resid.data_ptr(), resid.stride(0)
+    tok = _prof_begin("gemm", 2.0 * M * N * K)
     _l.check(_l.load().hriemo_gemm_bf16(C.byref(args), _stream()), "gemm_bf16")
+    _prof_end(tok)
     return out
 
 
@@ -106,7 +127,9 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], T: 
     args.M, args.N, args.K, args.epilogue = M, N, K, _l.EPI_QKV
     args.out, args.ldo = qk.data_ptr(), qk.stride(0)
     args.vt, args.T, args.T_pad, args.v_col_begin = vt.data_ptr(), T, T_pad, v_col_begin
+    tok = _prof_begin("gemm", 2.0 * M * N * K)
     _l.check(_l.load().hriemo_gemm_bf16(C.byref(args), _stream()), "gemm_bf16[qkv]")
+    _prof_end(tok)
     return qk, vt
 
 
@@ -127,7 +150,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, key_pad: Optio
     args.out, args.ldo = out.data_ptr(), out.stride(0)
     args.B, args.H, args.Tq, args.Tk, args.dh = B, H, Tq, Tk, dh
     args.scale = 1.0 / math.sqrt(dh)
+    tok = _prof_begin("attention", 4.0 * B * H * Tq * Tk * dh)
     _l.check(_l.load().hriemo_attention_bf16(C.byref(args), _stream()), "attention_bf16")
+    _prof_end(tok)
     return out
 
 
