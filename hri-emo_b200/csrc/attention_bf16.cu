@@ -186,11 +186,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const int quad = warp & 3;
     const int r = quad * 32 + lane;  // query row inside the tile == TMEM lane
     const int st_tid = threadIdx.x - 64;
-    // additive key mask: 0 for valid keys, -inf for PAD keys and for keys >= Tk
+    // key cap: +inf for valid keys, -inf for PAD keys and keys >= Tk.  score = fminf(s*scale, cap):
+    // fminf returns the non-NaN operand, so whatever a masked column holds (rows of the next
+    // utterance inside the 128-key box, possibly NaN) becomes exactly -inf.
     for (int kk = st_tid; kk < n_kv * ATT_BKV; kk += 128) {
       bool pad = kk >= p.Tk;
       if (!pad && p.key_pad != nullptr) pad = p.key_pad[static_cast<int64_t>(b) * p.Tk + kk] != 0;
-      madd[kk] = pad ? -INFINITY : 0.0f;
+      madd[kk] = pad ? -INFINITY : INFINITY;
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
 
@@ -218,10 +220,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 mk = mp[i];
-          tile_max = fmaxf(tile_max, fmaf(__uint_as_float(v[i * 4 + 0]), p.scale_log2, mk.x));
-          tile_max = fmaxf(tile_max, fmaf(__uint_as_float(v[i * 4 + 1]), p.scale_log2, mk.y));
-          tile_max = fmaxf(tile_max, fmaf(__uint_as_float(v[i * 4 + 2]), p.scale_log2, mk.z));
-          tile_max = fmaxf(tile_max, fmaf(__uint_as_float(v[i * 4 + 3]), p.scale_log2, mk.w));
+          tile_max = fmaxf(tile_max, fminf(__uint_as_float(v[i * 4 + 0]) * p.scale_log2, mk.x));
+          tile_max = fmaxf(tile_max, fminf(__uint_as_float(v[i * 4 + 1]) * p.scale_log2, mk.y));
+          tile_max = fmaxf(tile_max, fminf(__uint_as_float(v[i * 4 + 2]) * p.scale_log2, mk.z));
+          tile_max = fmaxf(tile_max, fminf(__uint_as_float(v[i * 4 + 3]) * p.scale_log2, mk.w));
         }
       }
 
@@ -262,10 +264,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 mk = mp[i];
-          e[i * 4 + 0] = fast_exp2(fmaf(__uint_as_float(v[i * 4 + 0]), p.scale_log2, mk.x) - m_eff);
-          e[i * 4 + 1] = fast_exp2(fmaf(__uint_as_float(v[i * 4 + 1]), p.scale_log2, mk.y) - m_eff);
-          e[i * 4 + 2] = fast_exp2(fmaf(__uint_as_float(v[i * 4 + 2]), p.scale_log2, mk.z) - m_eff);
-          e[i * 4 + 3] = fast_exp2(fmaf(__uint_as_float(v[i * 4 + 3]), p.scale_log2, mk.w) - m_eff);
+          e[i * 4 + 0] = fast_exp2(fminf(__uint_as_float(v[i * 4 + 0]) * p.scale_log2, mk.x) - m_eff);
+          e[i * 4 + 1] = fast_exp2(fminf(__uint_as_float(v[i * 4 + 1]) * p.scale_log2, mk.y) - m_eff);
+          e[i * 4 + 2] = fast_exp2(fminf(__uint_as_float(v[i * 4 + 2]) * p.scale_log2, mk.z) - m_eff);
+          e[i * 4 + 3] = fast_exp2(fminf(__uint_as_float(v[i * 4 + 3]) * p.scale_log2, mk.w) - m_eff);
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) l_add += e[i];

@@ -2,7 +2,8 @@
 //   out = epilogue(A[M,K] . W[N,K]^T + bias)
 // TMA (128B-swizzled tiles) -> shared-memory ring -> tcgen05.mma (fp32 accumulators
 // in TMEM, double-buffered) -> epilogue warps (tcgen05.ld, bias/ReLU/residual,
-// bf16 or fp32 stores, optional per-utterance V^T scatter).
+// bf16 tiles staged in swizzled smem + TMA store, fp32 direct stores, optional per-utterance
+// V^T scatter).
 //
 // Replaces the nn.Linear / MHA projection calls of the reference forward
 // (models/cross_modal_block_tacfn.py:24-52,74-119; models/emotion_decoder.py:14-27;
@@ -20,6 +21,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int GEMM_THREADS = 256;
+constexpr int OUT_BOX_BYTES = 32 * 128;  // one epilogue warp's staging box: 32 rows x 64 bf16
 
 struct GemmKernelParams {
   int64_t M;
@@ -41,7 +43,8 @@ struct GemmSmem {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
-  static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;
+  static constexpr int OUT_OFF = B_OFF + STAGES * B_STAGE_BYTES;   // 4 warps x 2 boxes of [32][64] bf16
+  static constexpr int BAR_OFF = OUT_OFF + 8 * OUT_BOX_BYTES;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
@@ -63,7 +66,7 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const GemmKernelParams p) {
+                 const __grid_constant__ CUtensorMap tm_c, const GemmKernelParams p) {
   using L = GemmSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages (power of two: 256 or 512)
   constexpr uint32_t STAGE_TX = A_STAGE_BYTES + L::B_STAGE_BYTES;
@@ -72,6 +75,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base + L::A_OFF;
   const uint32_t sB = smem_base + L::B_OFF;
+  const uint32_t sOut = smem_base + L::OUT_OFF;
   const uint32_t bar_full = smem_base + L::BAR_OFF;
   const uint32_t bar_empty = bar_full + STAGES * 8;
   const uint32_t bar_tfull = bar_empty + STAGES * 8;
@@ -86,6 +90,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -150,13 +155,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // Each warp owns 32 accumulator rows (TMEM lanes 32*quad..+31), one row per thread, and
+    // drains them in 64-column slabs.  bf16 outputs are staged in a private, 128B-swizzled
+    // [32 rows][64 cols] shared-memory box (double-buffered) and written with a TMA store, so
+    // HBM/L2 see full 128-byte lines; the four warps never synchronise with each other.
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane;
-    uint32_t it = 0;
+    const uint32_t my_stage = sOut + static_cast<uint32_t>(quad) * (2 * OUT_BOX_BYTES);
+    const bool bf16_out = p.epilogue != HRIEMO_EPI_BIAS_RESID_F32 && p.epilogue != HRIEMO_EPI_BIAS_F32;
+    uint32_t it = 0, slab_ctr = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1u;
       const uint32_t aphase = (it >> 1) & 1u;
-      const int64_t m = (tile / p.num_n_blocks) * BM + row_in_tile;
+      const int64_t m_tile = (tile / p.num_n_blocks) * BM;
+      const int64_t m = m_tile + row_in_tile;
       const int n0 = static_cast<int>(tile % p.num_n_blocks) * BN;
       const bool row_ok = m < p.M;
       int64_t vt_row_base = 0;  // (b * dv) * T_pad + t
@@ -169,33 +181,44 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n = n0 + c * 32;
-        if (n >= p.N) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(t_row + c * 32, v);
+      for (int s = 0; s < BN / 64; ++s) {
+        const int n = n0 + s * 64;
+        if (n >= p.N) break;                   // warp-uniform
+        const bool two = n + 32 < p.N;         // N is a multiple of 32
+        uint32_t v[2][32];
+        tmem_ld32(t_row + s * 64, v[0]);
+        if (two) tmem_ld32(t_row + s * 64 + 32, v[1]);
         tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        if (p.bias != nullptr) {
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b4 = __ldg(bp + i);
-            f[i * 4 + 0] += b4.x; f[i * 4 + 1] += b4.y; f[i * 4 + 2] += b4.z; f[i * 4 + 3] += b4.w;
-          }
+        const bool to_vt = p.epilogue == HRIEMO_EPI_QKV && n >= p.v_col_begin;
+        const bool staged = bf16_out && !to_vt;
+        uint32_t buf = 0;
+        if (staged) {
+          buf = my_stage + (slab_ctr & 1u) * OUT_BOX_BYTES;
+          ++slab_ctr;
+          if (lane == 0) bulk_wait_read<1>();  // the store issued two slabs ago has left this buffer
+          __syncwarp();
         }
-        if (row_ok) {
-        switch (p.epilogue) {
-          case HRIEMO_EPI_BIAS_RELU:
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          if (hf == 1 && !two) break;
+          const int nn = n + hf * 32;
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[hf][i]);
+          if (p.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + nn);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = __ldg(bp + i);
+              f[i * 4 + 0] += b4.x; f[i * 4 + 1] += b4.y; f[i * 4 + 2] += b4.z; f[i * 4 + 3] += b4.w;
+            }
+          }
+          if (p.epilogue == HRIEMO_EPI_BIAS_RELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
-            store_bf16x32(static_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n, f);
-            break;
-          case HRIEMO_EPI_BIAS_RESID: {
+          } else if (p.epilogue == HRIEMO_EPI_BIAS_RESID && row_ok) {
             const uint4* rp = reinterpret_cast<const uint4*>(
-                static_cast<const __nv_bfloat16*>(p.resid) + m * p.ldr + n);
+                static_cast<const __nv_bfloat16*>(p.resid) + m * p.ldr + nn);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint4 r4 = __ldg(rp + i);
@@ -204,40 +227,46 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               f[i * 8 + 4] += bf16_lo(r4.z); f[i * 8 + 5] += bf16_hi(r4.z);
               f[i * 8 + 6] += bf16_lo(r4.w); f[i * 8 + 7] += bf16_hi(r4.w);
             }
-            store_bf16x32(static_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n, f);
-            break;
-          }
-          case HRIEMO_EPI_BIAS_RESID_F32:
-          case HRIEMO_EPI_BIAS_F32: {
-            if (p.epilogue == HRIEMO_EPI_BIAS_RESID_F32) {
-              const float4* rp =
-                  reinterpret_cast<const float4*>(static_cast<const float*>(p.resid) + m * p.ldr + n);
+          } else if (p.epilogue == HRIEMO_EPI_BIAS_RESID_F32 && row_ok) {
+            const float4* rp =
+                reinterpret_cast<const float4*>(static_cast<const float*>(p.resid) + m * p.ldr + nn);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 r4 = __ldg(rp + i);
-                f[i * 4 + 0] += r4.x; f[i * 4 + 1] += r4.y; f[i * 4 + 2] += r4.z; f[i * 4 + 3] += r4.w;
-              }
+            for (int i = 0; i < 8; ++i) {
+              const float4 r4 = __ldg(rp + i);
+              f[i * 4 + 0] += r4.x; f[i * 4 + 1] += r4.y; f[i * 4 + 2] += r4.z; f[i * 4 + 3] += r4.w;
             }
-            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + m * p.ldo + n);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              op[i] = make_float4(f[i * 4 + 0], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
-            break;
           }
-          case HRIEMO_EPI_QKV:
-            if (n < p.v_col_begin) {
-              store_bf16x32(static_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n, f);
-            } else {
+          if (staged) {
+            // swizzled 16-byte chunks: chunk j of row r lives at slot j ^ (r & 7)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t slot = static_cast<uint32_t>((hf * 4 + g) ^ (lane & 7));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + lane * 128 + slot * 16),
+                           "r"(pack_bf16(f[g * 8 + 0], f[g * 8 + 1])), "r"(pack_bf16(f[g * 8 + 2], f[g * 8 + 3])),
+                           "r"(pack_bf16(f[g * 8 + 4], f[g * 8 + 5])), "r"(pack_bf16(f[g * 8 + 6], f[g * 8 + 7]))
+                           : "memory");
+            }
+          } else if (to_vt) {
+            if (row_ok) {
               // V^T scatter: consecutive lanes hold consecutive t -> coalesced 2-byte stores
-              __nv_bfloat16* vp = p.vt + vt_row_base + static_cast<int64_t>(n - p.v_col_begin) * p.T_pad;
+              __nv_bfloat16* vp = p.vt + vt_row_base + static_cast<int64_t>(nn - p.v_col_begin) * p.T_pad;
 #pragma unroll
               for (int i = 0; i < 32; ++i) vp[static_cast<int64_t>(i) * p.T_pad] = __float2bfloat16_rn(f[i]);
             }
-            break;
-          default:  // HRIEMO_EPI_BIAS
-            store_bf16x32(static_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n, f);
-            break;
+          } else if (row_ok) {  // fp32 outputs (decoder stream): direct 16-byte stores
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + m * p.ldo + nn);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              op[i] = make_float4(f[i * 4 + 0], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
+          }
         }
+        if (staged) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm_c, buf, n, static_cast<int>(m_tile) + quad * 32);
+            bulk_commit();
+          }
         }
         __syncwarp();  // reconverge before the next warp-collective tcgen05.ld
       }
@@ -245,6 +274,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + as * 8);
     }
+    if (lane == 0) bulk_wait_all();  // staged tiles must be out before shared memory is released
   }
 
   // ===================== teardown =====================
@@ -260,11 +290,19 @@ template <int BN, int STAGES>
 static int launch_gemm(const hriemo_gemm_args& a, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
   static_assert(L::DYN_BYTES <= 227 * 1024, "shared memory budget");
-  CUtensorMap tm_a, tm_b;
+  CUtensorMap tm_a, tm_b, tm_c;
   int rc = make_tmap_bf16_2d(&tm_a, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, BK, BM);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_b, a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldw, BK, BN);
   if (rc) return rc;
+  const bool f32_out = a.epilogue == HRIEMO_EPI_BIAS_RESID_F32 || a.epilogue == HRIEMO_EPI_BIAS_F32;
+  if (f32_out) {
+    tm_c = tm_a;  // unused by the fp32 epilogues
+  } else {
+    const uint64_t out_cols = a.epilogue == HRIEMO_EPI_QKV ? (uint64_t)a.v_col_begin : (uint64_t)a.N;
+    rc = make_tmap_bf16_2d(&tm_c, a.out, out_cols, (uint64_t)a.M, (uint64_t)a.ldo, 64, 32);
+    if (rc) return rc;
+  }
 
   GemmKernelParams p;
   p.M = a.M; p.N = a.N; p.K = a.K; p.epilogue = a.epilogue; p.bias = a.bias;
@@ -285,7 +323,7 @@ static int launch_gemm(const hriemo_gemm_args& a, cudaStream_t stream) {
   }
   const int64_t sms = device_sm_count();
   const unsigned grid = static_cast<unsigned>(p.num_tiles < sms ? p.num_tiles : sms);
-  gemm_bf16_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tm_a, tm_b, p);
+  gemm_bf16_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tm_a, tm_b, tm_c, p);
   return check_launch("gemm_bf16");
 }
 
@@ -315,7 +353,7 @@ extern "C" int hriemo_gemm_bf16(const hriemo_gemm_args* a, void* stream) {
   if (a->epilogue == HRIEMO_EPI_QKV) {
     HRIEMO_REQUIRE(a->vt != nullptr && a->T > 0 && a->T_pad >= a->T && a->T_pad % 8 == 0,
                    "gemm: QKV epilogue needs vt, T, T_pad (multiple of 8)");
-    HRIEMO_REQUIRE(a->v_col_begin > 0 && a->v_col_begin < a->N && a->v_col_begin % 32 == 0,
+    HRIEMO_REQUIRE(a->v_col_begin > 0 && a->v_col_begin < a->N && a->v_col_begin % 64 == 0,
                    "gemm: bad v_col_begin %d", a->v_col_begin);
     HRIEMO_REQUIRE(a->M % a->T == 0, "gemm: M must be B*T in QKV mode");
   }
