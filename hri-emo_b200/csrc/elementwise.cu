@@ -25,15 +25,17 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return u;
 }
 
-// A row of d elements held by one warp: lane l owns elements [(i*32 + l)*8, +8) for i < nv.
+// A row of d elements held by one warp: lane l owns elements [(i*32 + l)*8, +8) for i < NV,
+// NV = ceil(d / 256) chosen at launch (template) so the register footprint matches d.
+template <int NV>
 struct RowRegs {
-  float v[ROW_MAX_VEC][8];
+  float v[NV][8];
 };
 
-template <bool F32>
-__device__ __forceinline__ void load_row(RowRegs& r, const void* row, int d, int lane) {
+template <bool F32, int NV>
+__device__ __forceinline__ void load_row(RowRegs<NV>& r, const void* row, int d, int lane) {
 #pragma unroll
-  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
     if (c < d) {
       if (F32) {
@@ -53,17 +55,18 @@ __device__ __forceinline__ void load_row(RowRegs& r, const void* row, int d, int
 }
 
 // In-place LayerNorm of a warp-held row (two-pass: mean, then biased variance).
-__device__ __forceinline__ void normalize_row(RowRegs& r, int d, int lane, const float* gamma,
+template <int NV>
+__device__ __forceinline__ void normalize_row(RowRegs<NV>& r, int d, int lane, const float* gamma,
                                               const float* beta, float eps) {
   float s = 0.0f;
 #pragma unroll
-  for (int i = 0; i < ROW_MAX_VEC; ++i)
+  for (int i = 0; i < NV; ++i)
 #pragma unroll
     for (int k = 0; k < 8; ++k) s += r.v[i][k];
   const float mean = warp_sum(s) / static_cast<float>(d);
   float q = 0.0f;
 #pragma unroll
-  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
     if (c < d) {
 #pragma unroll
@@ -75,7 +78,7 @@ __device__ __forceinline__ void normalize_row(RowRegs& r, int d, int lane, const
   }
   const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(d) + eps);
 #pragma unroll
-  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
     if (c < d) {
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
@@ -90,9 +93,10 @@ __device__ __forceinline__ void normalize_row(RowRegs& r, int d, int lane, const
   }
 }
 
-__device__ __forceinline__ void store_row(const RowRegs& r, __nv_bfloat16* yb, float* yf, int d, int lane) {
+template <int NV>
+__device__ __forceinline__ void store_row(const RowRegs<NV>& r, __nv_bfloat16* yb, float* yf, int d, int lane) {
 #pragma unroll
-  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
     if (c < d) {
       if (yb) *reinterpret_cast<uint4*>(yb + c) = pack8(r.v[i]);
@@ -130,7 +134,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, int64_t ld_in
 }
 
 // ------------------------------------------------------------------ LayerNorm
-template <bool F32>
+template <bool F32, int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ yb,
@@ -138,10 +142,10 @@ layernorm_kernel(const void* __restrict__ x, int64_t ldx, const float* __restric
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  RowRegs r;
+  RowRegs<NV> r;
   const void* xr = F32 ? static_cast<const void*>(static_cast<const float*>(x) + row * ldx)
                        : static_cast<const void*>(static_cast<const __nv_bfloat16*>(x) + row * ldx);
-  load_row<F32>(r, xr, d, lane);
+  load_row<F32, NV>(r, xr, d, lane);
   normalize_row(r, d, lane, gamma, beta, eps);
   store_row(r, yb ? yb + row * ldy : nullptr, yf ? yf + row * ldy : nullptr, d, lane);
 }
@@ -149,6 +153,7 @@ layernorm_kernel(const void* __restrict__ x, int64_t ldx, const float* __restric
 // ------------------------------------------------------------------ gate: LN + masked mean
 // One CTA per utterance; warp w reduces rows t = w, w+8, ... in registers, then the
 // 8 partial sums are combined through shared memory in a fixed order (deterministic).
+template <int NV>
 __global__ void __launch_bounds__(256)
 ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
                       const float* __restrict__ beta, float eps, int apply_ln,
@@ -157,9 +162,9 @@ ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const fl
   extern __shared__ float part[];  // [8][d]
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  RowRegs acc;
+  RowRegs<NV> acc;
 #pragma unroll
-  for (int i = 0; i < ROW_MAX_VEC; ++i)
+  for (int i = 0; i < NV; ++i)
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc.v[i][k] = 0.0f;
   int count = 0;
@@ -167,18 +172,18 @@ ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const fl
     const bool valid = pad == nullptr || pad[static_cast<int64_t>(b) * T + t] == 0;
     if (!valid) continue;  // warp-uniform
     ++count;
-    RowRegs r;
-    load_row<false>(r, x + (static_cast<int64_t>(b) * T + t) * ldx, d, lane);
+    RowRegs<NV> r;
+    load_row<false, NV>(r, x + (static_cast<int64_t>(b) * T + t) * ldx, d, lane);
     if (apply_ln) normalize_row(r, d, lane, gamma, beta, eps);
 #pragma unroll
-    for (int i = 0; i < ROW_MAX_VEC; ++i)
+    for (int i = 0; i < NV; ++i)
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc.v[i][k] += r.v[i][k];
   }
   __shared__ int counts[8];
   if (lane == 0) counts[warp] = count;
 #pragma unroll
-  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
     if (c < d) {
 #pragma unroll
@@ -216,6 +221,7 @@ __global__ void gate_input_kernel(const float* __restrict__ a, const float* __re
 }
 
 // ------------------------------------------------------------------ gate: blend
+template <int NV>
 __global__ void __launch_bounds__(256)
 gate_blend_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int T_a,
                   const __nv_bfloat16* __restrict__ t, int64_t ldt, const float* __restrict__ ga,
@@ -228,16 +234,16 @@ gate_blend_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int T_a,
   if (row >= static_cast<int64_t>(B) * L) return;
   const int b = static_cast<int>(row / L);
   const int tt = static_cast<int>(row - static_cast<int64_t>(b) * L);
-  RowRegs ra, rt;
-  load_row<false>(ra, a + (static_cast<int64_t>(b) * T_a + tt) * lda, d, lane);
-  load_row<false>(rt, t + (static_cast<int64_t>(b) * L + tt) * ldt, d, lane);
+  RowRegs<NV> ra, rt;
+  load_row<false, NV>(ra, a + (static_cast<int64_t>(b) * T_a + tt) * lda, d, lane);
+  load_row<false, NV>(rt, t + (static_cast<int64_t>(b) * L + tt) * ldt, d, lane);
   if (apply_ln) {
     normalize_row(ra, d, lane, ga, ba, eps);
     normalize_row(rt, d, lane, gt, bt, eps);
   }
   float wsum = 0.0f;
 #pragma unroll
-  for (int i = 0; i < ROW_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
     if (c < d) {
 #pragma unroll
@@ -276,6 +282,17 @@ static unsigned grid_for(int64_t work_items, int block) {
   return static_cast<unsigned>(g);
 }
 
+// NV dispatch: instantiate the row kernels for 1, 2, 3, 4 and 8 vectors per lane (d <= 256 ... 2048)
+#define HRIEMO_DISPATCH_NV(d, ...)                              \
+  do {                                                          \
+    const int nv_ = ((d) + 255) / 256;                          \
+    if (nv_ <= 1) { constexpr int NV = 1; __VA_ARGS__; }        \
+    else if (nv_ == 2) { constexpr int NV = 2; __VA_ARGS__; }   \
+    else if (nv_ == 3) { constexpr int NV = 3; __VA_ARGS__; }   \
+    else if (nv_ == 4) { constexpr int NV = 4; __VA_ARGS__; }   \
+    else { constexpr int NV = 8; __VA_ARGS__; }                 \
+  } while (0)
+
 static bool row_shape_ok(int d) { return d > 0 && d % 8 == 0 && d <= ROW_MAX_VEC * 256; }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -309,12 +326,11 @@ extern "C" int hriemo_layernorm(const void* x, int32_t x_is_f32, int64_t ldx, co
   if (rows <= 0) return HRIEMO_OK;
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y_bf16);
   if (x_is_f32)
-    layernorm_kernel<true><<<grid, 256, 0, s>>>(x, ldx, gamma, beta, eps, static_cast<__nv_bfloat16*>(y_bf16),
-                                                y_f32, ldy, rows, d);
+    HRIEMO_DISPATCH_NV(d, (layernorm_kernel<true, NV><<<grid, 256, 0, s>>>(x, ldx, gamma, beta, eps, yb, y_f32, ldy, rows, d)));
   else
-    layernorm_kernel<false><<<grid, 256, 0, s>>>(x, ldx, gamma, beta, eps, static_cast<__nv_bfloat16*>(y_bf16),
-                                                 y_f32, ldy, rows, d);
+    HRIEMO_DISPATCH_NV(d, (layernorm_kernel<false, NV><<<grid, 256, 0, s>>>(x, ldx, gamma, beta, eps, yb, y_f32, ldy, rows, d)));
   return check_launch("layernorm");
 }
 
@@ -326,13 +342,11 @@ extern "C" int hriemo_ln_masked_mean(const void* x, int64_t ldx, const float* ga
   HRIEMO_REQUIRE(ldx % 8 == 0 && aligned16(x) && aligned16(gamma) && aligned16(beta),
                  "ln_masked_mean: misaligned operand");
   const size_t smem = static_cast<size_t>(8) * d * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(ln_masked_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4);
-    attr = true;
-  }
-  ln_masked_mean_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, apply_ln, pad, pooled, ld_pooled, T, d);
+  // 8 * d * 4 bytes <= 48 KB for d <= 1536; the d <= 2048 instance (NV = 8) may need 64 KB
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(ln_masked_mean_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4);
+  HRIEMO_DISPATCH_NV(d, (ln_masked_mean_kernel<NV><<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, apply_ln, pad, pooled, ld_pooled, T, d)));
   return check_launch("ln_masked_mean");
 }
 
@@ -357,10 +371,10 @@ extern "C" int hriemo_gate_blend(const void* a, int64_t lda, int32_t T_a, const 
                      aligned16(h_bf16) && aligned16(h_f32),
                  "gate_blend: misaligned operand");
   const int64_t rows = static_cast<int64_t>(B) * L;
-  gate_blend_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  HRIEMO_DISPATCH_NV(d, (gate_blend_kernel<NV><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(a), lda, T_a, static_cast<const __nv_bfloat16*>(t), ldt, gamma_a,
       beta_a, gamma_t, beta_t, eps, apply_ln, w, w_is_scalar, static_cast<__nv_bfloat16*>(h_bf16), h_f32,
-      ldh, beta_out, B, L, d);
+      ldh, beta_out, B, L, d)));
   return check_launch("gate_blend");
 }
 
