@@ -21,8 +21,10 @@ def timeit(fn, iters=10, warm=3):
 def main():
     dev = "cuda"
     res = []
-    for (M, N, K, epi) in [(2048000 // 4, 2304, 768, L.EPI_BIAS), (2048000 // 4, 3072, 768, L.EPI_BIAS_RELU), (2048000 // 4, 768, 3072, L.EPI_BIAS),
-                           (2048000 // 4, 768, 768, L.EPI_BIAS), (262144 // 4, 2304, 768, L.EPI_BIAS), (16384, 768, 768, L.EPI_BIAS)]:
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+    gemm_shapes = [] if only not in (None, "gemm") else [(2048000 // 4, 2304, 768, L.EPI_BIAS), (2048000 // 4, 3072, 768, L.EPI_BIAS_RELU), (2048000 // 4, 768, 3072, L.EPI_BIAS),
+                           (2048000 // 4, 768, 768, L.EPI_BIAS), (262144 // 4, 2304, 768, L.EPI_BIAS), (16384, 768, 768, L.EPI_BIAS)]
+    for (M, N, K, epi) in gemm_shapes:
         a = torch.randn(M, K, device=dev).bfloat16(); w = torch.randn(N, K, device=dev).bfloat16(); b = torch.randn(N, device=dev)
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         med, best = timeit(lambda: ops.gemm(a, w, b, epi, out=out))
@@ -30,7 +32,8 @@ def main():
         fl = 2.0 * M * N * K
         res.append(dict(kernel="gemm", M=M, N=N, K=K, ms=med, tflops=fl / med / 1e9, frac_burst=fl / med / 1e9 / PEAKS["bf16_tflops"], cublas_ms=medc, cublas_tflops=fl / medc / 1e9))
         print(res[-1], flush=True)
-    for (B, H, Tq, Tk, dh) in [(512, 8, 500, 500, 96), (512, 8, 500, 64, 96), (512, 8, 64, 500, 96), (512, 4, 300, 128, 64)]:
+    attn_shapes = [] if only not in (None, "attention") else [(512, 8, 500, 500, 96), (512, 8, 500, 64, 96), (512, 8, 64, 500, 96), (512, 8, 300, 300, 96), (512, 4, 300, 128, 64), (64, 8, 1000, 1000, 96)]
+    for (B, H, Tq, Tk, dh) in attn_shapes:
         d = H * dh
         q = torch.randn(B * Tq, d, device=dev).bfloat16(); k = torch.randn(B * Tk, d, device=dev).bfloat16()
         v = torch.randn(B, Tk, d, device=dev).bfloat16()
@@ -41,6 +44,8 @@ def main():
         fl = 4.0 * B * H * Tq * Tk * dh
         res.append(dict(kernel="attention", B=B, H=H, Tq=Tq, Tk=Tk, dh=dh, ms=med, tflops=fl / med / 1e9, frac_burst=fl / med / 1e9 / PEAKS["bf16_tflops"], sdpa_ms=meds))
         print(res[-1], flush=True)
+    if only not in (None, "elem"):
+        return
     rows, d = 2048000 // 4, 768
     x = torch.randn(rows, d, device=dev).bfloat16(); g = torch.ones(d, device=dev); bb = torch.zeros(d, device=dev)
     med, best = timeit(lambda: ops.layernorm(x, g, bb))
