@@ -1,19 +1,20 @@
-// Flash-style multi-head attention forward for sm_100a (tcgen05 + TMEM + TMA), v2:
+// Flash-style multi-head attention forward for sm_100a (tcgen05 + TMEM + TMA), v3:
 //   O[b, tq, h*dh:(h+1)*dh] = softmax_k(Q K^T * scale + key_padding) V
 //
-// Persistent kernel, one CTA per SM, looping over work items (utterance, head, pair of
-// 128-row query tiles).  320 threads:
-//   warp 0       TMA producer: Q tiles (one per query tile), K / V^T tiles of 128 keys in a
-//                2-stage ring; runs ahead across work items, so the next item's operands land
-//                while the current one is still being reduced.
-//   warp 1       tcgen05.mma issuer.  S_t = Q_t K^T (both operands in smem), O_t += P_t V with
-//                P_t read from tensor memory (it aliases the S_t columns).  The two query tiles
-//                ping-pong: while warpgroup A does softmax on S_A(j) the tensor core runs
-//                PV_B / S_B(j+1), and vice versa; each K / V^T tile is loaded once for 256 rows.
+// Persistent kernel, one CTA per SM, walking a flat sequence of steps
+// (work item = (utterance, head, pair of 128-row query tiles)) x (64-key step).  352 threads:
+//   warp 0       TMA producer: Q tiles (double-buffered per query tile), K / V^T tiles of 64 keys
+//                in a ring; it runs ahead across work items.
+//   warps 1, 10  tcgen05.mma issuers, one per query tile, so the two tiles never wait on each other.
+//                S_t = Q_t K^T is DOUBLE-BUFFERED in tensor memory and issued two steps ahead of
+//                the softmax (also across work-item boundaries); O_t += P_t V reads P_t from tensor
+//                memory (P aliases the S buffer it was computed from) and V^T from shared memory.
 //   warps 2..5   softmax warpgroup of query tile 0 \ one query row per thread (TMEM lane = row):
-//   warps 6..9   softmax warpgroup of query tile 1 / raw row max, lazy running max (rescale only
-//                when it grows by more than 2^8), p = ex2(fma(s, scale*log2e, -m)), P stored as
-//                bf16 into TMEM, row sums in fp32; final O / l written as bf16.
+//   warps 6..9   softmax warpgroup of query tile 1 / 64 scores held in registers, row max, lazy
+//                running max (O / l rescaled only when it grows by more than 2^8),
+//                p = ex2(fma(s, scale*log2e, -m)), P stored as bf16 into TMEM, fp32 row sums;
+//                final O / l written as bf16.
+// Tensor memory per query tile: S0 [0,64) S1 [64,128) O [128,128+dh)  -> 2 x 256 columns.
 //
 // Replaces the scaled_dot_product_attention inside nn.MultiheadAttention at
 // models/cross_modal_block_tacfn.py:74-80,85-91,98-104,111-117 and
@@ -28,30 +29,32 @@ namespace hriemo {
 
 int attention_v1_dispatch(const hriemo_attn_args* a, cudaStream_t s);  // attention_v1.cu (A/B only)
 
-constexpr int A2_BQ = 128;    // query rows per tile (UMMA M)
-constexpr int A2_BKV = 128;   // keys per tile
-constexpr int A2_THREADS = 320;
-constexpr float A2_LAZY_TAU = 8.0f;  // log2 units
+constexpr int A3_BQ = 128;   // query rows per tile (UMMA M)
+constexpr int A3_BKV = 64;   // keys per step (UMMA N of S, K extent of PV)
+constexpr int A3_THREADS = 352;  // TMA, MMA(tile 0), 2 x 4 softmax warps, MMA(tile 1)
+constexpr float A3_LAZY_TAU = 8.0f;  // log2 units
 
 template <int DH>
-struct Attn2Smem {
-  static constexpr int QCH = (DH + 63) / 64;   // 64-column (128-byte) chunks of Q / K rows
-  static constexpr int CHUNK = 128 * 128;      // [128 rows][128 B], 128B-swizzled
-  static constexpr int Q_TILE = QCH * CHUNK;
-  static constexpr int K_STAGE = QCH * CHUNK;
-  static constexpr int V_CHUNK = DH * 128;     // [DH rows][64 keys]
-  static constexpr int V_STAGE = 2 * V_CHUNK;
-  static constexpr int Q_OFF = 0;
-  static constexpr int K_OFF = Q_OFF + 2 * Q_TILE;
-  static constexpr int V_OFF = K_OFF + 2 * K_STAGE;
-  static constexpr int BAR_OFF = V_OFF + 2 * V_STAGE;
-  static constexpr int NUM_BARS = 18;
+struct Attn3Smem {
+  static constexpr int QCH = (DH + 63) / 64;       // 64-column (128-byte) chunks of Q / K rows
+  static constexpr int Q_CHUNK = A3_BQ * 128;      // [128 rows][128 B], 128B-swizzled
+  static constexpr int Q_TILE = QCH * Q_CHUNK;
+  static constexpr int K_CHUNK = A3_BKV * 128;     // [64 keys][128 B]
+  static constexpr int K_STAGE = QCH * K_CHUNK;
+  static constexpr int V_STAGE = DH * 128;         // [DH rows][64 keys]
+  static constexpr int KV_STAGES = (DH > 96) ? 2 : 3;
+  static constexpr int Q_OFF = 0;                  // [tile 2][buffer 2]
+  static constexpr int K_OFF = Q_OFF + 4 * Q_TILE;
+  static constexpr int V_OFF = K_OFF + KV_STAGES * K_STAGE;
+  static constexpr int BAR_OFF = V_OFF + KV_STAGES * V_STAGE;
+  // q_full[2][2] q_empty[2][2] k_full[3] k_empty[3] v_full[3] v_empty[3] s_full[2][2] p_full[2][2] pv_done[2][2]
+  static constexpr int NUM_BARS = 32;
   static constexpr int TMEM_SLOT_OFF = BAR_OFF + NUM_BARS * 8;
-  static constexpr int DYN_OFF = TMEM_SLOT_OFF + 16;   // caps[2][n_kv*128] f32, flags[2][n_kv] i32
-  static int dyn_bytes(int n_kv) { return DYN_OFF + 2 * n_kv * A2_BKV * 4 + 2 * n_kv * 4 + 1024; }
+  static constexpr int DYN_OFF = TMEM_SLOT_OFF + 16;   // caps[2][n_kv*64] f32, flags[2][n_kv] i32
+  static int dyn_bytes(int n_kv) { return DYN_OFF + 2 * n_kv * A3_BKV * 4 + 2 * n_kv * 4 + 1024; }
 };
 
-struct Attn2Params {
+struct Attn3Params {
   const uint8_t* key_pad;
   __nv_bfloat16* out;
   int64_t ldo;
@@ -67,14 +70,52 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// score = fminf(s, cap): cap is +inf for a valid key and -inf for a masked one; fminf returns the
+// non-NaN operand, so garbage (even NaN) in a masked column becomes exactly -inf.
+__device__ __forceinline__ void apply_caps(uint32_t (&v)[32], const float* cap) {
+  const float4* cp = reinterpret_cast<const float4*>(cap);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 ck = cp[i];
+    v[i * 4 + 0] = __float_as_uint(fminf(__uint_as_float(v[i * 4 + 0]), ck.x));
+    v[i * 4 + 1] = __float_as_uint(fminf(__uint_as_float(v[i * 4 + 1]), ck.y));
+    v[i * 4 + 2] = __float_as_uint(fminf(__uint_as_float(v[i * 4 + 2]), ck.z));
+    v[i * 4 + 3] = __float_as_uint(fminf(__uint_as_float(v[i * 4 + 3]), ck.w));
+  }
+}
+
+__device__ __forceinline__ void max4(float (&m4)[4], const uint32_t (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    m4[0] = fmaxf(m4[0], __uint_as_float(v[i + 0]));
+    m4[1] = fmaxf(m4[1], __uint_as_float(v[i + 1]));
+    m4[2] = fmaxf(m4[2], __uint_as_float(v[i + 2]));
+    m4[3] = fmaxf(m4[3], __uint_as_float(v[i + 3]));
+  }
+}
+
+// p = 2^(s*sc + neg_m) for 32 scores -> 16 packed bf16 pairs; four independent row-sum chains.
+__device__ __forceinline__ void exp_pack(const uint32_t (&v)[32], float sc, float neg_m, float (&l4)[4],
+                                         uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), sc, neg_m));
+    const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), sc, neg_m));
+    l4[i & 1] += e0;
+    l4[2 + (i & 1)] += e1;
+    pk[i] = pack_bf16(e0, e1);
+  }
+}
+
 template <int DH>
-__global__ void __launch_bounds__(A2_THREADS, 1)
-attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                      const __grid_constant__ CUtensorMap tm_v, const Attn2Params p) {
-  using L = Attn2Smem<DH>;
+__global__ void __launch_bounds__(A3_THREADS, 1)
+attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                      const __grid_constant__ CUtensorMap tm_v, const Attn3Params p) {
+  using L = Attn3Smem<DH>;
   constexpr uint32_t TMEM_COLS = 512;
-  constexpr uint32_t TILE_COLS = 256;   // per query tile: S / P at +0 (128 cols), O at +128 (DH cols)
+  constexpr uint32_t TILE_COLS = 256;   // per query tile: S0 at +0, S1 at +64, O at +128
   constexpr uint32_t O_COL = 128;
+  constexpr int KS = L::KV_STAGES;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -82,15 +123,18 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   uint8_t* base_ptr = smem_raw + (base - raw_u32);
   const uint32_t sQ = base + L::Q_OFF, sK = base + L::K_OFF, sV = base + L::V_OFF;
   const uint32_t bars = base + L::BAR_OFF;
-  const uint32_t b_qfull = bars + 0 * 8;     // [2] per query tile
-  const uint32_t b_qempty = bars + 2 * 8;    // [2]
-  const uint32_t b_kfull = bars + 4 * 8;     // [2] per stage
-  const uint32_t b_kempty = bars + 6 * 8;    // [2]
-  const uint32_t b_vfull = bars + 8 * 8;     // [2]
-  const uint32_t b_vempty = bars + 10 * 8;   // [2]
-  const uint32_t b_sfull = bars + 12 * 8;    // [2] per query tile
-  const uint32_t b_pfull = bars + 14 * 8;    // [2]
-  const uint32_t b_pvdone = bars + 16 * 8;   // [2]
+  const uint32_t b_qfull = bars + 0 * 8;     // [tile][buffer]
+  const uint32_t b_qempty = bars + 4 * 8;    // [tile][buffer]
+  const uint32_t b_kfull = bars + 8 * 8;     // [stage]
+  const uint32_t b_kempty = bars + 11 * 8;
+  const uint32_t b_vfull = bars + 14 * 8;
+  const uint32_t b_vempty = bars + 17 * 8;
+  const uint32_t b_sfull = bars + 20 * 8;    // [tile][S buffer]
+  // p_full / pv_done are indexed [tile][k & 1] by the tile's running step count k: an mbarrier wait
+  // only sees one parity bit, and with S issued two steps ahead the two sides may be up to two
+  // steps apart; alternating barriers keep every wait at most one phase behind its barrier.
+  const uint32_t b_pfull = bars + 24 * 8;
+  const uint32_t b_pvdone = bars + 28 * 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + L::TMEM_SLOT_OFF);
 
   const int warp = threadIdx.x >> 5;
@@ -101,17 +145,19 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(b_qfull + s * 8, 1);
       mbar_init(b_qempty + s * 8, 1);
-      mbar_init(b_kfull + s * 8, 1);
-      mbar_init(b_kempty + s * 8, 1);
-      mbar_init(b_vfull + s * 8, 1);
-      mbar_init(b_vempty + s * 8, 1);
       mbar_init(b_sfull + s * 8, 1);
-      mbar_init(b_pfull + s * 8, 128);
       mbar_init(b_pvdone + s * 8, 1);
     }
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(b_kfull + s * 8, 1);
+      mbar_init(b_kempty + s * 8, 2);   // one arrival per MMA issuer
+      mbar_init(b_vfull + s * 8, 1);
+      mbar_init(b_vempty + s * 8, 2);
+    }
+    for (int s = 0; s < 4; ++s) mbar_init(b_pfull + s * 8, 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(base + L::TMEM_SLOT_OFF);
@@ -123,98 +169,126 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t qcnt[2] = {0, 0};
-      uint32_t g = 0;  // running K/V tile index -> ring stage and phase
+      uint32_t qcnt[2] = {0, 0};  // Q loads issued per query tile -> buffer and phase
+      uint32_t g = 0;             // flat step index -> K/V ring stage and phase
       for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int qp = static_cast<int>(item % p.n_qp);
         const int64_t bh = item / p.n_qp;
         const int h = static_cast<int>(bh % p.H);
         const int b = static_cast<int>(bh / p.H);
-        const int q0 = qp * 2 * A2_BQ;
+        const int q0 = qp * 2 * A3_BQ;
         for (int t = 0; t < 2; ++t) {
-          if (q0 + t * A2_BQ >= p.Tq) break;
-          mbar_wait(b_qempty + t * 8, (qcnt[t] & 1) ^ 1);
-          mbar_arrive_expect_tx(b_qfull + t * 8, L::Q_TILE);
+          if (q0 + t * A3_BQ >= p.Tq) break;
+          const uint32_t qb = qcnt[t] & 1u, qpar = (qcnt[t] >> 1) & 1u;
+          const uint32_t bar = (t * 2 + qb) * 8;
+          mbar_wait(b_qempty + bar, qpar ^ 1);
+          mbar_arrive_expect_tx(b_qfull + bar, L::Q_TILE);
           for (int c = 0; c < L::QCH; ++c)
-            tma_load_2d(&tm_q, b_qfull + t * 8, sQ + t * L::Q_TILE + c * L::CHUNK, h * DH + c * 64,
-                        b * p.Tq + q0 + t * A2_BQ);
+            tma_load_2d(&tm_q, b_qfull + bar, sQ + (t * 2 + qb) * L::Q_TILE + c * L::Q_CHUNK, h * DH + c * 64,
+                        b * p.Tq + q0 + t * A3_BQ);
           ++qcnt[t];
         }
         for (int j = 0; j < n_kv; ++j, ++g) {
-          const uint32_t s = g & 1u, par = (g >> 1) & 1u;
+          const uint32_t s = g % KS, par = (g / KS) & 1u;
           mbar_wait(b_kempty + s * 8, par ^ 1);
           mbar_arrive_expect_tx(b_kfull + s * 8, L::K_STAGE);
           for (int c = 0; c < L::QCH; ++c)
-            tma_load_2d(&tm_k, b_kfull + s * 8, sK + s * L::K_STAGE + c * L::CHUNK, h * DH + c * 64,
-                        b * p.Tk + j * A2_BKV);
+            tma_load_2d(&tm_k, b_kfull + s * 8, sK + s * L::K_STAGE + c * L::K_CHUNK, h * DH + c * 64,
+                        b * p.Tk + j * A3_BKV);
           mbar_wait(b_vempty + s * 8, par ^ 1);
           mbar_arrive_expect_tx(b_vfull + s * 8, L::V_STAGE);
-          for (int c = 0; c < 2; ++c)
-            tma_load_2d(&tm_v, b_vfull + s * 8, sV + s * L::V_STAGE + c * L::V_CHUNK, j * A2_BKV + c * 64,
-                        (b * p.H + h) * DH);
+          tma_load_2d(&tm_v, b_vfull + s * 8, sV + s * L::V_STAGE, j * A3_BKV, (b * p.H + h) * DH);
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 10) {
+    // ===================== MMA issuers: warp 1 drives query tile 0, warp 10 query tile 1 =====
+    // Each walks the CTA's flat step sequence for its own tile: PV_t(g) as soon as P_t(g) is
+    // there, then S_t(g+2) into the S buffer PV_t(g) just consumed (same thread => in order).
+    // The two tiles only meet at the shared K / V^T stages, whose "empty" barriers expect one
+    // arrival from each issuer (a plain arrive when the tile does not exist for an item).
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(A2_BQ, A2_BKV);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(A2_BQ, DH);
-      uint32_t qcnt[2] = {0, 0}, pcnt[2] = {0, 0};
-      uint32_t g = 0;
-      auto issue_s = [&](int t, uint32_t stage) {
-#pragma unroll
-        for (int st = 0; st < DH / 16; ++st) {
-          const uint32_t off = (st >> 2) * L::CHUNK + (st & 3) * 32;
-          umma_bf16(tmem_base + t * TILE_COLS, umma_desc_sw128(sQ + t * L::Q_TILE + off),
-                    umma_desc_sw128(sK + stage * L::K_STAGE + off), idesc_s, st != 0);
-        }
-        umma_commit(b_sfull + t * 8);
+      const int t = (warp == 1) ? 0 : 1;
+      constexpr uint32_t idesc_s = umma_idesc_bf16(A3_BQ, A3_BKV);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(A3_BQ, DH);
+      const uint32_t n_items = static_cast<uint32_t>(p.n_items);
+      const uint32_t my_items = (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x;
+      const uint32_t total = my_items * static_cast<uint32_t>(n_kv);  // flat steps of this CTA
+      const uint32_t tile_tmem = tmem_base + t * TILE_COLS;
+      const uint64_t k_desc0 = umma_desc_sw128(sK);
+      const uint64_t v_desc0 = umma_desc_sw128(sV);
+      auto tile_active = [&](uint32_t item) {
+        return t == 0 || static_cast<int>(item % static_cast<uint32_t>(p.n_qp)) * 2 * A3_BQ + A3_BQ < p.Tq;
       };
-      for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int qp = static_cast<int>(item % p.n_qp);
-        const int nt = (qp * 2 * A2_BQ + A2_BQ < p.Tq) ? 2 : 1;  // active query tiles
-        // ---- S_t(0)
-        {
-          const uint32_t s = g & 1u, par = (g >> 1) & 1u;
-          for (int t = 0; t < nt; ++t) mbar_wait(b_qfull + t * 8, qcnt[t] & 1);
-          mbar_wait(b_kfull + s * 8, par);
+      // ---- S cursor (two steps ahead of the PV cursor)
+      uint32_t s_g = 0, s_item = blockIdx.x, qcnt = 0;
+      int s_j = 0;
+      bool s_act = tile_active(s_item);
+      auto issue_s = [&]() {
+        const uint32_t ks = s_g % KS, kpar = (s_g / KS) & 1u;
+        const uint32_t qslot = t * 2 + (qcnt & 1u);
+        if (s_act && s_j == 0) mbar_wait(b_qfull + qslot * 8, (qcnt >> 1) & 1u);
+        mbar_wait(b_kfull + ks * 8, kpar);
+        if (s_act) {
           tc_fence_after_sync();
-          for (int t = 0; t < nt; ++t) {
-            issue_s(t, s);
-            if (n_kv == 1) umma_commit(b_qempty + t * 8);
-          }
-          umma_commit(b_kempty + s * 8);
-        }
-        for (int j = 0; j < n_kv; ++j, ++g) {
-          const uint32_t s = g & 1u, par = (g >> 1) & 1u;
-          const bool more = j + 1 < n_kv;
-          const uint32_t s2 = (g + 1) & 1u, par2 = ((g + 1) >> 1) & 1u;
-          const int rem = p.Tk - j * A2_BKV;  // keys left from this tile on (> 0)
-          mbar_wait(b_vfull + s * 8, par);
-          if (more) mbar_wait(b_kfull + s2 * 8, par2);
-          for (int t = 0; t < nt; ++t) {
-            mbar_wait(b_pfull + t * 8, pcnt[t] & 1);
-            ++pcnt[t];
-            tc_fence_after_sync();
+          const uint64_t q_desc = umma_desc_sw128(sQ + qslot * L::Q_TILE);
+          const uint64_t k_desc = k_desc0 + ((ks * L::K_STAGE) >> 4);
+          const uint32_t d_tmem = tile_tmem + (s_g & 1u) * A3_BKV;
 #pragma unroll
-            for (int st = 0; st < A2_BKV / 16; ++st) {
-              if (st * 16 < rem) {  // P is zero and V^T zero-filled beyond Tk: skip those K-steps
-                umma_bf16_ts(tmem_base + t * TILE_COLS + O_COL, tmem_base + t * TILE_COLS + st * 8,
-                             umma_desc_sw128(sV + s * L::V_STAGE + (st >> 2) * L::V_CHUNK + (st & 3) * 32),
-                             idesc_pv, (j | st) != 0);
-              }
-            }
-            umma_commit(b_pvdone + t * 8);
-            if (more) {
-              issue_s(t, s2);  // overwrites S_t / P_t: ordered after PV_t(j) by in-order MMA execution
-              if (j + 2 == n_kv) umma_commit(b_qempty + t * 8);
-            }
+          for (int st = 0; st < DH / 16; ++st) {
+            umma_bf16(d_tmem, q_desc + (((st >> 2) * L::Q_CHUNK + (st & 3) * 32) >> 4),
+                      k_desc + (((st >> 2) * L::K_CHUNK + (st & 3) * 32) >> 4), idesc_s, st != 0);
           }
-          umma_commit(b_vempty + s * 8);
-          if (more) umma_commit(b_kempty + s2 * 8);
+          umma_commit(b_sfull + (t * 2 + (s_g & 1u)) * 8);
+          umma_commit(b_kempty + ks * 8);
+          if (s_j == n_kv - 1) {
+            umma_commit(b_qempty + qslot * 8);
+            ++qcnt;
+          }
+        } else {
+          mbar_arrive(b_kempty + ks * 8);
         }
-        for (int t = 0; t < nt; ++t) ++qcnt[t];
+        ++s_g;
+        if (++s_j == n_kv) {
+          s_j = 0;
+          s_item += gridDim.x;
+          s_act = s_item < n_items && tile_active(s_item);
+        }
+      };
+      if (total > 0) issue_s();
+      if (total > 1) issue_s();
+      // ---- PV cursor
+      uint32_t pcnt = 0, pv_item = blockIdx.x;
+      int pv_j = 0;
+      bool pv_act = tile_active(pv_item);
+      for (uint32_t g = 0; g < total; ++g) {
+        const uint32_t vs = g % KS, vpar = (g / KS) & 1u;
+        mbar_wait(b_vfull + vs * 8, vpar);
+        if (pv_act) {
+          const int rem = p.Tk - pv_j * A3_BKV;  // keys left from this step on (> 0)
+          const uint32_t slot = t * 2 + (pcnt & 1u);
+          mbar_wait(b_pfull + slot * 8, (pcnt >> 1) & 1u);
+          ++pcnt;
+          tc_fence_after_sync();
+          const uint64_t v_desc = v_desc0 + ((vs * L::V_STAGE) >> 4);
+          const uint32_t p_tmem = tile_tmem + (g & 1u) * A3_BKV;
+#pragma unroll
+          for (int st = 0; st < A3_BKV / 16; ++st) {
+            if (st * 16 < rem)  // P is zero and V^T zero-filled beyond Tk: skip those K-steps
+              umma_bf16_ts(tile_tmem + O_COL, p_tmem + st * 8, v_desc + ((st * 32) >> 4), idesc_pv,
+                           (pv_j | st) != 0);
+          }
+          umma_commit(b_pvdone + slot * 8);
+          umma_commit(b_vempty + vs * 8);
+        } else {
+          mbar_arrive(b_vempty + vs * 8);
+        }
+        if (s_g < total) issue_s();  // S(g+2) reuses the S buffer whose P was just consumed
+        if (++pv_j == n_kv) {
+          pv_j = 0;
+          pv_item += gridDim.x;
+          pv_act = pv_item < n_items && tile_active(pv_item);
+        }
       }
     }
   } else {
@@ -223,34 +297,44 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;          // query row inside the tile == TMEM lane
     const int wg_tid = threadIdx.x - 64 - wg * 128;
-    float* caps = reinterpret_cast<float*>(base_ptr + L::DYN_OFF) + wg * n_kv * A2_BKV;
-    int* flags = reinterpret_cast<int*>(base_ptr + L::DYN_OFF + 2 * n_kv * A2_BKV * 4) + wg * n_kv;
+    float* caps = reinterpret_cast<float*>(base_ptr + L::DYN_OFF) + wg * n_kv * A3_BKV;
+    int* flags = reinterpret_cast<int*>(base_ptr + L::DYN_OFF + 2 * n_kv * A3_BKV * 4) + wg * n_kv;
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_sel + wg * TILE_COLS;
-    const uint32_t t_o = t_s + O_COL;
-    uint32_t scnt = 0, pvcnt = 0;
+    const uint32_t t_tile = tmem_base + lane_sel + wg * TILE_COLS;
+    const uint32_t t_o = t_tile + O_COL;
+    const float sc = p.scale_log2;
+    uint32_t scnt0 = 0, scnt1 = 0;   // completed uses of each S buffer of this tile
+    // PV(k) of this tile commits to pv_done[k & 1].  Waiting for PV(k) is only safe while PV(k+2)
+    // cannot have completed (mbarrier waits see one parity bit), i.e. before P(k+2) is handed over:
+    // the consumer may lag the producer by at most two tiles, and never does more.
+    uint32_t pv_seen = 0;        // PVs of this tile known to have retired
+    uint32_t pv_issued = 0;      // P tiles handed to the MMA warp so far
+    auto consume_pv = [&](uint32_t target) {
+      while (pv_seen < target) {
+        mbar_wait(b_pvdone + (wg * 2 + (pv_seen & 1u)) * 8, (pv_seen >> 1) & 1u);
+        ++pv_seen;
+      }
+    };
+    int64_t g = 0;               // flat step index of this CTA
     int cur_b = -1;
 
-    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, g += n_kv) {
       const int qp = static_cast<int>(item % p.n_qp);
       const int64_t bh = item / p.n_qp;
       const int h = static_cast<int>(bh % p.H);
       const int b = static_cast<int>(bh / p.H);
-      const int q0 = qp * 2 * A2_BQ + wg * A2_BQ;
+      const int q0 = qp * 2 * A3_BQ + wg * A3_BQ;
       if (q0 >= p.Tq) continue;  // this warpgroup's tile does not exist for this item
 
       if (b != cur_b) {
-        // key caps: +inf for valid keys, -inf for PAD keys and keys >= Tk.  score = fminf(s, cap):
-        // fminf returns the non-NaN operand, so whatever a masked column holds (rows of the next
-        // utterance inside the 128-key box, possibly NaN) becomes exactly -inf.
         asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
         for (int j = wg_tid; j < n_kv; j += 128) flags[j] = 0;
         asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
-        for (int kk = wg_tid; kk < n_kv * A2_BKV; kk += 128) {
+        for (int kk = wg_tid; kk < n_kv * A3_BKV; kk += 128) {
           bool pad = kk >= p.Tk;
           if (!pad && p.key_pad != nullptr) pad = p.key_pad[static_cast<int64_t>(b) * p.Tk + kk] != 0;
           caps[kk] = pad ? -INFINITY : INFINITY;
-          if (pad) flags[kk / A2_BKV] = 1;
+          if (pad) flags[kk / A3_BKV] = 1;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
         cur_b = b;
@@ -259,46 +343,39 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       float m_run = -INFINITY;  // running reference maximum, in log2 units (score * scale * log2 e)
       float l_run = 0.0f;
       for (int j = 0; j < n_kv; ++j) {
-        const int rem = p.Tk - j * A2_BKV;
-        const int nch = rem >= A2_BKV ? 4 : (rem + 31) / 32;  // 32-key chunks holding any valid key
-        const bool masked = flags[j] != 0;                    // warp-uniform
-        const float* cap_j = caps + j * A2_BKV;
-        mbar_wait(b_sfull + wg * 8, scnt & 1);
-        ++scnt;
+        const uint32_t sbuf = static_cast<uint32_t>((g + j) & 1);
+        const uint32_t t_s = t_tile + sbuf * A3_BKV;
+        const int rem = p.Tk - j * A3_BKV;
+        const bool two = rem > 32;                   // second 32-key chunk holds a valid key
+        const bool masked = flags[j] != 0;           // warp-uniform
+        const float* cap_j = caps + j * A3_BKV;
+        mbar_wait(b_sfull + (wg * 2 + sbuf) * 8, (sbuf ? scnt1 : scnt0) & 1u);
+        if (sbuf) ++scnt1; else ++scnt0;
         tc_fence_after_sync();
 
-        // ---- pass 1: raw row maximum
-        float mx = -INFINITY;
-        for (int c = 0; c < nch; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_s + c * 32, v);
-          tmem_ld_wait();
-          if (masked) {
-            const float4* cp = reinterpret_cast<const float4*>(cap_j + c * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 ck = cp[i];
-              mx = fmaxf(mx, fminf(__uint_as_float(v[i * 4 + 0]), ck.x));
-              mx = fmaxf(mx, fminf(__uint_as_float(v[i * 4 + 1]), ck.y));
-              mx = fmaxf(mx, fminf(__uint_as_float(v[i * 4 + 2]), ck.z));
-              mx = fmaxf(mx, fminf(__uint_as_float(v[i * 4 + 3]), ck.w));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-          }
+        uint32_t va[32], vb[32];
+        tmem_ld32(t_s, va);
+        if (two) tmem_ld32(t_s + 32, vb);
+        tmem_ld_wait();
+        if (masked) {
+          apply_caps(va, cap_j);
+          if (two) apply_caps(vb, cap_j + 32);
         }
-        const float tile_max = mx * p.scale_log2;  // scale > 0; -inf stays -inf
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        max4(m4, va);
+        if (two) max4(m4, vb);
+        const float tile_max = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;  // sc > 0
 
         // ---- lazy running maximum; O / l rescale only when the maximum grew by more than 2^TAU
         if (j == 0) {
           m_run = tile_max;
         } else {
-          const bool need = tile_max > m_run + A2_LAZY_TAU;
-          mbar_wait(b_pvdone + wg * 8, pvcnt & 1);  // PV(j-1) retired: O is stable
-          ++pvcnt;
-          tc_fence_after_sync();
-          if (__any_sync(0xffffffffu, need)) {
+          const bool need = tile_max > m_run + A3_LAZY_TAU;
+          const bool any_need = __any_sync(0xffffffffu, need);
+          // all but the latest PV retired long ago; the latest one is awaited only for a rescale
+          consume_pv(any_need ? pv_issued : pv_issued - 1);
+          if (any_need) {
+            tc_fence_after_sync();
             const float alpha = need ? ex2_approx(m_run - tile_max) : 1.0f;
             if (need) m_run = tile_max;
             l_run *= alpha;
@@ -315,44 +392,24 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
         const float neg_m = (m_run == -INFINITY) ? 0.0f : -m_run;
 
-        // ---- pass 2: p = 2^(s*scale - m), row sum, bf16 P into TMEM (aliases the S columns already read)
-        float l_add = 0.0f;
-        for (int c = 0; c < nch; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_s + c * 32, v);
-          tmem_ld_wait();
-          float e[32];
-          if (masked) {
-            const float4* cp = reinterpret_cast<const float4*>(cap_j + c * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 ck = cp[i];
-              e[i * 4 + 0] = ex2_approx(fmaf(fminf(__uint_as_float(v[i * 4 + 0]), ck.x), p.scale_log2, neg_m));
-              e[i * 4 + 1] = ex2_approx(fmaf(fminf(__uint_as_float(v[i * 4 + 1]), ck.y), p.scale_log2, neg_m));
-              e[i * 4 + 2] = ex2_approx(fmaf(fminf(__uint_as_float(v[i * 4 + 2]), ck.z), p.scale_log2, neg_m));
-              e[i * 4 + 3] = ex2_approx(fmaf(fminf(__uint_as_float(v[i * 4 + 3]), ck.w), p.scale_log2, neg_m));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
-          }
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            l_add += e[2 * i] + e[2 * i + 1];
-            pk[i] = pack_bf16(e[2 * i], e[2 * i + 1]);
-          }
-          tmem_st16(t_s + c * 16, pk);
+        // ---- p = 2^(s*scale - m), row sum, bf16 P into the first 32 columns of this S buffer
+        float l4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        uint32_t pk[16];
+        exp_pack(va, sc, neg_m, l4, pk);
+        tmem_st16(t_s, pk);
+        if (two) {
+          exp_pack(vb, sc, neg_m, l4, pk);
+          tmem_st16(t_s + 16, pk);
         }
-        l_run += l_add;
+        l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
         tmem_st_wait();
         tc_fence_before_sync();
-        mbar_arrive(b_pfull + wg * 8);
+        mbar_arrive(b_pfull + (wg * 2 + (pv_issued & 1u)) * 8);
+        ++pv_issued;
       }
 
       // ---- epilogue: O / l -> bf16 rows of the [B*Tq, H*dh] output
-      mbar_wait(b_pvdone + wg * 8, pvcnt & 1);
-      ++pvcnt;
+      consume_pv(pv_issued);
       tc_fence_after_sync();
       const float inv_l = 1.0f / l_run;  // l == 0 (every key masked) -> inf -> NaN like torch.softmax
       const bool row_ok = q0 + r < p.Tq;
@@ -376,7 +433,7 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
         __syncwarp();
       }
-      tc_fence_before_sync();  // O reads are complete before the next item's p_full arrival lets PV overwrite O
+      tc_fence_before_sync();  // O reads retire before the next item's first p_full lets PV overwrite O
     }
   }
 
@@ -389,33 +446,35 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 }
 
 template <int DH>
-static int launch_attention2(const hriemo_attn_args& a, cudaStream_t stream) {
-  using L = Attn2Smem<DH>;
+static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
+  using L = Attn3Smem<DH>;
   const int d = a.H * DH;
-  const int n_kv = (a.Tk + A2_BKV - 1) / A2_BKV;
+  const int n_kv = (a.Tk + A3_BKV - 1) / A3_BKV;
   const int smem = L::dyn_bytes(n_kv);
   if (smem > 227 * 1024)
     return set_error(HRIEMO_ERR_INVALID, "attention: Tk=%d too long for the shared-memory key caps (dh=%d)",
                      a.Tk, DH);
   CUtensorMap tq, tk, tv;
-  int rc = make_tmap_bf16_2d(&tq, a.q, (uint64_t)d, (uint64_t)a.B * a.Tq, (uint64_t)a.ldq, 64, A2_BQ);
+  int rc = make_tmap_bf16_2d(&tq, a.q, (uint64_t)d, (uint64_t)a.B * a.Tq, (uint64_t)a.ldq, 64, A3_BQ);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tk, a.k, (uint64_t)d, (uint64_t)a.B * a.Tk, (uint64_t)a.ldk, 64, A2_BKV);
+  rc = make_tmap_bf16_2d(&tk, a.k, (uint64_t)d, (uint64_t)a.B * a.Tk, (uint64_t)a.ldk, 64, A3_BKV);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tv, a.vt, (uint64_t)a.Tk, (uint64_t)a.B * d, (uint64_t)a.Tk_pad, 64, DH);
   if (rc) return rc;
-  Attn2Params p;
+  Attn3Params p;
   p.key_pad = a.key_pad;
   p.out = static_cast<__nv_bfloat16*>(a.out);
   p.ldo = a.ldo;
   p.B = a.B; p.H = a.H; p.Tq = a.Tq; p.Tk = a.Tk;
   p.n_kv = n_kv;
-  p.n_qp = (a.Tq + 2 * A2_BQ - 1) / (2 * A2_BQ);
+  p.n_qp = (a.Tq + 2 * A3_BQ - 1) / (2 * A3_BQ);
   p.n_items = static_cast<int64_t>(a.B) * a.H * p.n_qp;
+  if (p.n_items * n_kv >= (1ll << 31))
+    return set_error(HRIEMO_ERR_INVALID, "attention: too many (item, step) pairs for 32-bit step counters");
   p.scale_log2 = a.scale * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_fwd2_kernel<DH>,
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd3_kernel<DH>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess)
       return set_error(HRIEMO_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -423,7 +482,7 @@ static int launch_attention2(const hriemo_attn_args& a, cudaStream_t stream) {
   }
   const int64_t sms = device_sm_count();
   const unsigned grid = static_cast<unsigned>(p.n_items < sms ? p.n_items : sms);
-  attention_fwd2_kernel<DH><<<grid, A2_THREADS, smem, stream>>>(tq, tk, tv, p);
+  attention_fwd3_kernel<DH><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, p);
   return check_launch("attention_bf16");
 }
 
@@ -442,12 +501,12 @@ extern "C" int hriemo_attention_bf16(const hriemo_attn_args* a, void* stream) {
   HRIEMO_REQUIRE(a->dh == 32 || a->dh == 64 || a->dh == 96 || a->dh == 128,
                  "attention: head dim %d not in {32,64,96,128}", a->dh);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static const bool use_v1 = getenv("HRIEMO_ATTN_V1") != nullptr;  // A/B switch while v2 is validated
+  static const bool use_v1 = getenv("HRIEMO_ATTN_V1") != nullptr;  // A/B switch while v3 is validated
   if (use_v1) return attention_v1_dispatch(a, s);
   switch (a->dh) {
-    case 32: return launch_attention2<32>(*a, s);
-    case 64: return launch_attention2<64>(*a, s);
-    case 96: return launch_attention2<96>(*a, s);
-    default: return launch_attention2<128>(*a, s);
+    case 32: return launch_attention3<32>(*a, s);
+    case 64: return launch_attention3<64>(*a, s);
+    case 96: return launch_attention3<96>(*a, s);
+    default: return launch_attention3<128>(*a, s);
   }
 }

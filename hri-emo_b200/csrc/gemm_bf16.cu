@@ -45,8 +45,8 @@ struct GemmSmem {
   static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
   static constexpr int OUT_OFF = B_OFF + STAGES * B_STAGE_BYTES;   // 4 warps x 2 boxes of [32][64] bf16
   static constexpr int BAR_OFF = OUT_OFF + 8 * OUT_BOX_BYTES;
-  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], resid_full[4 warps][2], tmem_ptr
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4 + 8) * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
 };
 
@@ -66,7 +66,8 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const __grid_constant__ CUtensorMap tm_c, const GemmKernelParams p) {
+                 const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_r,
+                 const GemmKernelParams p) {
   using L = GemmSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages (power of two: 256 or 512)
   constexpr uint32_t STAGE_TX = A_STAGE_BYTES + L::B_STAGE_BYTES;
@@ -80,7 +81,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t bar_empty = bar_full + STAGES * 8;
   const uint32_t bar_tfull = bar_empty + STAGES * 8;
   const uint32_t bar_tempty = bar_tfull + 2 * 8;
-  const uint32_t tmem_slot = bar_tempty + 2 * 8;
+  const uint32_t bar_resid = bar_tempty + 2 * 8;
+  const uint32_t tmem_slot = bar_resid + 8 * 8;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -91,6 +93,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     tma_prefetch_desc(&tm_c);
+    tma_prefetch_desc(&tm_r);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -101,6 +104,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_init(bar_tfull + s * 8, 1);
       mbar_init(bar_tempty + s * 8, 4);  // one arrive per epilogue warp
     }
+    for (int s = 0; s < 8; ++s) mbar_init(bar_resid + s * 8, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -163,7 +167,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int row_in_tile = quad * 32 + lane;
     const uint32_t my_stage = sOut + static_cast<uint32_t>(quad) * (2 * OUT_BOX_BYTES);
     const bool bf16_out = p.epilogue != HRIEMO_EPI_BIAS_RESID_F32 && p.epilogue != HRIEMO_EPI_BIAS_F32;
+    // bf16 residual (pre-LayerNorm epilogue): the [32 x 64] residual box of the NEXT slab is
+    // prefetched by TMA into the idle staging buffer and the sum is formed in place.
+    const bool tma_resid = p.epilogue == HRIEMO_EPI_BIAS_RESID;
+    const uint32_t my_rbar = bar_resid + static_cast<uint32_t>(quad) * 16;
+    auto prefetch_resid = [&](int64_t tile_, int slab_, uint32_t ctr_) {
+      const int n_ = static_cast<int>(tile_ % p.num_n_blocks) * BN + slab_ * 64;
+      const int m_ = static_cast<int>((tile_ / p.num_n_blocks) * BM) + quad * 32;
+      const uint32_t b_ = ctr_ & 1u;
+      mbar_arrive_expect_tx(my_rbar + b_ * 8, OUT_BOX_BYTES);
+      tma_load_2d(&tm_r, my_rbar + b_ * 8, my_stage + b_ * OUT_BOX_BYTES, n_, m_);
+    };
     uint32_t it = 0, slab_ctr = 0;
+    if (tma_resid && lane == 0 && blockIdx.x < p.num_tiles) prefetch_resid(blockIdx.x, 0, 0);
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1u;
       const uint32_t aphase = (it >> 1) & 1u;
@@ -194,9 +210,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         uint32_t buf = 0;
         if (staged) {
           buf = my_stage + (slab_ctr & 1u) * OUT_BOX_BYTES;
-          ++slab_ctr;
-          if (lane == 0) bulk_wait_read<1>();  // the store issued two slabs ago has left this buffer
-          __syncwarp();
+          if (tma_resid) {
+            mbar_wait(my_rbar + (slab_ctr & 1u) * 8, (slab_ctr >> 1) & 1u);  // residual box has landed
+          } else {
+            if (lane == 0) bulk_wait_read<1>();  // the store issued two slabs ago has left this buffer
+            __syncwarp();
+          }
         }
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -216,12 +235,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (p.epilogue == HRIEMO_EPI_BIAS_RELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
-          } else if (p.epilogue == HRIEMO_EPI_BIAS_RESID && row_ok) {
-            const uint4* rp = reinterpret_cast<const uint4*>(
-                static_cast<const __nv_bfloat16*>(p.resid) + m * p.ldr + nn);
+          } else if (tma_resid) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const uint4 r4 = __ldg(rp + i);
+              const uint32_t slot = static_cast<uint32_t>((hf * 4 + i) ^ (lane & 7));
+              uint4 r4;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(r4.x), "=r"(r4.y), "=r"(r4.z), "=r"(r4.w)
+                           : "r"(buf + lane * 128 + slot * 16)
+                           : "memory");
               f[i * 8 + 0] += bf16_lo(r4.x); f[i * 8 + 1] += bf16_hi(r4.x);
               f[i * 8 + 2] += bf16_lo(r4.y); f[i * 8 + 3] += bf16_hi(r4.y);
               f[i * 8 + 4] += bf16_lo(r4.z); f[i * 8 + 5] += bf16_hi(r4.z);
@@ -266,7 +288,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (lane == 0) {
             tma_store_2d(&tm_c, buf, n, static_cast<int>(m_tile) + quad * 32);
             bulk_commit();
+            if (tma_resid) {
+              // next slab of this warp: same tile, or slab 0 of this CTA's next tile
+              int64_t nt_ = tile;
+              int ns_ = s + 1;
+              if (ns_ >= BN / 64 || n0 + ns_ * 64 >= p.N) { nt_ = tile + gridDim.x; ns_ = 0; }
+              if (nt_ < p.num_tiles) {
+                bulk_wait_read<1>();  // the store that last read the other buffer has drained
+                prefetch_resid(nt_, ns_, slab_ctr + 1);
+              }
+            }
           }
+          ++slab_ctr;
         }
         __syncwarp();  // reconverge before the next warp-collective tcgen05.ld
       }
@@ -290,7 +323,7 @@ template <int BN, int STAGES>
 static int launch_gemm(const hriemo_gemm_args& a, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
   static_assert(L::DYN_BYTES <= 227 * 1024, "shared memory budget");
-  CUtensorMap tm_a, tm_b, tm_c;
+  CUtensorMap tm_a, tm_b, tm_c, tm_r;
   int rc = make_tmap_bf16_2d(&tm_a, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, BK, BM);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_b, a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldw, BK, BN);
@@ -301,6 +334,11 @@ static int launch_gemm(const hriemo_gemm_args& a, cudaStream_t stream) {
   } else {
     const uint64_t out_cols = a.epilogue == HRIEMO_EPI_QKV ? (uint64_t)a.v_col_begin : (uint64_t)a.N;
     rc = make_tmap_bf16_2d(&tm_c, a.out, out_cols, (uint64_t)a.M, (uint64_t)a.ldo, 64, 32);
+    if (rc) return rc;
+  }
+  tm_r = tm_a;  // only read by the bf16 residual epilogue
+  if (a.epilogue == HRIEMO_EPI_BIAS_RESID) {
+    rc = make_tmap_bf16_2d(&tm_r, a.resid, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldr, 64, 32);
     if (rc) return rc;
   }
 
@@ -323,7 +361,7 @@ static int launch_gemm(const hriemo_gemm_args& a, cudaStream_t stream) {
   }
   const int64_t sms = device_sm_count();
   const unsigned grid = static_cast<unsigned>(p.num_tiles < sms ? p.num_tiles : sms);
-  gemm_bf16_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tm_a, tm_b, tm_c, p);
+  gemm_bf16_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tm_a, tm_b, tm_c, tm_r, p);
   return check_launch("gemm_bf16");
 }
 
