@@ -110,7 +110,8 @@ __device__ __forceinline__ void exp_pack(const uint32_t (&v)[32], float sc, floa
 template <int DH>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                      const __grid_constant__ CUtensorMap tm_v, const Attn3Params p) {
+                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
+                      const Attn3Params p) {
   using L = Attn3Smem<DH>;
   constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t TILE_COLS = 256;   // per query tile: S0 at +0, S1 at +64, O at +128
@@ -145,9 +146,10 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_o);
     for (int s = 0; s < 4; ++s) {
       mbar_init(b_qfull + s * 8, 1);
-      mbar_init(b_qempty + s * 8, 1);
+      mbar_init(b_qempty + s * 8, 4);   // released by the 4 warps of the tile's warpgroup (epilogue staging)
       mbar_init(b_sfull + s * 8, 1);
       mbar_init(b_pvdone + s * 8, 1);
     }
@@ -171,11 +173,12 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     if (lane == 0) {
       uint32_t qcnt[2] = {0, 0};  // Q loads issued per query tile -> buffer and phase
       uint32_t g = 0;             // flat step index -> K/V ring stage and phase
-      for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int qp = static_cast<int>(item % p.n_qp);
-        const int64_t bh = item / p.n_qp;
-        const int h = static_cast<int>(bh % p.H);
-        const int b = static_cast<int>(bh / p.H);
+      const uint32_t n_items_u = static_cast<uint32_t>(p.n_items);
+      for (uint32_t item = blockIdx.x; item < n_items_u; item += gridDim.x) {
+        const uint32_t bh = item / static_cast<uint32_t>(p.n_qp);
+        const int qp = static_cast<int>(item - bh * static_cast<uint32_t>(p.n_qp));
+        const int b = static_cast<int>(bh / static_cast<uint32_t>(p.H));
+        const int h = static_cast<int>(bh - static_cast<uint32_t>(b) * static_cast<uint32_t>(p.H));
         const int q0 = qp * 2 * A3_BQ;
         for (int t = 0; t < 2; ++t) {
           if (q0 + t * A3_BQ >= p.Tq) break;
@@ -241,10 +244,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           }
           umma_commit(b_sfull + (t * 2 + (s_g & 1u)) * 8);
           umma_commit(b_kempty + ks * 8);
-          if (s_j == n_kv - 1) {
-            umma_commit(b_qempty + qslot * 8);
-            ++qcnt;
-          }
+          if (s_j == n_kv - 1) ++qcnt;  // the Q buffer is released by the warpgroup after its epilogue
         } else {
           mbar_arrive(b_kempty + ks * 8);
         }
@@ -315,14 +315,16 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         ++pv_seen;
       }
     };
-    int64_t g = 0;               // flat step index of this CTA
+    uint32_t g = 0;              // flat step index of this CTA
+    uint32_t qcnt_w = 0;         // items this tile has processed -> which Q buffer it used
     int cur_b = -1;
+    const uint32_t n_items_u = static_cast<uint32_t>(p.n_items);
 
-    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, g += n_kv) {
-      const int qp = static_cast<int>(item % p.n_qp);
-      const int64_t bh = item / p.n_qp;
-      const int h = static_cast<int>(bh % p.H);
-      const int b = static_cast<int>(bh / p.H);
+    for (uint32_t item = blockIdx.x; item < n_items_u; item += gridDim.x, g += n_kv) {
+      const uint32_t bh = item / static_cast<uint32_t>(p.n_qp);
+      const int qp = static_cast<int>(item - bh * static_cast<uint32_t>(p.n_qp));
+      const int b = static_cast<int>(bh / static_cast<uint32_t>(p.H));
+      const int h = static_cast<int>(bh - static_cast<uint32_t>(b) * static_cast<uint32_t>(p.H));
       const int q0 = qp * 2 * A3_BQ + wg * A3_BQ;
       if (q0 >= p.Tq) continue;  // this warpgroup's tile does not exist for this item
 
@@ -408,32 +410,41 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         ++pv_issued;
       }
 
-      // ---- epilogue: O / l -> bf16 rows of the [B*Tq, H*dh] output
+      // ---- epilogue: O / l -> bf16, staged in this item's (now dead) Q buffer and written with one
+      // TMA store per warp; the 3-D tensor map (column, t, utterance) clips rows t >= Tq.
       consume_pv(pv_issued);
       tc_fence_after_sync();
       const float inv_l = 1.0f / l_run;  // l == 0 (every key masked) -> inf -> NaN like torch.softmax
-      const bool row_ok = q0 + r < p.Tq;
-      __nv_bfloat16* orow = p.out + (static_cast<int64_t>(b) * p.Tq + q0 + r) * p.ldo + h * DH;
+      const uint32_t qslot = wg * 2 + (qcnt_w & 1u);
+      const uint32_t stage_warp = sQ + qslot * L::Q_TILE + static_cast<uint32_t>(quad) * (32 * DH * 2);
+      const uint32_t stage_row = stage_warp + static_cast<uint32_t>(lane) * (DH * 2);
 #pragma unroll 1
       for (int c = 0; c < DH / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(t_o + c * 32, v);
         tmem_ld_wait();
-        if (row_ok) {
-          uint4* d4 = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
-          for (int g4 = 0; g4 < 4; ++g4) {
-            uint4 w;
-            w.x = pack_bf16(__uint_as_float(v[g4 * 8 + 0]) * inv_l, __uint_as_float(v[g4 * 8 + 1]) * inv_l);
-            w.y = pack_bf16(__uint_as_float(v[g4 * 8 + 2]) * inv_l, __uint_as_float(v[g4 * 8 + 3]) * inv_l);
-            w.z = pack_bf16(__uint_as_float(v[g4 * 8 + 4]) * inv_l, __uint_as_float(v[g4 * 8 + 5]) * inv_l);
-            w.w = pack_bf16(__uint_as_float(v[g4 * 8 + 6]) * inv_l, __uint_as_float(v[g4 * 8 + 7]) * inv_l);
-            d4[g4] = w;
-          }
+        for (int g4 = 0; g4 < 4; ++g4) {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + c * 64 + g4 * 16),
+                       "r"(pack_bf16(__uint_as_float(v[g4 * 8 + 0]) * inv_l, __uint_as_float(v[g4 * 8 + 1]) * inv_l)),
+                       "r"(pack_bf16(__uint_as_float(v[g4 * 8 + 2]) * inv_l, __uint_as_float(v[g4 * 8 + 3]) * inv_l)),
+                       "r"(pack_bf16(__uint_as_float(v[g4 * 8 + 4]) * inv_l, __uint_as_float(v[g4 * 8 + 5]) * inv_l)),
+                       "r"(pack_bf16(__uint_as_float(v[g4 * 8 + 6]) * inv_l, __uint_as_float(v[g4 * 8 + 7]) * inv_l))
+                       : "memory");
         }
-        __syncwarp();
       }
-      tc_fence_before_sync();  // O reads retire before the next item's first p_full lets PV overwrite O
+      tc_fence_before_sync();   // O reads retire before the next item's first p_full lets PV overwrite O
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (q0 + quad * 32 < p.Tq) {
+          tma_store_3d(&tm_o, stage_warp, h * DH, q0 + quad * 32, b);
+          bulk_commit();
+          bulk_wait_read<0>();  // staging bytes have been read: the Q buffer may be refilled
+        }
+        mbar_arrive(b_qempty + qslot * 8);
+      }
+      ++qcnt_w;
     }
   }
 
@@ -461,6 +472,14 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tv, a.vt, (uint64_t)a.Tk, (uint64_t)a.B * d, (uint64_t)a.Tk_pad, 64, DH);
   if (rc) return rc;
+  CUtensorMap to;
+  {
+    const uint64_t dims[3] = {(uint64_t)d, (uint64_t)a.Tq, (uint64_t)a.B};
+    const uint64_t pitch[2] = {(uint64_t)a.ldo, (uint64_t)a.ldo * a.Tq};
+    const uint32_t box[3] = {(uint32_t)DH, 32u, 1u};
+    rc = make_tmap_bf16_3d_plain(&to, a.out, dims, pitch, box);
+    if (rc) return rc;
+  }
   Attn3Params p;
   p.key_pad = a.key_pad;
   p.out = static_cast<__nv_bfloat16*>(a.out);
@@ -482,7 +501,7 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
   }
   const int64_t sms = device_sm_count();
   const unsigned grid = static_cast<unsigned>(p.n_items < sms ? p.n_items : sms);
-  attention_fwd3_kernel<DH><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, p);
+  attention_fwd3_kernel<DH><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);
   return check_launch("attention_bf16");
 }
 

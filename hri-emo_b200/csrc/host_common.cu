@@ -67,6 +67,23 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
   return HRIEMO_OK;
 }
 
+int make_tmap_bf16_3d_plain(CUtensorMap* map, const void* base, const uint64_t dims[3],
+                            const uint64_t pitch_elems[2], const uint32_t box[3]) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(HRIEMO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) || (pitch_elems[0] * 2) % 16 || (pitch_elems[1] * 2) % 16)
+    return set_error(HRIEMO_ERR_INVALID, "TMA operand needs 16-byte aligned base and pitches");
+  cuuint64_t d[3] = {dims[0], dims[1], dims[2]};
+  cuuint64_t strides[2] = {pitch_elems[0] * 2, pitch_elems[1] * 2};
+  cuuint32_t b[3] = {box[0], box[1], box[2]};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), d, strides, b, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(HRIEMO_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r);
+  return HRIEMO_OK;
+}
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {

@@ -19,6 +19,10 @@ int check_launch(const char* what);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
                       uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer);
 
+// 3-D bf16 tensor map without swizzle: dims {d0 (contiguous), d1, d2}, pitches in elements for d1, d2.
+int make_tmap_bf16_3d_plain(CUtensorMap* map, const void* base, const uint64_t dims[3],
+                            const uint64_t pitch_elems[2], const uint32_t box[3]);
+
 int device_sm_count();
 
 #define HRIEMO_REQUIRE(cond, ...)                                      \
