@@ -1,0 +1,60 @@
+"""Host-side logic of the N > 1 path on CPU: contiguous batch sharding and the single
+all_gather of logits + beta, exercised with world_size 2 over gloo."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_shard_bounds_cover_the_batch_exactly():
+    from hriemo.pipeline import shard_bounds
+
+    for B in (0, 1, 7, 8, 4096, 4099):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_bounds(B, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))   # contiguous, no overlap
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1                                     # balanced
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, B, n_e, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hriemo.pipeline import gather_outputs, shard_bounds
+
+        g = torch.Generator().manual_seed(123)               # every rank builds the same "global" result
+        logits_all = torch.randn(B, n_e, generator=g)
+        beta_all = torch.rand(B, 1, generator=g)
+        lo, hi = shard_bounds(B, rank, world)
+        logits, beta = gather_outputs(logits_all[lo:hi].clone(), beta_all[lo:hi].clone())
+        ok = torch.equal(logits, logits_all) and torch.equal(beta, beta_all)
+        out_q.put((rank, bool(ok), tuple(logits.shape), tuple(beta.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gather_outputs_world_size_2_gloo():
+    world, B, n_e = 2, 12, 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, B, n_e, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert res == [(0, True, (B, n_e), (B, 1)), (1, True, (B, n_e), (B, 1))]
