@@ -3,12 +3,14 @@
 //
 // Persistent kernel, one CTA per SM, walking a flat sequence of steps
 // (work item = (utterance, head, pair of 128-row query tiles)) x (64-key step).  352 threads:
-//   warp 0       TMA producer: Q tiles (double-buffered per query tile), K / V^T tiles of 64 keys
+//   warp 0       TMA producer: Q tiles (double-buffered per query tile), K / V tiles of 64 keys
 //                in a ring; it runs ahead across work items.
 //   warps 1, 10  tcgen05.mma issuers, one per query tile, so the two tiles never wait on each other.
 //                S_t = Q_t K^T is DOUBLE-BUFFERED in tensor memory and issued two steps ahead of
 //                the softmax (also across work-item boundaries); O_t += P_t V reads P_t from tensor
-//                memory (P aliases the S buffer it was computed from) and V^T from shared memory.
+//                memory (P aliases the S buffer it was computed from) and V from shared memory as an
+//                MN-major operand (row-major [key][column] tiles exactly as the projection GEMM wrote
+//                them: no transposed copy of V exists anywhere).
 //   warps 2..5   softmax warpgroup of query tile 0 \ one query row per thread (TMEM lane = row):
 //   warps 6..9   softmax warpgroup of query tile 1 / 64 scores held in registers, row max, lazy
 //                running max (O / l rescaled only when it grows by more than 2^8),
@@ -27,8 +29,6 @@
 
 namespace hriemo {
 
-int attention_v1_dispatch(const hriemo_attn_args* a, cudaStream_t s);  // attention_v1.cu (A/B only)
-
 constexpr int A3_BQ = 128;   // query rows per tile (UMMA M)
 constexpr int A3_BKV = 64;   // keys per step (UMMA N of S, K extent of PV)
 constexpr int A3_THREADS = 352;  // TMA, MMA(tile 0), 2 x 4 softmax warps, MMA(tile 1)
@@ -41,7 +41,8 @@ struct Attn3Smem {
   static constexpr int Q_TILE = QCH * Q_CHUNK;
   static constexpr int K_CHUNK = A3_BKV * 128;     // [64 keys][128 B]
   static constexpr int K_STAGE = QCH * K_CHUNK;
-  static constexpr int V_STAGE = DH * 128;         // [DH rows][64 keys]
+  static constexpr int V_GROUP = A3_BKV * 64;      // [64 keys][32 columns = 64 B], 64B-swizzled
+  static constexpr int V_STAGE = (DH / 32) * V_GROUP;
   static constexpr int KV_STAGES = (DH > 96) ? 2 : 3;
   static constexpr int Q_OFF = 0;                  // [tile 2][buffer 2]
   static constexpr int K_OFF = Q_OFF + 4 * Q_TILE;
@@ -200,7 +201,9 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                         b * p.Tk + j * A3_BKV);
           mbar_wait(b_vempty + s * 8, par ^ 1);
           mbar_arrive_expect_tx(b_vfull + s * 8, L::V_STAGE);
-          tma_load_2d(&tm_v, b_vfull + s * 8, sV + s * L::V_STAGE, j * A3_BKV, (b * p.H + h) * DH);
+          for (int c = 0; c < DH / 32; ++c)
+            tma_load_3d(&tm_v, b_vfull + s * 8, sV + s * L::V_STAGE + c * L::V_GROUP, h * DH + c * 32,
+                        j * A3_BKV, b);
         }
       }
     }
@@ -213,13 +216,13 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     if (lane == 0) {
       const int t = (warp == 1) ? 0 : 1;
       constexpr uint32_t idesc_s = umma_idesc_bf16(A3_BQ, A3_BKV);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(A3_BQ, DH);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(A3_BQ, DH) | kUmmaBMajorMN;
       const uint32_t n_items = static_cast<uint32_t>(p.n_items);
       const uint32_t my_items = (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x;
       const uint32_t total = my_items * static_cast<uint32_t>(n_kv);  // flat steps of this CTA
       const uint32_t tile_tmem = tmem_base + t * TILE_COLS;
       const uint64_t k_desc0 = umma_desc_sw128(sK);
-      const uint64_t v_desc0 = umma_desc_sw128(sV);
+      const uint64_t v_desc0 = umma_desc_mn_sw64(sV, L::V_GROUP);
       auto tile_active = [&](uint32_t item) {
         return t == 0 || static_cast<int>(item % static_cast<uint32_t>(p.n_qp)) * 2 * A3_BQ + A3_BQ < p.Tq;
       };
@@ -274,8 +277,8 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           const uint32_t p_tmem = tile_tmem + (g & 1u) * A3_BKV;
 #pragma unroll
           for (int st = 0; st < A3_BKV / 16; ++st) {
-            if (st * 16 < rem)  // P is zero and V^T zero-filled beyond Tk: skip those K-steps
-              umma_bf16_ts(tile_tmem + O_COL, p_tmem + st * 8, v_desc + ((st * 32) >> 4), idesc_pv,
+            if (st * 16 < rem)  // P is zero beyond Tk: skip those K-steps (16 keys = 16 rows of 64 B)
+              umma_bf16_ts(tile_tmem + O_COL, p_tmem + st * 8, v_desc + ((st * 16 * 64) >> 4), idesc_pv,
                            (pv_j | st) != 0);
           }
           umma_commit(b_pvdone + slot * 8);
@@ -295,8 +298,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     // ===================== softmax warpgroups =====================
     const int wg = (warp - 2) >> 2;          // query tile handled by this warpgroup
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
-    const int r = quad * 32 + lane;          // query row inside the tile == TMEM lane
-    const int wg_tid = threadIdx.x - 64 - wg * 128;
+      const int wg_tid = threadIdx.x - 64 - wg * 128;
     float* caps = reinterpret_cast<float*>(base_ptr + L::DYN_OFF) + wg * n_kv * A3_BKV;
     int* flags = reinterpret_cast<int*>(base_ptr + L::DYN_OFF + 2 * n_kv * A3_BKV * 4) + wg * n_kv;
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
@@ -470,8 +472,16 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tk, a.k, (uint64_t)d, (uint64_t)a.B * a.Tk, (uint64_t)a.ldk, 64, A3_BKV);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tv, a.vt, (uint64_t)a.Tk, (uint64_t)a.B * d, (uint64_t)a.Tk_pad, 64, DH);
-  if (rc) return rc;
+  {
+    // 3-D (column, key, utterance): keys past Tk in an utterance's last tile read as ZERO instead of
+    // the next utterance's rows -- P is 0 there, but 0 x NaN from a neighbouring (e.g. fully padded)
+    // utterance would poison this one.
+    const uint64_t dims[3] = {(uint64_t)d, (uint64_t)a.Tk, (uint64_t)a.B};
+    const uint64_t pitch[2] = {(uint64_t)a.ldv, (uint64_t)a.ldv * a.Tk};
+    const uint32_t box[3] = {32u, (uint32_t)A3_BKV, 1u};
+    rc = make_tmap_bf16_3d_plain(&tv, a.v, dims, pitch, box, 64);
+    if (rc) return rc;
+  }
   CUtensorMap to;
   {
     const uint64_t dims[3] = {(uint64_t)d, (uint64_t)a.Tq, (uint64_t)a.B};
@@ -509,19 +519,16 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
 
 extern "C" int hriemo_attention_bf16(const hriemo_attn_args* a, void* stream) {
   using namespace hriemo;
-  HRIEMO_REQUIRE(a != nullptr && a->q && a->k && a->vt && a->out, "attention: null operand");
+  HRIEMO_REQUIRE(a != nullptr && a->q && a->k && a->v && a->out, "attention: null operand");
   HRIEMO_REQUIRE(a->B > 0 && a->H > 0 && a->Tq > 0 && a->Tk > 0, "attention: bad shape");
   HRIEMO_REQUIRE(a->B <= 65535 && a->H <= 65535, "attention: B and H must fit a grid dimension");
-  HRIEMO_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldo % 8 == 0 && a->Tk_pad % 8 == 0 &&
-                     a->Tk_pad >= a->Tk,
+  HRIEMO_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0,
                  "attention: leading dimensions must be multiples of 8");
   HRIEMO_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15u) == 0, "attention: out misaligned");
   HRIEMO_REQUIRE(a->scale > 0.0f, "attention: scale must be positive");
   HRIEMO_REQUIRE(a->dh == 32 || a->dh == 64 || a->dh == 96 || a->dh == 128,
                  "attention: head dim %d not in {32,64,96,128}", a->dh);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static const bool use_v1 = getenv("HRIEMO_ATTN_V1") != nullptr;  // A/B switch while v3 is validated
-  if (use_v1) return attention_v1_dispatch(a, s);
   switch (a->dh) {
     case 32: return launch_attention3<32>(*a, s);
     case 64: return launch_attention3<64>(*a, s);

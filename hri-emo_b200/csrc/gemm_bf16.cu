@@ -2,25 +2,33 @@
 //   out = epilogue(A[M,K] . W[N,K]^T + bias)
 // TMA (128B-swizzled tiles) -> shared-memory ring -> tcgen05.mma (fp32 accumulators
 // in TMEM, double-buffered) -> epilogue warps (tcgen05.ld, bias/ReLU/residual,
-// bf16 tiles staged in swizzled smem + TMA store, fp32 direct stores, optional per-utterance
-// V^T scatter).
+// bf16 tiles staged in swizzled shared memory + TMA store, fp32 direct stores).
 //
 // Replaces the nn.Linear / MHA projection calls of the reference forward
 // (models/cross_modal_block_tacfn.py:24-52,74-119; models/emotion_decoder.py:14-27;
 //  models/mosei_fusion_with_emotion_decoder.py:41-42).
 //
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4..7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31, one
-// accumulator row per thread).
+// Roles (128 + 32*EW threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4..4+EW-1 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31, one accumulator
+// row per thread; with EW = 8 two warps share a lane quadrant and split the tile's columns).
+//
+// CTAS = 2 is the CTA-pair form (cluster of two SMs, tcgen05 cta_group::2): the pair owns a
+// 256 x BN output tile; each CTA loads its 128 rows of A and its BN/2 rows of W, the leader's
+// single thread issues M=256 MMAs that read both CTAs' shared memory, and each CTA's tensor
+// memory receives (and its epilogue warps drain) its own 128 rows.  Per SM this halves the
+// W bytes that TMA writes into and the tensor core reads out of shared memory per FLOP, which is
+// what bounds the one-CTA form (24 KB of smem traffic per 128-cycle K16 step).
 #include "host_common.h"
 #include "sm100_ptx.cuh"
+
+#include <cstdlib>
 
 namespace hriemo {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int GEMM_THREADS = 256;
+constexpr int gemm_threads(int epi_warps) { return 128 + 32 * epi_warps; }
 constexpr int OUT_BOX_BYTES = 32 * 128;  // one epilogue warp's staging box: 32 rows x 64 bf16
 
 struct GemmKernelParams {
@@ -32,21 +40,19 @@ struct GemmKernelParams {
   int64_t ldo;
   const void* resid;
   int64_t ldr;
-  __nv_bfloat16* vt;
-  int T, T_pad, v_col_begin;
   int num_n_blocks, num_k_blocks;
   int64_t num_tiles;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CTAS, int EW>
 struct GemmSmem {
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int B_STAGE_BYTES = (BN / CTAS) * BK * 2;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
-  static constexpr int OUT_OFF = B_OFF + STAGES * B_STAGE_BYTES;   // 4 warps x 2 boxes of [32][64] bf16
-  static constexpr int BAR_OFF = OUT_OFF + 8 * OUT_BOX_BYTES;
-  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], resid_full[4 warps][2], tmem_ptr
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4 + 8) * 8 + 16;
+  static constexpr int OUT_OFF = B_OFF + STAGES * B_STAGE_BYTES;   // EW warps x 2 boxes of [32][64] bf16
+  static constexpr int BAR_OFF = OUT_OFF + 2 * EW * OUT_BOX_BYTES;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], resid_full[EW warps][2], tmem_ptr
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4 + 2 * EW) * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
 };
 
@@ -63,14 +69,22 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&
   }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int STAGES, int CTAS, int EW>
+__global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_r,
                  const GemmKernelParams p) {
-  using L = GemmSmem<BN, STAGES>;
+  using L = GemmSmem<BN, STAGES, CTAS, EW>;
+  static_assert(EW == 4 || EW == 8, "one or two epilogue warps per TMEM lane quadrant");
+  constexpr int SLABS = (BN / 64) / (EW / 4);  // 64-column slabs each epilogue warp drains per tile
   constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages (power of two: 256 or 512)
-  constexpr uint32_t STAGE_TX = A_STAGE_BYTES + L::B_STAGE_BYTES;
+  constexpr uint32_t STAGE_TX = (A_STAGE_BYTES + L::B_STAGE_BYTES) * CTAS;  // both CTAs' loads land on the leader's barrier
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  // tiles are owned by a CTA (CTAS = 1) or a CTA pair (CTAS = 2) and are BM*CTAS rows tall
+  const int64_t tile_first = blockIdx.x / CTAS;
+  const int64_t tile_step = gridDim.x / CTAS;
+  constexpr int TILE_M = BM * CTAS;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -82,7 +96,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t bar_tfull = bar_empty + STAGES * 8;
   const uint32_t bar_tempty = bar_tfull + 2 * 8;
   const uint32_t bar_resid = bar_tempty + 2 * 8;
-  const uint32_t tmem_slot = bar_resid + 8 * 8;
+  const uint32_t tmem_slot = bar_resid + 2 * EW * 8;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -102,14 +116,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + s * 8, 1);
-      mbar_init(bar_tempty + s * 8, 4);  // one arrive per epilogue warp
+      mbar_init(bar_tempty + s * 8, EW * CTAS);  // one arrive per epilogue warp (of both CTAs: the leader waits)
     }
-    for (int s = 0; s < 8; ++s) mbar_init(bar_resid + s * 8, 1);
+    for (int s = 0; s < 2 * EW; ++s) mbar_init(bar_resid + s * 8, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (CTAS == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+    else tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -117,25 +135,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m0 = static_cast<int>(tile / p.num_n_blocks) * BM;
-        const int n0 = static_cast<int>(tile % p.num_n_blocks) * BN;
+      for (int64_t tile = tile_first; tile < p.num_tiles; tile += tile_step) {
+        const int m0 = static_cast<int>(tile / p.num_n_blocks) * TILE_M + static_cast<int>(rank) * BM;
+        const int n0 = static_cast<int>(tile % p.num_n_blocks) * BN + static_cast<int>(rank) * (BN / CTAS);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(bar_empty + stage * 8, phase ^ 1);
-          mbar_arrive_expect_tx(bar_full + stage * 8, STAGE_TX);
-          tma_load_2d(&tm_a, bar_full + stage * 8, sA + stage * A_STAGE_BYTES, kb * BK, m0);
-          tma_load_2d(&tm_b, bar_full + stage * 8, sB + stage * L::B_STAGE_BYTES, kb * BK, n0);
+          mbar_wait(bar_empty + stage * 8, phase ^ 1);  // this CTA's slot is free
+          if constexpr (CTAS == 2) {
+            if (leader) mbar_arrive_expect_tx(bar_full + stage * 8, STAGE_TX);
+            tma_load_2d_pair(&tm_a, bar_full + stage * 8, sA + stage * A_STAGE_BYTES, kb * BK, m0);
+            tma_load_2d_pair(&tm_b, bar_full + stage * 8, sB + stage * L::B_STAGE_BYTES, kb * BK, n0);
+          } else {
+            mbar_arrive_expect_tx(bar_full + stage * 8, STAGE_TX);
+            tma_load_2d(&tm_a, bar_full + stage * 8, sA + stage * A_STAGE_BYTES, kb * BK, m0);
+            tma_load_2d(&tm_b, bar_full + stage * 8, sB + stage * L::B_STAGE_BYTES, kb * BK, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
       uint32_t stage = 0, phase = 0;
       uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int64_t tile = tile_first; tile < p.num_tiles; tile += tile_step, ++it) {
         const uint32_t as = it & 1u;
         const uint32_t aphase = (it >> 1) & 1u;
         mbar_wait(bar_tempty + as * 8, aphase ^ 1);  // epilogue drained this accumulator
@@ -149,55 +173,64 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 bytes (= 16 bf16) along K inside the swizzle atom: +2 in addr>>4 units
-            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (CTAS == 2) umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(bar_empty + stage * 8);  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if constexpr (CTAS == 2) umma_commit_pair(bar_empty + stage * 8, 3);
+          else umma_commit(bar_empty + stage * 8);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(bar_tfull + as * 8);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if constexpr (CTAS == 2) umma_commit_pair(bar_tfull + as * 8, 3);
+        else umma_commit(bar_tfull + as * 8);
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    // Each warp owns 32 accumulator rows (TMEM lanes 32*quad..+31), one row per thread, and
-    // drains them in 64-column slabs.  bf16 outputs are staged in a private, 128B-swizzled
-    // [32 rows][64 cols] shared-memory box (double-buffered) and written with a TMA store, so
-    // HBM/L2 see full 128-byte lines; the four warps never synchronise with each other.
+    // Warp w may read TMEM lanes 32*(w%4)..+31: the EW warps split the tile into (lane quadrant,
+    // column range) blocks -- 32 accumulator rows x SLABS 64-column slabs each, one row per thread.
+    // bf16 outputs are staged in a private, double-buffered, 128B-swizzled [32 rows][64 cols]
+    // shared-memory box and written with a TMA store, so HBM/L2 see full lines and the warps
+    // never synchronise with each other.
+    const int ew = warp - 4;
     const int quad = warp & 3;
+    const int slab0 = (ew >> 2) * SLABS;
     const int row_in_tile = quad * 32 + lane;
-    const uint32_t my_stage = sOut + static_cast<uint32_t>(quad) * (2 * OUT_BOX_BYTES);
+    const uint32_t my_stage = sOut + static_cast<uint32_t>(ew) * (2 * OUT_BOX_BYTES);
     const bool bf16_out = p.epilogue != HRIEMO_EPI_BIAS_RESID_F32 && p.epilogue != HRIEMO_EPI_BIAS_F32;
     // bf16 residual (pre-LayerNorm epilogue): the [32 x 64] residual box of the NEXT slab is
     // prefetched by TMA into the idle staging buffer and the sum is formed in place.
     const bool tma_resid = p.epilogue == HRIEMO_EPI_BIAS_RESID;
-    const uint32_t my_rbar = bar_resid + static_cast<uint32_t>(quad) * 16;
+    const uint32_t my_rbar = bar_resid + static_cast<uint32_t>(ew) * 16;
     auto prefetch_resid = [&](int64_t tile_, int slab_, uint32_t ctr_) {
       const int n_ = static_cast<int>(tile_ % p.num_n_blocks) * BN + slab_ * 64;
-      const int m_ = static_cast<int>((tile_ / p.num_n_blocks) * BM) + quad * 32;
+      const int m_ = static_cast<int>((tile_ / p.num_n_blocks) * TILE_M) + static_cast<int>(rank) * BM + quad * 32;
       const uint32_t b_ = ctr_ & 1u;
       mbar_arrive_expect_tx(my_rbar + b_ * 8, OUT_BOX_BYTES);
       tma_load_2d(&tm_r, my_rbar + b_ * 8, my_stage + b_ * OUT_BOX_BYTES, n_, m_);
     };
+    // first slab this warp owns in a tile (none when the tile's columns end before its range)
+    auto has_slab = [&](int64_t tile_, int slab_) {
+      return static_cast<int>(tile_ % p.num_n_blocks) * BN + slab_ * 64 < p.N;
+    };
     uint32_t it = 0, slab_ctr = 0;
-    if (tma_resid && lane == 0 && blockIdx.x < p.num_tiles) prefetch_resid(blockIdx.x, 0, 0);
-    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const uint32_t tempty_leader = CTAS == 2 ? mapa_shared(bar_tempty, 0) : bar_tempty;
+    if (tma_resid && lane == 0 && tile_first < p.num_tiles && has_slab(tile_first, slab0))
+      prefetch_resid(tile_first, slab0, 0);
+    for (int64_t tile = tile_first; tile < p.num_tiles; tile += tile_step, ++it) {
       const uint32_t as = it & 1u;
       const uint32_t aphase = (it >> 1) & 1u;
-      const int64_t m_tile = (tile / p.num_n_blocks) * BM;
+      const int64_t m_tile = (tile / p.num_n_blocks) * TILE_M + static_cast<int64_t>(rank) * BM;
       const int64_t m = m_tile + row_in_tile;
       const int n0 = static_cast<int>(tile % p.num_n_blocks) * BN;
       const bool row_ok = m < p.M;
-      int64_t vt_row_base = 0;  // (b * dv) * T_pad + t
-      if (p.epilogue == HRIEMO_EPI_QKV && row_ok) {
-        const int64_t b = m / p.T;
-        const int t = static_cast<int>(m - b * p.T);
-        vt_row_base = b * static_cast<int64_t>(p.N - p.v_col_begin) * p.T_pad + t;
-      }
       mbar_wait(bar_tfull + as * 8, aphase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int s = 0; s < BN / 64; ++s) {
+      for (int sl = 0; sl < SLABS; ++sl) {
+        const int s = slab0 + sl;
         const int n = n0 + s * 64;
         if (n >= p.N) break;                   // warp-uniform
         const bool two = n + 32 < p.N;         // N is a multiple of 32
@@ -205,10 +238,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         tmem_ld32(t_row + s * 64, v[0]);
         if (two) tmem_ld32(t_row + s * 64 + 32, v[1]);
         tmem_ld_wait();
-        const bool to_vt = p.epilogue == HRIEMO_EPI_QKV && n >= p.v_col_begin;
-        const bool staged = bf16_out && !to_vt;
         uint32_t buf = 0;
-        if (staged) {
+        if (bf16_out) {
           buf = my_stage + (slab_ctr & 1u) * OUT_BOX_BYTES;
           if (tma_resid) {
             mbar_wait(my_rbar + (slab_ctr & 1u) * 8, (slab_ctr >> 1) & 1u);  // residual box has landed
@@ -258,7 +289,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               f[i * 4 + 0] += r4.x; f[i * 4 + 1] += r4.y; f[i * 4 + 2] += r4.z; f[i * 4 + 3] += r4.w;
             }
           }
-          if (staged) {
+          if (bf16_out) {
             // swizzled 16-byte chunks: chunk j of row r lives at slot j ^ (r & 7)
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -268,13 +299,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                            "r"(pack_bf16(f[g * 8 + 4], f[g * 8 + 5])), "r"(pack_bf16(f[g * 8 + 6], f[g * 8 + 7]))
                            : "memory");
             }
-          } else if (to_vt) {
-            if (row_ok) {
-              // V^T scatter: consecutive lanes hold consecutive t -> coalesced 2-byte stores
-              __nv_bfloat16* vp = p.vt + vt_row_base + static_cast<int64_t>(nn - p.v_col_begin) * p.T_pad;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) vp[static_cast<int64_t>(i) * p.T_pad] = __float2bfloat16_rn(f[i]);
-            }
           } else if (row_ok) {  // fp32 outputs (decoder stream): direct 16-byte stores
             float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + m * p.ldo + nn);
 #pragma unroll
@@ -282,18 +306,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               op[i] = make_float4(f[i * 4 + 0], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
           }
         }
-        if (staged) {
+        if (bf16_out) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tm_c, buf, n, static_cast<int>(m_tile) + quad * 32);
             bulk_commit();
             if (tma_resid) {
-              // next slab of this warp: same tile, or slab 0 of this CTA's next tile
+              // next slab of this warp: same tile, or its first slab of this CTA's next tile
               int64_t nt_ = tile;
               int ns_ = s + 1;
-              if (ns_ >= BN / 64 || n0 + ns_ * 64 >= p.N) { nt_ = tile + gridDim.x; ns_ = 0; }
-              if (nt_ < p.num_tiles) {
+              if (sl + 1 >= SLABS || n0 + ns_ * 64 >= p.N) { nt_ = tile + tile_step; ns_ = slab0; }
+              if (nt_ < p.num_tiles && has_slab(nt_, ns_)) {
                 bulk_wait_read<1>();  // the store that last read the other buffer has drained
                 prefetch_resid(nt_, ns_, slab_ctr + 1);
               }
@@ -305,35 +329,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + as * 8);
+      if (lane == 0) {
+        if constexpr (CTAS == 2) mbar_arrive_cluster(tempty_leader + as * 8);
+        else mbar_arrive(bar_tempty + as * 8);
+      }
     }
     if (lane == 0) bulk_wait_all();  // staged tiles must be out before shared memory is released
   }
 
   // ===================== teardown =====================
   tc_fence_before_sync();
-  __syncthreads();
+  __syncwarp();  // role branches diverge inside warps 0 and 1; the aligned cluster barrier needs them whole
+  if constexpr (CTAS == 2) cluster_sync_all();  // the peer's barriers and tensor memory stay valid until both are done
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after_sync();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if constexpr (CTAS == 2) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CTAS, int EW>
 static int launch_gemm(const hriemo_gemm_args& a, cudaStream_t stream) {
-  using L = GemmSmem<BN, STAGES>;
+  using L = GemmSmem<BN, STAGES, CTAS, EW>;
   static_assert(L::DYN_BYTES <= 227 * 1024, "shared memory budget");
   CUtensorMap tm_a, tm_b, tm_c, tm_r;
   int rc = make_tmap_bf16_2d(&tm_a, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, BK, BM);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tm_b, a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldw, BK, BN);
+  rc = make_tmap_bf16_2d(&tm_b, a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldw, BK, BN / CTAS);
   if (rc) return rc;
   const bool f32_out = a.epilogue == HRIEMO_EPI_BIAS_RESID_F32 || a.epilogue == HRIEMO_EPI_BIAS_F32;
   if (f32_out) {
     tm_c = tm_a;  // unused by the fp32 epilogues
   } else {
-    const uint64_t out_cols = a.epilogue == HRIEMO_EPI_QKV ? (uint64_t)a.v_col_begin : (uint64_t)a.N;
-    rc = make_tmap_bf16_2d(&tm_c, a.out, out_cols, (uint64_t)a.M, (uint64_t)a.ldo, 64, 32);
+    rc = make_tmap_bf16_2d(&tm_c, a.out, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldo, 64, 32);
     if (rc) return rc;
   }
   tm_r = tm_a;  // only read by the bf16 residual epilogue
@@ -345,23 +374,35 @@ static int launch_gemm(const hriemo_gemm_args& a, cudaStream_t stream) {
   GemmKernelParams p;
   p.M = a.M; p.N = a.N; p.K = a.K; p.epilogue = a.epilogue; p.bias = a.bias;
   p.out = a.out; p.ldo = a.ldo; p.resid = a.resid; p.ldr = a.ldr;
-  p.vt = static_cast<__nv_bfloat16*>(a.vt); p.T = a.T; p.T_pad = a.T_pad; p.v_col_begin = a.v_col_begin;
   p.num_n_blocks = (a.N + BN - 1) / BN;
   p.num_k_blocks = (a.K + BK - 1) / BK;
-  const int64_t num_m_blocks = (a.M + BM - 1) / BM;
+  const int64_t num_m_blocks = (a.M + BM * CTAS - 1) / (BM * CTAS);
   p.num_tiles = num_m_blocks * p.num_n_blocks;
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, CTAS, EW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
     if (e != cudaSuccess)
       return set_error(HRIEMO_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int64_t sms = device_sm_count();
-  const unsigned grid = static_cast<unsigned>(p.num_tiles < sms ? p.num_tiles : sms);
-  gemm_bf16_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tm_a, tm_b, tm_c, tm_r, p);
+  const int64_t owners = device_sm_count() / CTAS;  // CTAs, or CTA pairs
+  const unsigned grid = static_cast<unsigned>(p.num_tiles < owners ? p.num_tiles : owners) * CTAS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(gemm_threads(EW));
+  cfg.dynamicSmemBytes = L::DYN_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, STAGES, CTAS, EW>, tm_a, tm_b, tm_c, tm_r, p);
+  if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "gemm: launch failed: %s", cudaGetErrorString(e));
   return check_launch("gemm_bf16");
 }
 
@@ -378,8 +419,10 @@ extern "C" int hriemo_gemm_bf16(const hriemo_gemm_args* a, void* stream) {
                  "gemm: K=%d, lda=%lld, ldw=%lld must be multiples of 8", a->K, (long long)a->lda,
                  (long long)a->ldw);
   HRIEMO_REQUIRE(a->lda >= a->K && a->ldw >= a->K, "gemm: leading dimension smaller than K");
-  HRIEMO_REQUIRE(a->epilogue >= HRIEMO_EPI_BIAS && a->epilogue <= HRIEMO_EPI_BIAS_F32,
+  HRIEMO_REQUIRE(a->epilogue >= HRIEMO_EPI_BIAS && a->epilogue <= HRIEMO_EPI_BIAS_F32 && a->epilogue != 4,
                  "gemm: unknown epilogue %d", a->epilogue);
+  HRIEMO_REQUIRE(a->cta_pair >= 0 && a->cta_pair <= 2, "gemm: cta_pair=%d (0 auto, 1 single, 2 pair)", a->cta_pair);
+  HRIEMO_REQUIRE(a->cta_pair != 2 || a->N % 256 == 0, "gemm: CTA-pair tiles need N %% 256 == 0 (N=%d)", a->N);
   const bool f32_out = a->epilogue == HRIEMO_EPI_BIAS_RESID_F32 || a->epilogue == HRIEMO_EPI_BIAS_F32;
   HRIEMO_REQUIRE(a->ldo % (f32_out ? 4 : 8) == 0, "gemm: ldo=%lld misaligned", (long long)a->ldo);
   HRIEMO_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15u) == 0, "gemm: out not 16-byte aligned");
@@ -388,17 +431,17 @@ extern "C" int hriemo_gemm_bf16(const hriemo_gemm_args* a, void* stream) {
     HRIEMO_REQUIRE(a->ldr % (f32_out ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(a->resid) & 15u) == 0,
                    "gemm: resid misaligned");
   }
-  if (a->epilogue == HRIEMO_EPI_QKV) {
-    HRIEMO_REQUIRE(a->vt != nullptr && a->T > 0 && a->T_pad >= a->T && a->T_pad % 8 == 0,
-                   "gemm: QKV epilogue needs vt, T, T_pad (multiple of 8)");
-    HRIEMO_REQUIRE(a->v_col_begin > 0 && a->v_col_begin < a->N && a->v_col_begin % 64 == 0,
-                   "gemm: bad v_col_begin %d", a->v_col_begin);
-    HRIEMO_REQUIRE(a->M % a->T == 0, "gemm: M must be B*T in QKV mode");
-  }
   if (a->bias) HRIEMO_REQUIRE((reinterpret_cast<uintptr_t>(a->bias) & 15u) == 0, "gemm: bias misaligned");
   if (a->M == 0) return HRIEMO_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // Wide tiles for wide outputs; 128-column tiles keep more CTAs busy when N is small.
-  if (a->N >= 256 && a->N % 256 == 0) return launch_gemm<256, 4>(*a, s);
-  return launch_gemm<128, 6>(*a, s);
+  if (a->N >= 256 && a->N % 256 == 0) {
+    // CTA pairs once there is at least one 256-row tile per pair (HRIEMO_GEMM_CTAS=1|2 overrides "auto")
+    static const int env_force = [] { const char* e = getenv("HRIEMO_GEMM_CTAS"); return e ? atoi(e) : 0; }();
+    const int force = a->cta_pair ? a->cta_pair : env_force;
+    const int64_t pair_tiles = ((a->M + 255) / 256) * (a->N / 256);
+    if (force != 1 && (force == 2 || pair_tiles >= device_sm_count() / 2)) return launch_gemm<256, 5, 2, 8>(*a, s);
+    return launch_gemm<256, 4, 1, 4>(*a, s);
+  }
+  return launch_gemm<128, 6, 1, 4>(*a, s);
 }

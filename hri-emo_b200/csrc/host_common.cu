@@ -47,7 +47,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
-                      uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer) {
+                      uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(HRIEMO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if ((reinterpret_cast<uintptr_t>(base) & 15u) || (pitch_elems * 2) % 16)
@@ -57,7 +57,8 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(HRIEMO_ERR_CUDA,
@@ -68,7 +69,7 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
 }
 
 int make_tmap_bf16_3d_plain(CUtensorMap* map, const void* base, const uint64_t dims[3],
-                            const uint64_t pitch_elems[2], const uint32_t box[3]) {
+                            const uint64_t pitch_elems[2], const uint32_t box[3], int swizzle_bytes) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(HRIEMO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if ((reinterpret_cast<uintptr_t>(base) & 15u) || (pitch_elems[0] * 2) % 16 || (pitch_elems[1] * 2) % 16)
@@ -78,7 +79,10 @@ int make_tmap_bf16_3d_plain(CUtensorMap* map, const void* base, const uint64_t d
   cuuint32_t b[3] = {box[0], box[1], box[2]};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), d, strides, b, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                      : (swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(HRIEMO_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r);
   return HRIEMO_OK;

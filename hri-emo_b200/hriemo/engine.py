@@ -157,27 +157,27 @@ def self_attention_block(x: Seq, P: dict, ln, mask, n_heads: int, want_attn: boo
     """LN(x + MHA(x, x, x)): models/cross_modal_block_tacfn.py:74-82 / :85-93."""
     d = x.d
     dh = d // n_heads
-    qk, vt = ops.gemm_qkv(x.x, P["w_qkv"], P["b_qkv"], x.T, 2 * d)
-    q, k = qk[:, :d], qk[:, d:]
-    o = ops.attention(q, k, vt, mask, x.B, n_heads, x.T, x.T, dh)
+    qkv = ops.gemm(x.x, P["w_qkv"], P["b_qkv"], L.EPI_BIAS)
+    q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+    o = ops.attention(q, k, v, mask, x.B, n_heads, x.T, x.T, dh)
     pre = ops.gemm(o, P["w_o"], P["b_o"], L.EPI_BIAS_RESID, resid=x.x)
     amap = ops.attention_probs(q, k, mask, x.B, n_heads, x.T, x.T, dh) if want_attn else None
     return residual_ln(pre, ln, x.B, x.T), amap
 
 
 def cross_projection(x: Seq, P: dict):
-    """One GEMM producing this stream's cross-attention query, and the key / V^T it
+    """One GEMM producing this stream's cross-attention query, and the key / value it
     offers to the other stream (SURVEY Appendix C "free algebraic fusions")."""
     d = x.d
-    qk, vt = ops.gemm_qkv(x.x, P["w_qkv"], P["b_qkv"], x.T, 2 * d)
-    return qk[:, :d], qk[:, d:], vt
+    qkv = ops.gemm(x.x, P["w_qkv"], P["b_qkv"], L.EPI_BIAS)
+    return qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
 
 
-def cross_attention_block(xq: Seq, q, k_other, vt_other, T_other: int, mask_other, w_o, b_o, ln,
+def cross_attention_block(xq: Seq, q, k_other, v_other, T_other: int, mask_other, w_o, b_o, ln,
                           n_heads: int, want_attn: bool):
     """LN(x + MHA(x, other, other)): models/cross_modal_block_tacfn.py:98-105 / :111-118."""
     dh = xq.d // n_heads
-    o = ops.attention(q, k_other, vt_other, mask_other, xq.B, n_heads, xq.T, T_other, dh)
+    o = ops.attention(q, k_other, v_other, mask_other, xq.B, n_heads, xq.T, T_other, dh)
     pre = ops.gemm(o, w_o, b_o, L.EPI_BIAS_RESID, resid=xq.x)
     amap = ops.attention_probs(q, k_other, mask_other, xq.B, n_heads, xq.T, T_other, dh) if want_attn else None
     return residual_ln(pre, ln, xq.B, xq.T), amap

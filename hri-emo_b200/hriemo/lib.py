@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhriemo_b200.so")
 
-EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESID, EPI_BIAS_RESID_F32, EPI_QKV, EPI_BIAS_F32 = range(6)
+EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESID, EPI_BIAS_RESID_F32, _EPI_RETIRED, EPI_BIAS_F32 = range(6)
 ACT_NONE, ACT_RELU, ACT_SIGMOID = range(3)
 
 
@@ -25,11 +25,9 @@ class GemmArgs(C.Structure):
         ("W", C.c_void_p), ("ldw", C.c_int64),
         ("bias", C.c_void_p),
         ("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32),
-        ("epilogue", C.c_int32), ("reserved0", C.c_int32),
+        ("epilogue", C.c_int32), ("cta_pair", C.c_int32),
         ("out", C.c_void_p), ("ldo", C.c_int64),
         ("resid", C.c_void_p), ("ldr", C.c_int64),
-        ("vt", C.c_void_p), ("T", C.c_int32), ("T_pad", C.c_int32),
-        ("v_col_begin", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -37,7 +35,7 @@ class AttnArgs(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("ldq", C.c_int64),
         ("k", C.c_void_p), ("ldk", C.c_int64),
-        ("vt", C.c_void_p), ("Tk_pad", C.c_int32), ("reserved0", C.c_int32),
+        ("v", C.c_void_p), ("ldv", C.c_int64),
         ("key_pad", C.c_void_p),
         ("out", C.c_void_p), ("ldo", C.c_int64),
         ("B", C.c_int32), ("H", C.c_int32), ("Tq", C.c_int32), ("Tk", C.c_int32), ("dh", C.c_int32),

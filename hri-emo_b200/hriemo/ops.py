@@ -83,8 +83,10 @@ def cast_bf16(x: torch.Tensor, ld_out: Optional[int] = None) -> torch.Tensor:
 
 # ------------------------------------------------------------------ GEMM
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int = _l.EPI_BIAS,
-         resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out = epilogue(a[M,K] @ w[N,K]^T + bias) on tcgen05 tensor cores."""
+         resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         cta_pair: int = 0) -> torch.Tensor:
+    """out = epilogue(a[M,K] @ w[N,K]^T + bias) on tcgen05 tensor cores.
+    cta_pair: 0 = library picks the tile form, 1 = one-CTA tiles, 2 = CTA-pair (cta_group::2) tiles."""
     _chk2d(a, bf16, "gemm A")
     _chk2d(w, bf16, "gemm W")
     M, K = a.shape
@@ -99,6 +101,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogu
     args.A, args.lda, args.W, args.ldw = a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0)
     args.bias = _ptr(bias)
     args.M, args.N, args.K, args.epilogue = M, N, K, epilogue
+    args.cta_pair = cta_pair
     args.out, args.ldo = out.data_ptr(), out.stride(0)
     if resid is not None:
         _chk2d(resid, f32 if f32_out else bf16, "gemm resid")
@@ -109,43 +112,22 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogu
     return out
 
 
-def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], T: int,
-             v_col_begin: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """[Q|K|V] projection of a [B*T, K] stream.  Returns (qk [B*T, v_col_begin] bf16 row-major,
-    vt [B, N - v_col_begin, T_pad] bf16 = per-utterance V^T, columns t >= T unspecified)."""
-    _chk2d(a, bf16, "gemm_qkv A")
-    _chk2d(w, bf16, "gemm_qkv W")
-    M, K = a.shape
-    N = w.shape[0]
-    B = M // T
-    T_pad = round_up(T, 8)
-    qk = torch.empty((M, v_col_begin), dtype=bf16, device=a.device)
-    vt = torch.empty((B, N - v_col_begin, T_pad), dtype=bf16, device=a.device)
-    args = _l.GemmArgs()
-    args.A, args.lda, args.W, args.ldw = a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0)
-    args.bias = _ptr(bias)
-    args.M, args.N, args.K, args.epilogue = M, N, K, _l.EPI_QKV
-    args.out, args.ldo = qk.data_ptr(), qk.stride(0)
-    args.vt, args.T, args.T_pad, args.v_col_begin = vt.data_ptr(), T, T_pad, v_col_begin
-    tok = _prof_begin("gemm", 2.0 * M * N * K)
-    _l.check(_l.load().hriemo_gemm_bf16(C.byref(args), _stream()), "gemm_bf16[qkv]")
-    _prof_end(tok)
-    return qk, vt
-
-
 # ------------------------------------------------------------------ attention
-def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, key_pad: Optional[torch.Tensor],
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Optional[torch.Tensor],
               B: int, H: int, Tq: int, Tk: int, dh: int) -> torch.Tensor:
-    """q: [B*Tq, >=H*dh] view, k: [B*Tk, >=H*dh] view, vt: [B, H*dh, Tk_pad].  Returns [B*Tq, H*dh] bf16."""
+    """q: [B*Tq, >=H*dh] view, k / v: [B*Tk, >=H*dh] views (column slices of a packed projection are
+    fine).  Returns [B*Tq, H*dh] bf16."""
     _chk2d(q, bf16, "attention q")
     _chk2d(k, bf16, "attention k")
-    if vt.dtype != bf16 or vt.dim() != 3 or not vt.is_contiguous() or vt.shape[0] != B or vt.shape[1] != H * dh:
-        raise _l.HriemoError(f"attention: vt must be contiguous bf16 [B, H*dh, Tk_pad], got {tuple(vt.shape)}")
+    _chk2d(v, bf16, "attention v")
+    if q.shape[0] != B * Tq or k.shape[0] != B * Tk or v.shape[0] != B * Tk:
+        raise _l.HriemoError(f"attention: row counts {q.shape[0]}, {k.shape[0]}, {v.shape[0]} do not match "
+                             f"B*Tq={B * Tq}, B*Tk={B * Tk}")
     out = torch.empty((B * Tq, H * dh), dtype=bf16, device=q.device)
     m = _mask_u8(key_pad, B, Tk, "attention")
     args = _l.AttnArgs()
     args.q, args.ldq, args.k, args.ldk = q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0)
-    args.vt, args.Tk_pad = vt.data_ptr(), vt.shape[2]
+    args.v, args.ldv = v.data_ptr(), v.stride(0)
     args.key_pad = _ptr(m)
     args.out, args.ldo = out.data_ptr(), out.stride(0)
     args.B, args.H, args.Tq, args.Tk, args.dh = B, H, Tq, Tk, dh

@@ -41,12 +41,12 @@ class CrossModalBlock(nn.Module):
         """Reference :56-69 — both directions read the layer inputs."""
         P = self._prep.get()
         H = self.n_heads
-        qa, ka, vta = E.cross_projection(a, P["cross_a"])
-        qt, kt, vtt = E.cross_projection(t, P["cross_t"])
-        a1, _ = E.cross_attention_block(a, qa, kt, vtt, t.T, mask_t, P["a2t_o"]["w"], P["a2t_o"]["b"],
+        qa, ka, va = E.cross_projection(a, P["cross_a"])
+        qt, kt, vt_ = E.cross_projection(t, P["cross_t"])
+        a1, _ = E.cross_attention_block(a, qa, kt, vt_, t.T, mask_t, P["a2t_o"]["w"], P["a2t_o"]["b"],
                                         P["norm_a1"], H, False)
         a_o = E.ffn_block(a1, P["ffn_a1"], P["ffn_a2"], P["norm_a2"], want_f32)
-        t1, _ = E.cross_attention_block(t, qt, ka, vta, a.T, mask_a, P["t2a_o"]["w"], P["t2a_o"]["b"],
+        t1, _ = E.cross_attention_block(t, qt, ka, va, a.T, mask_a, P["t2a_o"]["w"], P["t2a_o"]["b"],
                                         P["norm_t1"], H, False)
         t_o = E.ffn_block(t1, P["ffn_t1"], P["ffn_t2"], P["norm_t2"], want_f32)
         return a_o, t_o

@@ -55,13 +55,13 @@ class CrossModalBlock(nn.Module):
         maps = {}
         a_s, maps["audio_self"] = E.self_attention_block(a, P["self_a"], P["self_norm_a"], mask_a, H, want_attn)
         t_s, maps["text_self"] = E.self_attention_block(t, P["self_t"], P["self_norm_t"], mask_t, H, want_attn)
-        qa, ka, vta = E.cross_projection(a_s, P["cross_a"])  # a2t query | t2a key | t2a V^T
-        qt, kt, vtt = E.cross_projection(t_s, P["cross_t"])  # t2a query | a2t key | a2t V^T
+        qa, ka, va = E.cross_projection(a_s, P["cross_a"])  # a2t query | t2a key | t2a value
+        qt, kt, vt_ = E.cross_projection(t_s, P["cross_t"])  # t2a query | a2t key | a2t value
         a1, maps["audio_queries_text"] = E.cross_attention_block(
-            a_s, qa, kt, vtt, t_s.T, mask_t, P["a2t_o"]["w"], P["a2t_o"]["b"], P["norm_a1"], H, want_attn)
+            a_s, qa, kt, vt_, t_s.T, mask_t, P["a2t_o"]["w"], P["a2t_o"]["b"], P["norm_a1"], H, want_attn)
         a_o = E.ffn_block(a1, P["ffn_a1"], P["ffn_a2"], P["norm_a2"], want_f32)
         t1, maps["text_queries_audio"] = E.cross_attention_block(
-            t_s, qt, ka, vta, a_s.T, mask_a, P["t2a_o"]["w"], P["t2a_o"]["b"], P["norm_t1"], H, want_attn)
+            t_s, qt, ka, va, a_s.T, mask_a, P["t2a_o"]["w"], P["t2a_o"]["b"], P["norm_t1"], H, want_attn)
         t_o = E.ffn_block(t1, P["ffn_t1"], P["ffn_t2"], P["norm_t2"], want_f32)
         return a_o, t_o, (maps if want_attn else None)
 

@@ -66,9 +66,7 @@ enum {
   HRIEMO_EPI_BIAS_RELU = 1,      /* out bf16 = relu(acc + bias)            (FFN first half) */
   HRIEMO_EPI_BIAS_RESID = 2,     /* out bf16 = acc + bias + resid(bf16)    (pre-LayerNorm)  */
   HRIEMO_EPI_BIAS_RESID_F32 = 3, /* out f32  = acc + bias + resid(f32)     (decoder stream) */
-  HRIEMO_EPI_QKV = 4,            /* cols [0,v_col_begin) -> out bf16 row-major;
-                                    cols [v_col_begin,N) -> vt[b][c][t] (per-utterance V^T) */
-  HRIEMO_EPI_BIAS_F32 = 5        /* out f32  = acc + bias                                   */
+  HRIEMO_EPI_BIAS_F32 = 5        /* out f32  = acc + bias   (4 is retired: a transposed-V epilogue) */
 };
 
 typedef struct hriemo_gemm_args {
@@ -81,18 +79,12 @@ typedef struct hriemo_gemm_args {
   int32_t N;         /* multiple of 32 */
   int32_t K;         /* multiple of 8  */
   int32_t epilogue;  /* HRIEMO_EPI_*   */
-  int32_t reserved0;
+  int32_t cta_pair;  /* 0 = library picks; 1 = one-CTA tiles (128 x BN); 2 = CTA-pair tiles
+                        (256 x 256, tcgen05 cta_group::2; needs N % 256 == 0) */
   void* out;         /* bf16 or f32, see epilogue */
   int64_t ldo;
   const void* resid; /* bf16 or f32 [M,N], RESID modes only */
   int64_t ldr;
-  /* HRIEMO_EPI_QKV only: rows are (b, t) = (m / T, m % T); V^T is
-   * vt[(b * (N - v_col_begin) + c) * T_pad + t] for c = n - v_col_begin. */
-  void* vt;          /* bf16 */
-  int32_t T;
-  int32_t T_pad;     /* multiple of 8, >= T */
-  int32_t v_col_begin;
-  int32_t reserved1;
 } hriemo_gemm_args;
 
 int hriemo_gemm_bf16(const hriemo_gemm_args* args, void* stream);
@@ -104,14 +96,14 @@ int hriemo_gemm_bf16(const hriemo_gemm_args* args, void* stream);
  *   models/cross_modal_block_tacfn.py:74-80, 85-91, 98-104, 111-117 and
  *   models/cross_modal_block.py:56-59, 64-67.
  * Q rows are (b, t_q) with row pitch ldq, head h at columns [h*dh, (h+1)*dh);
- * K likewise over t_k; V is given transposed per utterance as written by
- * HRIEMO_EPI_QKV: vt[(b*d + h*dh + c) * Tk_pad + t_k].
+ * K and V likewise over t_k (row pitches ldk, ldv): all three may be column
+ * slices of one packed [Q|K|V] projection output, exactly PyTorch's layout.
  * A fully masked key row yields NaN, as torch.softmax does in the reference.
  */
 typedef struct hriemo_attn_args {
   const void* q;  int64_t ldq;   /* bf16 */
   const void* k;  int64_t ldk;   /* bf16 */
-  const void* vt; int32_t Tk_pad; int32_t reserved0;
+  const void* v;  int64_t ldv;   /* bf16 */
   const uint8_t* key_pad;        /* [B, Tk] 1 = PAD, or NULL */
   void* out;      int64_t ldo;   /* bf16 [B*Tq, H*dh] */
   int32_t B, H, Tq, Tk, dh;      /* dh in {32, 64, 96, 128} */

@@ -77,8 +77,8 @@ def test_argument_validation_without_gpu(lib):
     rc = lib.hriemo_gemm_bf16(ctypes.byref(a), None)
     assert rc == -1 and b"multiple of 32" in lib.hriemo_last_error()
     t = L.AttnArgs()
-    t.q, t.k, t.vt, t.out = 16, 16, 16, 16
-    t.B, t.H, t.Tq, t.Tk, t.dh, t.ldq, t.ldk, t.ldo, t.Tk_pad = 1, 1, 8, 8, 48, 48, 48, 48, 8
+    t.q, t.k, t.v, t.out = 16, 16, 16, 16
+    t.B, t.H, t.Tq, t.Tk, t.dh, t.ldq, t.ldk, t.ldv, t.ldo = 1, 1, 8, 8, 48, 48, 48, 48, 48
     t.scale = 0.125
     rc = lib.hriemo_attention_bf16(ctypes.byref(t), None)
     assert rc == -1 and b"head dim" in lib.hriemo_last_error()

@@ -60,14 +60,49 @@ def test_gemm_bias(M, N, K):
     w = _rand((N, K), 2, 1.0 / math.sqrt(K), dtype=torch.bfloat16)
     bias = _rand((N,), 3)
     ref = a.float() @ w.float().t() + bias
-    out = ops.gemm(a, w, bias, L.EPI_BIAS)
+    out = ops.gemm(a, w, bias, L.EPI_BIAS, cta_pair=1)
     torch.cuda.synchronize()
     _report(f"gemm bias {M}x{N}x{K}", out, ref, atol=1e-2, rtol=1e-2)  # one bf16 rounding of O(1) values
 
 
-def test_gemm_epilogues():
+# CTA-pair (cta_group::2) tiles: odd numbers of 128-row blocks (the second CTA of the last pair is
+# entirely out of range), single tiles, K tails, many tiles per pair.
+PAIR_SHAPES = [(128, 256, 64), (129, 256, 768), (300, 256, 768), (1000, 768, 3072), (4096, 2304, 768),
+               (1, 256, 8), (64, 512, 80), (20000, 3072, 768), (37889, 768, 768)]
+
+
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
+def test_gemm_bias_cta_pair(M, N, K):
     from hriemo import lib as L, ops
 
+    a = _rand((M, K), 1, dtype=torch.bfloat16)
+    w = _rand((N, K), 2, 1.0 / math.sqrt(K), dtype=torch.bfloat16)
+    bias = _rand((N,), 3)
+    ref = a.float() @ w.float().t() + bias
+    out = ops.gemm(a, w, bias, L.EPI_BIAS, cta_pair=2)
+    torch.cuda.synchronize()
+    _report(f"gemm pair {M}x{N}x{K}", out, ref, atol=1e-2, rtol=1e-2)
+    # same accumulation order per output element -> the two tile forms agree bit for bit
+    assert torch.equal(out, ops.gemm(a, w, bias, L.EPI_BIAS, cta_pair=1))
+
+
+def test_gemm_cta_pair_rejects_narrow_n():
+    from hriemo import lib as L, ops
+
+    a = _rand((256, 64), 1, dtype=torch.bfloat16)
+    w = _rand((384, 64), 2, dtype=torch.bfloat16)
+    with pytest.raises(L.HriemoError):
+        ops.gemm(a, w, None, L.EPI_BIAS, cta_pair=2)
+
+
+@pytest.mark.parametrize("cta_pair", [1, 2])
+def test_gemm_epilogues(cta_pair):
+    from hriemo import lib as L, ops
+    import functools
+
+    class _O:  # ops with the tile form pinned
+        gemm = staticmethod(functools.partial(ops.gemm, cta_pair=cta_pair))
+    ops = _O
     M, N, K = 1500, 768, 768
     a = _rand((M, K), 4, dtype=torch.bfloat16)
     w = _rand((N, K), 5, 1.0 / math.sqrt(K), dtype=torch.bfloat16)
@@ -102,19 +137,24 @@ def test_gemm_strided_views():
     assert outbig[:, :N].abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("B,T,d", [(3, 50, 192), (5, 300, 768), (2, 64, 256), (7, 13, 128)])
-def test_gemm_qkv_layout(B, T, d):
-    from hriemo import ops
+@pytest.mark.parametrize("B,H,T,dh,cta_pair", [(3, 2, 50, 96, 1), (5, 8, 300, 96, 0), (2, 4, 64, 64, 2), (33, 8, 500, 96, 2)])
+def test_packed_qkv_projection_feeds_attention(B, H, T, dh, cta_pair):
+    """The [Q|K|V] projection output is consumed in place: Q, K and V are column slices of one
+    row-major buffer (PyTorch's packed in-projection layout; no transposed copy of V)."""
+    from hriemo import lib as L, ops
 
+    d = H * dh
     a = _rand((B * T, d), 11, dtype=torch.bfloat16)
     w = _rand((3 * d, d), 12, 1.0 / math.sqrt(d), dtype=torch.bfloat16)
     bias = _rand((3 * d,), 13)
     ref = a.float() @ w.float().t() + bias
-    qk, vt = ops.gemm_qkv(a, w, bias, T, 2 * d)
-    _report("qk", qk, ref[:, :2 * d], 1e-2, 1e-2)
-    v_ref = ref[:, 2 * d:].view(B, T, d).transpose(1, 2)  # [B, d, T]
-    assert vt.shape == (B, d, (T + 7) // 8 * 8)
-    _report("vt", vt[:, :, :T], v_ref, 1e-2, 1e-2)
+    qkv = ops.gemm(a, w, bias, L.EPI_BIAS, cta_pair=cta_pair)
+    _report("qkv", qkv, ref, 1e-2, 1e-2)
+    pad = _ragged(B, T, 14)
+    q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+    o_ref, _ = _attn_ref(q.reshape(B, T, d), k.reshape(B, T, d), v.reshape(B, T, d), pad, H)
+    out = ops.attention(q, k, v, pad, B, H, T, T, dh)
+    _report("attention on packed qkv", out, o_ref, atol=1.5e-2, rtol=2e-2)
 
 
 # ------------------------------------------------------------------ attention
@@ -162,10 +202,7 @@ def test_attention(B, H, Tq, Tk, dh, masked):
     v = _rand((B, Tk, d), 23, dtype=torch.bfloat16)
     pad = _ragged(B, Tk, 24) if masked else None
     ref, _ = _attn_ref(q, k, v, pad, H)
-    Tk_pad = (Tk + 7) // 8 * 8
-    vt = torch.full((B, d, Tk_pad), float("nan"), dtype=torch.bfloat16, device=DEV)  # padding must never be read
-    vt[:, :, :Tk] = v.transpose(1, 2)
-    out = ops.attention(q.view(B * Tq, d), k.view(B * Tk, d), vt, pad, B, H, Tq, Tk, dh)
+    out = ops.attention(q.view(B * Tq, d), k.view(B * Tk, d), v.view(B * Tk, d), pad, B, H, Tq, Tk, dh)
     torch.cuda.synchronize()
     # P is rounded to bf16 before PV and O to bf16 after: ~2^-8 relative on O(0.1..1) values
     _report(f"attention {B,H,Tq,Tk,dh,masked}", out, ref, atol=1.5e-2, rtol=2e-2)
@@ -180,10 +217,8 @@ def test_attention_strided_qk_and_large_scores():
     d = H * dh
     qk = _rand((B * T, 2 * d), 31, 3.0, dtype=torch.bfloat16)  # scores with std ~9*8/8
     v = _rand((B, T, d), 32, dtype=torch.bfloat16)
-    vt = torch.zeros((B, d, T), dtype=torch.bfloat16, device=DEV)
-    vt[:] = v.transpose(1, 2)
     ref, _ = _attn_ref(qk[:, :d].reshape(B, T, d), qk[:, d:].reshape(B, T, d), v, None, H)
-    out = ops.attention(qk[:, :d], qk[:, d:], vt, None, B, H, T, T, dh)
+    out = ops.attention(qk[:, :d], qk[:, d:], v.view(B * T, d), None, B, H, T, T, dh)
     _report("attention strided/peaky", out, ref, atol=2e-2, rtol=3e-2)
 
 
@@ -193,12 +228,30 @@ def test_attention_fully_masked_row_is_nan():
     B, H, T, dh = 2, 2, 40, 64
     d = H * dh
     q = _rand((B, T, d), 41, dtype=torch.bfloat16)
-    vt = torch.zeros((B, d, T), dtype=torch.bfloat16, device=DEV)
+    v = torch.zeros((B * T, d), dtype=torch.bfloat16, device=DEV)
     pad = torch.zeros((B, T), dtype=torch.bool, device=DEV)
     pad[1] = True  # utterance 1: every key is PAD -> torch.softmax gives NaN
-    out = ops.attention(q.view(B * T, d), q.view(B * T, d), vt, pad, B, H, T, T, dh).view(B, T, d)
+    out = ops.attention(q.view(B * T, d), q.view(B * T, d), v, pad, B, H, T, T, dh).view(B, T, d)
     assert torch.isfinite(out[0]).all()
     assert torch.isnan(out[1]).all()
+
+
+def test_attention_nan_in_neighbour_utterance_does_not_leak():
+    """The last key tile of utterance b overhangs into utterance b+1's rows; those keys carry P = 0
+    but 0 x NaN would still poison utterance b (a fully padded neighbour is NaN by design)."""
+    from hriemo import ops
+
+    B, H, Tq, Tk, dh = 3, 2, 70, 50, 96
+    d = H * dh
+    q = _rand((B, Tq, d), 45, dtype=torch.bfloat16)
+    k = _rand((B, Tk, d), 46, dtype=torch.bfloat16)
+    v = _rand((B, Tk, d), 47, dtype=torch.bfloat16)
+    k[1] = float("nan")
+    v[1] = float("nan")
+    ref, _ = _attn_ref(q, k, v, None, H)
+    out = ops.attention(q.view(B * Tq, d), k.view(B * Tk, d), v.view(B * Tk, d), None, B, H, Tq, Tk, dh)
+    _report("attention nan isolation", out, ref, atol=1.5e-2, rtol=2e-2)
+    assert torch.isfinite(out.view(B, Tq, d)[[0, 2]]).all() and torch.isnan(out.view(B, Tq, d)[1]).all()
 
 
 # ------------------------------------------------------------------ elementwise

@@ -21,7 +21,7 @@ def main():
     d = H * dh
     dev = "cuda"
     q = torch.randn(Bsz * Tq, d, device=dev).bfloat16(); k = torch.randn(Bsz * Tk, d, device=dev).bfloat16()
-    vt = torch.randn(Bsz, d, (Tk + 7) // 8 * 8, device=dev).bfloat16()
+    vt = torch.randn(Bsz * Tk, d, device=dev).bfloat16()
     for _ in range(3): ops.attention(q, k, vt, None, Bsz, H, Tq, Tk, dh)
     trace = torch.zeros(4 * 64 * 8, dtype=torch.int64, device=dev)
     fn = lib.hriemo_debug_set_attn_trace; fn.restype = ctypes.c_int; fn.argtypes = [ctypes.c_void_p]

@@ -27,18 +27,19 @@ def main():
     for (M, N, K, epi) in gemm_shapes:
         a = torch.randn(M, K, device=dev).bfloat16(); w = torch.randn(N, K, device=dev).bfloat16(); b = torch.randn(N, device=dev)
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        med, best = timeit(lambda: ops.gemm(a, w, b, epi, out=out))
+        med, best = timeit(lambda: ops.gemm(a, w, b, epi, out=out, cta_pair=1))
+        med2, best2 = timeit(lambda: ops.gemm(a, w, b, epi, out=out, cta_pair=2))
         medc, bestc = timeit(lambda: torch.nn.functional.linear(a, w, b.bfloat16()))
         fl = 2.0 * M * N * K
-        res.append(dict(kernel="gemm", M=M, N=N, K=K, ms=med, tflops=fl / med / 1e9, frac_burst=fl / med / 1e9 / PEAKS["bf16_tflops"], cublas_ms=medc, cublas_tflops=fl / medc / 1e9))
+        res.append(dict(kernel="gemm", M=M, N=N, K=K, ms_1cta=med, tflops_1cta=fl / med / 1e9, ms_pair=med2, tflops_pair=fl / med2 / 1e9,
+                        frac_burst_pair=fl / med2 / 1e9 / PEAKS["bf16_tflops"], cublas_ms=medc, cublas_tflops=fl / medc / 1e9))
         print(res[-1], flush=True)
     attn_shapes = [] if only not in (None, "attention") else [(512, 8, 500, 500, 96), (512, 8, 500, 64, 96), (512, 8, 64, 500, 96), (512, 8, 300, 300, 96), (512, 4, 300, 128, 64), (64, 8, 1000, 1000, 96)]
     for (B, H, Tq, Tk, dh) in attn_shapes:
         d = H * dh
         q = torch.randn(B * Tq, d, device=dev).bfloat16(); k = torch.randn(B * Tk, d, device=dev).bfloat16()
         v = torch.randn(B, Tk, d, device=dev).bfloat16()
-        vt = torch.zeros(B, d, (Tk + 7) // 8 * 8, device=dev, dtype=torch.bfloat16); vt[:, :, :Tk] = v.transpose(1, 2)
-        med, best = timeit(lambda: ops.attention(q, k, vt, None, B, H, Tq, Tk, dh))
+        med, best = timeit(lambda: ops.attention(q, k, v.view(B * Tk, d), None, B, H, Tq, Tk, dh))
         qh = q.view(B, Tq, H, dh).transpose(1, 2); kh = k.view(B, Tk, H, dh).transpose(1, 2); vh = v.view(B, Tk, H, dh).transpose(1, 2)
         meds, _ = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qh, kh, vh))
         fl = 4.0 * B * H * Tq * Tk * dh
