@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256)
 ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
                       const float* __restrict__ beta, float eps, int apply_ln,
                       const uint8_t* __restrict__ pad, float* __restrict__ pooled, int64_t ld_pooled,
-                      int T, int d) {
+                      int T, int d, const float* __restrict__ pre_g, const float* __restrict__ pre_b) {
   extern __shared__ float part[];  // [8][d]
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,6 +174,7 @@ ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const fl
     ++count;
     RowRegs<NV> r;
     load_row<false, NV>(r, x + (static_cast<int64_t>(b) * T + t) * ldx, d, lane);
+    if (pre_g != nullptr) normalize_row(r, d, lane, pre_g, pre_b, eps);
     if (apply_ln) normalize_row(r, d, lane, gamma, beta, eps);
 #pragma unroll
     for (int i = 0; i < NV; ++i)
@@ -228,7 +229,8 @@ gate_blend_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int T_a,
                   const float* __restrict__ ba, const float* __restrict__ gt, const float* __restrict__ bt,
                   float eps, int apply_ln, const float* __restrict__ w, int w_is_scalar,
                   __nv_bfloat16* __restrict__ hb, float* __restrict__ hf, int64_t ldh,
-                  float* __restrict__ beta_out, int B, int L, int d) {
+                  float* __restrict__ beta_out, int B, int L, int d, const float* __restrict__ pga,
+                  const float* __restrict__ pba, const float* __restrict__ pgt, const float* __restrict__ pbt) {
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= static_cast<int64_t>(B) * L) return;
@@ -237,6 +239,8 @@ gate_blend_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int T_a,
   RowRegs<NV> ra, rt;
   load_row<false, NV>(ra, a + (static_cast<int64_t>(b) * T_a + tt) * lda, d, lane);
   load_row<false, NV>(rt, t + (static_cast<int64_t>(b) * L + tt) * ldt, d, lane);
+  if (pga != nullptr) normalize_row(ra, d, lane, pga, pba, eps);
+  if (pgt != nullptr) normalize_row(rt, d, lane, pgt, pbt, eps);
   if (apply_ln) {
     normalize_row(ra, d, lane, ga, ba, eps);
     normalize_row(rt, d, lane, gt, bt, eps);
@@ -258,6 +262,47 @@ gate_blend_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int T_a,
   if (tt == 0 && beta_out != nullptr) {
     wsum = warp_sum(wsum);
     if (lane == 0) beta_out[b] = w_is_scalar ? __ldg(w + b) : wsum / static_cast<float>(d);
+  }
+}
+
+// ------------------------------------------------------------------ fused-LayerNorm helpers
+// partials[slab][row] = (sum, sum of squares) over that slab's columns -> stats[row] = (mean, rstd)
+__global__ void ln_stats_finalize_kernel(const float2* __restrict__ partials, int n_slabs, int64_t rows, int d,
+                                         float eps, float2* __restrict__ stats) {
+  const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (row >= rows) return;
+  float s1 = 0.0f, s2 = 0.0f;
+  for (int s = 0; s < n_slabs; ++s) {
+    const float2 v = __ldg(partials + static_cast<int64_t>(s) * rows + row);
+    s1 += v.x;
+    s2 += v.y;
+  }
+  const float mean = s1 / static_cast<float>(d);
+  const float var = fmaxf(s2 / static_cast<float>(d) - mean * mean, 0.0f);
+  stats[row] = make_float2(mean, rsqrtf(var + eps));
+}
+
+// One warp per output row n of W [N,K]: W*gamma -> bf16, its row sum, and bias + W.beta
+__global__ void fold_ln_weight_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, const float* __restrict__ bias,
+                                      __nv_bfloat16* __restrict__ wf, int64_t ldo, float* __restrict__ colsum,
+                                      float* __restrict__ bias_f, int N, int K) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float cs = 0.0f, bs = 0.0f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[static_cast<int64_t>(n) * ldw + k];
+    const __nv_bfloat16 h = __float2bfloat16_rn(w * gamma[k]);
+    wf[static_cast<int64_t>(n) * ldo + k] = h;
+    cs += __bfloat162float(h);
+    bs = fmaf(w, beta[k], bs);
+  }
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if (lane == 0) {
+    colsum[n] = cs;
+    bias_f[n] = bs + (bias != nullptr ? bias[n] : 0.0f);
   }
 }
 
@@ -336,8 +381,11 @@ extern "C" int hriemo_layernorm(const void* x, int32_t x_is_f32, int64_t ldx, co
 
 extern "C" int hriemo_ln_masked_mean(const void* x, int64_t ldx, const float* gamma, const float* beta,
                                      float eps, int32_t apply_ln, const uint8_t* pad, float* pooled,
-                                     int64_t ld_pooled, int32_t B, int32_t T, int32_t d, void* stream) {
+                                     int64_t ld_pooled, int32_t B, int32_t T, int32_t d, const float* pre_gamma,
+                                     const float* pre_beta, void* stream) {
   HRIEMO_REQUIRE(x && pooled && (!apply_ln || (gamma && beta)), "ln_masked_mean: null pointer");
+  HRIEMO_REQUIRE((pre_gamma == nullptr) == (pre_beta == nullptr) && aligned16(pre_gamma) && aligned16(pre_beta),
+                 "ln_masked_mean: pre_gamma / pre_beta go together, 16-byte aligned");
   HRIEMO_REQUIRE(row_shape_ok(d) && B > 0 && T > 0, "ln_masked_mean: bad shape B=%d T=%d d=%d", B, T, d);
   HRIEMO_REQUIRE(ldx % 8 == 0 && aligned16(x) && aligned16(gamma) && aligned16(beta),
                  "ln_masked_mean: misaligned operand");
@@ -346,7 +394,8 @@ extern "C" int hriemo_ln_masked_mean(const void* x, int64_t ldx, const float* ga
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(ln_masked_mean_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4);
   HRIEMO_DISPATCH_NV(d, (ln_masked_mean_kernel<NV><<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, apply_ln, pad, pooled, ld_pooled, T, d)));
+      static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, apply_ln, pad, pooled, ld_pooled, T, d,
+      pre_gamma, pre_beta)));
   return check_launch("ln_masked_mean");
 }
 
@@ -362,8 +411,13 @@ extern "C" int hriemo_gate_blend(const void* a, int64_t lda, int32_t T_a, const 
                                  const float* gamma_a, const float* beta_a, const float* gamma_t,
                                  const float* beta_t, float eps, int32_t apply_ln, const float* w,
                                  int32_t w_is_scalar, void* h_bf16, float* h_f32, int64_t ldh,
-                                 float* beta_out, int32_t B, int32_t L, int32_t d, void* stream) {
+                                 float* beta_out, int32_t B, int32_t L, int32_t d, const float* pre_gamma_a,
+                                 const float* pre_beta_a, const float* pre_gamma_t, const float* pre_beta_t,
+                                 void* stream) {
   HRIEMO_REQUIRE(a && t && w && (h_bf16 || h_f32), "gate_blend: null pointer");
+  HRIEMO_REQUIRE((pre_gamma_a == nullptr) == (pre_beta_a == nullptr) && (pre_gamma_t == nullptr) == (pre_beta_t == nullptr) &&
+                     aligned16(pre_gamma_a) && aligned16(pre_beta_a) && aligned16(pre_gamma_t) && aligned16(pre_beta_t),
+                 "gate_blend: pre-LayerNorm parameters come in (gamma, beta) pairs, 16-byte aligned");
   HRIEMO_REQUIRE(!apply_ln || (gamma_a && beta_a && gamma_t && beta_t), "gate_blend: LN params missing");
   HRIEMO_REQUIRE(row_shape_ok(d) && B > 0 && L > 0 && T_a >= L, "gate_blend: bad shape B=%d L=%d T_a=%d d=%d",
                  B, L, T_a, d);
@@ -374,8 +428,29 @@ extern "C" int hriemo_gate_blend(const void* a, int64_t lda, int32_t T_a, const 
   HRIEMO_DISPATCH_NV(d, (gate_blend_kernel<NV><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(a), lda, T_a, static_cast<const __nv_bfloat16*>(t), ldt, gamma_a,
       beta_a, gamma_t, beta_t, eps, apply_ln, w, w_is_scalar, static_cast<__nv_bfloat16*>(h_bf16), h_f32,
-      ldh, beta_out, B, L, d)));
+      ldh, beta_out, B, L, d, pre_gamma_a, pre_beta_a, pre_gamma_t, pre_beta_t)));
   return check_launch("gate_blend");
+}
+
+extern "C" int hriemo_ln_stats_finalize(const float* partials, int32_t n_slabs, int64_t rows, int32_t d, float eps,
+                                        float* stats, void* stream) {
+  HRIEMO_REQUIRE(partials && stats && n_slabs > 0 && rows >= 0 && d > 0, "ln_stats_finalize: bad argument");
+  HRIEMO_REQUIRE(((reinterpret_cast<uintptr_t>(partials) | reinterpret_cast<uintptr_t>(stats)) & 7u) == 0,
+                 "ln_stats_finalize: misaligned operand");
+  if (rows == 0) return HRIEMO_OK;
+  ln_stats_finalize_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(partials), n_slabs, rows, d, eps, reinterpret_cast<float2*>(stats));
+  return check_launch("ln_stats_finalize");
+}
+
+extern "C" int hriemo_fold_ln_weight(const float* W, int64_t ldw, const float* gamma, const float* beta,
+                                     const float* bias, void* w_folded, int64_t ldo, float* colsum,
+                                     float* bias_folded, int32_t N, int32_t K, void* stream) {
+  HRIEMO_REQUIRE(W && gamma && beta && w_folded && colsum && bias_folded, "fold_ln_weight: null pointer");
+  HRIEMO_REQUIRE(N > 0 && K > 0 && ldw >= K && ldo >= K, "fold_ln_weight: bad shape N=%d K=%d", N, K);
+  fold_ln_weight_kernel<<<(N + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      W, ldw, gamma, beta, bias, static_cast<__nv_bfloat16*>(w_folded), ldo, colsum, bias_folded, N, K);
+  return check_launch("fold_ln_weight");
 }
 
 extern "C" int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d,

@@ -40,6 +40,14 @@ struct GemmKernelParams {
   int64_t ldo;
   const void* resid;
   int64_t ldr;
+  // fused LayerNorm (see hriemo.h): A rows / residual rows are pre-LayerNorm tensors with known
+  // per-row (mean, rstd); per-slab (sum, sum of squares) of the output rows are written out
+  const float2* a_stats;
+  const float* a_colsum;
+  const float2* resid_stats;
+  const float* resid_gamma;
+  const float* resid_beta;
+  float2* stats_out;
   int num_n_blocks, num_k_blocks;
   int64_t num_tiles;
 };
@@ -50,7 +58,10 @@ struct GemmSmem {
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
   static constexpr int OUT_OFF = B_OFF + STAGES * B_STAGE_BYTES;   // EW warps x 2 boxes of [32][64] bf16
-  static constexpr int BAR_OFF = OUT_OFF + 2 * EW * OUT_BOX_BYTES;
+  // per-column epilogue vectors (bias | colsum or gamma | beta), copied once per CTA when they fit
+  static constexpr int VEC_OFF = OUT_OFF + 2 * EW * OUT_BOX_BYTES;
+  static constexpr int VEC_BYTES = (CTAS == 2) ? 32 * 1024 : 0;
+  static constexpr int BAR_OFF = VEC_OFF + VEC_BYTES;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], resid_full[EW warps][2], tmem_ptr
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4 + 2 * EW) * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
@@ -91,6 +102,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t sA = smem_base + L::A_OFF;
   const uint32_t sB = smem_base + L::B_OFF;
   const uint32_t sOut = smem_base + L::OUT_OFF;
+  // Per-column vectors of the epilogue live in shared memory for the kernel's lifetime when
+  // 3 x N floats fit (an L1 hit costs a long-scoreboard round trip per use; ld.shared does not).
+  const bool vec_smem = L::VEC_BYTES > 0 && 3 * p.N * 4 <= L::VEC_BYTES;
+  const uint32_t sVec = smem_base + L::VEC_OFF;
+  if (vec_smem) {
+    float* vs = reinterpret_cast<float*>(smem_raw + (sVec - smem_u32(smem_raw)));
+    const float* v1 = p.a_colsum != nullptr ? p.a_colsum : p.resid_gamma;
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+      vs[i] = p.bias != nullptr ? p.bias[i] : 0.0f;
+      if (v1 != nullptr) vs[p.N + i] = v1[i];
+      if (p.resid_beta != nullptr) vs[2 * p.N + i] = p.resid_beta[i];
+    }
+  }
   const uint32_t bar_full = smem_base + L::BAR_OFF;
   const uint32_t bar_empty = bar_full + STAGES * 8;
   const uint32_t bar_tfull = bar_empty + STAGES * 8;
@@ -214,6 +238,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     auto has_slab = [&](int64_t tile_, int slab_) {
       return static_cast<int>(tile_ % p.num_n_blocks) * BN + slab_ * 64 < p.N;
     };
+    // float4 of per-column vector `which` (0 bias, 1 colsum / gamma, 2 beta) at column n
+    auto vec4 = [&](int which, const float* gptr, int n_) -> float4 {
+      if (vec_smem) {
+        float4 r;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                     : "r"(sVec + static_cast<uint32_t>(which * p.N + n_) * 4u));
+        return r;
+      }
+      return __ldg(reinterpret_cast<const float4*>(gptr + n_));
+    };
     uint32_t it = 0, slab_ctr = 0;
     const uint32_t tempty_leader = CTAS == 2 ? mapa_shared(bar_tempty, 0) : bar_tempty;
     if (tma_resid && lane == 0 && tile_first < p.num_tiles && has_slab(tile_first, slab0))
@@ -225,9 +260,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int64_t m = m_tile + row_in_tile;
       const int n0 = static_cast<int>(tile % p.num_n_blocks) * BN;
       const bool row_ok = m < p.M;
+      // LayerNorm folded into this GEMM: out = rstd_a * (acc - mean_a * colsum[n]) + bias[n]
+      float a_mean = 0.0f, a_rstd = 1.0f;
+      if (p.a_stats != nullptr && row_ok) {
+        const float2 st = __ldg(p.a_stats + m);
+        a_mean = st.x; a_rstd = st.y;
+      }
+      // residual given pre-LayerNorm: LN(r) = (r * r_scale + r_shift) * gamma[n] + beta[n]
+      float2 r_st = make_float2(0.0f, 1.0f);  // consumed after the accumulator wait: the load overlaps it
+      if (p.resid_stats != nullptr && row_ok) r_st = __ldg(p.resid_stats + m);
       mbar_wait(bar_tfull + as * 8, aphase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+      const float r_scale = r_st.y, r_shift = -r_st.x * r_st.y;
 #pragma unroll 1
       for (int sl = 0; sl < SLABS; ++sl) {
         const int s = slab0 + sl;
@@ -238,6 +283,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         tmem_ld32(t_row + s * 64, v[0]);
         if (two) tmem_ld32(t_row + s * 64 + 32, v[1]);
         tmem_ld_wait();
+        float s1 = 0.0f, s2 = 0.0f;  // per-row partial LayerNorm statistics of this slab's outputs
         uint32_t buf = 0;
         if (bf16_out) {
           buf = my_stage + (slab_ctr & 1u) * OUT_BOX_BYTES;
@@ -255,11 +301,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[hf][i]);
-          if (p.bias != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + nn);
+          if (p.a_stats != nullptr) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 b4 = __ldg(bp + i);
+              const float4 c4 = vec4(1, p.a_colsum, nn + i * 4);
+              f[i * 4 + 0] = a_rstd * fmaf(-a_mean, c4.x, f[i * 4 + 0]);
+              f[i * 4 + 1] = a_rstd * fmaf(-a_mean, c4.y, f[i * 4 + 1]);
+              f[i * 4 + 2] = a_rstd * fmaf(-a_mean, c4.z, f[i * 4 + 2]);
+              f[i * 4 + 3] = a_rstd * fmaf(-a_mean, c4.w, f[i * 4 + 3]);
+            }
+          }
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = vec4(0, p.bias, nn + i * 4);
               f[i * 4 + 0] += b4.x; f[i * 4 + 1] += b4.y; f[i * 4 + 2] += b4.z; f[i * 4 + 3] += b4.w;
             }
           }
@@ -275,10 +330,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                            : "=r"(r4.x), "=r"(r4.y), "=r"(r4.z), "=r"(r4.w)
                            : "r"(buf + lane * 128 + slot * 16)
                            : "memory");
-              f[i * 8 + 0] += bf16_lo(r4.x); f[i * 8 + 1] += bf16_hi(r4.x);
-              f[i * 8 + 2] += bf16_lo(r4.y); f[i * 8 + 3] += bf16_hi(r4.y);
-              f[i * 8 + 4] += bf16_lo(r4.z); f[i * 8 + 5] += bf16_hi(r4.z);
-              f[i * 8 + 6] += bf16_lo(r4.w); f[i * 8 + 7] += bf16_hi(r4.w);
+              float r[8] = {bf16_lo(r4.x), bf16_hi(r4.x), bf16_lo(r4.y), bf16_hi(r4.y),
+                            bf16_lo(r4.z), bf16_hi(r4.z), bf16_lo(r4.w), bf16_hi(r4.w)};
+              if (p.resid_stats != nullptr) {
+                const float4 g0 = vec4(1, p.resid_gamma, nn + i * 8), g1 = vec4(1, p.resid_gamma, nn + i * 8 + 4);
+                const float4 b0 = vec4(2, p.resid_beta, nn + i * 8), b1 = vec4(2, p.resid_beta, nn + i * 8 + 4);
+                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) r[k] = fmaf(fmaf(r[k], r_scale, r_shift), g[k], bb[k]);
+              }
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[i * 8 + k] += r[k];
             }
           } else if (p.epilogue == HRIEMO_EPI_BIAS_RESID_F32 && row_ok) {
             const float4* rp =
@@ -287,6 +350,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             for (int i = 0; i < 8; ++i) {
               const float4 r4 = __ldg(rp + i);
               f[i * 4 + 0] += r4.x; f[i * 4 + 1] += r4.y; f[i * 4 + 2] += r4.z; f[i * 4 + 3] += r4.w;
+            }
+          }
+          if (p.stats_out != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              s1 += f[i];
+              s2 = fmaf(f[i], f[i], s2);
             }
           }
           if (bf16_out) {
@@ -306,6 +376,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               op[i] = make_float4(f[i * 4 + 0], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
           }
         }
+        if (p.stats_out != nullptr && row_ok)  // [slab][row]: consecutive lanes -> consecutive 8 bytes
+          p.stats_out[static_cast<int64_t>(n >> 6) * p.M + m] = make_float2(s1, s2);
         if (bf16_out) {
           fence_proxy_async_smem();
           __syncwarp();
@@ -374,6 +446,10 @@ static int launch_gemm(const hriemo_gemm_args& a, cudaStream_t stream) {
   GemmKernelParams p;
   p.M = a.M; p.N = a.N; p.K = a.K; p.epilogue = a.epilogue; p.bias = a.bias;
   p.out = a.out; p.ldo = a.ldo; p.resid = a.resid; p.ldr = a.ldr;
+  p.a_stats = reinterpret_cast<const float2*>(a.a_stats); p.a_colsum = a.a_colsum;
+  p.resid_stats = reinterpret_cast<const float2*>(a.resid_stats);
+  p.resid_gamma = a.resid_gamma; p.resid_beta = a.resid_beta;
+  p.stats_out = reinterpret_cast<float2*>(a.stats_out);
   p.num_n_blocks = (a.N + BN - 1) / BN;
   p.num_k_blocks = (a.K + BK - 1) / BK;
   const int64_t num_m_blocks = (a.M + BM * CTAS - 1) / (BM * CTAS);
@@ -432,6 +508,16 @@ extern "C" int hriemo_gemm_bf16(const hriemo_gemm_args* a, void* stream) {
                    "gemm: resid misaligned");
   }
   if (a->bias) HRIEMO_REQUIRE((reinterpret_cast<uintptr_t>(a->bias) & 15u) == 0, "gemm: bias misaligned");
+  HRIEMO_REQUIRE((a->a_stats == nullptr) == (a->a_colsum == nullptr), "gemm: a_stats and a_colsum go together");
+  HRIEMO_REQUIRE(a->resid_stats == nullptr || (a->epilogue == HRIEMO_EPI_BIAS_RESID && a->resid_gamma && a->resid_beta),
+                 "gemm: resid_stats needs the bf16 residual epilogue and resid_gamma / resid_beta");
+  HRIEMO_REQUIRE((a->a_stats == nullptr && a->stats_out == nullptr) || !f32_out,
+                 "gemm: fused LayerNorm is implemented for the bf16-output epilogues");
+  HRIEMO_REQUIRE(((reinterpret_cast<uintptr_t>(a->a_stats) | reinterpret_cast<uintptr_t>(a->resid_stats) |
+                   reinterpret_cast<uintptr_t>(a->stats_out)) & 7u) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(a->a_colsum) | reinterpret_cast<uintptr_t>(a->resid_gamma) |
+                       reinterpret_cast<uintptr_t>(a->resid_beta)) & 15u) == 0,
+                 "gemm: fused-LayerNorm operand misaligned");
   if (a->M == 0) return HRIEMO_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // Wide tiles for wide outputs; 128-column tiles keep more CTAs busy when N is small.
@@ -440,7 +526,7 @@ extern "C" int hriemo_gemm_bf16(const hriemo_gemm_args* a, void* stream) {
     static const int env_force = [] { const char* e = getenv("HRIEMO_GEMM_CTAS"); return e ? atoi(e) : 0; }();
     const int force = a->cta_pair ? a->cta_pair : env_force;
     const int64_t pair_tiles = ((a->M + 255) / 256) * (a->N / 256);
-    if (force != 1 && (force == 2 || pair_tiles >= device_sm_count() / 2)) return launch_gemm<256, 5, 2, 8>(*a, s);
+    if (force != 1 && (force == 2 || pair_tiles >= device_sm_count() / 2)) return launch_gemm<256, 4, 2, 8>(*a, s);
     return launch_gemm<256, 4, 1, 4>(*a, s);
   }
   return launch_gemm<128, 6, 1, 4>(*a, s);

@@ -177,7 +177,9 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // relaxed: the callers order their tensor-memory reads with tcgen05.wait::ld + tcgen05.fence; a
+  // release at cluster scope would add a full memory barrier per arrival
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // CTA-pair (cta_group::2) variants.  A pair shares one MMA: the leader (cluster rank 0) issues it,
 // each CTA supplies its half of the operands from its own shared memory at the SAME offsets, and

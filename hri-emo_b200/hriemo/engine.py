@@ -26,12 +26,23 @@ f32 = torch.float32
 # activations
 # --------------------------------------------------------------------------- #
 @dataclass
+class LazyLN:
+    """A LayerNorm that has not been applied yet: the stream holds the pre-LayerNorm sum and every
+    consumer applies (x - mean) * rstd * gamma + beta itself (fused GEMM epilogues, gate kernels)."""
+    gamma: torch.Tensor   # fp32 [d]
+    beta: torch.Tensor    # fp32 [d]
+    stats: torch.Tensor   # fp32 [B*T, 2] = (mean, rstd) per row
+
+
+@dataclass
 class Seq:
-    """A batch of sequences as one row-major matrix: x[b*T + t, :]."""
+    """A batch of sequences as one row-major matrix: x[b*T + t, :].  When `ln` is set, the logical
+    value of the stream is LN(x) and x is the pre-LayerNorm tensor."""
     x: torch.Tensor                      # bf16 [B*T, d]
     B: int
     T: int
     x32: Optional[torch.Tensor] = None   # fp32 copy when the caller asked for one
+    ln: Optional[LazyLN] = None
 
     @property
     def d(self) -> int:
@@ -123,6 +134,21 @@ def v32(v: torch.Tensor) -> torch.Tensor:
     return v.contiguous() if v.dtype == f32 else v.float().contiguous()
 
 
+def prep_folded(w: torch.Tensor, b: Optional[torch.Tensor], ln_module) -> dict:
+    """Operands of a Linear fed by LN(x) when only the pre-LayerNorm x is in memory
+    (hriemo_fold_ln_weight): w*gamma in bf16, its row sums, and b + w.beta."""
+    wf, cs, bf = ops.fold_ln_weight(v32(w), v32(b) if b is not None else None, v32(ln_module.weight),
+                                    v32(ln_module.bias))
+    return dict(w=wf, b=bf, colsum=cs)
+
+
+def cross_pair_weights(mha_q, mha_kv):
+    d = mha_q.in_proj_weight.shape[1]
+    w = torch.cat([mha_q.in_proj_weight.detach()[:d], mha_kv.in_proj_weight.detach()[d:]], dim=0)
+    b = torch.cat([mha_q.in_proj_bias.detach()[:d], mha_kv.in_proj_bias.detach()[d:]], dim=0)
+    return w, b
+
+
 def prep_mha_self(mha) -> dict:
     return dict(w_qkv=w16(mha.in_proj_weight), b_qkv=v32(mha.in_proj_bias),
                 w_o=w16(mha.out_proj.weight), b_o=v32(mha.out_proj.bias))
@@ -131,9 +157,7 @@ def prep_mha_self(mha) -> dict:
 def prep_cross_pair(mha_q, mha_kv) -> dict:
     """Operands of the fused projection of ONE stream that is the query side of `mha_q`
     and the key/value side of `mha_kv`: rows [Wq(mha_q); Wk(mha_kv); Wv(mha_kv)]."""
-    d = mha_q.in_proj_weight.shape[1]
-    w = torch.cat([mha_q.in_proj_weight.detach()[:d], mha_kv.in_proj_weight.detach()[d:]], dim=0)
-    b = torch.cat([mha_q.in_proj_bias.detach()[:d], mha_kv.in_proj_bias.detach()[d:]], dim=0)
+    w, b = cross_pair_weights(mha_q, mha_kv)
     return dict(w_qkv=w16(w), b_qkv=v32(b))
 
 
@@ -148,47 +172,86 @@ def prep_linear(lin, k_pad: Optional[int] = None) -> dict:
 # --------------------------------------------------------------------------- #
 # encoder building blocks
 # --------------------------------------------------------------------------- #
+# Every sub-layer of the reference is LN(x + f(x)).  With lazy=True the LayerNorm is not run as a
+# pass of its own: the out-projection / FFN GEMM writes the pre-LayerNorm sum together with per-row
+# statistics, and the result is a Seq carrying a LazyLN that its consumers apply in their epilogues
+# (projection GEMMs through folded weights, residual adds, the gate kernels).  lazy=False keeps the
+# explicit LayerNorm kernel (legacy block, utterance-level classifier, anything that needs the
+# normalised tensor itself).
+def materialize(x: Seq, want_f32: bool = False) -> Seq:
+    """Apply a pending LayerNorm with the stand-alone kernel."""
+    if x.ln is None:
+        if want_f32 and x.x32 is None:
+            raise L.HriemoError("internal: fp32 copy of a materialised stream was not requested")
+        return x
+    yb, yf = ops.layernorm(x.x, x.ln.gamma, x.ln.beta, want_bf16=True, want_f32=want_f32)
+    return Seq(yb, x.B, x.T, yf)
+
+
 def residual_ln(x_pre: torch.Tensor, ln, B: int, T: int, want_f32: bool = False) -> Seq:
     yb, yf = ops.layernorm(x_pre, ln[0], ln[1], want_bf16=True, want_f32=want_f32)
     return Seq(yb, B, T, yf)
 
 
-def self_attention_block(x: Seq, P: dict, ln, mask, n_heads: int, want_attn: bool):
+def project(x: Seq, P: dict, P_folded: Optional[dict], epilogue: int, tag: str) -> torch.Tensor:
+    """Linear over the logical value of x: plain operands, or the folded ones when x is lazy."""
+    if x.ln is None:
+        return ops.gemm(x.x, P["w"], P["b"], epilogue, tag=tag)
+    if P_folded is None:
+        return project(materialize(x), P, None, epilogue, tag)
+    return ops.gemm(x.x, P_folded["w"], P_folded["b"], epilogue, a_ln=(x.ln.stats, P_folded["colsum"]), tag=tag)
+
+
+def out_residual(o: torch.Tensor, w, b, x: Seq, ln, lazy: bool, tag: str, want_f32: bool = False) -> Seq:
+    """LN(x + o W^T + b): the residual is the logical value of x (normalised on the fly if x is lazy)."""
+    resid_ln = None if x.ln is None else (x.ln.stats, x.ln.gamma, x.ln.beta)
+    if lazy and not want_f32:
+        pre, stats = ops.gemm(o, w, b, L.EPI_BIAS_RESID, resid=x.x, resid_ln=resid_ln, want_stats=True, tag=tag)
+        return Seq(pre, x.B, x.T, None, LazyLN(ln[0], ln[1], stats))
+    pre = ops.gemm(o, w, b, L.EPI_BIAS_RESID, resid=x.x, resid_ln=resid_ln, tag=tag)
+    return residual_ln(pre, ln, x.B, x.T, want_f32)
+
+
+def self_attention_block(x: Seq, P: dict, ln, mask, n_heads: int, want_attn: bool, lazy: bool = False,
+                         P_folded: Optional[dict] = None):
     """LN(x + MHA(x, x, x)): models/cross_modal_block_tacfn.py:74-82 / :85-93."""
     d = x.d
     dh = d // n_heads
-    qkv = ops.gemm(x.x, P["w_qkv"], P["b_qkv"], L.EPI_BIAS)
+    if x.ln is not None and P_folded is None:
+        x = materialize(x)
+    qkv = project(x, dict(w=P["w_qkv"], b=P["b_qkv"]), P_folded, L.EPI_BIAS, "attn_proj")
     q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
     o = ops.attention(q, k, v, mask, x.B, n_heads, x.T, x.T, dh)
-    pre = ops.gemm(o, P["w_o"], P["b_o"], L.EPI_BIAS_RESID, resid=x.x)
     amap = ops.attention_probs(q, k, mask, x.B, n_heads, x.T, x.T, dh) if want_attn else None
-    return residual_ln(pre, ln, x.B, x.T), amap
+    return out_residual(o, P["w_o"], P["b_o"], x, ln, lazy, "attn_proj"), amap
 
 
-def cross_projection(x: Seq, P: dict):
+def cross_projection(x: Seq, P: dict, P_folded: Optional[dict] = None):
     """One GEMM producing this stream's cross-attention query, and the key / value it
     offers to the other stream (SURVEY Appendix C "free algebraic fusions")."""
     d = x.d
-    qkv = ops.gemm(x.x, P["w_qkv"], P["b_qkv"], L.EPI_BIAS)
+    qkv = project(x, dict(w=P["w_qkv"], b=P["b_qkv"]), P_folded, L.EPI_BIAS, "attn_proj")
     return qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
 
 
 def cross_attention_block(xq: Seq, q, k_other, v_other, T_other: int, mask_other, w_o, b_o, ln,
-                          n_heads: int, want_attn: bool):
+                          n_heads: int, want_attn: bool, lazy: bool = False):
     """LN(x + MHA(x, other, other)): models/cross_modal_block_tacfn.py:98-105 / :111-118."""
     dh = xq.d // n_heads
     o = ops.attention(q, k_other, v_other, mask_other, xq.B, n_heads, xq.T, T_other, dh)
-    pre = ops.gemm(o, w_o, b_o, L.EPI_BIAS_RESID, resid=xq.x)
     amap = ops.attention_probs(q, k_other, mask_other, xq.B, n_heads, xq.T, T_other, dh) if want_attn else None
-    return residual_ln(pre, ln, xq.B, xq.T), amap
+    return out_residual(o, w_o, b_o, xq, ln, lazy, "attn_proj"), amap
 
 
-def ffn_block(x: Seq, P1: dict, P2: dict, ln, want_f32: bool = False) -> Seq:
+def ffn_block(x: Seq, P1: dict, P2: dict, ln, want_f32: bool = False, lazy: bool = False,
+              P1_folded: Optional[dict] = None) -> Seq:
     """LN(x + W2 relu(W1 x + b1) + b2): models/cross_modal_block_tacfn.py:106 / :119."""
-    h = ops.gemm(x.x, P1["w"], P1["b"], L.EPI_BIAS_RELU)
-    pre = ops.gemm(h, P2["w"], P2["b"], L.EPI_BIAS_RESID, resid=x.x)
+    if x.ln is not None and P1_folded is None:
+        x = materialize(x)
+    h = project(x, P1, P1_folded, L.EPI_BIAS_RELU, "ffn")
+    out = out_residual(h, P2["w"], P2["b"], x, ln, lazy, "ffn", want_f32)
     del h
-    return residual_ln(pre, ln, x.B, x.T, want_f32)
+    return out
 
 
 # --------------------------------------------------------------------------- #

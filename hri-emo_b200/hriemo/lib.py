@@ -28,6 +28,9 @@ class GemmArgs(C.Structure):
         ("epilogue", C.c_int32), ("cta_pair", C.c_int32),
         ("out", C.c_void_p), ("ldo", C.c_int64),
         ("resid", C.c_void_p), ("ldr", C.c_int64),
+        ("a_stats", C.c_void_p), ("a_colsum", C.c_void_p),
+        ("resid_stats", C.c_void_p), ("resid_gamma", C.c_void_p), ("resid_beta", C.c_void_p),
+        ("stats_out", C.c_void_p),
     ]
 
 
@@ -57,11 +60,13 @@ SIGNATURES = {
     "hriemo_small_attention": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P,
                                           _I32, _I32, _I32, _I32, _I32, _F, _P]),
     "hriemo_layernorm": (C.c_int, [_P, _I32, _I64, _P, _P, _F, _P, _P, _I64, _I64, _I32, _P]),
-    "hriemo_ln_masked_mean": (C.c_int, [_P, _I64, _P, _P, _F, _I32, _P, _P, _I64, _I32, _I32, _I32, _P]),
+    "hriemo_ln_masked_mean": (C.c_int, [_P, _I64, _P, _P, _F, _I32, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P]),
+    "hriemo_ln_stats_finalize": (C.c_int, [_P, _I32, _I64, _I32, _F, _P, _P]),
+    "hriemo_fold_ln_weight": (C.c_int, [_P, _I64, _P, _P, _P, _P, _I64, _P, _P, _I32, _I32, _P]),
     "hriemo_gate_input": (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
     "hriemo_sgemm_f32": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I64, _I64, _I32, _I32, _I32, _P]),
     "hriemo_gate_blend": (C.c_int, [_P, _I64, _I32, _P, _I64, _P, _P, _P, _P, _F, _I32, _P, _I32,
-                                     _P, _P, _I64, _P, _I32, _I32, _I32, _P]),
+                                     _P, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "hriemo_mean_over_time": (C.c_int, [_P, _P, _I32, _I32, _I32, _P]),
 }
 

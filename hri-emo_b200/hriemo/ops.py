@@ -84,9 +84,12 @@ def cast_bf16(x: torch.Tensor, ld_out: Optional[int] = None) -> torch.Tensor:
 # ------------------------------------------------------------------ GEMM
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int = _l.EPI_BIAS,
          resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-         cta_pair: int = 0) -> torch.Tensor:
+         cta_pair: int = 0, a_ln=None, resid_ln=None, want_stats: bool = False, tag: str = "gemm"):
     """out = epilogue(a[M,K] @ w[N,K]^T + bias) on tcgen05 tensor cores.
-    cta_pair: 0 = library picks the tile form, 1 = one-CTA tiles, 2 = CTA-pair (cta_group::2) tiles."""
+    cta_pair: 0 = library picks the tile form, 1 = one-CTA tiles, 2 = CTA-pair (cta_group::2) tiles.
+    Fused LayerNorm (include/hriemo.h): a_ln = (stats [M,2], colsum [N]) -- `a` is pre-LayerNorm and
+    `w` / `bias` are the folded operands of fold_ln_weight; resid_ln = (stats [M,2], gamma, beta) --
+    `resid` is pre-LayerNorm; want_stats -> returns (out, stats [M,2] = (mean, rstd) of out's rows)."""
     _chk2d(a, bf16, "gemm A")
     _chk2d(w, bf16, "gemm W")
     M, K = a.shape
@@ -106,10 +109,53 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogu
     if resid is not None:
         _chk2d(resid, f32 if f32_out else bf16, "gemm resid")
         args.resid, args.ldr = resid.data_ptr(), resid.stride(0)
-    tok = _prof_begin("gemm", 2.0 * M * N * K)
+    keep = []
+    if a_ln is not None:
+        st, cs = a_ln
+        _chk_f32(st, (M, 2), "gemm a_ln stats")
+        _chk_f32(cs, (N,), "gemm a_ln colsum")
+        args.a_stats, args.a_colsum = st.data_ptr(), cs.data_ptr()
+    if resid_ln is not None:
+        st, g, b = resid_ln
+        _chk_f32(st, (M, 2), "gemm resid_ln stats")
+        _chk_f32(g, (N,), "gemm resid_ln gamma")
+        _chk_f32(b, (N,), "gemm resid_ln beta")
+        args.resid_stats, args.resid_gamma, args.resid_beta = st.data_ptr(), g.data_ptr(), b.data_ptr()
+    partials = None
+    if want_stats:
+        partials = torch.empty(((N + 63) // 64, M, 2), dtype=f32, device=a.device)
+        args.stats_out = partials.data_ptr()
+    tok = _prof_begin(tag, 2.0 * M * N * K)
     _l.check(_l.load().hriemo_gemm_bf16(C.byref(args), _stream()), "gemm_bf16")
     _prof_end(tok)
-    return out
+    if not want_stats:
+        return out
+    stats = torch.empty((M, 2), dtype=f32, device=a.device)
+    _l.check(_l.load().hriemo_ln_stats_finalize(partials.data_ptr(), partials.shape[0], M, N, LN_EPS,
+                                                 stats.data_ptr(), _stream()), "ln_stats_finalize")
+    return out, stats
+
+
+def _chk_f32(t: torch.Tensor, shape, name: str) -> None:
+    if not t.is_cuda or t.dtype != f32 or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+        raise _l.HriemoError(f"{name}: expected a contiguous CUDA fp32 tensor of shape {tuple(shape)}, "
+                             f"got {t.dtype} {tuple(t.shape)} on {t.device}")
+
+
+def fold_ln_weight(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
+                   k_pad: Optional[int] = None):
+    """One-time preparation of a Linear that consumes LN(x): returns (w*gamma as bf16 [N, K_pad],
+    colsum [N] fp32, bias + w.beta [N] fp32)."""
+    _chk2d(w, f32, "fold_ln_weight W")
+    N, K = w.shape
+    ld = round_up(K, 8) if k_pad is None else k_pad
+    wf = torch.zeros((N, ld), dtype=bf16, device=w.device)
+    cs = torch.empty((N,), dtype=f32, device=w.device)
+    bf = torch.empty((N,), dtype=f32, device=w.device)
+    _l.check(_l.load().hriemo_fold_ln_weight(w.data_ptr(), w.stride(0), gamma.data_ptr(), beta.data_ptr(), _ptr(bias),
+                                              wf.data_ptr(), ld, cs.data_ptr(), bf.data_ptr(), N, K, _stream()),
+             "fold_ln_weight")
+    return wf, cs, bf
 
 
 # ------------------------------------------------------------------ attention
@@ -185,14 +231,17 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, want_bf1
 # ------------------------------------------------------------------ gate
 def ln_masked_mean(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
                    pad: Optional[torch.Tensor], B: int, T: int, apply_ln: bool = True,
-                   eps: float = LN_EPS) -> torch.Tensor:
-    """x: [B*T, d] bf16 -> pooled [B, d] fp32 = masked_mean_t(LN(x))."""
+                   eps: float = LN_EPS, pre_ln=None) -> torch.Tensor:
+    """x: [B*T, d] bf16 -> pooled [B, d] fp32 = masked_mean_t(LN(x)); with pre_ln = (gamma', beta')
+    x is pre-LayerNorm and the rows are LN(LN'(x))."""
     _chk2d(x, bf16, "ln_masked_mean x")
     d = x.shape[1]
     pooled = torch.empty((B, d), dtype=f32, device=x.device)
     m = _mask_u8(pad, B, T, "ln_masked_mean")
     _l.check(_l.load().hriemo_ln_masked_mean(x.data_ptr(), x.stride(0), _ptr(gamma), _ptr(beta), eps,
-                                              int(apply_ln), _ptr(m), pooled.data_ptr(), d, B, T, d, _stream()),
+                                              int(apply_ln), _ptr(m), pooled.data_ptr(), d, B, T, d,
+                                              _ptr(pre_ln[0]) if pre_ln else None,
+                                              _ptr(pre_ln[1]) if pre_ln else None, _stream()),
              "ln_masked_mean")
     return pooled
 
@@ -219,7 +268,7 @@ def sgemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: i
 
 def gate_blend(a: torch.Tensor, T_a: int, t: torch.Tensor, ln_a, ln_t, w: torch.Tensor, B: int, L: int,
                apply_ln: bool = True, w_is_scalar: bool = False, want_bf16: bool = True,
-               want_f32: bool = False, eps: float = LN_EPS):
+               want_f32: bool = False, eps: float = LN_EPS, pre_ln_a=None, pre_ln_t=None):
     """a: [B*T_a, d] bf16, t: [B*L, d] bf16, w: [B, d] (or [B, 1] scalar gate) fp32.
     Returns (h_bf16|None, h_f32|None, beta [B,1] fp32)."""
     _chk2d(a, bf16, "gate_blend a")
@@ -233,7 +282,10 @@ def gate_blend(a: torch.Tensor, T_a: int, t: torch.Tensor, ln_a, ln_t, w: torch.
     _l.check(_l.load().hriemo_gate_blend(a.data_ptr(), a.stride(0), T_a, t.data_ptr(), t.stride(0), _ptr(ga),
                                           _ptr(ba), _ptr(gt), _ptr(bt), eps, int(apply_ln), w.data_ptr(),
                                           int(w_is_scalar), _ptr(hb), _ptr(hf), d, beta.data_ptr(), B, L, d,
-                                          _stream()), "gate_blend")
+                                          _ptr(pre_ln_a[0]) if pre_ln_a else None,
+                                          _ptr(pre_ln_a[1]) if pre_ln_a else None,
+                                          _ptr(pre_ln_t[0]) if pre_ln_t else None,
+                                          _ptr(pre_ln_t[1]) if pre_ln_t else None, _stream()), "gate_blend")
     return hb, hf, beta
 
 

@@ -30,13 +30,16 @@ class BetaGate(nn.Module):
         if a.T != t.T and a.T < t.T:
             raise RuntimeError(f"BetaGate: audio length {a.T} is shorter than text length {t.T}")
         P = self._prep.get()
-        a_pool = ops.ln_masked_mean(a.x, None, None, mask_a, a.B, a.T, apply_ln=False)  # :81
-        t_pool = ops.ln_masked_mean(t.x, None, None, mask_t, t.B, t.T, apply_ln=False)  # :82
+        pre_a = None if a.ln is None else (a.ln.gamma, a.ln.beta)  # unapplied encoder LayerNorm (engine.LazyLN)
+        pre_t = None if t.ln is None else (t.ln.gamma, t.ln.beta)
+        a_pool = ops.ln_masked_mean(a.x, None, None, mask_a, a.B, a.T, apply_ln=False, pre_ln=pre_a)  # :81
+        t_pool = ops.ln_masked_mean(t.x, None, None, mask_t, t.B, t.T, apply_ln=False, pre_ln=pre_t)  # :82
         g = ops.gate_input(a_pool, t_pool)                                               # :85-87
         hid = ops.sgemm(g, P["w0"], P["b0"], L.ACT_RELU)
         beta = ops.sgemm(hid, P["w2"], P["b2"], L.ACT_SIGMOID)                           # :90  [B,1]
         hb, hf, beta_out = ops.gate_blend(a.x, a.T, t.x, None, None, beta, a.B, t.T, apply_ln=False,
-                                          w_is_scalar=True, want_bf16=want_bf16, want_f32=want_f32)
+                                          w_is_scalar=True, want_bf16=want_bf16, want_f32=want_f32,
+                                          pre_ln_a=pre_a, pre_ln_t=pre_t)
         return E.Seq(hb, a.B, t.T, hf), beta_out
 
     @torch.no_grad()

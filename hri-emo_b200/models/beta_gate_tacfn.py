@@ -41,13 +41,18 @@ class BetaGate(nn.Module):
             # reference :107-116 slices audio to L = T_t and then fails to broadcast
             raise RuntimeError(f"BetaGate: audio length {a.T} is shorter than text length {t.T}")
         P = self._prep.get()
-        a_pool = ops.ln_masked_mean(a.x, *P["norm_a"], mask_a, a.B, a.T)  # :79, :83
-        t_pool = ops.ln_masked_mean(t.x, *P["norm_t"], mask_t, t.B, t.T)  # :80, :84
+        # streams that arrive with an unapplied encoder LayerNorm (engine.LazyLN) get it applied per
+        # row inside the gate kernels, in front of norm_a / norm_t
+        pre_a = None if a.ln is None else (a.ln.gamma, a.ln.beta)
+        pre_t = None if t.ln is None else (t.ln.gamma, t.ln.beta)
+        a_pool = ops.ln_masked_mean(a.x, *P["norm_a"], mask_a, a.B, a.T, pre_ln=pre_a)  # :79, :83
+        t_pool = ops.ln_masked_mean(t.x, *P["norm_t"], mask_t, t.B, t.T, pre_ln=pre_t)  # :80, :84
         g = ops.gate_input(a_pool, t_pool)                                 # :87-89
         hid = ops.sgemm(g, P["w0"], P["b0"], L.ACT_RELU)
         w = ops.sgemm(hid, P["w2"], P["b2"], L.ACT_SIGMOID)                # :92
         hb, hf, beta = ops.gate_blend(a.x, a.T, t.x, P["norm_a"], P["norm_t"], w, a.B, t.T,
-                                      want_bf16=want_bf16, want_f32=want_f32)  # :95-116
+                                      want_bf16=want_bf16, want_f32=want_f32, pre_ln_a=pre_a,
+                                      pre_ln_t=pre_t)  # :95-116
         return E.Seq(hb, a.B, t.T, hf), beta
 
     @torch.no_grad()

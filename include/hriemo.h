@@ -85,6 +85,21 @@ typedef struct hriemo_gemm_args {
   int64_t ldo;
   const void* resid; /* bf16 or f32 [M,N], RESID modes only */
   int64_t ldr;
+  /* Fused LayerNorm (all optional, bf16-output epilogues only).  It replaces the separate
+   * nn.LayerNorm pass after each residual (models/cross_modal_block_tacfn.py:81,92,105,106,118,119):
+   * the pre-LayerNorm sum x is what lives in HBM, and LN is applied where x is consumed.
+   *  - a_stats/a_colsum: the rows of A are pre-LayerNorm; W must already be W*gamma (columnwise),
+   *    bias must be b + W.beta, a_colsum[n] = sum_k W[n,k]; then
+   *      out = rstd[m] * (acc - mean[m] * a_colsum[n]) + bias[n]  ==  LN(A) . W_orig^T + b.
+   *  - resid_stats/resid_gamma/resid_beta: the residual is pre-LayerNorm; LN(resid) is added.
+   *  - stats_out: [ceil(N/64)][M][2] f32, per 64-column slab (sum, sum of squares) of the fp32
+   *    outputs of each row; hriemo_ln_stats_finalize turns them into (mean, rstd). */
+  const float* a_stats;     /* [M][2] (mean, rstd) */
+  const float* a_colsum;    /* [N] */
+  const float* resid_stats; /* [M][2] (mean, rstd) */
+  const float* resid_gamma; /* [N] */
+  const float* resid_beta;  /* [N] */
+  float* stats_out;
 } hriemo_gemm_args;
 
 int hriemo_gemm_bf16(const hriemo_gemm_args* args, void* stream);
@@ -141,13 +156,28 @@ int hriemo_layernorm(const void* x, int32_t x_is_f32, int64_t ldx, const float* 
                      const float* beta, float eps, void* y_bf16, float* y_f32, int64_t ldy,
                      int64_t rows, int32_t d, void* stream);
 
+/* (sum, sum of squares) partials written by hriemo_gemm_bf16 (stats_out) -> stats[m] = (mean,
+ * rstd = 1/sqrt(biased variance + eps)) over d columns. */
+int hriemo_ln_stats_finalize(const float* partials, int32_t n_slabs, int64_t rows, int32_t d, float eps,
+                             float* stats, void* stream);
+
+/* One-time operand preparation for a GEMM that consumes LN(x) given pre-LayerNorm x (a_stats mode):
+ * w_folded[n,k] = bf16(W[n,k] * gamma[k]),  colsum[n] = sum_k float(w_folded[n,k]),
+ * bias_folded[n] = bias[n] + sum_k W[n,k] * beta[k]   (bias may be NULL = 0). */
+int hriemo_fold_ln_weight(const float* W, int64_t ldw, const float* gamma, const float* beta,
+                          const float* bias, void* w_folded_bf16, int64_t ldo, float* colsum,
+                          float* bias_folded, int32_t N, int32_t K, void* stream);
+
 /* -------------------------------------------------------------- β-gate ----
  * models/beta_gate_tacfn.py:79-84 (and models/beta_gate.py:81-82 with
  * apply_ln = 0): pooled[b,:] = masked_mean_t(LN(x[b,t,:])).  x bf16 [B,T,d].
  */
+/* pre_gamma/pre_beta (optional): x is itself a pre-LayerNorm tensor; LN_pre is applied to each row
+ * first (the encoder's last LayerNorm, models/cross_modal_block_tacfn.py:106,119, fused here). */
 int hriemo_ln_masked_mean(const void* x_bf16, int64_t ldx, const float* gamma, const float* beta,
                           float eps, int32_t apply_ln, const uint8_t* pad, float* pooled,
-                          int64_t ld_pooled, int32_t B, int32_t T, int32_t d, void* stream);
+                          int64_t ld_pooled, int32_t B, int32_t T, int32_t d, const float* pre_gamma,
+                          const float* pre_beta, void* stream);
 
 /* models/beta_gate_tacfn.py:87-89: g = [a, t, |a-t|, a*t]  (f32 [B,4d]). */
 int hriemo_gate_input(const float* a_pool, const float* t_pool, float* g, int32_t B, int32_t d,
@@ -164,13 +194,15 @@ int hriemo_sgemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, c
 /* models/beta_gate_tacfn.py:95-116: beta[b] = mean_d w[b,:];
  * h[b,t,:] = w[b,:]*LN_a(a[b,t,:]) + (1-w[b,:])*LN_t(t[b,t,:]) for t < L.
  * With apply_ln = 0 and w_is_scalar = 1 it is the legacy scalar gate
- * (models/beta_gate.py:103-112; beta_out then just copies w).
+ * (models/beta_gate.py:103-112; beta_out then just copies w).  pre_gamma_x / pre_beta_x (optional):
+ * that stream is a pre-LayerNorm tensor and LN_pre is applied to its rows first.
  * a is [B,T_a,d] bf16 (row pitch lda; only the first L rows are read), t is [B,L,d]. */
 int hriemo_gate_blend(const void* a_bf16, int64_t lda, int32_t T_a, const void* t_bf16, int64_t ldt,
                       const float* gamma_a, const float* beta_a, const float* gamma_t,
                       const float* beta_t, float eps, int32_t apply_ln, const float* w,
                       int32_t w_is_scalar, void* h_bf16, float* h_f32, int64_t ldh, float* beta_out,
-                      int32_t B, int32_t L, int32_t d, void* stream);
+                      int32_t B, int32_t L, int32_t d, const float* pre_gamma_a, const float* pre_beta_a,
+                      const float* pre_gamma_t, const float* pre_beta_t, void* stream);
 
 /* Mean over time (UNMASKED) of an f32 [B,L,d] tensor — models/fusion_classifier.py:145. */
 int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d, void* stream);

@@ -123,6 +123,77 @@ def test_gemm_epilogues(cta_pair):
     _report("bias f32", out, acc, 1e-3, 1e-4)
 
 
+@pytest.mark.parametrize("M,N,K,cta_pair", [(1500, 768, 768, 2), (700, 2304, 768, 0), (300, 384, 256, 1), (129, 256, 3072, 2)])
+def test_gemm_fused_layernorm(M, N, K, cta_pair):
+    """The three fused-LayerNorm epilogue features against explicit LayerNorms in fp32:
+    (a) consumer: A is pre-LN, operands folded; (b) residual is pre-LN; (c) row statistics out."""
+    from hriemo import lib as L, ops
+
+    F = torch.nn.functional
+    x = (_rand((M, K), 61, 1.5) + 0.3).to(torch.bfloat16)           # pre-LN rows with a non-zero mean
+    g, b = _rand((K,), 62) * 0.2 + 1.0, _rand((K,), 63) * 0.2
+    w = _rand((N, K), 64, 1.0 / math.sqrt(K))
+    bias = _rand((N,), 65)
+    mean = x.float().mean(1)
+    rstd = torch.rsqrt(x.float().var(1, unbiased=False) + 1e-5)
+    stats = torch.stack([mean, rstd], dim=1).contiguous()
+    wf, cs, bf = ops.fold_ln_weight(w, bias, g, b)
+    assert wf.shape == (N, K) and wf.dtype == torch.bfloat16
+    _report("fold w", wf, w * g, 1e-3, 1e-2)
+    _report("fold colsum", cs, wf.float().sum(1), 1e-3, 1e-4)
+    _report("fold bias", bf, bias + w @ b, 1e-3, 1e-4)
+    ref = F.layer_norm(x.float(), (K,), g, b, 1e-5) @ w.t() + bias
+    out = ops.gemm(x, wf, bf, L.EPI_BIAS_RELU, a_ln=(stats, cs), cta_pair=cta_pair)
+    _report("consumer relu", out, ref.clamp(min=0), 2e-2, 2e-2)
+
+    # (b) + (c): out = A W^T + bias + LN(resid); statistics of out
+    if N % 64 == 0 or True:
+        a = _rand((M, K), 66, dtype=torch.bfloat16)
+        wb = w.to(torch.bfloat16)
+        r = (_rand((M, N), 67, 2.0) - 0.5).to(torch.bfloat16)
+        gr, br = _rand((N,), 68) * 0.2 + 1.0, _rand((N,), 69) * 0.2
+        rmean = r.float().mean(1)
+        rrstd = torch.rsqrt(r.float().var(1, unbiased=False) + 1e-5)
+        rstats = torch.stack([rmean, rrstd], dim=1).contiguous()
+        ref2 = a.float() @ wb.float().t() + bias + F.layer_norm(r.float(), (N,), gr, br, 1e-5)
+        out2, st2 = ops.gemm(a, wb, bias, L.EPI_BIAS_RESID, resid=r, resid_ln=(rstats, gr, br), want_stats=True,
+                             cta_pair=cta_pair)
+        _report("resid-ln", out2, ref2, 2e-2, 1e-2)
+        _report("stats mean", st2[:, 0], ref2.mean(1), 2e-3, 1e-3)
+        _report("stats rstd", st2[:, 1], torch.rsqrt(ref2.var(1, unbiased=False) + 1e-5), 1e-3, 2e-3)
+        # plain residual + statistics
+        out3, st3 = ops.gemm(a, wb, bias, L.EPI_BIAS_RESID, resid=r, want_stats=True, cta_pair=cta_pair)
+        ref3 = a.float() @ wb.float().t() + bias + r.float()
+        _report("resid plain", out3, ref3, 3e-2, 1e-2)
+        _report("stats3 mean", st3[:, 0], ref3.mean(1), 2e-3, 1e-3)
+
+
+def test_gate_kernels_with_pending_layernorm():
+    """ln_masked_mean / gate_blend applied to a stream whose encoder LayerNorm is still pending."""
+    from hriemo import ops
+
+    F = torch.nn.functional
+    B, Ta, L_, d = 3, 70, 20, 768
+    xa = (_rand((B * Ta, d), 71, 2.0) + 0.5).to(torch.bfloat16)
+    xt = (_rand((B * L_, d), 72, 2.0) - 0.5).to(torch.bfloat16)
+    g2a, b2a = _rand((d,), 73) * 0.2 + 1.0, _rand((d,), 74) * 0.2
+    g2t, b2t = _rand((d,), 75) * 0.2 + 1.0, _rand((d,), 76) * 0.2
+    ga, ba = _rand((d,), 77) * 0.2 + 1.0, _rand((d,), 78) * 0.2
+    gt, bt = _rand((d,), 79) * 0.2 + 1.0, _rand((d,), 80) * 0.2
+    pad = _ragged(B, Ta, 81)
+    ya = F.layer_norm(F.layer_norm(xa.float(), (d,), g2a, b2a, 1e-5), (d,), ga, ba, 1e-5).view(B, Ta, d)
+    yt = F.layer_norm(F.layer_norm(xt.float(), (d,), g2t, b2t, 1e-5), (d,), gt, bt, 1e-5).view(B, L_, d)
+    valid = (~pad).float()[:, :, None]
+    pooled_ref = (ya * valid).sum(1) / valid.sum(1).clamp(min=1)
+    pooled = ops.ln_masked_mean(xa, ga, ba, pad, B, Ta, pre_ln=(g2a, b2a))
+    _report("pooled double LN", pooled, pooled_ref, 1e-4, 1e-4)
+    w = torch.sigmoid(_rand((B, d), 82))
+    _, hf, beta = ops.gate_blend(xa, Ta, xt, (ga, ba), (gt, bt), w, B, L_, want_bf16=False, want_f32=True,
+                                 pre_ln_a=(g2a, b2a), pre_ln_t=(g2t, b2t))
+    href = w[:, None, :] * ya[:, :L_] + (1 - w[:, None, :]) * yt
+    _report("blend double LN", hf.view(B, L_, d), href, 1e-4, 1e-4)
+
+
 def test_gemm_strided_views():
     """A as a column slice of a wider buffer, output into a column slice."""
     from hriemo import lib as L, ops
