@@ -60,7 +60,7 @@ struct GemmSmem {
   static constexpr int OUT_OFF = B_OFF + STAGES * B_STAGE_BYTES;   // EW warps x 2 boxes of [32][64] bf16
   // per-column epilogue vectors (bias | colsum or gamma | beta), copied once per CTA when they fit
   static constexpr int VEC_OFF = OUT_OFF + 2 * EW * OUT_BOX_BYTES;
-  static constexpr int VEC_BYTES = (CTAS == 2) ? 32 * 1024 : 0;
+  static constexpr int VEC_BYTES = 0;  // (a 32 KB region cost a pipeline stage: slower overall)
   static constexpr int BAR_OFF = VEC_OFF + VEC_BYTES;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], resid_full[EW warps][2], tmem_ptr
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4 + 2 * EW) * 8 + 16;
@@ -526,7 +526,7 @@ extern "C" int hriemo_gemm_bf16(const hriemo_gemm_args* a, void* stream) {
     static const int env_force = [] { const char* e = getenv("HRIEMO_GEMM_CTAS"); return e ? atoi(e) : 0; }();
     const int force = a->cta_pair ? a->cta_pair : env_force;
     const int64_t pair_tiles = ((a->M + 255) / 256) * (a->N / 256);
-    if (force != 1 && (force == 2 || pair_tiles >= device_sm_count() / 2)) return launch_gemm<256, 4, 2, 8>(*a, s);
+    if (force != 1 && (force == 2 || pair_tiles >= device_sm_count() / 2)) return launch_gemm<256, 5, 2, 8>(*a, s);
     return launch_gemm<256, 4, 1, 4>(*a, s);
   }
   return launch_gemm<128, 6, 1, 4>(*a, s);

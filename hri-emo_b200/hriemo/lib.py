@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhriemo_b200.so")
+# HRIEMO_LIB_PATH: an alternative build of the same library (tools/ A/B experiments only)
+LIB_PATH = os.environ.get("HRIEMO_LIB_PATH") or os.path.join(_HERE, "libhriemo_b200.so")
 
 EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESID, EPI_BIAS_RESID_F32, _EPI_RETIRED, EPI_BIAS_F32 = range(6)
 ACT_NONE, ACT_RELU, ACT_SIGMOID = range(3)
