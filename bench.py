@@ -121,7 +121,7 @@ def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_B = args.cpu_sample
+    sample_B = args.cpu_sample or 96
     times, cores = cpu_forward_timer(wl["T_a"], wl["T_t"], sample_B, args.steps, min(args.warmup, 1))
     total = sum(times)
     value = sample_B * len(times) / total
@@ -144,7 +144,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ns", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (default: workload's)")
-    ap.add_argument("--cpu-sample", type=int, default=16, help="utterances per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="utterances per CPU step (default: 256 for the in-line cpu_baseline = ~15 s of CPU work "
+                         "over 1 warm-up + 2 timed passes; 96 per step for --impl reference)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -193,6 +195,7 @@ def main():
         step()
     sync_all()
     ops.PROFILE = []
+    ops.PROFILE_BYTES = []
     n0 = lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
@@ -203,6 +206,7 @@ def main():
         sync_all()
     launches = lib.launch_count() - n0
     prof, ops.PROFILE = ops.PROFILE, None
+    prof_bytes, ops.PROFILE_BYTES = ops.PROFILE_BYTES, None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -224,9 +228,19 @@ def main():
     attn_tf = a_fl / (a_ms * 1e-3) / 1e12 if a_ms else 0.0
     # SURVEY 8(d) "attention-kernel % of roofline": in-proj + QK^T + PV + out-proj FLOPs over their time
     mha_tf = (a_fl + p_fl) / ((a_ms + p_ms) * 1e-3) / 1e12 if (a_ms + p_ms) else 0.0
+    # DRAM traffic per launch of the dominant kernel comes from the committed ncu capture of this same
+    # command (profiles/r01_traffic.json, written by tools/traffic_from_ncu.py); None if absent
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and args.workload == "ns" and B == WORKLOADS["ns"]["B"]:
+        tj = json.load(open(tpath))
+        traffic, traffic_note = tj["gemm"]["dram_bytes_per_launch"], tj["gemm"]["note"]
+    g_bytes = sum(w for (k, w, a, b) in prof_bytes) / max(g_n, 1) if prof_bytes else None
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05 GEMM, all projections + FFN)",
                 "achieved": gemm_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["tf_sust"],
-                "traffic": None, "launches": g_n, "share_of_step": g_ms / ms_total, "peak_source": peaks["src"] + ", sustained"}
+                "traffic": traffic, "traffic_note": traffic_note, "algorithmic_bytes_per_launch": g_bytes,
+                "flops_per_launch": g_fl / max(g_n, 1), "avg_launch_ms": g_ms / max(g_n, 1),
+                "launches": g_n, "share_of_step": g_ms / ms_total, "peak_source": peaks["src"] + ", sustained"}
     attention_roofline = {"bound": "tensor", "kernel": "attention_fwd3_kernel (tcgen05 QK^T/PV + online softmax)",
                           "achieved": attn_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": attn_tf / peaks["tf_sust"],
                           "launches": a_n, "share_of_step": a_ms / ms_total,
@@ -276,9 +290,11 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        times, cores = cpu_forward_timer(T_a, T_t, args.cpu_sample, 2, 1)
-        cpu_baseline = {"value": args.cpu_sample * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{args.cpu_sample} utterances x {len(times)} passes of the same workload, fp32 torch CPU oracle port"}
+        n_cpu = args.cpu_sample or 256
+        times, cores = cpu_forward_timer(T_a, T_t, n_cpu, 2, 1)
+        cpu_baseline = {"value": n_cpu * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{n_cpu} utterances x {len(times)} timed passes (+1 warm-up) of the same workload "
+                                  f"(T_a={T_a}, T_t={T_t}), fp32, all host threads, oracle port of the reference forward"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

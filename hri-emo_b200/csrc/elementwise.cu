@@ -93,6 +93,27 @@ __device__ __forceinline__ void normalize_row(RowRegs<NV>& r, int d, int lane, c
   }
 }
 
+// (x - mean) * rstd * gamma + beta with the row statistics already known (written by the GEMM
+// epilogue that produced x): no reduction.
+template <int NV>
+__device__ __forceinline__ void affine_row(RowRegs<NV>& r, int d, int lane, const float* gamma, const float* beta,
+                                           float mean, float rstd) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < d) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r.v[i][k] = (r.v[i][k] - mean) * rstd * g[k] + bb[k];
+    }
+  }
+}
+
 template <int NV>
 __device__ __forceinline__ void store_row(const RowRegs<NV>& r, __nv_bfloat16* yb, float* yf, int d, int lane) {
 #pragma unroll
@@ -158,7 +179,8 @@ __global__ void __launch_bounds__(256)
 ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
                       const float* __restrict__ beta, float eps, int apply_ln,
                       const uint8_t* __restrict__ pad, float* __restrict__ pooled, int64_t ld_pooled,
-                      int T, int d, const float* __restrict__ pre_g, const float* __restrict__ pre_b) {
+                      int T, int d, const float* __restrict__ pre_g, const float* __restrict__ pre_b,
+                      const float2* __restrict__ pre_stats) {
   extern __shared__ float part[];  // [8][d]
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,7 +196,14 @@ ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const fl
     ++count;
     RowRegs<NV> r;
     load_row<false, NV>(r, x + (static_cast<int64_t>(b) * T + t) * ldx, d, lane);
-    if (pre_g != nullptr) normalize_row(r, d, lane, pre_g, pre_b, eps);
+    if (pre_g != nullptr) {
+      if (pre_stats != nullptr) {
+        const float2 st = __ldg(pre_stats + static_cast<int64_t>(b) * T + t);
+        affine_row(r, d, lane, pre_g, pre_b, st.x, st.y);
+      } else {
+        normalize_row(r, d, lane, pre_g, pre_b, eps);
+      }
+    }
     if (apply_ln) normalize_row(r, d, lane, gamma, beta, eps);
 #pragma unroll
     for (int i = 0; i < NV; ++i)
@@ -230,7 +259,8 @@ gate_blend_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int T_a,
                   float eps, int apply_ln, const float* __restrict__ w, int w_is_scalar,
                   __nv_bfloat16* __restrict__ hb, float* __restrict__ hf, int64_t ldh,
                   float* __restrict__ beta_out, int B, int L, int d, const float* __restrict__ pga,
-                  const float* __restrict__ pba, const float* __restrict__ pgt, const float* __restrict__ pbt) {
+                  const float* __restrict__ pba, const float* __restrict__ pgt, const float* __restrict__ pbt,
+                  const float2* __restrict__ psa, const float2* __restrict__ pst) {
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= static_cast<int64_t>(B) * L) return;
@@ -239,8 +269,22 @@ gate_blend_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int T_a,
   RowRegs<NV> ra, rt;
   load_row<false, NV>(ra, a + (static_cast<int64_t>(b) * T_a + tt) * lda, d, lane);
   load_row<false, NV>(rt, t + (static_cast<int64_t>(b) * L + tt) * ldt, d, lane);
-  if (pga != nullptr) normalize_row(ra, d, lane, pga, pba, eps);
-  if (pgt != nullptr) normalize_row(rt, d, lane, pgt, pbt, eps);
+  if (pga != nullptr) {
+    if (psa != nullptr) {
+      const float2 st = __ldg(psa + static_cast<int64_t>(b) * T_a + tt);
+      affine_row(ra, d, lane, pga, pba, st.x, st.y);
+    } else {
+      normalize_row(ra, d, lane, pga, pba, eps);
+    }
+  }
+  if (pgt != nullptr) {
+    if (pst != nullptr) {
+      const float2 st = __ldg(pst + static_cast<int64_t>(b) * L + tt);
+      affine_row(rt, d, lane, pgt, pbt, st.x, st.y);
+    } else {
+      normalize_row(rt, d, lane, pgt, pbt, eps);
+    }
+  }
   if (apply_ln) {
     normalize_row(ra, d, lane, ga, ba, eps);
     normalize_row(rt, d, lane, gt, bt, eps);
@@ -382,7 +426,7 @@ extern "C" int hriemo_layernorm(const void* x, int32_t x_is_f32, int64_t ldx, co
 extern "C" int hriemo_ln_masked_mean(const void* x, int64_t ldx, const float* gamma, const float* beta,
                                      float eps, int32_t apply_ln, const uint8_t* pad, float* pooled,
                                      int64_t ld_pooled, int32_t B, int32_t T, int32_t d, const float* pre_gamma,
-                                     const float* pre_beta, void* stream) {
+                                     const float* pre_beta, const float* pre_stats, void* stream) {
   HRIEMO_REQUIRE(x && pooled && (!apply_ln || (gamma && beta)), "ln_masked_mean: null pointer");
   HRIEMO_REQUIRE((pre_gamma == nullptr) == (pre_beta == nullptr) && aligned16(pre_gamma) && aligned16(pre_beta),
                  "ln_masked_mean: pre_gamma / pre_beta go together, 16-byte aligned");
@@ -395,7 +439,7 @@ extern "C" int hriemo_ln_masked_mean(const void* x, int64_t ldx, const float* ga
     cudaFuncSetAttribute(ln_masked_mean_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4);
   HRIEMO_DISPATCH_NV(d, (ln_masked_mean_kernel<NV><<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, apply_ln, pad, pooled, ld_pooled, T, d,
-      pre_gamma, pre_beta)));
+      pre_gamma, pre_beta, reinterpret_cast<const float2*>(pre_stats))));
   return check_launch("ln_masked_mean");
 }
 
@@ -413,7 +457,7 @@ extern "C" int hriemo_gate_blend(const void* a, int64_t lda, int32_t T_a, const 
                                  int32_t w_is_scalar, void* h_bf16, float* h_f32, int64_t ldh,
                                  float* beta_out, int32_t B, int32_t L, int32_t d, const float* pre_gamma_a,
                                  const float* pre_beta_a, const float* pre_gamma_t, const float* pre_beta_t,
-                                 void* stream) {
+                                 const float* pre_stats_a, const float* pre_stats_t, void* stream) {
   HRIEMO_REQUIRE(a && t && w && (h_bf16 || h_f32), "gate_blend: null pointer");
   HRIEMO_REQUIRE((pre_gamma_a == nullptr) == (pre_beta_a == nullptr) && (pre_gamma_t == nullptr) == (pre_beta_t == nullptr) &&
                      aligned16(pre_gamma_a) && aligned16(pre_beta_a) && aligned16(pre_gamma_t) && aligned16(pre_beta_t),
@@ -428,7 +472,8 @@ extern "C" int hriemo_gate_blend(const void* a, int64_t lda, int32_t T_a, const 
   HRIEMO_DISPATCH_NV(d, (gate_blend_kernel<NV><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(a), lda, T_a, static_cast<const __nv_bfloat16*>(t), ldt, gamma_a,
       beta_a, gamma_t, beta_t, eps, apply_ln, w, w_is_scalar, static_cast<__nv_bfloat16*>(h_bf16), h_f32,
-      ldh, beta_out, B, L, d, pre_gamma_a, pre_beta_a, pre_gamma_t, pre_beta_t)));
+      ldh, beta_out, B, L, d, pre_gamma_a, pre_beta_a, pre_gamma_t, pre_beta_t,
+      reinterpret_cast<const float2*>(pre_stats_a), reinterpret_cast<const float2*>(pre_stats_t))));
   return check_launch("gate_blend");
 }
 

@@ -89,7 +89,10 @@ small_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const _
   if (probs)
     for (int i = tid; i < SA_NQ * Tk; i += SA_THREADS) pavg[i] = 0.0f;
 
-  for (int h = 0; h < H; ++h) {
+  // gridDim.z == H: one head per CTA (no head-averaged map to accumulate); else this CTA loops over heads
+  const int h_begin = gridDim.z > 1 ? blockIdx.z : 0;
+  const int h_end = gridDim.z > 1 ? blockIdx.z + 1 : H;
+  for (int h = h_begin; h < h_end; ++h) {
     __syncthreads();
     for (int i = tid; i < nq * dh; i += SA_THREADS) {
       const int qi = i / dh, c = i - qi * dh;
@@ -184,7 +187,7 @@ static int launch_small_attention(const void* q, int64_t ldq, const void* k, int
     if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "small_attention: %s", cudaGetErrorString(e));
     attr = 200 * 1024;
   }
-  dim3 grid(B, (Nq + SA_NQ - 1) / SA_NQ);
+  dim3 grid(B, (Nq + SA_NQ - 1) / SA_NQ, (probs == nullptr && H <= 65535) ? H : 1);
   small_attention_kernel<<<grid, SA_THREADS, smem, s>>>(
       static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k), ldk,
       static_cast<const __nv_bfloat16*>(v), ldv, key_pad, static_cast<__nv_bfloat16*>(out), ldo, probs, H, Nq,

@@ -61,13 +61,13 @@ SIGNATURES = {
     "hriemo_small_attention": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P,
                                           _I32, _I32, _I32, _I32, _I32, _F, _P]),
     "hriemo_layernorm": (C.c_int, [_P, _I32, _I64, _P, _P, _F, _P, _P, _I64, _I64, _I32, _P]),
-    "hriemo_ln_masked_mean": (C.c_int, [_P, _I64, _P, _P, _F, _I32, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P]),
+    "hriemo_ln_masked_mean": (C.c_int, [_P, _I64, _P, _P, _F, _I32, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P]),
     "hriemo_ln_stats_finalize": (C.c_int, [_P, _I32, _I64, _I32, _F, _P, _P]),
     "hriemo_fold_ln_weight": (C.c_int, [_P, _I64, _P, _P, _P, _P, _I64, _P, _P, _I32, _I32, _P]),
     "hriemo_gate_input": (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
     "hriemo_sgemm_f32": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I64, _I64, _I32, _I32, _I32, _P]),
     "hriemo_gate_blend": (C.c_int, [_P, _I64, _I32, _P, _I64, _P, _P, _P, _P, _F, _I32, _P, _I32,
-                                     _P, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+                                     _P, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "hriemo_mean_over_time": (C.c_int, [_P, _P, _I32, _I32, _I32, _P]),
 }
 

@@ -23,6 +23,8 @@ LN_EPS = 1e-5
 # When set to a list (bench.py), every tensor-core launch is bracketed by CUDA events on the
 # launching stream and (kind, algorithmic FLOPs, start, end) is appended.
 PROFILE = None
+# When set to a list, GEMM launches append (tag, algorithmic bytes = (M*K + N*K + M*N [+ M*N residual]) * 2, None, None).
+PROFILE_BYTES = None
 
 
 def _prof_begin(kind: str, work: float):
@@ -126,6 +128,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogu
         partials = torch.empty(((N + 63) // 64, M, 2), dtype=f32, device=a.device)
         args.stats_out = partials.data_ptr()
     tok = _prof_begin(tag, 2.0 * M * N * K)
+    if PROFILE_BYTES is not None:
+        osz = 4 if f32_out else 2
+        PROFILE_BYTES.append((tag, 2.0 * (M * K + N * K) + osz * M * N * (2 if resid is not None else 1), None, None))
     _l.check(_l.load().hriemo_gemm_bf16(C.byref(args), _stream()), "gemm_bf16")
     _prof_end(tok)
     if not want_stats:
@@ -232,8 +237,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, want_bf1
 def ln_masked_mean(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
                    pad: Optional[torch.Tensor], B: int, T: int, apply_ln: bool = True,
                    eps: float = LN_EPS, pre_ln=None) -> torch.Tensor:
-    """x: [B*T, d] bf16 -> pooled [B, d] fp32 = masked_mean_t(LN(x)); with pre_ln = (gamma', beta')
-    x is pre-LayerNorm and the rows are LN(LN'(x))."""
+    """x: [B*T, d] bf16 -> pooled [B, d] fp32 = masked_mean_t(LN(x)); with pre_ln = (gamma', beta'[, stats'])
+    x is pre-LayerNorm and the rows are LN(LN'(x)) (stats' [B*T, 2] spares the kernel LN's statistics)."""
     _chk2d(x, bf16, "ln_masked_mean x")
     d = x.shape[1]
     pooled = torch.empty((B, d), dtype=f32, device=x.device)
@@ -241,7 +246,8 @@ def ln_masked_mean(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optiona
     _l.check(_l.load().hriemo_ln_masked_mean(x.data_ptr(), x.stride(0), _ptr(gamma), _ptr(beta), eps,
                                               int(apply_ln), _ptr(m), pooled.data_ptr(), d, B, T, d,
                                               _ptr(pre_ln[0]) if pre_ln else None,
-                                              _ptr(pre_ln[1]) if pre_ln else None, _stream()),
+                                              _ptr(pre_ln[1]) if pre_ln else None,
+                                              _ptr(pre_ln[2]) if pre_ln and len(pre_ln) > 2 else None, _stream()),
              "ln_masked_mean")
     return pooled
 
@@ -285,7 +291,10 @@ def gate_blend(a: torch.Tensor, T_a: int, t: torch.Tensor, ln_a, ln_t, w: torch.
                                           _ptr(pre_ln_a[0]) if pre_ln_a else None,
                                           _ptr(pre_ln_a[1]) if pre_ln_a else None,
                                           _ptr(pre_ln_t[0]) if pre_ln_t else None,
-                                          _ptr(pre_ln_t[1]) if pre_ln_t else None, _stream()), "gate_blend")
+                                          _ptr(pre_ln_t[1]) if pre_ln_t else None,
+                                          _ptr(pre_ln_a[2]) if pre_ln_a and len(pre_ln_a) > 2 else None,
+                                          _ptr(pre_ln_t[2]) if pre_ln_t and len(pre_ln_t) > 2 else None,
+                                          _stream()), "gate_blend")
     return hb, hf, beta
 
 

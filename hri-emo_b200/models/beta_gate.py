@@ -30,8 +30,8 @@ class BetaGate(nn.Module):
         if a.T != t.T and a.T < t.T:
             raise RuntimeError(f"BetaGate: audio length {a.T} is shorter than text length {t.T}")
         P = self._prep.get()
-        pre_a = None if a.ln is None else (a.ln.gamma, a.ln.beta)  # unapplied encoder LayerNorm (engine.LazyLN)
-        pre_t = None if t.ln is None else (t.ln.gamma, t.ln.beta)
+        pre_a = None if a.ln is None else (a.ln.gamma, a.ln.beta, a.ln.stats)  # unapplied encoder LayerNorm (engine.LazyLN)
+        pre_t = None if t.ln is None else (t.ln.gamma, t.ln.beta, t.ln.stats)
         a_pool = ops.ln_masked_mean(a.x, None, None, mask_a, a.B, a.T, apply_ln=False, pre_ln=pre_a)  # :81
         t_pool = ops.ln_masked_mean(t.x, None, None, mask_t, t.B, t.T, apply_ln=False, pre_ln=pre_t)  # :82
         g = ops.gate_input(a_pool, t_pool)                                               # :85-87

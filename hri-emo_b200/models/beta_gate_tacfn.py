@@ -43,8 +43,8 @@ class BetaGate(nn.Module):
         P = self._prep.get()
         # streams that arrive with an unapplied encoder LayerNorm (engine.LazyLN) get it applied per
         # row inside the gate kernels, in front of norm_a / norm_t
-        pre_a = None if a.ln is None else (a.ln.gamma, a.ln.beta)
-        pre_t = None if t.ln is None else (t.ln.gamma, t.ln.beta)
+        pre_a = None if a.ln is None else (a.ln.gamma, a.ln.beta, a.ln.stats)
+        pre_t = None if t.ln is None else (t.ln.gamma, t.ln.beta, t.ln.stats)
         a_pool = ops.ln_masked_mean(a.x, *P["norm_a"], mask_a, a.B, a.T, pre_ln=pre_a)  # :79, :83
         t_pool = ops.ln_masked_mean(t.x, *P["norm_t"], mask_t, t.B, t.T, pre_ln=pre_t)  # :80, :84
         g = ops.gate_input(a_pool, t_pool)                                 # :87-89

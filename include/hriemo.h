@@ -173,11 +173,13 @@ int hriemo_fold_ln_weight(const float* W, int64_t ldw, const float* gamma, const
  * apply_ln = 0): pooled[b,:] = masked_mean_t(LN(x[b,t,:])).  x bf16 [B,T,d].
  */
 /* pre_gamma/pre_beta (optional): x is itself a pre-LayerNorm tensor; LN_pre is applied to each row
- * first (the encoder's last LayerNorm, models/cross_modal_block_tacfn.py:106,119, fused here). */
+ * first (the encoder's last LayerNorm, models/cross_modal_block_tacfn.py:106,119, fused here).
+ * pre_stats (optional, [B*T][2] = (mean, rstd) as written by hriemo_ln_stats_finalize) spares the
+ * kernel the statistics of LN_pre. */
 int hriemo_ln_masked_mean(const void* x_bf16, int64_t ldx, const float* gamma, const float* beta,
                           float eps, int32_t apply_ln, const uint8_t* pad, float* pooled,
                           int64_t ld_pooled, int32_t B, int32_t T, int32_t d, const float* pre_gamma,
-                          const float* pre_beta, void* stream);
+                          const float* pre_beta, const float* pre_stats, void* stream);
 
 /* models/beta_gate_tacfn.py:87-89: g = [a, t, |a-t|, a*t]  (f32 [B,4d]). */
 int hriemo_gate_input(const float* a_pool, const float* t_pool, float* g, int32_t B, int32_t d,
@@ -195,14 +197,16 @@ int hriemo_sgemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, c
  * h[b,t,:] = w[b,:]*LN_a(a[b,t,:]) + (1-w[b,:])*LN_t(t[b,t,:]) for t < L.
  * With apply_ln = 0 and w_is_scalar = 1 it is the legacy scalar gate
  * (models/beta_gate.py:103-112; beta_out then just copies w).  pre_gamma_x / pre_beta_x (optional):
- * that stream is a pre-LayerNorm tensor and LN_pre is applied to its rows first.
+ * that stream is a pre-LayerNorm tensor and LN_pre is applied to its rows first; pre_stats_a is indexed
+ * [b*T_a + t], pre_stats_t [b*L + t] (optional, as for hriemo_ln_masked_mean).
  * a is [B,T_a,d] bf16 (row pitch lda; only the first L rows are read), t is [B,L,d]. */
 int hriemo_gate_blend(const void* a_bf16, int64_t lda, int32_t T_a, const void* t_bf16, int64_t ldt,
                       const float* gamma_a, const float* beta_a, const float* gamma_t,
                       const float* beta_t, float eps, int32_t apply_ln, const float* w,
                       int32_t w_is_scalar, void* h_bf16, float* h_f32, int64_t ldh, float* beta_out,
                       int32_t B, int32_t L, int32_t d, const float* pre_gamma_a, const float* pre_beta_a,
-                      const float* pre_gamma_t, const float* pre_beta_t, void* stream);
+                      const float* pre_gamma_t, const float* pre_beta_t, const float* pre_stats_a,
+                      const float* pre_stats_t, void* stream);
 
 /* Mean over time (UNMASKED) of an f32 [B,L,d] tensor — models/fusion_classifier.py:145. */
 int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d, void* stream);

@@ -192,6 +192,15 @@ def test_gate_kernels_with_pending_layernorm():
                                  pre_ln_a=(g2a, b2a), pre_ln_t=(g2t, b2t))
     href = w[:, None, :] * ya[:, :L_] + (1 - w[:, None, :]) * yt
     _report("blend double LN", hf.view(B, L_, d), href, 1e-4, 1e-4)
+    # same with the statistics of the pending LayerNorm supplied (as the GEMM epilogue writes them)
+    def stats(x):
+        return torch.stack([x.float().mean(1), torch.rsqrt(x.float().var(1, unbiased=False) + 1e-5)], dim=1).contiguous()
+    sa, st_ = stats(xa), stats(xt)
+    pooled2 = ops.ln_masked_mean(xa, ga, ba, pad, B, Ta, pre_ln=(g2a, b2a, sa))
+    _report("pooled double LN (given stats)", pooled2, pooled_ref, 1e-4, 1e-4)
+    _, hf2, _ = ops.gate_blend(xa, Ta, xt, (ga, ba), (gt, bt), w, B, L_, want_bf16=False, want_f32=True,
+                               pre_ln_a=(g2a, b2a, sa), pre_ln_t=(g2t, b2t, st_))
+    _report("blend double LN (given stats)", hf2.view(B, L_, d), href, 1e-4, 1e-4)
 
 
 def test_gemm_strided_views():
