@@ -95,17 +95,20 @@ __device__ __forceinline__ void max4(float (&m4)[4], const uint32_t (&v)[32]) {
   }
 }
 
-// p = 2^(s*sc + neg_m) for 32 scores -> 16 packed bf16 pairs; four independent row-sum chains.
+// p = 2^(s*sc + neg_m) for 32 scores -> 16 packed bf16 pairs; the scale/shift and the row sums run on
+// packed fp32 pairs (FFMA2 / FADD2: half the instructions of the scalar form), two sum chains.
 __device__ __forceinline__ void exp_pack(const uint32_t (&v)[32], float sc, float neg_m, float (&l4)[4],
                                          uint32_t (&pk)[16]) {
+  const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(neg_m, neg_m);
+  float2 la = make_float2(l4[0], l4[2]), lb = make_float2(l4[1], l4[3]);
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), sc, neg_m));
-    const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), sc, neg_m));
-    l4[i & 1] += e0;
-    l4[2 + (i & 1)] += e1;
-    pk[i] = pack_bf16(e0, e1);
+    const float2 x = ffma2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
+    const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+    if (i & 1) lb = fadd2(lb, e); else la = fadd2(la, e);
+    pk[i] = pack_bf16(e.x, e.y);
   }
+  l4[0] = la.x; l4[2] = la.y; l4[1] = lb.x; l4[3] = lb.y;
 }
 
 template <int DH>

@@ -283,7 +283,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         tmem_ld32(t_row + s * 64, v[0]);
         if (two) tmem_ld32(t_row + s * 64 + 32, v[1]);
         tmem_ld_wait();
-        float s1 = 0.0f, s2 = 0.0f;  // per-row partial LayerNorm statistics of this slab's outputs
+        float2 s1_2 = make_float2(0.0f, 0.0f), s2_2 = make_float2(0.0f, 0.0f);  // per-row partial LayerNorm statistics
         uint32_t buf = 0;
         if (bf16_out) {
           buf = my_stage + (slab_ctr & 1u) * OUT_BOX_BYTES;
@@ -298,30 +298,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int hf = 0; hf < 2; ++hf) {
           if (hf == 1 && !two) break;
           const int nn = n + hf * 32;
-          float f[32];
+          // all elementwise math on packed fp32 pairs (FFMA2): f2[i] = columns nn + 2i, nn + 2i + 1
+          float2 f2[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[hf][i]);
+          for (int i = 0; i < 16; ++i) f2[i] = make_float2(__uint_as_float(v[hf][2 * i]), __uint_as_float(v[hf][2 * i + 1]));
           if (p.a_stats != nullptr) {
+            // rstd * (acc - mean * colsum) + bias  ==  fma(rstd, acc, fma(-rstd * mean, colsum, bias))
+            const float2 k1 = make_float2(a_rstd, a_rstd), k2 = make_float2(-a_rstd * a_mean, -a_rstd * a_mean);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 c4 = vec4(1, p.a_colsum, nn + i * 4);
-              f[i * 4 + 0] = a_rstd * fmaf(-a_mean, c4.x, f[i * 4 + 0]);
-              f[i * 4 + 1] = a_rstd * fmaf(-a_mean, c4.y, f[i * 4 + 1]);
-              f[i * 4 + 2] = a_rstd * fmaf(-a_mean, c4.z, f[i * 4 + 2]);
-              f[i * 4 + 3] = a_rstd * fmaf(-a_mean, c4.w, f[i * 4 + 3]);
+              float4 b4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+              if (p.bias != nullptr) b4 = vec4(0, p.bias, nn + i * 4);
+              f2[2 * i] = ffma2(k1, f2[2 * i], ffma2(k2, make_float2(c4.x, c4.y), make_float2(b4.x, b4.y)));
+              f2[2 * i + 1] = ffma2(k1, f2[2 * i + 1], ffma2(k2, make_float2(c4.z, c4.w), make_float2(b4.z, b4.w)));
             }
-          }
-          if (p.bias != nullptr) {
+          } else if (p.bias != nullptr) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 b4 = vec4(0, p.bias, nn + i * 4);
-              f[i * 4 + 0] += b4.x; f[i * 4 + 1] += b4.y; f[i * 4 + 2] += b4.z; f[i * 4 + 3] += b4.w;
+              f2[2 * i] = fadd2(f2[2 * i], make_float2(b4.x, b4.y));
+              f2[2 * i + 1] = fadd2(f2[2 * i + 1], make_float2(b4.z, b4.w));
             }
           }
           if (p.epilogue == HRIEMO_EPI_BIAS_RELU) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+            for (int i = 0; i < 16; ++i) f2[i] = make_float2(fmaxf(f2[i].x, 0.0f), fmaxf(f2[i].y, 0.0f));
           } else if (tma_resid) {
+            const float2 rs = make_float2(r_scale, r_scale), rh = make_float2(r_shift, r_shift);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint32_t slot = static_cast<uint32_t>((hf * 4 + i) ^ (lane & 7));
@@ -330,18 +334,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                            : "=r"(r4.x), "=r"(r4.y), "=r"(r4.z), "=r"(r4.w)
                            : "r"(buf + lane * 128 + slot * 16)
                            : "memory");
-              float r[8] = {bf16_lo(r4.x), bf16_hi(r4.x), bf16_lo(r4.y), bf16_hi(r4.y),
-                            bf16_lo(r4.z), bf16_hi(r4.z), bf16_lo(r4.w), bf16_hi(r4.w)};
+              float2 r[4] = {make_float2(bf16_lo(r4.x), bf16_hi(r4.x)), make_float2(bf16_lo(r4.y), bf16_hi(r4.y)),
+                             make_float2(bf16_lo(r4.z), bf16_hi(r4.z)), make_float2(bf16_lo(r4.w), bf16_hi(r4.w))};
               if (p.resid_stats != nullptr) {
                 const float4 g0 = vec4(1, p.resid_gamma, nn + i * 8), g1 = vec4(1, p.resid_gamma, nn + i * 8 + 4);
                 const float4 b0 = vec4(2, p.resid_beta, nn + i * 8), b1 = vec4(2, p.resid_beta, nn + i * 8 + 4);
-                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int k = 0; k < 8; ++k) r[k] = fmaf(fmaf(r[k], r_scale, r_shift), g[k], bb[k]);
+                r[0] = ffma2(ffma2(r[0], rs, rh), make_float2(g0.x, g0.y), make_float2(b0.x, b0.y));
+                r[1] = ffma2(ffma2(r[1], rs, rh), make_float2(g0.z, g0.w), make_float2(b0.z, b0.w));
+                r[2] = ffma2(ffma2(r[2], rs, rh), make_float2(g1.x, g1.y), make_float2(b1.x, b1.y));
+                r[3] = ffma2(ffma2(r[3], rs, rh), make_float2(g1.z, g1.w), make_float2(b1.z, b1.w));
               }
 #pragma unroll
-              for (int k = 0; k < 8; ++k) f[i * 8 + k] += r[k];
+              for (int k = 0; k < 4; ++k) f2[i * 4 + k] = fadd2(f2[i * 4 + k], r[k]);
             }
           } else if (p.epilogue == HRIEMO_EPI_BIAS_RESID_F32 && row_ok) {
             const float4* rp =
@@ -349,14 +353,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 r4 = __ldg(rp + i);
-              f[i * 4 + 0] += r4.x; f[i * 4 + 1] += r4.y; f[i * 4 + 2] += r4.z; f[i * 4 + 3] += r4.w;
+              f2[2 * i] = fadd2(f2[2 * i], make_float2(r4.x, r4.y));
+              f2[2 * i + 1] = fadd2(f2[2 * i + 1], make_float2(r4.z, r4.w));
             }
           }
           if (p.stats_out != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              s1 += f[i];
-              s2 = fmaf(f[i], f[i], s2);
+            for (int i = 0; i < 16; ++i) {
+              s1_2 = fadd2(s1_2, f2[i]);
+              s2_2 = ffma2(f2[i], f2[i], s2_2);
+            }
+          }
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { f[2 * i] = f2[i].x; f[2 * i + 1] = f2[i].y; }
+          if (hf == 0 && tma_resid && lane == 0) {
+            // Residual box of this warp's NEXT slab (same tile, or its first slab of this CTA's next
+            // tile) -> the idle staging buffer.  Issued here, half a slab after the store that last
+            // read that buffer, so that store has normally drained and the load has a full slab of
+            // lead time instead of sitting on the critical path.
+            int64_t nt_ = tile;
+            int ns_ = s + 1;
+            if (sl + 1 >= SLABS || n0 + ns_ * 64 >= p.N) { nt_ = tile + tile_step; ns_ = slab0; }
+            if (nt_ < p.num_tiles && has_slab(nt_, ns_)) {
+              bulk_wait_read<0>();
+              prefetch_resid(nt_, ns_, slab_ctr + 1);
             }
           }
           if (bf16_out) {
@@ -377,23 +398,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
         }
         if (p.stats_out != nullptr && row_ok)  // [slab][row]: consecutive lanes -> consecutive 8 bytes
-          p.stats_out[static_cast<int64_t>(n >> 6) * p.M + m] = make_float2(s1, s2);
+          p.stats_out[static_cast<int64_t>(n >> 6) * p.M + m] = make_float2(s1_2.x + s1_2.y, s2_2.x + s2_2.y);
         if (bf16_out) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tm_c, buf, n, static_cast<int>(m_tile) + quad * 32);
             bulk_commit();
-            if (tma_resid) {
-              // next slab of this warp: same tile, or its first slab of this CTA's next tile
-              int64_t nt_ = tile;
-              int ns_ = s + 1;
-              if (sl + 1 >= SLABS || n0 + ns_ * 64 >= p.N) { nt_ = tile + tile_step; ns_ = slab0; }
-              if (nt_ < p.num_tiles && has_slab(nt_, ns_)) {
-                bulk_wait_read<1>();  // the store that last read the other buffer has drained
-                prefetch_resid(nt_, ns_, slab_ctr + 1);
-              }
-            }
           }
           ++slab_ctr;
         }
