@@ -64,11 +64,18 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None   # wall-clock bounds of the timed region (mark_start / mark_end)
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -77,7 +84,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([c.strip() for c in line.split(",")] + [time.time()])
 
     def __exit__(self, *a):
         if self.proc:
@@ -86,6 +93,13 @@ class ClockSampler:
             self.t.join(timeout=2)
 
     def summary(self):
+        # the sampler is started before the warm-up (nvidia-smi takes a few hundred ms to come up);
+        # keep the rows read inside the timed region, or failing that the ones closest after its start
+        rows = [r for r in self.rows if len(r) >= 8]
+        if self.t0 is not None:
+            inside = [r for r in rows if self.t0 <= r[-1] <= (self.t1 or 1e30) + 0.25]
+            rows = inside or [r for r in rows if r[-1] >= self.t0 - 0.25][:3] or rows[-2:]
+        self.rows = rows
         sm = sorted(int(float(r[0])) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
@@ -191,19 +205,21 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sync_all()
-    ops.PROFILE = []
-    ops.PROFILE_BYTES = []
-    n0 = lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
+        for _ in range(max(args.warmup, 3)):
+            step()
+        sync_all()
+        ops.PROFILE = []
+        ops.PROFILE_BYTES = []
+        n0 = lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clk.mark_start()
         e0.record()
         for _ in range(args.steps):
             step()
         e1.record()
         sync_all()
+        clk.mark_end()
     launches = lib.launch_count() - n0
     prof, ops.PROFILE = ops.PROFILE, None
     prof_bytes, ops.PROFILE_BYTES = ops.PROFILE_BYTES, None
