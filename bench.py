@@ -34,6 +34,8 @@ WORKLOADS = {
     "ns": dict(T_a=500, T_t=64, B=4096, desc="FusionWithEmotionDecoder fwd, B=4096/GPU, T_a=500, T_t=64, d=768, H=8, N_e=4, 2+2 layers"),
     # BASELINE.json configs[1]
     "cfg2": dict(T_a=300, T_t=50, B=4096, desc="FusionWithEmotionDecoder fwd, B=4096/GPU, T_a=300, T_t=50, d=768, H=8, N_e=4, 2+2 layers"),
+    # BASELINE.json config 4's longest sequences
+    "long": dict(T_a=1000, T_t=64, B=2048, desc="FusionWithEmotionDecoder fwd, B=2048/GPU, T_a=1000, T_t=64, d=768, H=8, N_e=4, 2+2 layers"),
 }
 METRIC = "seq-level utterances/sec"
 UNIT = "utterances/s"

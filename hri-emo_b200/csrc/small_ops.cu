@@ -175,6 +175,23 @@ small_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const _
   }
 }
 
+// ------------------------------------------------------------------ post-path outputs
+// probs = sigmoid(logits); decisions = probs >= threshold[class] (per-class calibrated thresholds,
+// or 0.5 when none are given: equivalent to logit > 0 up to the tie at 0).
+__global__ void emotion_outputs_kernel(const float* __restrict__ logits, const float* __restrict__ thresholds,
+                                       float* __restrict__ probs, uint8_t* __restrict__ decisions, int64_t total,
+                                       int n_classes) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float pr = 1.0f / (1.0f + expf(-logits[i]));
+    if (probs != nullptr) probs[i] = pr;
+    if (decisions != nullptr) {
+      const float th = thresholds != nullptr ? thresholds[i % n_classes] : 0.5f;
+      decisions[i] = pr >= th ? 1 : 0;   // NaN logits -> NaN prob -> 0, as numpy's >= does
+    }
+  }
+}
+
 static int launch_small_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                                   int64_t ldv, const uint8_t* key_pad, void* out, int64_t ldo, float* probs,
                                   int B, int H, int Nq, int Tk, int dh, float scale, cudaStream_t s) {
@@ -223,6 +240,18 @@ extern "C" int hriemo_small_attention(const void* q, int64_t ldq, const void* k,
   HRIEMO_REQUIRE(ldk % 8 == 0 && (reinterpret_cast<uintptr_t>(k) & 15u) == 0, "small_attention: K misaligned");
   return launch_small_attention(q, ldq, k, ldk, v, ldv, key_pad, out_bf16, ldo, probs, B, H, Nq, Tk, dh, scale,
                                 static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int hriemo_emotion_outputs(const float* logits, const float* thresholds, float* probs,
+                                      uint8_t* decisions, int64_t B, int32_t n_classes, void* stream) {
+  HRIEMO_REQUIRE(logits && (probs || decisions) && B >= 0 && n_classes > 0, "emotion_outputs: bad argument");
+  if (B == 0) return HRIEMO_OK;
+  const int64_t total = B * n_classes;
+  int64_t grid = (total + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  emotion_outputs_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, thresholds, probs, decisions, total, n_classes);
+  return check_launch("emotion_outputs");
 }
 
 extern "C" int hriemo_attention_probs(const void* q, int64_t ldq, const void* k, int64_t ldk,

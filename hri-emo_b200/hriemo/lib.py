@@ -69,6 +69,7 @@ SIGNATURES = {
     "hriemo_gate_blend": (C.c_int, [_P, _I64, _I32, _P, _I64, _P, _P, _P, _P, _F, _I32, _P, _I32,
                                      _P, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "hriemo_mean_over_time": (C.c_int, [_P, _P, _I32, _I32, _I32, _P]),
+    "hriemo_emotion_outputs": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
 }
 
 _lib = None

@@ -304,3 +304,19 @@ def mean_over_time(x: torch.Tensor, B: int, L: int) -> torch.Tensor:
     out = torch.empty((B, d), dtype=f32, device=x.device)
     _l.check(_l.load().hriemo_mean_over_time(x.data_ptr(), out.data_ptr(), B, L, d, _stream()), "mean_over_time")
     return out
+
+
+def emotion_outputs(logits: torch.Tensor, thresholds: Optional[torch.Tensor] = None):
+    """Post-path outputs of the reference's inference script (mosei_eval_infer.py:237-270):
+    (probs = sigmoid(logits) fp32 [B, C], decisions = probs >= thresholds[c] as bool [B, C])."""
+    _chk2d(logits, f32, "emotion_outputs logits")
+    if not logits.is_contiguous():
+        logits = logits.contiguous()
+    B, Cn = logits.shape
+    if thresholds is not None:
+        _chk_f32(thresholds, (Cn,), "emotion_outputs thresholds")
+    probs = torch.empty_like(logits)
+    dec = torch.empty((B, Cn), dtype=torch.uint8, device=logits.device)
+    _l.check(_l.load().hriemo_emotion_outputs(logits.data_ptr(), _ptr(thresholds), probs.data_ptr(), dec.data_ptr(),
+                                               B, Cn, _stream()), "emotion_outputs")
+    return probs, dec.view(torch.bool)

@@ -208,6 +208,13 @@ int hriemo_gate_blend(const void* a_bf16, int64_t lda, int32_t T_a, const void* 
                       const float* pre_gamma_t, const float* pre_beta_t, const float* pre_stats_a,
                       const float* pre_stats_t, void* stream);
 
+/* Post-path outputs of the inference script (scripts/infer/mosei_eval_infer.py:237-270,
+ * scripts/analysis/mosei_summary_metrics.py:51): probs = sigmoid(logits) [B, n_classes] f32 and
+ * decisions = probs >= thresholds[class] (uint8; thresholds NULL = 0.5 for every class).
+ * Either output may be NULL. */
+int hriemo_emotion_outputs(const float* logits, const float* thresholds, float* probs, uint8_t* decisions,
+                           int64_t B, int32_t n_classes, void* stream);
+
 /* Mean over time (UNMASKED) of an f32 [B,L,d] tensor — models/fusion_classifier.py:145. */
 int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d, void* stream);
 

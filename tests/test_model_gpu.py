@@ -238,3 +238,47 @@ def test_forward_from_host_equals_device_forward(name, slab):
     assert lo.device.type == "cpu"
     # same kernels on the same rows; only the slab boundaries differ
     assert torch.equal(lo, ref[0].cpu()) and torch.equal(be, ref[1].cpu()) and torch.equal(z, ref[2].cpu())
+
+
+def test_full_size_properties_north_star():
+    """BASELINE.json's full size (B = 4096, T_a = 500, T_t = 64, default model), where the oracle is too
+    slow for every sample: size-independent properties of the path plus an oracle spot check.
+      (1) utterances are independent: permuting the batch permutes the outputs bit for bit
+          (this crosses slab boundaries: B*T_a = 2.05 M rows = two slabs);
+      (2) a PAD tail behind a mask changes nothing that is not masked: extending T_a by 12 PAD frames
+          leaves logits / beta within the parity tolerance;
+      (3) eight samples drawn from the batch agree with the float64 CPU oracle."""
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    B, T_a, T_t = 4096, 500, 64
+    torch.manual_seed(1234)
+    m = FusionWithEmotionDecoder().eval()
+    sd = O.cast_state(m.state_dict(), torch.float64)
+    m = m.to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(4321)
+    h_a = torch.randn(B, T_a, 768, generator=g, device=DEV)
+    h_t = torch.randn(B, T_t, 768, generator=g, device=DEV)
+    gc = torch.Generator().manual_seed(99)
+    m_a, m_t = O.ragged_masks(B, T_a, gc).to(DEV), O.ragged_masks(B, T_t, gc).to(DEV)
+    lo, be, z = m(h_a, h_t, m_a, m_t)
+    assert torch.isfinite(lo).all() and torch.isfinite(be).all() and torch.isfinite(z).all()
+
+    perm = torch.randperm(B, generator=gc).to(DEV)
+    lo_p, be_p, z_p = m(h_a[perm], h_t[perm], m_a[perm], m_t[perm])
+    assert torch.equal(lo_p, lo[perm]) and torch.equal(be_p, be[perm]) and torch.equal(z_p, z[perm])
+    del lo_p, be_p, z_p
+
+    sub = slice(0, 512)  # (2) on one slab's worth keeps the test's memory modest
+    pad = 12
+    h_a2 = torch.cat([h_a[sub], torch.randn(512, pad, 768, generator=g, device=DEV) * 50.0], dim=1)
+    m_a2 = torch.cat([m_a[sub], torch.ones(512, pad, dtype=torch.bool, device=DEV)], dim=1)
+    lo2, be2, _ = m(h_a2, h_t[sub], m_a2, m_t[sub])
+    assert (lo2 - lo[sub]).abs().max().item() <= LOGIT_TOL and (be2 - be[sub]).abs().max().item() <= BETA_TOL
+
+    idx = torch.tensor([0, 1, 777, 2047, 2048, 3000, 4094, 4095])
+    lo_o, be_o, z_o = O.fusion_with_emotion_decoder(sd, h_a[idx].double().cpu(), h_t[idx].double().cpu(),
+                                                    m_a[idx].cpu(), m_t[idx].cpu(), n_heads=8)
+    assert (lo[idx].cpu() - lo_o).abs().max().item() <= LOGIT_TOL
+    assert (be[idx].cpu() - be_o).abs().max().item() <= BETA_TOL
+    assert (z[idx].cpu() - z_o).abs().max().item() <= Z_TOL
+    assert torch.equal(be[idx].cpu() > 0.5, be_o > 0.5)

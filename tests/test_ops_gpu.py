@@ -451,3 +451,21 @@ def test_small_attention(B, H, Nq, Tk, dh, masked):
     _report("small_attention probs", probs, pref, 1e-5, 1e-4)
     p2 = ops.attention_probs(q.view(B * Nq, d), kv[:, :d], pad, B, H, Nq, Tk, dh)
     _report("attention_probs", p2, pref, 1e-5, 1e-4)
+
+
+def test_emotion_outputs_sigmoid_and_thresholds():
+    """sigmoid -> y_prob and the per-class threshold compare of the reference's inference / metrics
+    scripts (mosei_eval_infer.py:237-270, mosei_summary_metrics.py:51)."""
+    from hriemo import ops
+
+    lo = _rand((1000, 6), 91, 2.0)
+    lo[3, 2] = float("nan")
+    th = torch.tensor([0.5, 0.3, 0.7, 0.45, 0.5, 0.62], device=DEV)
+    probs, dec = ops.emotion_outputs(lo, th)
+    ref = torch.sigmoid(lo.double())
+    _report("probs", probs, ref, 1e-6, 1e-6)
+    clear = (ref - th.double()).abs() > 1e-6
+    assert torch.equal(dec[clear], (ref >= th.double())[clear]) and not dec[3, 2]
+    _, dec0 = ops.emotion_outputs(lo[:, :4].contiguous())
+    lo4 = lo[:, :4]
+    assert torch.equal(dec0[lo4 != 0], (lo4 > 0)[lo4 != 0])   # default threshold 0.5 == logit > 0
