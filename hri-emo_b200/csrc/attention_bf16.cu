@@ -55,6 +55,19 @@ struct Attn3Smem {
   static int dyn_bytes(int n_kv) { return DYN_OFF + 2 * n_kv * A3_BKV * 4 + 2 * n_kv * 4 + 1024; }
 };
 
+// Pipeline trace (tools/attn_trace.py builds with -DHRIEMO_ATTN_TRACE): CTA 0 records clock64() at fixed
+// points of its first 64 steps, per role (MMA issuer 0/1, softmax warpgroup 0/1).  Compiled out otherwise.
+#ifdef HRIEMO_ATTN_TRACE
+__device__ long long* g_attn_trace = nullptr;
+#define ATRACE(role, step, ev)                                                                       \
+  do {                                                                                               \
+    if (blockIdx.x == 0 && g_attn_trace != nullptr && (step) < 64u)                                  \
+      g_attn_trace[((role) * 64 + (step)) * 8 + (ev)] = clock64();                                    \
+  } while (0)
+#else
+#define ATRACE(role, step, ev) do {} while (0)
+#endif
+
 struct Attn3Params {
   const uint8_t* key_pad;
   __nv_bfloat16* out;
@@ -236,8 +249,10 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       auto issue_s = [&]() {
         const uint32_t ks = s_g % KS, kpar = (s_g / KS) & 1u;
         const uint32_t qslot = t * 2 + (qcnt & 1u);
+        ATRACE(t, s_g, 4);
         if (s_act && s_j == 0) mbar_wait(b_qfull + qslot * 8, (qcnt >> 1) & 1u);
         mbar_wait(b_kfull + ks * 8, kpar);
+        ATRACE(t, s_g, 5);
         if (s_act) {
           tc_fence_after_sync();
           const uint64_t q_desc = umma_desc_sw128(sQ + qslot * L::Q_TILE);
@@ -250,6 +265,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           }
           umma_commit(b_sfull + (t * 2 + (s_g & 1u)) * 8);
           umma_commit(b_kempty + ks * 8);
+          ATRACE(t, s_g, 6);
           if (s_j == n_kv - 1) ++qcnt;  // the Q buffer is released by the warpgroup after its epilogue
         } else {
           mbar_arrive(b_kempty + ks * 8);
@@ -269,11 +285,14 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       bool pv_act = tile_active(pv_item);
       for (uint32_t g = 0; g < total; ++g) {
         const uint32_t vs = g % KS, vpar = (g / KS) & 1u;
+        ATRACE(t, g, 0);
         mbar_wait(b_vfull + vs * 8, vpar);
+        ATRACE(t, g, 1);
         if (pv_act) {
           const int rem = p.Tk - pv_j * A3_BKV;  // keys left from this step on (> 0)
           const uint32_t slot = t * 2 + (pcnt & 1u);
           mbar_wait(b_pfull + slot * 8, (pcnt >> 1) & 1u);
+          ATRACE(t, g, 2);
           ++pcnt;
           tc_fence_after_sync();
           const uint64_t v_desc = v_desc0 + ((vs * L::V_STAGE) >> 4);
@@ -286,6 +305,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           }
           umma_commit(b_pvdone + slot * 8);
           umma_commit(b_vempty + vs * 8);
+          ATRACE(t, g, 3);
         } else {
           mbar_arrive(b_vempty + vs * 8);
         }
@@ -356,14 +376,17 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         const bool two = rem > 32;                   // second 32-key chunk holds a valid key
         const bool masked = flags[j] != 0;           // warp-uniform
         const float* cap_j = caps + j * A3_BKV;
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 0);
         mbar_wait(b_sfull + (wg * 2 + sbuf) * 8, (sbuf ? scnt1 : scnt0) & 1u);
         if (sbuf) ++scnt1; else ++scnt0;
         tc_fence_after_sync();
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 1);
 
         uint32_t va[32], vb[32];
         tmem_ld32(t_s, va);
         if (two) tmem_ld32(t_s + 32, vb);
         tmem_ld_wait();
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 2);
         if (masked) {
           apply_caps(va, cap_j);
           if (two) apply_caps(vb, cap_j + 32);
@@ -398,6 +421,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           }
         }
         const float neg_m = (m_run == -INFINITY) ? 0.0f : -m_run;
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 3);
 
         // ---- p = 2^(s*scale - m), row sum, bf16 P into the first 32 columns of this S buffer
         float l4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -409,10 +433,13 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           tmem_st16(t_s + 16, pk);
         }
         l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 4);
         tmem_st_wait();
         tc_fence_before_sync();
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 5);
         mbar_arrive(b_pfull + (wg * 2 + (pv_issued & 1u)) * 8);
         ++pv_issued;
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 6);
       }
 
       // ---- epilogue: O / l -> bf16, staged in this item's (now dead) Q buffer and written with one
@@ -449,6 +476,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
         mbar_arrive(b_qempty + qslot * 8);
       }
+      if (wg_tid == 0) ATRACE(2 + wg, g + n_kv - 1, 7);
       ++qcnt_w;
     }
   }
@@ -519,6 +547,13 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
 }
 
 }  // namespace hriemo
+
+#ifdef HRIEMO_ATTN_TRACE
+extern "C" int hriemo_debug_set_attn_trace(long long* buf) {  // trace builds only; not part of the ABI
+  cudaError_t e = cudaMemcpyToSymbol(hriemo::g_attn_trace, &buf, sizeof(buf));
+  return e == cudaSuccess ? 0 : -2;
+}
+#endif
 
 extern "C" int hriemo_attention_bf16(const hriemo_attn_args* a, void* stream) {
   using namespace hriemo;

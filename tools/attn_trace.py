@@ -8,7 +8,8 @@ TRACE_SO = os.path.join(ROOT, "tools", "_build", "libhriemo_trace.so")
 
 def build_trace():
     os.makedirs(os.path.dirname(TRACE_SO), exist_ok=True)
-    cmd = [B._nvcc(), *B.NVCC_FLAGS, "-DHRIEMO_ATTN_TRACE", *[os.path.join(B.CSRC, s) for s in B.SOURCES], "-o", TRACE_SO]
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    cmd = [B._nvcc(), *B.NVCC_FLAGS, "-DHRIEMO_ATTN_TRACE", *extra, *[os.path.join(B.CSRC, s) for s in B.SOURCES], "-o", TRACE_SO]
     subprocess.run(cmd, check=True)
 
 def main():
@@ -32,21 +33,18 @@ def main():
     t = trace.view(4, 64, 8).cpu()
     t0 = int(t[t > 0].min())
     names = {0: "MMA0", 1: "MMA1", 2: "WG0", 3: "WG1"}
-    ev = {0: ["pre_sfree", "sfree_ok", "S_issued", "vfull_ok", "pfull_ok", "PV_issued"],
-          2: ["pre_sfull", "sfull_ok", "S_loaded", "exp_done", "pv_ok", "P_handed", "pre_epi", "epi_done"]}
-    for role in range(4):
-        print(f"== {names[role]} (cycles since first event; deltas in brackets)")
+    ev = {0: ["top", "vfull_ok", "pfull_ok", "PV_issued", "S_top", "kfull_ok", "S_issued"],
+          2: ["pre_sfull", "sfull_ok", "S_loaded", "max_done", "exp_done", "st_done", "handed", "epi_done"]}
+    for role in (0, 2, 3):
+        print(f"== {names[role]} (cycles since the first event; [delta to the previous event of the step])")
         labels = ev[0] if role < 2 else ev[2]
-        prev_end = None
-        for step in range(24):
+        for step in range(4, 28):
             row = t[role, step]
             if int(row.max()) == 0: continue
-            vals = [int(x) - t0 if int(x) > 0 else None for x in row]
-            parts = []
-            last = None
-            for lab, v in zip(labels, vals):
-                if v is None: continue
-                parts.append(f"{lab}={v}" + (f"(+{v - last})" if last is not None else ""))
+            pairs = sorted((int(x) - t0, lab) for lab, x in zip(labels, row) if int(x) > 0)
+            parts, last = [], None
+            for v, lab in pairs:
+                parts.append(f"{lab}={v}" + (f"[+{v - last}]" if last is not None else ""))
                 last = v
             print(f"  step {step:2d}: " + " ".join(parts))
 
