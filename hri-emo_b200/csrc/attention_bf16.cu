@@ -118,8 +118,8 @@ __device__ __forceinline__ void exp_pack(const uint32_t (&v)[32], float sc, floa
   for (int i = 0; i < 16; ++i) {
     const float2 x = ffma2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
     const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-    if (i & 1) lb = fadd2(lb, e); else la = fadd2(la, e);
     pk[i] = pack_bf16(e.x, e.y);
+    if (i & 1) lb = fadd2(lb, e); else la = fadd2(la, e);
   }
   l4[0] = la.x; l4[2] = la.y; l4[1] = lb.x; l4[3] = lb.y;
 }
@@ -341,6 +341,9 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       }
     };
     uint32_t g = 0;              // flat step index of this CTA
+#ifndef HRIEMO_ATTN_NO_PINGPONG
+    if (wg == 1) asm volatile("bar.arrive %0, 256;" ::"r"(3) : "memory");   // warpgroup 0 takes the first turn
+#endif
     uint32_t qcnt_w = 0;         // items this tile has processed -> which Q buffer it used
     int cur_b = -1;
     const uint32_t n_items_u = static_cast<uint32_t>(p.n_items);
@@ -351,7 +354,15 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       const int b = static_cast<int>(bh / static_cast<uint32_t>(p.H));
       const int h = static_cast<int>(bh - static_cast<uint32_t>(b) * static_cast<uint32_t>(p.H));
       const int q0 = qp * 2 * A3_BQ + wg * A3_BQ;
-      if (q0 >= p.Tq) continue;  // this warpgroup's tile does not exist for this item
+      if (q0 >= p.Tq) {  // this warpgroup's tile does not exist for this item: only keep the exp turn-taking alive
+#ifndef HRIEMO_ATTN_NO_PINGPONG
+        for (int j = 0; j < n_kv; ++j) {
+          asm volatile("bar.sync %0, 256;" ::"r"(3 + wg) : "memory");
+          asm volatile("bar.arrive %0, 256;" ::"r"(4 - wg) : "memory");
+        }
+#endif
+        continue;
+      }
 
       if (b != cur_b) {
         asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
@@ -423,7 +434,13 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         const float neg_m = (m_run == -INFINITY) ? 0.0f : -m_run;
         if (wg_tid == 0) ATRACE(2 + wg, g + j, 3);
 
-        // ---- p = 2^(s*scale - m), row sum, bf16 P into the first 32 columns of this S buffer
+        // ---- p = 2^(s*scale - m), row sum, bf16 P into the first 32 columns of this S buffer.
+        // The two warpgroups take turns here (named barriers 3 / 4): left alone they run in lock-step
+        // and their exponentials collide on the quarter-rate XU pipe (profiles/r01_attention_v8_pipeline_trace);
+        // in turns, one warpgroup's exp phase overlaps the other's waits, loads and row maxima.
+#ifndef HRIEMO_ATTN_NO_PINGPONG
+        asm volatile("bar.sync %0, 256;" ::"r"(3 + wg) : "memory");
+#endif
         float l4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         uint32_t pk[16];
         exp_pack(va, sc, neg_m, l4, pk);
@@ -433,6 +450,9 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           tmem_st16(t_s + 16, pk);
         }
         l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+#ifndef HRIEMO_ATTN_NO_PINGPONG
+        asm volatile("bar.arrive %0, 256;" ::"r"(4 - wg) : "memory");   // the other warpgroup's turn
+#endif
         if (wg_tid == 0) ATRACE(2 + wg, g + j, 4);
         tmem_st_wait();
         tc_fence_before_sync();
