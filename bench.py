@@ -37,8 +37,17 @@ WORKLOADS = {
     # BASELINE.json config 4's longest sequences
     "long": dict(T_a=1000, T_t=64, B=2048, desc="FusionWithEmotionDecoder fwd, B=2048/GPU, T_a=1000, T_t=64, d=768, H=8, N_e=4, 2+2 layers"),
 }
+# BASELINE.json config 3: MOSEI wrapper (d_audio 74, d_text 300 -> d_model 256, 4 heads, 6 emotion queries)
+WORKLOADS["cfg3"] = dict(T_a=300, T_t=128, B=8192, mosei=True,
+                         desc="MoseiFusionWithEmotionDecoder fwd, B=8192/GPU, T_a=300, T_t=128, d_audio=74, d_text=300, d=256, H=4, N_e=6, 2+2 layers")
 METRIC = "seq-level utterances/sec"
 UNIT = "utterances/s"
+
+
+def lo_shape_bytes(model, B):
+    """bytes read back per e2e step: logits [B,N_e] + beta [B,1] + z [B,N_e,d], fp32"""
+    dec = model.backbone.emotion_decoder if hasattr(model, "backbone") else model.emotion_decoder
+    return B * (dec.num_emotions + 1 + dec.num_emotions * dec.d_model) * 4
 
 
 def load_peaks():
@@ -50,10 +59,10 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
 
 
-def flops_per_utt(T_a, T_t, d=768, n_e=4, L_f=2, L_d=2, h_beta=256, ffn_dec=2048):
-    """SURVEY sec. 8(d) closed form (matmul FLOPs, 2*MAC)."""
+def flops_per_utt(T_a, T_t, d=768, n_e=4, L_f=2, L_d=2, h_beta=256, ffn_dec=2048, d_a=0, d_t=0):
+    """SURVEY sec. 8(d) closed form (matmul FLOPs, 2*MAC); d_a / d_t > 0 adds the MOSEI input projections."""
     L = T_t
-    f = L_f * (32 * d * d * (T_a + T_t) + 4 * d * (T_a + T_t) ** 2)
+    f = L_f * (32 * d * d * (T_a + T_t) + 4 * d * (T_a + T_t) ** 2) + 2 * (T_a * d_a + T_t * d_t) * d
     f += 10 * d * h_beta
     f += L_d * (12 * n_e * d * d + 4 * L * d * d + 4 * n_e * n_e * d + 4 * n_e * L * d + 4 * n_e * d * ffn_dec)
     return f + 2 * n_e * d
@@ -112,22 +121,28 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------- CPU arm
-def cpu_forward_timer(T_a, T_t, sample_B, steps, warmup):
+def cpu_forward_timer(T_a, T_t, sample_B, steps, warmup, mosei=False):
     """The reference algorithm on the host cores: the oracle port (torch CPU fp32, all threads).
     The reference itself is a Python package that cannot travel to the GPU box."""
     import hriemo_oracle as O
     from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+    from models.mosei_fusion_with_emotion_decoder import MoseiFusionWithEmotionDecoder
 
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(1234)
-    sd = {k: v.detach() for k, v in FusionWithEmotionDecoder().state_dict().items()}
+    m = MoseiFusionWithEmotionDecoder(74, 300, d_model=256, num_emotions=6, n_heads=4) if mosei else FusionWithEmotionDecoder()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    d_a, d_t = (74, 300) if mosei else (768, 768)
     g = torch.Generator().manual_seed(1234)
-    h_a, h_t = torch.randn(sample_B, T_a, 768, generator=g), torch.randn(sample_B, T_t, 768, generator=g)
+    h_a, h_t = torch.randn(sample_B, T_a, d_a, generator=g), torch.randn(sample_B, T_t, d_t, generator=g)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            O.fusion_with_emotion_decoder(sd, h_a, h_t, None, None, n_heads=8)
+            if mosei:
+                O.mosei_fusion_with_emotion_decoder(sd, h_a, h_t, None, None, n_heads=4)
+            else:
+                O.fusion_with_emotion_decoder(sd, h_a, h_t, None, None, n_heads=8)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     return times, torch.get_num_threads()
@@ -138,7 +153,7 @@ def run_reference_arm(args, wl):
     if rank != 0:
         return
     sample_B = args.cpu_sample or 96
-    times, cores = cpu_forward_timer(wl["T_a"], wl["T_t"], sample_B, args.steps, min(args.warmup, 1))
+    times, cores = cpu_forward_timer(wl["T_a"], wl["T_t"], sample_B, args.steps, min(args.warmup, 1), bool(wl.get("mosei")))
     total = sum(times)
     value = sample_B * len(times) / total
     sample = f"{sample_B} utterances per step of the same workload (T_a={wl['T_a']}, T_t={wl['T_t']}), fp32, oracle port of the reference forward"
@@ -190,10 +205,17 @@ def main():
     B, T_a, T_t = wl["B"], wl["T_a"], wl["T_t"]
 
     torch.manual_seed(1234)
-    model = FusionWithEmotionDecoder().eval().to(dev)
+    mosei = bool(wl.get("mosei"))
+    if mosei:
+        from models.mosei_fusion_with_emotion_decoder import MoseiFusionWithEmotionDecoder
+        model = MoseiFusionWithEmotionDecoder(74, 300, d_model=256, num_emotions=6, n_heads=4).eval().to(dev)
+        d_a, d_t = 74, 300
+    else:
+        model = FusionWithEmotionDecoder().eval().to(dev)
+        d_a = d_t = 768
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    h_a = torch.randn(B, T_a, 768, generator=g, device=dev)
-    h_t = torch.randn(B, T_t, 768, generator=g, device=dev)
+    h_a = torch.randn(B, T_a, d_a, generator=g, device=dev)
+    h_t = torch.randn(B, T_t, d_t, generator=g, device=dev)
 
     def step():
         logits, beta, _ = model(h_a, h_t)
@@ -265,7 +287,7 @@ def main():
                           "mha_incl_projections": {"achieved": mha_tf, "frac": mha_tf / peaks["tf_sust"], "unit": "TFLOP/s",
                                                    "launches": a_n + p_n, "share_of_step": (a_ms + p_ms) / ms_total,
                                                    "definition": "SURVEY 8(d): (in-proj + QK^T + PV + out-proj FLOPs) / their kernel time"}}
-    fpu = flops_per_utt(T_a, T_t)
+    fpu = (flops_per_utt(T_a, T_t, d=256, n_e=6, h_beta=128, d_a=74, d_t=300) if mosei else flops_per_utt(T_a, T_t))
     path_tf = fpu * value / world / 1e12
 
     # ---- end to end from pinned host memory
@@ -276,12 +298,12 @@ def main():
             avail = psutil.virtual_memory().available
         except Exception:
             avail = 64 << 30
-        bytes_per_utt = (T_a + T_t) * 768 * 4
+        bytes_per_utt = (T_a * d_a + T_t * d_t) * 4
         Be = B
         while Be > 256 and Be * bytes_per_utt * world * 1.5 > avail * 0.5:
             Be //= 2
-        ha_h = torch.empty((Be, T_a, 768), dtype=torch.float32).pin_memory()
-        ht_h = torch.empty((Be, T_t, 768), dtype=torch.float32).pin_memory()
+        ha_h = torch.empty((Be, T_a, d_a), dtype=torch.float32).pin_memory()
+        ht_h = torch.empty((Be, T_t, d_t), dtype=torch.float32).pin_memory()
         ha_h.normal_(generator=torch.Generator().manual_seed(99 + rank))
         ht_h.normal_(generator=torch.Generator().manual_seed(199 + rank))
 
@@ -302,14 +324,14 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * Be * n_e2e / float(dt.item()), "unit": UNIT, "batch_per_gpu": Be,
-               "h2d_bytes_per_step": Be * bytes_per_utt, "d2h_bytes_per_step": Be * (4 + 1 + 4 * 768) * 4,
+               "h2d_bytes_per_step": Be * bytes_per_utt, "d2h_bytes_per_step": int(lo_shape_bytes(model, Be)),
                "api": "hriemo.pipeline.forward_from_host(model, pinned h_a, pinned h_t) -> host logits/beta/z"}
         del ha_h, ht_h
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         n_cpu = args.cpu_sample or 256
-        times, cores = cpu_forward_timer(T_a, T_t, n_cpu, 2, 1)
+        times, cores = cpu_forward_timer(T_a, T_t, n_cpu, 2, 1, mosei)
         cpu_baseline = {"value": n_cpu * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{n_cpu} utterances x {len(times)} timed passes (+1 warm-up) of the same workload "
                                   f"(T_a={T_a}, T_t={T_t}), fp32, all host threads, oracle port of the reference forward"}
