@@ -74,6 +74,7 @@ struct Attn3Params {
   int64_t ldo;
   int B, H, Tq, Tk;
   int n_kv, n_qp;
+  int contiguous;   // item -> CTA assignment, see the kernel
   int64_t n_items;
   float scale_log2;
 };
@@ -158,6 +159,16 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_kv = p.n_kv;
+  // Work items (utterance, head, query-tile pair) are dealt to the CTAs either round-robin or in
+  // contiguous runs (p.contiguous).  Measured on B200: short key sequences (<= 6 steps per item,
+  // where the per-item work is small and consecutive items share K / V and the key mask) gain 5-9 %
+  // from contiguous runs, long ones lose 3-8 % (neighbouring CTAs then no longer stream the same
+  // K / V tiles at the same time), so the launcher picks by the number of key steps.
+  const uint32_t n_items_all = static_cast<uint32_t>(p.n_items);
+  const uint32_t per_cta = (n_items_all + gridDim.x - 1) / gridDim.x;
+  const uint32_t item_first = p.contiguous ? blockIdx.x * per_cta : blockIdx.x;
+  const uint32_t item_stride = p.contiguous ? 1u : gridDim.x;
+  const uint32_t item_last = p.contiguous ? min(item_first + per_cta, n_items_all) : n_items_all;  // exclusive
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -190,8 +201,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     if (lane == 0) {
       uint32_t qcnt[2] = {0, 0};  // Q loads issued per query tile -> buffer and phase
       uint32_t g = 0;             // flat step index -> K/V ring stage and phase
-      const uint32_t n_items_u = static_cast<uint32_t>(p.n_items);
-      for (uint32_t item = blockIdx.x; item < n_items_u; item += gridDim.x) {
+      for (uint32_t item = item_first; item < item_last; item += item_stride) {
         const uint32_t bh = item / static_cast<uint32_t>(p.n_qp);
         const int qp = static_cast<int>(item - bh * static_cast<uint32_t>(p.n_qp));
         const int b = static_cast<int>(bh / static_cast<uint32_t>(p.H));
@@ -233,8 +243,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       const int t = (warp == 1) ? 0 : 1;
       constexpr uint32_t idesc_s = umma_idesc_bf16(A3_BQ, A3_BKV);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(A3_BQ, DH) | kUmmaBMajorMN;
-      const uint32_t n_items = static_cast<uint32_t>(p.n_items);
-      const uint32_t my_items = (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x;
+      const uint32_t my_items = item_last > item_first ? (item_last - item_first + item_stride - 1) / item_stride : 0u;
       const uint32_t total = my_items * static_cast<uint32_t>(n_kv);  // flat steps of this CTA
       const uint32_t tile_tmem = tmem_base + t * TILE_COLS;
       const uint64_t k_desc0 = umma_desc_sw128(sK);
@@ -243,7 +252,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         return t == 0 || static_cast<int>(item % static_cast<uint32_t>(p.n_qp)) * 2 * A3_BQ + A3_BQ < p.Tq;
       };
       // ---- S cursor (two steps ahead of the PV cursor)
-      uint32_t s_g = 0, s_item = blockIdx.x, qcnt = 0;
+      uint32_t s_g = 0, s_item = item_first, qcnt = 0;
       int s_j = 0;
       bool s_act = tile_active(s_item);
       auto issue_s = [&]() {
@@ -273,14 +282,14 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         ++s_g;
         if (++s_j == n_kv) {
           s_j = 0;
-          s_item += gridDim.x;
-          s_act = s_item < n_items && tile_active(s_item);
+          s_item += item_stride;
+          s_act = s_item < item_last && tile_active(s_item);
         }
       };
       if (total > 0) issue_s();
       if (total > 1) issue_s();
       // ---- PV cursor
-      uint32_t pcnt = 0, pv_item = blockIdx.x;
+      uint32_t pcnt = 0, pv_item = item_first;
       int pv_j = 0;
       bool pv_act = tile_active(pv_item);
       for (uint32_t g = 0; g < total; ++g) {
@@ -312,8 +321,8 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if (s_g < total) issue_s();  // S(g+2) reuses the S buffer whose P was just consumed
         if (++pv_j == n_kv) {
           pv_j = 0;
-          pv_item += gridDim.x;
-          pv_act = pv_item < n_items && tile_active(pv_item);
+          pv_item += item_stride;
+          pv_act = pv_item < item_last && tile_active(pv_item);
         }
       }
     }
@@ -346,9 +355,8 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 #endif
     uint32_t qcnt_w = 0;         // items this tile has processed -> which Q buffer it used
     int cur_b = -1;
-    const uint32_t n_items_u = static_cast<uint32_t>(p.n_items);
 
-    for (uint32_t item = blockIdx.x; item < n_items_u; item += gridDim.x, g += n_kv) {
+    for (uint32_t item = item_first; item < item_last; item += item_stride, g += n_kv) {
       const uint32_t bh = item / static_cast<uint32_t>(p.n_qp);
       const int qp = static_cast<int>(item - bh * static_cast<uint32_t>(p.n_qp));
       const int b = static_cast<int>(bh / static_cast<uint32_t>(p.H));
@@ -364,7 +372,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         continue;
       }
 
-      if (b != cur_b) {
+      if (cur_b < 0 || (b != cur_b && p.key_pad != nullptr)) {   // without a mask the caps only depend on Tk
         asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
         for (int j = wg_tid; j < n_kv; j += 128) flags[j] = 0;
         asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
@@ -549,6 +557,7 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
   p.n_kv = n_kv;
   p.n_qp = (a.Tq + 2 * A3_BQ - 1) / (2 * A3_BQ);
   p.n_items = static_cast<int64_t>(a.B) * a.H * p.n_qp;
+  p.contiguous = n_kv <= 6 ? 1 : 0;
   if (p.n_items * n_kv >= (1ll << 31))
     return set_error(HRIEMO_ERR_INVALID, "attention: too many (item, step) pairs for 32-bit step counters");
   p.scale_log2 = a.scale * 1.4426950408889634f;
