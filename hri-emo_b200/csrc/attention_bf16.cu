@@ -576,13 +576,12 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
   if (p.n_items * n_kv >= (1ll << 31))
     return set_error(HRIEMO_ERR_INVALID, "attention: too many (item, step) pairs for 32-bit step counters");
   p.scale_log2 = a.scale * 1.4426950408889634f;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t attr_done = 0;
+  if (device_needs_attr(&attr_done)) {
     cudaError_t e = cudaFuncSetAttribute(attention_fwd3_kernel<DH>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess)
       return set_error(HRIEMO_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   const int64_t sms = device_sm_count();
   const unsigned grid = static_cast<unsigned>(p.n_items < sms ? p.n_items : sms);

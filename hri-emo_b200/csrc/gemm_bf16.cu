@@ -466,13 +466,12 @@ static int launch_gemm(const hriemo_gemm_args& a, cudaStream_t stream) {
   const int64_t num_m_blocks = (a.M + BM * CTAS - 1) / (BM * CTAS);
   p.num_tiles = num_m_blocks * p.num_n_blocks;
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t attr_done = 0;
+  if (device_needs_attr(&attr_done)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, CTAS, EW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
     if (e != cudaSuccess)
       return set_error(HRIEMO_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   const int64_t owners = device_sm_count() / CTAS;  // CTAs, or CTA pairs
   const unsigned grid = static_cast<unsigned>(p.num_tiles < owners ? p.num_tiles : owners) * CTAS;

@@ -88,6 +88,15 @@ int make_tmap_bf16_3d_plain(CUtensorMap* map, const void* base, const uint64_t d
   return HRIEMO_OK;
 }
 
+bool device_needs_attr(uint64_t* done) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (*done & bit) return false;
+  *done |= bit;   // benign race: setting the attribute twice is harmless
+  return true;
+}
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {

@@ -26,6 +26,10 @@ int make_tmap_bf16_3d_plain(CUtensorMap* map, const void* base, const uint64_t d
 
 int device_sm_count();
 
+// Function attributes (opt-in shared memory) are per device: `done` is a per-kernel bitmask of the
+// devices the attribute has been set on; returns true when the current device still needs it.
+bool device_needs_attr(uint64_t* done);
+
 #define HRIEMO_REQUIRE(cond, ...)                                      \
   do {                                                                 \
     if (!(cond)) return ::hriemo::set_error(HRIEMO_ERR_INVALID, __VA_ARGS__); \

@@ -197,12 +197,11 @@ static int launch_small_attention(const void* q, int64_t ldq, const void* k, int
                                   int B, int H, int Nq, int Tk, int dh, float scale, cudaStream_t s) {
   const size_t smem = sizeof(float) * (static_cast<size_t>(SA_NQ) * dh + static_cast<size_t>(SA_NQ) * Tk * (probs ? 2 : 1));
   if (smem > 200 * 1024) return set_error(HRIEMO_ERR_INVALID, "small_attention: Tk=%d too long", Tk);
-  static size_t attr = 48 * 1024;
-  if (smem > attr) {
+  static uint64_t attr_done = 0;
+  if (smem > 48 * 1024 && device_needs_attr(&attr_done)) {
     cudaError_t e = cudaFuncSetAttribute(small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          200 * 1024);
     if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "small_attention: %s", cudaGetErrorString(e));
-    attr = 200 * 1024;
   }
   dim3 grid(B, (Nq + SA_NQ - 1) / SA_NQ, (probs == nullptr && H <= 65535) ? H : 1);
   small_attention_kernel<<<grid, SA_THREADS, smem, s>>>(
