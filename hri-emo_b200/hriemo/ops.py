@@ -45,6 +45,21 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_tensor_device(fn):
+    """Run the wrapper with the CUDA device of its first tensor argument current (the C ABI launches
+    on the current device and stream; a model on cuda:1 must not launch on cuda:0)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = next((a.device for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def _chk2d(t: torch.Tensor, dtype, name: str) -> None:
     if not t.is_cuda:
         raise _l.HriemoError(f"{name}: expected a CUDA tensor (no CPU fallback exists)")
@@ -72,6 +87,7 @@ def round_up(x: int, m: int) -> int:
 
 
 # ------------------------------------------------------------------ cast
+@_on_tensor_device
 def cast_bf16(x: torch.Tensor, ld_out: Optional[int] = None) -> torch.Tensor:
     """fp32 [rows, cols] -> bf16 [rows, ld_out] (zero-padded columns)."""
     _chk2d(x, f32, "cast_bf16")
@@ -84,6 +100,7 @@ def cast_bf16(x: torch.Tensor, ld_out: Optional[int] = None) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------ GEMM
+@_on_tensor_device
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int = _l.EPI_BIAS,
          resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
          cta_pair: int = 0, a_ln=None, resid_ln=None, want_stats: bool = False, tag: str = "gemm"):
@@ -147,6 +164,7 @@ def _chk_f32(t: torch.Tensor, shape, name: str) -> None:
                              f"got {t.dtype} {tuple(t.shape)} on {t.device}")
 
 
+@_on_tensor_device
 def fold_ln_weight(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
                    k_pad: Optional[int] = None):
     """One-time preparation of a Linear that consumes LN(x): returns (w*gamma as bf16 [N, K_pad],
@@ -164,6 +182,7 @@ def fold_ln_weight(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.T
 
 
 # ------------------------------------------------------------------ attention
+@_on_tensor_device
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Optional[torch.Tensor],
               B: int, H: int, Tq: int, Tk: int, dh: int) -> torch.Tensor:
     """q: [B*Tq, >=H*dh] view, k / v: [B*Tk, >=H*dh] views (column slices of a packed projection are
@@ -189,6 +208,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Option
     return out
 
 
+@_on_tensor_device
 def attention_probs(q: torch.Tensor, k: torch.Tensor, key_pad: Optional[torch.Tensor], B: int, H: int,
                     Tq: int, Tk: int, dh: int) -> torch.Tensor:
     """Head-averaged softmax probabilities [B, Tq, Tk] fp32 (return_attention path)."""
@@ -202,6 +222,7 @@ def attention_probs(q: torch.Tensor, k: torch.Tensor, key_pad: Optional[torch.Te
     return probs
 
 
+@_on_tensor_device
 def small_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Optional[torch.Tensor],
                     B: int, H: int, Nq: int, Tk: int, dh: int, want_probs: bool = False):
     """Decoder attention: q [B*Nq, *], k/v [B*Tk, *] row-major views.  Returns (out bf16, probs|None)."""
@@ -218,6 +239,7 @@ def small_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: 
 
 
 # ------------------------------------------------------------------ LayerNorm
+@_on_tensor_device
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, want_bf16: bool = True,
               want_f32: bool = False, eps: float = LN_EPS):
     """x: [rows, d] bf16 or f32 (residual already added).  Returns (y_bf16|None, y_f32|None)."""
@@ -234,6 +256,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, want_bf1
 
 
 # ------------------------------------------------------------------ gate
+@_on_tensor_device
 def ln_masked_mean(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
                    pad: Optional[torch.Tensor], B: int, T: int, apply_ln: bool = True,
                    eps: float = LN_EPS, pre_ln=None) -> torch.Tensor:
@@ -252,6 +275,7 @@ def ln_masked_mean(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optiona
     return pooled
 
 
+@_on_tensor_device
 def gate_input(a_pool: torch.Tensor, t_pool: torch.Tensor) -> torch.Tensor:
     B, d = a_pool.shape
     g = torch.empty((B, 4 * d), dtype=f32, device=a_pool.device)
@@ -260,6 +284,7 @@ def gate_input(a_pool: torch.Tensor, t_pool: torch.Tensor) -> torch.Tensor:
     return g
 
 
+@_on_tensor_device
 def sgemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = _l.ACT_NONE) -> torch.Tensor:
     """fp32 CUDA-core GEMM: act(a[M,K] @ w[N,K]^T + bias)."""
     _chk2d(a, f32, "sgemm A")
@@ -272,6 +297,7 @@ def sgemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: i
     return out
 
 
+@_on_tensor_device
 def gate_blend(a: torch.Tensor, T_a: int, t: torch.Tensor, ln_a, ln_t, w: torch.Tensor, B: int, L: int,
                apply_ln: bool = True, w_is_scalar: bool = False, want_bf16: bool = True,
                want_f32: bool = False, eps: float = LN_EPS, pre_ln_a=None, pre_ln_t=None):
@@ -298,6 +324,7 @@ def gate_blend(a: torch.Tensor, T_a: int, t: torch.Tensor, ln_a, ln_t, w: torch.
     return hb, hf, beta
 
 
+@_on_tensor_device
 def mean_over_time(x: torch.Tensor, B: int, L: int) -> torch.Tensor:
     _chk2d(x, f32, "mean_over_time")
     d = x.shape[1]
@@ -306,6 +333,7 @@ def mean_over_time(x: torch.Tensor, B: int, L: int) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def emotion_outputs(logits: torch.Tensor, thresholds: Optional[torch.Tensor] = None):
     """Post-path outputs of the reference's inference script (mosei_eval_infer.py:237-270):
     (probs = sigmoid(logits) fp32 [B, C], decisions = probs >= thresholds[c] as bool [B, C])."""

@@ -282,3 +282,19 @@ def test_full_size_properties_north_star():
     assert (be[idx].cpu() - be_o).abs().max().item() <= BETA_TOL
     assert (z[idx].cpu() - z_o).abs().max().item() <= Z_TOL
     assert torch.equal(be[idx].cpu() > 0.5, be_o > 0.5)
+
+
+def test_model_on_second_gpu_with_other_current_device():
+    """The C ABI launches on the current device: the wrappers must switch to the tensors' device
+    (a model on cuda:1 while cuda:0 is current), including the per-device shared-memory opt-in."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    fx = G.load("cfg2_iemocap_ragged")
+    model, ins = G.build_fusion(fx)
+    model = model.to("cuda:1")
+    assert torch.cuda.current_device() == 0
+    lo, be, z = model(*[G.to_dev(x, "cuda:1") for x in ins])
+    torch.cuda.synchronize("cuda:1")
+    assert lo.device.index == 1
+    assert (lo.cpu() - fx["logits"]).abs().max().item() <= LOGIT_TOL
+    assert (be.cpu() - fx["beta"]).abs().max().item() <= BETA_TOL
