@@ -308,7 +308,7 @@ def main():
         ht_h.normal_(generator=torch.Generator().manual_seed(199 + rank))
 
         def e2e_step():
-            lo, be, z = pipeline.forward_from_host(model, ha_h, ht_h, device=dev, slab=256, out_device="cpu")
+            lo, be, z = pipeline.forward_from_host(model, ha_h, ht_h, device=dev, slab=512, out_device="cpu")
             if world > 1:
                 pass  # results are already on the host of each rank; nothing to gather on device
             return lo

@@ -10,14 +10,15 @@ model = FusionWithEmotionDecoder().eval().to(dev)
 B, Ta, Tt = 4096, 500, 64
 ha = torch.empty((B, Ta, 768)).pin_memory(); ht = torch.empty((B, Tt, 768)).pin_memory()
 ha.normal_(); ht.normal_()
-for slab in (256, 512, 1024):
+for every in (0, 2, 3):
+  for slab in (256, 512):
     for _ in range(2):
-        pipeline.forward_from_host(model, ha, ht, device=dev, slab=slab)
+        pipeline.forward_from_host(model, ha, ht, device=dev, slab=slab, host_cast_every=every)
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(2):
-        pipeline.forward_from_host(model, ha, ht, device=dev, slab=slab)
-    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 2
-    print(f"slab {slab}: {dt*1e3:.1f} ms  {B/dt:.0f} utt/s")
+    for _ in range(3):
+        pipeline.forward_from_host(model, ha, ht, device=dev, slab=slab, host_cast_every=every)
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
+    print(f"host_cast_every {every} slab {slab}: {dt*1e3:.1f} ms  {B/dt:.0f} utt/s")
 # staging path with a no-op model: pure copy pipeline
 class Nop(torch.nn.Module):
     def forward(self, a, t, ma=None, mt=None):
