@@ -327,7 +327,8 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * Be * n_e2e / float(dt.item()), "unit": UNIT, "batch_per_gpu": Be,
-               "h2d_bytes_per_step": Be * bytes_per_utt, "d2h_bytes_per_step": int(lo_shape_bytes(model, Be)),
+               "h2d_bytes_per_step": (pipeline.h2d_bytes(Be, bytes_per_utt) if d_a % 8 == 0 and d_t % 8 == 0 else Be * bytes_per_utt),
+               "host_bytes_read_per_step": Be * bytes_per_utt, "d2h_bytes_per_step": int(lo_shape_bytes(model, Be)),
                "api": "hriemo.pipeline.forward_from_host(model, pinned h_a, pinned h_t) -> host logits/beta/z (pinned); every 2nd slab pre-cast to bf16 on the host cores"}
         del ha_h, ht_h
 

@@ -37,6 +37,19 @@ def gather_outputs(logits: torch.Tensor, beta: torch.Tensor, group=None):
     return out[:, :n_e], out[:, n_e:]
 
 
+def h2d_bytes(B: int, fp32_bytes_per_utt: int, slab: int = 512, host_cast_every: int = 2) -> int:
+    """Bytes forward_from_host copies host->device for B utterances of fp32 features whose feature
+    dims are multiples of 8: host-pre-cast slabs travel as bf16 (half the bytes)."""
+    starts = list(range(0, B, max(1, min(slab, B))))
+    ends = starts[1:] + [B]
+    host_cast = host_cast_every > 0 and len(starts) > 2
+    total = 0
+    for i, (s, e) in enumerate(zip(starts, ends)):
+        half = host_cast and (i % host_cast_every == host_cast_every - 1)
+        total += (e - s) * fp32_bytes_per_utt // (2 if half else 1)
+    return total
+
+
 _STAGING = {}   # (device, slab, shapes, ...) -> staging buffers + events, reused across calls
 
 
