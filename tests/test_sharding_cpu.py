@@ -58,3 +58,14 @@ def test_gather_outputs_world_size_2_gloo():
         p.join(timeout=30)
         assert p.exitcode == 0
     assert res == [(0, True, (B, n_e), (B, 1)), (1, True, (B, n_e), (B, 1))]
+
+
+def test_h2d_byte_accounting_matches_the_staging_schedule():
+    """pipeline.h2d_bytes mirrors forward_from_host's slab schedule: every second slab travels as bf16."""
+    from hriemo import pipeline
+
+    per = 564 * 768 * 4
+    assert pipeline.h2d_bytes(4096, per, slab=512, host_cast_every=0) == 4096 * per
+    assert pipeline.h2d_bytes(4096, per, slab=512, host_cast_every=2) == 4096 * per * 3 // 4   # 4 of 8 slabs halved
+    assert pipeline.h2d_bytes(1000, per, slab=512, host_cast_every=2) == 1000 * per            # two slabs: no pre-cast
+    assert pipeline.h2d_bytes(1100, per, slab=512, host_cast_every=2) == (512 + 76) * per + 512 * per // 2
