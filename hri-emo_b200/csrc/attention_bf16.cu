@@ -69,6 +69,7 @@ __device__ long long* g_attn_trace = nullptr;
 #endif
 
 struct Attn3Params {
+  const int32_t* kv_steps;   // [B] key steps to run per utterance (trailing all-PAD tiles skipped), or null
   const uint8_t* key_pad;
   __nv_bfloat16* out;
   int64_t ldo;
@@ -169,6 +170,13 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const uint32_t item_first = p.contiguous ? blockIdx.x * per_cta : blockIdx.x;
   const uint32_t item_stride = p.contiguous ? 1u : gridDim.x;
   const uint32_t item_last = p.contiguous ? min(item_first + per_cta, n_items_all) : n_items_all;  // exclusive
+  // key steps of a work item: all of them, or only up to the utterance's last valid key (a tile of
+  // PAD keys adds exactly 0 to every row sum, so skipping it is bit-exact); every role asks the same way
+  auto steps_of = [&](uint32_t item) -> int {
+    if (p.kv_steps == nullptr) return n_kv;
+    const uint32_t b_ = item / static_cast<uint32_t>(p.n_qp) / static_cast<uint32_t>(p.H);
+    return __ldg(p.kv_steps + b_);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -218,7 +226,8 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                         b * p.Tq + q0 + t * A3_BQ);
           ++qcnt[t];
         }
-        for (int j = 0; j < n_kv; ++j, ++g) {
+        const int nk = steps_of(item);
+        for (int j = 0; j < nk; ++j, ++g) {
           const uint32_t s = g % KS, par = (g / KS) & 1u;
           mbar_wait(b_kempty + s * 8, par ^ 1);
           mbar_arrive_expect_tx(b_kfull + s * 8, L::K_STAGE);
@@ -243,8 +252,6 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       const int t = (warp == 1) ? 0 : 1;
       constexpr uint32_t idesc_s = umma_idesc_bf16(A3_BQ, A3_BKV);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(A3_BQ, DH) | kUmmaBMajorMN;
-      const uint32_t my_items = item_last > item_first ? (item_last - item_first + item_stride - 1) / item_stride : 0u;
-      const uint32_t total = my_items * static_cast<uint32_t>(n_kv);  // flat steps of this CTA
       const uint32_t tile_tmem = tmem_base + t * TILE_COLS;
       const uint64_t k_desc0 = umma_desc_sw128(sK);
       const uint64_t v_desc0 = umma_desc_mn_sw64(sV, L::V_GROUP);
@@ -254,6 +261,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       // ---- S cursor (two steps ahead of the PV cursor)
       uint32_t s_g = 0, s_item = item_first, qcnt = 0;
       int s_j = 0;
+      int s_nk = s_item < item_last ? steps_of(s_item) : 0;
       bool s_act = tile_active(s_item);
       auto issue_s = [&]() {
         const uint32_t ks = s_g % KS, kpar = (s_g / KS) & 1u;
@@ -275,24 +283,26 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           umma_commit(b_sfull + (t * 2 + (s_g & 1u)) * 8);
           umma_commit(b_kempty + ks * 8);
           ATRACE(t, s_g, 6);
-          if (s_j == n_kv - 1) ++qcnt;  // the Q buffer is released by the warpgroup after its epilogue
+          if (s_j == s_nk - 1) ++qcnt;  // the Q buffer is released by the warpgroup after its epilogue
         } else {
           mbar_arrive(b_kempty + ks * 8);
         }
         ++s_g;
-        if (++s_j == n_kv) {
+        if (++s_j == s_nk) {
           s_j = 0;
           s_item += item_stride;
           s_act = s_item < item_last && tile_active(s_item);
+          s_nk = s_item < item_last ? steps_of(s_item) : 0;
         }
       };
-      if (total > 0) issue_s();
-      if (total > 1) issue_s();
+      if (s_item < item_last) issue_s();
+      if (s_item < item_last) issue_s();
       // ---- PV cursor
       uint32_t pcnt = 0, pv_item = item_first;
       int pv_j = 0;
+      int pv_nk = pv_item < item_last ? steps_of(pv_item) : 0;
       bool pv_act = tile_active(pv_item);
-      for (uint32_t g = 0; g < total; ++g) {
+      for (uint32_t g = 0; pv_item < item_last; ++g) {
         const uint32_t vs = g % KS, vpar = (g / KS) & 1u;
         ATRACE(t, g, 0);
         mbar_wait(b_vfull + vs * 8, vpar);
@@ -318,11 +328,12 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         } else {
           mbar_arrive(b_vempty + vs * 8);
         }
-        if (s_g < total) issue_s();  // S(g+2) reuses the S buffer whose P was just consumed
-        if (++pv_j == n_kv) {
+        if (s_item < item_last) issue_s();  // S(g+2) reuses the S buffer whose P was just consumed
+        if (++pv_j == pv_nk) {
           pv_j = 0;
           pv_item += item_stride;
           pv_act = pv_item < item_last && tile_active(pv_item);
+          pv_nk = pv_item < item_last ? steps_of(pv_item) : 0;
         }
       }
     }
@@ -366,7 +377,9 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     uint32_t qcnt_w = 0;         // items this tile has processed -> which Q buffer it used
     int cur_b = -1;
 
-    for (uint32_t item = item_first; item < item_last; item += item_stride, g += n_kv) {
+    int nk = 0;
+    for (uint32_t item = item_first; item < item_last; item += item_stride, g += nk) {
+      nk = steps_of(item);
       const uint32_t bh = item / static_cast<uint32_t>(p.n_qp);
       const int qp = static_cast<int>(item - bh * static_cast<uint32_t>(p.n_qp));
       const int b = static_cast<int>(bh / static_cast<uint32_t>(p.H));
@@ -374,7 +387,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       const int q0 = qp * 2 * A3_BQ + wg * A3_BQ;
       if (q0 >= p.Tq) {  // this warpgroup's tile does not exist for this item: only keep the exp turn-taking alive
 #ifndef HRIEMO_ATTN_NO_PINGPONG
-        for (int j = 0; j < n_kv; ++j) {
+        for (int j = 0; j < nk; ++j) {
           asm volatile("bar.sync %0, 256;" ::"r"(3 + wg) : "memory");
           asm volatile("bar.arrive %0, 256;" ::"r"(4 - wg) : "memory");
         }
@@ -396,10 +409,10 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         cur_b = b;
       }
 
-      if (n_kv <= 2) release_q();   // short items: the producer needs the buffer back sooner (two items ahead)
+      if (nk <= 2) release_q();   // short items: the producer needs the buffer back sooner (two items ahead)
       float m_run = -INFINITY;  // running reference maximum, in log2 units (score * scale * log2 e)
       float l_run = 0.0f;
-      for (int j = 0; j < n_kv; ++j) {
+      for (int j = 0; j < nk; ++j) {
         const uint32_t sbuf = static_cast<uint32_t>((g + j) & 1);
         const uint32_t t_s = t_tile + sbuf * A3_BKV;
         const int rem = p.Tk - j * A3_BKV;
@@ -478,7 +491,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if (wg_tid == 0) ATRACE(2 + wg, g + j, 5);
         mbar_arrive(b_pfull + (wg * 2 + (pv_issued & 1u)) * 8);
         ++pv_issued;
-        if (j == 0 && n_kv > 2) release_q();
+        if (j == 0 && nk > 2) release_q();
         if (wg_tid == 0) ATRACE(2 + wg, g + j, 6);
       }
 
@@ -518,7 +531,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       // next item's first hand-off, when the store has long since read it: waiting here would sit on
       // the critical path of every item (1 000 - 3 000 cycles; the trace of the 500 x 64 shape).
       pending_qslot = static_cast<int>(qslot);
-      if (wg_tid == 0) ATRACE(2 + wg, g + n_kv - 1, 7);
+      if (wg_tid == 0) ATRACE(2 + wg, g + nk - 1, 7);
       ++qcnt_w;
     }
     release_q();
@@ -566,6 +579,7 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
   }
   Attn3Params p;
   p.key_pad = a.key_pad;
+  p.kv_steps = a.kv_steps;
   p.out = static_cast<__nv_bfloat16*>(a.out);
   p.ldo = a.ldo;
   p.B = a.B; p.H = a.H; p.Tq = a.Tq; p.Tk = a.Tk;
@@ -591,6 +605,29 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
 
 }  // namespace hriemo
 
+namespace hriemo {
+// steps[b] = number of 64-key tiles up to and including the one holding the last valid key (>= 1, so a
+// fully padded utterance still runs one all-masked tile and comes out NaN like torch.softmax)
+__global__ void attention_kv_steps_kernel(const uint8_t* __restrict__ key_pad, int B, int Tk, int32_t* __restrict__ steps) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = threadIdx.x & 31;
+  int last = -1;
+  for (int k = lane; k < Tk; k += 32)
+    if (key_pad[static_cast<int64_t>(b) * Tk + k] == 0) last = k;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  if (lane == 0) steps[b] = last < 0 ? 1 : last / A3_BKV + 1;
+}
+}  // namespace hriemo
+
+extern "C" int hriemo_attention_kv_steps(const uint8_t* key_pad, int32_t B, int32_t Tk, int32_t* steps, void* stream) {
+  using namespace hriemo;
+  HRIEMO_REQUIRE(key_pad && steps && B > 0 && Tk > 0, "attention_kv_steps: bad argument");
+  attention_kv_steps_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(key_pad, B, Tk, steps);
+  return check_launch("attention_kv_steps");
+}
+
 #ifdef HRIEMO_ATTN_TRACE
 extern "C" int hriemo_debug_set_attn_trace(long long* buf) {  // trace builds only; not part of the ABI
   cudaError_t e = cudaMemcpyToSymbol(hriemo::g_attn_trace, &buf, sizeof(buf));
@@ -607,6 +644,7 @@ extern "C" int hriemo_attention_bf16(const hriemo_attn_args* a, void* stream) {
                  "attention: leading dimensions must be multiples of 8");
   HRIEMO_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15u) == 0, "attention: out misaligned");
   HRIEMO_REQUIRE(a->scale > 0.0f, "attention: scale must be positive");
+  HRIEMO_REQUIRE(a->kv_steps == nullptr || a->key_pad != nullptr, "attention: kv_steps comes with key_pad");
   HRIEMO_REQUIRE(a->dh == 32 || a->dh == 64 || a->dh == 96 || a->dh == 128,
                  "attention: head dim %d not in {32,64,96,128}", a->dh);
   cudaStream_t s = static_cast<cudaStream_t>(stream);

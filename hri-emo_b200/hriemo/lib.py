@@ -44,6 +44,7 @@ class AttnArgs(C.Structure):
         ("out", C.c_void_p), ("ldo", C.c_int64),
         ("B", C.c_int32), ("H", C.c_int32), ("Tq", C.c_int32), ("Tk", C.c_int32), ("dh", C.c_int32),
         ("scale", C.c_float),
+        ("kv_steps", C.c_void_p),
     ]
 
 
@@ -57,6 +58,7 @@ SIGNATURES = {
     "hriemo_cast_f32_to_bf16": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _P]),
     "hriemo_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _P]),
     "hriemo_attention_bf16": (C.c_int, [C.POINTER(AttnArgs), _P]),
+    "hriemo_attention_kv_steps": (C.c_int, [_P, _I32, _I32, _P, _P]),
     "hriemo_attention_probs": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I32, _I32, _I32, _I32, _I32, _F, _P]),
     "hriemo_small_attention": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P,
                                           _I32, _I32, _I32, _I32, _I32, _F, _P]),

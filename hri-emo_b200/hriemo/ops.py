@@ -183,8 +183,18 @@ def fold_ln_weight(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.T
 
 # ------------------------------------------------------------------ attention
 @_on_tensor_device
+def kv_steps(key_pad: torch.Tensor) -> torch.Tensor:
+    """[B, Tk] PAD mask -> int32 [B]: 64-key tiles up to the last valid key (>= 1) of each utterance."""
+    B, Tk = key_pad.shape
+    m = _mask_u8(key_pad, B, Tk, "kv_steps")
+    out = torch.empty((B,), dtype=torch.int32, device=key_pad.device)
+    _l.check(_l.load().hriemo_attention_kv_steps(m.data_ptr(), B, Tk, out.data_ptr(), _stream()), "attention_kv_steps")
+    return out
+
+
+@_on_tensor_device
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Optional[torch.Tensor],
-              B: int, H: int, Tq: int, Tk: int, dh: int) -> torch.Tensor:
+              B: int, H: int, Tq: int, Tk: int, dh: int, skip_padded_tiles: bool = True) -> torch.Tensor:
     """q: [B*Tq, >=H*dh] view, k / v: [B*Tk, >=H*dh] views (column slices of a packed projection are
     fine).  Returns [B*Tq, H*dh] bf16."""
     _chk2d(q, bf16, "attention q")
@@ -199,6 +209,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Option
     args.q, args.ldq, args.k, args.ldk = q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0)
     args.v, args.ldv = v.data_ptr(), v.stride(0)
     args.key_pad = _ptr(m)
+    steps = None
+    if m is not None and skip_padded_tiles and Tk > 320:   # measured: pays from 6 key tiles on
+        steps = kv_steps(m)   # trailing all-PAD key tiles are not processed (bit-identical result)
+        args.kv_steps = steps.data_ptr()
     args.out, args.ldo = out.data_ptr(), out.stride(0)
     args.B, args.H, args.Tq, args.Tk, args.dh = B, H, Tq, Tk, dh
     args.scale = 1.0 / math.sqrt(dh)

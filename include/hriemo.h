@@ -123,7 +123,16 @@ typedef struct hriemo_attn_args {
   void* out;      int64_t ldo;   /* bf16 [B*Tq, H*dh] */
   int32_t B, H, Tq, Tk, dh;      /* dh in {32, 64, 96, 128} */
   float scale;                   /* 1/sqrt(dh) */
+  /* Optional, with key_pad: kv_steps[b] = number of 64-key tiles to process for utterance b (from
+   * hriemo_attention_kv_steps).  Trailing tiles that hold only PAD keys are skipped; the result is
+   * bit-identical (a masked key contributes exactly 0).  This is the padded-tensor form of the
+   * reference's collate (scripts/fusion/train_fusion_seq_level_decoder.py:191-232: zero-pad to the
+   * batch maximum + True=PAD mask) without paying for the padding in the attention. */
+  const int32_t* kv_steps;
 } hriemo_attn_args;
+
+/* steps[b] = (index of the last valid key of utterance b) / 64 + 1, or 1 when every key is PAD. */
+int hriemo_attention_kv_steps(const uint8_t* key_pad, int32_t B, int32_t Tk, int32_t* steps, void* stream);
 
 int hriemo_attention_bf16(const hriemo_attn_args* args, void* stream);
 

@@ -316,6 +316,35 @@ def test_attention_fully_masked_row_is_nan():
     assert torch.isnan(out[1]).all()
 
 
+@pytest.mark.parametrize("B,H,Tq,Tk,dh", [(6, 8, 500, 500, 96), (5, 4, 300, 128, 64), (4, 8, 64, 500, 96), (3, 2, 130, 1000, 128)])
+def test_attention_skipping_padded_key_tiles_is_bit_exact(B, H, Tq, Tk, dh):
+    """Trailing key tiles that hold only PAD keys are not processed (per-utterance step counts): a masked
+    key contributes exactly 0, so the output is bit-identical to processing every tile.  Covers short,
+    full-length and fully padded utterances and a mask with a hole."""
+    from hriemo import ops
+
+    d = H * dh
+    q = _rand((B * Tq, d), 101, dtype=torch.bfloat16)
+    k = _rand((B * Tk, d), 102, dtype=torch.bfloat16)
+    v = _rand((B * Tk, d), 103, dtype=torch.bfloat16)
+    lens = torch.tensor([Tk, 1, Tk // 3, 70, 0, Tk - 1][:B])
+    pad = (torch.arange(Tk)[None, :] >= lens[:, None])
+    pad[0, 5:90] = True                      # a hole in a full-length utterance
+    pad = pad.to(DEV)
+    steps = ops.kv_steps(pad).cpu()
+    want = torch.tensor([max(1, -(-int(l) // 64)) for l in lens], dtype=torch.int32)
+    assert torch.equal(steps, want), (steps, want)
+    full = ops.attention(q, k, v, pad, B, H, Tq, Tk, dh, skip_padded_tiles=False)
+    skip = ops.attention(q, k, v, pad, B, H, Tq, Tk, dh, skip_padded_tiles=True)
+    fv, sv = full.view(torch.int16), skip.view(torch.int16)
+    nan = torch.isnan(full)
+    assert torch.equal(torch.isnan(skip), nan) and torch.equal(fv[~nan], sv[~nan])
+    if B > 4:
+        assert torch.isnan(skip.view(B, Tq, d)[4]).all()     # fully padded utterance -> NaN, like torch.softmax
+    ref, _ = _attn_ref(q.view(B, Tq, d), k.view(B, Tk, d), v.view(B, Tk, d), pad, H)
+    _report("attention with skipped tiles", skip, ref, atol=1.5e-2, rtol=2e-2)
+
+
 def test_attention_nan_in_neighbour_utterance_does_not_leak():
     """The last key tile of utterance b overhangs into utterance b+1's rows; those keys carry P = 0
     but 0 x NaN would still poison utterance b (a fully padded neighbour is NaN by design)."""

@@ -45,6 +45,18 @@ def main():
         fl = 4.0 * B * H * Tq * Tk * dh
         res.append(dict(kernel="attention", B=B, H=H, Tq=Tq, Tk=Tk, dh=dh, ms=med, tflops=fl / med / 1e9, frac_burst=fl / med / 1e9 / PEAKS["bf16_tflops"], sdpa_ms=meds))
         print(res[-1], flush=True)
+    if only in (None, "attention", "ragged"):
+        # ragged batch (key lengths uniform in [T/2, T]): skipping trailing all-PAD key tiles
+        for (B, H, Tq, Tk, dh) in [(512, 8, 500, 500, 96), (512, 8, 64, 500, 96), (512, 8, 300, 300, 96)]:
+            d = H * dh
+            q = torch.randn(B * Tq, d, device=dev).bfloat16(); k = torch.randn(B * Tk, d, device=dev).bfloat16()
+            v = torch.randn(B * Tk, d, device=dev).bfloat16()
+            lens = torch.randint(Tk // 2, Tk + 1, (B, 1), device=dev)
+            pad = torch.arange(Tk, device=dev)[None, :] >= lens
+            m0, _ = timeit(lambda: ops.attention(q, k, v, pad, B, H, Tq, Tk, dh, skip_padded_tiles=False))
+            m1, _ = timeit(lambda: ops.attention(q, k, v, pad, B, H, Tq, Tk, dh, skip_padded_tiles=True))
+            res.append(dict(kernel="attention_ragged", B=B, H=H, Tq=Tq, Tk=Tk, dh=dh, ms_all_tiles=m0, ms_skip=m1, speedup=m0 / m1))
+            print(res[-1], flush=True)
     if only not in (None, "elem"):
         return
     rows, d = 2048000 // 4, 768
