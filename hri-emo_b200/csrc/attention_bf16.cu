@@ -503,19 +503,26 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       const uint32_t qslot = wg * 2 + (qcnt_w & 1u);
       const uint32_t stage_warp = sQ + qslot * L::Q_TILE + static_cast<uint32_t>(quad) * (32 * DH * 2);
       const uint32_t stage_row = stage_warp + static_cast<uint32_t>(lane) * (DH * 2);
-#pragma unroll 1
-      for (int c = 0; c < DH / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_o + c * 32, v);
+      // all DH/32 loads are in flight before the first wait (the S registers are dead here): one
+      // tensor-memory round trip per item instead of DH/32
+      constexpr int OB = (DH / 32 > 3) ? 2 : DH / 32;   // chunks per batch (dh = 128 would spill with 4)
+#pragma unroll
+      for (int c0 = 0; c0 < DH / 32; c0 += OB) {
+        uint32_t vo[OB][32];
+#pragma unroll
+        for (int c = 0; c < OB; ++c) tmem_ld32(t_o + (c0 + c) * 32, vo[c]);
         tmem_ld_wait();
 #pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4) {
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + c * 64 + g4 * 16),
-                       "r"(pack_bf16(__uint_as_float(v[g4 * 8 + 0]) * inv_l, __uint_as_float(v[g4 * 8 + 1]) * inv_l)),
-                       "r"(pack_bf16(__uint_as_float(v[g4 * 8 + 2]) * inv_l, __uint_as_float(v[g4 * 8 + 3]) * inv_l)),
-                       "r"(pack_bf16(__uint_as_float(v[g4 * 8 + 4]) * inv_l, __uint_as_float(v[g4 * 8 + 5]) * inv_l)),
-                       "r"(pack_bf16(__uint_as_float(v[g4 * 8 + 6]) * inv_l, __uint_as_float(v[g4 * 8 + 7]) * inv_l))
-                       : "memory");
+        for (int c = 0; c < OB; ++c) {
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + (c0 + c) * 64 + g4 * 16),
+                         "r"(pack_bf16(__uint_as_float(vo[c][g4 * 8 + 0]) * inv_l, __uint_as_float(vo[c][g4 * 8 + 1]) * inv_l)),
+                         "r"(pack_bf16(__uint_as_float(vo[c][g4 * 8 + 2]) * inv_l, __uint_as_float(vo[c][g4 * 8 + 3]) * inv_l)),
+                         "r"(pack_bf16(__uint_as_float(vo[c][g4 * 8 + 4]) * inv_l, __uint_as_float(vo[c][g4 * 8 + 5]) * inv_l)),
+                         "r"(pack_bf16(__uint_as_float(vo[c][g4 * 8 + 6]) * inv_l, __uint_as_float(vo[c][g4 * 8 + 7]) * inv_l))
+                         : "memory");
+          }
         }
       }
       tc_fence_before_sync();   // O reads retire before the next item's first p_full lets PV overwrite O

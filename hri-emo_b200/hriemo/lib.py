@@ -72,6 +72,11 @@ SIGNATURES = {
                                      _P, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "hriemo_mean_over_time": (C.c_int, [_P, _P, _I32, _I32, _I32, _P]),
     "hriemo_emotion_outputs": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
+    "hriemo_mask_lengths": (C.c_int, [_P, _I32, _I32, _P, _P]),
+    "hriemo_gather_utterances_bf16": (C.c_int, [_P, _I32, _I64, _I32, _P, _P, _I64, _I32, _I32, _I32, _P]),
+    "hriemo_gather_masks": (C.c_int, [_P, _I32, _P, _P, _I32, _I32, _P]),
+    "hriemo_scatter_rows_f32": (C.c_int, [_P, _P, _P, _I64, _I64, _P]),
+    "hriemo_host_pack_bf16": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, _I64, _I64, _I32]),
 }
 
 _lib = None

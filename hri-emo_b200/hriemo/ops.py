@@ -362,3 +362,90 @@ def emotion_outputs(logits: torch.Tensor, thresholds: Optional[torch.Tensor] = N
     _l.check(_l.load().hriemo_emotion_outputs(logits.data_ptr(), _ptr(thresholds), probs.data_ptr(), dec.data_ptr(),
                                                B, Cn, _stream()), "emotion_outputs")
     return probs, dec.view(torch.bool)
+
+
+# ------------------------------------------------------------------ length-bucketed staging
+@_on_tensor_device
+def mask_lengths(pad: torch.Tensor) -> torch.Tensor:
+    """[B, T] PAD mask -> int32 [B]: index of the last valid position + 1 (0 = everything is PAD)."""
+    B, T = pad.shape
+    m = _mask_u8(pad, B, T, "mask_lengths")
+    out = torch.empty((B,), dtype=torch.int32, device=pad.device)
+    _l.check(_l.load().hriemo_mask_lengths(m.data_ptr(), B, T, out.data_ptr(), _stream()), "mask_lengths")
+    return out
+
+
+def _chk_utt(utt: torch.Tensor, dev, name: str) -> None:
+    if utt.device != dev or utt.dtype != torch.int32 or utt.dim() != 1 or not utt.is_contiguous():
+        raise _l.HriemoError(f"{name}: utterance index must be a contiguous int32 vector on {dev}")
+
+
+@_on_tensor_device
+def gather_utterances(x: torch.Tensor, utt: torch.Tensor, T_out: int, ld_out: Optional[int] = None) -> torch.Tensor:
+    """x [B, T, cols] (fp32 or bf16, CUDA) -> bf16 [n, T_out, ld_out]: utterances utt[i], time axis trimmed
+    (or zero-extended) to T_out, columns zero-padded to ld_out."""
+    if not x.is_cuda or x.dim() != 3 or x.dtype not in (f32, bf16):
+        raise _l.HriemoError("gather_utterances: expected a CUDA [B, T, cols] fp32 / bf16 tensor")
+    x = x.contiguous()
+    _chk_utt(utt, x.device, "gather_utterances")
+    B, T, cols = x.shape
+    ld_out = round_up(cols, 8) if ld_out is None else ld_out
+    n = utt.shape[0]
+    out = torch.empty((n, T_out, ld_out), dtype=bf16, device=x.device)
+    _l.check(_l.load().hriemo_gather_utterances_bf16(x.data_ptr(), 1 if x.dtype == f32 else 0, cols, T, utt.data_ptr(),
+                                                      out.data_ptr(), ld_out, n, T_out, cols, _stream()),
+             "gather_utterances_bf16")
+    return out
+
+
+@_on_tensor_device
+def gather_masks(pad: torch.Tensor, utt: torch.Tensor, T_out: int) -> torch.Tensor:
+    """[B, T] PAD mask -> bool [n, T_out] for utterances utt[i] (positions past T are PAD)."""
+    B, T = pad.shape
+    m = _mask_u8(pad, B, T, "gather_masks")
+    _chk_utt(utt, pad.device, "gather_masks")
+    n = utt.shape[0]
+    out = torch.empty((n, T_out), dtype=torch.uint8, device=pad.device)
+    _l.check(_l.load().hriemo_gather_masks(m.data_ptr(), T, utt.data_ptr(), out.data_ptr(), n, T_out, _stream()),
+             "gather_masks")
+    return out.view(torch.bool)
+
+
+@_on_tensor_device
+def scatter_rows(src: torch.Tensor, utt: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst[utt[i]] = src[i] for fp32 tensors whose leading dim indexes utterances."""
+    if src.dtype != f32 or dst.dtype != f32 or not src.is_cuda or not dst.is_contiguous() or dst.device != src.device:
+        raise _l.HriemoError("scatter_rows: expected contiguous fp32 CUDA tensors on one device")
+    src = src.contiguous()
+    _chk_utt(utt, src.device, "scatter_rows")
+    n = src.shape[0]
+    cols = src.numel() // max(n, 1)
+    if n != utt.shape[0] or (dst.numel() // max(dst.shape[0], 1)) != cols:
+        raise _l.HriemoError(f"scatter_rows: shapes {tuple(src.shape)} -> {tuple(dst.shape)} with {utt.shape[0]} indices")
+    _l.check(_l.load().hriemo_scatter_rows_f32(src.data_ptr(), utt.data_ptr(), dst.data_ptr(), n, cols, _stream()),
+             "scatter_rows_f32")
+
+
+def host_pack_bf16(src: torch.Tensor, dst: torch.Tensor, T_out: int, utt: Optional[torch.Tensor] = None,
+                   lens: Optional[torch.Tensor] = None, n: Optional[int] = None, threads: int = 0) -> torch.Tensor:
+    """HOST tensors only: dst[:n, :T_out, :] = bf16(src[utt[i], :T_out, :]) (rows past lens[i] zeroed), by C++
+    threads (the GIL is released for the duration of the call).  src fp32 [B, T, cols] contiguous, dst a
+    contiguous bf16 buffer with room for n * T_out * cols elements.  Returns the [n, T_out, cols] view."""
+    import os
+    if src.is_cuda or dst.is_cuda or src.dtype != f32 or dst.dtype != bf16 or src.dim() != 3:
+        raise _l.HriemoError("host_pack_bf16: expected host tensors, fp32 [B, T, cols] -> bf16")
+    if not src.is_contiguous() or not dst.is_contiguous():
+        raise _l.HriemoError("host_pack_bf16: tensors must be contiguous")
+    B, T, cols = src.shape
+    n = (utt.shape[0] if utt is not None else B) if n is None else n
+    for v, name in ((utt, "utt"), (lens, "lens")):
+        if v is not None and (v.is_cuda or v.dtype != torch.int32 or not v.is_contiguous() or v.shape[0] < n):
+            raise _l.HriemoError(f"host_pack_bf16: {name} must be a contiguous host int32 vector with >= n entries")
+    if utt is None and n > B:
+        raise _l.HriemoError("host_pack_bf16: n exceeds the batch")
+    if dst.numel() < n * T_out * cols:
+        raise _l.HriemoError("host_pack_bf16: destination too small")
+    threads = threads or max(1, min(32, (os.cpu_count() or 1)))
+    _l.check(_l.load().hriemo_host_pack_bf16(src.data_ptr(), cols, T, cols, _ptr(utt), _ptr(lens), dst.data_ptr(), cols,
+                                              T_out, n, threads), "host_pack_bf16")
+    return dst.view(-1)[: n * T_out * cols].view(n, T_out, cols)

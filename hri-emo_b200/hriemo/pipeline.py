@@ -1,27 +1,55 @@
-"""Host staging and batch sharding around the forward path.
+"""Host staging, length bucketing and batch sharding around the forward path.
 
 * ``forward_from_host``: the end-to-end call for features that live in (pinned) host
   memory, as the reference's DataLoader/collate delivers them
   (scripts/fusion/train_fusion_seq_level_decoder.py:191-232, :306-308).  The batch is cut
   into slabs of utterances; slab i+1 is copied host->device on a side stream while slab i
   computes, and only logits / beta / z come back.
-* ``shard_bounds`` / ``gather_outputs``: batch sharding over ranks (utterances are
-  independent); the only collective is one all_gather of the small outputs.
+* ``bucket=True`` / ``forward_bucketed``: the collate zero-pads every utterance to the batch
+  maximum (True = PAD mask).  Padded rows never reach logits / beta / z -- keys are masked,
+  pooled means are masked, the decoder reads the fused mask -- so utterances are sorted by valid
+  length and each slab is trimmed to its own maximum (``bucket_plan``): the GEMMs and the attention
+  no longer pay for the padding, and the padding never crosses PCIe.
+* ``shard_bounds`` / ``shard_by_length`` / ``gather_outputs``: batch sharding over ranks
+  (utterances are independent); the only collective is one all_gather of the
+  small outputs.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
 from . import engine as E
+from . import ops
 
 
+# --------------------------------------------------------------------------- #
+# sharding
+# --------------------------------------------------------------------------- #
 def shard_bounds(B: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous split of the batch: rank r gets [lo, hi); the first B % world ranks get one extra."""
     base, extra = divmod(B, world)
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_by_length(len_a: torch.Tensor, len_t: Optional[torch.Tensor], world: int) -> List[torch.Tensor]:
+    """Length-balanced split of a ragged batch ("sort/bucket by length before sharding"):
+    utterances sorted by (len_a, len_t) are dealt in a serpentine (0..w-1, w-1..0, ...), so every rank
+    gets the same number of utterances (+-1) and the same length distribution -- the per-rank work,
+    which grows with (T_a + T_t)^2 in the attention and linearly elsewhere, is balanced to a fraction of
+    a percent.  Returns one int64 index vector per rank (ascending length within a rank)."""
+    key = len_a.to("cpu", torch.int64)
+    if len_t is not None and len_t.numel():
+        lt = len_t.to("cpu", torch.int64)
+        key = key * (int(lt.max().item()) + 1) + lt
+    order = torch.argsort(key, stable=True)
+    pos = torch.arange(order.shape[0])
+    lane = pos % world
+    rank_of = torch.where((pos // world) % 2 == 0, lane, world - 1 - lane)
+    return [order[rank_of == r].contiguous() for r in range(world)]
 
 
 def gather_outputs(logits: torch.Tensor, beta: torch.Tensor, group=None):
@@ -37,40 +65,179 @@ def gather_outputs(logits: torch.Tensor, beta: torch.Tensor, group=None):
     return out[:, :n_e], out[:, n_e:]
 
 
-def h2d_bytes(B: int, fp32_bytes_per_utt: int, slab: int = 512, host_cast_every: int = 2) -> int:
-    """Bytes forward_from_host copies host->device for B utterances of fp32 features whose feature
+# --------------------------------------------------------------------------- #
+# slab plans
+# --------------------------------------------------------------------------- #
+def slab_schedule(B: int, slab: int = 512, host_cast_every: int = 2, ramp: bool = True):
+    """The slab plan forward_from_host follows for a dense batch: [(start, end, host_cast)], in order.
+
+    Nothing computes until the first slab has landed, so the plan opens with a short RAMP of small
+    fp32 slabs (slab/8, slab/4, slab/2 utterances; only when at least four full slabs follow) and
+    continues with full slabs, every `host_cast_every`-th of which (0 = never) is converted to bf16 by
+    the host cores and travels at half the bytes.  Ramp slabs are never host-cast: the host has had
+    no time to convert them."""
+    slab = max(1, min(slab, B))
+    sizes = []
+    left = B
+    if ramp and slab >= 64 and B >= 5 * slab:
+        for n in (slab // 8, slab // 4, slab // 2):
+            sizes.append(n)
+            left -= n
+    n_ramp = len(sizes)
+    while left > 0:
+        n = min(slab, left)
+        sizes.append(n)
+        left -= n
+    n_full = len(sizes) - n_ramp
+    host_cast = host_cast_every > 0 and n_full > 2
+    plan, s = [], 0
+    for i, n in enumerate(sizes):
+        j = i - n_ramp
+        plan.append((s, s + n, bool(host_cast and j >= 0 and j % host_cast_every == host_cast_every - 1)))
+        s += n
+    return plan
+
+
+def h2d_bytes(B: int, fp32_bytes_per_utt: int, slab: int = 512, host_cast_every: int = 2, ramp: bool = True) -> int:
+    """Bytes forward_from_host copies host->device for B dense utterances of fp32 features whose feature
     dims are multiples of 8: host-pre-cast slabs travel as bf16 (half the bytes)."""
-    starts = list(range(0, B, max(1, min(slab, B))))
-    ends = starts[1:] + [B]
-    host_cast = host_cast_every > 0 and len(starts) > 2
-    total = 0
-    for i, (s, e) in enumerate(zip(starts, ends)):
-        half = host_cast and (i % host_cast_every == host_cast_every - 1)
-        total += (e - s) * fp32_bytes_per_utt // (2 if half else 1)
-    return total
+    return sum((e - s) * fp32_bytes_per_utt // (2 if half else 1)
+               for s, e, half in slab_schedule(B, slab, host_cast_every, ramp))
 
 
-_STAGING = {}   # (device, slab, shapes, ...) -> staging buffers + events, reused across calls
+def valid_lengths(mask: Optional[torch.Tensor], B: int, T: int) -> torch.Tensor:
+    """int32 [B] (on the mask's device, CPU when mask is None): index of the last valid position + 1;
+    T without a mask, 0 when every position is PAD.  Host masks are handled with torch index
+    bookkeeping, device masks by the hriemo_mask_lengths kernel."""
+    if mask is None:
+        return torch.full((B,), T, dtype=torch.int32)
+    if mask.is_cuda:
+        return ops.mask_lengths(mask)
+    valid = ~mask.to(torch.bool)
+    pos = torch.arange(1, T + 1, dtype=torch.int32)
+    return (valid.to(torch.int32) * pos).amax(dim=1).to(torch.int32)
 
 
-def _staging(dev, slab, h_a, h_t, mask_a, mask_t, host_cast):
-    key = (str(dev), slab, tuple(h_a.shape[1:]), tuple(h_t.shape[1:]), h_a.dtype, h_t.dtype,
-           mask_a is not None, mask_t is not None, host_cast)
+@dataclass
+class Bucket:
+    start: int   # [start, end) in the sorted order
+    end: int
+    T_a: int     # time extents of this slab after trimming
+    T_t: int
+
+
+def bucket_plan(len_a: torch.Tensor, len_t: torch.Tensor, T_a: int, T_t: int, rows_per_slab: int = 512 * 500,
+                max_utts: int = 2048) -> Tuple[torch.Tensor, List[Bucket]]:
+    """Sort utterances by valid length (audio first, then text; ascending, so the plan opens with the
+    cheap slabs and the pipeline fills quickly) and cut the order into slabs of at most `rows_per_slab`
+    audio rows / `max_utts` utterances, each trimmed to its own maxima.
+
+    The trimmed extents keep what the reference's forward needs: at least one row per stream (a fully
+    padded utterance still runs, all-masked, and comes out NaN like the reference), and T_a >= T_t
+    unless T_a == 1 (models/beta_gate_tacfn.py:116 slices h_a[:, :T_t]).  Returns (order, buckets);
+    order is an int32 host vector, order[k] = original index of the k-th utterance in sorted order."""
+    la = len_a.to("cpu", torch.int64).clamp(1, T_a)
+    lt = len_t.to("cpu", torch.int64).clamp(1, T_t)
+    B = la.shape[0]
+    order = torch.argsort(la * (T_t + 1) + lt, stable=True)
+    la_s, lt_s = la[order].tolist(), lt[order].tolist()
+    buckets: List[Bucket] = []
+    s = 0
+    while s < B:
+        e = s
+        ta = tt = 1
+        while e < B and e - s < max_utts:
+            ta2, tt2 = max(ta, la_s[e]), max(tt, lt_s[e])
+            if e > s and (e - s + 1) * max(ta2, tt2) > rows_per_slab:
+                break
+            ta, tt = ta2, tt2
+            e += 1
+        if T_a > 1:
+            ta = min(T_a, max(ta, tt))   # the gate blends h_a[:, :T_t] with h_t
+        buckets.append(Bucket(s, e, ta, tt))
+        s = e
+    return order.to(torch.int32), buckets
+
+
+def bucket_stats(len_a: torch.Tensor, len_t: torch.Tensor, T_a: int, T_t: int, buckets: Sequence[Bucket]) -> dict:
+    """Rows the padded batch holds, rows the bucketed plan processes, and rows that are actually valid."""
+    B = int(len_a.shape[0])
+    return {"padded_rows": B * (T_a + T_t),
+            "bucketed_rows": sum((b.end - b.start) * (b.T_a + b.T_t) for b in buckets),
+            "valid_rows": int(len_a.clamp(1, T_a).sum() + len_t.clamp(1, T_t).sum())}
+
+
+# --------------------------------------------------------------------------- #
+# device-resident bucketed forward
+# --------------------------------------------------------------------------- #
+@torch.no_grad()
+def forward_bucketed(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optional[torch.Tensor] = None,
+                     mask_t: Optional[torch.Tensor] = None, rows_per_slab: int = 512 * 500, max_utts: int = 2048):
+    """model(h_a, h_t, mask_a, mask_t)[:3] for DEVICE tensors, without the padding: utterances are sorted
+    by valid length (one small D2H of the lengths -- this call synchronises the host once), gathered into
+    slabs trimmed to their own maxima (hriemo_gather_utterances_bf16 / _masks), run through the model,
+    and the results scattered back to the original order.  Same outputs as the padded forward up to the
+    bf16 path's own rounding (a masked key contributes exactly 0; padded query rows reach no output)."""
+    if h_a.dim() != 3 or h_t.dim() != 3 or (mask_a is None and mask_t is None) or h_a.shape[1] == 1:
+        return tuple(model(h_a, h_t, mask_a, mask_t)[:3])
+    E.require_cuda(h_a, "h_a")
+    E.require_cuda(h_t, "h_t")
+    B, T_a, T_t = h_a.shape[0], h_a.shape[1], h_t.shape[1]
+    mask_a = E.check_mask(mask_a, B, T_a, "mask_a")
+    mask_t = E.check_mask(mask_t, B, T_t, "mask_t")
+    la = valid_lengths(mask_a, B, T_a)
+    lt = valid_lengths(mask_t, B, T_t)
+    order, buckets = bucket_plan(la, lt, T_a, T_t, rows_per_slab, max_utts)
+    order_dev = order.to(h_a.device, non_blocking=True)
+    d_a, d_t = h_a.shape[2], h_t.shape[2]
+    outs = None
+    for bk in buckets:
+        utt = order_dev[bk.start:bk.end]
+        a = ops.gather_utterances(h_a, utt, bk.T_a)
+        t = ops.gather_utterances(h_t, utt, bk.T_t)
+        ma = None if mask_a is None else ops.gather_masks(mask_a, utt, bk.T_a)
+        mt = None if mask_t is None else ops.gather_masks(mask_t, utt, bk.T_t)
+        # feature dims that are not multiples of 8 (MOSEI 74 / 300) come back zero-padded: hand the model
+        # the logical columns; its own input cast pads them again
+        res = model(a if a.shape[2] == d_a else a[:, :, :d_a].float(), t if t.shape[2] == d_t else t[:, :, :d_t].float(),
+                    ma, mt)[:3]
+        if outs is None:
+            outs = [torch.empty((B,) + tuple(r.shape[1:]), dtype=torch.float32, device=h_a.device) for r in res]
+        for dst, r in zip(outs, res):
+            ops.scatter_rows(r.float() if r.dtype != torch.float32 else r, utt, dst)
+    return tuple(outs)
+
+
+# --------------------------------------------------------------------------- #
+# host staging
+# --------------------------------------------------------------------------- #
+_STAGING = {}   # configuration -> staging buffers + events, reused across calls
+
+
+def _staging(dev, dtype_a, dtype_t, elems_a: int, elems_t: int, rows_a: int, rows_t: int, direct_sets: bool,
+             host_sets: bool, with_ma: bool, with_mt: bool):
+    key = (str(dev), dtype_a, dtype_t, elems_a, elems_t, rows_a, rows_t, direct_sets, host_sets, with_ma, with_mt)
     st = _STAGING.get(key)
     if st is None:
-        def mk(dtype_a, dtype_t):
-            return dict(a=torch.empty((slab,) + tuple(h_a.shape[1:]), dtype=dtype_a, device=dev),
-                        t=torch.empty((slab,) + tuple(h_t.shape[1:]), dtype=dtype_t, device=dev),
-                        ma=None if mask_a is None else torch.empty((slab, mask_a.shape[1]), dtype=torch.bool, device=dev),
-                        mt=None if mask_t is None else torch.empty((slab, mask_t.shape[1]), dtype=torch.bool, device=dev),
+        def mk(da, dt):
+            return dict(a=torch.empty((elems_a,), dtype=da, device=dev),
+                        t=torch.empty((elems_t,), dtype=dt, device=dev),
+                        ma=torch.empty((rows_a,), dtype=torch.bool, device=dev) if with_ma else None,
+                        mt=torch.empty((rows_t,), dtype=torch.bool, device=dev) if with_mt else None,
                         copied=torch.cuda.Event(), consumed=torch.cuda.Event())
-        st = dict(bufs=[mk(h_a.dtype, h_t.dtype), mk(h_a.dtype, h_t.dtype)], copy=torch.cuda.Stream(dev))
-        if host_cast:
+
+        st = dict(copy=torch.cuda.Stream(dev))
+        if direct_sets:
+            # landing sets of the source dtype: free again as soon as the GPU bf16 cast has read them
+            st["direct"] = [mk(dtype_a, dtype_t), mk(dtype_a, dtype_t)]
+        if host_sets:
             # slabs converted to bf16 by the host cores: pinned bf16 staging on the host (ping-pong) and
             # bf16 landing buffers on the device (ping-pong, released when the slab's forward is done)
             def mk_host():
-                return dict(a=torch.empty((slab,) + tuple(h_a.shape[1:]), dtype=torch.bfloat16).pin_memory(),
-                            t=torch.empty((slab,) + tuple(h_t.shape[1:]), dtype=torch.bfloat16).pin_memory(),
+                return dict(a=torch.empty((elems_a,), dtype=torch.bfloat16).pin_memory(),
+                            t=torch.empty((elems_t,), dtype=torch.bfloat16).pin_memory(),
+                            ma=torch.empty((rows_a,), dtype=torch.bool).pin_memory() if with_ma else None,
+                            mt=torch.empty((rows_t,), dtype=torch.bool).pin_memory() if with_mt else None,
                             sent=torch.cuda.Event())
             st["host16"] = [mk_host(), mk_host()]
             st["dev16"] = [mk(torch.bfloat16, torch.bfloat16), mk(torch.bfloat16, torch.bfloat16)]
@@ -79,10 +246,35 @@ def _staging(dev, slab, h_a, h_t, mask_a, mask_t, host_cast):
     return st
 
 
+@dataclass
+class _Slab:
+    lo: int                         # dense plan: utterances [lo, hi) of the batch
+    hi: int                         # bucketed plan: positions [lo, hi) of the sorted order
+    T_a: int
+    T_t: int
+    host_cast: bool
+    utt: Optional[torch.Tensor] = None      # bucketed: int32 host indices of the slab's utterances
+    utt_dev: Optional[torch.Tensor] = None
+
+    @property
+    def n(self) -> int:
+        return self.hi - self.lo
+
+
+def _trim_mask(mask: torch.Tensor, utt: torch.Tensor, T_out: int) -> torch.Tensor:
+    """Host [B, T] bool mask -> [n, T_out] for utterances utt (positions past T are PAD)."""
+    m = mask.index_select(0, utt.long())
+    T = m.shape[1]
+    if T_out <= T:
+        return m[:, :T_out]
+    return torch.cat([m, torch.ones((m.shape[0], T_out - T), dtype=torch.bool)], dim=1)
+
+
 @torch.no_grad()
 def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optional[torch.Tensor] = None,
                       mask_t: Optional[torch.Tensor] = None, device="cuda", slab: int = 512,
-                      out_device="cpu", host_cast_every: int = 2):
+                      out_device="cpu", host_cast_every: int = 2, ramp: bool = True, bucket: bool = False,
+                      trace: Optional[list] = None):
     """model(h_a, h_t, mask_a, mask_t) for HOST tensors with copy/compute overlap.
 
     The batch is cut into slabs of utterances that flow through fixed staging buffers (nothing is
@@ -90,12 +282,19 @@ def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optio
       * fp32 slabs are copied as they are and cast to bf16 on the GPU; their staging set is free again
         as soon as the cast has read it;
       * every `host_cast_every`-th slab (0 = never) is instead converted to bf16 by the host cores
-        (a worker thread, torch CPU intra-op threads) into pinned bf16 staging and copied at half the
+        (hriemo_host_pack_bf16 in a worker thread) into pinned bf16 staging and copied at half the
         bytes.  A step is bounded by the 55 GB/s H2D copy of the fp32 features (7.1 GB at the
         north-star batch); with every second slab pre-cast the copy drops under the compute time.
         The rounding is the same round-to-nearest-even as the GPU cast: results are bit-identical.
-    Returns (logits, beta, z) on `out_device`; host results are fresh PINNED tensors filled by one
-    asynchronous D2H copy per slab (a pageable `.cpu()` of the 50 MB of z cost 31 ms per step)."""
+      * the plan opens with a ramp of small slabs (`slab_schedule`) so the GPU starts computing after
+        2 ms of copying instead of 16.
+      * bucket=True (needs at least one mask): utterances are sorted by valid length and every slab is
+        trimmed to its own maxima (`bucket_plan`, `slab` x T_a audio rows per slab); all slabs are packed
+        by the host cores, which gather the slab's utterances, drop the padding and cast in one pass, and
+        the results are scattered back to the original order on the device.
+    Returns (logits, beta, z) on `out_device`; host results are fresh PINNED tensors filled by
+    asynchronous D2H copies (a pageable `.cpu()` of the 50 MB of z cost 31 ms per step).
+    trace (optional list): receives one dict of CUDA events per slab (tools/e2e_timeline.py)."""
     import threading
 
     dev = torch.device(device)
@@ -105,33 +304,58 @@ def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optio
         out = model(h_a.to(dev), h_t.to(dev), None if mask_a is None else mask_a.to(dev),
                     None if mask_t is None else mask_t.to(dev))[:3]
         return tuple(o.to(out_device) for o in out)
+    T_a, d_a = h_a.shape[1], h_a.shape[2]
+    T_t, d_t = h_t.shape[1], h_t.shape[2]
     slab = max(1, min(slab, B))
-    early = (h_a.dtype == torch.float32 and h_t.dtype == torch.float32 and h_a.shape[2] % 8 == 0
-             and h_t.shape[2] % 8 == 0)
-    starts = list(range(0, B, slab))
-    ends = starts[1:] + [B]
-    host_cast = bool(early and host_cast_every > 0 and len(starts) > 2)
-    on_host = [host_cast and (i % host_cast_every == host_cast_every - 1) for i in range(len(starts))]
-    st = _staging(dev, slab, h_a, h_t, mask_a, mask_t, host_cast)
+    h_a, h_t = h_a.contiguous(), h_t.contiguous()
+    early = (h_a.dtype == torch.float32 and h_t.dtype == torch.float32 and d_a % 8 == 0 and d_t % 8 == 0)
+    bucket = bool(bucket and early and (mask_a is not None or mask_t is not None) and T_a > 1)
+    mask_a = None if mask_a is None else mask_a.to(torch.bool).contiguous()
+    mask_t = None if mask_t is None else mask_t.to(torch.bool).contiguous()
+
+    # ---- the plan
+    if bucket:
+        len_a = valid_lengths(mask_a, B, T_a).clamp_(min=1)
+        len_t = valid_lengths(mask_t, B, T_t).clamp_(min=1)
+        order, buckets = bucket_plan(len_a, len_t, T_a, T_t, rows_per_slab=slab * T_a, max_utts=4 * slab)
+        order_dev = order.to(dev, non_blocking=True)
+        len_a_s, len_t_s = len_a[order.long()].contiguous(), len_t[order.long()].contiguous()
+        slabs = [_Slab(b.start, b.end, b.T_a, b.T_t, True, order[b.start:b.end].contiguous(), order_dev[b.start:b.end])
+                 for b in buckets]
+    else:
+        slabs = [_Slab(s, e, T_a, T_t, hc) for s, e, hc in slab_schedule(B, slab, host_cast_every if early else 0, ramp)]
+    rows_a = max(s.n * s.T_a for s in slabs)
+    rows_t = max(s.n * s.T_t for s in slabs)
+    any_host = any(s.host_cast for s in slabs)
+    st = _staging(dev, h_a.dtype, h_t.dtype, rows_a * d_a, rows_t * d_t, rows_a, rows_t,
+                  any(not s.host_cast for s in slabs), any_host, mask_a is not None, mask_t is not None)
     main = torch.cuda.current_stream(dev)
     copy = st["copy"]
-    outs = []
+    threads = max(1, torch.get_num_threads())
 
-    # ---- worker: host-side bf16 conversion of the designated slabs, in order
-    ready = [threading.Event() for _ in starts]
+    # ---- worker: host-side gather / trim / bf16 conversion of the designated slabs, in order
+    ready = [threading.Event() for _ in slabs]
     failure = []
 
     def convert():
         try:
             k = 0
-            for i, s in enumerate(starts):
-                if not on_host[i]:
+            for i, s in enumerate(slabs):
+                if not s.host_cast:
                     continue
                 hb = st["host16"][k % 2]
                 hb["sent"].synchronize()          # the copy that last read this host buffer is done
-                n = ends[i] - s
-                hb["a"][:n].copy_(h_a[s:s + n])   # fp32 -> bf16, round to nearest even, all intra-op threads
-                hb["t"][:n].copy_(h_t[s:s + n])
+                if s.utt is None:
+                    ops.host_pack_bf16(h_a[s.lo:s.hi], hb["a"], s.T_a, threads=threads)
+                    ops.host_pack_bf16(h_t[s.lo:s.hi], hb["t"], s.T_t, threads=threads)
+                else:
+                    ops.host_pack_bf16(h_a, hb["a"], s.T_a, s.utt, len_a_s[s.lo:s.hi], threads=threads)
+                    ops.host_pack_bf16(h_t, hb["t"], s.T_t, s.utt, len_t_s[s.lo:s.hi], threads=threads)
+                    # trimmed masks of the slab's utterances: boolean index bookkeeping on the host
+                    if mask_a is not None:
+                        hb["ma"][: s.n * s.T_a].view(s.n, s.T_a).copy_(_trim_mask(mask_a, s.utt, s.T_a))
+                    if mask_t is not None:
+                        hb["mt"][: s.n * s.T_t].view(s.n, s.T_t).copy_(_trim_mask(mask_t, s.utt, s.T_t))
                 ready[i].set()
                 k += 1
         except Exception as e:   # surfaced on the main thread
@@ -140,78 +364,113 @@ def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optio
                 ev.set()
 
     worker = None
-    if host_cast:
+    if any_host:
         worker = threading.Thread(target=convert, daemon=True)
         worker.start()
 
     n_host = [0]
+    n_direct = [0]
 
     def stage(i):
-        s = starts[i]
-        n = ends[i] - s
-        if on_host[i]:
+        s = slabs[i]
+        na, nt = s.n * s.T_a, s.n * s.T_t
+        if s.host_cast:
             k = n_host[0]
             n_host[0] += 1
             hb, buf = st["host16"][k % 2], st["dev16"][k % 2]
             ready[i].wait()
             if failure:
                 raise failure[0]
-            src_a, src_t = hb["a"], hb["t"]
+            src_a, src_t = hb["a"][: na * d_a], hb["t"][: nt * d_t]
         else:
-            hb, buf = None, st["bufs"][i % 2]
-            src_a, src_t = h_a[s:s + n], h_t[s:s + n]
+            hb, buf = None, st["direct"][n_direct[0] % 2]
+            n_direct[0] += 1
+            src_a, src_t = h_a[s.lo:s.hi].view(-1), h_t[s.lo:s.hi].view(-1)
         with torch.cuda.stream(copy):
             copy.wait_event(buf["consumed"])     # the slab that last used this device set is done with it
-            buf["a"][:n].copy_(src_a[:n], non_blocking=True)
-            buf["t"][:n].copy_(src_t[:n], non_blocking=True)
+            if trace is not None:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record(copy)
+            buf["a"][: na * d_a].copy_(src_a, non_blocking=True)
+            buf["t"][: nt * d_t].copy_(src_t, non_blocking=True)
+            if mask_a is not None:
+                buf["ma"][:na].copy_(hb["ma"][:na] if s.utt is not None else mask_a[s.lo:s.hi].view(-1), non_blocking=True)
+            if mask_t is not None:
+                buf["mt"][:nt].copy_(hb["mt"][:nt] if s.utt is not None else mask_t[s.lo:s.hi].view(-1), non_blocking=True)
             if hb is not None:
                 hb["sent"].record(copy)
-            if mask_a is not None:
-                buf["ma"][:n].copy_(mask_a[s:s + n], non_blocking=True)
-            if mask_t is not None:
-                buf["mt"][:n].copy_(mask_t[s:s + n], non_blocking=True)
+            if trace is not None:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record(copy)
+                trace.append(dict(slab=i, n=s.n, T_a=s.T_a, T_t=s.T_t, host_cast=s.host_cast, copy0=ev0, copy1=ev1))
             buf["copied"].record(copy)
-        return n, buf
+        return buf
 
     to_host = torch.device(out_device).type == "cpu"
-    host_out = None   # pinned result tensors (from torch's caching host allocator), filled slab by slab
+    outs = []
+    host_out = None   # pinned result tensors (from torch's caching host allocator)
+    dev_out = None    # bucketed plan: full-size device results in the ORIGINAL order
 
     def emit(i, res):
-        nonlocal host_out
+        nonlocal host_out, dev_out
+        s = slabs[i]
+        if s.utt is not None:
+            if dev_out is None:
+                dev_out = [torch.empty((B,) + tuple(r.shape[1:]), dtype=torch.float32, device=dev) for r in res]
+            for dst, r in zip(dev_out, res):
+                ops.scatter_rows(r if r.dtype == torch.float32 else r.float(), s.utt_dev, dst)
+            return
         if not to_host:
             outs.append(res)
             return
         if host_out is None:
             host_out = [torch.empty((B,) + tuple(r.shape[1:]), dtype=r.dtype, pin_memory=True) for r in res]
-        s0 = starts[i]
         for dst, r in zip(host_out, res):
-            dst[s0:s0 + r.shape[0]].copy_(r, non_blocking=True)   # D2H on the compute stream, behind this slab
+            dst[s.lo:s.lo + r.shape[0]].copy_(r, non_blocking=True)   # D2H on the compute stream, behind this slab
 
     staged = {0: stage(0)}
-    if len(starts) > 1:
+    if len(slabs) > 1:
         staged[1] = stage(1)
-    for i in range(len(starts)):
-        n, buf = staged.pop(i)
+    for i, s in enumerate(slabs):
+        n = s.n
+        buf = staged.pop(i)
         main.wait_event(buf["copied"])
-        ma = None if mask_a is None else buf["ma"][:n].clone()
-        mt = None if mask_t is None else buf["mt"][:n].clone()
-        if on_host[i]:
+        if trace is not None:
+            k0 = torch.cuda.Event(enable_timing=True)
+            k0.record(main)
+        ma = None if mask_a is None else buf["ma"][: n * s.T_a].view(n, s.T_a).clone()
+        mt = None if mask_t is None else buf["mt"][: n * s.T_t].view(n, s.T_t).clone()
+        va = buf["a"][: n * s.T_a * d_a].view(n, s.T_a, d_a)
+        vt = buf["t"][: n * s.T_t * d_t].view(n, s.T_t, d_t)
+        if s.host_cast:
             # bf16 landed on the device: the model reads it in place; the set is free after the forward
-            emit(i, model(buf["a"][:n], buf["t"][:n], ma, mt)[:3])
+            emit(i, model(va, vt, ma, mt)[:3])
             buf["consumed"].record(main)
         elif early:
             # the fp32 features are only read by the bf16 cast: after it the staging set is free again
-            xa = E.to_seq(buf["a"][:n], "h_a").x.view(n, h_a.shape[1], -1)
-            xt = E.to_seq(buf["t"][:n], "h_t").x.view(n, h_t.shape[1], -1)
+            xa = E.to_seq(va, "h_a").x.view(n, s.T_a, -1)
+            xt = E.to_seq(vt, "h_t").x.view(n, s.T_t, -1)
             buf["consumed"].record(main)
             emit(i, model(xa, xt, ma, mt)[:3])
         else:
-            emit(i, model(buf["a"][:n], buf["t"][:n], ma, mt)[:3])
+            emit(i, model(va, vt, ma, mt)[:3])
             buf["consumed"].record(main)
-        if i + 2 < len(starts):
+        if trace is not None:
+            k1 = torch.cuda.Event(enable_timing=True)
+            k1.record(main)
+            trace[i]["comp0"], trace[i]["comp1"] = k0, k1
+        if i + 2 < len(slabs):
             staged[i + 2] = stage(i + 2)
     if worker is not None:
         worker.join()
+    if dev_out is not None:
+        if not to_host:
+            return tuple(o.to(out_device) for o in dev_out)
+        host_out = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in dev_out]
+        for dst, o in zip(host_out, dev_out):
+            dst.copy_(o, non_blocking=True)
+        main.synchronize()
+        return tuple(host_out)
     if to_host:
         main.synchronize()
         return tuple(host_out)

@@ -224,6 +224,40 @@ int hriemo_gate_blend(const void* a_bf16, int64_t lda, int32_t T_a, const void* 
 int hriemo_emotion_outputs(const float* logits, const float* thresholds, float* probs, uint8_t* decisions,
                            int64_t B, int32_t n_classes, void* stream);
 
+/* ------------------------------------------------- length-bucketed staging ----
+ * The step BEFORE the path.  The reference's collate zero-pads every
+ * utterance to the batch maximum and marks the tail True = PAD
+ * (scripts/fusion/train_fusion_seq_level_decoder.py:191-232, scripts/infer/mosei_eval_infer.py:128-147).
+ * Padded rows never reach logits / beta / z, so hriemo.pipeline sorts utterances by valid length
+ * and runs slabs trimmed to their own maximum; these entry points build and un-build such slabs.
+ */
+/* lens[b] = (index of the last entry of pad[b, :] that is 0) + 1, or 0 when every entry is PAD. */
+int hriemo_mask_lengths(const uint8_t* pad, int32_t B, int32_t T, int32_t* lens, void* stream);
+
+/* out[i, t, :] = bf16(in[utt[i], t, :]) for t < min(T_in, T_out); rows T_in <= t < T_out and columns
+ * cols <= c < ld_out are zero.  in is [B, T_in, ld_in] f32 (in_is_f32 = 1) or bf16; utt is int32 [n]. */
+int hriemo_gather_utterances_bf16(const void* in, int32_t in_is_f32, int64_t ld_in, int32_t T_in,
+                                  const int32_t* utt, void* out_bf16, int64_t ld_out, int32_t n,
+                                  int32_t T_out, int32_t cols, void* stream);
+
+/* out[i, t] = pad[utt[i], t] for t < min(T_in, T_out), 1 (PAD) for T_in <= t < T_out. */
+int hriemo_gather_masks(const uint8_t* pad, int32_t T_in, const int32_t* utt, uint8_t* out, int32_t n,
+                        int32_t T_out, void* stream);
+
+/* out[utt[i], :] = in[i, :] (f32, `cols` contiguous elements per row): a slab's logits / beta / z
+ * go back to the utterances' original positions. */
+int hriemo_scatter_rows_f32(const float* in, const int32_t* utt, float* out, int64_t n, int64_t cols,
+                            void* stream);
+
+/* HOST function: every pointer is a HOST pointer, no device work, no stream.  Same gather + trim as
+ * hriemo_gather_utterances_bf16 for a padded fp32 batch that lives in host memory, written as bf16 into
+ * (pinned) staging memory by `n_threads` C++ threads: dst[i, t, :] = bf16_rne(src[utt[i], t, :]) for
+ * t < min(lens[i], T_in, T_out), zero elsewhere.  utt NULL = identity, lens NULL = T_in for everyone.
+ * Rounding is round-to-nearest-even like the GPU cast, so results are bit-identical to it. */
+int hriemo_host_pack_bf16(const float* src, int64_t ld_src, int64_t T_in, int64_t cols, const int32_t* utt,
+                          const int32_t* lens, void* dst_bf16, int64_t ld_dst, int64_t T_out, int64_t n,
+                          int32_t n_threads);
+
 /* Mean over time (UNMASKED) of an f32 [B,L,d] tensor — models/fusion_classifier.py:145. */
 int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d, void* stream);
 

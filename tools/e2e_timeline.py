@@ -1,46 +1,36 @@
-"""Timeline of one forward_from_host call: per-slab copy and compute intervals (CUDA events)."""
+"""Timeline of forward_from_host calls (its `trace` argument): per-slab copy and compute intervals.
+    python tools/e2e_timeline.py [--slab N] [--every K] [--no-ramp] [--ragged] [--bucket]"""
 import os, sys, time, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "hri-emo_b200"))
-from hriemo import pipeline, engine as E
+from hriemo import pipeline
 from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+def arg(name, default):
+    return type(default)(sys.argv[sys.argv.index(name) + 1]) if name in sys.argv else default
+
 dev = torch.device("cuda")
 torch.manual_seed(0)
 model = FusionWithEmotionDecoder().eval().to(dev)
-B, Ta, Tt, slab = 4096, 500, 64, 512
+B, Ta, Tt = arg("--batch", 4096), 500, 64
+slab, every = arg("--slab", 512), arg("--every", 2)
+ramp, ragged, bucket = "--no-ramp" not in sys.argv, "--ragged" in sys.argv, "--bucket" in sys.argv
 ha = torch.empty((B, Ta, 768)).pin_memory(); ht = torch.empty((B, Tt, 768)).pin_memory()
 ha.normal_(); ht.normal_()
-# hand-rolled version of the fp32 path with events
-bufs = [(torch.empty((slab, Ta, 768), device=dev), torch.empty((slab, Tt, 768), device=dev)) for _ in range(2)]
-copy = torch.cuda.Stream()
-main = torch.cuda.current_stream()
-def run(do_compute, do_copy):
-    ev = []
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
-    t00 = torch.cuda.Event(enable_timing=True); t00.record()
-    torch.cuda.synchronize(); w0 = time.perf_counter()
-    for i, s in enumerate(range(0, B, slab)):
-        a, t = bufs[i % 2]
-        c0, c1, k0, k1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
-        with torch.cuda.stream(copy):
-            copy.wait_event(consumed[i % 2])
-            c0.record(copy)
-            if do_copy:
-                a.copy_(ha[s:s + slab], non_blocking=True); t.copy_(ht[s:s + slab], non_blocking=True)
-            c1.record(copy)
-        main.wait_event(c1)
-        k0.record(main)
-        if do_compute:
-            xa = E.to_seq(a, "a").x.view(slab, Ta, -1); xt = E.to_seq(t, "t").x.view(slab, Tt, -1)
-            consumed[i % 2].record(main)
-            model(xa, xt)
-        else:
-            consumed[i % 2].record(main)
-        k1.record(main)
-        ev.append((c0, c1, k0, k1))
-    cpu_enqueue = time.perf_counter() - w0
-    torch.cuda.synchronize(); wall = time.perf_counter() - w0
-    print(f"compute={do_compute} copy={do_copy}: wall {wall*1e3:.1f} ms, CPU enqueue {cpu_enqueue*1e3:.1f} ms")
-    for i, (c0, c1, k0, k1) in enumerate(ev):
-        print(f"  slab {i}: copy {t00.elapsed_time(c0):6.1f} -> {t00.elapsed_time(c1):6.1f} ({c0.elapsed_time(c1):5.1f})   compute {t00.elapsed_time(k0):6.1f} -> {t00.elapsed_time(k1):6.1f} ({k0.elapsed_time(k1):5.1f})")
-run(True, True); run(True, True); run(True, False); run(False, True)
+ma = mt = None
+if ragged:
+    g = torch.Generator().manual_seed(1)
+    la = torch.randint(Ta // 2, Ta + 1, (B,), generator=g); lt = torch.randint(Tt // 2, Tt + 1, (B,), generator=g)
+    ma = (torch.arange(Ta)[None] >= la[:, None]).pin_memory(); mt = (torch.arange(Tt)[None] >= lt[:, None]).pin_memory()
+print(f"B={B} slab={slab} host_cast_every={every} ramp={ramp} ragged={ragged} bucket={bucket} threads={torch.get_num_threads()}")
+for rep in range(3):
+    trace = [] if rep == 2 else None
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True); t0.record()
+    w0 = time.perf_counter()
+    pipeline.forward_from_host(model, ha, ht, ma, mt, device=dev, slab=slab, host_cast_every=every, ramp=ramp, bucket=bucket, trace=trace)
+    wall = time.perf_counter() - w0
+    print(f"  call {rep}: wall {wall*1e3:.1f} ms = {B / wall:.0f} utt/s")
+for r in trace:
+    print(f"  slab {r['slab']:2d} n={r['n']:4d} T_a={r['T_a']:3d} {'host' if r['host_cast'] else 'fp32'}: copy {t0.elapsed_time(r['copy0']):6.1f} -> {t0.elapsed_time(r['copy1']):6.1f} ({r['copy0'].elapsed_time(r['copy1']):5.1f})"
+          f"   compute {t0.elapsed_time(r['comp0']):6.1f} -> {t0.elapsed_time(r['comp1']):6.1f} ({r['comp0'].elapsed_time(r['comp1']):5.1f})")
