@@ -172,8 +172,36 @@ layernorm_kernel(const void* __restrict__ x, int64_t ldx, const float* __restric
 }
 
 // ------------------------------------------------------------------ gate: LN + masked mean
+// Row statistics of a warp-held row (two-pass: mean, then biased variance).
+template <int NV>
+__device__ __forceinline__ void row_stats(const RowRegs<NV>& r, int d, int lane, float eps, float& mean, float& rstd) {
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += r.v[i][k];
+  mean = warp_sum(s) / static_cast<float>(d);
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < d) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float t = r.v[i][k] - mean;
+        q += t * t;
+      }
+    }
+  }
+  rstd = rsqrtf(warp_sum(q) / static_cast<float>(d) + eps);
+}
+
 // One CTA per utterance; warp w reduces rows t = w, w+8, ... in registers, then the
 // 8 partial sums are combined through shared memory in a fixed order (deterministic).
+// The parameter vectors are kept off the per-row path (a row is 2 d bytes, each parameter vector 4 d):
+// the pending LayerNorm's (gamma, beta) live in registers for the whole utterance, and the gate's own
+// LayerNorm is linear after the row statistics, so its gamma / beta are applied once to the sum:
+//   mean_t LN(y_t) = gamma * [sum_t (y_t - m_t) rstd_t] / n + beta * count / n.
 template <int NV>
 __global__ void __launch_bounds__(256)
 ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
@@ -184,31 +212,73 @@ ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const fl
   extern __shared__ float part[];  // [8][d]
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  RowRegs<NV> acc;
+  RowRegs<NV> acc, pg, pb;
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc.v[i][k] = 0.0f;
+    for (int k = 0; k < 8; ++k) {
+      acc.v[i][k] = 0.0f;
+      pg.v[i][k] = (pre_g != nullptr && c < d) ? __ldg(pre_g + c + k) : 0.0f;
+      pb.v[i][k] = (pre_g != nullptr && c < d) ? __ldg(pre_b + c + k) : 0.0f;
+    }
+  }
   int count = 0;
-  for (int t = warp; t < T; t += 8) {
-    const bool valid = pad == nullptr || pad[static_cast<int64_t>(b) * T + t] == 0;
-    if (!valid) continue;  // warp-uniform
+  // the next valid row is already in flight (as raw bf16) while the current one is reduced
+  auto next_valid = [&](int t) {
+    while (t < T && pad != nullptr && pad[static_cast<int64_t>(b) * T + t] != 0) t += 8;   // warp-uniform
+    return t;
+  };
+  uint4 raw[NV];
+  auto fetch = [&](int t) {
+    const __nv_bfloat16* row = x + (static_cast<int64_t>(b) * T + t) * ldx;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      raw[i] = c < d ? __ldg(reinterpret_cast<const uint4*>(row + c)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  int t = next_valid(warp);
+  if (t < T) fetch(t);
+  while (t < T) {
     ++count;
     RowRegs<NV> r;
-    load_row<false, NV>(r, x + (static_cast<int64_t>(b) * T + t) * ldx, d, lane);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) unpack8(raw[i], r.v[i]);
+    const int t_next = next_valid(t + 8);
+    if (t_next < T) fetch(t_next);
     if (pre_g != nullptr) {
+      float m1, r1;
       if (pre_stats != nullptr) {
         const float2 st = __ldg(pre_stats + static_cast<int64_t>(b) * T + t);
-        affine_row(r, d, lane, pre_g, pre_b, st.x, st.y);
+        m1 = st.x;
+        r1 = st.y;
       } else {
-        normalize_row(r, d, lane, pre_g, pre_b, eps);
+        row_stats(r, d, lane, eps, m1, r1);
       }
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r.v[i][k] = (r.v[i][k] - m1) * r1 * pg.v[i][k] + pb.v[i][k];  // 0 past d
     }
-    if (apply_ln) normalize_row(r, d, lane, gamma, beta, eps);
+    if (apply_ln) {
+      float m2, r2;
+      row_stats(r, d, lane, eps, m2, r2);
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        if (c < d) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc.v[i][k] += r.v[i][k];
+          for (int k = 0; k < 8; ++k) acc.v[i][k] += (r.v[i][k] - m2) * r2;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc.v[i][k] += r.v[i][k];
+    }
+    t = t_next;
   }
   __shared__ int counts[8];
   if (lane == 0) counts[warp] = count;
@@ -226,11 +296,13 @@ ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const fl
   for (int w = 0; w < 8; ++w) total += counts[w];
   // mask None -> plain mean over T; else sum / clamp(count, 1)   (beta_gate_tacfn.py:17-24)
   const float denom = pad == nullptr ? static_cast<float>(T) : fmaxf(static_cast<float>(total), 1.0f);
+  const float frac = static_cast<float>(total) / denom;   // 1, or 0 when every row is PAD
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     float s = 0.0f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += part[w * d + c];
-    pooled[static_cast<int64_t>(b) * ld_pooled + c] = s / denom;
+    s /= denom;
+    pooled[static_cast<int64_t>(b) * ld_pooled + c] = apply_ln ? fmaf(__ldg(gamma + c), s, __ldg(beta + c) * frac) : s;
   }
 }
 

@@ -48,6 +48,12 @@ class AttnArgs(C.Structure):
     ]
 
 
+class ShardInfo(C.Structure):
+    _fields_ = [("n_utt", C.c_int64), ("rows_a", C.c_int64), ("rows_t", C.c_int64), ("meta_bytes", C.c_int64),
+                ("d_a", C.c_int32), ("d_t", C.c_int32), ("dtype", C.c_int32),
+                ("max_len_a", C.c_int32), ("max_len_t", C.c_int32)]
+
+
 _P, _I64, _I32, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 
 # name -> (restype, argtypes); must list every symbol include/hriemo.h declares
@@ -76,6 +82,12 @@ SIGNATURES = {
     "hriemo_gather_utterances_bf16": (C.c_int, [_P, _I32, _I64, _I32, _P, _P, _I64, _I32, _I32, _I32, _P]),
     "hriemo_gather_masks": (C.c_int, [_P, _I32, _P, _P, _I32, _I32, _P]),
     "hriemo_scatter_rows_f32": (C.c_int, [_P, _P, _P, _I64, _I64, _P]),
+    "hriemo_shard_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "hriemo_shard_info": (C.c_int, [_P, C.POINTER(ShardInfo)]),
+    "hriemo_shard_lengths": (C.c_int, [_P, _P, _P]),
+    "hriemo_shard_meta": (C.c_int, [_P, _P, _I64]),
+    "hriemo_shard_read": (C.c_int, [_P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _I32]),
+    "hriemo_shard_close": (C.c_int, [_P]),
     "hriemo_host_pack_bf16": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, _I64, _I64, _I32]),
 }
 

@@ -22,6 +22,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import engine as E
+from . import lib as L
 from . import ops
 
 
@@ -68,14 +69,15 @@ def gather_outputs(logits: torch.Tensor, beta: torch.Tensor, group=None):
 # --------------------------------------------------------------------------- #
 # slab plans
 # --------------------------------------------------------------------------- #
-def slab_schedule(B: int, slab: int = 512, host_cast_every: int = 2, ramp: bool = True):
+def slab_schedule(B: int, slab: int = 512, host_cast_every: int = 2, ramp: bool = False):
     """The slab plan forward_from_host follows for a dense batch: [(start, end, host_cast)], in order.
 
-    Nothing computes until the first slab has landed, so the plan opens with a short RAMP of small
-    fp32 slabs (slab/8, slab/4, slab/2 utterances; only when at least four full slabs follow) and
-    continues with full slabs, every `host_cast_every`-th of which (0 = never) is converted to bf16 by
-    the host cores and travels at half the bytes.  Ramp slabs are never host-cast: the host has had
-    no time to convert them."""
+    Full slabs, every `host_cast_every`-th of which (0 = never) is converted to bf16 by the host cores
+    and travels at half the bytes.  ramp=True opens the plan with small fp32 slabs (slab/8, slab/4,
+    slab/2 utterances; only when at least four full slabs follow) so that the GPU starts after 2 ms of
+    copying instead of 16 -- measured on B200 it does not pay: a 64-utterance slab computes at half the
+    rate of a 512-utterance one (launch-bound decoder tail), which costs what the earlier start saves
+    (tools/e2e_schedule_sim.py, profiles/r01_e2e_timeline_v11.txt), so it is off by default."""
     slab = max(1, min(slab, B))
     sizes = []
     left = B
@@ -98,7 +100,7 @@ def slab_schedule(B: int, slab: int = 512, host_cast_every: int = 2, ramp: bool 
     return plan
 
 
-def h2d_bytes(B: int, fp32_bytes_per_utt: int, slab: int = 512, host_cast_every: int = 2, ramp: bool = True) -> int:
+def h2d_bytes(B: int, fp32_bytes_per_utt: int, slab: int = 512, host_cast_every: int = 2, ramp: bool = False) -> int:
     """Bytes forward_from_host copies host->device for B dense utterances of fp32 features whose feature
     dims are multiples of 8: host-pre-cast slabs travel as bf16 (half the bytes)."""
     return sum((e - s) * fp32_bytes_per_utt // (2 if half else 1)
@@ -127,10 +129,11 @@ class Bucket:
 
 
 def bucket_plan(len_a: torch.Tensor, len_t: torch.Tensor, T_a: int, T_t: int, rows_per_slab: int = 512 * 500,
-                max_utts: int = 2048) -> Tuple[torch.Tensor, List[Bucket]]:
+                max_utts: int = 2048, ramp: bool = False) -> Tuple[torch.Tensor, List[Bucket]]:
     """Sort utterances by valid length (audio first, then text; ascending, so the plan opens with the
     cheap slabs and the pipeline fills quickly) and cut the order into slabs of at most `rows_per_slab`
-    audio rows / `max_utts` utterances, each trimmed to its own maxima.
+    audio rows / `max_utts` utterances, each trimmed to its own maxima.  ramp: the first two slabs get a
+    quarter and a half of the row budget (host staging: nothing computes until the first slab has landed).
 
     The trimmed extents keep what the reference's forward needs: at least one row per stream (a fully
     padded utterance still runs, all-masked, and comes out NaN like the reference), and T_a >= T_t
@@ -142,13 +145,17 @@ def bucket_plan(len_a: torch.Tensor, len_t: torch.Tensor, T_a: int, T_t: int, ro
     order = torch.argsort(la * (T_t + 1) + lt, stable=True)
     la_s, lt_s = la[order].tolist(), lt[order].tolist()
     buckets: List[Bucket] = []
+    total_rows = sum(la_s)
     s = 0
     while s < B:
         e = s
         ta = tt = 1
+        budget = rows_per_slab
+        if ramp and len(buckets) < 2 and total_rows > 4 * rows_per_slab:
+            budget = rows_per_slab // (4 >> len(buckets))
         while e < B and e - s < max_utts:
             ta2, tt2 = max(ta, la_s[e]), max(tt, lt_s[e])
-            if e > s and (e - s + 1) * max(ta2, tt2) > rows_per_slab:
+            if e > s and (e - s + 1) * max(ta2, tt2) > budget:
                 break
             ta, tt = ta2, tt2
             e += 1
@@ -214,9 +221,9 @@ def forward_bucketed(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Option
 _STAGING = {}   # configuration -> staging buffers + events, reused across calls
 
 
-def _staging(dev, dtype_a, dtype_t, elems_a: int, elems_t: int, rows_a: int, rows_t: int, direct_sets: bool,
+def _staging(dev, dtype_a, dtype_t, host_dtype, elems_a: int, elems_t: int, rows_a: int, rows_t: int, direct_sets: bool,
              host_sets: bool, with_ma: bool, with_mt: bool):
-    key = (str(dev), dtype_a, dtype_t, elems_a, elems_t, rows_a, rows_t, direct_sets, host_sets, with_ma, with_mt)
+    key = (str(dev), dtype_a, dtype_t, host_dtype, elems_a, elems_t, rows_a, rows_t, direct_sets, host_sets, with_ma, with_mt)
     st = _STAGING.get(key)
     if st is None:
         def mk(da, dt):
@@ -231,16 +238,15 @@ def _staging(dev, dtype_a, dtype_t, elems_a: int, elems_t: int, rows_a: int, row
             # landing sets of the source dtype: free again as soon as the GPU bf16 cast has read them
             st["direct"] = [mk(dtype_a, dtype_t), mk(dtype_a, dtype_t)]
         if host_sets:
-            # slabs converted to bf16 by the host cores: pinned bf16 staging on the host (ping-pong) and
-            # bf16 landing buffers on the device (ping-pong, released when the slab's forward is done)
+            # slabs prepared by the host cores (bf16 pack of a padded batch, or rows of a shard): pinned staging
+            # on the host (ping-pong) and landing buffers on the device (ping-pong, released when the slab's
+            # forward is done)
             def mk_host():
-                return dict(a=torch.empty((elems_a,), dtype=torch.bfloat16).pin_memory(),
-                            t=torch.empty((elems_t,), dtype=torch.bfloat16).pin_memory(),
-                            ma=torch.empty((rows_a,), dtype=torch.bool).pin_memory() if with_ma else None,
-                            mt=torch.empty((rows_t,), dtype=torch.bool).pin_memory() if with_mt else None,
+                return dict(a=torch.empty((elems_a,), dtype=host_dtype).pin_memory(),
+                            t=torch.empty((elems_t,), dtype=host_dtype).pin_memory(),
                             sent=torch.cuda.Event())
             st["host16"] = [mk_host(), mk_host()]
-            st["dev16"] = [mk(torch.bfloat16, torch.bfloat16), mk(torch.bfloat16, torch.bfloat16)]
+            st["dev16"] = [mk(host_dtype, host_dtype), mk(host_dtype, host_dtype)]
         _STAGING.clear()      # keep one configuration resident
         _STAGING[key] = st
     return st
@@ -252,112 +258,54 @@ class _Slab:
     hi: int                         # bucketed plan: positions [lo, hi) of the sorted order
     T_a: int
     T_t: int
-    host_cast: bool
-    utt: Optional[torch.Tensor] = None      # bucketed: int32 host indices of the slab's utterances
-    utt_dev: Optional[torch.Tensor] = None
+    host_cast: bool                 # prepared by the host worker (pack / shard read) instead of copied as it is
+    utt: Optional[torch.Tensor] = None      # bucketed: host indices of the slab's utterances
+    utt_dev: Optional[torch.Tensor] = None  # the same as int32 on the device (mask gather, result scatter)
 
     @property
     def n(self) -> int:
         return self.hi - self.lo
 
 
-def _trim_mask(mask: torch.Tensor, utt: torch.Tensor, T_out: int) -> torch.Tensor:
-    """Host [B, T] bool mask -> [n, T_out] for utterances utt (positions past T are PAD)."""
-    m = mask.index_select(0, utt.long())
-    T = m.shape[1]
-    if T_out <= T:
-        return m[:, :T_out]
-    return torch.cat([m, torch.ones((m.shape[0], T_out - T), dtype=torch.bool)], dim=1)
-
-
-@torch.no_grad()
-def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optional[torch.Tensor] = None,
-                      mask_t: Optional[torch.Tensor] = None, device="cuda", slab: int = 512,
-                      out_device="cpu", host_cast_every: int = 2, ramp: bool = True, bucket: bool = False,
-                      trace: Optional[list] = None):
-    """model(h_a, h_t, mask_a, mask_t) for HOST tensors with copy/compute overlap.
-
-    The batch is cut into slabs of utterances that flow through fixed staging buffers (nothing is
-    allocated or freed per slab for the inputs) on a side stream while earlier slabs compute:
-      * fp32 slabs are copied as they are and cast to bf16 on the GPU; their staging set is free again
-        as soon as the cast has read it;
-      * every `host_cast_every`-th slab (0 = never) is instead converted to bf16 by the host cores
-        (hriemo_host_pack_bf16 in a worker thread) into pinned bf16 staging and copied at half the
-        bytes.  A step is bounded by the 55 GB/s H2D copy of the fp32 features (7.1 GB at the
-        north-star batch); with every second slab pre-cast the copy drops under the compute time.
-        The rounding is the same round-to-nearest-even as the GPU cast: results are bit-identical.
-      * the plan opens with a ramp of small slabs (`slab_schedule`) so the GPU starts computing after
-        2 ms of copying instead of 16.
-      * bucket=True (needs at least one mask): utterances are sorted by valid length and every slab is
-        trimmed to its own maxima (`bucket_plan`, `slab` x T_a audio rows per slab); all slabs are packed
-        by the host cores, which gather the slab's utterances, drop the padding and cast in one pass, and
-        the results are scattered back to the original order on the device.
-    Returns (logits, beta, z) on `out_device`; host results are fresh PINNED tensors filled by
-    asynchronous D2H copies (a pageable `.cpu()` of the 50 MB of z cost 31 ms per step).
-    trace (optional list): receives one dict of CUDA events per slab (tools/e2e_timeline.py)."""
+def _run_pipeline(model, dev, B: int, slabs: List[_Slab], d_a: int, d_t: int, dtype_a, dtype_t, host_dtype,
+                  pack, direct_src, mask_a, mask_t, mask_a_dev, mask_t_dev, early: bool, out_device, trace):
+    """The staging engine behind forward_from_host / forward_from_shard: slab i+1 (and i+2) is prepared
+    and copied on a side stream while slab i computes.
+      pack(s, hb)      fills the pinned host set hb["a"], hb["t"] for a host-prepared slab (worker thread);
+      direct_src(s)    -> flat host views (a, t) of a slab that is copied as it is;
+      mask_a / mask_t  host masks of dense slabs (copied per slab); mask_*_dev: whole masks already on the
+                       device for bucketed slabs (each slab gathers and trims its own)."""
     import threading
 
-    dev = torch.device(device)
-    B = h_a.shape[0]
-    if h_a.dim() != 3 or h_t.dim() != 3:
-        # utterance-level [B, d] inputs: nothing to pipeline
-        out = model(h_a.to(dev), h_t.to(dev), None if mask_a is None else mask_a.to(dev),
-                    None if mask_t is None else mask_t.to(dev))[:3]
-        return tuple(o.to(out_device) for o in out)
-    T_a, d_a = h_a.shape[1], h_a.shape[2]
-    T_t, d_t = h_t.shape[1], h_t.shape[2]
-    slab = max(1, min(slab, B))
-    h_a, h_t = h_a.contiguous(), h_t.contiguous()
-    early = (h_a.dtype == torch.float32 and h_t.dtype == torch.float32 and d_a % 8 == 0 and d_t % 8 == 0)
-    bucket = bool(bucket and early and (mask_a is not None or mask_t is not None) and T_a > 1)
-    mask_a = None if mask_a is None else mask_a.to(torch.bool).contiguous()
-    mask_t = None if mask_t is None else mask_t.to(torch.bool).contiguous()
-
-    # ---- the plan
-    if bucket:
-        len_a = valid_lengths(mask_a, B, T_a).clamp_(min=1)
-        len_t = valid_lengths(mask_t, B, T_t).clamp_(min=1)
-        order, buckets = bucket_plan(len_a, len_t, T_a, T_t, rows_per_slab=slab * T_a, max_utts=4 * slab)
-        order_dev = order.to(dev, non_blocking=True)
-        len_a_s, len_t_s = len_a[order.long()].contiguous(), len_t[order.long()].contiguous()
-        slabs = [_Slab(b.start, b.end, b.T_a, b.T_t, True, order[b.start:b.end].contiguous(), order_dev[b.start:b.end])
-                 for b in buckets]
-    else:
-        slabs = [_Slab(s, e, T_a, T_t, hc) for s, e, hc in slab_schedule(B, slab, host_cast_every if early else 0, ramp)]
     rows_a = max(s.n * s.T_a for s in slabs)
     rows_t = max(s.n * s.T_t for s in slabs)
     any_host = any(s.host_cast for s in slabs)
-    st = _staging(dev, h_a.dtype, h_t.dtype, rows_a * d_a, rows_t * d_t, rows_a, rows_t,
-                  any(not s.host_cast for s in slabs), any_host, mask_a is not None, mask_t is not None)
+    dense_masks = any(s.utt is None for s in slabs)
+    st = _staging(dev, dtype_a, dtype_t, host_dtype, rows_a * d_a, rows_t * d_t, rows_a, rows_t,
+                  any(not s.host_cast for s in slabs), any_host, mask_a is not None and dense_masks,
+                  mask_t is not None and dense_masks)
     main = torch.cuda.current_stream(dev)
     copy = st["copy"]
-    threads = max(1, torch.get_num_threads())
 
-    # ---- worker: host-side gather / trim / bf16 conversion of the designated slabs, in order
+    # ---- worker: host-side preparation of the designated slabs, in order
     ready = [threading.Event() for _ in slabs]
+    enqueued = [threading.Event() for _ in slabs]   # the main thread has enqueued slab i's copies (and recorded `sent`)
+    host_ids = [i for i, s in enumerate(slabs) if s.host_cast]
     failure = []
 
-    def convert():
+    def prepare():
         try:
-            k = 0
-            for i, s in enumerate(slabs):
-                if not s.host_cast:
-                    continue
+            for k, i in enumerate(host_ids):
                 hb = st["host16"][k % 2]
+                if k >= 2:
+                    # this host buffer last carried host slab k-2: its copy must have been ENQUEUED (the event
+                    # below is re-recorded per use) before waiting for it to have been READ
+                    enqueued[host_ids[k - 2]].wait()
+                    if failure:
+                        return
                 hb["sent"].synchronize()          # the copy that last read this host buffer is done
-                if s.utt is None:
-                    ops.host_pack_bf16(h_a[s.lo:s.hi], hb["a"], s.T_a, threads=threads)
-                    ops.host_pack_bf16(h_t[s.lo:s.hi], hb["t"], s.T_t, threads=threads)
-                else:
-                    ops.host_pack_bf16(h_a, hb["a"], s.T_a, s.utt, len_a_s[s.lo:s.hi], threads=threads)
-                    ops.host_pack_bf16(h_t, hb["t"], s.T_t, s.utt, len_t_s[s.lo:s.hi], threads=threads)
-                    # trimmed masks of the slab's utterances: boolean index bookkeeping on the host
-                    if mask_a is not None:
-                        hb["ma"][: s.n * s.T_a].view(s.n, s.T_a).copy_(_trim_mask(mask_a, s.utt, s.T_a))
-                    if mask_t is not None:
-                        hb["mt"][: s.n * s.T_t].view(s.n, s.T_t).copy_(_trim_mask(mask_t, s.utt, s.T_t))
+                pack(slabs[i], hb)
                 ready[i].set()
-                k += 1
         except Exception as e:   # surfaced on the main thread
             failure.append(e)
             for ev in ready:
@@ -365,7 +313,7 @@ def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optio
 
     worker = None
     if any_host:
-        worker = threading.Thread(target=convert, daemon=True)
+        worker = threading.Thread(target=prepare, daemon=True)
         worker.start()
 
     n_host = [0]
@@ -385,7 +333,7 @@ def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optio
         else:
             hb, buf = None, st["direct"][n_direct[0] % 2]
             n_direct[0] += 1
-            src_a, src_t = h_a[s.lo:s.hi].view(-1), h_t[s.lo:s.hi].view(-1)
+            src_a, src_t = direct_src(s)
         with torch.cuda.stream(copy):
             copy.wait_event(buf["consumed"])     # the slab that last used this device set is done with it
             if trace is not None:
@@ -393,10 +341,11 @@ def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optio
                 ev0.record(copy)
             buf["a"][: na * d_a].copy_(src_a, non_blocking=True)
             buf["t"][: nt * d_t].copy_(src_t, non_blocking=True)
-            if mask_a is not None:
-                buf["ma"][:na].copy_(hb["ma"][:na] if s.utt is not None else mask_a[s.lo:s.hi].view(-1), non_blocking=True)
-            if mask_t is not None:
-                buf["mt"][:nt].copy_(hb["mt"][:nt] if s.utt is not None else mask_t[s.lo:s.hi].view(-1), non_blocking=True)
+            if s.utt is None:
+                if mask_a is not None:
+                    buf["ma"][:na].copy_(mask_a[s.lo:s.hi].view(-1), non_blocking=True)
+                if mask_t is not None:
+                    buf["mt"][:nt].copy_(mask_t[s.lo:s.hi].view(-1), non_blocking=True)
             if hb is not None:
                 hb["sent"].record(copy)
             if trace is not None:
@@ -404,6 +353,7 @@ def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optio
                 ev1.record(copy)
                 trace.append(dict(slab=i, n=s.n, T_a=s.T_a, T_t=s.T_t, host_cast=s.host_cast, copy0=ev0, copy1=ev1))
             buf["copied"].record(copy)
+        enqueued[i].set()
         return buf
 
     to_host = torch.device(out_device).type == "cpu"
@@ -428,53 +378,176 @@ def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optio
         for dst, r in zip(host_out, res):
             dst[s.lo:s.lo + r.shape[0]].copy_(r, non_blocking=True)   # D2H on the compute stream, behind this slab
 
-    staged = {0: stage(0)}
-    if len(slabs) > 1:
-        staged[1] = stage(1)
-    for i, s in enumerate(slabs):
-        n = s.n
-        buf = staged.pop(i)
-        main.wait_event(buf["copied"])
-        if trace is not None:
-            k0 = torch.cuda.Event(enable_timing=True)
-            k0.record(main)
-        ma = None if mask_a is None else buf["ma"][: n * s.T_a].view(n, s.T_a).clone()
-        mt = None if mask_t is None else buf["mt"][: n * s.T_t].view(n, s.T_t).clone()
-        va = buf["a"][: n * s.T_a * d_a].view(n, s.T_a, d_a)
-        vt = buf["t"][: n * s.T_t * d_t].view(n, s.T_t, d_t)
-        if s.host_cast:
-            # bf16 landed on the device: the model reads it in place; the set is free after the forward
-            emit(i, model(va, vt, ma, mt)[:3])
-            buf["consumed"].record(main)
-        elif early:
-            # the fp32 features are only read by the bf16 cast: after it the staging set is free again
-            xa = E.to_seq(va, "h_a").x.view(n, s.T_a, -1)
-            xt = E.to_seq(vt, "h_t").x.view(n, s.T_t, -1)
-            buf["consumed"].record(main)
-            emit(i, model(xa, xt, ma, mt)[:3])
+    def run_slabs():
+        nonlocal host_out
+        staged = {0: stage(0)}
+        if len(slabs) > 1:
+            staged[1] = stage(1)
+        for i, s in enumerate(slabs):
+            n = s.n
+            buf = staged.pop(i)
+            main.wait_event(buf["copied"])
+            if trace is not None:
+                k0 = torch.cuda.Event(enable_timing=True)
+                k0.record(main)
+            if s.utt is not None:
+                # the whole (small) masks went to the device once; each slab gathers and trims its own
+                ma = None if mask_a_dev is None else ops.gather_masks(mask_a_dev, s.utt_dev, s.T_a)
+                mt = None if mask_t_dev is None else ops.gather_masks(mask_t_dev, s.utt_dev, s.T_t)
+            else:
+                ma = None if mask_a is None else buf["ma"][: n * s.T_a].view(n, s.T_a).clone()
+                mt = None if mask_t is None else buf["mt"][: n * s.T_t].view(n, s.T_t).clone()
+            va = buf["a"][: n * s.T_a * d_a].view(n, s.T_a, d_a)
+            vt = buf["t"][: n * s.T_t * d_t].view(n, s.T_t, d_t)
+            if va.dtype == torch.float32 and early:
+                # fp32 features are only read by the bf16 cast: after it the staging set is free again
+                xa = E.to_seq(va, "h_a").x.view(n, s.T_a, -1)
+                xt = E.to_seq(vt, "h_t").x.view(n, s.T_t, -1)
+                buf["consumed"].record(main)
+                emit(i, model(xa, xt, ma, mt)[:3])
+            else:
+                # bf16 landed on the device: the model reads it in place; the set is free after the forward
+                emit(i, model(va, vt, ma, mt)[:3])
+                buf["consumed"].record(main)
+            if trace is not None:
+                k1 = torch.cuda.Event(enable_timing=True)
+                k1.record(main)
+                trace[i]["comp0"], trace[i]["comp1"] = k0, k1
+            if i + 2 < len(slabs):
+                staged[i + 2] = stage(i + 2)
+        if worker is not None:
+            worker.join()
+        if dev_out is not None:
+            if not to_host:
+                return tuple(o.to(out_device) for o in dev_out)
+            host_out = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in dev_out]
+            for dst, o in zip(host_out, dev_out):
+                dst.copy_(o, non_blocking=True)
+            main.synchronize()
+            return tuple(host_out)
+        if to_host:
+            main.synchronize()
+            return tuple(host_out)
+        logits = torch.cat([o[0] for o in outs]).to(out_device)
+        beta = torch.cat([o[1] for o in outs]).to(out_device)
+        z = torch.cat([o[2] for o in outs]).to(out_device)
+        return logits, beta, z
+
+    try:
+        return run_slabs()
+    except BaseException as e:
+        failure.append(e)
+        for ev in enqueued:
+            ev.set()          # never leave the worker waiting on the main thread
+        raise
+
+
+@torch.no_grad()
+def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optional[torch.Tensor] = None,
+                      mask_t: Optional[torch.Tensor] = None, device="cuda", slab: int = 512,
+                      out_device="cpu", host_cast_every: int = 2, ramp: bool = False, bucket: bool = False,
+                      trace: Optional[list] = None):
+    """model(h_a, h_t, mask_a, mask_t) for HOST tensors with copy/compute overlap.
+
+    The batch is cut into slabs of utterances that flow through fixed staging buffers (nothing is
+    allocated or freed per slab for the inputs) on a side stream while earlier slabs compute:
+      * fp32 slabs are copied as they are and cast to bf16 on the GPU; their staging set is free again
+        as soon as the cast has read it;
+      * every `host_cast_every`-th slab (0 = never) is instead converted to bf16 by the host cores
+        (hriemo_host_pack_bf16 in a worker thread) into pinned bf16 staging and copied at half the
+        bytes.  A step is bounded by the 55 GB/s H2D copy of the fp32 features (7.1 GB at the
+        north-star batch); with every second slab pre-cast the copy drops under the compute time.
+        The rounding is the same round-to-nearest-even as the GPU cast: results are bit-identical.
+      * bucket=True (needs at least one mask): utterances are sorted by valid length and every slab is
+        trimmed to its own maxima (`bucket_plan`, `slab` x T_a audio rows per slab, the first two slabs
+        smaller).  Every slab is gathered, trimmed and cast by the host cores in one pass
+        (hriemo_host_pack_bf16) and travels as bf16; the masks go to the device once and each slab
+        gathers its own; results are scattered back to the original order on the device.
+    Returns (logits, beta, z) on `out_device`; host results are fresh PINNED tensors filled by
+    asynchronous D2H copies (a pageable `.cpu()` of the 50 MB of z cost 31 ms per step).
+    trace (optional list): receives one dict of CUDA events per slab (tools/e2e_timeline.py)."""
+    dev = torch.device(device)
+    B = h_a.shape[0]
+    if h_a.dim() != 3 or h_t.dim() != 3:
+        # utterance-level [B, d] inputs: nothing to pipeline
+        out = model(h_a.to(dev), h_t.to(dev), None if mask_a is None else mask_a.to(dev),
+                    None if mask_t is None else mask_t.to(dev))[:3]
+        return tuple(o.to(out_device) for o in out)
+    T_a, d_a = h_a.shape[1], h_a.shape[2]
+    T_t, d_t = h_t.shape[1], h_t.shape[2]
+    slab = max(1, min(slab, B))
+    h_a, h_t = h_a.contiguous(), h_t.contiguous()
+    early = (h_a.dtype == torch.float32 and h_t.dtype == torch.float32 and d_a % 8 == 0 and d_t % 8 == 0)
+    bucket = bool(bucket and early and (mask_a is not None or mask_t is not None) and T_a > 1)
+    mask_a = None if mask_a is None else mask_a.to(torch.bool).contiguous()
+    mask_t = None if mask_t is None else mask_t.to(torch.bool).contiguous()
+    threads = max(1, torch.get_num_threads())
+    mask_a_dev = mask_t_dev = None
+
+    if bucket:
+        len_a = valid_lengths(mask_a, B, T_a).clamp_(min=1)
+        len_t = valid_lengths(mask_t, B, T_t).clamp_(min=1)
+        order, buckets = bucket_plan(len_a, len_t, T_a, T_t, rows_per_slab=slab * T_a, max_utts=4 * slab, ramp=True)
+        order_dev = order.to(dev, non_blocking=True)
+        len_a_s, len_t_s = len_a[order.long()].contiguous(), len_t[order.long()].contiguous()
+        # every slab is gathered, trimmed and cast by the host cores and travels as bf16.  (Sending every
+        # second slab as fp32 with one async copy per utterance, valid rows only, was slower: 8 192 copies
+        # of ~1 MB / ~0.15 MB per step run the copy engine at 30 GB/s instead of 55 --
+        # profiles/r01_e2e_timeline_v11.txt.)
+        slabs = [_Slab(b.start, b.end, b.T_a, b.T_t, True, order[b.start:b.end].contiguous(), order_dev[b.start:b.end])
+                 for b in buckets]
+        mask_a_dev = None if mask_a is None else mask_a.to(dev, non_blocking=True)
+        mask_t_dev = None if mask_t is None else mask_t.to(dev, non_blocking=True)
+    else:
+        slabs = [_Slab(s, e, T_a, T_t, hc) for s, e, hc in slab_schedule(B, slab, host_cast_every if early else 0, ramp)]
+
+    def pack(s, hb):
+        if s.utt is None:
+            ops.host_pack_bf16(h_a[s.lo:s.hi], hb["a"], s.T_a, threads=threads)
+            ops.host_pack_bf16(h_t[s.lo:s.hi], hb["t"], s.T_t, threads=threads)
         else:
-            emit(i, model(va, vt, ma, mt)[:3])
-            buf["consumed"].record(main)
-        if trace is not None:
-            k1 = torch.cuda.Event(enable_timing=True)
-            k1.record(main)
-            trace[i]["comp0"], trace[i]["comp1"] = k0, k1
-        if i + 2 < len(slabs):
-            staged[i + 2] = stage(i + 2)
-    if worker is not None:
-        worker.join()
-    if dev_out is not None:
-        if not to_host:
-            return tuple(o.to(out_device) for o in dev_out)
-        host_out = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in dev_out]
-        for dst, o in zip(host_out, dev_out):
-            dst.copy_(o, non_blocking=True)
-        main.synchronize()
-        return tuple(host_out)
-    if to_host:
-        main.synchronize()
-        return tuple(host_out)
-    logits = torch.cat([o[0] for o in outs]).to(out_device)
-    beta = torch.cat([o[1] for o in outs]).to(out_device)
-    z = torch.cat([o[2] for o in outs]).to(out_device)
-    return logits, beta, z
+            ops.host_pack_bf16(h_a, hb["a"], s.T_a, s.utt, len_a_s[s.lo:s.hi], threads=threads)
+            ops.host_pack_bf16(h_t, hb["t"], s.T_t, s.utt, len_t_s[s.lo:s.hi], threads=threads)
+
+    def direct_src(s):
+        return h_a[s.lo:s.hi].view(-1), h_t[s.lo:s.hi].view(-1)
+
+    return _run_pipeline(model, dev, B, slabs, d_a, d_t, h_a.dtype, h_t.dtype, torch.bfloat16, pack, direct_src,
+                         mask_a, mask_t, mask_a_dev, mask_t_dev, early, out_device, trace)
+
+
+@torch.no_grad()
+def forward_from_shard(model, shard, device="cuda", slab_rows: int = 512 * 500, max_utts: int = 2048,
+                       out_device="cpu", trace: Optional[list] = None):
+    """The forward over every utterance of a packed feature shard (hriemo.shards.Shard),
+    results in SHARD order (shard.original_order() maps back to the writer's input order).
+
+    The shard stores each utterance's valid rows back to back, so nothing is converted on the way: the plan
+    is `bucket_plan` over the stored lengths (a shard written with sort_by_length=True is already in plan
+    order), a worker thread copies each slab's rows from the mapped file into pinned staging, zero-padded to
+    the slab's own extents (hriemo_shard_read), and the slabs flow through the same staging engine as
+    forward_from_host(bucket=True): bf16 shards are read by the model in place, fp32 shards are cast on the
+    GPU.  The True = PAD masks are rebuilt from the stored PAD bytes once and gathered per slab on the device."""
+    dev = torch.device(device)
+    B = len(shard)
+    T_a, T_t = max(1, shard.max_len_a), max(1, shard.max_len_t)
+    d_a, d_t = shard.d_a, shard.d_t
+    if d_a % 8 or d_t % 8:
+        raise L.HriemoError("forward_from_shard: feature dims must be multiples of 8 (pad them when writing the shard)")
+    threads = max(1, torch.get_num_threads())
+    order, buckets = bucket_plan(shard.len_a, shard.len_t, T_a, T_t, rows_per_slab=slab_rows, max_utts=max_utts, ramp=True)
+    order64 = order.long()
+    order_dev = order.to(dev, non_blocking=True)
+    slabs = [_Slab(b.start, b.end, b.T_a, b.T_t, True, order64[b.start:b.end].contiguous(), order_dev[b.start:b.end])
+             for b in buckets]
+    # the whole masks (rows x 1 byte) once: host -> pinned -> device
+    ma_h = torch.empty((B, T_a), dtype=torch.bool).pin_memory()
+    mt_h = torch.empty((B, T_t), dtype=torch.bool).pin_memory()
+    shard.read(first=0, n=B, T_a=T_a, T_t=T_t, out_mask_a=ma_h, out_mask_t=mt_h, features=False, threads=threads)
+    mask_a_dev, mask_t_dev = ma_h.to(dev, non_blocking=True), mt_h.to(dev, non_blocking=True)
+
+    def pack(s, hb):
+        shard.read(utt=s.utt, T_a=s.T_a, T_t=s.T_t, out_a=hb["a"], out_t=hb["t"], masks=False, threads=threads)
+
+    return _run_pipeline(model, dev, B, slabs, d_a, d_t, shard.dtype, shard.dtype, shard.dtype, pack, None,
+                         None, None, mask_a_dev, mask_t_dev, True, out_device, trace)

@@ -258,6 +258,36 @@ int hriemo_host_pack_bf16(const float* src, int64_t ld_src, int64_t T_in, int64_
                           const int32_t* lens, void* dst_bf16, int64_t ld_dst, int64_t T_out, int64_t n,
                           int32_t n_threads);
 
+/* ---------------------------------------------------- packed feature shards ----
+ * The on-disk side of the step before the path.  The reference keeps one torch
+ * pickle per utterance and modality, {"hidden": [L,d] f32, "attention_mask": [L]}
+ * (scripts/iemocap_feature_extraction_seq_level/extract_audio_feats_wavlm_seq.py:118-135, read back one by
+ * one at scripts/fusion/train_fusion_seq_level_decoder.py:139-156).  A shard (format HRIEMOS1, written by
+ * hri-emo_b200/hriemo/shards.py, layout in hri-emo_b200/csrc/host_shard.cpp) packs many utterances into one
+ * file: valid rows back to back (bf16 or f32), per-row PAD bytes, an index of lengths.  These HOST functions
+ * mmap a shard and copy slabs of utterances into caller-provided (pinned) buffers as the zero-padded
+ * [n, T, d] tensors + True = PAD masks the reference's collate would have produced
+ * (scripts/fusion/train_fusion_seq_level_decoder.py:191-232).  No device work, no stream. */
+typedef struct hriemo_shard_info_t {
+  int64_t n_utt, rows_a, rows_t, meta_bytes;
+  int32_t d_a, d_t;
+  int32_t dtype;                /* 1 = bf16, 2 = f32 */
+  int32_t max_len_a, max_len_t; /* longest stored utterance per modality */
+} hriemo_shard_info_t;
+
+int hriemo_shard_open(const char* path, void** handle);
+int hriemo_shard_info(void* handle, hriemo_shard_info_t* info);
+/* len_a / len_t: int32 [n_utt], rows stored per utterance (= index of the last valid position + 1). */
+int hriemo_shard_lengths(void* handle, int32_t* len_a, int32_t* len_t);
+/* The writer's JSON metadata (uids, labels, provenance), meta_bytes bytes, not NUL-terminated. */
+int hriemo_shard_meta(void* handle, char* dst, int64_t dst_bytes);
+/* Utterances utt[0..n) (or first..first+n when utt is NULL) as dst_a [n, T_a, d_a] / dst_t [n, T_t, d_t] of the
+ * shard's dtype (rows past an utterance's length are zero; longer utterances are cut at T) and
+ * mask_a [n, T_a] / mask_t [n, T_t] (1 = PAD).  Any of the four outputs may be NULL.  n_threads C++ threads. */
+int hriemo_shard_read(void* handle, const int64_t* utt, int64_t first, int64_t n, int32_t T_a, int32_t T_t,
+                      void* dst_a, void* dst_t, uint8_t* mask_a, uint8_t* mask_t, int32_t n_threads);
+int hriemo_shard_close(void* handle);
+
 /* Mean over time (UNMASKED) of an f32 [B,L,d] tensor — models/fusion_classifier.py:145. */
 int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d, void* stream);
 

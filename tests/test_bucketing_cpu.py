@@ -115,3 +115,20 @@ def test_trimmed_buckets_reproduce_the_reference_outputs(name):
     assert (lo - fx["logits"]).abs().max().item() < 2e-5
     assert (be - fx["beta"]).abs().max().item() < 2e-5
     assert (z - fx["z"]).abs().max().item() < 1e-4
+
+
+def test_bucket_plan_ramp_opens_with_small_slabs():
+    g = torch.Generator().manual_seed(9)
+    _, la = _ragged(4096, 500, g, lo=250)
+    _, lt = _ragged(4096, 64, g, lo=32)
+    rows = 512 * 500
+    order, plain = pipeline.bucket_plan(la, lt, 500, 64, rows, 2048)
+    order2, ramped = pipeline.bucket_plan(la, lt, 500, 64, rows, 2048, ramp=True)
+    assert torch.equal(order, order2)
+    size = lambda b: (b.end - b.start) * b.T_a
+    assert size(ramped[0]) <= rows // 4 and size(ramped[1]) <= rows // 2 and size(ramped[2]) > rows // 2
+    assert size(plain[0]) > rows // 2
+    assert ramped[-1].end == 4096 and all(a.end == b.start for a, b in zip(ramped, ramped[1:]))
+    # a batch that fits a few slabs gets no ramp
+    _, small = pipeline.bucket_plan(la[:600], lt[:600], 500, 64, rows, 2048, ramp=True)
+    assert size(small[0]) > rows // 2

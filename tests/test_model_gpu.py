@@ -298,3 +298,34 @@ def test_model_on_second_gpu_with_other_current_device():
     assert lo.device.index == 1
     assert (lo.cpu() - fx["logits"]).abs().max().item() <= LOGIT_TOL
     assert (be.cpu() - fx["beta"]).abs().max().item() <= BETA_TOL
+
+
+def test_run_split_writes_the_reference_inference_outputs(tmp_path):
+    """hriemo.infer.run_split: the files scripts/infer/mosei_eval_infer.py:237-284 writes, same names, dtypes and
+    nesting; probabilities against the reference's golden logits."""
+    import numpy as np
+    from hriemo import infer
+
+    fx = G.load("cfg3_mosei_default")
+    model, (h_a, h_t, m_a, m_t) = G.build_fusion(fx)
+    model = model.to(DEV)
+    B = h_a.shape[0]
+    y = (torch.arange(B * 6).view(B, 6) % 2).float()
+    batches = [(h_a[:3], m_a[:3], h_t[:3], m_t[:3], y[:3]), (h_a[3:], m_a[3:], h_t[3:], m_t[3:], y[3:])]
+    thr = [0.5, 0.4, 0.6, 0.5, 0.3, 0.7]
+    out = infer.run_split(model, batches, DEV, str(tmp_path), "val", dump_beta=True, dump_attn=True, attn_max_samples=3,
+                          thresholds=thr)
+    prob = np.load(tmp_path / "val_y_prob.npy")
+    assert prob.dtype == np.float32 and prob.shape == (B, 6)
+    assert np.abs(prob - torch.sigmoid(fx["logits"]).numpy()).max() <= 2.5e-3      # d sigmoid <= 1/4 of the 1e-2 logit bar
+    assert np.array_equal(np.load(tmp_path / "val_y_true.npy"), y.numpy())
+    beta = np.load(tmp_path / "val_beta_mean.npy")
+    assert beta.shape == (B,) and np.abs(beta - fx["beta"].numpy()[:, 0]).max() <= BETA_TOL
+    pred = np.load(tmp_path / "val_y_pred.npy")
+    assert pred.dtype == np.uint8 and np.array_equal(pred, (prob >= np.asarray(thr, dtype=np.float32)[None]).astype(np.uint8))
+    att = torch.load(tmp_path / "val_attentions.pt", weights_only=False)
+    assert set(att) == {"encoder", "decoder"} and len(att["encoder"]) == 1 and out["attn_samples"] == 3   # capped after batch 1
+    layers = att["encoder"][0]
+    assert len(layers) == 2 and set(layers[0]) == {"audio_self", "text_self", "audio_queries_text", "text_queries_audio"}
+    assert layers[0]["audio_self"].shape == (3, h_a.shape[1], h_a.shape[1]) and isinstance(layers[0]["audio_self"], np.ndarray)
+    assert att["decoder"][0][0].shape == (3, 6, h_t.shape[1])

@@ -66,9 +66,9 @@ def test_h2d_byte_accounting_matches_the_staging_schedule():
 
     per = 564 * 768 * 4
     assert pipeline.h2d_bytes(4096, per, slab=512, host_cast_every=0) == 4096 * per
-    assert pipeline.h2d_bytes(4096, per, slab=512, host_cast_every=2, ramp=False) == 4096 * per * 3 // 4   # 4 of 8 slabs halved
+    assert pipeline.h2d_bytes(4096, per, slab=512, host_cast_every=2) == 4096 * per * 3 // 4   # 4 of 8 slabs halved
     # ramp 64+128+256 (fp32), then 512-slabs alternating fp32 / host-cast, 64 left over (host-cast)
-    assert pipeline.h2d_bytes(4096, per, slab=512, host_cast_every=2) == (4096 - 1600) * per + 1600 * per // 2
+    assert pipeline.h2d_bytes(4096, per, slab=512, host_cast_every=2, ramp=True) == (4096 - 1600) * per + 1600 * per // 2
     assert pipeline.h2d_bytes(1000, per, slab=512, host_cast_every=2) == 1000 * per            # two slabs: no pre-cast
     assert pipeline.h2d_bytes(1100, per, slab=512, host_cast_every=2) == (512 + 76) * per + 512 * per // 2
 
@@ -81,12 +81,12 @@ def test_slab_schedule_covers_the_batch_in_order():
     for B in (1, 3, 511, 512, 1000, 1100, 2048, 2559, 2560, 4096, 16384):
         for slab in (2, 64, 512):
             for every in (0, 2, 3):
-                plan = pipeline.slab_schedule(B, slab, every)
+                plan = pipeline.slab_schedule(B, slab, every, ramp=(B % 2 == 0))
                 assert plan[0][0] == 0 and plan[-1][1] == B
                 assert all(a[1] == b[0] for a, b in zip(plan, plan[1:]))
                 assert all(0 < e - s <= slab for s, e, _ in plan)
                 if every == 0:
                     assert not any(h for _, _, h in plan)
-    plan = pipeline.slab_schedule(4096, 512, 2)
+    plan = pipeline.slab_schedule(4096, 512, 2, ramp=True)
     assert [e - s for s, e, _ in plan[:3]] == [64, 128, 256] and not any(h for _, _, h in plan[:4])
     assert [e - s for s, e, _ in pipeline.slab_schedule(2048, 512, 2)] == [512] * 4
