@@ -18,6 +18,13 @@
 //                final O / l written as bf16.
 // Tensor memory per query tile: S0 [0,64) S1 [64,128) O [128,128+dh)  -> 2 x 256 columns.
 //
+// Short query sequences (Tq <= 128, H even: text self-attention, text->audio, MOSEI text) have ONE query
+// tile per (utterance, head); in the form above the second tile's MMA issuer and softmax warpgroup would
+// idle.  In PAIRED-HEAD mode a work item is (utterance, pair of heads): tile t carries head 2h'+t, and the
+// item's flat steps alternate between the two heads (flat step f: tile f & 1, key step f >> 1), so the two
+// tiles share the K / V ring in time instead of sharing its contents.  Each role skips the flat steps of the
+// other tile exactly as it skips a tile that does not exist; S buffers are indexed by the tile's own step count.
+//
 // Replaces the scaled_dot_product_attention inside nn.MultiheadAttention at
 // models/cross_modal_block_tacfn.py:74-80,85-91,98-104,111-117 and
 // models/cross_modal_block.py:56-59,64-67 of the reference.
@@ -75,6 +82,8 @@ struct Attn3Params {
   int64_t ldo;
   int B, H, Tq, Tk;
   int n_kv, n_qp;
+  int paired;       // paired-head mode (see the header): items are (utterance, head pair)
+  int items_per_b;  // work items per utterance: H * n_qp, or H / 2 in paired-head mode
   int contiguous;   // item -> CTA assignment, see the kernel
   int64_t n_items;
   float scale_log2;
@@ -174,9 +183,9 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   // PAD keys adds exactly 0 to every row sum, so skipping it is bit-exact); every role asks the same way
   auto steps_of = [&](uint32_t item) -> int {
     if (p.kv_steps == nullptr) return n_kv;
-    const uint32_t b_ = item / static_cast<uint32_t>(p.n_qp) / static_cast<uint32_t>(p.H);
-    return __ldg(p.kv_steps + b_);
+    return __ldg(p.kv_steps + item / static_cast<uint32_t>(p.items_per_b));
   };
+  const bool paired = p.paired != 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -207,39 +216,94 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      // Two cursors over the CTA's flat step sequence: the K cursor (which also brings in the Q tiles at the
+      // start of an item) and the V cursor.  General mode: K(g) then V(g), step by step.  Paired-head mode:
+      // the K cursor runs up to two flat steps ahead of the V cursor WITHOUT ever blocking while it is ahead
+      // -- a V stage is held until its PV has retired (a whole softmax step), K stages are free again as soon
+      // as S has been issued, and the S look-ahead of both tiles needs K(g+2), K(g+3) long before V(g+1)'s
+      // slot frees (with K and V in lock-step the 64 x 500 shape gained nothing from the second tile).
+      struct Cur { uint32_t item, g; int f, nk; };
+      auto cur_init = [&]() {
+        Cur c;
+        c.item = item_first; c.g = 0; c.f = 0;
+        c.nk = item_first < item_last ? steps_of(item_first) : 0;
+        return c;
+      };
+      auto cur_next = [&](Cur& c) {
+        ++c.g;
+        if (++c.f == (paired ? 2 * c.nk : c.nk)) {
+          c.f = 0;
+          c.item += item_stride;
+          c.nk = c.item < item_last ? steps_of(c.item) : 0;
+        }
+      };
+      // general: (b, h, query-tile pair qp), tile t = rows q0 + t*128 of head h;
+      // paired : (b, head pair), tile t = rows 0.. of head h + t
+      auto decode = [&](uint32_t item, int& b, int& h, int& q0) {
+        b = static_cast<int>(item / static_cast<uint32_t>(p.items_per_b));
+        const uint32_t in_b = item - static_cast<uint32_t>(b) * static_cast<uint32_t>(p.items_per_b);
+        h = paired ? static_cast<int>(in_b) * 2 : static_cast<int>(in_b / static_cast<uint32_t>(p.n_qp));
+        q0 = paired ? 0 : static_cast<int>(in_b % static_cast<uint32_t>(p.n_qp)) * 2 * A3_BQ;
+      };
       uint32_t qcnt[2] = {0, 0};  // Q loads issued per query tile -> buffer and phase
-      uint32_t g = 0;             // flat step index -> K/V ring stage and phase
-      for (uint32_t item = item_first; item < item_last; item += item_stride) {
-        const uint32_t bh = item / static_cast<uint32_t>(p.n_qp);
-        const int qp = static_cast<int>(item - bh * static_cast<uint32_t>(p.n_qp));
-        const int b = static_cast<int>(bh / static_cast<uint32_t>(p.H));
-        const int h = static_cast<int>(bh - static_cast<uint32_t>(b) * static_cast<uint32_t>(p.H));
-        const int q0 = qp * 2 * A3_BQ;
-        for (int t = 0; t < 2; ++t) {
-          if (q0 + t * A3_BQ >= p.Tq) break;
-          const uint32_t qb = qcnt[t] & 1u, qpar = (qcnt[t] >> 1) & 1u;
-          const uint32_t bar = (t * 2 + qb) * 8;
-          mbar_wait(b_qempty + bar, qpar ^ 1);
-          mbar_arrive_expect_tx(b_qfull + bar, L::Q_TILE);
-          for (int c = 0; c < L::QCH; ++c)
-            tma_load_2d(&tm_q, b_qfull + bar, sQ + (t * 2 + qb) * L::Q_TILE + c * L::Q_CHUNK, h * DH + c * 64,
-                        b * p.Tq + q0 + t * A3_BQ);
-          ++qcnt[t];
+      // Q tiles (first flat step of an item) + K tile of the cursor's step.  Non-blocking form: returns false,
+      // with nothing issued, unless every buffer the step needs is free.
+      auto k_issue = [&](Cur& c, bool blocking) -> bool {
+        int b, h, q0;
+        decode(c.item, b, h, q0);
+        const uint32_t s = c.g % KS, par = (c.g / KS) & 1u;
+        if (c.f == 0) {
+          for (int t = 0; t < 2; ++t) {
+            if (!paired && q0 + t * A3_BQ >= p.Tq) break;
+            const uint32_t bar = (t * 2 + (qcnt[t] & 1u)) * 8, qpar = (qcnt[t] >> 1) & 1u;
+            if (blocking) mbar_wait(b_qempty + bar, qpar ^ 1);
+            else if (!mbar_try_wait(b_qempty + bar, qpar ^ 1)) return false;
+          }
         }
-        const int nk = steps_of(item);
-        for (int j = 0; j < nk; ++j, ++g) {
-          const uint32_t s = g % KS, par = (g / KS) & 1u;
-          mbar_wait(b_kempty + s * 8, par ^ 1);
-          mbar_arrive_expect_tx(b_kfull + s * 8, L::K_STAGE);
-          for (int c = 0; c < L::QCH; ++c)
-            tma_load_2d(&tm_k, b_kfull + s * 8, sK + s * L::K_STAGE + c * L::K_CHUNK, h * DH + c * 64,
-                        b * p.Tk + j * A3_BKV);
-          mbar_wait(b_vempty + s * 8, par ^ 1);
-          mbar_arrive_expect_tx(b_vfull + s * 8, L::V_STAGE);
-          for (int c = 0; c < DH / 32; ++c)
-            tma_load_3d(&tm_v, b_vfull + s * 8, sV + s * L::V_STAGE + c * L::V_GROUP, h * DH + c * 32,
-                        j * A3_BKV, b);
+        if (blocking) mbar_wait(b_kempty + s * 8, par ^ 1);
+        else if (!mbar_try_wait(b_kempty + s * 8, par ^ 1)) return false;
+        if (c.f == 0) {
+          for (int t = 0; t < 2; ++t) {
+            const int q_t = paired ? 0 : q0 + t * A3_BQ, h_t = paired ? h + t : h;
+            if (q_t >= p.Tq) break;
+            const uint32_t qb = qcnt[t] & 1u;
+            const uint32_t bar = (t * 2 + qb) * 8;
+            mbar_arrive_expect_tx(b_qfull + bar, L::Q_TILE);
+            for (int cc = 0; cc < L::QCH; ++cc)
+              tma_load_2d(&tm_q, b_qfull + bar, sQ + (t * 2 + qb) * L::Q_TILE + cc * L::Q_CHUNK, h_t * DH + cc * 64,
+                          b * p.Tq + q_t);
+            ++qcnt[t];
+          }
         }
+        const int j = paired ? c.f >> 1 : c.f;            // key step
+        const int hk = paired ? h + (c.f & 1) : h;        // head whose K / V this flat step carries
+        mbar_arrive_expect_tx(b_kfull + s * 8, L::K_STAGE);
+        for (int cc = 0; cc < L::QCH; ++cc)
+          tma_load_2d(&tm_k, b_kfull + s * 8, sK + s * L::K_STAGE + cc * L::K_CHUNK, hk * DH + cc * 64,
+                      b * p.Tk + j * A3_BKV);
+        cur_next(c);
+        return true;
+      };
+      auto v_issue = [&](Cur& c) {
+        int b, h, q0;
+        decode(c.item, b, h, q0);
+        const uint32_t s = c.g % KS, par = (c.g / KS) & 1u;
+        const int j = paired ? c.f >> 1 : c.f;
+        const int hk = paired ? h + (c.f & 1) : h;
+        mbar_wait(b_vempty + s * 8, par ^ 1);
+        mbar_arrive_expect_tx(b_vfull + s * 8, L::V_STAGE);
+        for (int cc = 0; cc < DH / 32; ++cc)
+          tma_load_3d(&tm_v, b_vfull + s * 8, sV + s * L::V_STAGE + cc * L::V_GROUP, hk * DH + cc * 32,
+                      j * A3_BKV, b);
+        cur_next(c);
+      };
+      Cur kc = cur_init(), vc = cur_init();
+      const uint32_t lead = paired ? 2u : 0u;
+      while (vc.item < item_last) {
+        while (kc.item < item_last && kc.g <= vc.g + lead) {
+          if (!k_issue(kc, /*blocking=*/kc.g == vc.g)) break;   // K(g) must be out before V(g); beyond that, opportunistic
+        }
+        v_issue(vc);
       }
     }
   } else if (warp == 1 || warp == 10) {
@@ -255,32 +319,42 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       const uint32_t tile_tmem = tmem_base + t * TILE_COLS;
       const uint64_t k_desc0 = umma_desc_sw128(sK);
       const uint64_t v_desc0 = umma_desc_mn_sw64(sV, L::V_GROUP);
+      // does this tile exist for the item (general mode; in paired-head mode both tiles always do)
       auto tile_active = [&](uint32_t item) {
-        return t == 0 || static_cast<int>(item % static_cast<uint32_t>(p.n_qp)) * 2 * A3_BQ + A3_BQ < p.Tq;
+        return paired || t == 0 ||
+               static_cast<int>(item % static_cast<uint32_t>(p.n_qp)) * 2 * A3_BQ + A3_BQ < p.Tq;
       };
-      // ---- S cursor (two steps ahead of the PV cursor)
+      // flat steps of an item, and which of them belong to this tile (paired-head mode: every second one)
+      auto flat_of = [&](int nk) { return paired ? 2 * nk : nk; };
+      auto mine = [&](int f) { return !paired || (f & 1) == t; };
+      auto key_step = [&](int f) { return paired ? f >> 1 : f; };
+      // S buffer of a flat step: by the tile's own step count (flat steps per item are even in paired-head mode)
+      auto sbuf_of = [&](uint32_t g) { return paired ? (g >> 1) & 1u : g & 1u; };
+      // ---- S cursor (two flat steps ahead of the PV cursor)
       uint32_t s_g = 0, s_item = item_first, qcnt = 0;
-      int s_j = 0;
+      int s_f = 0;
       int s_nk = s_item < item_last ? steps_of(s_item) : 0;
       bool s_act = tile_active(s_item);
       auto issue_s = [&]() {
         const uint32_t ks = s_g % KS, kpar = (s_g / KS) & 1u;
         const uint32_t qslot = t * 2 + (qcnt & 1u);
+        const bool act = s_act && mine(s_f);
+        const int s_j = key_step(s_f);
         ATRACE(t, s_g, 4);
-        if (s_act && s_j == 0) mbar_wait(b_qfull + qslot * 8, (qcnt >> 1) & 1u);
+        if (act && s_j == 0) mbar_wait(b_qfull + qslot * 8, (qcnt >> 1) & 1u);
         mbar_wait(b_kfull + ks * 8, kpar);
         ATRACE(t, s_g, 5);
-        if (s_act) {
+        if (act) {
           tc_fence_after_sync();
           const uint64_t q_desc = umma_desc_sw128(sQ + qslot * L::Q_TILE);
           const uint64_t k_desc = k_desc0 + ((ks * L::K_STAGE) >> 4);
-          const uint32_t d_tmem = tile_tmem + (s_g & 1u) * A3_BKV;
+          const uint32_t d_tmem = tile_tmem + sbuf_of(s_g) * A3_BKV;
 #pragma unroll
           for (int st = 0; st < DH / 16; ++st) {
             umma_bf16(d_tmem, q_desc + (((st >> 2) * L::Q_CHUNK + (st & 3) * 32) >> 4),
                       k_desc + (((st >> 2) * L::K_CHUNK + (st & 3) * 32) >> 4), idesc_s, st != 0);
           }
-          umma_commit(b_sfull + (t * 2 + (s_g & 1u)) * 8);
+          umma_commit(b_sfull + (t * 2 + sbuf_of(s_g)) * 8);
           umma_commit(b_kempty + ks * 8);
           ATRACE(t, s_g, 6);
           if (s_j == s_nk - 1) ++qcnt;  // the Q buffer is released by the warpgroup after its epilogue
@@ -288,18 +362,24 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           mbar_arrive(b_kempty + ks * 8);
         }
         ++s_g;
-        if (++s_j == s_nk) {
-          s_j = 0;
+        if (++s_f == flat_of(s_nk)) {
+          s_f = 0;
           s_item += item_stride;
           s_act = s_item < item_last && tile_active(s_item);
           s_nk = s_item < item_last ? steps_of(s_item) : 0;
         }
       };
+      // General mode: the S cursor leads the PV cursor by two steps (S(g+2) goes into the buffer whose P the
+      // PV(g) just issued consumed).  Paired-head mode: by THREE flat steps, so that the tile's next own step
+      // S(g+2) is issued one iteration early, at the other tile's flat step g-1 (where this issuer only passes
+      // the stage on): it lands in the buffer of P(g-2), whose PV was issued at iteration g-2 -- the same
+      // one-step look-ahead for the softmax as in general mode.
       if (s_item < item_last) issue_s();
       if (s_item < item_last) issue_s();
+      if (paired && s_item < item_last) issue_s();
       // ---- PV cursor
       uint32_t pcnt = 0, pv_item = item_first;
-      int pv_j = 0;
+      int pv_f = 0;
       int pv_nk = pv_item < item_last ? steps_of(pv_item) : 0;
       bool pv_act = tile_active(pv_item);
       for (uint32_t g = 0; pv_item < item_last; ++g) {
@@ -307,7 +387,8 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         ATRACE(t, g, 0);
         mbar_wait(b_vfull + vs * 8, vpar);
         ATRACE(t, g, 1);
-        if (pv_act) {
+        if (pv_act && mine(pv_f)) {
+          const int pv_j = key_step(pv_f);
           const int rem = p.Tk - pv_j * A3_BKV;  // keys left from this step on (> 0)
           const uint32_t slot = t * 2 + (pcnt & 1u);
           mbar_wait(b_pfull + slot * 8, (pcnt >> 1) & 1u);
@@ -315,7 +396,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           ++pcnt;
           tc_fence_after_sync();
           const uint64_t v_desc = v_desc0 + ((vs * L::V_STAGE) >> 4);
-          const uint32_t p_tmem = tile_tmem + (g & 1u) * A3_BKV;
+          const uint32_t p_tmem = tile_tmem + sbuf_of(g) * A3_BKV;
 #pragma unroll
           for (int st = 0; st < A3_BKV / 16; ++st) {
             if (st * 16 < rem)  // P is zero beyond Tk: skip those K-steps (16 keys = 16 rows of 64 B)
@@ -328,9 +409,9 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         } else {
           mbar_arrive(b_vempty + vs * 8);
         }
-        if (s_item < item_last) issue_s();  // S(g+2) reuses the S buffer whose P was just consumed
-        if (++pv_j == pv_nk) {
-          pv_j = 0;
+        if (s_item < item_last) issue_s();  // general: S(g+2) reuses the S buffer whose P was just consumed
+        if (++pv_f == flat_of(pv_nk)) {
+          pv_f = 0;
           pv_item += item_stride;
           pv_act = pv_item < item_last && tile_active(pv_item);
           pv_nk = pv_item < item_last ? steps_of(pv_item) : 0;
@@ -360,7 +441,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         ++pv_seen;
       }
     };
-    uint32_t g = 0;              // flat step index of this CTA
+    uint32_t g = 0;              // flat step index of this CTA at the start of the current item
     int pending_qslot = -1;      // Q buffer whose O store has been issued but not yet waited for
     auto release_q = [&]() {
       if (pending_qslot >= 0) {
@@ -378,13 +459,12 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     int cur_b = -1;
 
     int nk = 0;
-    for (uint32_t item = item_first; item < item_last; item += item_stride, g += nk) {
+    for (uint32_t item = item_first; item < item_last; item += item_stride, g += paired ? 2 * nk : nk) {
       nk = steps_of(item);
-      const uint32_t bh = item / static_cast<uint32_t>(p.n_qp);
-      const int qp = static_cast<int>(item - bh * static_cast<uint32_t>(p.n_qp));
-      const int b = static_cast<int>(bh / static_cast<uint32_t>(p.H));
-      const int h = static_cast<int>(bh - static_cast<uint32_t>(b) * static_cast<uint32_t>(p.H));
-      const int q0 = qp * 2 * A3_BQ + wg * A3_BQ;
+      const int b = static_cast<int>(item / static_cast<uint32_t>(p.items_per_b));
+      const uint32_t in_b = item - static_cast<uint32_t>(b) * static_cast<uint32_t>(p.items_per_b);
+      const int h = paired ? static_cast<int>(in_b) * 2 + wg : static_cast<int>(in_b / static_cast<uint32_t>(p.n_qp));
+      const int q0 = paired ? 0 : static_cast<int>(in_b % static_cast<uint32_t>(p.n_qp)) * 2 * A3_BQ + wg * A3_BQ;
       if (q0 >= p.Tq) {  // this warpgroup's tile does not exist for this item: only keep the exp turn-taking alive
 #ifndef HRIEMO_ATTN_NO_PINGPONG
         for (int j = 0; j < nk; ++j) {
@@ -413,7 +493,8 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       float m_run = -INFINITY;  // running reference maximum, in log2 units (score * scale * log2 e)
       float l_run = 0.0f;
       for (int j = 0; j < nk; ++j) {
-        const uint32_t sbuf = static_cast<uint32_t>((g + j) & 1);
+        // flat step of this tile's j-th key step: g + j, or g + 2 j + wg in paired-head mode (g is even there)
+        const uint32_t sbuf = paired ? ((g >> 1) + static_cast<uint32_t>(j)) & 1u : (g + static_cast<uint32_t>(j)) & 1u;
         const uint32_t t_s = t_tile + sbuf * A3_BKV;
         const int rem = p.Tk - j * A3_BKV;
         const bool two = rem > 32;                   // second 32-key chunk holds a valid key
@@ -592,9 +673,11 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
   p.B = a.B; p.H = a.H; p.Tq = a.Tq; p.Tk = a.Tk;
   p.n_kv = n_kv;
   p.n_qp = (a.Tq + 2 * A3_BQ - 1) / (2 * A3_BQ);
-  p.n_items = static_cast<int64_t>(a.B) * a.H * p.n_qp;
+  p.paired = (a.Tq <= A3_BQ && a.H % 2 == 0 && !a.no_head_pairs) ? 1 : 0;
+  p.items_per_b = p.paired ? a.H / 2 : a.H * p.n_qp;
+  p.n_items = static_cast<int64_t>(a.B) * p.items_per_b;
   p.contiguous = n_kv <= 6 ? 1 : 0;
-  if (p.n_items * n_kv >= (1ll << 31))
+  if (p.n_items * n_kv * (p.paired ? 2 : 1) >= (1ll << 31))
     return set_error(HRIEMO_ERR_INVALID, "attention: too many (item, step) pairs for 32-bit step counters");
   p.scale_log2 = a.scale * 1.4426950408889634f;
   static uint64_t attr_done = 0;

@@ -45,6 +45,7 @@ class AttnArgs(C.Structure):
         ("B", C.c_int32), ("H", C.c_int32), ("Tq", C.c_int32), ("Tk", C.c_int32), ("dh", C.c_int32),
         ("scale", C.c_float),
         ("kv_steps", C.c_void_p),
+        ("no_head_pairs", C.c_int32),
     ]
 
 

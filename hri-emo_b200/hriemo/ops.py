@@ -194,9 +194,11 @@ def kv_steps(key_pad: torch.Tensor) -> torch.Tensor:
 
 @_on_tensor_device
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Optional[torch.Tensor],
-              B: int, H: int, Tq: int, Tk: int, dh: int, skip_padded_tiles: bool = True) -> torch.Tensor:
+              B: int, H: int, Tq: int, Tk: int, dh: int, skip_padded_tiles: bool = True,
+              pair_heads: bool = True) -> torch.Tensor:
     """q: [B*Tq, >=H*dh] view, k / v: [B*Tk, >=H*dh] views (column slices of a packed projection are
-    fine).  Returns [B*Tq, H*dh] bf16."""
+    fine).  Returns [B*Tq, H*dh] bf16.  pair_heads=False switches the two-heads-per-work-item form of
+    short query sequences off (include/hriemo.h: no_head_pairs; same result bit for bit)."""
     _chk2d(q, bf16, "attention q")
     _chk2d(k, bf16, "attention k")
     _chk2d(v, bf16, "attention v")
@@ -216,6 +218,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Option
     args.out, args.ldo = out.data_ptr(), out.stride(0)
     args.B, args.H, args.Tq, args.Tk, args.dh = B, H, Tq, Tk, dh
     args.scale = 1.0 / math.sqrt(dh)
+    args.no_head_pairs = 0 if pair_heads else 1
     tok = _prof_begin("attention", 4.0 * B * H * Tq * Tk * dh)
     _l.check(_l.load().hriemo_attention_bf16(C.byref(args), _stream()), "attention_bf16")
     _prof_end(tok)

@@ -129,6 +129,9 @@ typedef struct hriemo_attn_args {
    * reference's collate (scripts/fusion/train_fusion_seq_level_decoder.py:191-232: zero-pad to the
    * batch maximum + True=PAD mask) without paying for the padding in the attention. */
   const int32_t* kv_steps;
+  /* Tq <= 128 with an even H runs two heads per work item (one per query tile of the CTA) instead of leaving
+   * the second tile idle; same result bit for bit.  Non-zero switches that off (A/B measurements, tests). */
+  int32_t no_head_pairs;
 } hriemo_attn_args;
 
 /* steps[b] = (index of the last valid key of utterance b) / 64 + 1, or 1 when every key is PAD. */

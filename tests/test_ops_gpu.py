@@ -345,6 +345,38 @@ def test_attention_skipping_padded_key_tiles_is_bit_exact(B, H, Tq, Tk, dh):
     _report("attention with skipped tiles", skip, ref, atol=1.5e-2, rtol=2e-2)
 
 
+@pytest.mark.parametrize("B,H,Tq,Tk,dh,masked", [
+    (5, 8, 64, 500, 96, True),      # text queries audio (north star)
+    (5, 8, 64, 64, 96, False),      # text self-attention: one key step per head
+    (37, 8, 64, 500, 96, False),    # more items than one pass over a few CTAs: item hand-over between heads
+    (3, 4, 128, 300, 64, True),     # MOSEI text: a full 128-row tile
+    (4, 2, 1, 1, 96, False),        # utterance-level
+    (3, 2, 100, 1000, 128, True),   # head dim 128: two K/V stages only
+    (7, 6, 40, 130, 32, True),
+])
+def test_attention_head_pairs_are_bit_exact(B, H, Tq, Tk, dh, masked):
+    """Tq <= 128 with an even head count runs TWO heads per work item (one per query tile of the CTA, the key
+    steps of the two heads interleaved on the shared K / V ring).  Every (utterance, head) still sees exactly
+    the same arithmetic as in the one-head form: outputs are bit-identical, with and without skipped PAD tiles."""
+    from hriemo import ops
+
+    d = H * dh
+    q = _rand((B * Tq, d), 201, dtype=torch.bfloat16)
+    k = _rand((B * Tk, d), 202, dtype=torch.bfloat16)
+    v = _rand((B * Tk, d), 203, dtype=torch.bfloat16)
+    pad = None
+    if masked:
+        pad = _ragged(B, Tk, 204)
+        pad[0] = False
+        pad[B - 1, 1:] = True       # one valid key
+    one = ops.attention(q, k, v, pad, B, H, Tq, Tk, dh, pair_heads=False)
+    two = ops.attention(q, k, v, pad, B, H, Tq, Tk, dh, pair_heads=True)
+    torch.cuda.synchronize()
+    assert torch.equal(one.view(torch.int16), two.view(torch.int16))
+    ref, _ = _attn_ref(q.view(B, Tq, d), k.view(B, Tk, d), v.view(B, Tk, d), pad, H)
+    _report(f"attention head pairs {B,H,Tq,Tk,dh,masked}", two, ref, atol=1.5e-2, rtol=2e-2)
+
+
 def test_attention_nan_in_neighbour_utterance_does_not_leak():
     """The last key tile of utterance b overhangs into utterance b+1's rows; those keys carry P = 0
     but 0 x NaN would still poison utterance b (a fully padded neighbour is NaN by design)."""

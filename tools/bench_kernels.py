@@ -45,6 +45,18 @@ def main():
         fl = 4.0 * B * H * Tq * Tk * dh
         res.append(dict(kernel="attention", B=B, H=H, Tq=Tq, Tk=Tk, dh=dh, ms=med, tflops=fl / med / 1e9, frac_burst=fl / med / 1e9 / PEAKS["bf16_tflops"], sdpa_ms=meds))
         print(res[-1], flush=True)
+    if only in (None, "attention", "pairs"):
+        # short query sequences: two heads per work item against one (bit-identical results)
+        for (B, H, Tq, Tk, dh) in [(2048, 8, 64, 500, 96), (2048, 8, 64, 64, 96), (2048, 4, 128, 128, 64), (2048, 4, 128, 300, 64)]:
+            d = H * dh
+            q = torch.randn(B * Tq, d, device=dev).bfloat16(); k = torch.randn(B * Tk, d, device=dev).bfloat16()
+            v = torch.randn(B * Tk, d, device=dev).bfloat16()
+            m1, _ = timeit(lambda: ops.attention(q, k, v, None, B, H, Tq, Tk, dh, pair_heads=False))
+            m2, _ = timeit(lambda: ops.attention(q, k, v, None, B, H, Tq, Tk, dh, pair_heads=True))
+            gb = (B * Tq * d * 2 + B * Tk * d * 2) * 2 / 1e9
+            res.append(dict(kernel="attention_head_pairs", B=B, H=H, Tq=Tq, Tk=Tk, dh=dh, ms_one_head=m1, ms_pairs=m2, speedup=m1 / m2,
+                            gbs_pairs=gb / m2 * 1e3, frac_hbm=gb / m2 * 1e3 / PEAKS["hbm_gbs"]))
+            print(res[-1], flush=True)
     if only in (None, "attention", "ragged"):
         # ragged batch (key lengths uniform in [T/2, T]): skipping trailing all-PAD key tiles
         for (B, H, Tq, Tk, dh) in [(512, 8, 500, 500, 96), (512, 8, 64, 500, 96), (512, 8, 300, 300, 96)]:
