@@ -135,7 +135,7 @@ __device__ __forceinline__ void exp_pack(const uint32_t (&v)[32], float sc, floa
   l4[0] = la.x; l4[2] = la.y; l4[1] = lb.x; l4[3] = lb.y;
 }
 
-template <int DH>
+template <int DH, bool PAIRED>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
@@ -185,7 +185,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     if (p.kv_steps == nullptr) return n_kv;
     return __ldg(p.kv_steps + item / static_cast<uint32_t>(p.items_per_b));
   };
-  const bool paired = p.paired != 0;
+  constexpr bool paired = PAIRED;   // compile-time: the general form keeps its original code paths
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -216,94 +216,115 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      // Two cursors over the CTA's flat step sequence: the K cursor (which also brings in the Q tiles at the
-      // start of an item) and the V cursor.  General mode: K(g) then V(g), step by step.  Paired-head mode:
-      // the K cursor runs up to two flat steps ahead of the V cursor WITHOUT ever blocking while it is ahead
-      // -- a V stage is held until its PV has retired (a whole softmax step), K stages are free again as soon
-      // as S has been issued, and the S look-ahead of both tiles needs K(g+2), K(g+3) long before V(g+1)'s
-      // slot frees (with K and V in lock-step the 64 x 500 shape gained nothing from the second tile).
-      struct Cur { uint32_t item, g; int f, nk; };
-      auto cur_init = [&]() {
-        Cur c;
-        c.item = item_first; c.g = 0; c.f = 0;
-        c.nk = item_first < item_last ? steps_of(item_first) : 0;
-        return c;
-      };
-      auto cur_next = [&](Cur& c) {
-        ++c.g;
-        if (++c.f == (paired ? 2 * c.nk : c.nk)) {
-          c.f = 0;
-          c.item += item_stride;
-          c.nk = c.item < item_last ? steps_of(c.item) : 0;
-        }
-      };
-      // general: (b, h, query-tile pair qp), tile t = rows q0 + t*128 of head h;
-      // paired : (b, head pair), tile t = rows 0.. of head h + t
-      auto decode = [&](uint32_t item, int& b, int& h, int& q0) {
-        b = static_cast<int>(item / static_cast<uint32_t>(p.items_per_b));
-        const uint32_t in_b = item - static_cast<uint32_t>(b) * static_cast<uint32_t>(p.items_per_b);
-        h = paired ? static_cast<int>(in_b) * 2 : static_cast<int>(in_b / static_cast<uint32_t>(p.n_qp));
-        q0 = paired ? 0 : static_cast<int>(in_b % static_cast<uint32_t>(p.n_qp)) * 2 * A3_BQ;
-      };
       uint32_t qcnt[2] = {0, 0};  // Q loads issued per query tile -> buffer and phase
-      // Q tiles (first flat step of an item) + K tile of the cursor's step.  Non-blocking form: returns false,
-      // with nothing issued, unless every buffer the step needs is free.
-      auto k_issue = [&](Cur& c, bool blocking) -> bool {
-        int b, h, q0;
-        decode(c.item, b, h, q0);
-        const uint32_t s = c.g % KS, par = (c.g / KS) & 1u;
-        if (c.f == 0) {
+      if constexpr (!PAIRED) {
+        // K(g) then V(g), step by step; Q tiles at the start of an item
+        uint32_t g = 0;             // flat step index -> K/V ring stage and phase
+        for (uint32_t item = item_first; item < item_last; item += item_stride) {
+          const uint32_t bh = item / static_cast<uint32_t>(p.n_qp);
+          const int qp = static_cast<int>(item - bh * static_cast<uint32_t>(p.n_qp));
+          const int b = static_cast<int>(bh / static_cast<uint32_t>(p.H));
+          const int h = static_cast<int>(bh - static_cast<uint32_t>(b) * static_cast<uint32_t>(p.H));
+          const int q0 = qp * 2 * A3_BQ;
           for (int t = 0; t < 2; ++t) {
-            if (!paired && q0 + t * A3_BQ >= p.Tq) break;
-            const uint32_t bar = (t * 2 + (qcnt[t] & 1u)) * 8, qpar = (qcnt[t] >> 1) & 1u;
-            if (blocking) mbar_wait(b_qempty + bar, qpar ^ 1);
-            else if (!mbar_try_wait(b_qempty + bar, qpar ^ 1)) return false;
-          }
-        }
-        if (blocking) mbar_wait(b_kempty + s * 8, par ^ 1);
-        else if (!mbar_try_wait(b_kempty + s * 8, par ^ 1)) return false;
-        if (c.f == 0) {
-          for (int t = 0; t < 2; ++t) {
-            const int q_t = paired ? 0 : q0 + t * A3_BQ, h_t = paired ? h + t : h;
-            if (q_t >= p.Tq) break;
-            const uint32_t qb = qcnt[t] & 1u;
+            if (q0 + t * A3_BQ >= p.Tq) break;
+            const uint32_t qb = qcnt[t] & 1u, qpar = (qcnt[t] >> 1) & 1u;
             const uint32_t bar = (t * 2 + qb) * 8;
+            mbar_wait(b_qempty + bar, qpar ^ 1);
             mbar_arrive_expect_tx(b_qfull + bar, L::Q_TILE);
-            for (int cc = 0; cc < L::QCH; ++cc)
-              tma_load_2d(&tm_q, b_qfull + bar, sQ + (t * 2 + qb) * L::Q_TILE + cc * L::Q_CHUNK, h_t * DH + cc * 64,
-                          b * p.Tq + q_t);
+            for (int c = 0; c < L::QCH; ++c)
+              tma_load_2d(&tm_q, b_qfull + bar, sQ + (t * 2 + qb) * L::Q_TILE + c * L::Q_CHUNK, h * DH + c * 64,
+                          b * p.Tq + q0 + t * A3_BQ);
             ++qcnt[t];
           }
+          const int nk = steps_of(item);
+          for (int j = 0; j < nk; ++j, ++g) {
+            const uint32_t s = g % KS, par = (g / KS) & 1u;
+            mbar_wait(b_kempty + s * 8, par ^ 1);
+            mbar_arrive_expect_tx(b_kfull + s * 8, L::K_STAGE);
+            for (int c = 0; c < L::QCH; ++c)
+              tma_load_2d(&tm_k, b_kfull + s * 8, sK + s * L::K_STAGE + c * L::K_CHUNK, h * DH + c * 64,
+                          b * p.Tk + j * A3_BKV);
+            mbar_wait(b_vempty + s * 8, par ^ 1);
+            mbar_arrive_expect_tx(b_vfull + s * 8, L::V_STAGE);
+            for (int c = 0; c < DH / 32; ++c)
+              tma_load_3d(&tm_v, b_vfull + s * 8, sV + s * L::V_STAGE + c * L::V_GROUP, h * DH + c * 32,
+                          j * A3_BKV, b);
+          }
         }
-        const int j = paired ? c.f >> 1 : c.f;            // key step
-        const int hk = paired ? h + (c.f & 1) : h;        // head whose K / V this flat step carries
-        mbar_arrive_expect_tx(b_kfull + s * 8, L::K_STAGE);
-        for (int cc = 0; cc < L::QCH; ++cc)
-          tma_load_2d(&tm_k, b_kfull + s * 8, sK + s * L::K_STAGE + cc * L::K_CHUNK, hk * DH + cc * 64,
-                      b * p.Tk + j * A3_BKV);
-        cur_next(c);
-        return true;
-      };
-      auto v_issue = [&](Cur& c) {
-        int b, h, q0;
-        decode(c.item, b, h, q0);
-        const uint32_t s = c.g % KS, par = (c.g / KS) & 1u;
-        const int j = paired ? c.f >> 1 : c.f;
-        const int hk = paired ? h + (c.f & 1) : h;
-        mbar_wait(b_vempty + s * 8, par ^ 1);
-        mbar_arrive_expect_tx(b_vfull + s * 8, L::V_STAGE);
-        for (int cc = 0; cc < DH / 32; ++cc)
-          tma_load_3d(&tm_v, b_vfull + s * 8, sV + s * L::V_STAGE + cc * L::V_GROUP, hk * DH + cc * 32,
-                      j * A3_BKV, b);
-        cur_next(c);
-      };
-      Cur kc = cur_init(), vc = cur_init();
-      const uint32_t lead = paired ? 2u : 0u;
-      while (vc.item < item_last) {
-        while (kc.item < item_last && kc.g <= vc.g + lead) {
-          if (!k_issue(kc, /*blocking=*/kc.g == vc.g)) break;   // K(g) must be out before V(g); beyond that, opportunistic
+      } else {
+        // Paired-head mode: two cursors over the flat step sequence, the K cursor (which also brings in the Q
+        // tiles at the start of an item) and the V cursor.  The K cursor runs up to two flat steps ahead of the
+        // V cursor WITHOUT ever blocking while it is ahead -- a V stage is held until its PV has retired (a
+        // whole softmax step), K stages are free again as soon as S has been issued, and the S look-ahead of
+        // both tiles needs K(g+2), K(g+3) long before V(g+1)'s slot frees (with K and V in lock-step the
+        // 64 x 500 shape gained nothing from the second tile).
+        struct Cur { uint32_t item, g; int f, nk, b, h; };
+        auto cur_item = [&](Cur& c) {   // (utterance, first head of the pair) of the cursor's item
+          c.nk = c.item < item_last ? steps_of(c.item) : 0;
+          c.b = static_cast<int>(c.item / static_cast<uint32_t>(p.items_per_b));
+          c.h = static_cast<int>(c.item - static_cast<uint32_t>(c.b) * static_cast<uint32_t>(p.items_per_b)) * 2;
+        };
+        auto cur_next = [&](Cur& c) {
+          ++c.g;
+          if (++c.f == 2 * c.nk) {
+            c.f = 0;
+            c.item += item_stride;
+            cur_item(c);
+          }
+        };
+        // Q tiles (first flat step of an item) + K tile of the cursor's step.  Non-blocking form: returns
+        // false, with nothing issued, unless every buffer the step needs is free.
+        auto k_issue = [&](Cur& c, bool blocking) -> bool {
+          const uint32_t s = c.g % KS, par = (c.g / KS) & 1u;
+          if (c.f == 0) {
+            for (int t = 0; t < 2; ++t) {
+              const uint32_t bar = (t * 2 + (qcnt[t] & 1u)) * 8, qpar = (qcnt[t] >> 1) & 1u;
+              if (blocking) mbar_wait(b_qempty + bar, qpar ^ 1);
+              else if (!mbar_try_wait(b_qempty + bar, qpar ^ 1)) return false;
+            }
+          }
+          if (blocking) mbar_wait(b_kempty + s * 8, par ^ 1);
+          else if (!mbar_try_wait(b_kempty + s * 8, par ^ 1)) return false;
+          if (c.f == 0) {
+            for (int t = 0; t < 2; ++t) {
+              const uint32_t qb = qcnt[t] & 1u;
+              const uint32_t bar = (t * 2 + qb) * 8;
+              mbar_arrive_expect_tx(b_qfull + bar, L::Q_TILE);
+              for (int cc = 0; cc < L::QCH; ++cc)
+                tma_load_2d(&tm_q, b_qfull + bar, sQ + (t * 2 + qb) * L::Q_TILE + cc * L::Q_CHUNK,
+                            (c.h + t) * DH + cc * 64, c.b * p.Tq);
+              ++qcnt[t];
+            }
+          }
+          const int hk = c.h + (c.f & 1);   // head whose K / V this flat step carries; key step f >> 1
+          mbar_arrive_expect_tx(b_kfull + s * 8, L::K_STAGE);
+          for (int cc = 0; cc < L::QCH; ++cc)
+            tma_load_2d(&tm_k, b_kfull + s * 8, sK + s * L::K_STAGE + cc * L::K_CHUNK, hk * DH + cc * 64,
+                        c.b * p.Tk + (c.f >> 1) * A3_BKV);
+          cur_next(c);
+          return true;
+        };
+        auto v_issue = [&](Cur& c) {
+          const uint32_t s = c.g % KS, par = (c.g / KS) & 1u;
+          const int hk = c.h + (c.f & 1);
+          mbar_wait(b_vempty + s * 8, par ^ 1);
+          mbar_arrive_expect_tx(b_vfull + s * 8, L::V_STAGE);
+          for (int cc = 0; cc < DH / 32; ++cc)
+            tma_load_3d(&tm_v, b_vfull + s * 8, sV + s * L::V_STAGE + cc * L::V_GROUP, hk * DH + cc * 32,
+                        (c.f >> 1) * A3_BKV, c.b);
+          cur_next(c);
+        };
+        Cur kc;
+        kc.item = item_first; kc.g = 0; kc.f = 0;
+        cur_item(kc);
+        Cur vc = kc;
+        while (vc.item < item_last) {
+          while (kc.item < item_last && kc.g <= vc.g + 2u) {
+            if (!k_issue(kc, /*blocking=*/kc.g == vc.g)) break;   // K(g) must be out before V(g); beyond that, opportunistic
+          }
+          v_issue(vc);
         }
-        v_issue(vc);
       }
     }
   } else if (warp == 1 || warp == 10) {
@@ -682,14 +703,19 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
   p.scale_log2 = a.scale * 1.4426950408889634f;
   static uint64_t attr_done = 0;
   if (device_needs_attr(&attr_done)) {
-    cudaError_t e = cudaFuncSetAttribute(attention_fwd3_kernel<DH>,
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd3_kernel<DH, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_fwd3_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess)
       return set_error(HRIEMO_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
   const int64_t sms = device_sm_count();
   const unsigned grid = static_cast<unsigned>(p.n_items < sms ? p.n_items : sms);
-  attention_fwd3_kernel<DH><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);
+  if (p.paired)
+    attention_fwd3_kernel<DH, true><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);
+  else
+    attention_fwd3_kernel<DH, false><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);
   return check_launch("attention_bf16");
 }
 

@@ -89,6 +89,10 @@ SIGNATURES = {
     "hriemo_shard_meta": (C.c_int, [_P, _P, _I64]),
     "hriemo_shard_read": (C.c_int, [_P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _I32]),
     "hriemo_shard_close": (C.c_int, [_P]),
+    "hriemo_bce_beta_loss": (C.c_int, [_P, _P, _P, _F, _I64, _I32, _P, _P, _P, _P]),
+    "hriemo_grad_norm_workspace_bytes": (C.c_int64, []),
+    "hriemo_grad_norm_clip": (C.c_int, [_P, _I64, _F, _P, _P, _P]),
+    "hriemo_adamw_step": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _F, _F, _F, _F, _F, _P, _P, _P]),
     "hriemo_host_pack_bf16": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, _I64, _I64, _I32]),
 }
 
@@ -107,6 +111,8 @@ def load() -> C.CDLL:
         )
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if os.environ.get("HRIEMO_LIB_PATH") and not hasattr(lib, name):
+            continue  # an older A/B build (tools/) may predate an entry point; the in-tree library never may
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args

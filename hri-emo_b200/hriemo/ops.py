@@ -453,3 +453,58 @@ def host_pack_bf16(src: torch.Tensor, dst: torch.Tensor, T_out: int, utt: Option
                                               T_out, n, threads), "host_pack_bf16")
     return dst.view(-1)[: n * T_out * cols].view(n, T_out, cols)
 
+
+
+# ------------------------------------------------------------------ loss and optimizer (training step)
+@_on_tensor_device
+def bce_beta_loss(logits: torch.Tensor, labels: torch.Tensor, beta: torch.Tensor, beta_weight: float = 0.01,
+                  want_grads: bool = True):
+    """BCEWithLogitsLoss(mean)(logits, labels) - beta_weight * mean(beta * (1 - beta)), the loss of
+    train_fusion_seq_level_decoder.py:319-327.  Returns (loss [1], d_logits | None, d_beta | None), all fp32."""
+    _chk2d(logits, f32, "bce_beta_loss logits")
+    B, Cn = logits.shape
+    logits = logits.contiguous()
+    labels = labels.to(f32).contiguous()
+    beta = beta.to(f32).contiguous().view(-1)
+    if tuple(labels.shape) != (B, Cn) or beta.shape[0] != B or not labels.is_cuda or not beta.is_cuda:
+        raise _l.HriemoError(f"bce_beta_loss: labels {tuple(labels.shape)} / beta {tuple(beta.shape)} do not match logits {(B, Cn)}")
+    loss = torch.empty((1,), dtype=f32, device=logits.device)
+    dl = torch.empty_like(logits) if want_grads else None
+    db = torch.empty((B, 1), dtype=f32, device=logits.device) if want_grads else None
+    _l.check(_l.load().hriemo_bce_beta_loss(logits.data_ptr(), labels.data_ptr(), beta.data_ptr(), beta_weight, B, Cn,
+                                             loss.data_ptr(), _ptr(dl), _ptr(db), _stream()), "bce_beta_loss")
+    return loss, dl, db
+
+
+def _chk_flat(t: torch.Tensor, n: int, name: str) -> None:
+    if not t.is_cuda or t.dtype != f32 or t.dim() != 1 or not t.is_contiguous() or t.shape[0] != n:
+        raise _l.HriemoError(f"{name}: expected a contiguous flat CUDA fp32 arena of {n} elements")
+
+
+@_on_tensor_device
+def grad_norm_clip(grads: torch.Tensor, max_norm: float) -> torch.Tensor:
+    """clip_grad_norm_ over a flat gradient arena without a host sync: returns a device tensor
+    [total L2 norm, clip coefficient]; pass out[1:] to adamw_step as grad_scale."""
+    _chk_flat(grads, grads.shape[0], "grad_norm_clip")
+    ws = torch.empty((int(_l.load().hriemo_grad_norm_workspace_bytes()) // 8,), dtype=torch.float64, device=grads.device)
+    out = torch.empty((2,), dtype=f32, device=grads.device)
+    _l.check(_l.load().hriemo_grad_norm_clip(grads.data_ptr(), grads.shape[0], max_norm, ws.data_ptr(), out.data_ptr(),
+                                              _stream()), "grad_norm_clip")
+    return out
+
+
+@_on_tensor_device
+def adamw_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
+               lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
+               grad_scale: Optional[torch.Tensor] = None, params_bf16: Optional[torch.Tensor] = None) -> None:
+    """In-place torch.optim.AdamW step over flat fp32 arenas (params, exp_avg, exp_avg_sq are updated)."""
+    n = params.shape[0]
+    for t, name in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _chk_flat(t, n, f"adamw_step {name}")
+    if grad_scale is not None and (not grad_scale.is_cuda or grad_scale.dtype != f32 or grad_scale.numel() < 1):
+        raise _l.HriemoError("adamw_step: grad_scale must be a CUDA fp32 tensor")
+    if params_bf16 is not None and (params_bf16.dtype != bf16 or params_bf16.numel() != n or not params_bf16.is_contiguous()):
+        raise _l.HriemoError("adamw_step: params_bf16 must be a contiguous bf16 tensor of the arena's size")
+    _l.check(_l.load().hriemo_adamw_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n,
+                                          step, lr, betas[0], betas[1], eps, weight_decay, _ptr(grad_scale),
+                                          _ptr(params_bf16), _stream()), "adamw_step")

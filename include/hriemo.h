@@ -291,6 +291,28 @@ int hriemo_shard_read(void* handle, const int64_t* utt, int64_t first, int64_t n
                       void* dst_a, void* dst_t, uint8_t* mask_a, uint8_t* mask_t, int32_t n_threads);
 int hriemo_shard_close(void* handle);
 
+/* ------------------------------------------------- loss and optimizer ----
+ * The parts of the reference's training step that are not the model's backward pass
+ * (scripts/fusion/train_fusion_seq_level_decoder.py:318-335, setup :405-416).  Parameters, gradients and
+ * the two AdamW moments are flat fp32 arenas (the module's tensors are views into them), so the global norm
+ * is one reduction, the update one launch and the data-parallel exchange one all-reduce.  The model's
+ * backward kernels are not part of this round. */
+/* loss_out[0] = BCEWithLogitsLoss(mean)(logits [B,C], labels [B,C]) - beta_weight * mean(beta * (1 - beta));
+ * d_logits [B,C] / d_beta [B] (optional) receive d loss / d logits and d loss / d beta. */
+int hriemo_bce_beta_loss(const float* logits, const float* labels, const float* beta, float beta_weight,
+                         int64_t B, int32_t C, float* loss_out, float* d_logits, float* d_beta, void* stream);
+/* clip_grad_norm_(max_norm) over a flat gradient arena, without touching the gradients and without a host
+ * sync: out2[0] = total L2 norm, out2[1] = min(1, max_norm / (total + 1e-6)); hriemo_adamw_step reads
+ * out2 + 1 as its grad_scale.  workspace: hriemo_grad_norm_workspace_bytes() bytes, 8-byte aligned. */
+int64_t hriemo_grad_norm_workspace_bytes(void);
+int hriemo_grad_norm_clip(const float* grads, int64_t n, float max_norm, void* workspace, float* out2, void* stream);
+/* torch.optim.AdamW step `step` (1-based) with decoupled weight decay over flat arenas; grad_scale (device
+ * pointer or NULL) multiplies every gradient first; params_bf16 (optional) receives the updated parameters as
+ * bf16 (the GEMM operand copy). */
+int hriemo_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      int32_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      const float* grad_scale, void* params_bf16, void* stream);
+
 /* Mean over time (UNMASKED) of an f32 [B,L,d] tensor — models/fusion_classifier.py:145. */
 int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d, void* stream);
 

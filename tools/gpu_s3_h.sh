@@ -1,0 +1,7 @@
+#!/bin/bash
+timeout 600 python -m pytest tests/test_ops_gpu.py -q -m gpu -x 2>&1 | tail -3
+bash tools/gpu_s3_g.sh
+for i in 1 2; do
+  echo "== new";  timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step'],2), 'gemm', round(d['roofline']['achieved']), 'attn', round(d['attention_roofline']['achieved']), d['clocks']['sm_mhz'])"
+  echo "== base"; HRIEMO_LIB_PATH=tools/_build/libhriemo_base.so timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step'],2), 'gemm', round(d['roofline']['achieved']), 'attn', round(d['attention_roofline']['achieved']), d['clocks']['sm_mhz'])"
+done
