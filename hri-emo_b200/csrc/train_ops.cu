@@ -90,16 +90,17 @@ __global__ void clip_finalize_kernel(const double* __restrict__ partials, int n_
 // operand copy), so no separate cast pass follows the step.
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-             int64_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
-             const float* __restrict__ grad_scale, __nv_bfloat16* __restrict__ w16) {
+             int64_t n, float decay, float b1, float omb1, float b2, float omb2, float eps, float step_size,
+             float bc2_sqrt, const float* __restrict__ grad_scale, __nv_bfloat16* __restrict__ w16) {
+  // decay = 1 - lr*wd, omb = 1 - beta, step_size = lr / (1 - beta1^t), bc2_sqrt = sqrt(1 - beta2^t): all formed
+  // in double on the host (1 - 0.999f in float is off by 1.3e-5 relative, which lands in exp_avg_sq)
   const float gs = grad_scale != nullptr ? __ldg(grad_scale) : 1.0f;
-  const float step_size = lr / bc1;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float gi = g[i] * gs;
-    float pi = p[i] * (1.0f - lr * wd);
-    const float mi = b1 * m[i] + (1.0f - b1) * gi;
-    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    float pi = p[i] * decay;
+    const float mi = b1 * m[i] + omb1 * gi;
+    const float vi = b2 * v[i] + omb2 * gi * gi;
     pi -= step_size * mi / (sqrtf(vi) / bc2_sqrt + eps);
     p[i] = pi;
     m[i] = mi;
@@ -146,14 +147,16 @@ extern "C" int hriemo_grad_norm_clip(const float* grads, int64_t n, float max_no
 }
 
 extern "C" int hriemo_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                                 int32_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                 int32_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
                                  const float* grad_scale, void* params_bf16, void* stream) {
   HRIEMO_REQUIRE(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adamw_step: bad argument");
-  HRIEMO_REQUIRE(beta1 >= 0.0f && beta1 < 1.0f && beta2 >= 0.0f && beta2 < 1.0f && eps > 0.0f, "adamw_step: bad hyper-parameter");
-  const float bc1 = 1.0f - static_cast<float>(pow(static_cast<double>(beta1), step));
-  const float bc2s = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
+  HRIEMO_REQUIRE(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps > 0.0, "adamw_step: bad hyper-parameter");
+  const double bc1 = 1.0 - pow(beta1, step);
+  const double bc2s = sqrt(1.0 - pow(beta2, step));
   adamw_kernel<<<flat_grid(n, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale,
+      params, grads, exp_avg, exp_avg_sq, n, static_cast<float>(1.0 - lr * weight_decay), static_cast<float>(beta1),
+      static_cast<float>(1.0 - beta1), static_cast<float>(beta2), static_cast<float>(1.0 - beta2),
+      static_cast<float>(eps), static_cast<float>(lr / bc1), static_cast<float>(bc2s), grad_scale,
       static_cast<__nv_bfloat16*>(params_bf16));
   return check_launch("adamw_step");
 }

@@ -92,7 +92,8 @@ SIGNATURES = {
     "hriemo_bce_beta_loss": (C.c_int, [_P, _P, _P, _F, _I64, _I32, _P, _P, _P, _P]),
     "hriemo_grad_norm_workspace_bytes": (C.c_int64, []),
     "hriemo_grad_norm_clip": (C.c_int, [_P, _I64, _F, _P, _P, _P]),
-    "hriemo_adamw_step": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _F, _F, _F, _F, _F, _P, _P, _P]),
+    "hriemo_adamw_step": (C.c_int, [_P, _P, _P, _P, _I64, _I32, C.c_double, C.c_double, C.c_double, C.c_double,
+                                    C.c_double, _P, _P, _P]),
     "hriemo_host_pack_bf16": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, _I64, _I64, _I32]),
 }
 

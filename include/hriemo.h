@@ -308,9 +308,10 @@ int64_t hriemo_grad_norm_workspace_bytes(void);
 int hriemo_grad_norm_clip(const float* grads, int64_t n, float max_norm, void* workspace, float* out2, void* stream);
 /* torch.optim.AdamW step `step` (1-based) with decoupled weight decay over flat arenas; grad_scale (device
  * pointer or NULL) multiplies every gradient first; params_bf16 (optional) receives the updated parameters as
- * bf16 (the GEMM operand copy). */
+ * bf16 (the GEMM operand copy).  Hyper-parameters are doubles: the derived constants (1 - beta, 1 - lr*wd,
+ * bias corrections) are formed in double like PyTorch does and only then rounded to the kernel's fp32. */
 int hriemo_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                      int32_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      int32_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
                       const float* grad_scale, void* params_bf16, void* stream);
 
 /* Mean over time (UNMASKED) of an f32 [B,L,d] tensor — models/fusion_classifier.py:145. */

@@ -530,3 +530,59 @@ def test_emotion_outputs_sigmoid_and_thresholds():
     _, dec0 = ops.emotion_outputs(lo[:, :4].contiguous())
     lo4 = lo[:, :4]
     assert torch.equal(dec0[lo4 != 0], (lo4 > 0)[lo4 != 0])   # default threshold 0.5 == logit > 0
+
+
+# ------------------------------------------------------------------ loss and optimizer (training step)
+def test_bce_beta_loss_matches_the_training_oracle():
+    """hriemo_bce_beta_loss against oracle/hriemo_oracle_train.py (pinned to the reference's own training steps)."""
+    import hriemo_oracle_train as OT
+    from hriemo import ops
+
+    g = torch.Generator().manual_seed(5)
+    for B, C in ((4, 4), (300, 6), (4096, 4)):
+        x = torch.randn(B, C, generator=g) * 3
+        x[0, 0], x[0, 1] = 60.0, -60.0                       # the stable form must not overflow
+        y = (torch.rand(B, C, generator=g) > 0.6).float()
+        beta = torch.rand(B, 1, generator=g)
+        xd = x.double().requires_grad_(True)
+        bd = beta.double().requires_grad_(True)
+        want = OT.bce_with_logits(xd, y.double()) - 0.01 * OT.beta_regulariser(bd)
+        gx, gb = torch.autograd.grad(want, [xd, bd])
+        loss, dl, db = ops.bce_beta_loss(x.to(DEV), y.to(DEV), beta.to(DEV), 0.01)
+        torch.cuda.synchronize()
+        assert abs(float(loss) - float(want)) <= 2e-6 * max(1.0, abs(float(want)))
+        assert (dl.cpu().double() - gx).abs().max().item() <= 1e-7 and dl.shape == (B, C)
+        assert (db.cpu().double() - gb).abs().max().item() <= 1e-8 and db.shape == (B, 1)
+    loss2, dl2, db2 = ops.bce_beta_loss(x.to(DEV), y.to(DEV), beta.to(DEV), 0.01, want_grads=False)
+    assert dl2 is None and db2 is None and float(loss2) == float(loss)
+
+
+def test_grad_norm_clip_and_adamw_match_the_training_oracle():
+    """Flat-arena global-norm clip + AdamW: two consecutive steps against the oracle's restatement of
+    clip_grad_norm_ / torch.optim.AdamW, with the clip coefficient staying on the device."""
+    import hriemo_oracle_train as OT
+    from hriemo import ops
+
+    g = torch.Generator().manual_seed(6)
+    n = 1_000_003                                              # not a multiple of 4: tail path of the reduction
+    p0 = torch.randn(n, generator=g)
+    p = p0.to(DEV).clone()
+    m = torch.zeros(n, device=DEV)
+    v = torch.zeros(n, device=DEV)
+    w16 = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    ref_p, ref_m, ref_v = p0.double(), torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+    for step, scale in ((1, 0.02), (2, 3e-5)):                 # step 1 is clipped (norm 20), step 2 is not
+        grad = torch.randn(n, generator=g) * scale
+        out = ops.grad_norm_clip(grad.to(DEV), 5.0)
+        total, coef = OT.clip_coefficient({"g": grad}, 5.0)
+        assert out.cpu().tolist() == pytest.approx([total, coef], rel=1e-5)
+        assert (coef < 1.0) == (step == 1)
+        ops.adamw_step(p, grad.to(DEV), m, v, step, lr=1e-3, weight_decay=1e-2, grad_scale=out[1:], params_bf16=w16)
+        ref_p, ref_m, ref_v = OT.adamw_update(ref_p, grad.double() * coef, ref_m, ref_v, step, lr=1e-3, weight_decay=1e-2)
+        torch.cuda.synchronize()
+        assert (p.cpu().double() - ref_p).abs().max().item() <= 1e-6
+        assert (m.cpu().double() - ref_m).abs().max().item() <= 1e-7 * max(1.0, float(ref_m.abs().max()) / 1e-3)
+        assert (v.cpu().double() - ref_v).abs().max().item() <= 1e-6 * max(float(ref_v.abs().max()), 1e-12) + 1e-12
+        assert torch.equal(w16, p.to(torch.bfloat16))
+    # no clipping requested: coefficient 1
+    assert ops.grad_norm_clip(grad.to(DEV), 0.0).cpu()[1].item() == 1.0
