@@ -267,8 +267,22 @@ class _Slab:
         return self.hi - self.lo
 
 
+class PendingResult:
+    """Results of a forward_from_host / forward_from_shard call made with wait=False: the pinned host tensors
+    are being filled by asynchronous D2H copies; wait() blocks until they are complete and returns them.
+    The next call may be issued before wait(): its first copies then overlap this call's last slabs."""
+
+    def __init__(self, tensors, event):
+        self._tensors, self._event = tuple(tensors), event
+
+    def wait(self):
+        self._event.synchronize()
+        return self._tensors
+
+
 def _run_pipeline(model, dev, B: int, slabs: List[_Slab], d_a: int, d_t: int, dtype_a, dtype_t, host_dtype,
-                  pack, direct_src, mask_a, mask_t, mask_a_dev, mask_t_dev, early: bool, out_device, trace):
+                  pack, direct_src, mask_a, mask_t, mask_a_dev, mask_t_dev, early: bool, out_device, trace,
+                  wait: bool = True):
     """The staging engine behind forward_from_host / forward_from_shard: slab i+1 (and i+2) is prepared
     and copied on a side stream while slab i computes.
       pack(s, hb)      fills the pinned host set hb["a"], hb["t"] for a host-prepared slab (worker thread);
@@ -423,9 +437,11 @@ def _run_pipeline(model, dev, B: int, slabs: List[_Slab], d_a: int, d_t: int, dt
             host_out = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in dev_out]
             for dst, o in zip(host_out, dev_out):
                 dst.copy_(o, non_blocking=True)
-            main.synchronize()
-            return tuple(host_out)
         if to_host:
+            if not wait:
+                done = torch.cuda.Event()
+                done.record(main)
+                return PendingResult(host_out, done)
             main.synchronize()
             return tuple(host_out)
         logits = torch.cat([o[0] for o in outs]).to(out_device)
@@ -446,7 +462,7 @@ def _run_pipeline(model, dev, B: int, slabs: List[_Slab], d_a: int, d_t: int, dt
 def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optional[torch.Tensor] = None,
                       mask_t: Optional[torch.Tensor] = None, device="cuda", slab: int = 512,
                       out_device="cpu", host_cast_every: int = 2, ramp: bool = False, bucket: bool = False,
-                      trace: Optional[list] = None):
+                      trace: Optional[list] = None, wait: bool = True):
     """model(h_a, h_t, mask_a, mask_t) for HOST tensors with copy/compute overlap.
 
     The batch is cut into slabs of utterances that flow through fixed staging buffers (nothing is
@@ -465,6 +481,9 @@ def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optio
         gathers its own; results are scattered back to the original order on the device.
     Returns (logits, beta, z) on `out_device`; host results are fresh PINNED tensors filled by
     asynchronous D2H copies (a pageable `.cpu()` of the 50 MB of z cost 31 ms per step).
+    wait=False (host outputs only) returns a PendingResult instead of synchronising: a stream of batches is
+    then pipelined two deep -- the next call's first slab is copied while this call's last slabs compute, which
+    hides the one latency a single call cannot (nothing computes until its first slab has landed).
     trace (optional list): receives one dict of CUDA events per slab (tools/e2e_timeline.py)."""
     dev = torch.device(device)
     B = h_a.shape[0]
@@ -513,12 +532,12 @@ def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optio
         return h_a[s.lo:s.hi].view(-1), h_t[s.lo:s.hi].view(-1)
 
     return _run_pipeline(model, dev, B, slabs, d_a, d_t, h_a.dtype, h_t.dtype, torch.bfloat16, pack, direct_src,
-                         mask_a, mask_t, mask_a_dev, mask_t_dev, early, out_device, trace)
+                         mask_a, mask_t, mask_a_dev, mask_t_dev, early, out_device, trace, wait)
 
 
 @torch.no_grad()
 def forward_from_shard(model, shard, device="cuda", slab_rows: int = 512 * 500, max_utts: int = 2048,
-                       out_device="cpu", trace: Optional[list] = None):
+                       out_device="cpu", trace: Optional[list] = None, wait: bool = True):
     """The forward over every utterance of a packed feature shard (hriemo.shards.Shard),
     results in SHARD order (shard.original_order() maps back to the writer's input order).
 
@@ -550,4 +569,4 @@ def forward_from_shard(model, shard, device="cuda", slab_rows: int = 512 * 500, 
         shard.read(utt=s.utt, T_a=s.T_a, T_t=s.T_t, out_a=hb["a"], out_t=hb["t"], masks=False, threads=threads)
 
     return _run_pipeline(model, dev, B, slabs, d_a, d_t, shard.dtype, shard.dtype, shard.dtype, pack, None,
-                         None, None, mask_a_dev, mask_t_dev, True, out_device, trace)
+                         None, None, mask_a_dev, mask_t_dev, True, out_device, trace, wait)

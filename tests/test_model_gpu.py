@@ -329,3 +329,37 @@ def test_run_split_writes_the_reference_inference_outputs(tmp_path):
     assert len(layers) == 2 and set(layers[0]) == {"audio_self", "text_self", "audio_queries_text", "text_queries_audio"}
     assert layers[0]["audio_self"].shape == (3, h_a.shape[1], h_a.shape[1]) and isinstance(layers[0]["audio_self"], np.ndarray)
     assert att["decoder"][0][0].shape == (3, 6, h_t.shape[1])
+
+
+def test_forward_from_host_two_calls_in_flight():
+    """wait=False: a second call is issued before the first is awaited (its copies overlap the first call's
+    compute and both share the persistent staging sets).  Different inputs per call: each call must return
+    exactly the device-resident forward of ITS batch, for dense and bucketed plans."""
+    from hriemo import pipeline
+
+    fx = G.load("cfg2_iemocap_ragged")
+    model, ins = G.build_fusion(fx)
+    model = model.to(DEV)
+    g = torch.Generator().manual_seed(77)
+    batches = []
+    for k in range(4):
+        B = 11
+        h_a, h_t = torch.randn(B, 300, 768, generator=g), torch.randn(B, 50, 768, generator=g)
+        m_a, m_t = O.ragged_masks(B, 300, g), O.ragged_masks(B, 50, g)
+        batches.append([x.pin_memory() for x in (h_a, h_t, m_a, m_t)])
+    want = [[o.cpu() for o in model(*[x.to(DEV) for x in b])] for b in batches]
+    torch.cuda.synchronize()
+    for kw in (dict(slab=2, host_cast_every=2), dict(slab=3, host_cast_every=1), dict(slab=4, bucket=True)):
+        pend, got = None, []
+        for b in batches:
+            nxt = pipeline.forward_from_host(model, *b, device=DEV, wait=False, **kw)
+            assert isinstance(nxt, pipeline.PendingResult)
+            if pend is not None:
+                got.append(pend.wait())
+            pend = nxt
+        got.append(pend.wait())
+        for res, ref in zip(got, want):
+            if kw.get("bucket"):
+                assert (res[0] - ref[0]).abs().max().item() <= 2e-3 and (res[1] - ref[1]).abs().max().item() <= 1e-5
+            else:
+                assert torch.equal(res[0], ref[0]) and torch.equal(res[1], ref[1]) and torch.equal(res[2], ref[2])
