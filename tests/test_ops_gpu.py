@@ -514,6 +514,38 @@ def test_small_attention(B, H, Nq, Tk, dh, masked):
     _report("attention_probs", p2, pref, 1e-5, 1e-4)
 
 
+@pytest.mark.parametrize("B,H,Nq,Tk,dh,masked", [(2048, 8, 4, 64, 96, False), (5, 8, 4, 50, 96, True), (3, 4, 6, 128, 64, False),
+                                                  (2, 8, 4, 4, 96, False), (3, 2, 8, 37, 128, True), (2, 4, 1, 1, 32, False),
+                                                  (2, 2, 4, 129, 64, True), (2, 2, 9, 40, 64, False)])
+def test_small_attention_without_probabilities(B, H, Nq, Tk, dh, masked):
+    """The decoder's own call (no probability map: one CTA per (utterance, head)) against the fp64 reference and
+    against the probability-map form (one CTA per utterance looping over heads), incl. NaN for a fully padded
+    utterance.  (A warp-per-head variant with scores in registers was measured at 0.31-0.36 ms against 0.29 ms
+    for the 4 x 64 decoder shape and dropped.)"""
+    from hriemo import ops
+
+    d = H * dh
+    q = _rand((B, Nq, d), 121, dtype=torch.bfloat16)
+    kv = _rand((B * Tk, 2 * d), 122, dtype=torch.bfloat16)
+    pad = _ragged(B, Tk, 123) if masked else None
+    if masked and B > 2:
+        pad[1] = True                                  # every key PAD -> NaN, like torch.softmax
+    out, probs = ops.small_attention(q.view(B * Nq, d), kv[:, :d], kv[:, d:], pad, B, H, Nq, Tk, dh)
+    assert probs is None
+    other, _ = ops.small_attention(q.view(B * Nq, d), kv[:, :d], kv[:, d:], pad, B, H, Nq, Tk, dh, want_probs=True)
+    torch.cuda.synchronize()
+    nan = torch.isnan(other)
+    assert torch.equal(torch.isnan(out), nan)
+    if masked and B > 2:
+        assert nan.view(B, Nq, d)[1].all() and not nan.view(B, Nq, d)[0].any()
+    ok = ~nan
+    assert (out.float() - other.float())[ok].abs().max().item() <= 1e-2      # bf16 outputs of two summation orders
+    sel = [i for i in range(B) if not (masked and B > 2 and i == 1)][:64]
+    ref, _ = _attn_ref(q[sel], kv[:, :d].reshape(B, Tk, d)[sel], kv[:, d:].reshape(B, Tk, d)[sel],
+                       None if pad is None else pad[sel], H)
+    _report("small_attention (no probs)", out.view(B, Nq, d)[sel].reshape(-1, d), ref, 1e-2, 1e-2)
+
+
 def test_emotion_outputs_sigmoid_and_thresholds():
     """sigmoid -> y_prob and the per-class threshold compare of the reference's inference / metrics
     scripts (mosei_eval_infer.py:237-270, mosei_summary_metrics.py:51)."""

@@ -57,6 +57,17 @@ def main():
             res.append(dict(kernel="attention_head_pairs", B=B, H=H, Tq=Tq, Tk=Tk, dh=dh, ms_one_head=m1, ms_pairs=m2, speedup=m1 / m2,
                             gbs_pairs=gb / m2 * 1e3, frac_hbm=gb / m2 * 1e3 / PEAKS["hbm_gbs"]))
             print(res[-1], flush=True)
+    if only in (None, "small"):
+        # decoder attention of one 2048-utterance slab: cross (4 queries x 64 keys) and self (4 x 4)
+        for (B, H, Nq, Tk, dh) in [(2048, 8, 4, 64, 96), (2048, 8, 4, 4, 96), (4096, 4, 6, 128, 64)]:
+            d = H * dh
+            q = torch.randn(B * Nq, d, device=dev).bfloat16(); kv = torch.randn(B * Tk, 2 * d, device=dev).bfloat16()
+            m1, _ = timeit(lambda: ops.small_attention(q, kv[:, :d], kv[:, d:], None, B, H, Nq, Tk, dh))
+            m2, _ = timeit(lambda: ops.small_attention(q, kv[:, :d], kv[:, d:], None, B, H, Nq, Tk, dh, want_probs=True))
+            gb = (B * Tk * 2 * d * 2 + 2 * B * Nq * d * 2) / 1e9
+            res.append(dict(kernel="small_attention", B=B, H=H, Nq=Nq, Tk=Tk, dh=dh, ms=m1, ms_with_probs=m2,
+                            gbs=gb / m1 * 1e3, frac_hbm=gb / m1 * 1e3 / PEAKS["hbm_gbs"]))
+            print(res[-1], flush=True)
     if only in (None, "attention", "ragged"):
         # ragged batch (key lengths uniform in [T/2, T]): skipping trailing all-PAD key tiles
         for (B, H, Tq, Tk, dh) in [(512, 8, 500, 500, 96), (512, 8, 64, 500, 96), (512, 8, 300, 300, 96)]:
