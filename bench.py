@@ -342,11 +342,12 @@ def main():
         stream = timed(e2e_stream, n_stream)
         e2e = {"value": stream, "unit": UNIT, "batch_per_gpu": Be, "steps": n_stream,
                "sequential_value": seq, "sequential_steps": n_e2e,
-               "h2d_bytes_per_step": (pipeline.h2d_bytes(Be, bytes_per_utt) if d_a % 8 == 0 and d_t % 8 == 0 else Be * bytes_per_utt),
+               "h2d_bytes_per_step": (pipeline.h2d_bytes(Be, bytes_per_utt, host_cast_every=pipeline.default_host_cast_every())
+                                      if d_a % 8 == 0 and d_t % 8 == 0 else Be * bytes_per_utt),
                "host_bytes_read_per_step": Be * bytes_per_utt, "d2h_bytes_per_step": int(lo_shape_bytes(model, Be)),
                "api": "hriemo.pipeline.forward_from_host(model, pinned h_a, pinned h_t, wait=False) -> pinned host logits/beta/z; "
                       "a stream of batches with two in flight (step i+1 issued before step i's results are awaited; the pipeline "
-                      "starts cold inside the timed region); every 2nd slab pre-cast to bf16 on the host cores; "
+                      "starts cold inside the timed region); every 2nd slab pre-cast to bf16 on the host cores when the rank has >= 8 host threads; "
                       "sequential_value = one call at a time, each awaited before the next"}
         del ha_h, ht_h
 

@@ -100,6 +100,14 @@ def slab_schedule(B: int, slab: int = 512, host_cast_every: int = 2, ramp: bool 
     return plan
 
 
+def default_host_cast_every(threads: Optional[int] = None) -> int:
+    """Every second slab is pre-cast by the host only when this process has the cores for it: 16 threads convert a
+    512-utterance north-star slab in 11-15 ms (about the GPU's 14 ms per slab), 2-4 threads (8 or 4 ranks sharing a
+    16-core host) in 45-130 ms -- slower than sending the slab as fp32."""
+    threads = max(1, torch.get_num_threads()) if threads is None else threads
+    return 2 if threads >= 8 else 0
+
+
 def h2d_bytes(B: int, fp32_bytes_per_utt: int, slab: int = 512, host_cast_every: int = 2, ramp: bool = False) -> int:
     """Bytes forward_from_host copies host->device for B dense utterances of fp32 features whose feature
     dims are multiples of 8: host-pre-cast slabs travel as bf16 (half the bytes)."""
@@ -461,7 +469,7 @@ def _run_pipeline(model, dev, B: int, slabs: List[_Slab], d_a: int, d_t: int, dt
 @torch.no_grad()
 def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optional[torch.Tensor] = None,
                       mask_t: Optional[torch.Tensor] = None, device="cuda", slab: int = 512,
-                      out_device="cpu", host_cast_every: int = 2, ramp: bool = False, bucket: bool = False,
+                      out_device="cpu", host_cast_every: Optional[int] = None, ramp: bool = False, bucket: bool = False,
                       trace: Optional[list] = None, wait: bool = True):
     """model(h_a, h_t, mask_a, mask_t) for HOST tensors with copy/compute overlap.
 
@@ -469,7 +477,8 @@ def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optio
     allocated or freed per slab for the inputs) on a side stream while earlier slabs compute:
       * fp32 slabs are copied as they are and cast to bf16 on the GPU; their staging set is free again
         as soon as the cast has read it;
-      * every `host_cast_every`-th slab (0 = never) is instead converted to bf16 by the host cores
+      * every `host_cast_every`-th slab (0 = never; default `default_host_cast_every()`: 2 with at least 8
+        host threads for this process, else 0) is instead converted to bf16 by the host cores
         (hriemo_host_pack_bf16 in a worker thread) into pinned bf16 staging and copied at half the
         bytes.  A step is bounded by the 55 GB/s H2D copy of the fp32 features (7.1 GB at the
         north-star batch); with every second slab pre-cast the copy drops under the compute time.
@@ -501,6 +510,8 @@ def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optio
     mask_a = None if mask_a is None else mask_a.to(torch.bool).contiguous()
     mask_t = None if mask_t is None else mask_t.to(torch.bool).contiguous()
     threads = max(1, torch.get_num_threads())
+    if host_cast_every is None:
+        host_cast_every = default_host_cast_every(threads)
     mask_a_dev = mask_t_dev = None
 
     if bucket:

@@ -73,6 +73,13 @@ def test_h2d_byte_accounting_matches_the_staging_schedule():
     assert pipeline.h2d_bytes(1100, per, slab=512, host_cast_every=2) == (512 + 76) * per + 512 * per // 2
 
 
+def test_host_cast_default_follows_the_rank_thread_budget():
+    from hriemo import pipeline
+
+    assert pipeline.default_host_cast_every(16) == 2 and pipeline.default_host_cast_every(8) == 2
+    assert pipeline.default_host_cast_every(4) == 0 and pipeline.default_host_cast_every(1) == 0
+
+
 def test_slab_schedule_covers_the_batch_in_order():
     """Every plan is a partition of [0, B) in order, no slab exceeds the staging size, ramp slabs are
     never host-cast, and small batches get no ramp."""
