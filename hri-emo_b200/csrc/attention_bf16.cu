@@ -79,6 +79,7 @@ struct Attn3Params {
   const int32_t* kv_steps;   // [B] key steps to run per utterance (trailing all-PAD tiles skipped), or null
   const uint8_t* key_pad;
   __nv_bfloat16* out;
+  float* lse;                // [B, H, Tq] natural-log sum of exponentials of the scaled scores, or null
   int64_t ldo;
   int B, H, Tq, Tk;
   int n_kv, n_qp;
@@ -602,6 +603,9 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       consume_pv(pv_issued);
       tc_fence_after_sync();
       const float inv_l = 1.0f / l_run;  // l == 0 (every key masked) -> inf -> NaN like torch.softmax
+      // what a backward pass needs to rebuild P: ln sum_k exp(s_k * scale); this thread's row is its TMEM lane
+      if (p.lse != nullptr && q0 + quad * 32 + lane < p.Tq)
+        p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Tq + q0 + quad * 32 + lane] = (m_run + log2f(l_run)) * 0.6931471805599453f;
       const uint32_t qslot = wg * 2 + (qcnt_w & 1u);
       const uint32_t stage_warp = sQ + qslot * L::Q_TILE + static_cast<uint32_t>(quad) * (32 * DH * 2);
       const uint32_t stage_row = stage_warp + static_cast<uint32_t>(lane) * (DH * 2);
@@ -690,6 +694,7 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
   p.key_pad = a.key_pad;
   p.kv_steps = a.kv_steps;
   p.out = static_cast<__nv_bfloat16*>(a.out);
+  p.lse = a.lse;
   p.ldo = a.ldo;
   p.B = a.B; p.H = a.H; p.Tq = a.Tq; p.Tk = a.Tk;
   p.n_kv = n_kv;

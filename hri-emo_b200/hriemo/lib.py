@@ -46,6 +46,7 @@ class AttnArgs(C.Structure):
         ("scale", C.c_float),
         ("kv_steps", C.c_void_p),
         ("no_head_pairs", C.c_int32),
+        ("lse", C.c_void_p),
     ]
 
 

@@ -195,10 +195,11 @@ def kv_steps(key_pad: torch.Tensor) -> torch.Tensor:
 @_on_tensor_device
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Optional[torch.Tensor],
               B: int, H: int, Tq: int, Tk: int, dh: int, skip_padded_tiles: bool = True,
-              pair_heads: bool = True) -> torch.Tensor:
+              pair_heads: bool = True, want_lse: bool = False):
     """q: [B*Tq, >=H*dh] view, k / v: [B*Tk, >=H*dh] views (column slices of a packed projection are
     fine).  Returns [B*Tq, H*dh] bf16.  pair_heads=False switches the two-heads-per-work-item form of
-    short query sequences off (include/hriemo.h: no_head_pairs; same result bit for bit)."""
+    short query sequences off (include/hriemo.h: no_head_pairs; same result bit for bit).
+    want_lse: also return lse [B, H, Tq] fp32 = ln sum_k exp(scale * q.k) over the unmasked keys."""
     _chk2d(q, bf16, "attention q")
     _chk2d(k, bf16, "attention k")
     _chk2d(v, bf16, "attention v")
@@ -219,10 +220,12 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Option
     args.B, args.H, args.Tq, args.Tk, args.dh = B, H, Tq, Tk, dh
     args.scale = 1.0 / math.sqrt(dh)
     args.no_head_pairs = 0 if pair_heads else 1
+    lse = torch.empty((B, H, Tq), dtype=f32, device=q.device) if want_lse else None
+    args.lse = _ptr(lse)
     tok = _prof_begin("attention", 4.0 * B * H * Tq * Tk * dh)
     _l.check(_l.load().hriemo_attention_bf16(C.byref(args), _stream()), "attention_bf16")
     _prof_end(tok)
-    return out
+    return (out, lse) if want_lse else out
 
 
 @_on_tensor_device

@@ -132,6 +132,9 @@ typedef struct hriemo_attn_args {
   /* Tq <= 128 with an even H runs two heads per work item (one per query tile of the CTA) instead of leaving
    * the second tile idle; same result bit for bit.  Non-zero switches that off (A/B measurements, tests). */
   int32_t no_head_pairs;
+  /* Optional: lse[b, h, t_q] = ln sum_k exp(scale * q.k) over the unmasked keys (f32 [B, H, Tq]; -inf when every key
+   * is masked) -- the per-row statistic a backward pass needs to rebuild the probabilities. */
+  float* lse;
 } hriemo_attn_args;
 
 /* steps[b] = (index of the last valid key of utterance b) / 64 + 1, or 1 when every key is PAD. */

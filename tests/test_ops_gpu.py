@@ -377,6 +377,38 @@ def test_attention_head_pairs_are_bit_exact(B, H, Tq, Tk, dh, masked):
     _report(f"attention head pairs {B,H,Tq,Tk,dh,masked}", two, ref, atol=1.5e-2, rtol=2e-2)
 
 
+@pytest.mark.parametrize("B,H,Tq,Tk,dh,masked", [(3, 8, 300, 300, 96, True), (2, 8, 64, 500, 96, True), (2, 4, 500, 64, 64, False),
+                                                  (2, 2, 130, 1000, 128, True)])
+def test_attention_log_sum_exp_output(B, H, Tq, Tk, dh, masked):
+    """Optional lse output (what a backward pass rebuilds P from): ln sum_k exp(scale * q.k) over the unmasked
+    keys, for the general and the paired-head form, and -inf where every key is masked."""
+    from hriemo import ops
+
+    d = H * dh
+    q = _rand((B, Tq, d), 301, dtype=torch.bfloat16)
+    k = _rand((B, Tk, d), 302, dtype=torch.bfloat16)
+    v = _rand((B, Tk, d), 303, dtype=torch.bfloat16)
+    pad = None
+    if masked:
+        pad = _ragged(B, Tk, 304)
+        pad[B - 1] = True
+    out, lse = ops.attention(q.view(B * Tq, d), k.view(B * Tk, d), v.view(B * Tk, d), pad, B, H, Tq, Tk, dh, want_lse=True)
+    plain = ops.attention(q.view(B * Tq, d), k.view(B * Tk, d), v.view(B * Tk, d), pad, B, H, Tq, Tk, dh)
+    torch.cuda.synchronize()
+    nan = torch.isnan(plain)
+    assert torch.equal(torch.isnan(out), nan) and torch.equal(out.view(torch.int16)[~nan], plain.view(torch.int16)[~nan])
+    s = (q.double().view(B, Tq, H, dh).transpose(1, 2) @ k.double().view(B, Tk, H, dh).transpose(1, 2).transpose(-1, -2)) / math.sqrt(dh)
+    if pad is not None:
+        s = s.masked_fill(pad[:, None, None, :], float("-inf"))
+    ref = torch.logsumexp(s, dim=-1)
+    assert lse.shape == (B, H, Tq) and lse.dtype == torch.float32
+    if masked:
+        assert bool(torch.isinf(lse[B - 1]).all()) and bool((lse[B - 1] < 0).all())
+        assert (lse[: B - 1].double() - ref[: B - 1]).abs().max().item() <= 2e-3
+    else:
+        assert (lse.double() - ref).abs().max().item() <= 2e-3
+
+
 def test_attention_nan_in_neighbour_utterance_does_not_leak():
     """The last key tile of utterance b overhangs into utterance b+1's rows; those keys carry P = 0
     but 0 x NaN would still poison utterance b (a fully padded neighbour is NaN by design)."""
