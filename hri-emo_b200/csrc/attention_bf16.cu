@@ -136,7 +136,7 @@ __device__ __forceinline__ void exp_pack(const uint32_t (&v)[32], float sc, floa
   l4[0] = la.x; l4[2] = la.y; l4[1] = lb.x; l4[3] = lb.y;
 }
 
-template <int DH, bool PAIRED>
+template <int DH, bool PAIRED, bool DEFER>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
@@ -282,11 +282,11 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             for (int t = 0; t < 2; ++t) {
               const uint32_t bar = (t * 2 + (qcnt[t] & 1u)) * 8, qpar = (qcnt[t] >> 1) & 1u;
               if (blocking) mbar_wait(b_qempty + bar, qpar ^ 1);
-              else if (!mbar_try_wait(b_qempty + bar, qpar ^ 1)) return false;
+              else if (!mbar_test_wait(b_qempty + bar, qpar ^ 1)) return false;
             }
           }
           if (blocking) mbar_wait(b_kempty + s * 8, par ^ 1);
-          else if (!mbar_try_wait(b_kempty + s * 8, par ^ 1)) return false;
+          else if (!mbar_test_wait(b_kempty + s * 8, par ^ 1)) return false;
           if (c.f == 0) {
             for (int t = 0; t < 2; ++t) {
               const uint32_t qb = qcnt[t] & 1u;
@@ -357,14 +357,23 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       int s_f = 0;
       int s_nk = s_item < item_last ? steps_of(s_item) : 0;
       bool s_act = tile_active(s_item);
-      auto issue_s = [&]() {
+      // S of the cursor's flat step.  Non-blocking form: returns false, with nothing issued, unless the Q tile
+      // (first key step of an item) and the K tile have landed.
+      auto issue_s = [&](bool blocking) -> bool {
         const uint32_t ks = s_g % KS, kpar = (s_g / KS) & 1u;
         const uint32_t qslot = t * 2 + (qcnt & 1u);
         const bool act = s_act && mine(s_f);
         const int s_j = key_step(s_f);
         ATRACE(t, s_g, 4);
-        if (act && s_j == 0) mbar_wait(b_qfull + qslot * 8, (qcnt >> 1) & 1u);
-        mbar_wait(b_kfull + ks * 8, kpar);
+        if (blocking) {
+          if (act && s_j == 0) mbar_wait(b_qfull + qslot * 8, (qcnt >> 1) & 1u);
+          mbar_wait(b_kfull + ks * 8, kpar);
+        } else {
+          // only the Q tile can be far away (it is loaded once the warpgroup has freed its buffer); a K tile is
+          // in flight, and waiting for it here is what keeps S(g+2) right behind PV(g) on the long-key shapes
+          if (act && s_j == 0 && !mbar_test_wait(b_qfull + qslot * 8, (qcnt >> 1) & 1u)) return false;
+          mbar_wait(b_kfull + ks * 8, kpar);
+        }
         ATRACE(t, s_g, 5);
         if (act) {
           tc_fence_after_sync();
@@ -390,15 +399,43 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           s_act = s_item < item_last && tile_active(s_item);
           s_nk = s_item < item_last ? steps_of(s_item) : 0;
         }
+        return true;
       };
       // General mode: the S cursor leads the PV cursor by two steps (S(g+2) goes into the buffer whose P the
       // PV(g) just issued consumed).  Paired-head mode: by THREE flat steps, so that the tile's next own step
       // S(g+2) is issued one iteration early, at the other tile's flat step g-1 (where this issuer only passes
       // the stage on): it lands in the buffer of P(g-2), whose PV was issued at iteration g-2 -- the same
       // one-step look-ahead for the softmax as in general mode.
-      if (s_item < item_last) issue_s();
-      if (s_item < item_last) issue_s();
-      if (paired && s_item < item_last) issue_s();
+      //
+      // DEFER form (items of one or two key steps, chosen by the launcher): the look-ahead never holds up a PV.
+      // S steps up to `s_allowed` are issued as soon as their Q tile has landed, polled while the issuer waits
+      // for V or P.  Issued unconditionally after each PV -- the other form, right for long items -- S(g+2) of a
+      // one-key-step item sat 4 500 - 7 600 cycles on the Q tile of the item two ahead (which is only loaded once
+      // the warpgroup frees the buffer at the start of item g+1), and the PV of item g+1, whose P had been ready
+      // for 3 000 cycles, waited behind it: profiles/r01_attention_v12_pipeline_trace.txt.  The polling form is
+      // not used for long items: an issuer that polls shares its scheduler with two softmax warps (-4..8 %).
+      constexpr uint32_t S_LEAD = paired ? 3u : 2u;
+      uint32_t s_allowed = S_LEAD;
+      auto pump = [&](bool blocking) {
+        while (s_item < item_last && s_g < s_allowed)
+          if (!issue_s(blocking)) break;
+      };
+      if constexpr (DEFER) {
+        pump(true);
+      } else {
+        if (s_item < item_last) issue_s(true);
+        if (s_item < item_last) issue_s(true);
+        if (paired && s_item < item_last) issue_s(true);
+      }
+      auto wait_pumping = [&](uint32_t bar, uint32_t parity) {
+        if constexpr (DEFER) {
+          while (s_item < item_last && s_g < s_allowed) {
+            if (mbar_test_wait(bar, parity)) return;
+            issue_s(false);
+          }
+        }
+        mbar_wait(bar, parity);
+      };
       // ---- PV cursor
       uint32_t pcnt = 0, pv_item = item_first;
       int pv_f = 0;
@@ -407,13 +444,13 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       for (uint32_t g = 0; pv_item < item_last; ++g) {
         const uint32_t vs = g % KS, vpar = (g / KS) & 1u;
         ATRACE(t, g, 0);
-        mbar_wait(b_vfull + vs * 8, vpar);
+        wait_pumping(b_vfull + vs * 8, vpar);   // never wait without moving the S cursor
         ATRACE(t, g, 1);
         if (pv_act && mine(pv_f)) {
           const int pv_j = key_step(pv_f);
           const int rem = p.Tk - pv_j * A3_BKV;  // keys left from this step on (> 0)
           const uint32_t slot = t * 2 + (pcnt & 1u);
-          mbar_wait(b_pfull + slot * 8, (pcnt >> 1) & 1u);
+          wait_pumping(b_pfull + slot * 8, (pcnt >> 1) & 1u);   // P(g) needs S(g): keep the S cursor moving
           ATRACE(t, g, 2);
           ++pcnt;
           tc_fence_after_sync();
@@ -431,7 +468,12 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         } else {
           mbar_arrive(b_vempty + vs * 8);
         }
-        if (s_item < item_last) issue_s();  // general: S(g+2) reuses the S buffer whose P was just consumed
+        if constexpr (DEFER) {
+          s_allowed = g + 1 + S_LEAD;
+          pump(false);
+        } else {
+          if (s_item < item_last) issue_s(true);  // general: S(g+2) reuses the S buffer whose P was just consumed
+        }
         if (++pv_f == flat_of(pv_nk)) {
           pv_f = 0;
           pv_item += item_stride;
@@ -708,19 +750,27 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
   p.scale_log2 = a.scale * 1.4426950408889634f;
   static uint64_t attr_done = 0;
   if (device_needs_attr(&attr_done)) {
-    cudaError_t e = cudaFuncSetAttribute(attention_fwd3_kernel<DH, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_fwd3_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaSuccess;
+    const void* forms[4] = {reinterpret_cast<const void*>(attention_fwd3_kernel<DH, false, false>),
+                            reinterpret_cast<const void*>(attention_fwd3_kernel<DH, false, true>),
+                            reinterpret_cast<const void*>(attention_fwd3_kernel<DH, true, false>),
+                            reinterpret_cast<const void*>(attention_fwd3_kernel<DH, true, true>)};
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+      e = cudaFuncSetAttribute(forms[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess)
       return set_error(HRIEMO_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
   const int64_t sms = device_sm_count();
   const unsigned grid = static_cast<unsigned>(p.n_items < sms ? p.n_items : sms);
-  if (p.paired)
-    attention_fwd3_kernel<DH, true><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);
+  const bool defer = n_kv <= 2;   // short items: S look-ahead must not hold up a PV (see the kernel)
+  if (p.paired && defer)
+    attention_fwd3_kernel<DH, true, true><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);
+  else if (p.paired)
+    attention_fwd3_kernel<DH, true, false><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);
+  else if (defer)
+    attention_fwd3_kernel<DH, false, true><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);
   else
-    attention_fwd3_kernel<DH, false><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);
+    attention_fwd3_kernel<DH, false, false><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);
   return check_launch("attention_bf16");
 }
 
