@@ -95,6 +95,9 @@ SIGNATURES = {
     "hriemo_grad_norm_clip": (C.c_int, [_P, _I64, _F, _P, _P, _P]),
     "hriemo_adamw_step": (C.c_int, [_P, _P, _P, _P, _I64, _I32, C.c_double, C.c_double, C.c_double, C.c_double,
                                     C.c_double, _P, _P, _P]),
+    "hriemo_linear_wgrad_workspace_bytes": (C.c_int64, [_I64, _I32, _I32]),
+    "hriemo_linear_wgrad_bf16": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _P, _I32, _P, _P]),
+    "hriemo_transpose_bf16": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P]),
     "hriemo_host_pack_bf16": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, _I64, _I64, _I32]),
 }
 

@@ -511,3 +511,66 @@ def adamw_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor,
     _l.check(_l.load().hriemo_adamw_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n,
                                           step, lr, betas[0], betas[1], eps, weight_decay, _ptr(grad_scale),
                                           _ptr(params_bf16), _stream()), "adamw_step")
+
+
+# ------------------------------------------------------------------ backward of a Linear layer
+@_on_tensor_device
+def transpose_bf16(w: torch.Tensor) -> torch.Tensor:
+    """bf16 [rows, cols] -> [cols, rows] (the operand of dX = dY . W for the forward GEMM kernel)."""
+    _chk2d(w, bf16, "transpose_bf16")
+    rows, cols = w.shape
+    out = torch.empty((cols, rows), dtype=bf16, device=w.device)
+    _l.check(_l.load().hriemo_transpose_bf16(w.data_ptr(), w.stride(0), out.data_ptr(), rows, rows, cols, _stream()),
+             "transpose_bf16")
+    return out
+
+
+@_on_tensor_device
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: Optional[torch.Tensor] = None, db: Optional[torch.Tensor] = None,
+                 want_bias: bool = True, accumulate: bool = False):
+    """Gradients of y = x W^T + b w.r.t. W and b: dW [N, K] = dy^T x, db [N] = column sums of dy (fp32), on tcgen05
+    tensor cores with both bf16 operands read as they are.  dw / db: existing fp32 tensors to write (or, with
+    accumulate=True, add) into; otherwise fresh ones are returned."""
+    _chk2d(dy, bf16, "linear_wgrad dy")
+    _chk2d(x, bf16, "linear_wgrad x")
+    M, N = dy.shape
+    K = x.shape[1]
+    if x.shape[0] != M:
+        raise _l.HriemoError(f"linear_wgrad: row counts differ: {tuple(dy.shape)} vs {tuple(x.shape)}")
+    if accumulate and dw is None:
+        raise _l.HriemoError("linear_wgrad: accumulate=True needs dw")
+    dw = torch.empty((N, K), dtype=f32, device=dy.device) if dw is None else dw
+    _chk_f32(dw, (N, K), "linear_wgrad dw")
+    if want_bias:
+        if accumulate and db is None:
+            raise _l.HriemoError("linear_wgrad: accumulate=True needs db when want_bias")
+        db = torch.empty((N,), dtype=f32, device=dy.device) if db is None else db
+        _chk_f32(db, (N,), "linear_wgrad db")
+    else:
+        db = None
+    nbytes = int(_l.load().hriemo_linear_wgrad_workspace_bytes(M, N, K))
+    if nbytes <= 0:
+        raise _l.HriemoError(f"linear_wgrad: unsupported shape M={M} N={N} K={K} (N and K must be multiples of 128)")
+    ws = torch.empty((nbytes // 4,), dtype=f32, device=dy.device)
+    tok = _prof_begin("wgrad", 2.0 * M * N * K)
+    _l.check(_l.load().hriemo_linear_wgrad_bf16(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), M, N, K,
+                                                 dw.data_ptr(), _ptr(db), 1 if accumulate else 0, ws.data_ptr(), _stream()),
+             "linear_wgrad_bf16")
+    _prof_end(tok)
+    return dw, db
+
+
+def linear_backward(dy: torch.Tensor, x: torch.Tensor, w_t: torch.Tensor, want_bias: bool = True):
+    """(dx bf16 [M, K], dW fp32 [N, K], db fp32 [N] | None) of y = x W^T + b given dy [M, N] (bf16), the layer's
+    input x [M, K] (bf16) and the TRANSPOSED weight w_t = transpose_bf16(W) [K, N]."""
+    dx = gemm(dy, _as_gemm_weight(w_t, x.shape[1]), None, _l.EPI_BIAS, tag="dgrad")
+    dw, db = linear_wgrad(dy, x, want_bias=want_bias)
+    return dx, dw, db
+
+
+def _as_gemm_weight(w_t: torch.Tensor, k_in: int) -> torch.Tensor:
+    """The forward GEMM computes A . B^T with B stored [out, contraction]; for dX = dY . W the output dimension is
+    the layer's input width K and the contraction its output width N, i.e. B = W^T stored as [K, N]."""
+    if w_t.shape[0] != k_in:
+        raise _l.HriemoError(f"linear_backward: w_t must be the transposed weight [K={k_in}, N], got {tuple(w_t.shape)}")
+    return w_t

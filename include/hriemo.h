@@ -317,6 +317,18 @@ int hriemo_adamw_step(float* params, const float* grads, float* exp_avg, float* 
                       int32_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
                       const float* grad_scale, void* params_bf16, void* stream);
 
+/* Weight and bias gradient of y = x W^T + b (what loss.backward() accumulates into nn.Linear.weight.grad / .bias.grad,
+ * scripts/fusion/train_fusion_seq_level_decoder.py:332):  dW[N,K] = dY[M,N]^T . X[M,K]  (f32, row pitch K),
+ * db[N] = column sums of dY (optional), both bf16 operands consumed as they lie in HBM (MN-major tcgen05 operands,
+ * split over the rows, partial tiles summed in a fixed order).  accumulate != 0 adds to what dW / db hold.
+ * N and K multiples of 128.  workspace: hriemo_linear_wgrad_workspace_bytes(M, N, K) bytes, 16-byte aligned.
+ * The input gradient dX = dY . W is hriemo_gemm_bf16 on the transposed weight (hriemo_transpose_bf16). */
+int64_t hriemo_linear_wgrad_workspace_bytes(int64_t M, int32_t N, int32_t K);
+int hriemo_linear_wgrad_bf16(const void* dY, int64_t lddy, const void* X, int64_t ldx, int64_t M, int32_t N, int32_t K,
+                             float* dW, float* db, int32_t accumulate, void* workspace, void* stream);
+/* out[c, r] = in[r, c] for a bf16 matrix [rows, cols] (leading dimensions in elements). */
+int hriemo_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int32_t rows, int32_t cols, void* stream);
+
 /* Mean over time (UNMASKED) of an f32 [B,L,d] tensor — models/fusion_classifier.py:145. */
 int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d, void* stream);
 

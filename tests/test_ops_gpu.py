@@ -650,3 +650,52 @@ def test_grad_norm_clip_and_adamw_match_the_training_oracle():
         assert torch.equal(w16, p.to(torch.bfloat16))
     # no clipping requested: coefficient 1
     assert ops.grad_norm_clip(grad.to(DEV), 0.0).cpu()[1].item() == 1.0
+
+
+# ------------------------------------------------------------------ backward of a Linear layer
+@pytest.mark.parametrize("M,N,K", [(64, 128, 128), (1000, 128, 256), (4100, 768, 768), (20000, 3072, 768), (9000, 768, 3072),
+                                   (130, 256, 128)])
+def test_linear_wgrad_matches_autograd(M, N, K):
+    """dW = dY^T X and db = column sums of dY on tcgen05 (both operands MN-major, split over the rows, partials
+    summed in a fixed order) against a float64 reference of what autograd accumulates for nn.Linear; twice the same
+    bits (deterministic); accumulate=True adds to the existing gradient."""
+    from hriemo import ops
+
+    dy = _rand((M, N), 401, dtype=torch.bfloat16)
+    x = _rand((M, K), 402, dtype=torch.bfloat16)
+    dw, db = ops.linear_wgrad(dy, x)
+    dw2, db2 = ops.linear_wgrad(dy, x)
+    torch.cuda.synchronize()
+    ref_w = dy.double().t() @ x.double()
+    ref_b = dy.double().sum(0)
+    scale = math.sqrt(M)
+    assert dw.shape == (N, K) and dw.dtype == torch.float32 and db.shape == (N,)
+    assert (dw.double() - ref_w).abs().max().item() <= 1e-4 * scale      # fp32 accumulation of exact bf16 products
+    assert (db.double() - ref_b).abs().max().item() <= 1e-4 * scale
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+    ops.linear_wgrad(dy, x, dw=dw2, db=db2, accumulate=True)
+    assert (dw2.double() - 2 * ref_w).abs().max().item() <= 2e-4 * scale
+    assert (db2.double() - 2 * ref_b).abs().max().item() <= 2e-4 * scale
+    only_w, none_b = ops.linear_wgrad(dy, x, want_bias=False)
+    assert none_b is None and torch.equal(only_w, dw)
+
+
+def test_linear_backward_of_a_strided_projection():
+    """dX, dW, db of y = x W^T + b for operands that are column slices of wider buffers (the packed QKV layout):
+    dX through the forward GEMM kernel on the transposed weight."""
+    from hriemo import ops
+
+    M, N, K = 3000, 768, 768
+    wide_dy = _rand((M, 3 * N), 411, dtype=torch.bfloat16)
+    wide_x = _rand((M, 2 * K), 412, dtype=torch.bfloat16)
+    dy, x = wide_dy[:, N:2 * N], wide_x[:, K:]
+    w = _rand((N, K), 413, 0.05, dtype=torch.bfloat16)
+    w_t = ops.transpose_bf16(w)
+    assert torch.equal(w_t, w.t().contiguous())
+    dx, dw, db = ops.linear_backward(dy, x, w_t)
+    torch.cuda.synchronize()
+    _report("linear_backward dx", dx, dy.double() @ w.double(), atol=2e-2, rtol=2e-2)
+    assert (dw.double() - dy.double().t() @ x.double()).abs().max().item() <= 1e-4 * math.sqrt(M)
+    assert (db.double() - dy.double().sum(0)).abs().max().item() <= 1e-4 * math.sqrt(M)
+    with pytest.raises(Exception):
+        ops.linear_wgrad(dy[:, :100], x)                                   # N not a multiple of 128
