@@ -147,24 +147,32 @@ __global__ void sum_partials_kernel(const float* __restrict__ partials, int spli
   }
 }
 
-// partial[split][n] = sum over the split's rows of dY[m, n]; block = 32 columns x 8 row lanes
+// partial[split][n] = sum over the split's rows of dY[m, n].  A warp reads 256 consecutive columns of a row (one
+// 16-byte load per lane), the 8 warps of the block stride over the rows; fixed-order combine through shared memory.
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld, int64_t M, int N, int64_t rows_per_split,
                       float* __restrict__ partial) {
-  __shared__ float red[8][33];
-  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int rl = threadIdx.x >> 5;
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
   const int64_t m0 = blockIdx.y * rows_per_split, m1 = min(M, m0 + rows_per_split);
-  float acc = 0.0f;
-  if (col < N)
-    for (int64_t m = m0 + rl; m < m1; m += 8) acc += __bfloat162float(dy[m * ld + col]);
-  red[rl][threadIdx.x & 31] = acc;
+  float acc[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  if (col < N) {   // N is a multiple of 128 and col of 8: a lane's eight columns are all in range or all out
+    for (int64_t m = m0 + w; m < m1; m += 8) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + m * ld + col));
+      acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
+      acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z); acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[w][lane * 8 + i] = acc[i];
   __syncthreads();
-  if (rl == 0 && col < N) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
     float s = 0.0f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) s += red[r][threadIdx.x & 31];
-    partial[static_cast<int64_t>(blockIdx.y) * N + col] = s;
+    for (int r = 0; r < 8; ++r) s += red[r][threadIdx.x];
+    partial[static_cast<int64_t>(blockIdx.y) * N + c] = s;
   }
 }
 
@@ -249,7 +257,7 @@ extern "C" int hriemo_linear_wgrad_bf16(const void* dY, int64_t lddy, const void
   if (rc || db == nullptr) return rc;
   float* bpart = partials + static_cast<int64_t>(splits) * nk;
   const int64_t rps = (M + WG_COLSUM_SPLITS - 1) / WG_COLSUM_SPLITS;
-  colsum_partial_kernel<<<dim3((N + 31) / 32, WG_COLSUM_SPLITS), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dY), lddy, M, N,
+  colsum_partial_kernel<<<dim3((N + 255) / 256, WG_COLSUM_SPLITS), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dY), lddy, M, N,
                                                                               rps, bpart);
   rc = check_launch("linear_wgrad (bias partials)");
   if (rc) return rc;

@@ -57,6 +57,17 @@ def main():
             res.append(dict(kernel="attention_head_pairs", B=B, H=H, Tq=Tq, Tk=Tk, dh=dh, ms_one_head=m1, ms_pairs=m2, speedup=m1 / m2,
                             gbs_pairs=gb / m2 * 1e3, frac_hbm=gb / m2 * 1e3 / PEAKS["hbm_gbs"]))
             print(res[-1], flush=True)
+    if only in (None, "wgrad"):
+        # weight gradients of the encoder's Linear layers for a 512-utterance training slab (M = 512 * 500 rows)
+        for (M, N, K) in [(256000, 2304, 768), (256000, 3072, 768), (256000, 768, 3072), (256000, 768, 768), (32768, 768, 768)]:
+            dy = torch.randn(M, N, device=dev).bfloat16(); x = torch.randn(M, K, device=dev).bfloat16()
+            med, best = timeit(lambda: ops.linear_wgrad(dy, x))
+            med_nb, _ = timeit(lambda: ops.linear_wgrad(dy, x, want_bias=False))
+            medc, _ = timeit(lambda: torch.matmul(dy.t(), x))
+            fl = 2.0 * M * N * K
+            res.append(dict(kernel="linear_wgrad", M=M, N=N, K=K, ms=med, ms_without_bias=med_nb, tflops=fl / med / 1e9, frac_sustained=fl / med / 1e9 / PEAKS.get("bf16_tflops_sustained", PEAKS["bf16_tflops"]),
+                            cublas_ms=medc, cublas_tflops=fl / medc / 1e9))
+            print(res[-1], flush=True)
     if only in (None, "small"):
         # decoder attention of one 2048-utterance slab: cross (4 queries x 64 keys) and self (4 x 4)
         for (B, H, Nq, Tk, dh) in [(2048, 8, 4, 64, 96), (2048, 8, 4, 4, 96), (4096, 4, 6, 128, 64)]:
