@@ -435,6 +435,116 @@ __global__ void mean_over_time_kernel(const float* __restrict__ x, float* __rest
   }
 }
 
+// ------------------------------------------------------------------ backward of LayerNorm and ReLU (training)
+// y = (x - mean) rstd gamma + beta.  dx = rstd (g - mean_c(g) - xhat mean_c(g xhat)), g = dy gamma; the parameter
+// gradients dgamma = sum_rows dy xhat, dbeta = sum_rows dy are accumulated per warp in registers over a grid-stride
+// loop, combined per CTA through shared memory and written as partial[cta][2][d] for a fixed-order final sum.
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_backward_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ dy,
+                          int64_t lddy, const float* __restrict__ gamma, float eps, __nv_bfloat16* __restrict__ dx,
+                          int64_t lddx, float* __restrict__ partial, int64_t rows, int d) {
+  extern __shared__ float part[];   // [8 warps][2][d]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  RowRegs<NV> g_acc, b_acc, gm;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      g_acc.v[i][k] = 0.0f;
+      b_acc.v[i][k] = 0.0f;
+      gm.v[i][k] = c < d ? __ldg(gamma + c + k) : 0.0f;
+    }
+  }
+  const float inv_d = 1.0f / static_cast<float>(d);
+  for (int64_t row = blockIdx.x * 8 + warp; row < rows; row += static_cast<int64_t>(gridDim.x) * 8) {
+    RowRegs<NV> xr, gr;
+    load_row<false, NV>(xr, x + row * ldx, d, lane);
+    load_row<false, NV>(gr, dy + row * lddy, d, lane);
+    float mean, rstd;
+    row_stats(xr, d, lane, eps, mean, rstd);
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < d) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xh = (xr.v[i][k] - mean) * rstd;
+          const float dyv = gr.v[i][k];
+          g_acc.v[i][k] += dyv * xh;
+          b_acc.v[i][k] += dyv;
+          const float g = dyv * gm.v[i][k];
+          xr.v[i][k] = xh;        // keep xhat
+          gr.v[i][k] = g;         // and g = dy * gamma
+          s1 += g;
+          s2 += g * xh;
+        }
+      }
+    }
+    s1 = warp_sum(s1) * inv_d;
+    s2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gr.v[i][k] = rstd * (gr.v[i][k] - s1 - xr.v[i][k] * s2);
+    store_row(gr, dx + row * lddx, nullptr, d, lane);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < d) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        part[(warp * 2 + 0) * d + c + k] = g_acc.v[i][k];
+        part[(warp * 2 + 1) * d + c + k] = b_acc.v[i][k];
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) {
+    const int which = c / d, col = c - which * d;
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[(w * 2 + which) * d + col];
+    partial[static_cast<int64_t>(blockIdx.x) * 2 * d + c] = s;
+  }
+}
+
+// out[0..d) = dgamma, out2[0..d) = dbeta: fixed-order sum of the per-CTA partials (optionally on top of the old value)
+__global__ void ln_param_grad_finalize_kernel(const float* __restrict__ partial, int n_ctas, int d, float* __restrict__ dgamma,
+                                              float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * d) return;
+  float s = 0.0f;
+  for (int i = 0; i < n_ctas; ++i) s += partial[static_cast<int64_t>(i) * 2 * d + c];
+  float* dst = c < d ? dgamma + c : dbeta + (c - d);
+  *dst = (accumulate ? *dst : 0.0f) + s;
+}
+
+// dx = dy where h > 0 else 0 (h = the ReLU's OUTPUT, which is what the forward keeps): 8 elements per thread
+__global__ void relu_backward_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __restrict__ h,
+                                     int64_t ldh, __nv_bfloat16* __restrict__ dx, int64_t lddx, int64_t rows, int cols) {
+  const int64_t chunks = cols / 8, total = rows * chunks;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = idx / chunks;
+    const int c = static_cast<int>(idx - r * chunks) * 8;
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(dy + r * lddy + c));
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(h + r * ldh + c));
+    uint4 o;
+    // a bf16 is positive iff its sign bit is clear and it is not zero
+    auto keep = [](uint32_t gv, uint32_t av) {
+      const uint32_t lo = ((av & 0x8000u) == 0u && (av & 0x7fffu) != 0u) ? (gv & 0xffffu) : 0u;
+      const uint32_t hi = ((av & 0x80000000u) == 0u && (av & 0x7fff0000u) != 0u) ? (gv & 0xffff0000u) : 0u;
+      return lo | hi;
+    };
+    o.x = keep(g.x, a.x); o.y = keep(g.y, a.y); o.z = keep(g.z, a.z); o.w = keep(g.w, a.w);
+    *reinterpret_cast<uint4*>(dx + r * lddx + c) = o;
+  }
+}
+
 static unsigned grid_for(int64_t work_items, int block) {
   int64_t g = (work_items + block - 1) / block;
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
@@ -576,4 +686,55 @@ extern "C" int hriemo_mean_over_time(const float* x, float* out, int32_t B, int3
   mean_over_time_kernel<<<grid_for(static_cast<int64_t>(B) * d, 256), 256, 0,
                           static_cast<cudaStream_t>(stream)>>>(x, out, B, L, d);
   return check_launch("mean_over_time");
+}
+
+static int ln_backward_ctas(int64_t rows) {
+  int64_t g = (rows + 7) / 8;
+  const int64_t cap = static_cast<int64_t>(device_sm_count()) * 2;
+  if (g > cap) g = cap;
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+
+extern "C" int64_t hriemo_layernorm_backward_workspace_bytes(int64_t rows, int32_t d) {
+  return static_cast<int64_t>(ln_backward_ctas(rows)) * 2 * d * static_cast<int64_t>(sizeof(float));
+}
+
+extern "C" int hriemo_layernorm_backward(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* gamma,
+                                         float eps, void* dx, int64_t lddx, float* dgamma, float* dbeta,
+                                         int32_t accumulate, void* workspace, int64_t rows, int32_t d, void* stream) {
+  HRIEMO_REQUIRE(x && dy && gamma && dx && dgamma && dbeta && workspace, "layernorm_backward: null pointer");
+  HRIEMO_REQUIRE(row_shape_ok(d) && d <= 1024 && rows > 0, "layernorm_backward: d=%d must be a multiple of 8 and <= 1024", d);
+  HRIEMO_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx) &&
+                     aligned16(gamma),
+                 "layernorm_backward: misaligned operand");
+  const int ctas = ln_backward_ctas(rows);
+  const size_t smem = static_cast<size_t>(8) * 2 * d * sizeof(float);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  const __nv_bfloat16 *xp = static_cast<const __nv_bfloat16*>(x), *gp = static_cast<const __nv_bfloat16*>(dy);
+  __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(dx);
+  const int nv = (d + 255) / 256;
+  if (smem > 48 * 1024) {
+    cudaFuncSetAttribute(layernorm_backward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4);
+  }
+  if (nv <= 1) layernorm_backward_kernel<1><<<ctas, 256, smem, s>>>(xp, ldx, gp, lddy, gamma, eps, dp, lddx, partial, rows, d);
+  else if (nv == 2) layernorm_backward_kernel<2><<<ctas, 256, smem, s>>>(xp, ldx, gp, lddy, gamma, eps, dp, lddx, partial, rows, d);
+  else if (nv == 3) layernorm_backward_kernel<3><<<ctas, 256, smem, s>>>(xp, ldx, gp, lddy, gamma, eps, dp, lddx, partial, rows, d);
+  else layernorm_backward_kernel<4><<<ctas, 256, smem, s>>>(xp, ldx, gp, lddy, gamma, eps, dp, lddx, partial, rows, d);
+  int rc = check_launch("layernorm_backward");
+  if (rc) return rc;
+  ln_param_grad_finalize_kernel<<<(2 * d + 255) / 256, 256, 0, s>>>(partial, ctas, d, dgamma, dbeta, accumulate);
+  return check_launch("layernorm_backward (parameter gradients)");
+}
+
+extern "C" int hriemo_relu_backward_bf16(const void* dy, int64_t lddy, const void* h, int64_t ldh, void* dx, int64_t lddx,
+                                         int64_t rows, int32_t cols, void* stream) {
+  HRIEMO_REQUIRE(dy && h && dx && rows >= 0 && cols > 0 && cols % 8 == 0, "relu_backward: cols must be a multiple of 8");
+  HRIEMO_REQUIRE(lddy % 8 == 0 && ldh % 8 == 0 && lddx % 8 == 0 && aligned16(dy) && aligned16(h) && aligned16(dx),
+                 "relu_backward: misaligned operand");
+  if (rows == 0) return HRIEMO_OK;
+  relu_backward_kernel<<<grid_for(rows * (cols / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), lddy, static_cast<const __nv_bfloat16*>(h), ldh, static_cast<__nv_bfloat16*>(dx),
+      lddx, rows, cols);
+  return check_launch("relu_backward");
 }

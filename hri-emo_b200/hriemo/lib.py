@@ -98,6 +98,9 @@ SIGNATURES = {
     "hriemo_linear_wgrad_workspace_bytes": (C.c_int64, [_I64, _I32, _I32]),
     "hriemo_linear_wgrad_bf16": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _P, _I32, _P, _P]),
     "hriemo_transpose_bf16": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P]),
+    "hriemo_layernorm_backward_workspace_bytes": (C.c_int64, [_I64, _I32]),
+    "hriemo_layernorm_backward": (C.c_int, [_P, _I64, _P, _I64, _P, _F, _P, _I64, _P, _P, _I32, _P, _I64, _I32, _P]),
+    "hriemo_relu_backward_bf16": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _P]),
     "hriemo_host_pack_bf16": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, _I64, _I64, _I32]),
 }
 

@@ -574,3 +574,41 @@ def _as_gemm_weight(w_t: torch.Tensor, k_in: int) -> torch.Tensor:
     if w_t.shape[0] != k_in:
         raise _l.HriemoError(f"linear_backward: w_t must be the transposed weight [K={k_in}, N], got {tuple(w_t.shape)}")
     return w_t
+
+
+@_on_tensor_device
+def layernorm_backward(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, dgamma: Optional[torch.Tensor] = None,
+                       dbeta: Optional[torch.Tensor] = None, accumulate: bool = False, eps: float = LN_EPS):
+    """Backward of LayerNorm: x [rows, d] bf16 (the layer's input), dy [rows, d] bf16 -> (dx bf16, dgamma fp32, dbeta fp32)."""
+    _chk2d(x, bf16, "layernorm_backward x")
+    _chk2d(dy, bf16, "layernorm_backward dy")
+    rows, d = x.shape
+    if tuple(dy.shape) != (rows, d):
+        raise _l.HriemoError("layernorm_backward: x and dy shapes differ")
+    if accumulate and (dgamma is None or dbeta is None):
+        raise _l.HriemoError("layernorm_backward: accumulate=True needs dgamma and dbeta")
+    dgamma = torch.empty((d,), dtype=f32, device=x.device) if dgamma is None else dgamma
+    dbeta = torch.empty((d,), dtype=f32, device=x.device) if dbeta is None else dbeta
+    _chk_f32(dgamma, (d,), "layernorm_backward dgamma")
+    _chk_f32(dbeta, (d,), "layernorm_backward dbeta")
+    _chk_f32(gamma, (d,), "layernorm_backward gamma")
+    dx = torch.empty((rows, d), dtype=bf16, device=x.device)
+    ws = torch.empty((int(_l.load().hriemo_layernorm_backward_workspace_bytes(rows, d)) // 4,), dtype=f32, device=x.device)
+    _l.check(_l.load().hriemo_layernorm_backward(x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), gamma.data_ptr(), eps,
+                                                  dx.data_ptr(), d, dgamma.data_ptr(), dbeta.data_ptr(), 1 if accumulate else 0,
+                                                  ws.data_ptr(), rows, d, _stream()), "layernorm_backward")
+    return dx, dgamma, dbeta
+
+
+@_on_tensor_device
+def relu_backward(dy: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
+    """dy where h > 0 else 0, h being the ReLU's output (bf16 [rows, cols])."""
+    _chk2d(dy, bf16, "relu_backward dy")
+    _chk2d(h, bf16, "relu_backward h")
+    rows, cols = dy.shape
+    if tuple(h.shape) != (rows, cols):
+        raise _l.HriemoError("relu_backward: shapes differ")
+    dx = torch.empty((rows, cols), dtype=bf16, device=dy.device)
+    _l.check(_l.load().hriemo_relu_backward_bf16(dy.data_ptr(), dy.stride(0), h.data_ptr(), h.stride(0), dx.data_ptr(), cols,
+                                                  rows, cols, _stream()), "relu_backward")
+    return dx

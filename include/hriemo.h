@@ -329,6 +329,18 @@ int hriemo_linear_wgrad_bf16(const void* dY, int64_t lddy, const void* X, int64_
 /* out[c, r] = in[r, c] for a bf16 matrix [rows, cols] (leading dimensions in elements). */
 int hriemo_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int32_t rows, int32_t cols, void* stream);
 
+/* Backward of nn.LayerNorm over the last dim (bf16 activations, fp32 parameter gradients): given the layer's INPUT x
+ * (the pre-LayerNorm sum the forward keeps) and dy, writes dx (bf16) and dgamma / dbeta [d] (f32; accumulate != 0 adds
+ * to what they hold).  Row statistics are recomputed from x.  d <= 1024, multiple of 8.
+ * workspace: hriemo_layernorm_backward_workspace_bytes(rows, d) bytes. */
+int64_t hriemo_layernorm_backward_workspace_bytes(int64_t rows, int32_t d);
+int hriemo_layernorm_backward(const void* x_bf16, int64_t ldx, const void* dy_bf16, int64_t lddy, const float* gamma,
+                              float eps, void* dx_bf16, int64_t lddx, float* dgamma, float* dbeta, int32_t accumulate,
+                              void* workspace, int64_t rows, int32_t d, void* stream);
+/* Backward of ReLU from its OUTPUT h (what the forward keeps): dx = dy where h > 0, else 0 (bf16 [rows, cols]). */
+int hriemo_relu_backward_bf16(const void* dy, int64_t lddy, const void* h, int64_t ldh, void* dx, int64_t lddx,
+                              int64_t rows, int32_t cols, void* stream);
+
 /* Mean over time (UNMASKED) of an f32 [B,L,d] tensor — models/fusion_classifier.py:145. */
 int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d, void* stream);
 

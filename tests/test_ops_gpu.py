@@ -699,3 +699,71 @@ def test_linear_backward_of_a_strided_projection():
     assert (db.double() - dy.double().sum(0)).abs().max().item() <= 1e-4 * math.sqrt(M)
     with pytest.raises(Exception):
         ops.linear_wgrad(dy[:, :100], x)                                   # N not a multiple of 128
+
+
+@pytest.mark.parametrize("rows,d", [(1000, 768), (37, 256), (5000, 192), (300, 1024)])
+def test_layernorm_and_relu_backward(rows, d):
+    from hriemo import ops
+
+    x = _rand((rows, d), 421, dtype=torch.bfloat16)
+    dy = _rand((rows, d), 422, dtype=torch.bfloat16)
+    gamma = (torch.rand(d, device=DEV) + 0.5)
+    beta = _rand((d,), 423)
+    xr = x.double().requires_grad_(True)
+    gr = gamma.double().requires_grad_(True)
+    br = beta.double().requires_grad_(True)
+    y = torch.nn.functional.layer_norm(xr, (d,), gr, br, 1e-5)
+    y.backward(dy.double())
+    dx, dg, db = ops.layernorm_backward(x, dy, gamma)
+    torch.cuda.synchronize()
+    _report("layernorm_backward dx", dx, xr.grad, atol=2e-2, rtol=2e-2)
+    assert (dg.double() - gr.grad).abs().max().item() <= 1e-4 * math.sqrt(rows) + 1e-5
+    assert (db.double() - br.grad).abs().max().item() <= 1e-4 * math.sqrt(rows) + 1e-5
+    dg2, db2 = dg.clone(), db.clone()
+    ops.layernorm_backward(x, dy, gamma, dgamma=dg2, dbeta=db2, accumulate=True)
+    assert torch.allclose(dg2, 2 * dg, rtol=1e-6, atol=1e-6) and torch.allclose(db2, 2 * db, rtol=1e-6, atol=1e-6)
+    h = torch.relu(_rand((rows, d), 424)).bfloat16()
+    got = ops.relu_backward(dy, h)
+    assert torch.equal(got, torch.where(h > 0, dy, torch.zeros_like(dy)))
+
+
+def test_ffn_sublayer_backward_matches_autograd():
+    """One whole sub-layer of the reference, LN(x + W2 relu(W1 x + b1) + b2) (cross_modal_block_tacfn.py:106): forward
+    and backward composed from the library's kernels, gradients against torch autograd in float64 on the same
+    bf16-rounded operands."""
+    from hriemo import lib as L, ops
+
+    M, d, dff = 2048, 768, 3072
+    x = _rand((M, d), 431, dtype=torch.bfloat16)
+    w1 = _rand((dff, d), 432, 0.03, dtype=torch.bfloat16)
+    b1 = _rand((dff,), 433, 0.1)
+    w2 = _rand((d, dff), 434, 0.02, dtype=torch.bfloat16)
+    b2 = _rand((d,), 435, 0.1)
+    gamma = torch.rand(d, device=DEV) + 0.5
+    beta = _rand((d,), 436, 0.1)
+    dy = _rand((M, d), 437, dtype=torch.bfloat16)
+    # ---- forward with the library (keeps h and the pre-LayerNorm sum)
+    h = ops.gemm(x, w1, b1, L.EPI_BIAS_RELU)
+    pre = ops.gemm(h, w2, b2, L.EPI_BIAS_RESID, resid=x)
+    # ---- backward
+    d_pre, dgamma, dbeta = ops.layernorm_backward(pre, dy, gamma)
+    dh_post, dw2, db2 = ops.linear_backward(d_pre, h, ops.transpose_bf16(w2))
+    dh = ops.relu_backward(dh_post, h)
+    dw1, db1 = ops.linear_wgrad(dh, x)
+    dx = ops.gemm(dh, ops.transpose_bf16(w1), None, L.EPI_BIAS_RESID, resid=d_pre)     # + the residual branch
+    torch.cuda.synchronize()
+    # ---- autograd reference
+    t = lambda a: a.double().requires_grad_(True)
+    xr, w1r, b1r, w2r, b2r, gr, br = t(x), t(w1), t(b1), t(w2), t(b2), t(gamma), t(beta)
+    hr = torch.relu(xr @ w1r.t() + b1r)
+    y = torch.nn.functional.layer_norm(xr + hr @ w2r.t() + b2r, (d,), gr, br, 1e-5)
+    y.backward(dy.double())
+
+    def rel(a, b):
+        return ((a.double() - b).norm() / b.norm()).item()
+
+    # bf16 activations and activation gradients on the way (h, pre, d_pre, dh): relative error of the whole tensor
+    assert rel(dx, xr.grad) <= 2e-2
+    assert rel(dw2, w2r.grad) <= 2e-2 and rel(db2, b2r.grad) <= 2e-2
+    assert rel(dw1, w1r.grad) <= 2e-2 and rel(db1, b1r.grad) <= 2e-2
+    assert rel(dgamma, gr.grad) <= 1e-2 and rel(dbeta, br.grad) <= 1e-2
