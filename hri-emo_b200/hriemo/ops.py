@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 

@@ -18,7 +18,7 @@ import ctypes as C
 import json
 import os
 import struct
-from typing import Iterable, List, Optional, Sequence, Tuple
+from typing import Iterable, Optional, Sequence, Tuple
 
 import torch
 

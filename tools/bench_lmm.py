@@ -1,5 +1,5 @@
 import os, sys, torch
-sys.path.insert(0, "hri-emo_b200")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hri-emo_b200"))
 from hriemo import ops
 B, T, d = 2048, 500, 768
 x = torch.randn(B * T, d, device="cuda").bfloat16()
