@@ -190,14 +190,27 @@ transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld_in, __nv_
     if (c0 + c < cols && r0 + tx < rows) out[static_cast<int64_t>(c0 + c) * ld_out + r0 + tx] = tile[tx][c];
 }
 
+// Number of row ranges: the CTAs (tiles x splits) should fill whole waves of the SMs -- 360 CTAs on 148 SMs run three
+// rounds for 2.4 rounds of work -- with at least 8 blocks (512 rows) per split and as few splits as that allows
+// (every split costs a partial tile in the workspace and in the final sum).
 static int wgrad_splits(int64_t M, int N, int K, int bnk) {
   const int64_t tiles = static_cast<int64_t>(N / WG_BN) * (K / bnk);
   const int64_t blocks = (M + WG_MB - 1) / WG_MB;
-  int64_t s = (2 * device_sm_count() + tiles - 1) / tiles;     // about two waves of CTAs
-  if (s > blocks / 8) s = blocks / 8;                          // at least 8 blocks (512 rows) per split
-  if (s < 1) s = 1;
-  if (s > 64) s = 64;
-  return static_cast<int>(s);
+  const int64_t sms = device_sm_count();
+  int64_t s_max = blocks / 8;
+  if (s_max > 64) s_max = 64;
+  if (s_max < 1) s_max = 1;
+  int best = 1;
+  double best_score = -1.0;
+  for (int64_t sp = 1; sp <= s_max; ++sp) {
+    const int64_t ctas = tiles * sp;
+    const int64_t rounds = (ctas + sms - 1) / sms;
+    double eff = static_cast<double>(ctas) / static_cast<double>(rounds * sms);   // filled fraction of the rounds
+    if (rounds > 4) break;                                                         // enough parallelism: stop growing
+    const double score = eff - 0.004 * static_cast<double>(sp);
+    if (score > best_score) { best_score = score; best = static_cast<int>(sp); }
+  }
+  return best;
 }
 constexpr int WG_COLSUM_SPLITS = 64;
 
