@@ -175,6 +175,109 @@ small_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const _
   }
 }
 
+// ------------------------------------------------------------------ small attention, backward (training)
+// Gradients of the decoder attention (models/emotion_decoder.py:42, :48-54; N_q learned queries, T_k keys) for one
+// (utterance, head) per CTA.  P is rebuilt from q, k (exact softmax, as in the forward); then
+//   dV = P^T dO,   dP = dO V^T,   dS = P * (dP - rowsum(dP * P)),   dQ = scale dS K,   dK = scale dS^T Q.
+// Everything is tiny (N_q <= 8, T_k <= a few hundred): fp32 on CUDA cores, shared memory for P / dS.
+constexpr int SB_THREADS = 128;
+
+__global__ void __launch_bounds__(SB_THREADS)
+small_attention_backward_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k,
+                                int64_t ldk, const __nv_bfloat16* __restrict__ v, int64_t ldv,
+                                const __nv_bfloat16* __restrict__ dout, int64_t lddo, const uint8_t* __restrict__ key_pad,
+                                __nv_bfloat16* __restrict__ dq, int64_t lddq, __nv_bfloat16* __restrict__ dk, int64_t lddk,
+                                __nv_bfloat16* __restrict__ dv, int64_t lddv, int H, int Nq, int Tk, int dh, float scale) {
+  extern __shared__ float sm[];
+  float* qs = sm;                       // [SA_NQ][dh]  q * scale
+  float* dos = qs + SA_NQ * dh;         // [SA_NQ][dh]  dO
+  float* ps = dos + SA_NQ * dh;         // [SA_NQ][Tk]  P
+  float* dss = ps + SA_NQ * Tk;         // [SA_NQ][Tk]  dP -> dS
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < Nq * dh; i += SB_THREADS) {
+    const int qi = i / dh, c = i - qi * dh;
+    qs[qi * dh + c] = __bfloat162float(q[(static_cast<int64_t>(b) * Nq + qi) * ldq + h * dh + c]) * scale;
+    dos[qi * dh + c] = __bfloat162float(dout[(static_cast<int64_t>(b) * Nq + qi) * lddo + h * dh + c]);
+  }
+  __syncthreads();
+  // scores and dP = dO . v_j, thread per key
+  for (int j = tid; j < Tk; j += SB_THREADS) {
+    const bool pad = key_pad != nullptr && key_pad[static_cast<int64_t>(b) * Tk + j] != 0;
+    const __nv_bfloat16* kr = k + (static_cast<int64_t>(b) * Tk + j) * ldk + h * dh;
+    const __nv_bfloat16* vr = v + (static_cast<int64_t>(b) * Tk + j) * ldv + h * dh;
+    float s[SA_NQ], dp[SA_NQ];
+#pragma unroll
+    for (int qi = 0; qi < SA_NQ; ++qi) { s[qi] = 0.0f; dp[qi] = 0.0f; }
+    for (int c = 0; c < dh; ++c) {
+      const float kv = __bfloat162float(kr[c]), vv = __bfloat162float(vr[c]);
+#pragma unroll
+      for (int qi = 0; qi < SA_NQ; ++qi) {
+        if (qi < Nq) {
+          s[qi] = fmaf(qs[qi * dh + c], kv, s[qi]);
+          dp[qi] = fmaf(dos[qi * dh + c], vv, dp[qi]);
+        }
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < SA_NQ; ++qi) {
+      if (qi < Nq) {
+        ps[qi * Tk + j] = pad ? -INFINITY : s[qi];
+        dss[qi * Tk + j] = dp[qi];
+      }
+    }
+  }
+  __syncthreads();
+  // softmax per query row, then dS = P * (dP - sum_j dP_j P_j)  (warp per row)
+  for (int qi = warp; qi < Nq; qi += SB_THREADS / 32) {
+    float m = -INFINITY;
+    for (int j = lane; j < Tk; j += 32) m = fmaxf(m, ps[qi * Tk + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.0f;
+    for (int j = lane; j < Tk; j += 32) {
+      const float e = expf(ps[qi * Tk + j] - m);
+      ps[qi * Tk + j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    float dot = 0.0f;
+    for (int j = lane; j < Tk; j += 32) {
+      const float pr = ps[qi * Tk + j] * inv;
+      ps[qi * Tk + j] = pr;
+      dot += pr * dss[qi * Tk + j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    for (int j = lane; j < Tk; j += 32) dss[qi * Tk + j] = ps[qi * Tk + j] * (dss[qi * Tk + j] - dot);
+  }
+  __syncthreads();
+  // dV_j = sum_q P_qj dO_q ; dK_j = sum_q dS_qj (q_q * scale)   (thread per (key, column))
+  for (int i = tid; i < Tk * dh; i += SB_THREADS) {
+    const int j = i / dh, c = i - j * dh;
+    float av = 0.0f, ak = 0.0f;
+#pragma unroll
+    for (int qi = 0; qi < SA_NQ; ++qi) {
+      if (qi < Nq) {
+        av = fmaf(ps[qi * Tk + j], dos[qi * dh + c], av);
+        ak = fmaf(dss[qi * Tk + j], qs[qi * dh + c], ak);
+      }
+    }
+    dv[(static_cast<int64_t>(b) * Tk + j) * lddv + h * dh + c] = __float2bfloat16_rn(av);
+    dk[(static_cast<int64_t>(b) * Tk + j) * lddk + h * dh + c] = __float2bfloat16_rn(ak);
+  }
+  // dQ_q = scale * sum_j dS_qj k_j   (thread per (query, column))
+  for (int i = tid; i < Nq * dh; i += SB_THREADS) {
+    const int qi = i / dh, c = i - qi * dh;
+    float a = 0.0f;
+    for (int j = 0; j < Tk; ++j)
+      a = fmaf(dss[qi * Tk + j], __bfloat162float(k[(static_cast<int64_t>(b) * Tk + j) * ldk + h * dh + c]), a);
+    dq[(static_cast<int64_t>(b) * Nq + qi) * lddq + h * dh + c] = __float2bfloat16_rn(a * scale);
+  }
+}
+
 // ------------------------------------------------------------------ post-path outputs
 // probs = sigmoid(logits); decisions = probs >= threshold[class] (per-class calibrated thresholds,
 // or 0.5 when none are given: equivalent to logit > 0 up to the tie at 0).
@@ -262,4 +365,27 @@ extern "C" int hriemo_attention_probs(const void* q, int64_t ldq, const void* k,
   HRIEMO_REQUIRE((Tq + SA_NQ - 1) / SA_NQ <= 65535, "attention_probs: Tq too large");
   return launch_small_attention(q, ldq, k, ldk, nullptr, 0, key_pad, nullptr, 0, probs, B, H, Tq, Tk, dh, scale,
                                 static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int hriemo_small_attention_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                               int64_t ldv, const void* d_out, int64_t lddo, const uint8_t* key_pad,
+                                               void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                                               int32_t B, int32_t H, int32_t Nq, int32_t Tk, int32_t dh, float scale,
+                                               void* stream) {
+  HRIEMO_REQUIRE(q && k && v && d_out && dq && dk && dv, "small_attention_backward: null pointer");
+  HRIEMO_REQUIRE(B > 0 && H > 0 && H <= 65535 && Nq > 0 && Nq <= SA_NQ && Tk > 0 && dh > 0,
+                 "small_attention_backward: bad shape (at most %d queries)", SA_NQ);
+  const size_t smem = sizeof(float) * (2 * static_cast<size_t>(SA_NQ) * dh + 2 * static_cast<size_t>(SA_NQ) * Tk);
+  HRIEMO_REQUIRE(smem <= 200 * 1024, "small_attention_backward: Tk=%d too long", Tk);
+  static uint64_t attr_done = 0;
+  if (smem > 48 * 1024 && device_needs_attr(&attr_done)) {
+    cudaError_t e = cudaFuncSetAttribute(small_attention_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "small_attention_backward: %s", cudaGetErrorString(e));
+  }
+  using bf = __nv_bfloat16;
+  small_attention_backward_kernel<<<dim3(B, H), SB_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf*>(q), ldq, static_cast<const bf*>(k), ldk, static_cast<const bf*>(v), ldv,
+      static_cast<const bf*>(d_out), lddo, key_pad, static_cast<bf*>(dq), lddq, static_cast<bf*>(dk), lddk,
+      static_cast<bf*>(dv), lddv, H, Nq, Tk, dh, scale);
+  return check_launch("small_attention_backward");
 }

@@ -101,6 +101,8 @@ SIGNATURES = {
     "hriemo_layernorm_backward_workspace_bytes": (C.c_int64, [_I64, _I32]),
     "hriemo_layernorm_backward": (C.c_int, [_P, _I64, _P, _I64, _P, _F, _P, _I64, _P, _P, _I32, _P, _I64, _I32, _P]),
     "hriemo_relu_backward_bf16": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _P]),
+    "hriemo_small_attention_backward": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _P, _I64,
+                                                  _I32, _I32, _I32, _I32, _I32, _F, _P]),
     "hriemo_host_pack_bf16": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, _I64, _I64, _I32]),
 }
 

@@ -612,3 +612,21 @@ def relu_backward(dy: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
     _l.check(_l.load().hriemo_relu_backward_bf16(dy.data_ptr(), dy.stride(0), h.data_ptr(), h.stride(0), dx.data_ptr(), cols,
                                                   rows, cols, _stream()), "relu_backward")
     return dx
+
+
+@_on_tensor_device
+def small_attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, d_out: torch.Tensor,
+                             key_pad: Optional[torch.Tensor], B: int, H: int, Nq: int, Tk: int, dh: int):
+    """Backward of small_attention: (dq [B*Nq, H*dh], dk [B*Tk, H*dh], dv [B*Tk, H*dh]) in bf16."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (d_out, "d_out")):
+        _chk2d(t, bf16, f"small_attention_backward {n}")
+    d = H * dh
+    dq = torch.empty((B * Nq, d), dtype=bf16, device=q.device)
+    dk = torch.empty((B * Tk, d), dtype=bf16, device=q.device)
+    dv = torch.empty((B * Tk, d), dtype=bf16, device=q.device)
+    m = _mask_u8(key_pad, B, Tk, "small_attention_backward")
+    _l.check(_l.load().hriemo_small_attention_backward(
+        q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), d_out.data_ptr(), d_out.stride(0),
+        _ptr(m), dq.data_ptr(), d, dk.data_ptr(), d, dv.data_ptr(), d, B, H, Nq, Tk, dh, 1.0 / math.sqrt(dh), _stream()),
+        "small_attention_backward")
+    return dq, dk, dv

@@ -341,6 +341,14 @@ int hriemo_layernorm_backward(const void* x_bf16, int64_t ldx, const void* dy_bf
 int hriemo_relu_backward_bf16(const void* dy, int64_t lddy, const void* h, int64_t ldh, void* dx, int64_t lddx,
                               int64_t rows, int32_t cols, void* stream);
 
+/* Backward of hriemo_small_attention (the decoder's attention, models/emotion_decoder.py:42, :48-54): given d_out
+ * [B*Nq, H*dh] writes dq [B*Nq, H*dh], dk and dv [B*Tk, H*dh] (bf16; the probabilities are rebuilt from q and k).
+ * At most 8 queries. */
+int hriemo_small_attention_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                    const void* d_out, int64_t lddo, const uint8_t* key_pad, void* dq, int64_t lddq,
+                                    void* dk, int64_t lddk, void* dv, int64_t lddv, int32_t B, int32_t H, int32_t Nq,
+                                    int32_t Tk, int32_t dh, float scale, void* stream);
+
 /* Mean over time (UNMASKED) of an f32 [B,L,d] tensor — models/fusion_classifier.py:145. */
 int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d, void* stream);
 

@@ -767,3 +767,29 @@ def test_ffn_sublayer_backward_matches_autograd():
     assert rel(dw2, w2r.grad) <= 2e-2 and rel(db2, b2r.grad) <= 2e-2
     assert rel(dw1, w1r.grad) <= 2e-2 and rel(db1, b1r.grad) <= 2e-2
     assert rel(dgamma, gr.grad) <= 1e-2 and rel(dbeta, br.grad) <= 1e-2
+
+
+@pytest.mark.parametrize("B,H,Nq,Tk,dh,masked", [(5, 8, 4, 64, 96, True), (3, 4, 6, 128, 64, False), (2, 8, 4, 4, 96, False),
+                                                  (3, 2, 8, 37, 32, True)])
+def test_small_attention_backward_matches_autograd(B, H, Nq, Tk, dh, masked):
+    """dq, dk, dv of the decoder attention against torch autograd (float64) on the same bf16 operands."""
+    from hriemo import ops
+
+    d = H * dh
+    q = _rand((B, Nq, d), 441, dtype=torch.bfloat16)
+    kv = _rand((B * Tk, 2 * d), 442, dtype=torch.bfloat16)
+    do = _rand((B * Nq, d), 443, dtype=torch.bfloat16)
+    pad = _ragged(B, Tk, 444) if masked else None
+    dq, dk, dv = ops.small_attention_backward(q.view(B * Nq, d), kv[:, :d], kv[:, d:], do, pad, B, H, Nq, Tk, dh)
+    torch.cuda.synchronize()
+    qr = q.double().requires_grad_(True)
+    kr = kv[:, :d].double().reshape(B, Tk, d).requires_grad_(True)
+    vr = kv[:, d:].double().reshape(B, Tk, d).requires_grad_(True)
+    s = (qr.view(B, Nq, H, dh).transpose(1, 2) @ kr.view(B, Tk, H, dh).transpose(1, 2).transpose(-1, -2)) / math.sqrt(dh)
+    if pad is not None:
+        s = s.masked_fill(pad[:, None, None, :], float("-inf"))
+    out = (torch.softmax(s, dim=-1) @ vr.view(B, Tk, H, dh).transpose(1, 2)).transpose(1, 2).reshape(B * Nq, d)
+    out.backward(do.double())
+    _report("small_attention_backward dq", dq, qr.grad.view(B * Nq, d), atol=2e-2, rtol=2e-2)
+    _report("small_attention_backward dk", dk, kr.grad.view(B * Tk, d), atol=2e-2, rtol=2e-2)
+    _report("small_attention_backward dv", dv, vr.grad.view(B * Tk, d), atol=2e-2, rtol=2e-2)
