@@ -1,0 +1,185 @@
+"""Backward pass from the loss to the encoder outputs (BASELINE config 5).
+
+What `loss.backward()` does in scripts/fusion/train_fusion_seq_level_decoder.py:332 for everything downstream of
+the cross-modal encoder: the loss (:319-327), the emotion decoder (models/emotion_decoder.py:33-64, :117-162) and
+the vector beta-gate (models/beta_gate_tacfn.py:68-118).  It is a schedule of C-ABI kernels like engine.py, not an
+autograd graph: the training-mode forward keeps the activations the backward needs in plain dicts ("tapes") and
+the backward walks the sub-layers in reverse order.
+
+Gradients are returned under the reference's own parameter names (what `named_parameters()` of the reference
+model yields), fp32, so that they can be written into the flat gradient arena of train_ops.cu.  Activation
+gradients travel as bf16 like the activations; the gate MLP and the head are fp32 in both directions.
+
+The gate's training forward differs from the inference schedule in one respect: LN(a) and LN(t) are written to
+HBM as bf16 tensors (the backward reads them twice) instead of being applied on the fly inside the pooling and
+blend kernels; streams that arrive with a pending encoder LayerNorm are materialised first.
+
+Dropout: the parity configuration is dropout = 0, which is what this computes.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import engine as E
+from . import lib as L
+from . import ops
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+Grads = Dict[str, torch.Tensor]
+
+
+def _t(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] bf16 weight -> [K, N]: the operand of dX = dY . W for the forward GEMM kernel."""
+    return ops.transpose_bf16(w)
+
+
+# --------------------------------------------------------------------------- #
+# beta-gate
+# --------------------------------------------------------------------------- #
+def gate_forward_train(gate, a: E.Seq, t: E.Seq, mask_a, mask_t) -> Tuple[E.Seq, torch.Tensor, dict]:
+    """BetaGate forward (beta_gate_tacfn.py:79-116) keeping what gate_backward needs.  -> (h, beta [B,1], tape)."""
+    if a.T < t.T:
+        raise RuntimeError(f"BetaGate: audio length {a.T} is shorter than text length {t.T}")
+    P = gate._prep.get()
+    a, t = E.materialize(a), E.materialize(t)
+    na, _ = ops.layernorm(a.x, *P["norm_a"])                                                   # :79
+    nt, _ = ops.layernorm(t.x, *P["norm_t"])                                                   # :80
+    a_pool = ops.ln_masked_mean(na, None, None, mask_a, a.B, a.T, apply_ln=False)              # :83
+    t_pool = ops.ln_masked_mean(nt, None, None, mask_t, t.B, t.T, apply_ln=False)              # :84
+    g = ops.gate_input(a_pool, t_pool)                                                         # :87-89
+    hid = ops.sgemm(g, P["w0"], P["b0"], L.ACT_RELU)
+    w = ops.sgemm(hid, P["w2"], P["b2"], L.ACT_SIGMOID)                                        # :92
+    hb, _, beta = ops.gate_blend(na, a.T, nt, None, None, w, a.B, t.T, apply_ln=False)         # :95-116
+    tape = dict(a=a, t=t, na=na, nt=nt, a_pool=a_pool, t_pool=t_pool, g=g, hid=hid, w=w, mask_a=mask_a, mask_t=mask_t)
+    return E.Seq(hb, a.B, t.T), beta, tape
+
+
+def gate_backward(gate, tape: dict, dh: torch.Tensor, dbeta: Optional[torch.Tensor]):
+    """dh: bf16 [B*L, d] gradient of the fused sequence, dbeta: fp32 [B, 1] | None.
+    -> (d_a bf16 [B*T_a, d], d_t bf16 [B*T_t, d], grads under the names of BetaGate's parameters)."""
+    P = gate._prep.get()
+    a, t = tape["a"], tape["t"]
+    B, T_a, Lf = a.B, a.T, t.T
+    G: Grads = {}
+    dw = ops.gate_blend_backward_w(dh, tape["na"], T_a, tape["nt"], dbeta, B, Lf)              # :95, :113-116
+    d_lin2 = ops.act_backward_f32(dw, tape["w"], L.ACT_SIGMOID)                                # :92
+    d_hid, G["mlp.2.weight"], G["mlp.2.bias"] = ops.linear_backward_f32(d_lin2, tape["hid"], P["w2"])
+    d_lin0 = ops.act_backward_f32(d_hid, tape["hid"], L.ACT_RELU)
+    dg, G["mlp.0.weight"], G["mlp.0.bias"] = ops.linear_backward_f32(d_lin0, tape["g"], P["w0"])
+    da_pool, dt_pool = ops.gate_input_backward(dg, tape["a_pool"], tape["t_pool"])             # :87-89
+    inv_a = ops.mask_inv_counts(dh, tape["mask_a"], B, T_a)                                    # :20-24
+    inv_t = ops.mask_inv_counts(dh, tape["mask_t"], B, Lf)
+    d_na = ops.gate_stream_grad(dh, Lf, tape["w"], False, da_pool, tape["mask_a"], inv_a, B, T_a)
+    d_nt = ops.gate_stream_grad(dh, Lf, tape["w"], True, dt_pool, tape["mask_t"], inv_t, B, Lf)
+    d_a, G["norm_a.weight"], G["norm_a.bias"] = ops.layernorm_backward(a.x, d_na, P["norm_a"][0])   # :79
+    d_t, G["norm_t.weight"], G["norm_t.bias"] = ops.layernorm_backward(t.x, d_nt, P["norm_t"][0])   # :80
+    return d_a, d_t, G
+
+
+# --------------------------------------------------------------------------- #
+# emotion decoder
+# --------------------------------------------------------------------------- #
+def decoder_forward_train(dec, mem: E.Seq, mem_mask):
+    """EmotionDecoder forward (the inference schedule, emotion_decoder.py:117-162) with tapes.
+    -> (z [B, N_e, d] fp32, logits [B, N_e] fp32, tape)."""
+    if dec.out_proj is None:
+        raise L.HriemoError("decoder_forward_train: the training step needs the output layer (use_output_layer=True)")
+    tapes: list = []
+    z, logits, _ = dec.run(mem, mem_mask, False, tapes=tapes)
+    return z, logits, dict(layers=tapes, mem=mem, mem_mask=mem_mask, z=z)
+
+
+def _decoder_layer_backward(P: dict, tape: dict, dz: torch.Tensor, d_mem: Optional[torch.Tensor], mem: E.Seq, mem_mask,
+                            Ne: int, n_heads: int):
+    """Reverse of engine.decoder_layer.  dz: bf16 [B*N_e, d] gradient of the layer's output; d_mem: the gradient of
+    the memory accumulated so far (the next layer's share) or None.  -> (dz_in, d_mem, grads)."""
+    B, Lm = mem.B, mem.T
+    d = dz.shape[1]
+    dh = d // n_heads
+    dev = dz.device
+    G: Grads = {}
+    # ---- z3 = LN3(z2 + W2 relu(W1 z2 + b1) + b2)                                              :58-59
+    d_pre3, G["norm3.weight"], G["norm3.bias"] = ops.layernorm_backward(ops.cast_bf16(tape["pre3"]), dz, P["norm3"][0])
+    d_hpost, G["linear2.weight"], G["linear2.bias"] = ops.linear_backward(d_pre3, tape["h"], _t(P["lin2"]["w"]))
+    d_hid = ops.relu_backward(d_hpost, tape["h"])
+    G["linear1.weight"], G["linear1.bias"] = ops.linear_wgrad(d_hid, tape["zb2"])
+    dz2 = ops.gemm(d_hid, _t(P["lin1"]["w"]), None, L.EPI_BIAS_RESID, resid=d_pre3, tag="dgrad")
+    # ---- z2 = LN2(z1 + MHA(z1, mem, mem))                                                     :48-55
+    d_pre2, G["norm2.weight"], G["norm2.bias"] = ops.layernorm_backward(ops.cast_bf16(tape["pre2"]), dz2, P["norm2"][0])
+    d_ca, G["cross_attn.out_proj.weight"], G["cross_attn.out_proj.bias"] = ops.linear_backward(
+        d_pre2, tape["ca"], _t(P["cross_wo"]))
+    kv = tape["kv_mem"]
+    dq = torch.empty((B * Ne, d), dtype=bf16, device=dev)
+    dkv = torch.empty((B * Lm, 2 * d), dtype=bf16, device=dev)
+    ops.small_attention_backward(tape["qc"], kv[:, :d], kv[:, d:], d_ca, mem_mask, B, n_heads, Ne, Lm, dh,
+                                 out=(dq, dkv[:, :d], dkv[:, d:]))
+    w_in = torch.empty((3 * d, d), dtype=f32, device=dev)
+    b_in = torch.empty((3 * d,), dtype=f32, device=dev)
+    ops.linear_wgrad(dq, tape["zb1"], dw=w_in[:d], db=b_in[:d])
+    ops.linear_wgrad(dkv, mem.x, dw=w_in[d:], db=b_in[d:])
+    G["cross_attn.in_proj_weight"], G["cross_attn.in_proj_bias"] = w_in, b_in
+    dz1 = ops.gemm(dq, _t(P["cross_wq"]), None, L.EPI_BIAS_RESID, resid=d_pre2, tag="dgrad")
+    if d_mem is None:
+        d_mem = ops.gemm(dkv, _t(P["cross_wkv"]), None, L.EPI_BIAS, tag="dgrad")
+    else:
+        d_mem = ops.gemm(dkv, _t(P["cross_wkv"]), None, L.EPI_BIAS_RESID, resid=d_mem, tag="dgrad")
+    # ---- z1 = LN1(z0 + MHA(z0, z0, z0))                                                       :42-43
+    d_pre1, G["norm1.weight"], G["norm1.bias"] = ops.layernorm_backward(ops.cast_bf16(tape["pre1"]), dz1, P["norm1"][0])
+    d_sa, G["self_attn.out_proj.weight"], G["self_attn.out_proj.bias"] = ops.linear_backward(
+        d_pre1, tape["sa"], _t(P["self"]["w_o"]))
+    qkv = tape["qkv"]
+    dqkv = torch.empty((B * Ne, 3 * d), dtype=bf16, device=dev)
+    ops.small_attention_backward(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], d_sa, None, B, n_heads, Ne, Ne, dh,
+                                 out=(dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:]))
+    G["self_attn.in_proj_weight"], G["self_attn.in_proj_bias"] = ops.linear_wgrad(dqkv, tape["zb_in"])
+    dz_in = ops.gemm(dqkv, _t(P["self"]["w_qkv"]), None, L.EPI_BIAS_RESID, resid=d_pre1, tag="dgrad")
+    return dz_in, d_mem, G
+
+
+def decoder_backward(dec, tape: dict, d_logits: torch.Tensor):
+    """d_logits: fp32 [B, N_e].  -> (d_mem bf16 [B*L, d], grads under the names of EmotionDecoder's parameters)."""
+    P = dec._prep.get()
+    mem, mem_mask = tape["mem"], tape["mem_mask"]
+    B, Ne, d = mem.B, dec.num_emotions, dec.d_model
+    G: Grads = {}
+    # logits = Linear(d, 1)(z).squeeze(-1)                                                      :153-155
+    z32 = tape["z"].view(B * Ne, d)
+    dz32, G["out_proj.weight"], G["out_proj.bias"] = ops.linear_backward_f32(
+        d_logits.contiguous().view(B * Ne, 1), z32, P["w_out"])
+    dz = ops.cast_bf16(dz32)
+    d_mem = None
+    for i in range(len(dec.layers) - 1, -1, -1):
+        layer = dec.layers[i]
+        dz, d_mem, g = _decoder_layer_backward(layer._prep.get(), tape["layers"][i], dz, d_mem, mem, mem_mask, Ne,
+                                               layer.nhead)
+        for k, v in g.items():
+            G[f"layers.{i}.{k}"] = v
+    # the queries are broadcast over the batch (:127): their gradient is the sum over it
+    G["emotion_queries"] = ops.sum_rows(dz.view(B, Ne * d)).view(Ne, d)
+    if d_mem is None:   # a decoder without layers never looks at the memory
+        d_mem = torch.zeros((B * mem.T, d), dtype=bf16, device=dz.device)
+    return d_mem, G
+
+
+# --------------------------------------------------------------------------- #
+# loss -> encoder outputs
+# --------------------------------------------------------------------------- #
+def decode_loss_and_backward(model, a: E.Seq, t: E.Seq, mask_a, mask_t, labels: torch.Tensor,
+                             beta_weight: float = 0.01) -> dict:
+    """Gate -> decoder -> loss and back, for a FusionWithEmotionDecoder-like `model` (attributes beta_gate and
+    emotion_decoder) given the encoder outputs a / t.  Returns a dict:
+      loss [1], logits [B, N_e], beta [B, 1], z [B, N_e, d]  (fp32);
+      grads: {"beta_gate.*", "emotion_decoder.*": fp32 tensors shaped like the parameters};
+      d_a [B*T_a, d], d_t [B*T_t, d]: bf16 gradients of the encoder outputs (input of the encoder's backward)."""
+    h, beta, gate_tape = gate_forward_train(model.beta_gate, a, t, mask_a, mask_t)
+    fused_mask = model._build_fused_mask(mask_a, mask_t, h.T)
+    z, logits, dec_tape = decoder_forward_train(model.emotion_decoder, h, fused_mask)
+    loss, d_logits, d_beta = ops.bce_beta_loss(logits, labels, beta, beta_weight)
+    d_h, g_dec = decoder_backward(model.emotion_decoder, dec_tape, d_logits)
+    d_a, d_t, g_gate = gate_backward(model.beta_gate, gate_tape, d_h, d_beta)
+    grads: Grads = {f"beta_gate.{k}": v for k, v in g_gate.items()}
+    grads.update({f"emotion_decoder.{k}": v for k, v in g_dec.items()})
+    return dict(loss=loss, logits=logits, beta=beta, z=z, grads=grads, d_a=d_a, d_t=d_t)

@@ -262,20 +262,25 @@ def dec_residual_ln(pre32: torch.Tensor, ln) -> Tuple[torch.Tensor, torch.Tensor
 
 
 def decoder_layer(zb, z32, kv_mem, mem_mask, P: dict, B: int, Ne: int, Lm: int, n_heads: int,
-                  want_attn: bool):
-    """models/emotion_decoder.py:33-64.  kv_mem = [K|V] projection of the memory for this layer."""
+                  want_attn: bool, tape: Optional[dict] = None):
+    """models/emotion_decoder.py:33-64.  kv_mem = [K|V] projection of the memory for this layer.
+    tape (training): receives the activations the backward pass needs (hriemo/backward.py)."""
     d = zb.shape[1]
     dh = d // n_heads
+    zb_in = zb
     qkv = ops.gemm(zb, P["self"]["w_qkv"], P["self"]["b_qkv"], L.EPI_BIAS)
     sa, _ = ops.small_attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], None, B, n_heads, Ne, Ne, dh)
-    pre = ops.gemm(sa, P["self"]["w_o"], P["self"]["b_o"], L.EPI_BIAS_RESID_F32, resid=z32)
-    zb, z32 = dec_residual_ln(pre, P["norm1"])
-    q = ops.gemm(zb, P["cross_wq"], P["cross_bq"], L.EPI_BIAS)
+    pre1 = ops.gemm(sa, P["self"]["w_o"], P["self"]["b_o"], L.EPI_BIAS_RESID_F32, resid=z32)
+    zb1, z32 = dec_residual_ln(pre1, P["norm1"])
+    q = ops.gemm(zb1, P["cross_wq"], P["cross_bq"], L.EPI_BIAS)
     ca, probs = ops.small_attention(q, kv_mem[:, :d], kv_mem[:, d:], mem_mask, B, n_heads, Ne, Lm, dh,
                                     want_probs=want_attn)
-    pre = ops.gemm(ca, P["cross_wo"], P["cross_bo"], L.EPI_BIAS_RESID_F32, resid=z32)
-    zb, z32 = dec_residual_ln(pre, P["norm2"])
-    h = ops.gemm(zb, P["lin1"]["w"], P["lin1"]["b"], L.EPI_BIAS_RELU)
-    pre = ops.gemm(h, P["lin2"]["w"], P["lin2"]["b"], L.EPI_BIAS_RESID_F32, resid=z32)
-    zb, z32 = dec_residual_ln(pre, P["norm3"])
+    pre2 = ops.gemm(ca, P["cross_wo"], P["cross_bo"], L.EPI_BIAS_RESID_F32, resid=z32)
+    zb2, z32 = dec_residual_ln(pre2, P["norm2"])
+    h = ops.gemm(zb2, P["lin1"]["w"], P["lin1"]["b"], L.EPI_BIAS_RELU)
+    pre3 = ops.gemm(h, P["lin2"]["w"], P["lin2"]["b"], L.EPI_BIAS_RESID_F32, resid=z32)
+    zb, z32 = dec_residual_ln(pre3, P["norm3"])
+    if tape is not None:
+        tape.update(zb_in=zb_in, qkv=qkv, sa=sa, pre1=pre1, zb1=zb1, qc=q, kv_mem=kv_mem, ca=ca, pre2=pre2, zb2=zb2,
+                    h=h, pre3=pre3)
     return zb, z32, probs

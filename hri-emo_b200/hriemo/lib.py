@@ -103,6 +103,13 @@ SIGNATURES = {
     "hriemo_relu_backward_bf16": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _P]),
     "hriemo_small_attention_backward": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _P, _I64,
                                                   _I32, _I32, _I32, _I32, _I32, _F, _P]),
+    "hriemo_linear_backward_f32": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _I32, _P, _I64, _P, _P, _I32, _P]),
+    "hriemo_act_backward_f32": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
+    "hriemo_sum_rows": (C.c_int, [_P, _I32, _I64, _P, _I64, _I32, _I32, _P]),
+    "hriemo_gate_input_backward": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P]),
+    "hriemo_mask_inv_counts": (C.c_int, [_P, _I32, _I32, _P, _P]),
+    "hriemo_gate_blend_backward_w": (C.c_int, [_P, _I64, _P, _I64, _I32, _P, _I64, _P, _P, _I32, _I32, _I32, _P]),
+    "hriemo_gate_stream_grad": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P]),
     "hriemo_host_pack_bf16": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, _I64, _I64, _I32]),
 }
 

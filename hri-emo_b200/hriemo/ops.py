@@ -616,17 +616,148 @@ def relu_backward(dy: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
 
 @_on_tensor_device
 def small_attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, d_out: torch.Tensor,
-                             key_pad: Optional[torch.Tensor], B: int, H: int, Nq: int, Tk: int, dh: int):
-    """Backward of small_attention: (dq [B*Nq, H*dh], dk [B*Tk, H*dh], dv [B*Tk, H*dh]) in bf16."""
+                             key_pad: Optional[torch.Tensor], B: int, H: int, Nq: int, Tk: int, dh: int, out=None):
+    """Backward of small_attention: (dq [B*Nq, H*dh], dk [B*Tk, H*dh], dv [B*Tk, H*dh]) in bf16.
+    out = (dq, dk, dv): existing row-major bf16 views to write (e.g. the columns of one [rows, 3d] / [rows, 2d]
+    buffer, so that the projection's backward sees one operand)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (d_out, "d_out")):
         _chk2d(t, bf16, f"small_attention_backward {n}")
     d = H * dh
-    dq = torch.empty((B * Nq, d), dtype=bf16, device=q.device)
-    dk = torch.empty((B * Tk, d), dtype=bf16, device=q.device)
-    dv = torch.empty((B * Tk, d), dtype=bf16, device=q.device)
+    if out is None:
+        dq = torch.empty((B * Nq, d), dtype=bf16, device=q.device)
+        dk = torch.empty((B * Tk, d), dtype=bf16, device=q.device)
+        dv = torch.empty((B * Tk, d), dtype=bf16, device=q.device)
+    else:
+        dq, dk, dv = out
+        for t, n, rows in ((dq, "dq", B * Nq), (dk, "dk", B * Tk), (dv, "dv", B * Tk)):
+            _chk2d(t, bf16, f"small_attention_backward {n}")
+            if tuple(t.shape) != (rows, d):
+                raise _l.HriemoError(f"small_attention_backward: {n} must be [{rows}, {d}], got {tuple(t.shape)}")
     m = _mask_u8(key_pad, B, Tk, "small_attention_backward")
     _l.check(_l.load().hriemo_small_attention_backward(
         q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), d_out.data_ptr(), d_out.stride(0),
-        _ptr(m), dq.data_ptr(), d, dk.data_ptr(), d, dv.data_ptr(), d, B, H, Nq, Tk, dh, 1.0 / math.sqrt(dh), _stream()),
+        _ptr(m), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0), B, H, Nq, Tk, dh,
+        1.0 / math.sqrt(dh), _stream()),
         "small_attention_backward")
     return dq, dk, dv
+
+
+# ------------------------------------------------------------------ backward of the fp32 gate / head
+@_on_tensor_device
+def linear_backward_f32(dy: torch.Tensor, x: Optional[torch.Tensor], w: Optional[torch.Tensor], want_dx: bool = True,
+                        want_dw: bool = True, want_bias: bool = True, dw: Optional[torch.Tensor] = None,
+                        db: Optional[torch.Tensor] = None, accumulate: bool = False):
+    """Backward of sgemm's y = x W^T + b in fp32: (dx [M,K] | None, dW [N,K] | None, db [N] | None)."""
+    _chk2d(dy, f32, "linear_backward_f32 dy")
+    M, N = dy.shape
+    if want_dx:
+        _chk2d(w, f32, "linear_backward_f32 W")
+        K = w.shape[1]
+    if want_dw:
+        _chk2d(x, f32, "linear_backward_f32 x")
+        K = x.shape[1]
+    if not (want_dx or want_dw):
+        K = 1
+    if (want_dx and tuple(w.shape) != (N, K)) or (want_dw and tuple(x.shape) != (M, K)):
+        raise _l.HriemoError("linear_backward_f32: operand shapes do not match dy")
+    if accumulate and ((want_dw and dw is None) or (want_bias and db is None)):
+        raise _l.HriemoError("linear_backward_f32: accumulate=True needs dw / db")
+    dx = torch.empty((M, K), dtype=f32, device=dy.device) if want_dx else None
+    if want_dw:
+        dw = torch.empty((N, K), dtype=f32, device=dy.device) if dw is None else dw
+        _chk_f32(dw, (N, K), "linear_backward_f32 dw")
+    else:
+        dw = None
+    if want_bias:
+        db = torch.empty((N,), dtype=f32, device=dy.device) if db is None else db
+        _chk_f32(db, (N,), "linear_backward_f32 db")
+    else:
+        db = None
+    _l.check(_l.load().hriemo_linear_backward_f32(dy.data_ptr(), dy.stride(0), _ptr(x) if want_dw else None,
+                                                   x.stride(0) if want_dw else 0, _ptr(w) if want_dx else None,
+                                                   w.stride(0) if want_dx else 0, M, N, K, _ptr(dx), K, _ptr(dw), _ptr(db),
+                                                   1 if accumulate else 0, _stream()), "linear_backward_f32")
+    return dx, dw, db
+
+
+@_on_tensor_device
+def act_backward_f32(dy: torch.Tensor, y: torch.Tensor, act: int) -> torch.Tensor:
+    """dy * act'(y) from the activation's output y (ACT_RELU / ACT_SIGMOID), contiguous fp32 tensors of one shape."""
+    if dy.dtype != f32 or y.dtype != f32 or dy.shape != y.shape or not dy.is_contiguous() or not y.is_contiguous():
+        raise _l.HriemoError("act_backward_f32: expected two contiguous fp32 tensors of one shape")
+    dx = torch.empty_like(dy)
+    _l.check(_l.load().hriemo_act_backward_f32(dy.data_ptr(), y.data_ptr(), dx.data_ptr(), dy.numel(), act, _stream()),
+             "act_backward_f32")
+    return dx
+
+
+@_on_tensor_device
+def sum_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """Column sums of a [rows, cols] bf16 / fp32 matrix in fp32 (fixed summation order)."""
+    if x.dtype not in (bf16, f32):
+        raise _l.HriemoError(f"sum_rows: unsupported dtype {x.dtype}")
+    _chk2d(x, x.dtype, "sum_rows x")
+    rows, cols = x.shape
+    if accumulate and out is None:
+        raise _l.HriemoError("sum_rows: accumulate=True needs out")
+    out = torch.empty((cols,), dtype=f32, device=x.device) if out is None else out
+    _chk_f32(out, (cols,), "sum_rows out")
+    _l.check(_l.load().hriemo_sum_rows(x.data_ptr(), int(x.dtype == f32), x.stride(0), out.data_ptr(), rows, cols,
+                                        1 if accumulate else 0, _stream()), "sum_rows")
+    return out
+
+
+@_on_tensor_device
+def gate_input_backward(dg: torch.Tensor, a_pool: torch.Tensor, t_pool: torch.Tensor):
+    B, d = a_pool.shape
+    _chk_f32(dg, (B, 4 * d), "gate_input_backward dg")
+    _chk_f32(a_pool, (B, d), "gate_input_backward a_pool")
+    _chk_f32(t_pool, (B, d), "gate_input_backward t_pool")
+    da, dt = torch.empty_like(a_pool), torch.empty_like(t_pool)
+    _l.check(_l.load().hriemo_gate_input_backward(dg.data_ptr(), a_pool.data_ptr(), t_pool.data_ptr(), da.data_ptr(),
+                                                   dt.data_ptr(), B, d, _stream()), "gate_input_backward")
+    return da, dt
+
+
+@_on_tensor_device
+def mask_inv_counts(like: torch.Tensor, pad: Optional[torch.Tensor], B: int, T: int) -> torch.Tensor:
+    """1 / max(1, #non-PAD positions) per utterance (1 / T without a mask), fp32 [B] on the device of `like`."""
+    m = _mask_u8(pad, B, T, "mask_inv_counts")
+    out = torch.empty((B,), dtype=f32, device=like.device)
+    _l.check(_l.load().hriemo_mask_inv_counts(_ptr(m), B, T, out.data_ptr(), _stream()), "mask_inv_counts")
+    return out
+
+
+@_on_tensor_device
+def gate_blend_backward_w(dh: torch.Tensor, na: torch.Tensor, T_a: int, nt: torch.Tensor, dbeta: Optional[torch.Tensor],
+                          B: int, L: int) -> torch.Tensor:
+    """dw [B, d] fp32 of h = w*na[:, :L] + (1-w)*nt, beta = mean_d(w), from dh [B*L, d] and dbeta [B, 1]."""
+    for t, n in ((dh, "dh"), (na, "na"), (nt, "nt")):
+        _chk2d(t, bf16, f"gate_blend_backward_w {n}")
+    d = dh.shape[1]
+    if dh.shape[0] != B * L or nt.shape[0] != B * L or na.shape[0] != B * T_a:
+        raise _l.HriemoError("gate_blend_backward_w: row counts do not match (B, L, T_a)")
+    if dbeta is not None:
+        _chk_f32(dbeta.view(-1), (B,), "gate_blend_backward_w dbeta")
+    dw = torch.empty((B, d), dtype=f32, device=dh.device)
+    _l.check(_l.load().hriemo_gate_blend_backward_w(dh.data_ptr(), dh.stride(0), na.data_ptr(), na.stride(0), T_a,
+                                                     nt.data_ptr(), nt.stride(0), _ptr(dbeta), dw.data_ptr(), B, L, d,
+                                                     _stream()), "gate_blend_backward_w")
+    return dw
+
+
+@_on_tensor_device
+def gate_stream_grad(dh: torch.Tensor, L: int, w: torch.Tensor, one_minus: bool, dpool: torch.Tensor,
+                     pad: Optional[torch.Tensor], inv_counts: torch.Tensor, B: int, T: int) -> torch.Tensor:
+    """Gradient w.r.t. a LayerNorm-ed gate stream [B*T, d] (bf16): blend share on the first L rows + pooled-mean share."""
+    _chk2d(dh, bf16, "gate_stream_grad dh")
+    d = dh.shape[1]
+    _chk_f32(w, (B, d), "gate_stream_grad w")
+    _chk_f32(dpool, (B, d), "gate_stream_grad dpool")
+    _chk_f32(inv_counts, (B,), "gate_stream_grad inv_counts")
+    m = _mask_u8(pad, B, T, "gate_stream_grad")
+    dn = torch.empty((B * T, d), dtype=bf16, device=dh.device)
+    _l.check(_l.load().hriemo_gate_stream_grad(dh.data_ptr(), dh.stride(0), L, w.data_ptr(), int(one_minus),
+                                                dpool.data_ptr(), _ptr(m), inv_counts.data_ptr(), dn.data_ptr(), d, B, T, d,
+                                                _stream()), "gate_stream_grad")
+    return dn

@@ -50,8 +50,8 @@ class ExplainableDecoderLayer(nn.Module):
         P = self._prep.get()
         return ops.gemm(mem.x, P["cross_wkv"], P["cross_bkv"], L.EPI_BIAS)  # [B*L, 2d] = [K|V]
 
-    def run(self, zb, z32, kv_mem, mem_mask, B: int, Ne: int, Lm: int, want_attn: bool):
-        return E.decoder_layer(zb, z32, kv_mem, mem_mask, self._prep.get(), B, Ne, Lm, self.nhead, want_attn)
+    def run(self, zb, z32, kv_mem, mem_mask, B: int, Ne: int, Lm: int, want_attn: bool, tape: dict | None = None):
+        return E.decoder_layer(zb, z32, kv_mem, mem_mask, self._prep.get(), B, Ne, Lm, self.nhead, want_attn, tape)
 
     @torch.no_grad()
     def forward(self, tgt, memory, memory_key_padding_mask=None, return_attention=False):
@@ -89,14 +89,19 @@ class EmotionDecoder(nn.Module):
             p.update(w_out=E.v32(self.out_proj.weight), b_out=E.v32(self.out_proj.bias))
         return p
 
-    def run(self, mem: E.Seq, mem_mask, want_attn: bool = False):
+    def run(self, mem: E.Seq, mem_mask, want_attn: bool = False, tapes: list | None = None):
+        """tapes (training): a list that receives one dict of saved activations per layer (hriemo/backward.py)."""
         P = self._prep.get()
         B, Ne, d = mem.B, self.num_emotions, self.d_model
         z32 = P["q32"].unsqueeze(0).expand(B, Ne, d).contiguous().view(B * Ne, d)  # :127 (broadcast copy)
         zb = ops.cast_bf16(z32)
         attn = []
         for layer in self.layers:
-            zb, z32, probs = layer.run(zb, z32, layer.project_memory(mem), mem_mask, B, Ne, mem.T, want_attn)
+            tape = None
+            if tapes is not None:
+                tape = {}
+                tapes.append(tape)
+            zb, z32, probs = layer.run(zb, z32, layer.project_memory(mem), mem_mask, B, Ne, mem.T, want_attn, tape)
             if want_attn and probs is not None:
                 attn.append(probs)
         logits = None

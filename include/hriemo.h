@@ -299,7 +299,7 @@ int hriemo_shard_close(void* handle);
  * (scripts/fusion/train_fusion_seq_level_decoder.py:318-335, setup :405-416).  Parameters, gradients and
  * the two AdamW moments are flat fp32 arenas (the module's tensors are views into them), so the global norm
  * is one reduction, the update one launch and the data-parallel exchange one all-reduce.  The model's
- * backward kernels are not part of this round. */
+ * backward kernels built so far follow below. */
 /* loss_out[0] = BCEWithLogitsLoss(mean)(logits [B,C], labels [B,C]) - beta_weight * mean(beta * (1 - beta));
  * d_logits [B,C] / d_beta [B] (optional) receive d loss / d logits and d loss / d beta. */
 int hriemo_bce_beta_loss(const float* logits, const float* labels, const float* beta, float beta_weight,
@@ -348,6 +348,37 @@ int hriemo_small_attention_backward(const void* q, int64_t ldq, const void* k, i
                                     const void* d_out, int64_t lddo, const uint8_t* key_pad, void* dq, int64_t lddq,
                                     void* dk, int64_t lddk, void* dv, int64_t lddv, int32_t B, int32_t H, int32_t Nq,
                                     int32_t Tk, int32_t dh, float scale, void* stream);
+
+/* ---- backward of the fp32 parts between the loss and the encoder outputs: the gate (models/beta_gate_tacfn.py:79-116)
+ * and the decoder's head and queries (models/emotion_decoder.py:127, :153-155).  All reductions in a fixed order. */
+/* Backward of y = x W^T + b in fp32 (the gate MLP, the Linear(d,1) head; forward: hriemo_sgemm_f32): any of
+ * dX [M,K] = dY . W, dW [N,K] = dY^T . X (row pitch K), db [N] = column sums of dY may be NULL; accumulate != 0 adds to
+ * what dW / db hold. */
+int hriemo_linear_backward_f32(const float* dY, int64_t lddy, const float* X, int64_t ldx, const float* W, int64_t ldw,
+                               int64_t M, int32_t N, int32_t K, float* dX, int64_t lddx, float* dW, float* db,
+                               int32_t accumulate, void* stream);
+/* dx = dy * act'(y) from the activation's OUTPUT y (HRIEMO_ACT_RELU / HRIEMO_ACT_SIGMOID / NONE), n fp32 elements. */
+int hriemo_act_backward_f32(const float* dy, const float* y, float* dx, int64_t n, int32_t act, void* stream);
+/* out[c] (+)= sum over the rows of x [rows, cols] (bf16, or f32 when x_is_f32): the gradient of the emotion queries
+ * (models/emotion_decoder.py:127 broadcasts them over the batch) from a [B, N_e*d] view. */
+int hriemo_sum_rows(const void* x, int32_t x_is_f32, int64_t ldx, float* out, int64_t rows, int32_t cols,
+                    int32_t accumulate, void* stream);
+/* Backward of hriemo_gate_input (g = [a, t, |a-t|, a*t], :87-89): dg [B,4d] -> da_pool, dt_pool [B,d]. */
+int hriemo_gate_input_backward(const float* dg, const float* a_pool, const float* t_pool, float* da_pool,
+                               float* dt_pool, int32_t B, int32_t d, void* stream);
+/* inv_counts[b] = 1 / max(1, number of non-PAD positions) (masked_mean's denominator, :20-24); pad NULL -> 1 / T. */
+int hriemo_mask_inv_counts(const uint8_t* pad, int32_t B, int32_t T, float* inv_counts, void* stream);
+/* Gradient of the gate vector through the blend h = w*na[:, :L] + (1-w)*nt and beta = mean_d(w) (:95, :113-116):
+ * dw[b,c] = sum_l dh[b,l,c] (na[b,l,c] - nt[b,l,c]) + dbeta[b] / d.  dh, nt: bf16 [B*L, d]; na: bf16 [B*T_a, d]
+ * (the LayerNorm-ed streams); dbeta [B] may be NULL. */
+int hriemo_gate_blend_backward_w(const void* dh, int64_t lddh, const void* na, int64_t ldna, int32_t T_a, const void* nt,
+                                 int64_t ldnt, const float* dbeta, float* dw, int32_t B, int32_t L, int32_t d,
+                                 void* stream);
+/* Gradient w.r.t. one LayerNorm-ed stream [B,T,d] of the gate: the blend's share on its first L rows (coefficient w, or
+ * 1 - w with one_minus) plus the masked mean's share dpool[b] * inv_counts[b] on its non-PAD rows.  dn: bf16 [B*T, d]. */
+int hriemo_gate_stream_grad(const void* dh, int64_t lddh, int32_t L, const float* w, int32_t one_minus,
+                            const float* dpool, const uint8_t* pad, const float* inv_counts, void* dn, int64_t lddn,
+                            int32_t B, int32_t T, int32_t d, void* stream);
 
 /* Mean over time (UNMASKED) of an f32 [B,L,d] tensor — models/fusion_classifier.py:145. */
 int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d, void* stream);

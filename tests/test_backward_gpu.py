@@ -1,0 +1,190 @@
+"""Backward from the loss to the encoder outputs (B200 only): the row kernels of csrc/train_rows.cu one by one against
+torch, then the whole gate -> decoder -> loss schedule of hriemo/backward.py against autograd over the oracle's
+restated forward in float64 (oracle/hriemo_oracle.py, pinned to the reference by tests/test_oracle_*.py).
+
+Tolerances: the fp32 kernels are compared element-wise (1e-5 relative to the tensor's scale: fp32 sums in another
+order); the composed backward carries bf16 activations and bf16 activation gradients through two decoder layers and
+the gate, so whole-tensor relative errors ||got - ref|| / ||ref|| are bounded by 5e-2 (measured values are written
+to gpurun_out/backward_errors.json when that directory exists)."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def _ragged(B, T, seed):
+    """Trailing-PAD masks (True = PAD) with at least one valid position per utterance; utterance 0 is full length."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    lens[0] = T
+    return (torch.arange(T)[None, :] >= lens[:, None]).to(DEV)
+
+
+def _close(got, ref, tol=1e-5):
+    scale = ref.abs().max().item() + 1e-30
+    err = (got.double() - ref.double()).abs().max().item()
+    assert err <= tol * scale, f"max err {err:.3g} vs scale {scale:.3g}"
+
+
+def _rel(got, ref):
+    ref = ref.double().to(got.device)
+    return ((got.double() - ref).norm() / (ref.norm() + 1e-300)).item()
+
+
+# ------------------------------------------------------------------ row kernels
+@pytest.mark.parametrize("M,N,K", [(37, 5, 70), (512, 256, 3072), (1000, 1, 768), (64, 768, 256)])
+def test_linear_backward_f32(M, N, K):
+    from hriemo import ops
+
+    dy, x, w = _rand((M, N), 501), _rand((M, K), 502), _rand((N, K), 503, 0.1)
+    dx, dw, db = ops.linear_backward_f32(dy, x, w)
+    _close(dx, dy.double() @ w.double(), 2e-5)
+    _close(dw, dy.double().t() @ x.double(), 2e-5)
+    _close(db, dy.double().sum(0), 2e-5)
+    # accumulate into existing gradients; strided dy (a column block of a wider matrix)
+    wide = _rand((M, N + 3), 504)
+    dw2, db2 = dw.clone(), db.clone()
+    ops.linear_backward_f32(wide[:, 3:], x, w, want_dx=False, dw=dw2, db=db2, accumulate=True)
+    _close(dw2, dw.double() + wide[:, 3:].double().t() @ x.double(), 2e-5)
+    _close(db2, db.double() + wide[:, 3:].double().sum(0), 2e-5)
+
+
+def test_act_backward_and_sum_rows_and_inv_counts():
+    from hriemo import lib as L, ops
+
+    dy = _rand((33, 257), 511)
+    y = torch.relu(_rand((33, 257), 512))
+    assert torch.equal(ops.act_backward_f32(dy, y, L.ACT_RELU), torch.where(y > 0, dy, torch.zeros_like(dy)))
+    s = torch.sigmoid(_rand((33, 257), 513))
+    _close(ops.act_backward_f32(dy, s, L.ACT_SIGMOID), dy.double() * s.double() * (1 - s.double()), 1e-6)
+    for dtype in (torch.float32, torch.bfloat16):
+        x = _rand((301, 1000), 514, dtype=dtype)
+        out = ops.sum_rows(x)
+        _close(out, x.double().sum(0), 2e-5)
+        ops.sum_rows(x, out=out, accumulate=True)
+        _close(out, 2 * x.double().sum(0), 2e-5)
+    pad = _ragged(19, 45, 515)
+    pad[3] = True   # an utterance without a valid position: the denominator is clamped to 1
+    inv = ops.mask_inv_counts(dy, pad, 19, 45)
+    _close(inv, 1.0 / (~pad).sum(1).clamp(min=1).double(), 1e-6)
+    _close(ops.mask_inv_counts(dy, None, 19, 45), torch.full((19,), 1.0 / 45, device=DEV), 1e-6)
+
+
+def test_gate_input_backward_matches_autograd():
+    from hriemo import ops
+
+    B, d = 21, 768
+    a, t, dg = _rand((B, d), 521), _rand((B, d), 522), _rand((B, 4 * d), 523)
+    t[0, :5] = a[0, :5]   # |a - t| at 0: torch's abs backward gives 0
+    da, dt = ops.gate_input_backward(dg, a, t)
+    ar, tr = a.double().requires_grad_(True), t.double().requires_grad_(True)
+    torch.cat([ar, tr, (ar - tr).abs(), ar * tr], dim=-1).backward(dg.double())
+    _close(da, ar.grad, 1e-6)
+    _close(dt, tr.grad, 1e-6)
+
+
+@pytest.mark.parametrize("B,T_a,L,d,masked", [(7, 50, 20, 768, True), (3, 16, 16, 256, False), (5, 33, 9, 384, True)])
+def test_gate_blend_backward_kernels_match_autograd(B, T_a, L, d, masked):
+    """dw through the blend and beta, and the gradients of the two LayerNorm-ed streams (blend + masked mean)."""
+    from hriemo import ops
+
+    na = _rand((B * T_a, d), 531, dtype=torch.bfloat16)
+    nt = _rand((B * L, d), 532, dtype=torch.bfloat16)
+    dh = _rand((B * L, d), 533, dtype=torch.bfloat16)
+    w = torch.sigmoid(_rand((B, d), 534))
+    dbeta = _rand((B, 1), 535)
+    dpa, dpt = _rand((B, d), 536), _rand((B, d), 537)
+    ma = _ragged(B, T_a, 538) if masked else None
+    mt = _ragged(B, L, 539) if masked else None
+    dw = ops.gate_blend_backward_w(dh, na, T_a, nt, dbeta, B, L)
+    d_na = ops.gate_stream_grad(dh, L, w, False, dpa, ma, ops.mask_inv_counts(dh, ma, B, T_a), B, T_a)
+    d_nt = ops.gate_stream_grad(dh, L, w, True, dpt, mt, ops.mask_inv_counts(dh, mt, B, L), B, L)
+    torch.cuda.synchronize()
+
+    def mm(x, m):   # masked_mean, beta_gate_tacfn.py:6-24
+        if m is None:
+            return x.mean(1)
+        v = (~m).double()
+        return (x * v[..., None]).sum(1) / v.sum(1, keepdim=True).clamp(min=1.0)
+
+    nar = na.double().view(B, T_a, d).requires_grad_(True)
+    ntr = nt.double().view(B, L, d).requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    h = wr[:, None, :] * nar[:, :L] + (1 - wr[:, None, :]) * ntr
+    obj = (h * dh.double().view(B, L, d)).sum() + (wr.mean(-1, keepdim=True) * dbeta.double()).sum() \
+        + (mm(nar, ma) * dpa.double()).sum() + (mm(ntr, mt) * dpt.double()).sum()
+    obj.backward()
+    _close(dw, wr.grad, 1e-5)
+    # bf16 outputs: one rounding
+    assert _rel(d_na, nar.grad.view(B * T_a, d)) <= 4e-3
+    assert _rel(d_nt, ntr.grad.view(B * L, d)) <= 4e-3
+
+
+# ------------------------------------------------------------------ the composed backward
+def _oracle_backward(model, a, t, ma, mt, labels, n_heads, beta_weight=0.01):
+    """Autograd over the oracle's float64 restatement of gate -> decoder -> loss on the CPU."""
+    import hriemo_oracle as O
+    import hriemo_oracle_train as OT
+
+    sd = {k: v.detach().double().cpu().requires_grad_(True) for k, v in model.state_dict().items()
+          if k.startswith(("beta_gate.", "emotion_decoder."))}
+    ar = a.double().cpu().requires_grad_(True)
+    tr = t.double().cpu().requires_grad_(True)
+    ma = None if ma is None else ma.cpu()
+    mt = None if mt is None else mt.cpu()
+    h, beta = O.beta_gate_tacfn(sd, "beta_gate.", ar, tr, ma, mt)
+    z, logits, _ = O.emotion_decoder(sd, "emotion_decoder.", h, O.build_fused_mask(ma, mt, h.shape[1]), n_heads)
+    loss = OT.bce_with_logits(logits, labels.double().cpu()) - beta_weight * OT.beta_regulariser(beta)
+    loss.backward()
+    return loss.detach(), logits.detach(), beta.detach(), {k: v.grad for k, v in sd.items()}, ar.grad, tr.grad
+
+
+@pytest.mark.parametrize("B,T_a,T_t,d,H,Ne,masked", [(24, 80, 32, 768, 8, 4, True), (16, 40, 40, 256, 4, 6, False)])
+def test_decode_loss_and_backward_matches_autograd(B, T_a, T_t, d, H, Ne, masked):
+    from hriemo import backward, engine as E
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    torch.manual_seed(541)
+    model = FusionWithEmotionDecoder(d_model=d, num_emotions=Ne, n_heads=H, num_layers_fusion=1, num_layers_decoder=2,
+                                     beta_hidden=128, dropout=0.0).to(DEV)
+    with torch.no_grad():   # LayerNorm parameters away from (1, 0), queries of unit scale already
+        for n, p in model.named_parameters():
+            if "norm" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    # stand-ins for the encoder outputs (post-LayerNorm scale), exactly representable in bf16
+    a = _rand((B, T_a, d), 542, dtype=torch.bfloat16)
+    t = _rand((B, T_t, d), 543, dtype=torch.bfloat16)
+    ma = _ragged(B, T_a, 544) if masked else None
+    mt = _ragged(B, T_t, 545) if masked else None
+    labels = (torch.rand(B, Ne, generator=torch.Generator().manual_seed(546)) < 0.4).float().to(DEV)
+
+    out = backward.decode_loss_and_backward(model, E.Seq(a.view(B * T_a, d), B, T_a), E.Seq(t.view(B * T_t, d), B, T_t),
+                                            ma, mt, labels)
+    torch.cuda.synchronize()
+    loss, logits, beta, grads, d_a, d_t = _oracle_backward(model, a, t, ma, mt, labels, H)
+
+    assert abs(out["loss"].item() - loss.item()) <= 5e-3
+    assert (out["logits"].double().cpu() - logits).abs().max().item() <= 3e-2
+    assert (out["beta"].double().cpu() - beta).abs().max().item() <= 2e-3
+    errs = {"d_a": _rel(out["d_a"], d_a.view(B * T_a, d)), "d_t": _rel(out["d_t"], d_t.view(B * T_t, d))}
+    assert set(out["grads"]) == set(grads), sorted(set(out["grads"]) ^ set(grads))
+    for k, ref in grads.items():
+        got = out["grads"][k]
+        assert got.dtype == torch.float32 and tuple(got.shape) == tuple(ref.shape), k
+        errs[k] = _rel(got, ref)
+    if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        with open(os.path.join(ROOT, "gpurun_out", f"backward_errors_d{d}.json"), "w") as f:
+            json.dump(errs, f, indent=1, sort_keys=True)
+    bad = {k: v for k, v in errs.items() if not v <= 5e-2}
+    assert not bad, f"relative errors above 5e-2: {bad}"

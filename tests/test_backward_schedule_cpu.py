@@ -1,0 +1,57 @@
+"""The schedule of hriemo/backward.py on the CPU: every kernel wrapper is replaced by a torch stand-in
+(tests/kernel_standins.py, test infrastructure) and the composed gate -> decoder -> loss backward is compared with
+autograd over the oracle's float64 forward.  This pins the host logic — saved activations, operand order,
+residual joins, parameter names — without a GPU; the kernels are checked on the B200 (tests/test_backward_gpu.py).
+Two modes: exact (all stand-ins in float64 without any rounding: the schedule must reproduce autograd to 1e-9,
+which is the logic check) and bf16 (stand-ins round where the kernels do: shows the noise level of bf16 activations
+and activation gradients on tiny batches, where a ReLU whose pre-activation changes sign under bf16 rounding costs
+a whole element of the gradient; bound 0.2 on the whole-tensor relative error)."""
+import pytest
+import torch
+
+import kernel_standins
+from test_backward_gpu import _oracle_backward, _rel
+
+
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("B,T_a,T_t,d,H,Ne,masked", [(6, 20, 12, 256, 4, 4, True), (5, 9, 9, 128, 2, 6, False)])
+def test_decode_loss_and_backward_schedule(monkeypatch, B, T_a, T_t, d, H, Ne, masked, exact):
+    kernel_standins.install(monkeypatch, exact=exact)
+    tol = 1e-9 if exact else 0.2
+    from hriemo import backward, engine as E
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    torch.manual_seed(7)
+    model = FusionWithEmotionDecoder(d_model=d, num_emotions=Ne, n_heads=H, num_layers_fusion=1, num_layers_decoder=2,
+                                     beta_hidden=64, dropout=0.0)
+    if exact:
+        model = model.double()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "norm" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    g = torch.Generator().manual_seed(8)
+    a = torch.randn(B, T_a, d, generator=g).bfloat16()
+    t = torch.randn(B, T_t, d, generator=g).bfloat16()
+    if exact:
+        a, t = a.double(), t.double()
+    ma = mt = None
+    if masked:
+        la = torch.randint(1, T_a + 1, (B,), generator=g)
+        lt = torch.randint(1, T_t + 1, (B,), generator=g)
+        ma = torch.arange(T_a)[None, :] >= la[:, None]
+        mt = torch.arange(T_t)[None, :] >= lt[:, None]
+    labels = (torch.rand(B, Ne, generator=g) < 0.4).to(torch.float64 if exact else torch.float32)
+
+    out = backward.decode_loss_and_backward(model, E.Seq(a.view(B * T_a, d), B, T_a), E.Seq(t.view(B * T_t, d), B, T_t),
+                                            ma, mt, labels)
+    loss, logits, beta, grads, d_a, d_t = _oracle_backward(model, a, t, ma, mt, labels, H)
+    assert abs(out["loss"].item() - loss.item()) <= (1e-12 if exact else 5e-3)
+    assert (out["logits"].double() - logits).abs().max().item() <= (1e-10 if exact else 3e-2)
+    assert set(out["grads"]) == set(grads), sorted(set(out["grads"]) ^ set(grads))
+    errs = {"d_a": _rel(out["d_a"], d_a.view(B * T_a, d)), "d_t": _rel(out["d_t"], d_t.view(B * T_t, d))}
+    for k, ref in grads.items():
+        assert tuple(out["grads"][k].shape) == tuple(ref.shape), k
+        errs[k] = _rel(out["grads"][k], ref)
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, f"relative errors above {tol}: {bad}"
