@@ -1,0 +1,376 @@
+// Backward of hriemo_attention_bf16 (the encoder's self- and cross-attention, models/cross_modal_block_tacfn.py:74-80,
+// 85-91, 98-104, 111-117) for the training step (BASELINE config 5).
+//
+//   P  = exp(scale * Q K^T - LSE)            (rebuilt from the forward's log-sum-exp, no running maximum needed)
+//   dV = P^T dO,  dP = dO V^T,  dS = scale * P o (dP - D),  D = rowsum(dO o O),  dQ = dS K,  dK = dS^T Q
+//
+// FIRST CORRECT VERSION, not the final one: the contractions run on the tensor cores through warp-level
+// mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with operands staged in padded shared memory, NOT through
+// tcgen05/TMEM/TMA like the forward kernel (attention_bf16.cu); DESIGN.md sec. 8 describes the tcgen05 form that
+// replaces it.  Two deterministic passes instead of atomics: one CTA per (utterance, head, 64-key tile) walks the
+// query tiles and owns dK / dV of its keys; one CTA per (utterance, head, 64-query tile) walks the key tiles and
+// owns dQ of its queries.  S and dP are therefore computed twice (7 tile GEMMs per tile pair instead of 5).
+//
+// use_fma != 0 replaces every mma.sync by plain fp32 FMA loops over the same shared-memory tiles (same
+// thread-to-element mapping): the slow reference form the tests compare the tensor-core form with.
+#include <cuda_bf16.h>
+
+#include "host_common.h"
+
+namespace hriemo {
+
+using bf = __nv_bfloat16;
+
+constexpr int AB_T = 64;          // queries per tile and keys per tile
+constexpr int AB_LDT = AB_T + 8;  // padded pitch of a [.][64] tile: 36 words, rows g = 0..7 fall on distinct banks
+constexpr int AB_THREADS = 256;   // 8 warps: 4 row blocks of 16 x 2 column halves
+
+// acc[16 x NT*8] += A[16 x K] . B[NT*8 x K]^T with A, B row-major bf16 in shared memory (A at the warp's first row,
+// B at the warp's first output column).  Fragment layout of mma.m16n8k16 (g = lane / 4, t = lane % 4):
+//   A regs: (g, 2t..2t+1) (g+8, 2t..) (g, 2t+8..) (g+8, 2t+8..);  B regs: (k = 2t..2t+1, n = g) (k = 2t+8.., n = g);
+//   C regs: (g, 2t) (g, 2t+1) (g+8, 2t) (g+8, 2t+1).
+template <int NT, bool USE_MMA>
+__device__ __forceinline__ void warp_gemm(float (&acc)[NT][4], const bf* __restrict__ A, int lda,
+                                          const bf* __restrict__ B, int ldb, int K, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  if constexpr (USE_MMA) {
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      const uint32_t a0 = *reinterpret_cast<const uint32_t*>(A + g * lda + k0 + 2 * t);
+      const uint32_t a1 = *reinterpret_cast<const uint32_t*>(A + (g + 8) * lda + k0 + 2 * t);
+      const uint32_t a2 = *reinterpret_cast<const uint32_t*>(A + g * lda + k0 + 2 * t + 8);
+      const uint32_t a3 = *reinterpret_cast<const uint32_t*>(A + (g + 8) * lda + k0 + 2 * t + 8);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(B + (nt * 8 + g) * ldb + k0 + 2 * t);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(B + (nt * 8 + g) * ldb + k0 + 2 * t + 8);
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+            : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+      }
+    }
+  } else {
+    for (int k = 0; k < K; ++k) {
+      const float x0 = __bfloat162float(A[g * lda + k]), x1 = __bfloat162float(A[(g + 8) * lda + k]);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const float y0 = __bfloat162float(B[(nt * 8 + 2 * t) * ldb + k]);
+        const float y1 = __bfloat162float(B[(nt * 8 + 2 * t + 1) * ldb + k]);
+        acc[nt][0] = fmaf(x0, y0, acc[nt][0]);
+        acc[nt][1] = fmaf(x0, y1, acc[nt][1]);
+        acc[nt][2] = fmaf(x1, y0, acc[nt][2]);
+        acc[nt][3] = fmaf(x1, y1, acc[nt][3]);
+      }
+    }
+  }
+}
+
+// Rows [row0, row0 + 64) of one head of a row-major bf16 matrix -> shared memory, as they are ([64][DH + 8]) and, when
+// dstT != nullptr, transposed ([DH][72]).  Rows >= row_end are zero.
+template <int DH>
+__device__ __forceinline__ void load_tile(const bf* __restrict__ src, int64_t ld, int64_t row0, int64_t row_end,
+                                          bf* __restrict__ dst, bf* __restrict__ dstT) {
+  constexpr int LDH = DH + 8, CH = DH / 8;
+  for (int idx = threadIdx.x; idx < AB_T * CH; idx += AB_THREADS) {
+    const int r = idx / CH, c = (idx - r * CH) * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row0 + r < row_end) v = __ldg(reinterpret_cast<const uint4*>(src + (row0 + r) * ld + c));
+    *reinterpret_cast<uint4*>(dst + r * LDH + c) = v;
+    if (dstT != nullptr) {
+      const bf* e = reinterpret_cast<const bf*>(&v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dstT[(c + k) * AB_LDT + r] = e[k];
+    }
+  }
+}
+
+struct AttnBwdParams {
+  const bf *q, *k, *v, *d_out;
+  int64_t ldq, ldk, ldv, lddo;
+  const float *lse, *dsum;        // [B, H, Tq]
+  const uint8_t* key_pad;         // [B, Tk] or null
+  bf *dq, *dk, *dv;
+  int64_t lddq, lddk, lddv;
+  int H, Tq, Tk;
+  float scale;
+};
+
+// dsum[b, h, t] = sum_c dO[b*Tq + t, h*dh + c] * O[b*Tq + t, h*dh + c]: one warp per (row, head)
+__global__ void __launch_bounds__(256)
+attn_bwd_dsum_kernel(const bf* __restrict__ d_out, int64_t lddo, const bf* __restrict__ out, int64_t ldo,
+                     float* __restrict__ dsum, int64_t rows, int H, int Tq, int dh) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t item = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); item < rows * H;
+       item += warps) {
+    const int64_t row = item / H;
+    const int h = static_cast<int>(item - row * H);
+    float acc = 0.0f;
+    for (int c = lane * 2; c < dh; c += 64) {
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d_out + row * lddo + h * dh + c));
+      const float2 o = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(out + row * ldo + h * dh + c));
+      acc = fmaf(a.x, o.x, fmaf(a.y, o.y, acc));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const int64_t b = row / Tq;
+      dsum[(b * H + h) * Tq + (row - b * Tq)] = acc;
+    }
+  }
+}
+
+// S and dP of one 64 x 64 tile pair, then P and dS of this thread's 16 elements.  Returns them in p[][] / ds[][].
+template <int DH, bool USE_MMA>
+__device__ __forceinline__ void tile_p_ds(const bf* sQ, const bf* sdO, const bf* sK, const bf* sV, const float* s_lse,
+                                          const float* s_dsum, const float* s_kvalid, float scale, int wm, int wn, int lane,
+                                          float (&p)[4][4], float (&ds)[4][4]) {
+  constexpr int LDH = DH + 8;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { p[nt][e] = 0.0f; ds[nt][e] = 0.0f; }
+  warp_gemm<4, USE_MMA>(p, sQ + wm * 16 * LDH, LDH, sK + wn * 32 * LDH, LDH, DH, lane);     // S = Q K^T
+  warp_gemm<4, USE_MMA>(ds, sdO + wm * 16 * LDH, LDH, sV + wn * 32 * LDH, LDH, DH, lane);   // dP = dO V^T
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int q = wm * 16 + g + (e >> 1) * 8;
+      const int k = wn * 32 + nt * 8 + 2 * t + (e & 1);
+      // rows past Tq carry lse = +inf (=> P = 0), PAD / out-of-range keys are switched off by s_kvalid
+      const float pv = s_kvalid[k] != 0.0f ? __expf(p[nt][e] * scale - s_lse[q]) : 0.0f;
+      p[nt][e] = pv;
+      ds[nt][e] = pv * (ds[nt][e] - s_dsum[q]) * scale;
+    }
+}
+
+template <int DH>
+struct AttnBwdSmem {
+  static constexpr int LDH = DH + 8;
+  static constexpr int TILE = AB_T * LDH;        // elements of a [64][DH + 8] tile
+  static constexpr int TILE_T = DH * AB_LDT;     // elements of a transposed [DH][72] tile
+  static constexpr int SQ_T = AB_T * AB_LDT;     // elements of a [64][72] tile
+  // dkv pass: K, V, Q, dO, Q^T, dO^T, P^T, dS^T ; dq pass: Q, dO, K, V, K^T, dS
+  static constexpr size_t DKV_BYTES = (4 * TILE + 2 * TILE_T + 2 * SQ_T) * sizeof(bf) + 3 * AB_T * sizeof(float);
+  static constexpr size_t DQ_BYTES = (4 * TILE + TILE_T + SQ_T) * sizeof(bf) + 3 * AB_T * sizeof(float);
+};
+
+// ---- pass 1: dK, dV of one 64-key tile of one (utterance, head)
+template <int DH, bool USE_MMA>
+__global__ void __launch_bounds__(AB_THREADS)
+attn_bwd_dkv_kernel(const AttnBwdParams p) {
+  using SM = AttnBwdSmem<DH>;
+  constexpr int NT = DH / 16;   // 8-column tiles per warp over half the head dim
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf* sK = reinterpret_cast<bf*>(smem_raw);
+  bf* sV = sK + SM::TILE;
+  bf* sQ = sV + SM::TILE;
+  bf* sdO = sQ + SM::TILE;
+  bf* sQT = sdO + SM::TILE;
+  bf* sdOT = sQT + SM::TILE_T;
+  bf* sPT = sdOT + SM::TILE_T;
+  bf* sdST = sPT + SM::SQ_T;
+  float* s_lse = reinterpret_cast<float*>(sdST + SM::SQ_T);
+  float* s_dsum = s_lse + AB_T;
+  float* s_kvalid = s_dsum + AB_T;
+
+  const int k0 = blockIdx.x * AB_T, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp & 3, wn = warp >> 2;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t krow0 = static_cast<int64_t>(b) * p.Tk, qrow0 = static_cast<int64_t>(b) * p.Tq;
+
+  load_tile<DH>(p.k + h * DH, p.ldk, krow0 + k0, krow0 + p.Tk, sK, nullptr);
+  load_tile<DH>(p.v + h * DH, p.ldv, krow0 + k0, krow0 + p.Tk, sV, nullptr);
+  if (threadIdx.x < AB_T) {
+    const int k = k0 + threadIdx.x;
+    s_kvalid[threadIdx.x] = (k < p.Tk && (p.key_pad == nullptr || p.key_pad[krow0 + k] == 0)) ? 1.0f : 0.0f;
+  }
+  float dk_acc[NT][4], dv_acc[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { dk_acc[nt][e] = 0.0f; dv_acc[nt][e] = 0.0f; }
+
+  const float* lse = p.lse + (static_cast<int64_t>(b) * p.H + h) * p.Tq;
+  const float* dsum = p.dsum + (static_cast<int64_t>(b) * p.H + h) * p.Tq;
+  for (int q0 = 0; q0 < p.Tq; q0 += AB_T) {
+    __syncthreads();   // the previous tile pair's shared-memory reads are done
+    load_tile<DH>(p.q + h * DH, p.ldq, qrow0 + q0, qrow0 + p.Tq, sQ, sQT);
+    load_tile<DH>(p.d_out + h * DH, p.lddo, qrow0 + q0, qrow0 + p.Tq, sdO, sdOT);
+    if (threadIdx.x < AB_T) {
+      const int q = q0 + threadIdx.x;
+      s_lse[threadIdx.x] = q < p.Tq ? lse[q] : INFINITY;
+      s_dsum[threadIdx.x] = q < p.Tq ? dsum[q] : 0.0f;
+    }
+    __syncthreads();
+    float pr[4][4], ds[4][4];
+    tile_p_ds<DH, USE_MMA>(sQ, sdO, sK, sV, s_lse, s_dsum, s_kvalid, p.scale, wm, wn, lane, pr, ds);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int q = wm * 16 + g + (e >> 1) * 8;
+        const int k = wn * 32 + nt * 8 + 2 * t + (e & 1);
+        sPT[k * AB_LDT + q] = __float2bfloat16_rn(pr[nt][e]);
+        sdST[k * AB_LDT + q] = __float2bfloat16_rn(ds[nt][e]);
+      }
+    __syncthreads();
+    // dV += P^T dO (rows = keys, contraction over the 64 queries), dK += dS^T Q
+    warp_gemm<NT, USE_MMA>(dv_acc, sPT + wm * 16 * AB_LDT, AB_LDT, sdOT + wn * (DH / 2) * AB_LDT, AB_LDT, AB_T, lane);
+    warp_gemm<NT, USE_MMA>(dk_acc, sdST + wm * 16 * AB_LDT, AB_LDT, sQT + wn * (DH / 2) * AB_LDT, AB_LDT, AB_T, lane);
+  }
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int k = k0 + wm * 16 + g + half * 8;
+      if (k < p.Tk) {
+        const int c = h * DH + wn * (DH / 2) + nt * 8 + 2 * t;
+        *reinterpret_cast<__nv_bfloat162*>(p.dk + (krow0 + k) * p.lddk + c) =
+            __floats2bfloat162_rn(dk_acc[nt][half * 2], dk_acc[nt][half * 2 + 1]);
+        *reinterpret_cast<__nv_bfloat162*>(p.dv + (krow0 + k) * p.lddv + c) =
+            __floats2bfloat162_rn(dv_acc[nt][half * 2], dv_acc[nt][half * 2 + 1]);
+      }
+    }
+}
+
+// ---- pass 2: dQ of one 64-query tile of one (utterance, head)
+template <int DH, bool USE_MMA>
+__global__ void __launch_bounds__(AB_THREADS)
+attn_bwd_dq_kernel(const AttnBwdParams p) {
+  using SM = AttnBwdSmem<DH>;
+  constexpr int NT = DH / 16;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf* sQ = reinterpret_cast<bf*>(smem_raw);
+  bf* sdO = sQ + SM::TILE;
+  bf* sK = sdO + SM::TILE;
+  bf* sV = sK + SM::TILE;
+  bf* sKT = sV + SM::TILE;
+  bf* sdS = sKT + SM::TILE_T;
+  float* s_lse = reinterpret_cast<float*>(sdS + SM::SQ_T);
+  float* s_dsum = s_lse + AB_T;
+  float* s_kvalid = s_dsum + AB_T;
+
+  const int q0 = blockIdx.x * AB_T, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp & 3, wn = warp >> 2;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t krow0 = static_cast<int64_t>(b) * p.Tk, qrow0 = static_cast<int64_t>(b) * p.Tq;
+
+  load_tile<DH>(p.q + h * DH, p.ldq, qrow0 + q0, qrow0 + p.Tq, sQ, nullptr);
+  load_tile<DH>(p.d_out + h * DH, p.lddo, qrow0 + q0, qrow0 + p.Tq, sdO, nullptr);
+  if (threadIdx.x < AB_T) {
+    const int q = q0 + threadIdx.x;
+    const int64_t o = (static_cast<int64_t>(b) * p.H + h) * p.Tq + q;
+    s_lse[threadIdx.x] = q < p.Tq ? p.lse[o] : INFINITY;
+    s_dsum[threadIdx.x] = q < p.Tq ? p.dsum[o] : 0.0f;
+  }
+  float dq_acc[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dq_acc[nt][e] = 0.0f;
+
+  for (int k0 = 0; k0 < p.Tk; k0 += AB_T) {
+    __syncthreads();
+    load_tile<DH>(p.k + h * DH, p.ldk, krow0 + k0, krow0 + p.Tk, sK, sKT);
+    load_tile<DH>(p.v + h * DH, p.ldv, krow0 + k0, krow0 + p.Tk, sV, nullptr);
+    if (threadIdx.x < AB_T) {
+      const int k = k0 + threadIdx.x;
+      s_kvalid[threadIdx.x] = (k < p.Tk && (p.key_pad == nullptr || p.key_pad[krow0 + k] == 0)) ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+    float pr[4][4], ds[4][4];
+    tile_p_ds<DH, USE_MMA>(sQ, sdO, sK, sV, s_lse, s_dsum, s_kvalid, p.scale, wm, wn, lane, pr, ds);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int q = wm * 16 + g + half * 8;
+        const int k = wn * 32 + nt * 8 + 2 * t;
+        *reinterpret_cast<__nv_bfloat162*>(sdS + q * AB_LDT + k) = __floats2bfloat162_rn(ds[nt][half * 2], ds[nt][half * 2 + 1]);
+      }
+    __syncthreads();
+    // dQ += dS K (rows = queries, contraction over the 64 keys)
+    warp_gemm<NT, USE_MMA>(dq_acc, sdS + wm * 16 * AB_LDT, AB_LDT, sKT + wn * (DH / 2) * AB_LDT, AB_LDT, AB_T, lane);
+  }
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int q = q0 + wm * 16 + g + half * 8;
+      if (q < p.Tq) {
+        const int c = h * DH + wn * (DH / 2) + nt * 8 + 2 * t;
+        *reinterpret_cast<__nv_bfloat162*>(p.dq + (qrow0 + q) * p.lddq + c) =
+            __floats2bfloat162_rn(dq_acc[nt][half * 2], dq_acc[nt][half * 2 + 1]);
+      }
+    }
+}
+
+template <int DH, bool USE_MMA>
+static int launch_attn_bwd(const AttnBwdParams& p, int B, cudaStream_t s) {
+  using SM = AttnBwdSmem<DH>;
+  static uint64_t attr_done = 0;
+  if (device_needs_attr(&attr_done)) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<DH, USE_MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(SM::DKV_BYTES));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_dq_kernel<DH, USE_MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(SM::DQ_BYTES));
+    if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "attention_backward: %s", cudaGetErrorString(e));
+  }
+  attn_bwd_dkv_kernel<DH, USE_MMA><<<dim3((p.Tk + AB_T - 1) / AB_T, p.H, B), AB_THREADS, SM::DKV_BYTES, s>>>(p);
+  int rc = check_launch("attention_backward (dK, dV)");
+  if (rc) return rc;
+  attn_bwd_dq_kernel<DH, USE_MMA><<<dim3((p.Tq + AB_T - 1) / AB_T, p.H, B), AB_THREADS, SM::DQ_BYTES, s>>>(p);
+  return check_launch("attention_backward (dQ)");
+}
+
+}  // namespace hriemo
+
+using namespace hriemo;
+
+extern "C" int hriemo_attention_backward_bf16(const hriemo_attn_bwd_args* a, void* stream) {
+  HRIEMO_REQUIRE(a != nullptr, "attention_backward: null args");
+  HRIEMO_REQUIRE(a->q && a->k && a->v && a->out && a->d_out && a->lse && a->dsum && a->dq && a->dk && a->dv,
+                 "attention_backward: null pointer");
+  HRIEMO_REQUIRE(a->B > 0 && a->B <= 65535 && a->H > 0 && a->H <= 65535 && a->Tq > 0 && a->Tk > 0,
+                 "attention_backward: bad shape B=%d H=%d Tq=%d Tk=%d", a->B, a->H, a->Tq, a->Tk);
+  HRIEMO_REQUIRE(a->dh == 32 || a->dh == 64 || a->dh == 96 || a->dh == 128, "attention_backward: dh=%d not in {32, 64, 96, 128}",
+                 a->dh);
+  const int64_t lds[] = {a->ldq, a->ldk, a->ldv, a->ldo, a->lddo, a->lddq, a->lddk, a->lddv};
+  for (int64_t ld : lds) HRIEMO_REQUIRE(ld % 8 == 0 && ld >= static_cast<int64_t>(a->H) * a->dh, "attention_backward: bad leading dimension");
+  const void* ptrs[] = {a->q, a->k, a->v, a->out, a->d_out, a->dq, a->dk, a->dv};
+  for (const void* ptr : ptrs)
+    HRIEMO_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, "attention_backward: operands must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t rows = static_cast<int64_t>(a->B) * a->Tq;
+  int64_t gb = (rows * a->H + 7) / 8;
+  const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
+  if (gb > cap) gb = cap;
+  attn_bwd_dsum_kernel<<<static_cast<unsigned>(gb), 256, 0, s>>>(static_cast<const bf*>(a->d_out), a->lddo,
+                                                               static_cast<const bf*>(a->out), a->ldo, a->dsum, rows, a->H,
+                                                               a->Tq, a->dh);
+  int rc = check_launch("attention_backward (D)");
+  if (rc) return rc;
+  AttnBwdParams p;
+  p.q = static_cast<const bf*>(a->q); p.k = static_cast<const bf*>(a->k); p.v = static_cast<const bf*>(a->v);
+  p.d_out = static_cast<const bf*>(a->d_out);
+  p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv; p.lddo = a->lddo;
+  p.lse = a->lse; p.dsum = a->dsum; p.key_pad = a->key_pad;
+  p.dq = static_cast<bf*>(a->dq); p.dk = static_cast<bf*>(a->dk); p.dv = static_cast<bf*>(a->dv);
+  p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
+  p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk; p.scale = a->scale;
+#define HRIEMO_AB_DISPATCH(DHV)                                                         \
+  case DHV:                                                                             \
+    return a->use_fma ? launch_attn_bwd<DHV, false>(p, a->B, s) : launch_attn_bwd<DHV, true>(p, a->B, s)
+  switch (a->dh) {
+    HRIEMO_AB_DISPATCH(32);
+    HRIEMO_AB_DISPATCH(64);
+    HRIEMO_AB_DISPATCH(96);
+    default:
+      HRIEMO_AB_DISPATCH(128);
+  }
+#undef HRIEMO_AB_DISPATCH
+}

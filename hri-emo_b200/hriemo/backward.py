@@ -165,6 +165,143 @@ def decoder_backward(dec, tape: dict, d_logits: torch.Tensor):
 
 
 # --------------------------------------------------------------------------- #
+# cross-modal encoder
+# --------------------------------------------------------------------------- #
+def _ffn_forward(x: torch.Tensor, P1: dict, P2: dict, ln, tape: dict, key: str) -> torch.Tensor:
+    """LN(x + W2 relu(W1 x + b1) + b2) on a materialised bf16 stream (cross_modal_block_tacfn.py:106 / :119)."""
+    h = ops.gemm(x, P1["w"], P1["b"], L.EPI_BIAS_RELU, tag="ffn")
+    pre = ops.gemm(h, P2["w"], P2["b"], L.EPI_BIAS_RESID, resid=x, tag="ffn")
+    y, _ = ops.layernorm(pre, *ln)
+    tape[key] = dict(x=x, h=h, pre=pre)
+    return y
+
+
+def _ffn_backward(dy: torch.Tensor, P1: dict, P2: dict, ln, tp: dict, G: Grads, name: str, norm: str) -> torch.Tensor:
+    d_pre, G[f"{norm}.weight"], G[f"{norm}.bias"] = ops.layernorm_backward(tp["pre"], dy, ln[0])
+    d_hpost, G[f"{name}.2.weight"], G[f"{name}.2.bias"] = ops.linear_backward(d_pre, tp["h"], _t(P2["w"]))
+    d_h = ops.relu_backward(d_hpost, tp["h"])
+    G[f"{name}.0.weight"], G[f"{name}.0.bias"] = ops.linear_wgrad(d_h, tp["x"])
+    return ops.gemm(d_h, _t(P1["w"]), None, L.EPI_BIAS_RESID, resid=d_pre, tag="dgrad")
+
+
+def encoder_layer_forward_train(block, a: E.Seq, t: E.Seq, mask_a, mask_t):
+    """CrossModalBlock forward (cross_modal_block_tacfn.py:62-125) on materialised streams: every LayerNorm is
+    applied by the stand-alone kernel and every sub-layer keeps its input, its pre-LayerNorm sum, the attention
+    output with its log-sum-exp and the FFN hidden.  -> (a_out, t_out, tape)."""
+    P = block._prep.get()
+    H = block.n_heads
+    a, t = E.materialize(a), E.materialize(t)
+    d = a.d
+    dh = d // H
+    B, Ta, Tt = a.B, a.T, t.T
+    tape: dict = dict(B=B, Ta=Ta, Tt=Tt, mask_a=mask_a, mask_t=mask_t)
+
+    def self_block(x, Pm, ln, mask, T, key):                                                  # :74-82 / :85-93
+        qkv = ops.gemm(x, Pm["w_qkv"], Pm["b_qkv"], L.EPI_BIAS, tag="attn_proj")
+        o, lse = ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], mask, B, H, T, T, dh, want_lse=True)
+        pre = ops.gemm(o, Pm["w_o"], Pm["b_o"], L.EPI_BIAS_RESID, resid=x, tag="attn_proj")
+        y, _ = ops.layernorm(pre, *ln)
+        tape[key] = dict(x=x, qkv=qkv, o=o, lse=lse, pre=pre)
+        return y
+
+    a_s = self_block(a.x, P["self_a"], P["self_norm_a"], mask_a, Ta, "self_a")
+    t_s = self_block(t.x, P["self_t"], P["self_norm_t"], mask_t, Tt, "self_t")
+    # one packed projection per stream: its cross-attention query and the key / value it offers the other stream
+    qkv_a = ops.gemm(a_s, P["cross_a"]["w_qkv"], P["cross_a"]["b_qkv"], L.EPI_BIAS, tag="attn_proj")
+    qkv_t = ops.gemm(t_s, P["cross_t"]["w_qkv"], P["cross_t"]["b_qkv"], L.EPI_BIAS, tag="attn_proj")
+    tape.update(a_s=a_s, t_s=t_s, qkv_a=qkv_a, qkv_t=qkv_t)
+
+    def cross_block(x, q, k, v, mask_kv, Tq, Tk, Po, ln, key):                                # :98-105 / :111-118
+        o, lse = ops.attention(q, k, v, mask_kv, B, H, Tq, Tk, dh, want_lse=True)
+        pre = ops.gemm(o, Po["w"], Po["b"], L.EPI_BIAS_RESID, resid=x, tag="attn_proj")
+        y, _ = ops.layernorm(pre, *ln)
+        tape[key] = dict(o=o, lse=lse, pre=pre)
+        return y
+
+    a1 = cross_block(a_s, qkv_a[:, :d], qkv_t[:, d:2 * d], qkv_t[:, 2 * d:], mask_t, Ta, Tt, P["a2t_o"], P["norm_a1"], "a2t")
+    a_o = _ffn_forward(a1, P["ffn_a1"], P["ffn_a2"], P["norm_a2"], tape, "ffn_a")             # :106
+    t1 = cross_block(t_s, qkv_t[:, :d], qkv_a[:, d:2 * d], qkv_a[:, 2 * d:], mask_a, Tt, Ta, P["t2a_o"], P["norm_t1"], "t2a")
+    t_o = _ffn_forward(t1, P["ffn_t1"], P["ffn_t2"], P["norm_t2"], tape, "ffn_t")             # :119
+    return E.Seq(a_o, B, Ta), E.Seq(t_o, B, Tt), tape
+
+
+def encoder_layer_backward(block, tape: dict, d_a: torch.Tensor, d_t: torch.Tensor, need_dx: bool = True):
+    """Reverse of encoder_layer_forward_train.  d_a [B*T_a, d], d_t [B*T_t, d]: bf16 gradients of the layer's outputs.
+    -> (d_a_in | None, d_t_in | None, grads under the names of CrossModalBlock's parameters).  need_dx=False skips the
+    gradient of the layer's inputs (the first layer reads frozen features)."""
+    P = block._prep.get()
+    H = block.n_heads
+    B, Ta, Tt = tape["B"], tape["Ta"], tape["Tt"]
+    mask_a, mask_t = tape["mask_a"], tape["mask_t"]
+    d = d_a.shape[1]
+    dh = d // H
+    dev = d_a.device
+    G: Grads = {}
+    qkv_a, qkv_t = tape["qkv_a"], tape["qkv_t"]
+    dqkv_a = torch.empty((B * Ta, 3 * d), dtype=bf16, device=dev)
+    dqkv_t = torch.empty((B * Tt, 3 * d), dtype=bf16, device=dev)
+    # ---- audio: FFN (:106), then a_s + MHA_a2t(a_s, t_s, t_s) (:98-105)
+    d_a1 = _ffn_backward(d_a, P["ffn_a1"], P["ffn_a2"], P["norm_a2"], tape["ffn_a"], G, "ffn_a", "norm_a2")
+    tp = tape["a2t"]
+    d_pre_a1, G["norm_a1.weight"], G["norm_a1.bias"] = ops.layernorm_backward(tp["pre"], d_a1, P["norm_a1"][0])
+    d_o, G["attn_a2t.out_proj.weight"], G["attn_a2t.out_proj.bias"] = ops.linear_backward(d_pre_a1, tp["o"], _t(P["a2t_o"]["w"]))
+    ops.attention_backward(qkv_a[:, :d], qkv_t[:, d:2 * d], qkv_t[:, 2 * d:], tp["o"], d_o, tp["lse"], mask_t, B, H, Ta, Tt, dh,
+                           grads=(dqkv_a[:, :d], dqkv_t[:, d:2 * d], dqkv_t[:, 2 * d:]))
+    # ---- text: FFN (:119), then t_s + MHA_t2a(t_s, a_s, a_s) (:111-118)
+    d_t1 = _ffn_backward(d_t, P["ffn_t1"], P["ffn_t2"], P["norm_t2"], tape["ffn_t"], G, "ffn_t", "norm_t2")
+    tp = tape["t2a"]
+    d_pre_t1, G["norm_t1.weight"], G["norm_t1.bias"] = ops.layernorm_backward(tp["pre"], d_t1, P["norm_t1"][0])
+    d_o, G["attn_t2a.out_proj.weight"], G["attn_t2a.out_proj.bias"] = ops.linear_backward(d_pre_t1, tp["o"], _t(P["t2a_o"]["w"]))
+    ops.attention_backward(qkv_t[:, :d], qkv_a[:, d:2 * d], qkv_a[:, 2 * d:], tp["o"], d_o, tp["lse"], mask_a, B, H, Tt, Ta, dh,
+                           grads=(dqkv_t[:, :d], dqkv_a[:, d:2 * d], dqkv_a[:, 2 * d:]))
+    # ---- the packed projections: rows [Wq(a2t); Wk(t2a); Wv(t2a)] read a_s, rows [Wq(t2a); Wk(a2t); Wv(a2t)] read t_s
+    for n in ("attn_a2t", "attn_t2a"):
+        G[f"{n}.in_proj_weight"] = torch.empty((3 * d, d), dtype=f32, device=dev)
+        G[f"{n}.in_proj_bias"] = torch.empty((3 * d,), dtype=f32, device=dev)
+    ops.linear_wgrad(dqkv_a[:, :d], tape["a_s"], dw=G["attn_a2t.in_proj_weight"][:d], db=G["attn_a2t.in_proj_bias"][:d])
+    ops.linear_wgrad(dqkv_a[:, d:], tape["a_s"], dw=G["attn_t2a.in_proj_weight"][d:], db=G["attn_t2a.in_proj_bias"][d:])
+    ops.linear_wgrad(dqkv_t[:, :d], tape["t_s"], dw=G["attn_t2a.in_proj_weight"][:d], db=G["attn_t2a.in_proj_bias"][:d])
+    ops.linear_wgrad(dqkv_t[:, d:], tape["t_s"], dw=G["attn_a2t.in_proj_weight"][d:], db=G["attn_a2t.in_proj_bias"][d:])
+    d_a_s = ops.gemm(dqkv_a, _t(P["cross_a"]["w_qkv"]), None, L.EPI_BIAS_RESID, resid=d_pre_a1, tag="dgrad")
+    d_t_s = ops.gemm(dqkv_t, _t(P["cross_t"]["w_qkv"]), None, L.EPI_BIAS_RESID, resid=d_pre_t1, tag="dgrad")
+
+    def self_backward(dy, Pm, ln, mask, T, tp, name, norm, buf):                               # :74-82 / :85-93
+        d_pre, G[f"{norm}.weight"], G[f"{norm}.bias"] = ops.layernorm_backward(tp["pre"], dy, ln[0])
+        d_o, G[f"{name}.out_proj.weight"], G[f"{name}.out_proj.bias"] = ops.linear_backward(d_pre, tp["o"], _t(Pm["w_o"]))
+        qkv = tp["qkv"]
+        ops.attention_backward(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], tp["o"], d_o, tp["lse"], mask, B, H, T, T, dh,
+                               grads=(buf[:, :d], buf[:, d:2 * d], buf[:, 2 * d:]))
+        G[f"{name}.in_proj_weight"], G[f"{name}.in_proj_bias"] = ops.linear_wgrad(buf, tp["x"])
+        if not need_dx:
+            return None
+        return ops.gemm(buf, _t(Pm["w_qkv"]), None, L.EPI_BIAS_RESID, resid=d_pre, tag="dgrad")
+
+    # the packed cross-projection gradients are consumed: their buffers are reused for the self-attention ones
+    d_a_in = self_backward(d_a_s, P["self_a"], P["self_norm_a"], mask_a, Ta, tape["self_a"], "self_attn_a", "self_norm_a", dqkv_a)
+    d_t_in = self_backward(d_t_s, P["self_t"], P["self_norm_t"], mask_t, Tt, tape["self_t"], "self_attn_t", "self_norm_t", dqkv_t)
+    return d_a_in, d_t_in, G
+
+
+def encoder_forward_train(enc, a: E.Seq, t: E.Seq, mask_a, mask_t):
+    """CrossModalTransformer forward (cross_modal_block_tacfn.py:145-166) with one tape per layer."""
+    tapes = []
+    for block in enc.layers:
+        a, t, tape = encoder_layer_forward_train(block, a, t, mask_a, mask_t)
+        tapes.append(tape)
+    return a, t, tapes
+
+
+def encoder_backward(enc, tapes: list, d_a: torch.Tensor, d_t: torch.Tensor, need_dx: bool = False):
+    """-> (d_a_in | None, d_t_in | None, grads under the names of CrossModalTransformer's parameters)."""
+    G: Grads = {}
+    for i in range(len(enc.layers) - 1, -1, -1):
+        d_a, d_t, g = encoder_layer_backward(enc.layers[i], tapes[i], d_a, d_t, need_dx=need_dx or i > 0)
+        for k, v in g.items():
+            G[f"layers.{i}.{k}"] = v
+    return d_a, d_t, G
+
+
+# --------------------------------------------------------------------------- #
 # loss -> encoder outputs
 # --------------------------------------------------------------------------- #
 def decode_loss_and_backward(model, a: E.Seq, t: E.Seq, mask_a, mask_t, labels: torch.Tensor,
@@ -183,3 +320,20 @@ def decode_loss_and_backward(model, a: E.Seq, t: E.Seq, mask_a, mask_t, labels: 
     grads: Grads = {f"beta_gate.{k}": v for k, v in g_gate.items()}
     grads.update({f"emotion_decoder.{k}": v for k, v in g_dec.items()})
     return dict(loss=loss, logits=logits, beta=beta, z=z, grads=grads, d_a=d_a, d_t=d_t)
+
+
+def loss_and_gradients(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a, mask_t, labels: torch.Tensor,
+                       beta_weight: float = 0.01) -> dict:
+    """Forward and backward of one training iteration of FusionWithEmotionDecoder
+    (scripts/fusion/train_fusion_seq_level_decoder.py:311-332: model(...), BCE + beta regulariser, loss.backward()).
+    h_a [B, T_a, d], h_t [B, T_t, d] fp32 / bf16 CUDA features, masks bool True = PAD, labels [B, N_e].
+    -> dict(loss, logits, beta, z, grads): grads holds one fp32 tensor per parameter of the model, under the
+    reference's parameter names."""
+    a, t = E.to_seq(h_a, "h_a"), E.to_seq(h_t, "h_t")
+    mask_a = E.check_mask(mask_a, a.B, a.T, "mask_a")
+    mask_t = E.check_mask(mask_t, t.B, t.T, "mask_t")
+    a_enc, t_enc, enc_tapes = encoder_forward_train(model.cross_modal, a, t, mask_a, mask_t)
+    out = decode_loss_and_backward(model, a_enc, t_enc, mask_a, mask_t, labels, beta_weight)
+    _, _, g_enc = encoder_backward(model.cross_modal, enc_tapes, out.pop("d_a"), out.pop("d_t"))
+    out["grads"].update({f"cross_modal.{k}": v for k, v in g_enc.items()})
+    return out

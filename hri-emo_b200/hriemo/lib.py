@@ -50,6 +50,24 @@ class AttnArgs(C.Structure):
     ]
 
 
+class AttnBwdArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_int64),
+        ("k", C.c_void_p), ("ldk", C.c_int64),
+        ("v", C.c_void_p), ("ldv", C.c_int64),
+        ("key_pad", C.c_void_p),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("d_out", C.c_void_p), ("lddo", C.c_int64),
+        ("lse", C.c_void_p), ("dsum", C.c_void_p),
+        ("dq", C.c_void_p), ("lddq", C.c_int64),
+        ("dk", C.c_void_p), ("lddk", C.c_int64),
+        ("dv", C.c_void_p), ("lddv", C.c_int64),
+        ("B", C.c_int32), ("H", C.c_int32), ("Tq", C.c_int32), ("Tk", C.c_int32), ("dh", C.c_int32),
+        ("scale", C.c_float),
+        ("use_fma", C.c_int32),
+    ]
+
+
 class ShardInfo(C.Structure):
     _fields_ = [("n_utt", C.c_int64), ("rows_a", C.c_int64), ("rows_t", C.c_int64), ("meta_bytes", C.c_int64),
                 ("d_a", C.c_int32), ("d_t", C.c_int32), ("dtype", C.c_int32),
@@ -110,6 +128,7 @@ SIGNATURES = {
     "hriemo_mask_inv_counts": (C.c_int, [_P, _I32, _I32, _P, _P]),
     "hriemo_gate_blend_backward_w": (C.c_int, [_P, _I64, _P, _I64, _I32, _P, _I64, _P, _P, _I32, _I32, _I32, _P]),
     "hriemo_gate_stream_grad": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P]),
+    "hriemo_attention_backward_bf16": (C.c_int, [C.POINTER(AttnBwdArgs), _P]),
     "hriemo_host_pack_bf16": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, _I64, _I64, _I32]),
 }
 

@@ -642,6 +642,48 @@ def small_attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, 
     return dq, dk, dv
 
 
+@_on_tensor_device
+def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor,
+                       lse: torch.Tensor, key_pad: Optional[torch.Tensor], B: int, H: int, Tq: int, Tk: int, dh: int,
+                       grads=None, use_fma: bool = False):
+    """Backward of `attention` (the encoder's attention): q / k / v as in the forward (column slices are fine), out
+    [B*Tq, H*dh] and lse [B, H, Tq] from attention(..., want_lse=True), d_out [B*Tq, H*dh].
+    -> (dq [B*Tq, H*dh], dk [B*Tk, H*dh], dv [B*Tk, H*dh]) bf16; grads = (dq, dk, dv): existing views to write into.
+    use_fma: the fp32-FMA form of the same tiles instead of mma.sync (slow; validation)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out"), (d_out, "d_out")):
+        _chk2d(t, bf16, f"attention_backward {n}")
+    d = H * dh
+    if q.shape[0] != B * Tq or k.shape[0] != B * Tk or v.shape[0] != B * Tk or tuple(out.shape) != (B * Tq, d) \
+            or tuple(d_out.shape) != (B * Tq, d):
+        raise _l.HriemoError("attention_backward: operand shapes do not match (B, H, Tq, Tk, dh)")
+    _chk_f32(lse, (B, H, Tq), "attention_backward lse")
+    if grads is None:
+        dq = torch.empty((B * Tq, d), dtype=bf16, device=q.device)
+        dk = torch.empty((B * Tk, d), dtype=bf16, device=q.device)
+        dv = torch.empty((B * Tk, d), dtype=bf16, device=q.device)
+    else:
+        dq, dk, dv = grads
+        for t, n, rows in ((dq, "dq", B * Tq), (dk, "dk", B * Tk), (dv, "dv", B * Tk)):
+            _chk2d(t, bf16, f"attention_backward {n}")
+            if tuple(t.shape) != (rows, d):
+                raise _l.HriemoError(f"attention_backward: {n} must be [{rows}, {d}], got {tuple(t.shape)}")
+    m = _mask_u8(key_pad, B, Tk, "attention_backward")
+    dsum = torch.empty((B, H, Tq), dtype=f32, device=q.device)
+    a = _l.AttnBwdArgs()
+    a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0)
+    a.key_pad = _ptr(m)
+    a.out, a.ldo, a.d_out, a.lddo = out.data_ptr(), out.stride(0), d_out.data_ptr(), d_out.stride(0)
+    a.lse, a.dsum = lse.data_ptr(), dsum.data_ptr()
+    a.dq, a.lddq, a.dk, a.lddk, a.dv, a.lddv = dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0)
+    a.B, a.H, a.Tq, a.Tk, a.dh = B, H, Tq, Tk, dh
+    a.scale = 1.0 / math.sqrt(dh)
+    a.use_fma = 1 if use_fma else 0
+    tok = _prof_begin("attention_bwd", 14.0 * B * H * Tq * Tk * dh)   # 7 tile GEMMs (S and dP are formed in both passes)
+    _l.check(_l.load().hriemo_attention_backward_bf16(C.byref(a), _stream()), "attention_backward_bf16")
+    _prof_end(tok)
+    return dq, dk, dv
+
+
 # ------------------------------------------------------------------ backward of the fp32 gate / head
 @_on_tensor_device
 def linear_backward_f32(dy: torch.Tensor, x: Optional[torch.Tensor], w: Optional[torch.Tensor], want_dx: bool = True,

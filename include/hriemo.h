@@ -380,6 +380,30 @@ int hriemo_gate_stream_grad(const void* dh, int64_t lddh, int32_t L, const float
                             const float* dpool, const uint8_t* pad, const float* inv_counts, void* dn, int64_t lddn,
                             int32_t B, int32_t T, int32_t d, void* stream);
 
+/* Backward of hriemo_attention_bf16 (the encoder's attention) for the training step: from the forward's operands, its
+ * output `out`, its log-sum-exp `lse` and the output gradient d_out, writes dq [B*Tq, H*dh], dk and dv [B*Tk, H*dh]
+ * (bf16; PAD keys receive zeros).  P is rebuilt as exp(scale * q.k - lse); dsum [B, H, Tq] (f32) is scratch that
+ * receives rowsum(d_out o out).  Deterministic (no atomics): one pass owns dK / dV per key tile, one owns dQ per query
+ * tile.  First correct version on warp-level mma.sync tensor-core instructions, not yet tcgen05;
+ * use_fma != 0 runs the same tiles with fp32 FMA loops instead (slow; the form the tests compare against). */
+typedef struct hriemo_attn_bwd_args {
+  const void* q;      int64_t ldq;    /* bf16, as in the forward */
+  const void* k;      int64_t ldk;
+  const void* v;      int64_t ldv;
+  const uint8_t* key_pad;             /* [B, Tk] 1 = PAD, or NULL */
+  const void* out;    int64_t ldo;    /* bf16 [B*Tq, H*dh]: the forward's output */
+  const void* d_out;  int64_t lddo;   /* bf16 [B*Tq, H*dh] */
+  const float* lse;                   /* f32 [B, H, Tq] from the forward */
+  float* dsum;                        /* f32 [B, H, Tq] scratch */
+  void* dq;           int64_t lddq;   /* bf16 outputs */
+  void* dk;           int64_t lddk;
+  void* dv;           int64_t lddv;
+  int32_t B, H, Tq, Tk, dh;           /* dh in {32, 64, 96, 128} */
+  float scale;
+  int32_t use_fma;
+} hriemo_attn_bwd_args;
+int hriemo_attention_backward_bf16(const hriemo_attn_bwd_args* args, void* stream);
+
 /* Mean over time (UNMASKED) of an f32 [B,L,d] tensor — models/fusion_classifier.py:145. */
 int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d, void* stream);
 

@@ -45,6 +45,12 @@ def gemm(a, w, bias, epilogue=EPI_BIAS, resid=None, out=None, cta_pair=0, a_ln=N
     return y if epilogue in (EPI_BIAS_RESID_F32, EPI_BIAS_F32) else y.to(LO)
 
 
+def fold_ln_weight(w, bias, gamma, beta, *args, **kwargs):
+    """Built by the modules' prepared-operand caches; the training schedule never reads the folded operands."""
+    wf = (w * gamma[None, :]).to(LO)
+    return wf, wf.to(HI).sum(1), (bias if bias is not None else 0) + w @ beta
+
+
 def sgemm(a, w, bias, act=ACT_NONE):
     assert a.dtype == HI and w.dtype == HI
     y = a @ w.t() + (bias if bias is not None else 0)
@@ -88,6 +94,32 @@ def small_attention_backward(q, k, v, d_out, key_pad, B, H, Nq, Tk, dh, out=None
         assert dst.dtype == LO and dst.shape == src.shape
         dst.copy_(src)
     return out
+
+
+def _attn(qr, kr, vr, key_pad, B, H, Tq, Tk, dh):
+    s = _heads(qr, B, Tq, H, dh) @ _heads(kr, B, Tk, H, dh).transpose(-1, -2) / math.sqrt(dh)
+    if key_pad is not None:
+        s = s.masked_fill(key_pad[:, None, None, :], float("-inf"))
+    return (torch.softmax(s, dim=-1) @ _heads(vr, B, Tk, H, dh)).transpose(1, 2).reshape(B * Tq, H * dh), s
+
+
+def attention(q, k, v, key_pad, B, H, Tq, Tk, dh, skip_padded_tiles=True, pair_heads=True, want_lse=False):
+    o, s = _attn(q, k, v, key_pad, B, H, Tq, Tk, dh)
+    return (o.to(LO), torch.logsumexp(s, dim=-1)) if want_lse else o.to(LO)
+
+
+def attention_backward(q, k, v, out, d_out, lse, key_pad, B, H, Tq, Tk, dh, grads=None, use_fma=False):
+    assert lse.shape == (B, H, Tq) and out.shape == d_out.shape == (B * Tq, H * dh)
+    qr, kr, vr = (t.to(HI).clone().requires_grad_(True) for t in (q, k, v))
+    o, _ = _attn(qr, kr, vr, key_pad, B, H, Tq, Tk, dh)
+    o.backward(d_out.to(HI))
+    res = (qr.grad.to(LO), kr.grad.to(LO), vr.grad.to(LO))
+    if grads is None:
+        return res
+    for dst, src in zip(grads, res):
+        assert dst.dtype == LO and dst.shape == src.shape
+        dst.copy_(src)
+    return grads
 
 
 def ln_masked_mean(x, gamma, beta, pad, B, T, apply_ln=True, eps=EPS, pre_ln=None):

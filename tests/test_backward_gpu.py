@@ -4,8 +4,12 @@ restated forward in float64 (oracle/hriemo_oracle.py, pinned to the reference by
 
 Tolerances: the fp32 kernels are compared element-wise (1e-5 relative to the tensor's scale: fp32 sums in another
 order); the composed backward carries bf16 activations and bf16 activation gradients through two decoder layers and
-the gate, so whole-tensor relative errors ||got - ref|| / ||ref|| are bounded by 5e-2 (measured values are written
-to gpurun_out/backward_errors.json when that directory exists)."""
+the gate, so whole-tensor relative errors ||got - ref|| / ||ref|| are bounded by 4e-2 (measured: <= 2.9e-2), and by
+1e-1 for linear1.weight / .bias (measured: <= 6.2e-2): a ReLU whose pre-activation changes sign under the bf16
+rounding of the forward costs a whole element of that gradient, so its error is sqrt(fraction of flipped units), not
+2^-9.  That this is noise and not logic is shown by tests/test_backward_schedule_cpu.py, where the same schedule
+reproduces autograd to 1e-9 in float64.  Measured values go to gpurun_out/backward_errors_d*.json when that
+directory exists (copied to profiles/r01_backward_errors.json)."""
 import json
 import os
 
@@ -131,6 +135,46 @@ def test_gate_blend_backward_kernels_match_autograd(B, T_a, L, d, masked):
     assert _rel(d_nt, ntr.grad.view(B * L, d)) <= 4e-3
 
 
+# ------------------------------------------------------------------ encoder attention backward
+@pytest.mark.parametrize("use_fma", [False, True])
+@pytest.mark.parametrize("B,H,Tq,Tk,dh,masked", [(3, 8, 100, 70, 96, True), (2, 4, 64, 64, 64, False), (2, 2, 37, 150, 32, True),
+                                                  (1, 2, 130, 20, 128, False), (2, 8, 300, 300, 96, True)])
+def test_attention_backward_matches_autograd(B, H, Tq, Tk, dh, masked, use_fma):
+    """dq, dk, dv of the encoder attention (packed [Q|K|V] column slices as operands, LSE and O from the forward kernel)
+    against torch autograd in float64 on the same bf16 operands.  P and dS are rounded to bf16 before the second GEMMs:
+    element-wise 2e-2 of the tensor's scale, whole-tensor relative error 1e-2."""
+    import math
+
+    from hriemo import ops
+
+    if use_fma and Tq * Tk > 20000:
+        pytest.skip("the FMA form is the slow reference: small shapes only")
+    d = H * dh
+    qkv_q = _rand((B * Tq, 3 * d), 551, dtype=torch.bfloat16)
+    qkv_k = _rand((B * Tk, 3 * d), 552, dtype=torch.bfloat16)
+    q, k, v = qkv_q[:, :d], qkv_k[:, d:2 * d], qkv_k[:, 2 * d:]
+    do = _rand((B * Tq, d), 553, dtype=torch.bfloat16)
+    pad = _ragged(B, Tk, 554) if masked else None
+    out, lse = ops.attention(q, k, v, pad, B, H, Tq, Tk, dh, want_lse=True)
+    dkv = torch.full((B * Tk, 2 * d), float("nan"), dtype=torch.bfloat16, device=DEV)
+    dq, dk, dv = ops.attention_backward(q, k, v, out, do, lse, pad, B, H, Tq, Tk, dh, use_fma=use_fma,
+                                        grads=(torch.empty((B * Tq, d), dtype=torch.bfloat16, device=DEV), dkv[:, :d], dkv[:, d:]))
+    torch.cuda.synchronize()
+    qr = q.double().reshape(B, Tq, d).requires_grad_(True)
+    kr = k.double().reshape(B, Tk, d).requires_grad_(True)
+    vr = v.double().reshape(B, Tk, d).requires_grad_(True)
+    s = (qr.view(B, Tq, H, dh).transpose(1, 2) @ kr.view(B, Tk, H, dh).transpose(1, 2).transpose(-1, -2)) / math.sqrt(dh)
+    if pad is not None:
+        s = s.masked_fill(pad[:, None, None, :], float("-inf"))
+    o = (torch.softmax(s, dim=-1) @ vr.view(B, Tk, H, dh).transpose(1, 2)).transpose(1, 2).reshape(B * Tq, d)
+    o.backward(do.double())
+    for name, got, ref in (("dq", dq, qr.grad.view(B * Tq, d)), ("dk", dk, kr.grad.view(B * Tk, d)),
+                           ("dv", dv, vr.grad.view(B * Tk, d))):
+        assert not torch.isnan(got.float()).any(), name
+        _close(got, ref, 2e-2)
+        assert _rel(got, ref) <= 1e-2, (name, _rel(got, ref))
+
+
 # ------------------------------------------------------------------ the composed backward
 def _oracle_backward(model, a, t, ma, mt, labels, n_heads, beta_weight=0.01):
     """Autograd over the oracle's float64 restatement of gate -> decoder -> loss on the CPU."""
@@ -186,5 +230,5 @@ def test_decode_loss_and_backward_matches_autograd(B, T_a, T_t, d, H, Ne, masked
     if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
         with open(os.path.join(ROOT, "gpurun_out", f"backward_errors_d{d}.json"), "w") as f:
             json.dump(errs, f, indent=1, sort_keys=True)
-    bad = {k: v for k, v in errs.items() if not v <= 5e-2}
-    assert not bad, f"relative errors above 5e-2: {bad}"
+    bad = {k: v for k, v in errs.items() if not v <= (1e-1 if ".linear1." in k else 4e-2)}
+    assert not bad, f"relative errors above 4e-2 (1e-1 for linear1): {bad}"

@@ -55,3 +55,53 @@ def test_decode_loss_and_backward_schedule(monkeypatch, B, T_a, T_t, d, H, Ne, m
         errs[k] = _rel(out["grads"][k], ref)
     bad = {k: v for k, v in errs.items() if not v <= tol}
     assert not bad, f"relative errors above {tol}: {bad}"
+
+
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("B,T_a,T_t,d,H,Ne,masked", [(4, 14, 9, 256, 4, 4, True), (3, 8, 8, 128, 2, 6, False)])
+def test_loss_and_gradients_schedule_whole_model(monkeypatch, B, T_a, T_t, d, H, Ne, masked, exact):
+    """Every one of the model's parameters (two encoder layers, gate, two decoder layers) against autograd over the
+    oracle's forward: 1e-9 in float64, the bf16 noise bound otherwise."""
+    import hriemo_oracle_train as OT
+
+    kernel_standins.install(monkeypatch, exact=exact)
+    from hriemo import backward
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    torch.manual_seed(11)
+    model = FusionWithEmotionDecoder(d_model=d, num_emotions=Ne, n_heads=H, num_layers_fusion=2, num_layers_decoder=2,
+                                     beta_hidden=64, dropout=0.0)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "norm" in n:
+                p.add_(0.1 * torch.randn_like(p))
+            if n.endswith("in_proj_bias") or n.endswith("out_proj.bias"):
+                p.add_(0.05 * torch.randn_like(p))
+    dt = torch.float64 if exact else torch.float32
+    if exact:
+        model = model.double()
+    g = torch.Generator().manual_seed(12)
+    h_a = torch.randn(B, T_a, d, generator=g).bfloat16().to(dt)
+    h_t = torch.randn(B, T_t, d, generator=g).bfloat16().to(dt)
+    ma = mt = None
+    if masked:
+        ma = torch.arange(T_a)[None, :] >= torch.randint(1, T_a + 1, (B,), generator=g)[:, None]
+        mt = torch.arange(T_t)[None, :] >= torch.randint(1, T_t + 1, (B,), generator=g)[:, None]
+    labels = (torch.rand(B, Ne, generator=g) < 0.4).to(dt)
+    if exact:   # to_seq casts fp32 features to bf16; in float64 mode hand the streams over as they are
+        monkeypatch.setattr(backward.E, "to_seq", lambda x, what, ld=None: backward.E.Seq(x.reshape(-1, x.shape[-1]), x.shape[0], x.shape[1]))
+    out = backward.loss_and_gradients(model, h_a, h_t, ma, mt, labels)
+
+    sd = {k: v.detach().double().requires_grad_(True) for k, v in model.state_dict().items()}
+    loss, _, _ = OT.train_loss(sd, h_a.double(), h_t.double(), ma, mt, labels.double(), n_heads=H)
+    loss.backward()
+    assert abs(out["loss"].item() - loss.item()) <= (1e-12 if exact else 5e-3)
+    assert set(out["grads"]) == set(sd), sorted(set(out["grads"]) ^ set(sd))
+    assert set(out["grads"]) == {n for n, _ in model.named_parameters()}
+    tol = 1e-9 if exact else 0.25
+    errs = {}
+    for k, p in sd.items():
+        assert tuple(out["grads"][k].shape) == tuple(p.shape), k
+        errs[k] = _rel(out["grads"][k], p.grad)
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, f"relative errors above {tol}: {bad}"
