@@ -238,6 +238,21 @@ def gate_stream_grad(dh, L, w, one_minus, dpool, pad, inv_counts, B, T):
     return dn.view(B * T, d).to(LO)
 
 
+def grad_norm_clip(grads, max_norm):
+    total = grads.norm()
+    return torch.stack([total, torch.clamp(max_norm / (total + 1e-6), max=1.0)])
+
+
+def adamw_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+               grad_scale=None, params_bf16=None):
+    g = grads * (grad_scale[0] if grad_scale is not None else 1.0)
+    params.mul_(1 - lr * weight_decay)
+    exp_avg.mul_(betas[0]).add_(g, alpha=1 - betas[0])
+    exp_avg_sq.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+    denom = exp_avg_sq.sqrt() / math.sqrt(1 - betas[1] ** step) + eps
+    params.addcdiv_(exp_avg, denom, value=-lr / (1 - betas[0] ** step))
+
+
 def install(monkeypatch, exact: bool = False):
     """Replace the kernel wrappers the backward schedule uses with the stand-ins above (pytest monkeypatch).
     exact: all tensors float64, no rounding anywhere (parameters must be float64 too)."""
@@ -257,3 +272,5 @@ def install(monkeypatch, exact: bool = False):
         monkeypatch.setattr(engine, "w16", lambda w, k_pad=None: w.detach().double().contiguous())
         monkeypatch.setattr(backward, "bf16", torch.float64)
         monkeypatch.setattr(backward, "f32", torch.float64)
+        from hriemo import train
+        monkeypatch.setattr(train, "f32", torch.float64)

@@ -232,3 +232,98 @@ def test_decode_loss_and_backward_matches_autograd(B, T_a, T_t, d, H, Ne, masked
             json.dump(errs, f, indent=1, sort_keys=True)
     bad = {k: v for k, v in errs.items() if not v <= (1e-1 if ".linear1." in k else 4e-2)}
     assert not bad, f"relative errors above 4e-2 (1e-1 for linear1): {bad}"
+
+
+# ------------------------------------------------------------------ the whole model and the training step
+def test_loss_and_gradients_whole_model_matches_autograd():
+    """All 119 parameter gradients of FusionWithEmotionDecoder (2 + 2 layers, d = 768, ragged masks) from
+    backward.loss_and_gradients against autograd over the oracle's float64 forward.  Bounds as above (4e-2; 1e-1 for
+    the first FFN / linear1 weights whose ReLU masks flip under bf16 rounding of the forward)."""
+    import hriemo_oracle_train as OT
+    from hriemo import backward
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    B, T_a, T_t, d, H, Ne = 8, 70, 24, 768, 8, 4
+    torch.manual_seed(561)
+    model = FusionWithEmotionDecoder(dropout=0.0).to(DEV)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "norm" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    h_a = _rand((B, T_a, d), 562, dtype=torch.bfloat16).float()
+    h_t = _rand((B, T_t, d), 563, dtype=torch.bfloat16).float()
+    ma, mt = _ragged(B, T_a, 564), _ragged(B, T_t, 565)
+    labels = torch.eye(Ne)[torch.randint(0, Ne, (B,), generator=torch.Generator().manual_seed(566))].to(DEV)
+    out = backward.loss_and_gradients(model, h_a, h_t, ma, mt, labels)
+    torch.cuda.synchronize()
+
+    sd = {k: v.detach().double().cpu().requires_grad_(True) for k, v in model.state_dict().items()}
+    loss, logits, beta = OT.train_loss(sd, h_a.double().cpu(), h_t.double().cpu(), ma.cpu(), mt.cpu(), labels.double().cpu(),
+                                       n_heads=H)
+    loss.backward()
+    assert abs(out["loss"].item() - loss.item()) <= 5e-3
+    assert (out["logits"].double().cpu() - logits.detach()).abs().max().item() <= 5e-2
+    assert set(out["grads"]) == set(sd)
+    errs = {k: _rel(out["grads"][k], p.grad) for k, p in sd.items()}
+    if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        with open(os.path.join(ROOT, "gpurun_out", "backward_errors_whole_model.json"), "w") as f:
+            json.dump(errs, f, indent=1, sort_keys=True)
+    bad = {k: v for k, v in errs.items() if not v <= (1e-1 if (".linear1." in k or ".ffn_a.0." in k or ".ffn_t.0." in k) else 4e-2)}
+    assert not bad, f"relative errors out of bounds: {bad}"
+
+
+def test_train_step_matches_two_reference_steps():
+    """hriemo.train.Trainer against the two consecutive optimizer steps of the UNMODIFIED reference held in
+    tests/golden/train_step_default.pt (d = 768, B = 4, T_a = 60, T_t = 20, AdamW lr 1e-4, clip 5.0).  bf16 bounds:
+    loss 5e-3, logits 3e-2, total gradient norm 3 %, every parameter's gradient norm 10 % (relative to
+    max(its norm, 1e-3 of the total)), the three gradients held in full 5e-2 whole-tensor relative; one AdamW step
+    moves every element by ~lr, so the updated parameters held in full agree to 2.5 lr and the update norms to 10 %."""
+    import golden_util as G
+    from hriemo.train import Trainer
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    fx = G.load("train_step_default")
+    torch.manual_seed(fx["model_seed"])
+    model = FusionWithEmotionDecoder(dropout=0.0, **fx["ctor"])
+    G.assert_same_weights(model, fx["weights"])
+    model = model.to(DEV)
+    d, n_e = fx["ctor"].get("d_model", 768), fx["ctor"].get("num_emotions", 4)
+    h_a, h_t, m_a, m_t = G.make_inputs(fx["in_seed"], fx["B"], fx["T_a"], fx["T_t"], d, d, True)
+    g = torch.Generator().manual_seed(fx["in_seed"] + 1)
+    labels = torch.eye(n_e)[torch.randint(0, n_e, (fx["B"],), generator=g)]
+    h_a, h_t, m_a, m_t, labels = (x.to(DEV) for x in (h_a, h_t, m_a, m_t, labels))
+    trainer = Trainer(model, lr=fx["lr"], weight_decay=fx["weight_decay"], max_norm=fx["max_norm"], distributed=False)
+    report = []
+    for want in fx["steps"]:
+        before = trainer.params.clone()
+        info = trainer.step(h_a, h_t, m_a, m_t, labels)
+        torch.cuda.synchronize()
+        assert abs(info["loss"].item() - want["loss"]) <= 5e-3
+        assert (info["logits"].cpu() - want["logits"]).abs().max().item() <= 3e-2
+        assert (info["beta"].cpu() - want["beta"]).abs().max().item() <= 2e-3
+        total = want["grad_norm"]
+        assert abs(info["grad_norm"].item() - total) <= 3e-2 * total
+        assert info["clip"].item() == pytest.approx(min(1.0, fx["max_norm"] / (total + 1e-6)), rel=3e-2)
+        worst_g = worst_u = 0.0
+        for k in fx["names"]:
+            o, n = trainer.slots[k]
+            got, ref = trainer.grads[o:o + n].double().norm().item(), want["grad_norms"][k]
+            worst_g = max(worst_g, abs(got - ref) / max(ref, 1e-3 * total))
+            got_u, ref_u = (trainer.params[o:o + n] - before[o:o + n]).double().norm().item(), want["update_norms"][k]
+            worst_u = max(worst_u, abs(got_u - ref_u) / max(ref_u, 1e-7))
+        report.append(dict(loss=info["loss"].item(), grad_norm=info["grad_norm"].item(), worst_grad_norm=worst_g,
+                           worst_update_norm=worst_u))
+        assert worst_g <= 0.1, worst_g
+        assert worst_u <= 0.1, worst_u
+        for k, ref in want["grads_full"].items():
+            assert _rel(trainer.gradient(k), ref) <= 5e-2, k
+        for k, ref in want["params_full"].items():
+            p = dict(model.named_parameters())[k]
+            assert (p.detach().cpu() - ref).abs().max().item() <= 2.5 * fx["lr"], k
+    if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        with open(os.path.join(ROOT, "gpurun_out", "train_step_report.json"), "w") as f:
+            json.dump(report, f, indent=1)
+    # the forward of the drop-in module sees the updated parameters (prepared operands were invalidated)
+    model.eval()
+    logits2, _, _ = model(h_a, h_t, m_a, m_t)
+    assert (logits2.cpu() - fx["steps"][1]["logits"]).abs().max().item() > 1e-4

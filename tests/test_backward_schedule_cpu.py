@@ -105,3 +105,37 @@ def test_loss_and_gradients_schedule_whole_model(monkeypatch, B, T_a, T_t, d, H,
         errs[k] = _rel(out["grads"][k], p.grad)
     bad = {k: v for k, v in errs.items() if not v <= tol}
     assert not bad, f"relative errors above {tol}: {bad}"
+
+
+def test_trainer_two_steps_match_the_training_oracle(monkeypatch):
+    """hriemo.train.Trainer (flat arenas, clip, AdamW, prepared-operand invalidation) over the float64 stand-ins
+    against two consecutive steps of oracle/hriemo_oracle_train.py (itself pinned to the reference's steps)."""
+    import hriemo_oracle_train as OT
+
+    kernel_standins.install(monkeypatch, exact=True)
+    from hriemo import backward
+    from hriemo.train import Trainer
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    B, T_a, T_t, d, H, Ne = 3, 10, 6, 128, 2, 4
+    torch.manual_seed(21)
+    model = FusionWithEmotionDecoder(d_model=d, num_emotions=Ne, n_heads=H, num_layers_fusion=1, num_layers_decoder=1,
+                                     beta_hidden=32, dropout=0.0).double()
+    g = torch.Generator().manual_seed(22)
+    h_a = torch.randn(B, T_a, d, generator=g, dtype=torch.float64)
+    h_t = torch.randn(B, T_t, d, generator=g, dtype=torch.float64)
+    labels = torch.eye(Ne, dtype=torch.float64)[torch.randint(0, Ne, (B,), generator=g)]
+    monkeypatch.setattr(backward.E, "to_seq", lambda x, what, ld=None: backward.E.Seq(x.reshape(-1, x.shape[-1]), x.shape[0], x.shape[1]))
+    sd = {k: p.detach().clone() for k, p in model.named_parameters()}
+    trainer = Trainer(model, lr=1e-3, max_norm=0.5, distributed=False)
+    assert all(p.data_ptr() >= trainer.params.data_ptr() for p in model.parameters())
+    opt = None
+    for _ in range(2):
+        info = trainer.step(h_a, h_t, None, None, labels)
+        sd, opt, want = OT.train_step(sd, opt, h_a, h_t, None, None, labels, n_heads=H, lr=1e-3, max_norm=0.5)
+        assert abs(info["loss"].item() - want["loss"]) <= 1e-12
+        assert abs(info["grad_norm"].item() - want["grad_norm"]) <= 1e-9 * want["grad_norm"]
+        assert abs(info["clip"].item() - want["clip"]) <= 1e-9
+        for k, p in model.named_parameters():
+            assert (p.detach() - sd[k]).abs().max().item() <= 1e-9, k
+    assert want["clip"] < 1.0   # the clip was active
