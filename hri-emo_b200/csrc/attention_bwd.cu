@@ -65,23 +65,52 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[NT][4], const bf* __restr
   }
 }
 
-// Rows [row0, row0 + 64) of one head of a row-major bf16 matrix -> shared memory, as they are ([64][DH + 8]) and, when
-// dstT != nullptr, transposed ([DH][72]).  Rows >= row_end are zero.
+// Rows [row0, row0 + 64) of one head of a row-major bf16 matrix, in two steps so that the global loads of the next
+// tile are in flight while the current one is being multiplied: fetch_tile (global -> registers) and stash_tile
+// (registers -> shared memory, as they are ([64][DH + 8]) and, when dstT != nullptr, transposed ([DH][72])).  Rows >=
+// row_end are zero.  Consecutive lanes take consecutive ROWS of one 8-column chunk: the transposed 2-byte stores of a
+// warp then fall into 16 consecutive words (no bank conflict; lanes with consecutive columns would all hit one bank,
+// 8 * 72 elements apart), and the 16-byte stores of the plain tile are conflict-free through the padded pitch.
 template <int DH>
-__device__ __forceinline__ void load_tile(const bf* __restrict__ src, int64_t ld, int64_t row0, int64_t row_end,
-                                          bf* __restrict__ dst, bf* __restrict__ dstT) {
-  constexpr int LDH = DH + 8, CH = DH / 8;
-  for (int idx = threadIdx.x; idx < AB_T * CH; idx += AB_THREADS) {
-    const int r = idx / CH, c = (idx - r * CH) * 8;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (row0 + r < row_end) v = __ldg(reinterpret_cast<const uint4*>(src + (row0 + r) * ld + c));
-    *reinterpret_cast<uint4*>(dst + r * LDH + c) = v;
+struct TileRegs {
+  static constexpr int N = (AB_T * (DH / 8)) / AB_THREADS;   // 16-byte chunks per thread: DH / 32
+  uint4 v[N];
+};
+
+template <int DH>
+__device__ __forceinline__ void fetch_tile(TileRegs<DH>& regs, const bf* __restrict__ src, int64_t ld, int64_t row0,
+                                           int64_t row_end) {
+#pragma unroll
+  for (int j = 0; j < TileRegs<DH>::N; ++j) {
+    const int idx = threadIdx.x + j * AB_THREADS;
+    const int r = idx % AB_T, c = (idx / AB_T) * 8;
+    regs.v[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (row0 + r < row_end) regs.v[j] = __ldg(reinterpret_cast<const uint4*>(src + (row0 + r) * ld + c));
+  }
+}
+
+template <int DH>
+__device__ __forceinline__ void stash_tile(const TileRegs<DH>& regs, bf* __restrict__ dst, bf* __restrict__ dstT) {
+  constexpr int LDH = DH + 8;
+#pragma unroll
+  for (int j = 0; j < TileRegs<DH>::N; ++j) {
+    const int idx = threadIdx.x + j * AB_THREADS;
+    const int r = idx % AB_T, c = (idx / AB_T) * 8;
+    *reinterpret_cast<uint4*>(dst + r * LDH + c) = regs.v[j];
     if (dstT != nullptr) {
-      const bf* e = reinterpret_cast<const bf*>(&v);
+      const bf* e = reinterpret_cast<const bf*>(&regs.v[j]);
 #pragma unroll
       for (int k = 0; k < 8; ++k) dstT[(c + k) * AB_LDT + r] = e[k];
     }
   }
+}
+
+template <int DH>
+__device__ __forceinline__ void load_tile(const bf* __restrict__ src, int64_t ld, int64_t row0, int64_t row_end,
+                                          bf* __restrict__ dst, bf* __restrict__ dstT) {
+  TileRegs<DH> regs;
+  fetch_tile<DH>(regs, src, ld, row0, row_end);
+  stash_tile<DH>(regs, dst, dstT);
 }
 
 struct AttnBwdParams {
@@ -159,7 +188,7 @@ struct AttnBwdSmem {
 
 // ---- pass 1: dK, dV of one 64-key tile of one (utterance, head)
 template <int DH, bool USE_MMA>
-__global__ void __launch_bounds__(AB_THREADS)
+__global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dkv_kernel(const AttnBwdParams p) {
   using SM = AttnBwdSmem<DH>;
   constexpr int NT = DH / 16;   // 8-column tiles per warp over half the head dim
@@ -195,16 +224,23 @@ attn_bwd_dkv_kernel(const AttnBwdParams p) {
 
   const float* lse = p.lse + (static_cast<int64_t>(b) * p.H + h) * p.Tq;
   const float* dsum = p.dsum + (static_cast<int64_t>(b) * p.H + h) * p.Tq;
+  TileRegs<DH> rq, rdo;   // the next query tile, in flight while the current one is multiplied
+  fetch_tile<DH>(rq, p.q + h * DH, p.ldq, qrow0, qrow0 + p.Tq);
+  fetch_tile<DH>(rdo, p.d_out + h * DH, p.lddo, qrow0, qrow0 + p.Tq);
   for (int q0 = 0; q0 < p.Tq; q0 += AB_T) {
     __syncthreads();   // the previous tile pair's shared-memory reads are done
-    load_tile<DH>(p.q + h * DH, p.ldq, qrow0 + q0, qrow0 + p.Tq, sQ, sQT);
-    load_tile<DH>(p.d_out + h * DH, p.lddo, qrow0 + q0, qrow0 + p.Tq, sdO, sdOT);
+    stash_tile<DH>(rq, sQ, sQT);
+    stash_tile<DH>(rdo, sdO, sdOT);
     if (threadIdx.x < AB_T) {
       const int q = q0 + threadIdx.x;
       s_lse[threadIdx.x] = q < p.Tq ? lse[q] : INFINITY;
       s_dsum[threadIdx.x] = q < p.Tq ? dsum[q] : 0.0f;
     }
     __syncthreads();
+    if (q0 + AB_T < p.Tq) {
+      fetch_tile<DH>(rq, p.q + h * DH, p.ldq, qrow0 + q0 + AB_T, qrow0 + p.Tq);
+      fetch_tile<DH>(rdo, p.d_out + h * DH, p.lddo, qrow0 + q0 + AB_T, qrow0 + p.Tq);
+    }
     float pr[4][4], ds[4][4];
     tile_p_ds<DH, USE_MMA>(sQ, sdO, sK, sV, s_lse, s_dsum, s_kvalid, p.scale, wm, wn, lane, pr, ds);
 #pragma unroll
@@ -238,7 +274,7 @@ attn_bwd_dkv_kernel(const AttnBwdParams p) {
 
 // ---- pass 2: dQ of one 64-query tile of one (utterance, head)
 template <int DH, bool USE_MMA>
-__global__ void __launch_bounds__(AB_THREADS)
+__global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dq_kernel(const AttnBwdParams p) {
   using SM = AttnBwdSmem<DH>;
   constexpr int NT = DH / 16;
@@ -272,15 +308,22 @@ attn_bwd_dq_kernel(const AttnBwdParams p) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) dq_acc[nt][e] = 0.0f;
 
+  TileRegs<DH> rk, rv;   // the next key tile, in flight while the current one is multiplied
+  fetch_tile<DH>(rk, p.k + h * DH, p.ldk, krow0, krow0 + p.Tk);
+  fetch_tile<DH>(rv, p.v + h * DH, p.ldv, krow0, krow0 + p.Tk);
   for (int k0 = 0; k0 < p.Tk; k0 += AB_T) {
     __syncthreads();
-    load_tile<DH>(p.k + h * DH, p.ldk, krow0 + k0, krow0 + p.Tk, sK, sKT);
-    load_tile<DH>(p.v + h * DH, p.ldv, krow0 + k0, krow0 + p.Tk, sV, nullptr);
+    stash_tile<DH>(rk, sK, sKT);
+    stash_tile<DH>(rv, sV, nullptr);
     if (threadIdx.x < AB_T) {
       const int k = k0 + threadIdx.x;
       s_kvalid[threadIdx.x] = (k < p.Tk && (p.key_pad == nullptr || p.key_pad[krow0 + k] == 0)) ? 1.0f : 0.0f;
     }
     __syncthreads();
+    if (k0 + AB_T < p.Tk) {
+      fetch_tile<DH>(rk, p.k + h * DH, p.ldk, krow0 + k0 + AB_T, krow0 + p.Tk);
+      fetch_tile<DH>(rv, p.v + h * DH, p.ldv, krow0 + k0 + AB_T, krow0 + p.Tk);
+    }
     float pr[4][4], ds[4][4];
     tile_p_ds<DH, USE_MMA>(sQ, sdO, sK, sV, s_lse, s_dsum, s_kvalid, p.scale, wm, wn, lane, pr, ds);
 #pragma unroll

@@ -31,6 +31,18 @@ f32 = torch.float32
 Grads = Dict[str, torch.Tensor]
 
 
+def zero_key_bias_gradients(grads: Grads) -> None:
+    """The key third of an attention in-projection bias has a gradient that is zero in exact arithmetic: adding a
+    constant to every key shifts all scores of a query by the same amount, which softmax ignores.  What arrives there
+    is round-off — ~1e-10 in the reference's float32 backward, below AdamW's eps, so the reference barely moves that
+    third; ~1e-6 from bf16 activation gradients, above eps, which AdamW would turn into steps of size lr.  The
+    round-off is replaced by the exact value."""
+    for name, g in grads.items():
+        if name.endswith("in_proj_bias"):
+            d = g.numel() // 3
+            g[d:2 * d].zero_()
+
+
 def _t(w: torch.Tensor) -> torch.Tensor:
     """[N, K] bf16 weight -> [K, N]: the operand of dX = dY . W for the forward GEMM kernel."""
     return ops.transpose_bf16(w)
@@ -319,6 +331,7 @@ def decode_loss_and_backward(model, a: E.Seq, t: E.Seq, mask_a, mask_t, labels: 
     d_a, d_t, g_gate = gate_backward(model.beta_gate, gate_tape, d_h, d_beta)
     grads: Grads = {f"beta_gate.{k}": v for k, v in g_gate.items()}
     grads.update({f"emotion_decoder.{k}": v for k, v in g_dec.items()})
+    zero_key_bias_gradients(grads)
     return dict(loss=loss, logits=logits, beta=beta, z=z, grads=grads, d_a=d_a, d_t=d_t)
 
 
@@ -336,4 +349,5 @@ def loss_and_gradients(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a, mask
     out = decode_loss_and_backward(model, a_enc, t_enc, mask_a, mask_t, labels, beta_weight)
     _, _, g_enc = encoder_backward(model.cross_modal, enc_tapes, out.pop("d_a"), out.pop("d_t"))
     out["grads"].update({f"cross_modal.{k}": v for k, v in g_enc.items()})
+    zero_key_bias_gradients(out["grads"])
     return out

@@ -304,25 +304,32 @@ def test_train_step_matches_two_reference_steps():
         total = want["grad_norm"]
         assert abs(info["grad_norm"].item() - total) <= 3e-2 * total
         assert info["clip"].item() == pytest.approx(min(1.0, fx["max_norm"] / (total + 1e-6)), rel=3e-2)
-        worst_g = worst_u = 0.0
+        worst_g, worst_u, worst_kb = (0.0, ""), (0.0, ""), (0.0, "")
         for k in fx["names"]:
             o, n = trainer.slots[k]
             got, ref = trainer.grads[o:o + n].double().norm().item(), want["grad_norms"][k]
-            worst_g = max(worst_g, abs(got - ref) / max(ref, 1e-3 * total))
+            worst_g = max(worst_g, (abs(got - ref) / max(ref, 1e-3 * total), k))
             got_u, ref_u = (trainer.params[o:o + n] - before[o:o + n]).double().norm().item(), want["update_norms"][k]
-            worst_u = max(worst_u, abs(got_u - ref_u) / max(ref_u, 1e-7))
+            e = abs(got_u - ref_u) / max(ref_u, 1e-7)
+            if k.endswith("in_proj_bias"):
+                worst_kb = max(worst_kb, (e, k))
+            else:
+                worst_u = max(worst_u, (e, k))
         report.append(dict(loss=info["loss"].item(), grad_norm=info["grad_norm"].item(), worst_grad_norm=worst_g,
-                           worst_update_norm=worst_u))
-        assert worst_g <= 0.1, worst_g
-        assert worst_u <= 0.1, worst_u
+                           worst_update_norm=worst_u, worst_update_norm_in_proj_bias=worst_kb))
+        if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+            with open(os.path.join(ROOT, "gpurun_out", "train_step_report.json"), "w") as f:
+                json.dump(report, f, indent=1)
+        assert worst_g[0] <= 0.1, worst_g
+        assert worst_u[0] <= 0.1, worst_u
+        # in-projection biases: the key third's gradient is exactly zero (backward.zero_key_bias_gradients); without that
+        # the bf16 round-off there made AdamW move it by ~lr per step (measured: update norm off by 19 % / 68 %)
+        assert worst_kb[0] <= 0.1, worst_kb
         for k, ref in want["grads_full"].items():
             assert _rel(trainer.gradient(k), ref) <= 5e-2, k
         for k, ref in want["params_full"].items():
             p = dict(model.named_parameters())[k]
             assert (p.detach().cpu() - ref).abs().max().item() <= 2.5 * fx["lr"], k
-    if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
-        with open(os.path.join(ROOT, "gpurun_out", "train_step_report.json"), "w") as f:
-            json.dump(report, f, indent=1)
     # the forward of the drop-in module sees the updated parameters (prepared operands were invalidated)
     model.eval()
     logits2, _, _ = model(h_a, h_t, m_a, m_t)
