@@ -11,7 +11,7 @@
 // query tiles and owns dK / dV of its keys; one CTA per (utterance, head, 64-query tile) walks the key tiles and
 // owns dQ of its queries.  S and dP are therefore computed twice (7 tile GEMMs per tile pair instead of 5).
 //
-// use_fma != 0 replaces every mma.sync by plain fp32 FMA loops over the same shared-memory tiles (same
+// impl == 1 replaces every mma.sync by plain fp32 FMA loops over the same shared-memory tiles (same
 // thread-to-element mapping): the slow reference form the tests compare the tensor-core form with.
 #include <cuda_bf16.h>
 
@@ -370,6 +370,295 @@ static int launch_attn_bwd(const AttnBwdParams& p, int B, cudaStream_t s) {
   return check_launch("attention_backward (dQ)");
 }
 
+
+// =====================================================================================================================
+// ldmatrix form (the default): the same two passes, but every fragment comes from ldmatrix(.trans), so NO transposed
+// copy of any tile exists in shared memory: the contraction-major operands of dV = P^T dO, dK = dS^T Q and dQ = dS K
+// are read with ldmatrix.trans straight from the row-major tiles.  Global loads are coalesced (lanes along the columns
+// of a row); P and dS are written [query][key] with 4-byte stores.  ncu of the first form
+// (profiles/r01_ncu_attention_bwd_v14_summary.txt): the LSU data pipe at 49 - 73 % of peak, 38 wavefronts per global
+// request from the row-per-lane loads that the transposed stores had asked for, mio_throttle the top stall.
+// =====================================================================================================================
+__device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const bf* ptr) {
+  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(ptr));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const bf* ptr) {
+  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(ptr));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// acc[16 x NT*8] += A . B^T over K (multiple of 16).  The 8x8 matrices of an x4 load are addressed by lane groups of 8
+// (mi = lane / 8); thread (g, t) receives (row g, elements 2t, 2t+1) of each, or of its transpose with .trans.
+//   A_TRANS = false: A stored [m][k] (row pitch lda), A points at (m0, 0).
+//   A_TRANS = true : A stored [k][m], A points at (0, m0)   (A = S^T: dV = P^T dO, dK = dS^T Q).
+//   B_TRANS = false: B stored [n][k] (row pitch ldb), B points at (n0, 0).
+//   B_TRANS = true : B stored [k][n], B points at (0, n0)   (dO, Q, K read as they lie).
+template <int NT, bool A_TRANS, bool B_TRANS>
+__device__ __forceinline__ void warp_gemm_lm(float (&acc)[NT][4], const bf* __restrict__ A, int lda,
+                                             const bf* __restrict__ B, int ldb, int K, int lane) {
+  static_assert(NT % 2 == 0, "B fragments are loaded two 8-column tiles at a time");
+  const int r8 = lane & 7, lo = (lane >> 3) & 1, hi = lane >> 4;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    uint32_t a0, a1, a2, a3;
+    if constexpr (!A_TRANS) {
+      // matrices: (m 0-7, k 0-7) (m 8-15, k 0-7) (m 0-7, k 8-15) (m 8-15, k 8-15)
+      ldsm_x4(a0, a1, a2, a3, A + (lo * 8 + r8) * lda + k0 + hi * 8);
+    } else {
+      // source blocks: (k 0-7, m 0-7) (k 0-7, m 8-15) (k 8-15, m 0-7) (k 8-15, m 8-15), transposed on the way
+      ldsm_x4_trans(a0, a1, a2, a3, A + (k0 + hi * 8 + r8) * lda + lo * 8);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; nt += 2) {
+      uint32_t b0, b1, b2, b3;   // (b0, b1) of column tile nt, (b0, b1) of column tile nt + 1
+      if constexpr (!B_TRANS) {
+        // matrices: (n 0-7, k 0-7) (n 0-7, k 8-15) (n 8-15, k 0-7) (n 8-15, k 8-15)
+        ldsm_x4(b0, b1, b2, b3, B + (nt * 8 + hi * 8 + r8) * ldb + k0 + lo * 8);
+      } else {
+        // source blocks: (k 0-7, n 0-7) (k 8-15, n 0-7) (k 0-7, n 8-15) (k 8-15, n 8-15), transposed on the way
+        ldsm_x4_trans(b0, b1, b2, b3, B + (k0 + lo * 8 + r8) * ldb + nt * 8 + hi * 8);
+      }
+      mma_16816(acc[nt], a0, a1, a2, a3, b0, b1);
+      mma_16816(acc[nt + 1], a0, a1, a2, a3, b2, b3);
+    }
+  }
+}
+
+// Coalesced tile staging: consecutive lanes take consecutive 16-byte chunks of a row.
+template <int DH>
+__device__ __forceinline__ void fetch_tile_rows(TileRegs<DH>& regs, const bf* __restrict__ src, int64_t ld, int64_t row0,
+                                                int64_t row_end) {
+  constexpr int CH = DH / 8;
+#pragma unroll
+  for (int j = 0; j < TileRegs<DH>::N; ++j) {
+    const int idx = threadIdx.x + j * AB_THREADS;
+    const int r = idx / CH, c = (idx - r * CH) * 8;
+    regs.v[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (row0 + r < row_end) regs.v[j] = __ldg(reinterpret_cast<const uint4*>(src + (row0 + r) * ld + c));
+  }
+}
+
+template <int DH>
+__device__ __forceinline__ void stash_tile_rows(const TileRegs<DH>& regs, bf* __restrict__ dst) {
+  constexpr int LDH = DH + 8, CH = DH / 8;
+#pragma unroll
+  for (int j = 0; j < TileRegs<DH>::N; ++j) {
+    const int idx = threadIdx.x + j * AB_THREADS;
+    const int r = idx / CH, c = (idx - r * CH) * 8;
+    *reinterpret_cast<uint4*>(dst + r * LDH + c) = regs.v[j];
+  }
+}
+
+// S and dP of one tile pair -> P and dS of this thread's 16 elements, written [query][key] into sP / sdS (either may be
+// null when the pass does not need it).
+template <int DH>
+__device__ __forceinline__ void tile_p_ds_lm(const bf* sQ, const bf* sdO, const bf* sK, const bf* sV, const float* s_lse,
+                                             const float* s_dsum, const float* s_kvalid, float scale, int wm, int wn,
+                                             int lane, bf* sP, bf* sdS) {
+  constexpr int LDH = DH + 8;
+  float p[4][4], ds[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { p[nt][e] = 0.0f; ds[nt][e] = 0.0f; }
+  warp_gemm_lm<4, false, false>(p, sQ + wm * 16 * LDH, LDH, sK + wn * 32 * LDH, LDH, DH, lane);     // S = Q K^T
+  warp_gemm_lm<4, false, false>(ds, sdO + wm * 16 * LDH, LDH, sV + wn * 32 * LDH, LDH, DH, lane);   // dP = dO V^T
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int q = wm * 16 + g + half * 8;
+      const int k = wn * 32 + nt * 8 + 2 * t;
+      const float lse = s_lse[q], dsum = s_dsum[q];
+      const float p0 = s_kvalid[k] != 0.0f ? __expf(p[nt][half * 2] * scale - lse) : 0.0f;
+      const float p1 = s_kvalid[k + 1] != 0.0f ? __expf(p[nt][half * 2 + 1] * scale - lse) : 0.0f;
+      if (sP != nullptr) *reinterpret_cast<__nv_bfloat162*>(sP + q * AB_LDT + k) = __floats2bfloat162_rn(p0, p1);
+      *reinterpret_cast<__nv_bfloat162*>(sdS + q * AB_LDT + k) =
+          __floats2bfloat162_rn(p0 * (ds[nt][half * 2] - dsum) * scale, p1 * (ds[nt][half * 2 + 1] - dsum) * scale);
+    }
+}
+
+template <int DH>
+struct AttnBwdSmemLm {
+  static constexpr int TILE = AB_T * (DH + 8);
+  static constexpr int SQ_T = AB_T * AB_LDT;
+  static constexpr size_t DKV_BYTES = (4 * TILE + 2 * SQ_T) * sizeof(bf) + 3 * AB_T * sizeof(float);   // K V Q dO P dS
+  static constexpr size_t DQ_BYTES = (4 * TILE + SQ_T) * sizeof(bf) + 3 * AB_T * sizeof(float);        // Q dO K V dS
+};
+
+template <int DH>
+__global__ void __launch_bounds__(AB_THREADS, 2)
+attn_bwd_dkv_lm_kernel(const AttnBwdParams p) {
+  using SM = AttnBwdSmemLm<DH>;
+  constexpr int NT = DH / 16, LDH = DH + 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf* sK = reinterpret_cast<bf*>(smem_raw);
+  bf* sV = sK + SM::TILE;
+  bf* sQ = sV + SM::TILE;
+  bf* sdO = sQ + SM::TILE;
+  bf* sP = sdO + SM::TILE;
+  bf* sdS = sP + SM::SQ_T;
+  float* s_lse = reinterpret_cast<float*>(sdS + SM::SQ_T);
+  float* s_dsum = s_lse + AB_T;
+  float* s_kvalid = s_dsum + AB_T;
+
+  const int k0 = blockIdx.x * AB_T, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp & 3, wn = warp >> 2;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t krow0 = static_cast<int64_t>(b) * p.Tk, qrow0 = static_cast<int64_t>(b) * p.Tq;
+
+  TileRegs<DH> rq, rdo;
+  fetch_tile_rows<DH>(rq, p.k + h * DH, p.ldk, krow0 + k0, krow0 + p.Tk);
+  fetch_tile_rows<DH>(rdo, p.v + h * DH, p.ldv, krow0 + k0, krow0 + p.Tk);
+  stash_tile_rows<DH>(rq, sK);
+  stash_tile_rows<DH>(rdo, sV);
+  if (threadIdx.x < AB_T) {
+    const int k = k0 + threadIdx.x;
+    s_kvalid[threadIdx.x] = (k < p.Tk && (p.key_pad == nullptr || p.key_pad[krow0 + k] == 0)) ? 1.0f : 0.0f;
+  }
+  float dk_acc[NT][4], dv_acc[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { dk_acc[nt][e] = 0.0f; dv_acc[nt][e] = 0.0f; }
+
+  const float* lse = p.lse + (static_cast<int64_t>(b) * p.H + h) * p.Tq;
+  const float* dsum = p.dsum + (static_cast<int64_t>(b) * p.H + h) * p.Tq;
+  fetch_tile_rows<DH>(rq, p.q + h * DH, p.ldq, qrow0, qrow0 + p.Tq);
+  fetch_tile_rows<DH>(rdo, p.d_out + h * DH, p.lddo, qrow0, qrow0 + p.Tq);
+  for (int q0 = 0; q0 < p.Tq; q0 += AB_T) {
+    __syncthreads();   // the previous tile pair's shared-memory reads are done
+    stash_tile_rows<DH>(rq, sQ);
+    stash_tile_rows<DH>(rdo, sdO);
+    if (threadIdx.x < AB_T) {
+      const int q = q0 + threadIdx.x;
+      s_lse[threadIdx.x] = q < p.Tq ? lse[q] : INFINITY;
+      s_dsum[threadIdx.x] = q < p.Tq ? dsum[q] : 0.0f;
+    }
+    __syncthreads();
+    if (q0 + AB_T < p.Tq) {
+      fetch_tile_rows<DH>(rq, p.q + h * DH, p.ldq, qrow0 + q0 + AB_T, qrow0 + p.Tq);
+      fetch_tile_rows<DH>(rdo, p.d_out + h * DH, p.lddo, qrow0 + q0 + AB_T, qrow0 + p.Tq);
+    }
+    tile_p_ds_lm<DH>(sQ, sdO, sK, sV, s_lse, s_dsum, s_kvalid, p.scale, wm, wn, lane, sP, sdS);
+    __syncthreads();
+    // dV[k][:] += sum_q P[q][k] dO[q][:],  dK[k][:] += sum_q dS[q][k] Q[q][:]   (rows = this warp's 16 keys)
+    warp_gemm_lm<NT, true, true>(dv_acc, sP + wm * 16, AB_LDT, sdO + wn * (DH / 2), LDH, AB_T, lane);
+    warp_gemm_lm<NT, true, true>(dk_acc, sdS + wm * 16, AB_LDT, sQ + wn * (DH / 2), LDH, AB_T, lane);
+  }
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int k = k0 + wm * 16 + g + half * 8;
+      if (k < p.Tk) {
+        const int c = h * DH + wn * (DH / 2) + nt * 8 + 2 * t;
+        *reinterpret_cast<__nv_bfloat162*>(p.dk + (krow0 + k) * p.lddk + c) =
+            __floats2bfloat162_rn(dk_acc[nt][half * 2], dk_acc[nt][half * 2 + 1]);
+        *reinterpret_cast<__nv_bfloat162*>(p.dv + (krow0 + k) * p.lddv + c) =
+            __floats2bfloat162_rn(dv_acc[nt][half * 2], dv_acc[nt][half * 2 + 1]);
+      }
+    }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(AB_THREADS, 2)
+attn_bwd_dq_lm_kernel(const AttnBwdParams p) {
+  using SM = AttnBwdSmemLm<DH>;
+  constexpr int NT = DH / 16, LDH = DH + 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf* sQ = reinterpret_cast<bf*>(smem_raw);
+  bf* sdO = sQ + SM::TILE;
+  bf* sK = sdO + SM::TILE;
+  bf* sV = sK + SM::TILE;
+  bf* sdS = sV + SM::TILE;
+  float* s_lse = reinterpret_cast<float*>(sdS + SM::SQ_T);
+  float* s_dsum = s_lse + AB_T;
+  float* s_kvalid = s_dsum + AB_T;
+
+  const int q0 = blockIdx.x * AB_T, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp & 3, wn = warp >> 2;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t krow0 = static_cast<int64_t>(b) * p.Tk, qrow0 = static_cast<int64_t>(b) * p.Tq;
+
+  TileRegs<DH> rk, rv;
+  fetch_tile_rows<DH>(rk, p.q + h * DH, p.ldq, qrow0 + q0, qrow0 + p.Tq);
+  fetch_tile_rows<DH>(rv, p.d_out + h * DH, p.lddo, qrow0 + q0, qrow0 + p.Tq);
+  stash_tile_rows<DH>(rk, sQ);
+  stash_tile_rows<DH>(rv, sdO);
+  if (threadIdx.x < AB_T) {
+    const int q = q0 + threadIdx.x;
+    const int64_t o = (static_cast<int64_t>(b) * p.H + h) * p.Tq + q;
+    s_lse[threadIdx.x] = q < p.Tq ? p.lse[o] : INFINITY;
+    s_dsum[threadIdx.x] = q < p.Tq ? p.dsum[o] : 0.0f;
+  }
+  float dq_acc[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dq_acc[nt][e] = 0.0f;
+
+  fetch_tile_rows<DH>(rk, p.k + h * DH, p.ldk, krow0, krow0 + p.Tk);
+  fetch_tile_rows<DH>(rv, p.v + h * DH, p.ldv, krow0, krow0 + p.Tk);
+  for (int k0 = 0; k0 < p.Tk; k0 += AB_T) {
+    __syncthreads();
+    stash_tile_rows<DH>(rk, sK);
+    stash_tile_rows<DH>(rv, sV);
+    if (threadIdx.x < AB_T) {
+      const int k = k0 + threadIdx.x;
+      s_kvalid[threadIdx.x] = (k < p.Tk && (p.key_pad == nullptr || p.key_pad[krow0 + k] == 0)) ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+    if (k0 + AB_T < p.Tk) {
+      fetch_tile_rows<DH>(rk, p.k + h * DH, p.ldk, krow0 + k0 + AB_T, krow0 + p.Tk);
+      fetch_tile_rows<DH>(rv, p.v + h * DH, p.ldv, krow0 + k0 + AB_T, krow0 + p.Tk);
+    }
+    tile_p_ds_lm<DH>(sQ, sdO, sK, sV, s_lse, s_dsum, s_kvalid, p.scale, wm, wn, lane, nullptr, sdS);
+    __syncthreads();
+    // dQ[q][:] += sum_k dS[q][k] K[k][:]   (rows = this warp's 16 queries; K read as it lies)
+    warp_gemm_lm<NT, false, true>(dq_acc, sdS + wm * 16 * AB_LDT, AB_LDT, sK + wn * (DH / 2), LDH, AB_T, lane);
+  }
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int q = q0 + wm * 16 + g + half * 8;
+      if (q < p.Tq) {
+        const int c = h * DH + wn * (DH / 2) + nt * 8 + 2 * t;
+        *reinterpret_cast<__nv_bfloat162*>(p.dq + (qrow0 + q) * p.lddq + c) =
+            __floats2bfloat162_rn(dq_acc[nt][half * 2], dq_acc[nt][half * 2 + 1]);
+      }
+    }
+}
+
+template <int DH>
+static int launch_attn_bwd_lm(const AttnBwdParams& p, int B, cudaStream_t s) {
+  using SM = AttnBwdSmemLm<DH>;
+  static uint64_t attr_done = 0;
+  if (device_needs_attr(&attr_done)) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_lm_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(SM::DKV_BYTES));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_dq_lm_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(SM::DQ_BYTES));
+    if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "attention_backward: %s", cudaGetErrorString(e));
+  }
+  attn_bwd_dkv_lm_kernel<DH><<<dim3((p.Tk + AB_T - 1) / AB_T, p.H, B), AB_THREADS, SM::DKV_BYTES, s>>>(p);
+  int rc = check_launch("attention_backward (dK, dV)");
+  if (rc) return rc;
+  attn_bwd_dq_lm_kernel<DH><<<dim3((p.Tq + AB_T - 1) / AB_T, p.H, B), AB_THREADS, SM::DQ_BYTES, s>>>(p);
+  return check_launch("attention_backward (dQ)");
+}
+
 }  // namespace hriemo
 
 using namespace hriemo;
@@ -380,6 +669,7 @@ extern "C" int hriemo_attention_backward_bf16(const hriemo_attn_bwd_args* a, voi
                  "attention_backward: null pointer");
   HRIEMO_REQUIRE(a->B > 0 && a->B <= 65535 && a->H > 0 && a->H <= 65535 && a->Tq > 0 && a->Tk > 0,
                  "attention_backward: bad shape B=%d H=%d Tq=%d Tk=%d", a->B, a->H, a->Tq, a->Tk);
+  HRIEMO_REQUIRE(a->impl >= 0 && a->impl <= 2, "attention_backward: impl=%d (0 ldmatrix tensor-core form, 1 FMA, 2 first tensor-core form)", a->impl);
   HRIEMO_REQUIRE(a->dh == 32 || a->dh == 64 || a->dh == 96 || a->dh == 128, "attention_backward: dh=%d not in {32, 64, 96, 128}",
                  a->dh);
   const int64_t lds[] = {a->ldq, a->ldk, a->ldv, a->ldo, a->lddo, a->lddq, a->lddk, a->lddv};
@@ -407,7 +697,9 @@ extern "C" int hriemo_attention_backward_bf16(const hriemo_attn_bwd_args* a, voi
   p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk; p.scale = a->scale;
 #define HRIEMO_AB_DISPATCH(DHV)                                                         \
   case DHV:                                                                             \
-    return a->use_fma ? launch_attn_bwd<DHV, false>(p, a->B, s) : launch_attn_bwd<DHV, true>(p, a->B, s)
+    return a->impl == 1 ? launch_attn_bwd<DHV, false>(p, a->B, s)                    \
+         : a->impl == 2 ? launch_attn_bwd<DHV, true>(p, a->B, s)                     \
+                           : launch_attn_bwd_lm<DHV>(p, a->B, s)
   switch (a->dh) {
     HRIEMO_AB_DISPATCH(32);
     HRIEMO_AB_DISPATCH(64);

@@ -64,7 +64,7 @@ class AttnBwdArgs(C.Structure):
         ("dv", C.c_void_p), ("lddv", C.c_int64),
         ("B", C.c_int32), ("H", C.c_int32), ("Tq", C.c_int32), ("Tk", C.c_int32), ("dh", C.c_int32),
         ("scale", C.c_float),
-        ("use_fma", C.c_int32),
+        ("impl", C.c_int32),
     ]
 
 

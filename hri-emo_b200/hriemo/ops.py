@@ -645,11 +645,12 @@ def small_attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, 
 @_on_tensor_device
 def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor,
                        lse: torch.Tensor, key_pad: Optional[torch.Tensor], B: int, H: int, Tq: int, Tk: int, dh: int,
-                       grads=None, use_fma: bool = False):
+                       grads=None, impl: int = 0):
     """Backward of `attention` (the encoder's attention): q / k / v as in the forward (column slices are fine), out
     [B*Tq, H*dh] and lse [B, H, Tq] from attention(..., want_lse=True), d_out [B*Tq, H*dh].
     -> (dq [B*Tq, H*dh], dk [B*Tk, H*dh], dv [B*Tk, H*dh]) bf16; grads = (dq, dk, dv): existing views to write into.
-    use_fma: the fp32-FMA form of the same tiles instead of mma.sync (slow; validation)."""
+    impl: 0 = the ldmatrix tensor-core form (default), 1 = fp32-FMA loops over the same tiles (slow; validation),
+    2 = the first tensor-core form (scalar fragment loads, transposed tile copies; kept for A/B measurements)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out"), (d_out, "d_out")):
         _chk2d(t, bf16, f"attention_backward {n}")
     d = H * dh
@@ -677,7 +678,7 @@ def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: t
     a.dq, a.lddq, a.dk, a.lddk, a.dv, a.lddv = dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0)
     a.B, a.H, a.Tq, a.Tk, a.dh = B, H, Tq, Tk, dh
     a.scale = 1.0 / math.sqrt(dh)
-    a.use_fma = 1 if use_fma else 0
+    a.impl = int(impl)
     tok = _prof_begin("attention_bwd", 14.0 * B * H * Tq * Tk * dh)   # 7 tile GEMMs (S and dP are formed in both passes)
     _l.check(_l.load().hriemo_attention_backward_bf16(C.byref(a), _stream()), "attention_backward_bf16")
     _prof_end(tok)

@@ -384,8 +384,9 @@ int hriemo_gate_stream_grad(const void* dh, int64_t lddh, int32_t L, const float
  * output `out`, its log-sum-exp `lse` and the output gradient d_out, writes dq [B*Tq, H*dh], dk and dv [B*Tk, H*dh]
  * (bf16; PAD keys receive zeros).  P is rebuilt as exp(scale * q.k - lse); dsum [B, H, Tq] (f32) is scratch that
  * receives rowsum(d_out o out).  Deterministic (no atomics): one pass owns dK / dV per key tile, one owns dQ per query
- * tile.  First correct version on warp-level mma.sync tensor-core instructions, not yet tcgen05;
- * use_fma != 0 runs the same tiles with fp32 FMA loops instead (slow; the form the tests compare against). */
+ * tile.  Warp-level mma.sync tensor-core instructions with ldmatrix(.trans) fragments, not yet tcgen05 (DESIGN.md
+ * sec. 8).  impl: 0 = that form; 1 = the same tiles with fp32 FMA loops (slow; validation); 2 = the first tensor-core
+ * form (scalar fragment loads, transposed tile copies; A/B measurements). */
 typedef struct hriemo_attn_bwd_args {
   const void* q;      int64_t ldq;    /* bf16, as in the forward */
   const void* k;      int64_t ldk;
@@ -400,7 +401,7 @@ typedef struct hriemo_attn_bwd_args {
   void* dv;           int64_t lddv;
   int32_t B, H, Tq, Tk, dh;           /* dh in {32, 64, 96, 128} */
   float scale;
-  int32_t use_fma;
+  int32_t impl;
 } hriemo_attn_bwd_args;
 int hriemo_attention_backward_bf16(const hriemo_attn_bwd_args* args, void* stream);
 

@@ -108,7 +108,7 @@ def attention(q, k, v, key_pad, B, H, Tq, Tk, dh, skip_padded_tiles=True, pair_h
     return (o.to(LO), torch.logsumexp(s, dim=-1)) if want_lse else o.to(LO)
 
 
-def attention_backward(q, k, v, out, d_out, lse, key_pad, B, H, Tq, Tk, dh, grads=None, use_fma=False):
+def attention_backward(q, k, v, out, d_out, lse, key_pad, B, H, Tq, Tk, dh, grads=None, impl=0):
     assert lse.shape == (B, H, Tq) and out.shape == d_out.shape == (B * Tq, H * dh)
     qr, kr, vr = (t.to(HI).clone().requires_grad_(True) for t in (q, k, v))
     o, _ = _attn(qr, kr, vr, key_pad, B, H, Tq, Tk, dh)

@@ -136,18 +136,19 @@ def test_gate_blend_backward_kernels_match_autograd(B, T_a, L, d, masked):
 
 
 # ------------------------------------------------------------------ encoder attention backward
-@pytest.mark.parametrize("use_fma", [False, True])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 @pytest.mark.parametrize("B,H,Tq,Tk,dh,masked", [(3, 8, 100, 70, 96, True), (2, 4, 64, 64, 64, False), (2, 2, 37, 150, 32, True),
                                                   (1, 2, 130, 20, 128, False), (2, 8, 300, 300, 96, True)])
-def test_attention_backward_matches_autograd(B, H, Tq, Tk, dh, masked, use_fma):
+def test_attention_backward_matches_autograd(B, H, Tq, Tk, dh, masked, impl):
     """dq, dk, dv of the encoder attention (packed [Q|K|V] column slices as operands, LSE and O from the forward kernel)
     against torch autograd in float64 on the same bf16 operands.  P and dS are rounded to bf16 before the second GEMMs:
-    element-wise 2e-2 of the tensor's scale, whole-tensor relative error 1e-2."""
+    element-wise 2e-2 of the tensor's scale, whole-tensor relative error 1e-2.  impl: 0 = ldmatrix form (default), 1 = FMA
+    loops, 2 = first tensor-core form."""
     import math
 
     from hriemo import ops
 
-    if use_fma and Tq * Tk > 20000:
+    if impl == 1 and Tq * Tk > 20000:
         pytest.skip("the FMA form is the slow reference: small shapes only")
     d = H * dh
     qkv_q = _rand((B * Tq, 3 * d), 551, dtype=torch.bfloat16)
@@ -157,7 +158,7 @@ def test_attention_backward_matches_autograd(B, H, Tq, Tk, dh, masked, use_fma):
     pad = _ragged(B, Tk, 554) if masked else None
     out, lse = ops.attention(q, k, v, pad, B, H, Tq, Tk, dh, want_lse=True)
     dkv = torch.full((B * Tk, 2 * d), float("nan"), dtype=torch.bfloat16, device=DEV)
-    dq, dk, dv = ops.attention_backward(q, k, v, out, do, lse, pad, B, H, Tq, Tk, dh, use_fma=use_fma,
+    dq, dk, dv = ops.attention_backward(q, k, v, out, do, lse, pad, B, H, Tq, Tk, dh, impl=impl,
                                         grads=(torch.empty((B * Tq, d), dtype=torch.bfloat16, device=DEV), dkv[:, :d], dkv[:, d:]))
     torch.cuda.synchronize()
     qr = q.double().reshape(B, Tq, d).requires_grad_(True)

@@ -25,9 +25,13 @@ def main():
     ap.add_argument("--T_t", type=int, default=64)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--attn-bwd-impl", type=int, default=0, help="ops.attention_backward impl (0 ldmatrix, 2 first form)")
     args = ap.parse_args()
     import torch.distributed as dist
     from hriemo import ops
+    if args.attn_bwd_impl:
+        import functools
+        ops.attention_backward = functools.partial(ops.attention_backward, impl=args.attn_bwd_impl)
     from hriemo.train import Trainer
     from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
 
