@@ -48,11 +48,16 @@ class Trainer:
     info = trainer.step(h_a, h_t, m_a, m_t, y)    # -> {"loss", "grad_norm", "clip", "logits", "beta"} (device tensors)
 
     process_group / torch.distributed initialised: gradients are averaged over the ranks (DistributedDataParallel's
-    semantics) with one all-reduce of the arena before the clip."""
+    semantics) with one all-reduce of the arena before the clip.
+
+    graph=True: from the third step with the same input shapes on, the forward + backward + arena fill (~500 kernel
+    launches, which at the reference's batch sizes take longer to enqueue from Python than to run) are replayed from
+    one CUDA graph; the all-reduce, the clip and AdamW (whose bias corrections depend on the step number) stay eager.
+    Inputs are copied into the graph's static buffers; the returned tensors are overwritten by the next step."""
 
     def __init__(self, model: torch.nn.Module, lr: float = 1e-4, weight_decay: float = 1e-2, betas=(0.9, 0.999),
                  eps: float = 1e-8, max_norm: float = 5.0, beta_weight: float = 0.01, process_group=None,
-                 distributed: Optional[bool] = None):
+                 distributed: Optional[bool] = None, graph: bool = False):
         params = list(model.named_parameters())
         if not params:
             raise L.HriemoError("Trainer: the model has no parameters")
@@ -84,6 +89,12 @@ class Trainer:
                 view.copy_(p.data)
                 p.data = view                          # the module's tensors ARE the arena from here on
         self.step_count = 0
+        self.use_graph = graph
+        self._graph = None
+        self._graph_key = None
+        self._graph_seen = 0
+        self._static_in = None
+        self._graph_out = None
         invalidate_prepared(model)
 
     def gradient(self, name: str) -> torch.Tensor:
@@ -91,21 +102,48 @@ class Trainer:
         o, n = self.slots[name]
         return self.grads[o:o + n].view(dict(self.model.named_parameters())[name].shape)
 
-    def step(self, h_a: torch.Tensor, h_t: torch.Tensor, mask_a, mask_t, labels: torch.Tensor) -> dict:
+    def _forward_backward(self, h_a, h_t, mask_a, mask_t, labels) -> dict:
+        """Forward with tapes, backward, gradients written into the arena.  -> loss / logits / beta / z."""
         out = backward.loss_and_gradients(self.model, h_a, h_t, mask_a, mask_t, labels, self.beta_weight)
         grads = out.pop("grads")
         if set(grads) != set(self.slots):
             raise L.HriemoError(f"Trainer: gradient names do not match the parameters: {sorted(set(grads) ^ set(self.slots))[:6]}")
         for name, (o, n) in self.slots.items():        # device-to-device copies into the arena
             self.grads[o:o + n].copy_(grads[name].reshape(-1))
-        del grads
+        return out
+
+    def _graphed_forward_backward(self, h_a, h_t, mask_a, mask_t, labels) -> dict:
+        ins = (h_a, h_t, mask_a, mask_t, labels)
+        key = tuple(None if x is None else (tuple(x.shape), x.dtype, x.device) for x in ins)
+        if key != self._graph_key:
+            self._graph, self._graph_key, self._graph_seen = None, key, 0
+        if self._graph is None:
+            self._graph_seen += 1
+            if self._graph_seen <= 2:                  # eager first: per-device kernel attributes, allocator warm-up
+                return self._forward_backward(*ins)
+            self._static_in = [None if x is None else x.clone() for x in ins]
+            invalidate_prepared(self.model)            # so that the weight casts are part of the captured work
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._graph_out = self._forward_backward(*self._static_in)
+        else:
+            for dst, src in zip(self._static_in, ins):
+                if dst is not None:
+                    dst.copy_(src)
+        self._graph.replay()
+        return dict(self._graph_out)
+
+    def step(self, h_a: torch.Tensor, h_t: torch.Tensor, mask_a, mask_t, labels: torch.Tensor) -> dict:
+        fb = self._graphed_forward_backward if self.use_graph else self._forward_backward
+        out = fb(h_a, h_t, mask_a, mask_t, labels)
         if self.distributed:
             self._all_reduce_mean(self.grads)
         norm_clip = ops.grad_norm_clip(self.grads, self.max_norm)          # [total norm, clip coefficient], on the device
         self.step_count += 1
         ops.adamw_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr,
                        betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, grad_scale=norm_clip[1:])
-        invalidate_prepared(self.model)
+        invalidate_prepared(self.model)   # eager callers (model.eval()(...)) re-cast; a captured step re-casts by itself
         out.update(grad_norm=norm_clip[0], clip=norm_clip[1])
         return out
 

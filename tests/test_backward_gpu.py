@@ -335,3 +335,33 @@ def test_train_step_matches_two_reference_steps():
     model.eval()
     logits2, _, _ = model(h_a, h_t, m_a, m_t)
     assert (logits2.cpu() - fx["steps"][1]["logits"]).abs().max().item() > 1e-4
+
+
+def test_trainer_graph_replay_matches_eager_steps():
+    """Trainer(graph=True) replays forward + backward + arena fill from one CUDA graph from the third step on: five
+    steps on changing batches must leave the same parameters as five eager steps (the kernels are deterministic; bound
+    1e-6 against lr = 1e-4, so one stale input or weight would show), and an eager forward afterwards must see the
+    updated weights."""
+    import copy
+
+    from hriemo.train import Trainer
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    B, T_a, T_t, d, Ne = 4, 40, 16, 768, 4
+    torch.manual_seed(571)
+    m1 = FusionWithEmotionDecoder(dropout=0.0).to(DEV)
+    m2 = copy.deepcopy(m1)
+    eager, graphed = Trainer(m1, distributed=False), Trainer(m2, distributed=False, graph=True)
+    ma, mt = _ragged(B, T_a, 572), _ragged(B, T_t, 573)
+    for i in range(5):
+        h_a, h_t = _rand((B, T_a, d), 580 + i), _rand((B, T_t, d), 590 + i)
+        labels = torch.eye(Ne)[torch.randint(0, Ne, (B,), generator=torch.Generator().manual_seed(600 + i))].to(DEV)
+        a = eager.step(h_a, h_t, ma, mt, labels)
+        b = graphed.step(h_a, h_t, ma, mt, labels)
+        assert abs(a["loss"].item() - b["loss"].item()) <= 1e-6, i
+    torch.cuda.synchronize()
+    assert graphed._graph is not None
+    assert (eager.params - graphed.params).abs().max().item() <= 1e-6
+    m1.eval(), m2.eval()
+    la, lb = m1(h_a, h_t, ma, mt)[0], m2(h_a, h_t, ma, mt)[0]
+    assert (la - lb).abs().max().item() <= 1e-4

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--T_t", type=int, default=64)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--graph", action="store_true", help="Trainer(graph=True): forward + backward replayed from a CUDA graph (no per-kernel breakdown)")
     ap.add_argument("--attn-bwd-impl", type=int, default=0, help="ops.attention_backward impl (0 ldmatrix, 2 first form)")
     args = ap.parse_args()
     import torch.distributed as dist
@@ -44,7 +45,7 @@ def main():
     dev = torch.device("cuda", local)
     torch.manual_seed(0)
     model = FusionWithEmotionDecoder(dropout=0.0).to(dev)
-    trainer = Trainer(model)
+    trainer = Trainer(model, graph=args.graph)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     B, d, n_e = args.batch, 768, 4
     h_a = torch.randn(B, args.T_a, d, device=dev, generator=g)
@@ -55,14 +56,14 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ops.PROFILE = []
+    ops.PROFILE = None if args.graph else []
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
         info = trainer.step(h_a, h_t, None, None, labels)
     t1.record()
     torch.cuda.synchronize()
-    prof, ops.PROFILE = ops.PROFILE, None
+    prof, ops.PROFILE = ops.PROFILE or [], None
     ms = torch.tensor([t0.elapsed_time(t1) / args.steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -82,7 +83,7 @@ def main():
                               data="synthetic", loss=info["loss"].item(), grad_norm=info["grad_norm"].item(),
                               config=dict(workload=f"FusionWithEmotionDecoder BCE training step, B={B}/GPU, T_a={args.T_a}, "
                                                    f"T_t={args.T_t}, d=768, H=8, N_e=4, 2+2 layers, AdamW, clip 5.0, dropout 0",
-                                          parameters=trainer.numel, exchange="one all-reduce (AVG) of the fp32 gradient arena"),
+                                          parameters=trainer.numel, cuda_graph=bool(args.graph), exchange="one all-reduce (AVG) of the fp32 gradient arena"),
                               breakdown=breakdown, peak_mem_gb=torch.cuda.max_memory_allocated() / 2**30)))
     if world > 1:
         dist.destroy_process_group()
