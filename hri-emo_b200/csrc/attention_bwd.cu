@@ -4,7 +4,7 @@
 //   P  = exp(scale * Q K^T - LSE)            (rebuilt from the forward's log-sum-exp, no running maximum needed)
 //   dV = P^T dO,  dP = dO V^T,  dS = scale * P o (dP - D),  D = rowsum(dO o O),  dQ = dS K,  dK = dS^T Q
 //
-// FIRST CORRECT VERSION, not the final one: the contractions run on the tensor cores through warp-level
+// NOT the final form: the contractions run on the tensor cores through warp-level
 // mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with operands staged in padded shared memory, NOT through
 // tcgen05/TMEM/TMA like the forward kernel (attention_bf16.cu); DESIGN.md sec. 8 describes the tcgen05 form that
 // replaces it.  Two deterministic passes instead of atomics: one CTA per (utterance, head, 64-key tile) walks the

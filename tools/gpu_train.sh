@@ -1,13 +1,13 @@
 #!/bin/bash
-# Training-step records: every GPU test, smoke(), the training-step benchmark at two batch sizes, and one
-# ncu --set full capture of the attention-backward kernels (first 4 launches of a small step).
+# Training-step records: every GPU test, smoke(), the training-step benchmark (eager with the per-kernel breakdown, and
+# CUDA-graph replay) at two batch sizes.  The ncu capture of the attention-backward kernels:
+#   ncu --set full --clock-control none --import-source on -k regex:attn_bwd_d -c 4 -f -o gpurun_out/prof_attn_bwd \
+#     python tools/bench_train.py --batch 32 --steps 1 --warmup 1
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -q -m gpu -x 2>&1 | tail -4
+timeout 600 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-for b in 128 512; do
-  timeout 120 python tools/bench_train.py --batch $b --steps 3 --warmup 2 > gpurun_out/bench_train_b$b.json 2> gpurun_out/bench_train_b$b.err || tail -3 gpurun_out/bench_train_b$b.err
-  cat gpurun_out/bench_train_b$b.json
+for cfg in "128" "128 --graph" "512" "512 --graph"; do
+  set -- $cfg
+  timeout 120 python tools/bench_train.py --batch $1 $2 --steps 5 --warmup 4 > "gpurun_out/bench_train_v15_b$1$2.json" 2> gpurun_out/bt.err || tail -3 gpurun_out/bt.err
+  python -c "import json;d=json.load(open('gpurun_out/bench_train_v15_b$1$2.json'));print('$cfg', round(d['value'],1), round(d['ms_per_step'],2), {k:(round(v['ms_per_step'],2), round(v['tflops'])) for k,v in d['breakdown'].items()})"
 done
-timeout 150 ncu --set full --clock-control none --import-source on -k regex:attn_bwd_d -c 4 -f -o gpurun_out/prof_attn_bwd \
-  python tools/bench_train.py --batch 32 --steps 1 --warmup 1 > gpurun_out/ncu_attn_bwd.log 2>&1
-tail -2 gpurun_out/ncu_attn_bwd.log
