@@ -118,6 +118,7 @@ struct AttnBwdParams {
   int64_t ldq, ldk, ldv, lddo;
   const float *lse, *dsum;        // [B, H, Tq]
   const uint8_t* key_pad;         // [B, Tk] or null
+  const int32_t* kv_steps;        // [B] 64-key tiles up to the last valid key, or null (ldmatrix form only)
   bf *dq, *dk, *dv;
   int64_t lddq, lddk, lddv;
   int H, Tq, Tk;
@@ -516,6 +517,18 @@ attn_bwd_dkv_lm_kernel(const AttnBwdParams p) {
   const int g = lane >> 2, t = lane & 3;
   const int64_t krow0 = static_cast<int64_t>(b) * p.Tk, qrow0 = static_cast<int64_t>(b) * p.Tq;
 
+  if (p.kv_steps != nullptr && static_cast<int>(blockIdx.x) >= p.kv_steps[b]) {
+    // a tile of trailing PAD keys: P = 0 for every query, so dK = dV = 0 without looking at anything
+    constexpr int CH = DH / 8;
+    for (int idx = threadIdx.x; idx < AB_T * CH; idx += AB_THREADS) {
+      const int r = idx / CH, c = (idx - r * CH) * 8;
+      if (k0 + r < p.Tk) {
+        *reinterpret_cast<uint4*>(p.dk + (krow0 + k0 + r) * p.lddk + h * DH + c) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(p.dv + (krow0 + k0 + r) * p.lddv + h * DH + c) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    return;
+  }
   TileRegs<DH> rq, rdo;
   fetch_tile_rows<DH>(rq, p.k + h * DH, p.ldk, krow0 + k0, krow0 + p.Tk);
   fetch_tile_rows<DH>(rdo, p.v + h * DH, p.ldv, krow0 + k0, krow0 + p.Tk);
@@ -607,9 +620,11 @@ attn_bwd_dq_lm_kernel(const AttnBwdParams p) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) dq_acc[nt][e] = 0.0f;
 
+  // trailing tiles of PAD keys contribute P = 0: not visited
+  const int k_end = p.kv_steps != nullptr ? min(p.Tk, p.kv_steps[b] * AB_T) : p.Tk;
   fetch_tile_rows<DH>(rk, p.k + h * DH, p.ldk, krow0, krow0 + p.Tk);
   fetch_tile_rows<DH>(rv, p.v + h * DH, p.ldv, krow0, krow0 + p.Tk);
-  for (int k0 = 0; k0 < p.Tk; k0 += AB_T) {
+  for (int k0 = 0; k0 < k_end; k0 += AB_T) {
     __syncthreads();
     stash_tile_rows<DH>(rk, sK);
     stash_tile_rows<DH>(rv, sV);
@@ -618,7 +633,7 @@ attn_bwd_dq_lm_kernel(const AttnBwdParams p) {
       s_kvalid[threadIdx.x] = (k < p.Tk && (p.key_pad == nullptr || p.key_pad[krow0 + k] == 0)) ? 1.0f : 0.0f;
     }
     __syncthreads();
-    if (k0 + AB_T < p.Tk) {
+    if (k0 + AB_T < k_end) {
       fetch_tile_rows<DH>(rk, p.k + h * DH, p.ldk, krow0 + k0 + AB_T, krow0 + p.Tk);
       fetch_tile_rows<DH>(rv, p.v + h * DH, p.ldv, krow0 + k0 + AB_T, krow0 + p.Tk);
     }
@@ -670,6 +685,7 @@ extern "C" int hriemo_attention_backward_bf16(const hriemo_attn_bwd_args* a, voi
   HRIEMO_REQUIRE(a->B > 0 && a->B <= 65535 && a->H > 0 && a->H <= 65535 && a->Tq > 0 && a->Tk > 0,
                  "attention_backward: bad shape B=%d H=%d Tq=%d Tk=%d", a->B, a->H, a->Tq, a->Tk);
   HRIEMO_REQUIRE(a->impl >= 0 && a->impl <= 2, "attention_backward: impl=%d (0 ldmatrix tensor-core form, 1 FMA, 2 first tensor-core form)", a->impl);
+  HRIEMO_REQUIRE(a->kv_steps == nullptr || a->key_pad != nullptr, "attention_backward: kv_steps comes with key_pad");
   HRIEMO_REQUIRE(a->dh == 32 || a->dh == 64 || a->dh == 96 || a->dh == 128, "attention_backward: dh=%d not in {32, 64, 96, 128}",
                  a->dh);
   const int64_t lds[] = {a->ldq, a->ldk, a->ldv, a->ldo, a->lddo, a->lddq, a->lddk, a->lddv};
@@ -691,7 +707,7 @@ extern "C" int hriemo_attention_backward_bf16(const hriemo_attn_bwd_args* a, voi
   p.q = static_cast<const bf*>(a->q); p.k = static_cast<const bf*>(a->k); p.v = static_cast<const bf*>(a->v);
   p.d_out = static_cast<const bf*>(a->d_out);
   p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv; p.lddo = a->lddo;
-  p.lse = a->lse; p.dsum = a->dsum; p.key_pad = a->key_pad;
+  p.lse = a->lse; p.dsum = a->dsum; p.key_pad = a->key_pad; p.kv_steps = a->kv_steps;
   p.dq = static_cast<bf*>(a->dq); p.dk = static_cast<bf*>(a->dk); p.dv = static_cast<bf*>(a->dv);
   p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
   p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk; p.scale = a->scale;

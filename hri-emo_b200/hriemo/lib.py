@@ -65,6 +65,7 @@ class AttnBwdArgs(C.Structure):
         ("B", C.c_int32), ("H", C.c_int32), ("Tq", C.c_int32), ("Tk", C.c_int32), ("dh", C.c_int32),
         ("scale", C.c_float),
         ("impl", C.c_int32),
+        ("kv_steps", C.c_void_p),
     ]
 
 

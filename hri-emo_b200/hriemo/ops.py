@@ -679,6 +679,10 @@ def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: t
     a.B, a.H, a.Tq, a.Tk, a.dh = B, H, Tq, Tk, dh
     a.scale = 1.0 / math.sqrt(dh)
     a.impl = int(impl)
+    steps = None
+    if m is not None and Tk > 64:
+        steps = kv_steps(m)   # trailing all-PAD key tiles are skipped (ragged batches; exact: a masked key has P = 0)
+        a.kv_steps = steps.data_ptr()
     tok = _prof_begin("attention_bwd", 14.0 * B * H * Tq * Tk * dh)   # 7 tile GEMMs (S and dP are formed in both passes)
     _l.check(_l.load().hriemo_attention_backward_bf16(C.byref(a), _stream()), "attention_backward_bf16")
     _prof_end(tok)

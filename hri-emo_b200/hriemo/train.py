@@ -19,6 +19,7 @@ involved; torch provides device memory, streams and the process group.
 """
 from __future__ import annotations
 
+import warnings
 from typing import Dict, Optional
 
 import torch
@@ -58,6 +59,10 @@ class Trainer:
     def __init__(self, model: torch.nn.Module, lr: float = 1e-4, weight_decay: float = 1e-2, betas=(0.9, 0.999),
                  eps: float = 1e-8, max_norm: float = 5.0, beta_weight: float = 0.01, process_group=None,
                  distributed: Optional[bool] = None, graph: bool = False):
+        p_drop = max((float(getattr(m, "p_drop", 0.0) or 0.0) for m in model.modules()), default=0.0)
+        if p_drop > 0:
+            warnings.warn(f"hri-emo_b200 Trainer: the model was built with dropout={p_drop}; the B200 training step does not "
+                          "apply dropout (it computes the dropout = 0 step, the configuration parity is defined on)", stacklevel=2)
         params = list(model.named_parameters())
         if not params:
             raise L.HriemoError("Trainer: the model has no parameters")

@@ -402,6 +402,9 @@ typedef struct hriemo_attn_bwd_args {
   int32_t B, H, Tq, Tk, dh;           /* dh in {32, 64, 96, 128} */
   float scale;
   int32_t impl;
+  /* Optional, with key_pad: kv_steps[b] from hriemo_attention_kv_steps -- tiles of trailing PAD keys are neither
+   * visited by the dQ pass nor computed by the dK / dV pass (they receive zeros); same result (impl 0 only). */
+  const int32_t* kv_steps;
 } hriemo_attn_bwd_args;
 int hriemo_attention_backward_bf16(const hriemo_attn_bwd_args* args, void* stream);
 

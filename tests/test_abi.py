@@ -47,7 +47,8 @@ def test_struct_layout_matches_header(tmp_path):
     import subprocess
     from hriemo import lib as L
 
-    fields = {"hriemo_gemm_args": L.GemmArgs, "hriemo_attn_args": L.AttnArgs, "hriemo_shard_info_t": L.ShardInfo}
+    fields = {"hriemo_gemm_args": L.GemmArgs, "hriemo_attn_args": L.AttnArgs, "hriemo_attn_bwd_args": L.AttnBwdArgs,
+              "hriemo_shard_info_t": L.ShardInfo}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "hriemo.h"', "int main(void){"]
     for cname, st in fields.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

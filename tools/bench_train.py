@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--T_t", type=int, default=64)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--ragged", action="store_true", help="trailing-PAD masks, valid lengths uniform in [T/2, T]")
     ap.add_argument("--graph", action="store_true", help="Trainer(graph=True): forward + backward replayed from a CUDA graph (no per-kernel breakdown)")
     ap.add_argument("--attn-bwd-impl", type=int, default=0, help="ops.attention_backward impl (0 ldmatrix, 2 first form)")
     args = ap.parse_args()
@@ -51,8 +52,14 @@ def main():
     h_a = torch.randn(B, args.T_a, d, device=dev, generator=g)
     h_t = torch.randn(B, args.T_t, d, device=dev, generator=g)
     labels = torch.eye(n_e, device=dev)[torch.randint(0, n_e, (B,), device=dev, generator=g)]
+    m_a = m_t = None
+    if args.ragged:
+        la = torch.randint(args.T_a // 2, args.T_a + 1, (B,), device=dev, generator=g)
+        lt = torch.randint(args.T_t // 2, args.T_t + 1, (B,), device=dev, generator=g)
+        m_a = torch.arange(args.T_a, device=dev)[None, :] >= la[:, None]
+        m_t = torch.arange(args.T_t, device=dev)[None, :] >= lt[:, None]
     for _ in range(args.warmup):
-        trainer.step(h_a, h_t, None, None, labels)
+        trainer.step(h_a, h_t, m_a, m_t, labels)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -60,7 +67,7 @@ def main():
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
-        info = trainer.step(h_a, h_t, None, None, labels)
+        info = trainer.step(h_a, h_t, m_a, m_t, labels)
     t1.record()
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE or [], None
@@ -83,7 +90,7 @@ def main():
                               data="synthetic", loss=info["loss"].item(), grad_norm=info["grad_norm"].item(),
                               config=dict(workload=f"FusionWithEmotionDecoder BCE training step, B={B}/GPU, T_a={args.T_a}, "
                                                    f"T_t={args.T_t}, d=768, H=8, N_e=4, 2+2 layers, AdamW, clip 5.0, dropout 0",
-                                          parameters=trainer.numel, cuda_graph=bool(args.graph), exchange="one all-reduce (AVG) of the fp32 gradient arena"),
+                                          parameters=trainer.numel, cuda_graph=bool(args.graph), ragged=bool(args.ragged), exchange="one all-reduce (AVG) of the fp32 gradient arena"),
                               breakdown=breakdown, peak_mem_gb=torch.cuda.max_memory_allocated() / 2**30)))
     if world > 1:
         dist.destroy_process_group()
