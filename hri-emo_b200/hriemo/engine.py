@@ -91,8 +91,8 @@ def warn_if_training(module: torch.nn.Module, p_drop: float) -> None:
     if module.training and p_drop > 0 and not _warned_train:
         _warned_train = True
         warnings.warn(
-            "hri-emo_b200: forward-only build — dropout is not applied and no autograd graph is "
-            "recorded even though the module is in training mode; call .eval() for inference.",
+            "hri-emo_b200: forward() applies no dropout and records no autograd graph even though the module is in "
+            "training mode; call .eval() for inference, hriemo.train.Trainer for training steps.",
             stacklevel=3)
 
 
