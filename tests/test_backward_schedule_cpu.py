@@ -139,3 +139,31 @@ def test_trainer_two_steps_match_the_training_oracle(monkeypatch):
         for k, p in model.named_parameters():
             assert (p.detach() - sd[k]).abs().max().item() <= 1e-9, k
     assert want["clip"] < 1.0   # the clip was active
+
+
+def test_trainer_keeps_the_state_dict_contract(monkeypatch):
+    """Moving the parameters into the flat arena leaves state_dict() keys / shapes / values as they were, and a strict
+    load_state_dict() afterwards writes INTO the arena (the modules' tensors stay views of it)."""
+    kernel_standins.install(monkeypatch, exact=True)
+    from hriemo.train import Trainer
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    torch.manual_seed(41)
+    model = FusionWithEmotionDecoder(d_model=128, num_emotions=4, n_heads=2, num_layers_fusion=1, num_layers_decoder=1,
+                                     beta_hidden=32, dropout=0.0).double()
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    trainer = Trainer(model, distributed=False)
+    after = model.state_dict()
+    assert list(after) == list(before)
+    assert all(torch.equal(after[k], before[k]) for k in before)
+    assert trainer.numel >= sum(v.numel() for v in before.values())
+    lo, hi = trainer.params.data_ptr(), trainer.params.data_ptr() + trainer.params.numel() * trainer.params.element_size()
+    assert all(lo <= p.data_ptr() < hi and p.data_ptr() % 16 == 0 for p in model.parameters())
+    other = {k: torch.randn_like(v) for k, v in before.items()}
+    model.load_state_dict(other, strict=True)
+    assert all(lo <= p.data_ptr() < hi for p in model.parameters())
+    for name, (o, n) in trainer.slots.items():
+        assert torch.equal(trainer.params[o:o + n], other[name].reshape(-1)), name
+    with pytest.warns(UserWarning, match="does not.*apply dropout|dropout"):
+        Trainer(FusionWithEmotionDecoder(d_model=128, num_emotions=4, n_heads=2, num_layers_fusion=1,
+                                         num_layers_decoder=1, beta_hidden=32, dropout=0.1).double(), distributed=False)
