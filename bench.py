@@ -11,6 +11,11 @@ metric through hriemo.pipeline.forward_from_host with pinned HOST buffers (H2D o
 features and D2H of logits/beta/z inside the timed region).  With N > 1 (torchrun) every
 rank owns its own shard of utterances (weak scaling) and the only collective is one
 all_gather of logits+beta per step, inside the timed region.  One JSON line on rank 0.
+
+At N = 1 on the default workload the line carries one extra, clearly separate key, "train_step": the BASELINE config 5
+record (FusionWithEmotionDecoder BCE training step, hriemo.train.Trainer, B = 512, CUDA-graph replay) measured by
+tools/bench_train.py in a child process after the contract's own timed regions are over (--no-train skips it; a
+failure there is reported inside the key and never fails the bench).
 """
 from __future__ import annotations
 
@@ -148,6 +153,27 @@ def cpu_forward_timer(T_a, T_t, sample_B, steps, warmup, mosei=False):
     return times, torch.get_num_threads()
 
 
+def train_step_leg(batch=512, timeout_s=180):
+    """Supplementary record for BASELINE config 5 (not part of the contract keys): one B200, FusionWithEmotionDecoder BCE
+    training step through hriemo.train.Trainer with CUDA-graph replay, measured by tools/bench_train.py in a CHILD process
+    (its own CUDA context and timed region; a failure there cannot touch this run).  -> dict for the "train_step" key."""
+    import subprocess
+    root = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, os.path.join(root, "tools", "bench_train.py"), "--batch", str(batch), "--graph",
+           "--steps", "5", "--warmup", "4"]
+    try:
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env, cwd=root)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": (r.stderr.strip().splitlines() or ["no output"])[-1][:300]}
+        d = json.loads(lines[-1])
+        return {k: d[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "dtype", "config", "loss",
+                                  "peak_mem_gb") if k in d}
+    except Exception as e:  # noqa: BLE001  (supplementary leg: never fails the bench)
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -180,6 +206,7 @@ def main():
                          "over 1 warm-up + 2 timed passes; 96 per step for --impl reference)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the supplementary training-step record (config 5)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -363,6 +390,11 @@ def main():
                         "sample": f"{n_cpu} utterances x {len(times)} timed passes (+1 warm-up) of the same workload "
                                   f"(T_a={T_a}, T_t={T_t}), fp32, all host threads, oracle port of the reference forward"}
 
+    train_step = None
+    if rank == 0 and world == 1 and args.workload == "ns" and not args.batch and not args.no_train:
+        torch.cuda.empty_cache()
+        train_step = train_step_leg()
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -372,6 +404,8 @@ def main():
                 "roofline": roofline, "attention_roofline": attention_roofline,
                 "path": {"flops_per_utt": fpu, "achieved_tflops_per_gpu": path_tf, "frac_of_tensor_peak": path_tf / peaks["tf_sust"]},
                 "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary()}
+        if train_step is not None:
+            line["train_step"] = train_step
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -97,3 +97,18 @@ def test_slab_schedule_covers_the_batch_in_order():
     plan = pipeline.slab_schedule(4096, 512, 2, ramp=True)
     assert [e - s for s, e, _ in plan[:3]] == [64, 128, 256] and not any(h for _, _, h in plan[:4])
     assert [e - s for s, e, _ in pipeline.slab_schedule(2048, 512, 2)] == [512] * 4
+
+
+def test_bench_training_leg_never_fails_the_bench():
+    """bench.py's supplementary "train_step" record runs tools/bench_train.py in a child process; without a GPU the child
+    fails, and the leg must hand back an error record instead of raising."""
+    import importlib.util
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    if torch.cuda.is_available():
+        pytest.skip("error path: CPU-only check")
+    rec = bench.train_step_leg(batch=4, timeout_s=120)
+    assert set(rec) == {"error"} and rec["error"]
