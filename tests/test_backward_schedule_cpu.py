@@ -167,3 +167,38 @@ def test_trainer_keeps_the_state_dict_contract(monkeypatch):
     with pytest.warns(UserWarning, match="does not.*apply dropout|dropout"):
         Trainer(FusionWithEmotionDecoder(d_model=128, num_emotions=4, n_heads=2, num_layers_fusion=1,
                                          num_layers_decoder=1, beta_hidden=32, dropout=0.1).double(), distributed=False)
+
+
+@pytest.mark.parametrize("L_f,L_d,Ne,mask_mode", [(3, 1, 8, "audio"), (1, 3, 1, "text"), (0, 2, 4, "both")])
+def test_loss_and_gradients_schedule_other_depths_and_masks(monkeypatch, L_f, L_d, Ne, mask_mode):
+    """Exact (float64) schedule check on the shapes the other tests do not visit: three encoder layers / none at all,
+    one and three decoder layers, one and eight emotion queries, a PAD mask on one modality only, T_a == T_t."""
+    import hriemo_oracle_train as OT
+
+    kernel_standins.install(monkeypatch, exact=True)
+    from hriemo import backward
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    B, T, d, H = 3, 7, 128, 4
+    torch.manual_seed(51)
+    model = FusionWithEmotionDecoder(d_model=d, num_emotions=Ne, n_heads=H, num_layers_fusion=L_f, num_layers_decoder=L_d,
+                                     beta_hidden=32, dropout=0.0).double()
+    g = torch.Generator().manual_seed(52)
+    h_a = torch.randn(B, T + (0 if mask_mode == "both" else 4), d, generator=g, dtype=torch.float64)
+    h_t = torch.randn(B, T, d, generator=g, dtype=torch.float64)
+    ma = torch.arange(h_a.shape[1])[None, :] >= torch.randint(1, h_a.shape[1] + 1, (B,), generator=g)[:, None]
+    mt = torch.arange(T)[None, :] >= torch.randint(1, T + 1, (B,), generator=g)[:, None]
+    if mask_mode == "audio":
+        mt = None
+    if mask_mode == "text":
+        ma = None
+    labels = (torch.rand(B, Ne, generator=g) < 0.5).double()
+    monkeypatch.setattr(backward.E, "to_seq", lambda x, what, ld=None: backward.E.Seq(x.reshape(-1, x.shape[-1]), x.shape[0], x.shape[1]))
+    out = backward.loss_and_gradients(model, h_a, h_t, ma, mt, labels)
+    sd = {k: v.detach().double().requires_grad_(True) for k, v in model.state_dict().items()}
+    loss, _, _ = OT.train_loss(sd, h_a, h_t, ma, mt, labels, n_heads=H)
+    loss.backward()
+    assert abs(out["loss"].item() - loss.item()) <= 1e-12
+    assert set(out["grads"]) == set(sd)
+    bad = {k: _rel(out["grads"][k], p.grad) for k, p in sd.items() if not _rel(out["grads"][k], p.grad) <= 1e-9}
+    assert not bad, bad
