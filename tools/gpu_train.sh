@@ -11,3 +11,7 @@ for cfg in "128" "128 --graph" "512" "512 --graph"; do
   timeout 120 python tools/bench_train.py --batch $1 $2 --steps 5 --warmup 4 > "gpurun_out/bench_train_v15_b$1$2.json" 2> gpurun_out/bt.err || tail -3 gpurun_out/bt.err
   python -c "import json;d=json.load(open('gpurun_out/bench_train_v15_b$1$2.json'));print('$cfg', round(d['value'],1), round(d['ms_per_step'],2), {k:(round(v['ms_per_step'],2), round(v['tflops'])) for k,v in d['breakdown'].items()})"
 done
+# ragged batch (trailing-PAD masks, lengths uniform in [T/2, T]): default attention backward vs its first form
+for cfg in "--ragged" "--ragged --attn-bwd-impl 2"; do
+  timeout 60 python tools/bench_train.py --batch 128 $cfg --steps 3 --warmup 2 2> gpurun_out/bt.err | tee -a gpurun_out/bench_train_ragged.jsonl | cut -c1-120
+done
