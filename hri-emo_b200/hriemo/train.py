@@ -107,14 +107,21 @@ class Trainer:
         o, n = self.slots[name]
         return self.grads[o:o + n].view(dict(self.model.named_parameters())[name].shape)
 
-    def _forward_backward(self, h_a, h_t, mask_a, mask_t, labels) -> dict:
-        """Forward with tapes, backward, gradients written into the arena.  -> loss / logits / beta / z."""
+    def _forward_backward(self, h_a, h_t, mask_a, mask_t, labels, scale: float = 1.0, accumulate: bool = False) -> dict:
+        """Forward with tapes, backward, gradients written (or, with accumulate, added) into the arena, multiplied by
+        `scale`.  -> loss / logits / beta / z."""
         out = backward.loss_and_gradients(self.model, h_a, h_t, mask_a, mask_t, labels, self.beta_weight)
         grads = out.pop("grads")
         if set(grads) != set(self.slots):
             raise L.HriemoError(f"Trainer: gradient names do not match the parameters: {sorted(set(grads) ^ set(self.slots))[:6]}")
         for name, (o, n) in self.slots.items():        # device-to-device copies into the arena
-            self.grads[o:o + n].copy_(grads[name].reshape(-1))
+            dst, g = self.grads[o:o + n], grads[name].reshape(-1)
+            if accumulate:
+                dst.add_(g, alpha=scale)
+            elif scale != 1.0:
+                torch.mul(g, scale, out=dst)
+            else:
+                dst.copy_(g)
         return out
 
     def _graphed_forward_backward(self, h_a, h_t, mask_a, mask_t, labels) -> dict:
@@ -142,6 +149,13 @@ class Trainer:
     def step(self, h_a: torch.Tensor, h_t: torch.Tensor, mask_a, mask_t, labels: torch.Tensor) -> dict:
         fb = self._graphed_forward_backward if self.use_graph else self._forward_backward
         out = fb(h_a, h_t, mask_a, mask_t, labels)
+        out.update(self.apply())
+        return out
+
+    def apply(self) -> dict:
+        """All-reduce (data parallel), global-norm clip and AdamW on what the gradient arena holds; the learning rate is
+        `self.lr` at the time of the call (set it per step for a schedule, e.g. the cosine + warm-up of
+        train_mosei_fusion_seq_level_decoder.py:574-590).  -> {"grad_norm", "clip"} (device tensors)."""
         if self.distributed:
             self._all_reduce_mean(self.grads)
         norm_clip = ops.grad_norm_clip(self.grads, self.max_norm)          # [total norm, clip coefficient], on the device
@@ -149,8 +163,23 @@ class Trainer:
         ops.adamw_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr,
                        betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, grad_scale=norm_clip[1:])
         invalidate_prepared(self.model)   # eager callers (model.eval()(...)) re-cast; a captured step re-casts by itself
-        out.update(grad_norm=norm_clip[0], clip=norm_clip[1])
-        return out
+        return dict(grad_norm=norm_clip[0], clip=norm_clip[1])
+
+    def step_accumulated(self, micro_batches) -> dict:
+        """Gradient accumulation as in train_mosei_fusion_seq_level_decoder.py:388-401 (`loss / grad_accum` per micro-batch,
+        one clip + optimizer step per `grad_accum` micro-batches).  micro_batches: sequence of (h_a, h_t, mask_a, mask_t,
+        labels).  -> {"loss": mean of the micro-batch losses, "grad_norm", "clip"}."""
+        micro_batches = list(micro_batches)
+        if not micro_batches:
+            raise L.HriemoError("Trainer.step_accumulated: no micro-batches")
+        k = len(micro_batches)
+        loss = None
+        for i, mb in enumerate(micro_batches):
+            out = self._forward_backward(*mb, scale=1.0 / k, accumulate=i > 0)
+            loss = out["loss"] / k if loss is None else loss + out["loss"] / k
+        res = self.apply()
+        res["loss"] = loss
+        return res
 
     def _all_reduce_mean(self, t: torch.Tensor) -> None:
         import torch.distributed as dist

@@ -202,3 +202,35 @@ def test_loss_and_gradients_schedule_other_depths_and_masks(monkeypatch, L_f, L_
     assert set(out["grads"]) == set(sd)
     bad = {k: _rel(out["grads"][k], p.grad) for k, p in sd.items() if not _rel(out["grads"][k], p.grad) <= 1e-9}
     assert not bad, bad
+
+
+def test_trainer_gradient_accumulation_and_lr_schedule(monkeypatch):
+    """step_accumulated over two equal micro-batches equals one oracle step on their union (the loss is a mean over
+    utterances), and `trainer.lr` set between steps is the learning rate AdamW uses (float64 stand-ins, 1e-9)."""
+    import hriemo_oracle_train as OT
+
+    kernel_standins.install(monkeypatch, exact=True)
+    from hriemo import backward
+    from hriemo.train import Trainer
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    B, T_a, T_t, d, H, Ne = 4, 9, 5, 128, 2, 4
+    torch.manual_seed(61)
+    model = FusionWithEmotionDecoder(d_model=d, num_emotions=Ne, n_heads=H, num_layers_fusion=1, num_layers_decoder=1,
+                                     beta_hidden=32, dropout=0.0).double()
+    g = torch.Generator().manual_seed(62)
+    h_a = torch.randn(B, T_a, d, generator=g, dtype=torch.float64)
+    h_t = torch.randn(B, T_t, d, generator=g, dtype=torch.float64)
+    labels = (torch.rand(B, Ne, generator=g) < 0.5).double()
+    monkeypatch.setattr(backward.E, "to_seq", lambda x, what, ld=None: backward.E.Seq(x.reshape(-1, x.shape[-1]), x.shape[0], x.shape[1]))
+    sd = {k: p.detach().clone() for k, p in model.named_parameters()}
+    trainer = Trainer(model, lr=1e-3, max_norm=0.5, distributed=False)
+    opt = None
+    for lr in (1e-3, 4e-4):
+        trainer.lr = lr
+        info = trainer.step_accumulated([(h_a[:2], h_t[:2], None, None, labels[:2]), (h_a[2:], h_t[2:], None, None, labels[2:])])
+        sd, opt, want = OT.train_step(sd, opt, h_a, h_t, None, None, labels, n_heads=H, lr=lr, max_norm=0.5)
+        assert abs(info["loss"].item() - want["loss"]) <= 1e-12
+        assert abs(info["grad_norm"].item() - want["grad_norm"]) <= 1e-9 * want["grad_norm"]
+        for k, p in model.named_parameters():
+            assert (p.detach() - sd[k]).abs().max().item() <= 1e-9, k
