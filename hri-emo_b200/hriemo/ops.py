@@ -453,7 +453,7 @@ def host_pack_bf16(src: torch.Tensor, dst: torch.Tensor, T_out: int, utt: Option
         raise _l.HriemoError("host_pack_bf16: destination too small")
     threads = threads or max(1, min(32, (os.cpu_count() or 1)))
     _l.check(_l.load().hriemo_host_pack_bf16(src.data_ptr(), cols, T, cols, _ptr(utt), _ptr(lens), dst.data_ptr(), cols,
-                                              T_out, n, threads), "host_pack_bf16")
+                                              T_out, n, B, threads), "host_pack_bf16")
     return dst.view(-1)[: n * T_out * cols].view(n, T_out, cols)
 
 

@@ -227,36 +227,61 @@ def forward_bucketed(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Option
 # host staging
 # --------------------------------------------------------------------------- #
 _STAGING = {}   # configuration -> staging buffers + events, reused across calls
+# what the host-staged entry points moved, accumulated over calls (bench.py reads and resets it): bytes copied
+# host -> device (counted from the tensors copied), slabs, and how many of them the host cores pre-cast
+STATS = dict(h2d_bytes=0, slabs=0, host_cast_slabs=0, calls=0)
+
+
+def reset_stats() -> None:
+    for k in STATS:
+        STATS[k] = 0
 
 
 def _staging(dev, dtype_a, dtype_t, host_dtype, elems_a: int, elems_t: int, rows_a: int, rows_t: int, direct_sets: bool,
              host_sets: bool, with_ma: bool, with_mt: bool):
-    key = (str(dev), dtype_a, dtype_t, host_dtype, elems_a, elems_t, rows_a, rows_t, direct_sets, host_sets, with_ma, with_mt)
+    """Staging sets for one configuration (device, dtypes).  Capacities only GROW: a stream of batches whose bucket
+    plans (or last partial batch) need slightly different sizes reuses the same pinned / device buffers through
+    slices instead of re-pinning hundreds of MB per call; a set is reallocated only when a call needs more room,
+    or a kind of buffer (masks, host sets, direct sets) the resident one lacks."""
+    key = (str(dev), dtype_a, dtype_t, host_dtype)
+    need = dict(elems_a=elems_a, elems_t=elems_t, rows_a=rows_a, rows_t=rows_t)
     st = _STAGING.get(key)
-    if st is None:
-        def mk(da, dt):
-            return dict(a=torch.empty((elems_a,), dtype=da, device=dev),
-                        t=torch.empty((elems_t,), dtype=dt, device=dev),
-                        ma=torch.empty((rows_a,), dtype=torch.bool, device=dev) if with_ma else None,
-                        mt=torch.empty((rows_t,), dtype=torch.bool, device=dev) if with_mt else None,
-                        copied=torch.cuda.Event(), consumed=torch.cuda.Event())
+    if st is not None:
+        cap, has = st["cap"], st["has"]
+        if (all(cap[k] >= v for k, v in need.items()) and (has["direct"] or not direct_sets) and (has["host"] or not host_sets)
+                and (has["ma"] or not with_ma) and (has["mt"] or not with_mt)):
+            return st
+        # grow: keep every capacity and every kind the resident configuration already had
+        need = {k: max(v, cap[k]) for k, v in need.items()}
+        direct_sets, host_sets = direct_sets or has["direct"], host_sets or has["host"]
+        with_ma, with_mt = with_ma or has["ma"], with_mt or has["mt"]
+    if _STAGING:
+        torch.cuda.synchronize(dev)       # copies in flight still read / write the buffers about to be dropped
+    ea, et, ra, rt = need["elems_a"], need["elems_t"], need["rows_a"], need["rows_t"]
 
-        st = dict(copy=torch.cuda.Stream(dev))
-        if direct_sets:
-            # landing sets of the source dtype: free again as soon as the GPU bf16 cast has read them
-            st["direct"] = [mk(dtype_a, dtype_t), mk(dtype_a, dtype_t)]
-        if host_sets:
-            # slabs prepared by the host cores (bf16 pack of a padded batch, or rows of a shard): pinned staging
-            # on the host (ping-pong) and landing buffers on the device (ping-pong, released when the slab's
-            # forward is done)
-            def mk_host():
-                return dict(a=torch.empty((elems_a,), dtype=host_dtype).pin_memory(),
-                            t=torch.empty((elems_t,), dtype=host_dtype).pin_memory(),
-                            sent=torch.cuda.Event())
-            st["host16"] = [mk_host(), mk_host()]
-            st["dev16"] = [mk(host_dtype, host_dtype), mk(host_dtype, host_dtype)]
-        _STAGING.clear()      # keep one configuration resident
-        _STAGING[key] = st
+    def mk(da, dt):
+        return dict(a=torch.empty((ea,), dtype=da, device=dev),
+                    t=torch.empty((et,), dtype=dt, device=dev),
+                    ma=torch.empty((ra,), dtype=torch.bool, device=dev) if with_ma else None,
+                    mt=torch.empty((rt,), dtype=torch.bool, device=dev) if with_mt else None,
+                    copied=torch.cuda.Event(), consumed=torch.cuda.Event())
+
+    _STAGING.clear()      # keep one configuration resident
+    st = dict(copy=torch.cuda.Stream(dev), cap=need, has=dict(direct=direct_sets, host=host_sets, ma=with_ma, mt=with_mt))
+    if direct_sets:
+        # landing sets of the source dtype: free again as soon as the GPU bf16 cast has read them
+        st["direct"] = [mk(dtype_a, dtype_t), mk(dtype_a, dtype_t)]
+    if host_sets:
+        # slabs prepared by the host cores (bf16 pack of a padded batch, or rows of a shard): pinned staging
+        # on the host (ping-pong) and landing buffers on the device (ping-pong, released when the slab's
+        # forward is done)
+        def mk_host():
+            return dict(a=torch.empty((ea,), dtype=host_dtype).pin_memory(),
+                        t=torch.empty((et,), dtype=host_dtype).pin_memory(),
+                        sent=torch.cuda.Event())
+        st["host16"] = [mk_host(), mk_host()]
+        st["dev16"] = [mk(host_dtype, host_dtype), mk(host_dtype, host_dtype)]
+    _STAGING[key] = st
     return st
 
 
@@ -363,6 +388,9 @@ def _run_pipeline(model, dev, B: int, slabs: List[_Slab], d_a: int, d_t: int, dt
                 ev0.record(copy)
             buf["a"][: na * d_a].copy_(src_a, non_blocking=True)
             buf["t"][: nt * d_t].copy_(src_t, non_blocking=True)
+            STATS["h2d_bytes"] += src_a.numel() * src_a.element_size() + src_t.numel() * src_t.element_size()
+            STATS["slabs"] += 1
+            STATS["host_cast_slabs"] += 1 if s.host_cast else 0
             if s.utt is None:
                 if mask_a is not None:
                     buf["ma"][:na].copy_(mask_a[s.lo:s.hi].view(-1), non_blocking=True)
@@ -458,6 +486,7 @@ def _run_pipeline(model, dev, B: int, slabs: List[_Slab], d_a: int, d_t: int, dt
         return logits, beta, z
 
     try:
+        STATS["calls"] += 1
         return run_slabs()
     except BaseException as e:
         failure.append(e)
@@ -466,10 +495,261 @@ def _run_pipeline(model, dev, B: int, slabs: List[_Slab], d_a: int, d_t: int, dt
         raise
 
 
+class TwoEndedPlan:
+    """The slabs of a dense batch, claimed from both ends: `next` (the copy side: fp32 slabs in order, or a slab
+    the host side has finished) and `claim_back` (the host side: slabs to pre-cast, last first).  Every slab is
+    handed out exactly once; the host side stops claiming when the slabs left are fewer than the copy side clears
+    during one conversion (both rates measured as the plan runs), so the batch does not end waiting for the host.
+    Thread-safe; no CUDA in here (tests/test_sharding_cpu.py drives it with plain threads)."""
+
+    def __init__(self, n_slabs: int):
+        import threading
+        from collections import deque
+        self.cv = threading.Condition()
+        self.front, self.back = 0, n_slabs
+        self.ready = deque()         # (slab, k) converted by the host side, not yet sent
+        self.busy = False            # the host side holds a claimed slab it has not published yet
+        self.failure = None
+        self.t_pack = None           # seconds per conversion (last)
+        self.t_step = None           # seconds between decisions of the copy side (running mean)
+        self._last = None
+
+    def claim_back(self):
+        """-> slab index for the host side, or None when it should stop."""
+        import math
+        with self.cv:
+            left = self.back - self.front
+            if self.t_pack is None or self.t_step is None:
+                guard = 2
+            else:
+                guard = max(1, math.ceil(self.t_pack / max(self.t_step, 1e-4)))
+            if left <= guard or self.failure is not None:
+                return None
+            self.back -= 1
+            self.busy = True
+            return self.back
+
+    def publish(self, slab: int, k: int, seconds: float) -> None:
+        with self.cv:
+            self.t_pack = seconds
+            self.ready.append((slab, k))
+            self.busy = False
+            self.cv.notify_all()
+
+    def host_done(self, failure=None) -> None:
+        with self.cv:
+            if failure is not None and self.failure is None:
+                self.failure = failure
+            self.busy = False
+            self.cv.notify_all()
+
+    def next(self):
+        """-> (slab, k) for the copy side: k >= 0 = the k-th slab the host side converted, k = -1 = send it as it
+        is; None when every slab has been handed out.  Blocks while the host side still holds a slab."""
+        import time
+        with self.cv:
+            while True:
+                if self.failure is not None:
+                    raise self.failure
+                if self.ready:
+                    item = self.ready.popleft()
+                    break
+                if self.front < self.back:
+                    item = (self.front, -1)
+                    self.front += 1
+                    break
+                if not self.busy:
+                    return None
+                self.cv.wait(0.05)
+            now = time.perf_counter()
+            if self._last is not None:
+                dt = now - self._last
+                self.t_step = dt if self.t_step is None else 0.5 * (self.t_step + dt)
+            self._last = now
+            return item
+
+
+def _run_dense_dynamic(model, dev, h_a, h_t, mask_a, mask_t, slab: int, out_device, threads: int, wait: bool,
+                       trace: Optional[list] = None):
+    """forward_from_host's default engine for a dense fp32 batch (host_cast_every="auto"): the copy engine and the
+    host cores work through the slabs FROM BOTH ENDS and meet wherever their speeds put them.
+
+      * The main thread sends fp32 slabs from the front of the batch, as they are, paced by the copy engine (it keeps
+        two copies queued and blocks on the older one before deciding what to send next).
+      * A worker thread converts slabs to bf16 from the BACK of the batch into pinned staging
+        (hriemo_host_pack_bf16: half the bytes cross PCIe); a slab it has finished is sent next, ahead of the
+        next fp32 one (`TwoEndedPlan`).
+    The share of pre-cast slabs thereby follows what the process actually has: host threads (16 threads convert a
+    512-utterance slab in ~8 ms, 2 threads in ~60 ms) and PCIe bandwidth (55 GB/s alone, ~23 GB/s per GPU when the
+    ranks of one box share switch uplinks: DESIGN sec. 7) -- the fixed "every 2nd slab, only with >= 8 threads"
+    plan switched the pre-cast off exactly where H2D was the bound.  Slabs are independent and both casts round to
+    nearest even, so the results do not depend on which slabs the host converted (bit-identical, tested)."""
+    import threading
+    import time
+    from collections import deque
+
+    B, T_a, d_a = h_a.shape
+    T_t, d_t = h_t.shape[1], h_t.shape[2]
+    bounds = [(s, min(B, s + slab)) for s in range(0, B, slab)]
+    n_sl = len(bounds)
+    st = _staging(dev, h_a.dtype, h_t.dtype, torch.bfloat16, slab * T_a * d_a, slab * T_t * d_t, slab * T_a, slab * T_t,
+                  True, True, mask_a is not None, mask_t is not None)
+    main = torch.cuda.current_stream(dev)
+    copy = st["copy"]
+    plan = TwoEndedPlan(n_sl)
+    host_enq = [threading.Event() for _ in range(n_sl)]   # k-th host-prepared slab: its copy has been enqueued
+
+    def prepare():
+        k = 0
+        try:
+            while True:
+                i = plan.claim_back()
+                if i is None:
+                    break
+                hb = st["host16"][k % 2]
+                if k >= 2:
+                    host_enq[k - 2].wait()        # the copy that last read this host set has been ENQUEUED ...
+                    if plan.failure is not None:
+                        break
+                hb["sent"].synchronize()          # ... and is done
+                t0 = time.perf_counter()
+                lo, hi = bounds[i]
+                ops.host_pack_bf16(h_a[lo:hi], hb["a"], T_a, threads=threads)
+                ops.host_pack_bf16(h_t[lo:hi], hb["t"], T_t, threads=threads)
+                plan.publish(i, k, time.perf_counter() - t0)
+                k += 1
+            plan.host_done()
+        except BaseException as e:   # surfaced on the main thread
+            plan.host_done(e)
+
+    worker = threading.Thread(target=prepare, daemon=True)
+    n_direct = [0]
+    n_host = [0]
+    copied_events = []
+
+    def next_stage():
+        """-> (slab index, device set, host-converted?) of the next slab to compute, its copies enqueued; None when
+        every slab is out."""
+        if len(copied_events) >= 2:
+            copied_events[-2].synchronize()       # pace the decisions by the copy engine: two copies queued at most
+        item = plan.next()
+        if item is None:
+            return None
+        i, k = item
+        lo, hi = bounds[i]
+        n = hi - lo
+        na, nt = n * T_a, n * T_t
+        if k >= 0:
+            hb, buf = st["host16"][k % 2], st["dev16"][n_host[0] % 2]
+            n_host[0] += 1
+            src_a, src_t = hb["a"][: na * d_a], hb["t"][: nt * d_t]
+        else:
+            hb, buf = None, st["direct"][n_direct[0] % 2]
+            n_direct[0] += 1
+            src_a, src_t = h_a[lo:hi].view(-1), h_t[lo:hi].view(-1)
+        with torch.cuda.stream(copy):
+            copy.wait_event(buf["consumed"])      # the slab that last used this device set is done with it
+            if trace is not None:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record(copy)
+            buf["a"][: na * d_a].copy_(src_a, non_blocking=True)
+            buf["t"][: nt * d_t].copy_(src_t, non_blocking=True)
+            STATS["h2d_bytes"] += src_a.numel() * src_a.element_size() + src_t.numel() * src_t.element_size()
+            STATS["slabs"] += 1
+            STATS["host_cast_slabs"] += 1 if k >= 0 else 0
+            if mask_a is not None:
+                buf["ma"][:na].copy_(mask_a[lo:hi].view(-1), non_blocking=True)
+            if mask_t is not None:
+                buf["mt"][:nt].copy_(mask_t[lo:hi].view(-1), non_blocking=True)
+            if hb is not None:
+                hb["sent"].record(copy)
+            if trace is not None:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record(copy)
+                trace.append(dict(slab=i, n=n, T_a=T_a, T_t=T_t, host_cast=k >= 0, copy0=ev0, copy1=ev1))
+            ev = torch.cuda.Event()
+            ev.record(copy)
+            buf["copied"].record(copy)
+        copied_events.append(ev)
+        if k >= 0:
+            host_enq[k].set()
+        return i, buf, k >= 0
+
+    to_host = torch.device(out_device).type == "cpu"
+    outs = {}
+    host_out = None
+
+    def emit(i, res):
+        nonlocal host_out
+        lo = bounds[i][0]
+        if not to_host:
+            outs[i] = res
+            return
+        if host_out is None:
+            host_out = [torch.empty((B,) + tuple(r.shape[1:]), dtype=r.dtype, pin_memory=True) for r in res]
+        for dst, r in zip(host_out, res):
+            dst[lo:lo + r.shape[0]].copy_(r, non_blocking=True)   # D2H on the compute stream, behind this slab
+
+    try:
+        worker.start()
+        pending = deque()
+        for _ in range(2):
+            nxt = next_stage()
+            if nxt is not None:
+                pending.append(nxt)
+        while pending:
+            i, buf, from_host = pending.popleft()
+            lo, hi = bounds[i]
+            n = hi - lo
+            main.wait_event(buf["copied"])
+            if trace is not None:
+                k0 = torch.cuda.Event(enable_timing=True)
+                k0.record(main)
+            ma = None if mask_a is None else buf["ma"][: n * T_a].view(n, T_a).clone()
+            mt = None if mask_t is None else buf["mt"][: n * T_t].view(n, T_t).clone()
+            va = buf["a"][: n * T_a * d_a].view(n, T_a, d_a)
+            vt = buf["t"][: n * T_t * d_t].view(n, T_t, d_t)
+            if not from_host:
+                # fp32 features are only read by the bf16 cast: after it the staging set is free again
+                xa = E.to_seq(va, "h_a").x.view(n, T_a, -1)
+                xt = E.to_seq(vt, "h_t").x.view(n, T_t, -1)
+                buf["consumed"].record(main)
+                emit(i, model(xa, xt, ma, mt)[:3])
+            else:
+                # bf16 landed on the device: the model reads it in place; the set is free after the forward
+                emit(i, model(va, vt, ma, mt)[:3])
+                buf["consumed"].record(main)
+            if trace is not None:
+                k1 = torch.cuda.Event(enable_timing=True)
+                k1.record(main)
+                for row in trace:
+                    if row["slab"] == i:
+                        row["comp0"], row["comp1"] = k0, k1
+            nxt = next_stage()
+            if nxt is not None:
+                pending.append(nxt)
+        worker.join()
+        STATS["calls"] += 1
+    except BaseException as e:
+        plan.host_done(e)
+        for ev in host_enq:
+            ev.set()          # never leave the worker waiting on the main thread
+        raise
+    if to_host:
+        if not wait:
+            done = torch.cuda.Event()
+            done.record(main)
+            return PendingResult(host_out, done)
+        main.synchronize()
+        return tuple(host_out)
+    order = sorted(outs)
+    return tuple(torch.cat([outs[i][j] for i in order]).to(out_device) for j in range(3))
+
+
 @torch.no_grad()
 def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optional[torch.Tensor] = None,
                       mask_t: Optional[torch.Tensor] = None, device="cuda", slab: int = 512,
-                      out_device="cpu", host_cast_every: Optional[int] = None, ramp: bool = False, bucket: bool = False,
+                      out_device="cpu", host_cast_every=None, ramp: bool = False, bucket: bool = False,
                       trace: Optional[list] = None, wait: bool = True):
     """model(h_a, h_t, mask_a, mask_t) for HOST tensors with copy/compute overlap.
 
@@ -477,9 +757,12 @@ def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optio
     allocated or freed per slab for the inputs) on a side stream while earlier slabs compute:
       * fp32 slabs are copied as they are and cast to bf16 on the GPU; their staging set is free again
         as soon as the cast has read it;
-      * every `host_cast_every`-th slab (0 = never; default `default_host_cast_every()`: 2 with at least 8
-        host threads for this process, else 0) is instead converted to bf16 by the host cores
-        (hriemo_host_pack_bf16 in a worker thread) into pinned bf16 staging and copied at half the
+      * host_cast_every=None / "auto" (default; dense fp32 batches of three or more slabs): the host cores
+        convert slabs to bf16 from the BACK of the batch while the copy engine sends fp32 slabs from the
+        front, and they meet wherever their speeds put them (`_run_dense_dynamic`); what crossed PCIe is
+        accumulated in `pipeline.STATS`;
+      * host_cast_every=k (an int; 0 = never): the fixed plan -- every k-th slab is converted to bf16 by the
+        host cores (hriemo_host_pack_bf16 in a worker thread) into pinned bf16 staging and copied at half the
         bytes.  A step is bounded by the 55 GB/s H2D copy of the fp32 features (7.1 GB at the
         north-star batch); with every second slab pre-cast the copy drops under the compute time.
         The rounding is the same round-to-nearest-even as the GPU cast: results are bit-identical.
@@ -510,7 +793,9 @@ def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optio
     mask_a = None if mask_a is None else mask_a.to(torch.bool).contiguous()
     mask_t = None if mask_t is None else mask_t.to(torch.bool).contiguous()
     threads = max(1, torch.get_num_threads())
-    if host_cast_every is None:
+    if host_cast_every is None or host_cast_every == "auto":
+        if early and not bucket and not ramp and (B + slab - 1) // slab >= 3:
+            return _run_dense_dynamic(model, dev, h_a, h_t, mask_a, mask_t, slab, out_device, threads, wait, trace)
         host_cast_every = default_host_cast_every(threads)
     mask_a_dev = mask_t_dev = None
 

@@ -259,10 +259,12 @@ int hriemo_scatter_rows_f32(const float* in, const int32_t* utt, float* out, int
  * hriemo_gather_utterances_bf16 for a padded fp32 batch that lives in host memory, written as bf16 into
  * (pinned) staging memory by `n_threads` C++ threads: dst[i, t, :] = bf16_rne(src[utt[i], t, :]) for
  * t < min(lens[i], T_in, T_out), zero elsewhere.  utt NULL = identity, lens NULL = T_in for everyone.
- * Rounding is round-to-nearest-even like the GPU cast, so results are bit-identical to it. */
+ * n_src = utterances the source batch holds: every utt[i] (or i) must lie in [0, n_src), checked before any
+ * row is touched (HRIEMO_ERR_INVALID otherwise).  Rounding is round-to-nearest-even like the GPU cast
+ * (AVX-512 integer path with non-temporal stores where the CPU has it), so results are bit-identical to it. */
 int hriemo_host_pack_bf16(const float* src, int64_t ld_src, int64_t T_in, int64_t cols, const int32_t* utt,
                           const int32_t* lens, void* dst_bf16, int64_t ld_dst, int64_t T_out, int64_t n,
-                          int32_t n_threads);
+                          int64_t n_src, int32_t n_threads);
 
 /* ---------------------------------------------------- packed feature shards ----
  * The on-disk side of the step before the path.  The reference keeps one torch

@@ -89,6 +89,20 @@ def test_host_pack_matches_torch_cast_and_trims():
             assert bool((out[i, keep:] == 0).all())
     with pytest.raises(Exception):
         ops.host_pack_bf16(x, torch.empty(10, dtype=torch.bfloat16), T)        # destination too small
+    # NaN payloads become the canonical bf16 NaN of the GPU cast; a row count that is not a multiple of 16 and an
+    # unaligned destination exercise the vector path's tail and its cached-store form
+    y = torch.randn(3, 5, 40, generator=g)
+    y[1, 2, 7] = float("nan")
+    dst = torch.empty(3 * 5 * 40 + 8, dtype=torch.bfloat16)
+    out = ops.host_pack_bf16(y, dst[3:], 5, threads=1)
+    want = y.to(torch.bfloat16)
+    ok = torch.isnan(want)
+    assert torch.equal(out.view(torch.int16)[~ok], want.view(torch.int16)[~ok]) and bool(torch.isnan(out[ok]).all())
+    # an utterance index outside the source batch is refused by the library itself (ABI check, not only the wrapper)
+    from hriemo import lib
+    bad = torch.tensor([0, 9], dtype=torch.int32)
+    rc = lib.load().hriemo_host_pack_bf16(x.data_ptr(), d, T, d, bad.data_ptr(), None, dst.data_ptr(), d, 1, 2, B, 1)
+    assert rc != 0 and b"outside the source batch" in lib.load().hriemo_last_error()
 
 
 @pytest.mark.parametrize("name", ["cfg2_iemocap_ragged", "ns_500x64_ragged", "cfg3_mosei_default"])

@@ -231,13 +231,18 @@ def test_forward_from_host_equals_device_forward(name, slab):
     model, ins = G.build_fusion(fx)
     model = model.to(DEV)
     host = [None if x is None else x.clone().pin_memory() for x in (list(ins) + [None, None])[:4]]
-    for _ in range(2):  # second call reuses the cached staging buffers
-        lo, be, z = pipeline.forward_from_host(model, *host, device=DEV, slab=slab)
     ref = model(*[G.to_dev(x, DEV) for x in ins])
     torch.cuda.synchronize()
-    assert lo.device.type == "cpu"
-    # same kernels on the same rows; only the slab boundaries differ
-    assert torch.equal(lo, ref[0].cpu()) and torch.equal(be, ref[1].cpu()) and torch.equal(z, ref[2].cpu())
+    # default plan = "auto" (copy engine from the front, host cast from the back: pipeline.TwoEndedPlan) when the
+    # batch has three or more slabs; the fixed plans with every slab / no slab pre-cast by the host; one thread
+    for kw in ({}, {}, dict(host_cast_every=1), dict(host_cast_every=0), dict(host_cast_every="auto")):
+        pipeline.reset_stats()
+        lo, be, z = pipeline.forward_from_host(model, *host, device=DEV, slab=slab, **kw)   # repeated calls reuse the staging sets
+        assert lo.device.type == "cpu"
+        # same kernels on the same rows; only the slab boundaries (and who cast a slab to bf16) differ
+        assert torch.equal(lo, ref[0].cpu()) and torch.equal(be, ref[1].cpu()) and torch.equal(z, ref[2].cpu()), kw
+        B = host[0].shape[0]
+        assert pipeline.STATS["slabs"] == (B + min(slab, B) - 1) // min(slab, B) and pipeline.STATS["h2d_bytes"] > 0
 
 
 def test_full_size_properties_north_star():
@@ -349,7 +354,7 @@ def test_forward_from_host_two_calls_in_flight():
         batches.append([x.pin_memory() for x in (h_a, h_t, m_a, m_t)])
     want = [[o.cpu() for o in model(*[x.to(DEV) for x in b])] for b in batches]
     torch.cuda.synchronize()
-    for kw in (dict(slab=2, host_cast_every=2), dict(slab=3, host_cast_every=1), dict(slab=4, bucket=True)):
+    for kw in (dict(slab=2, host_cast_every=2), dict(slab=3, host_cast_every=1), dict(slab=4, bucket=True), dict(slab=2)):
         pend, got = None, []
         for b in batches:
             nxt = pipeline.forward_from_host(model, *b, device=DEV, wait=False, **kw)

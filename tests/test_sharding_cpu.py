@@ -112,3 +112,60 @@ def test_bench_training_leg_never_fails_the_bench():
         pytest.skip("error path: CPU-only check")
     rec = bench.train_step_leg(batch=4, timeout_s=120)
     assert set(rec) == {"error"} and rec["error"]
+
+
+@pytest.mark.parametrize("n_slabs,t_copy,t_pack", [(8, 0.004, 0.002), (8, 0.002, 0.02), (3, 0.002, 0.001), (1, 0.001, 0.001),
+                                                   (16, 0.003, 0.004)])
+def test_two_ended_plan_hands_every_slab_out_once(n_slabs, t_copy, t_pack):
+    """forward_from_host's default plan: the copy side takes slabs from the front, the host side converts from the
+    back; whatever their speeds, every slab is handed out exactly once, converted slabs are sent under the index the
+    host side gave them, and the batch does not end with a long wait for the host."""
+    import threading
+    import time
+
+    from hriemo import pipeline
+
+    plan = pipeline.TwoEndedPlan(n_slabs)
+    packed = []
+
+    def host():
+        k = 0
+        while True:
+            i = plan.claim_back()
+            if i is None:
+                break
+            time.sleep(t_pack)
+            packed.append((i, k))
+            plan.publish(i, k, t_pack)
+            k += 1
+        plan.host_done()
+
+    th = threading.Thread(target=host)
+    th.start()
+    sent = []
+    t_last_front = None
+    while True:
+        item = plan.next()
+        if item is None:
+            break
+        sent.append(item)
+        time.sleep(t_copy if item[1] < 0 else t_copy / 2)
+    th.join()
+    assert sorted(i for i, _ in sent) == list(range(n_slabs))
+    assert sorted(x for x in sent if x[1] >= 0) == sorted(packed)
+    fronts = [i for i, k in sent if k < 0]
+    assert fronts == sorted(fronts) and (not fronts or fronts[0] == 0)
+    if n_slabs >= 8 and t_pack <= t_copy:
+        assert len(packed) >= n_slabs // 2 - 1      # a fast host takes about half or more
+    if t_pack >= 5 * t_copy:
+        assert len(packed) <= 2                     # a slow host only what it can finish in time
+
+
+def test_two_ended_plan_surfaces_a_host_failure():
+    from hriemo import pipeline
+
+    plan = pipeline.TwoEndedPlan(4)
+    assert plan.claim_back() == 3
+    plan.host_done(RuntimeError("pack failed"))
+    with pytest.raises(RuntimeError, match="pack failed"):
+        plan.next()
