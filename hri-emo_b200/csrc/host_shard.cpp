@@ -131,16 +131,26 @@ extern "C" int hriemo_shard_open(const char* path, void** handle) {
   memcpy(&s->h, m, sizeof(ShardHeader));
   const ShardHeader& h = s->h;
   s->elem = h.dtype == 1 ? 2 : 4;
+  // every size below is a product / sum of 64-bit fields a corrupt or crafted file controls: overflow-checked, so a
+  // wrapped value can never pass the bounds test and send read_range outside the mapping
+  uint64_t sz_index = 0, sz_audio = 0, sz_text = 0;
   bool ok = memcmp(h.magic, "HRIEMOS1", 8) == 0 && h.version == 1 && (h.dtype == 1 || h.dtype == 2) && h.d_a > 0 &&
-            h.d_t > 0 && h.file_bytes == s->bytes && section_ok(*s, h.off_index, h.n_utt * sizeof(ShardIndex)) &&
-            section_ok(*s, h.off_audio, h.rows_a * h.d_a * s->elem) && section_ok(*s, h.off_text, h.rows_t * h.d_t * s->elem) &&
-            section_ok(*s, h.off_mask_a, h.rows_a) && section_ok(*s, h.off_mask_t, h.rows_t) &&
-            section_ok(*s, h.off_meta, h.meta_bytes);
+            h.d_t > 0 && h.file_bytes == s->bytes &&
+            !__builtin_mul_overflow(h.n_utt, static_cast<uint64_t>(sizeof(ShardIndex)), &sz_index) &&
+            !__builtin_mul_overflow(h.rows_a, static_cast<uint64_t>(h.d_a), &sz_audio) &&
+            !__builtin_mul_overflow(sz_audio, static_cast<uint64_t>(s->elem), &sz_audio) &&
+            !__builtin_mul_overflow(h.rows_t, static_cast<uint64_t>(h.d_t), &sz_text) &&
+            !__builtin_mul_overflow(sz_text, static_cast<uint64_t>(s->elem), &sz_text) &&
+            section_ok(*s, h.off_index, sz_index) && section_ok(*s, h.off_audio, sz_audio) &&
+            section_ok(*s, h.off_text, sz_text) && section_ok(*s, h.off_mask_a, h.rows_a) &&
+            section_ok(*s, h.off_mask_t, h.rows_t) && section_ok(*s, h.off_meta, h.meta_bytes);
   if (ok) {
     s->index = reinterpret_cast<const ShardIndex*>(s->base + h.off_index);
     for (uint64_t i = 0; i < h.n_utt && ok; ++i) {
       const ShardIndex& e = s->index[i];
-      ok = e.row_a + e.len_a <= h.rows_a && e.row_t + e.len_t <= h.rows_t && e.len_a <= h.max_len_a && e.len_t <= h.max_len_t;
+      // len <= rows first, then row <= rows - len: no sum that could wrap
+      ok = e.len_a <= h.rows_a && e.row_a <= h.rows_a - e.len_a && e.len_t <= h.rows_t && e.row_t <= h.rows_t - e.len_t &&
+           e.len_a <= h.max_len_a && e.len_t <= h.max_len_t;
     }
   }
   if (!ok) {

@@ -3,18 +3,38 @@
 Same signatures, outputs, dtypes and padding conventions as
   collate_seq_batch(batch, loss_type)   scripts/fusion/train_fusion_seq_level_decoder.py:191-232   (IEMOCAP)
   collate_seq_batch(batch)              scripts/infer/mosei_eval_infer.py:128-147                   (MOSEI)
--- zero-pad every utterance to the batch maximum, masks default to True = PAD -- but the padded tensors are
-allocated in page-locked memory (torch's caching host allocator), so hriemo.pipeline.forward_from_host and a
-plain `.to(device, non_blocking=True)` copy them asynchronously.  Pass as `collate_fn=` to a DataLoader."""
+-- zero-pad every utterance to the batch maximum, masks default to True = PAD.  Pass as `collate_fn=` to a DataLoader.
+
+Pinning.  Called in the MAIN process (num_workers=0, or a collate applied by hand) the padded tensors are allocated
+in page-locked memory (torch's caching host allocator), so hriemo.pipeline.forward_from_host and a plain
+`.to(device, non_blocking=True)` copy them asynchronously.  Inside a DataLoader WORKER process (the reference runs
+num_workers=4, train_fusion_seq_level_decoder.py:275-282) nothing is pinned: a page-locked allocation needs a CUDA
+context, which a forked worker must not create ("Cannot re-initialize CUDA in forked subprocess"), and the property
+would be lost anyway when the batch travels back through shared memory.  There the main process pins:
+`DataLoader(..., num_workers=4, collate_fn=collate_seq_batch, pin_memory=True)` (torch's pin thread), or
+`pin_batch(batch)` below."""
 from __future__ import annotations
 
 import torch
+from torch.utils.data import get_worker_info
+
+
+def _in_worker() -> bool:
+    return get_worker_info() is not None
 
 
 def _pinned(shape, dtype, fill):
-    pin = torch.cuda.is_available()
+    pin = (not _in_worker()) and torch.cuda.is_available()
     t = torch.empty(shape, dtype=dtype, pin_memory=pin)
     return t.fill_(fill)
+
+
+def pin_batch(batch):
+    """Main-process pin step for batches collated in worker processes: every tensor of the tuple that is not yet
+    page-locked is copied into pinned memory (no-op without a CUDA device)."""
+    if not torch.cuda.is_available():
+        return batch
+    return tuple(x.pin_memory() if isinstance(x, torch.Tensor) and not x.is_pinned() else x for x in batch)
 
 
 def collate_seq_batch(batch, loss_type: str = "multi_label"):

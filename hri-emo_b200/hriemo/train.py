@@ -48,8 +48,9 @@ class Trainer:
     trainer = Trainer(model)                      # model on a CUDA device; its parameters move into the flat arena
     info = trainer.step(h_a, h_t, m_a, m_t, y)    # -> {"loss", "grad_norm", "clip", "logits", "beta"} (device tensors)
 
-    process_group / torch.distributed initialised: gradients are averaged over the ranks (DistributedDataParallel's
-    semantics) with one all-reduce of the arena before the clip.
+    process_group / torch.distributed initialised: DistributedDataParallel's semantics -- rank 0's parameters are
+    broadcast when the arena is built (after checking that every rank holds the same layout), and gradients are
+    averaged over the ranks with one all-reduce of the arena before the clip.
 
     graph=True: from the third step with the same input shapes on, the forward + backward + arena fill (~500 kernel
     launches, which at the reference's batch sizes take longer to enqueue from Python than to run) are replayed from
@@ -93,6 +94,9 @@ class Trainer:
                 view = self.params[o:o + n].view(p.shape)
                 view.copy_(p.data)
                 p.data = view                          # the module's tensors ARE the arena from here on
+        if self.distributed:
+            self._sync_initial_state()
+        self.allreduce_events = None                   # a list -> (start, end) CUDA events of every all-reduce (benchmarks)
         self.step_count = 0
         self.use_graph = graph
         self._graph = None
@@ -101,6 +105,27 @@ class Trainer:
         self._static_in = None
         self._graph_out = None
         invalidate_prepared(model)
+
+    def _sync_initial_state(self) -> None:
+        """DistributedDataParallel's contract at construction: every rank starts from rank 0's parameters.  Only the
+        gradients are exchanged afterwards, so replicas built from different seeds or checkpoints would otherwise
+        train apart silently.  The arena layout (names, sizes) must be the same on every rank: checked first.
+        The AdamW moments start at zero everywhere; on a resume, restore `exp_avg`, `exp_avg_sq` and `step_count`
+        identically on every rank (they are never exchanged)."""
+        import torch.distributed as dist
+
+        world = dist.get_world_size(self.process_group)
+        if world == 1:
+            return
+        sizes = torch.tensor([self.numel, len(self.slots)], dtype=torch.int64, device=self.params.device)
+        lo, hi = sizes.clone(), sizes.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.process_group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.process_group)
+        if not (torch.equal(lo, sizes) and torch.equal(hi, sizes)):
+            raise L.HriemoError(f"Trainer: the ranks hold different models (arena {self.numel} elements / {len(self.slots)} "
+                                f"tensors here; min {lo.tolist()}, max {hi.tolist()} over the ranks)")
+        dist.broadcast(self.params, src=dist.get_global_rank(self.process_group, 0) if self.process_group is not None else 0,
+                       group=self.process_group)
 
     def gradient(self, name: str) -> torch.Tensor:
         """View of one parameter's gradient in the arena (as of the last step, after the all-reduce, before the clip)."""
@@ -187,8 +212,15 @@ class Trainer:
         world = dist.get_world_size(self.process_group)
         if world == 1:
             return
+        ev = None
+        if self.allreduce_events is not None and t.is_cuda:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         if dist.get_backend(self.process_group) == "nccl":
             dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.process_group)
         else:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group)
             t.mul_(1.0 / world)
+        if ev is not None:
+            ev[1].record()
+            self.allreduce_events.append(ev)

@@ -118,7 +118,12 @@ def test_shard_reader_rejects_bad_files(tmp_path):
     shards.write_shard(path, _utterances(4, 8, 8, g))
     raw = open(path, "rb").read()
     for name, data in (("trunc", raw[:-10]), ("magic", b"NOTASHRD" + raw[8:]), ("tiny", raw[:50]),
-                       ("rows", raw[:32] + (10 ** 9).to_bytes(8, "little") + raw[40:])):
+                       ("rows", raw[:32] + (10 ** 9).to_bytes(8, "little") + raw[40:]),
+                       # sizes whose 64-bit products wrap: rows_a * d_a * elem == 0 (mod 2^64), n_utt * 32 == 128 (mod 2^64)
+                       ("wrap_rows", raw[:32] + (1 << 61).to_bytes(8, "little") + raw[40:]),
+                       ("wrap_utts", raw[:16] + ((1 << 59) + 4).to_bytes(8, "little") + raw[24:]),
+                       # an index entry whose row_a + len_a wraps past 2^64
+                       ("wrap_index", raw[:128] + ((1 << 64) - 1).to_bytes(8, "little") + raw[136:])):
         bad = str(tmp_path / name)
         open(bad, "wb").write(data)
         with pytest.raises(lib.HriemoError):
@@ -150,3 +155,50 @@ def test_collate_mirrors_the_reference_collates():
     for i, it in enumerate(items):
         assert not m_a2[i, :it[0].shape[0]].any() and bool(m_a2[i, it[0].shape[0]:].all())
         assert not m_t2[i, :it[2].shape[0]].any() and bool(m_t2[i, it[2].shape[0]:].all())
+
+
+class _ListDataset(torch.utils.data.Dataset):
+    def __init__(self, items):
+        self.items = items
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, i):
+        return self.items[i]
+
+
+def test_collate_in_dataloader_worker_processes(monkeypatch):
+    """The reference's loaders run the collate in worker PROCESSES (num_workers=4): there nothing may be pinned (a
+    page-locked allocation would need a CUDA context in a forked child) even when the parent sees a GPU; the batches
+    must equal the in-process collate's."""
+    from functools import partial
+
+    from hriemo import collate
+
+    g = torch.Generator().manual_seed(5)
+    items = _utterances(10, 8, 12, g)
+    data = [it + (torch.eye(4)[i % 4],) for i, it in enumerate(items)]
+    # pretend the parent process has a GPU: a worker must still not try to pin
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    seen_pin = []
+    real_empty = torch.empty
+
+    def spy_empty(*a, **kw):
+        seen_pin.append(bool(kw.get("pin_memory", False)))
+        kw["pin_memory"] = False
+        return real_empty(*a, **kw)
+
+    monkeypatch.setattr(collate, "_in_worker", lambda: True)
+    monkeypatch.setattr(torch, "empty", spy_empty)
+    collate.collate_seq_batch(data[:3], "multi_label")
+    assert seen_pin and not any(seen_pin)                      # worker context: pageable allocations only
+    monkeypatch.undo()
+    loader = torch.utils.data.DataLoader(_ListDataset(data), batch_size=4, shuffle=False, num_workers=2,
+                                         collate_fn=partial(collate.collate_seq_batch, loss_type="multi_label"))
+    got = list(loader)
+    assert len(got) == 3
+    for k, batch in enumerate(got):
+        want = collate.collate_seq_batch(data[4 * k:4 * k + 4], "multi_label")
+        assert all(torch.equal(a, b) for a, b in zip(batch, want))
+        assert collate.pin_batch(batch)[0].shape == want[0].shape

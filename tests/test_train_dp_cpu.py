@@ -48,6 +48,12 @@ def _worker(rank, world, port, shape, out_q):
 
         model, h_a, h_t, labels = _setup(_Patch(), *shape)
         lo, hi = shard_bounds(shape[0], rank, world)
+        if rank == 1:
+            # a replica that was built differently (other seed / checkpoint): the Trainer must start it from rank 0's
+            # parameters (DistributedDataParallel broadcasts module state at construction), or the ranks diverge
+            with torch.no_grad():
+                for p in model.parameters():
+                    p.add_(0.25)
         trainer = Trainer(model, lr=1e-3, max_norm=0.5)
         assert trainer.distributed
         for _ in range(2):
