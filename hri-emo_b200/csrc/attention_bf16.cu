@@ -31,6 +31,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 
@@ -205,7 +207,11 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       mbar_init(b_vfull + s * 8, 1);
       mbar_init(b_vempty + s * 8, 2);
     }
+#ifdef HRIEMO_ATTN_V3_SOFTMAX
     for (int s = 0; s < 4; ++s) mbar_init(b_pfull + s * 8, 128);
+#else
+    for (int s = 0; s < 4; ++s) mbar_init(b_pfull + s * 8, 4);   // one arrival per softmax warp (lane 0, after __syncwarp)
+#endif
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(base + L::TMEM_SLOT_OFF);
@@ -216,7 +222,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not lane == 0: cp.async.bulk.tensor takes uniform-register operands (see the issuers)
       uint32_t qcnt[2] = {0, 0};  // Q loads issued per query tile -> buffer and phase
       if constexpr (!PAIRED) {
         // K(g) then V(g), step by step; Q tiles at the start of an item
@@ -334,11 +340,28 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     // there, then S_t(g+2) into the S buffer PV_t(g) just consumed (same thread => in order).
     // The two tiles only meet at the shared K / V^T stages, whose "empty" barriers expect one
     // arrival from each issuer (a plain arrive when the tile does not exist for an item).
-    if (lane == 0) {
-      const int t = (warp == 1) ? 0 : 1;
+    //
+    // ONE lane runs the loop, and it is chosen with elect.sync, not `lane == 0`: tcgen05.mma / commit take their
+    // descriptors in UNIFORM registers, and only behind elect.sync does the compiler know that a single lane is
+    // active.  Behind `if (lane == 0)` it wrapped every MMA in an elect / 3 x R2UR.BROADCAST / branch-back loop
+    // (for lanes that might hold different values) -- ~75 cycles per instruction by the pipeline trace, 1 100 cycles
+    // of issuing per 64-key step for 384 cycles of tensor work, which made the ISSUER the critical path of the
+    // kernel (the softmax warpgroups sat waiting for S: the v4 softmax loop alone changed nothing).  The tile index
+    // is a compile-time constant (one copy of the loop per issuer warp) and the tensor-memory base is the
+    // constant 0, so the descriptors are formed by the uniform datapath and the MMAs issue back to back.
+    auto run_issuer = [&](auto tile_c) {
+      constexpr int t = decltype(tile_c)::value;
+      // This CTA allocates all 512 tensor-memory columns of its SM, so the allocation starts at column 0, lane 0:
+      // the base is the CONSTANT 0 (checked), not a value loaded from shared memory.
+      if (tmem_base != 0u) __trap();
+      constexpr uint32_t tmem_base_u = 0u;
+      auto wait_u = [&](uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); };
+      auto test_u = [&](uint32_t bar, uint32_t parity) -> bool { return mbar_test_wait(bar, parity); };
+      auto steps_u = [&](uint32_t item) -> int { return steps_of(item); };
+      constexpr bool leader = true;
       constexpr uint32_t idesc_s = umma_idesc_bf16(A3_BQ, A3_BKV);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(A3_BQ, DH) | kUmmaBMajorMN;
-      const uint32_t tile_tmem = tmem_base + t * TILE_COLS;
+      const uint32_t tile_tmem = tmem_base_u + t * TILE_COLS;
       const uint64_t k_desc0 = umma_desc_sw128(sK);
       const uint64_t v_desc0 = umma_desc_mn_sw64(sV, L::V_GROUP);
       // does this tile exist for the item (general mode; in paired-head mode both tiles always do)
@@ -355,7 +378,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       // ---- S cursor (two flat steps ahead of the PV cursor)
       uint32_t s_g = 0, s_item = item_first, qcnt = 0;
       int s_f = 0;
-      int s_nk = s_item < item_last ? steps_of(s_item) : 0;
+      int s_nk = s_item < item_last ? steps_u(s_item) : 0;
       bool s_act = tile_active(s_item);
       // S of the cursor's flat step.  Non-blocking form: returns false, with nothing issued, unless the Q tile
       // (first key step of an item) and the K tile have landed.
@@ -364,32 +387,34 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         const uint32_t qslot = t * 2 + (qcnt & 1u);
         const bool act = s_act && mine(s_f);
         const int s_j = key_step(s_f);
-        ATRACE(t, s_g, 4);
+        if (leader) ATRACE(t, s_g, 4);
         if (blocking) {
-          if (act && s_j == 0) mbar_wait(b_qfull + qslot * 8, (qcnt >> 1) & 1u);
-          mbar_wait(b_kfull + ks * 8, kpar);
+          if (act && s_j == 0) wait_u(b_qfull + qslot * 8, (qcnt >> 1) & 1u);
+          wait_u(b_kfull + ks * 8, kpar);
         } else {
           // only the Q tile can be far away (it is loaded once the warpgroup has freed its buffer); a K tile is
           // in flight, and waiting for it here is what keeps S(g+2) right behind PV(g) on the long-key shapes
-          if (act && s_j == 0 && !mbar_test_wait(b_qfull + qslot * 8, (qcnt >> 1) & 1u)) return false;
-          mbar_wait(b_kfull + ks * 8, kpar);
+          if (act && s_j == 0 && !test_u(b_qfull + qslot * 8, (qcnt >> 1) & 1u)) return false;
+          wait_u(b_kfull + ks * 8, kpar);
         }
-        ATRACE(t, s_g, 5);
+        if (leader) ATRACE(t, s_g, 5);
         if (act) {
           tc_fence_after_sync();
           const uint64_t q_desc = umma_desc_sw128(sQ + qslot * L::Q_TILE);
           const uint64_t k_desc = k_desc0 + ((ks * L::K_STAGE) >> 4);
           const uint32_t d_tmem = tile_tmem + sbuf_of(s_g) * A3_BKV;
+          {
 #pragma unroll
-          for (int st = 0; st < DH / 16; ++st) {
-            umma_bf16(d_tmem, q_desc + (((st >> 2) * L::Q_CHUNK + (st & 3) * 32) >> 4),
-                      k_desc + (((st >> 2) * L::K_CHUNK + (st & 3) * 32) >> 4), idesc_s, st != 0);
+            for (int st = 0; st < DH / 16; ++st) {
+              umma_bf16(d_tmem, q_desc + (((st >> 2) * L::Q_CHUNK + (st & 3) * 32) >> 4),
+                        k_desc + (((st >> 2) * L::K_CHUNK + (st & 3) * 32) >> 4), idesc_s, st != 0);
+            }
+            umma_commit(b_sfull + (t * 2 + sbuf_of(s_g)) * 8);
+            umma_commit(b_kempty + ks * 8);
+            ATRACE(t, s_g, 6);
           }
-          umma_commit(b_sfull + (t * 2 + sbuf_of(s_g)) * 8);
-          umma_commit(b_kempty + ks * 8);
-          ATRACE(t, s_g, 6);
           if (s_j == s_nk - 1) ++qcnt;  // the Q buffer is released by the warpgroup after its epilogue
-        } else {
+        } else if (leader) {
           mbar_arrive(b_kempty + ks * 8);
         }
         ++s_g;
@@ -397,7 +422,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           s_f = 0;
           s_item += item_stride;
           s_act = s_item < item_last && tile_active(s_item);
-          s_nk = s_item < item_last ? steps_of(s_item) : 0;
+          s_nk = s_item < item_last ? steps_u(s_item) : 0;
         }
         return true;
       };
@@ -430,42 +455,44 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       auto wait_pumping = [&](uint32_t bar, uint32_t parity) {
         if constexpr (DEFER) {
           while (s_item < item_last && s_g < s_allowed) {
-            if (mbar_test_wait(bar, parity)) return;
+            if (test_u(bar, parity)) return;
             issue_s(false);
           }
         }
-        mbar_wait(bar, parity);
+        wait_u(bar, parity);
       };
       // ---- PV cursor
       uint32_t pcnt = 0, pv_item = item_first;
       int pv_f = 0;
-      int pv_nk = pv_item < item_last ? steps_of(pv_item) : 0;
+      int pv_nk = pv_item < item_last ? steps_u(pv_item) : 0;
       bool pv_act = tile_active(pv_item);
       for (uint32_t g = 0; pv_item < item_last; ++g) {
         const uint32_t vs = g % KS, vpar = (g / KS) & 1u;
-        ATRACE(t, g, 0);
+        if (leader) ATRACE(t, g, 0);
         wait_pumping(b_vfull + vs * 8, vpar);   // never wait without moving the S cursor
-        ATRACE(t, g, 1);
+        if (leader) ATRACE(t, g, 1);
         if (pv_act && mine(pv_f)) {
           const int pv_j = key_step(pv_f);
           const int rem = p.Tk - pv_j * A3_BKV;  // keys left from this step on (> 0)
           const uint32_t slot = t * 2 + (pcnt & 1u);
           wait_pumping(b_pfull + slot * 8, (pcnt >> 1) & 1u);   // P(g) needs S(g): keep the S cursor moving
-          ATRACE(t, g, 2);
+          if (leader) ATRACE(t, g, 2);
           ++pcnt;
           tc_fence_after_sync();
           const uint64_t v_desc = v_desc0 + ((vs * L::V_STAGE) >> 4);
           const uint32_t p_tmem = tile_tmem + sbuf_of(g) * A3_BKV;
+          {
 #pragma unroll
-          for (int st = 0; st < A3_BKV / 16; ++st) {
-            if (st * 16 < rem)  // P is zero beyond Tk: skip those K-steps (16 keys = 16 rows of 64 B)
-              umma_bf16_ts(tile_tmem + O_COL, p_tmem + st * 8, v_desc + ((st * 16 * 64) >> 4), idesc_pv,
-                           (pv_j | st) != 0);
+            for (int st = 0; st < A3_BKV / 16; ++st) {
+              if (st * 16 < rem)  // P is zero beyond Tk: skip those K-steps (16 keys = 16 rows of 64 B)
+                umma_bf16_ts(tile_tmem + O_COL, p_tmem + st * 8, v_desc + ((st * 16 * 64) >> 4), idesc_pv,
+                             (pv_j | st) != 0);
+            }
+            umma_commit(b_pvdone + slot * 8);
+            umma_commit(b_vempty + vs * 8);
+            ATRACE(t, g, 3);
           }
-          umma_commit(b_pvdone + slot * 8);
-          umma_commit(b_vempty + vs * 8);
-          ATRACE(t, g, 3);
-        } else {
+        } else if (leader) {
           mbar_arrive(b_vempty + vs * 8);
         }
         if constexpr (DEFER) {
@@ -478,9 +505,13 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           pv_f = 0;
           pv_item += item_stride;
           pv_act = pv_item < item_last && tile_active(pv_item);
-          pv_nk = pv_item < item_last ? steps_of(pv_item) : 0;
+          pv_nk = pv_item < item_last ? steps_u(pv_item) : 0;
         }
       }
+    };
+    if (elect_one()) {
+      if (warp == 1) run_issuer(std::integral_constant<int, 0>{});
+      else run_issuer(std::integral_constant<int, 1>{});
     }
   } else {
     // ===================== softmax warpgroups =====================
@@ -553,6 +584,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         cur_b = b;
       }
 
+#ifdef HRIEMO_ATTN_V3_SOFTMAX
       if (nk <= 2) release_q();   // short items: the producer needs the buffer back sooner (two items ahead)
       float m_run = -INFINITY;  // running reference maximum, in log2 units (score * scale * log2 e)
       float l_run = 0.0f;
@@ -640,9 +672,137 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if (wg_tid == 0) ATRACE(2 + wg, g + j, 6);
       }
 
+#else
+      // ---- v4 softmax loop.  Against the first form (kept under HRIEMO_ATTN_V3_SOFTMAX for A/B runs):
+      //  * the scores of step j+1 are fetched (wait S, tcgen05.ld issued) while the P stores of step j drain, so the
+      //    fixed latencies of a step (barrier wait, tensor-memory load, store drain, hand-off) overlap instead of adding up;
+      //  * no barrier wait per step for the PV two steps back: S(k) is issued behind PV(k-2) by the same thread, so
+      //    S(k) landed implies PV(k-2) retired, and PV(k-1) is only awaited when a rescale or the epilogue needs O;
+      //  * P is handed over with one mbarrier arrival per warp.
+      if (nk <= 2) release_q();   // short items: the producer needs the buffer back sooner (two items ahead)
+      float m_run = -INFINITY;  // running reference maximum, in log2 units (score * scale * log2 e)
+      float l_run = 0.0f;
+      uint32_t va[32], vb[32];
+      // the item's first scores
+      {
+        const uint32_t sbuf0 = paired ? (g >> 1) & 1u : g & 1u;
+        if (wg_tid == 0) ATRACE(2 + wg, g, 0);
+        mbar_wait(b_sfull + (wg * 2 + sbuf0) * 8, (sbuf0 ? scnt1 : scnt0) & 1u);
+        if (sbuf0) ++scnt1; else ++scnt0;
+        tc_fence_after_sync();
+        if (wg_tid == 0) ATRACE(2 + wg, g, 1);
+        tmem_ld32(t_tile + sbuf0 * A3_BKV, va);
+        if (p.Tk > 32) tmem_ld32(t_tile + sbuf0 * A3_BKV + 32, vb);
+      }
+      for (int j = 0; j < nk; ++j) {
+        // flat step of this tile's j-th key step: g + j, or g + 2 j + wg in paired-head mode (g is even there)
+        const uint32_t sbuf = paired ? ((g >> 1) + static_cast<uint32_t>(j)) & 1u : (g + static_cast<uint32_t>(j)) & 1u;
+        const uint32_t t_s = t_tile + sbuf * A3_BKV;
+        const int rem = p.Tk - j * A3_BKV;
+        const bool two = rem > 32;                   // second 32-key chunk holds a valid key
+        const bool masked = flags[j] != 0;           // warp-uniform
+        const float* cap_j = caps + j * A3_BKV;
+        tmem_ld_wait();
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 2);
+        if (masked) {
+          apply_caps(va, cap_j);
+          if (two) apply_caps(vb, cap_j + 32);
+        }
+        // ---- row maximum of this step.  Only the item's FIRST step needs it before the exponentials (it sets the
+        // reference maximum).  Later steps keep the reference unless the maximum grew by more than 2^TAU (lazy
+        // rescale), which is rare: they compute p = 2^(s - m_run) with the reference they have (SPECULATIVELY) while
+        // the maximum is formed on the ALU pipe next to the exponentials on the XU pipe, and check afterwards; the
+        // few steps that do need a rescale repair O / l and redo their exponentials before P is handed over.
+        auto row_max = [&]() {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          max4(m4, va);
+          if (two) max4(m4, vb);
+          return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;  // sc > 0
+        };
+        if (j == 0) m_run = row_max();     // (a real branch, j is warp-uniform: later steps must not wait for their maximum)
+        float neg_m = (m_run == -INFINITY) ? 0.0f : -m_run;
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 3);
+
+        // ---- p = 2^(s*scale - m), row sum, bf16 P into the first 32 columns of this S buffer; the two warpgroups
+        // take turns (named barriers 3 / 4) so that their exponentials do not collide on the quarter-rate XU pipe
+#ifndef HRIEMO_ATTN_NO_PINGPONG
+        asm volatile("bar.sync %0, 256;" ::"r"(3 + wg) : "memory");
+#endif
+        float l4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        uint32_t pk[16];
+        exp_pack(va, sc, neg_m, l4, pk);
+        tmem_st16(t_s, pk);
+        if (two) {
+          exp_pack(vb, sc, neg_m, l4, pk);
+          tmem_st16(t_s + 16, pk);
+        }
+#ifndef HRIEMO_ATTN_NO_PINGPONG
+        asm volatile("bar.arrive %0, 256;" ::"r"(4 - wg) : "memory");   // the other warpgroup's turn
+#endif
+        if (j > 0) {
+          const float tile_max = row_max();
+          const bool need = tile_max > m_run + A3_LAZY_TAU;
+          if (__any_sync(0xffffffffu, need)) {
+            // every PV of this tile must have retired: the latest one is PV(pv_issued - 1); the one before retired
+            // before this step's S landed (see above), so this wait can not be answered by a stale phase
+            const uint32_t kk = pv_issued - 1u;
+            mbar_wait(b_pvdone + (wg * 2 + (kk & 1u)) * 8, (kk >> 1) & 1u);
+            tc_fence_after_sync();
+            const float alpha = need ? ex2_approx(m_run - tile_max) : 1.0f;
+            if (need) m_run = tile_max;
+            l_run *= alpha;
+#pragma unroll 1
+            for (int c = 0; c < DH / 32; ++c) {
+              uint32_t v[32];
+              tmem_ld32(t_o + c * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st32(t_o + c * 32, v);
+            }
+            // this step's exponentials again, against the new reference (the scores are still in registers)
+            neg_m = (m_run == -INFINITY) ? 0.0f : -m_run;
+            l4[0] = l4[1] = l4[2] = l4[3] = 0.0f;
+            exp_pack(va, sc, neg_m, l4, pk);
+            tmem_st16(t_s, pk);
+            if (two) {
+              exp_pack(vb, sc, neg_m, l4, pk);
+              tmem_st16(t_s + 16, pk);
+            }
+          }
+        }
+        l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 4);
+        // ---- the next step's scores: wait for S(j+1) and issue its loads while the P stores drain
+        if (j + 1 < nk) {
+          const uint32_t nbuf = sbuf ^ 1u;
+          mbar_wait(b_sfull + (wg * 2 + nbuf) * 8, (nbuf ? scnt1 : scnt0) & 1u);
+          if (nbuf) ++scnt1; else ++scnt0;
+          tc_fence_after_sync();
+          tmem_ld32(t_tile + nbuf * A3_BKV, va);
+          if (p.Tk - (j + 1) * A3_BKV > 32) tmem_ld32(t_tile + nbuf * A3_BKV + 32, vb);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 5);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_pfull + (wg * 2 + (pv_issued & 1u)) * 8);
+        ++pv_issued;
+        if (j == 0 && nk > 2) release_q();
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 6);
+      }
+#endif
+
       // ---- epilogue: O / l -> bf16, staged in this item's (now dead) Q buffer and written with one
       // TMA store per warp; the 3-D tensor map (column, t, utterance) clips rows t >= Tq.
+#ifdef HRIEMO_ATTN_V3_SOFTMAX
       consume_pv(pv_issued);
+#else
+      {
+        const uint32_t kk = pv_issued - 1u;   // the item's last PV (its predecessor retired before the last S landed)
+        mbar_wait(b_pvdone + (wg * 2 + (kk & 1u)) * 8, (kk >> 1) & 1u);
+      }
+#endif
       tc_fence_after_sync();
       const float inv_l = 1.0f / l_run;  // l == 0 (every key masked) -> inf -> NaN like torch.softmax
       // what a backward pass needs to rebuild P: ln sum_k exp(s_k * scale); this thread's row is its TMEM lane
