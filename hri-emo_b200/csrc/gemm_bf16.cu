@@ -157,7 +157,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // one lane, chosen with elect.sync (not `lane == 0`): TMA and tcgen05 instructions take uniform-register
+    // operands, and only behind elect.sync does the compiler know a single lane is active -- otherwise it wraps
+    // each of them in an ELECT / R2UR.BROADCAST / branch-back loop (see csrc/attention_bf16.cu)
+    if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       for (int64_t tile = tile_first; tile < p.num_tiles; tile += tile_step) {
         const int m0 = static_cast<int>(tile / p.num_n_blocks) * TILE_M + static_cast<int>(rank) * BM;
@@ -179,7 +182,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && leader) {
+    if (leader && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
       uint32_t stage = 0, phase = 0;
       uint32_t it = 0;
@@ -251,8 +254,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     };
     uint32_t it = 0, slab_ctr = 0;
     const uint32_t tempty_leader = CTAS == 2 ? mapa_shared(bar_tempty, 0) : bar_tempty;
-    if (tma_resid && lane == 0 && tile_first < p.num_tiles && has_slab(tile_first, slab0))
-      prefetch_resid(tile_first, slab0, 0);
+    if (tma_resid && tile_first < p.num_tiles && has_slab(tile_first, slab0)) {
+      if (elect_one()) prefetch_resid(tile_first, slab0, 0);
+    }
     for (int64_t tile = tile_first; tile < p.num_tiles; tile += tile_step, ++it) {
       const uint32_t as = it & 1u;
       const uint32_t aphase = (it >> 1) & 1u;
@@ -290,7 +294,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (tma_resid) {
             mbar_wait(my_rbar + (slab_ctr & 1u) * 8, (slab_ctr >> 1) & 1u);  // residual box has landed
           } else {
-            if (lane == 0) bulk_wait_read<1>();  // the store issued two slabs ago has left this buffer
+            if (elect_one()) bulk_wait_read<1>();  // the store issued two slabs ago has left this buffer (same elected lane every time)
             __syncwarp();
           }
         }
@@ -367,7 +371,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           float f[32];
 #pragma unroll
           for (int i = 0; i < 16; ++i) { f[2 * i] = f2[i].x; f[2 * i + 1] = f2[i].y; }
-          if (hf == 0 && tma_resid && lane == 0) {
+          if (hf == 0 && tma_resid && elect_one()) {
             // Residual box of this warp's NEXT slab (same tile, or its first slab of this CTA's next
             // tile) -> the idle staging buffer.  Issued here, half a slab after the store that last
             // read that buffer, so that store has normally drained and the load has a full slab of
@@ -402,7 +406,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (bf16_out) {
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             tma_store_2d(&tm_c, buf, n, static_cast<int>(m_tile) + quad * 32);
             bulk_commit();
           }
@@ -417,7 +421,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         else mbar_arrive(bar_tempty + as * 8);
       }
     }
-    if (lane == 0) bulk_wait_all();  // staged tiles must be out before shared memory is released
+    __syncwarp();
+    if (elect_one()) bulk_wait_all();  // staged tiles must be out before shared memory is released
   }
 
   // ===================== teardown =====================
