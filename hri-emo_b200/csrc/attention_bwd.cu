@@ -678,13 +678,19 @@ static int launch_attn_bwd_lm(const AttnBwdParams& p, int B, cudaStream_t s) {
 
 using namespace hriemo;
 
+namespace hriemo {
+template <int DH>
+int launch_attn_bwd_tc(const hriemo_attn_bwd_args& a, cudaStream_t stream);   // attention_bwd_tc.cu
+}
+
 extern "C" int hriemo_attention_backward_bf16(const hriemo_attn_bwd_args* a, void* stream) {
   HRIEMO_REQUIRE(a != nullptr, "attention_backward: null args");
   HRIEMO_REQUIRE(a->q && a->k && a->v && a->out && a->d_out && a->lse && a->dsum && a->dq && a->dk && a->dv,
                  "attention_backward: null pointer");
   HRIEMO_REQUIRE(a->B > 0 && a->B <= 65535 && a->H > 0 && a->H <= 65535 && a->Tq > 0 && a->Tk > 0,
                  "attention_backward: bad shape B=%d H=%d Tq=%d Tk=%d", a->B, a->H, a->Tq, a->Tk);
-  HRIEMO_REQUIRE(a->impl >= 0 && a->impl <= 2, "attention_backward: impl=%d (0 ldmatrix tensor-core form, 1 FMA, 2 first tensor-core form)", a->impl);
+  HRIEMO_REQUIRE(a->impl >= 0 && a->impl <= 4,
+                 "attention_backward: impl=%d (0 / 3 tcgen05 form, 1 FMA, 2 first mma.sync form, 4 ldmatrix mma.sync form)", a->impl);
   HRIEMO_REQUIRE(a->kv_steps == nullptr || a->key_pad != nullptr, "attention_backward: kv_steps comes with key_pad");
   HRIEMO_REQUIRE(a->dh == 32 || a->dh == 64 || a->dh == 96 || a->dh == 128, "attention_backward: dh=%d not in {32, 64, 96, 128}",
                  a->dh);
@@ -703,6 +709,14 @@ extern "C" int hriemo_attention_backward_bf16(const hriemo_attn_bwd_args* a, voi
                                                                a->Tq, a->dh);
   int rc = check_launch("attention_backward (D)");
   if (rc) return rc;
+  if (a->impl == 0 || a->impl == 3) {   // the tcgen05 form (attention_bwd_tc.cu)
+    switch (a->dh) {
+      case 32: return launch_attn_bwd_tc<32>(*a, s);
+      case 64: return launch_attn_bwd_tc<64>(*a, s);
+      case 96: return launch_attn_bwd_tc<96>(*a, s);
+      default: return launch_attn_bwd_tc<128>(*a, s);
+    }
+  }
   AttnBwdParams p;
   p.q = static_cast<const bf*>(a->q); p.k = static_cast<const bf*>(a->k); p.v = static_cast<const bf*>(a->v);
   p.d_out = static_cast<const bf*>(a->d_out);

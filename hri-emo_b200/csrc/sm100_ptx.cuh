@@ -323,6 +323,19 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw64(uint32_t smem_addr, uint32
   d |= static_cast<uint64_t>(4) << 61;                 // SWIZZLE_64B
   return d;
 }
+// The same for the 128-byte-swizzle layout: groups of 64 columns; inside a group row k (128 B) sits at k * 128 B, 8-row
+// swizzle atoms of 1024 B stacked densely (SBO = 1024 B); consecutive column groups `group_bytes` apart (LBO).  This is
+// byte for byte the K-major SWIZZLE_128B tile a TMA box of 64 columns produces: one shared-memory tile can be read
+// K-major (contraction over its columns) and MN-major (contraction over its rows) by two descriptors.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t group_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>(group_bytes >> 4) << 16;  // LBO
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;         // SBO
+  d |= static_cast<uint64_t>(1) << 46;                 // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                 // SWIZZLE_128B
+  return d;
+}
 constexpr uint32_t kUmmaBMajorMN = 1u << 16;  // instruction-descriptor flag: B operand is MN-major
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {

@@ -649,8 +649,8 @@ def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: t
     """Backward of `attention` (the encoder's attention): q / k / v as in the forward (column slices are fine), out
     [B*Tq, H*dh] and lse [B, H, Tq] from attention(..., want_lse=True), d_out [B*Tq, H*dh].
     -> (dq [B*Tq, H*dh], dk [B*Tk, H*dh], dv [B*Tk, H*dh]) bf16; grads = (dq, dk, dv): existing views to write into.
-    impl: 0 = the ldmatrix tensor-core form (default), 1 = fp32-FMA loops over the same tiles (slow; validation),
-    2 = the first tensor-core form (scalar fragment loads, transposed tile copies; kept for A/B measurements)."""
+    impl: 0 (default) / 3 = the tcgen05 form (csrc/attention_bwd_tc.cu), 1 = fp32-FMA loops over mma.sync-sized tiles
+    (slow; validation), 2 = the first mma.sync form, 4 = the ldmatrix mma.sync form (kept for A/B measurements)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out"), (d_out, "d_out")):
         _chk2d(t, bf16, f"attention_backward {n}")
     d = H * dh

@@ -386,9 +386,10 @@ int hriemo_gate_stream_grad(const void* dh, int64_t lddh, int32_t L, const float
  * output `out`, its log-sum-exp `lse` and the output gradient d_out, writes dq [B*Tq, H*dh], dk and dv [B*Tk, H*dh]
  * (bf16; PAD keys receive zeros).  P is rebuilt as exp(scale * q.k - lse); dsum [B, H, Tq] (f32) is scratch that
  * receives rowsum(d_out o out).  Deterministic (no atomics): one pass owns dK / dV per key tile, one owns dQ per query
- * tile.  Warp-level mma.sync tensor-core instructions with ldmatrix(.trans) fragments, not yet tcgen05 (DESIGN.md
- * sec. 8).  impl: 0 = that form; 1 = the same tiles with fp32 FMA loops (slow; validation); 2 = the first tensor-core
- * form (scalar fragment loads, transposed tile copies; A/B measurements). */
+ * tile.  impl: 0 (default) / 3 = tcgen05 + TMEM + TMA (csrc/attention_bwd_tc.cu: 128-row tiles, S | dP side by side in
+ * tensor memory, P / dS written back over them as the A operand of the accumulating MMAs, step rows read as MN-major
+ * shared-memory operands); 1 = fp32 FMA loops (slow; validation); 2 = the first warp-level mma.sync form; 4 = the
+ * mma.sync form with ldmatrix(.trans) fragments (the round-1 kernel, kept for A/B measurements). */
 typedef struct hriemo_attn_bwd_args {
   const void* q;      int64_t ldq;    /* bf16, as in the forward */
   const void* k;      int64_t ldk;

@@ -136,14 +136,15 @@ def test_gate_blend_backward_kernels_match_autograd(B, T_a, L, d, masked):
 
 
 # ------------------------------------------------------------------ encoder attention backward
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2, 4])
 @pytest.mark.parametrize("B,H,Tq,Tk,dh,masked", [(3, 8, 100, 70, 96, True), (2, 4, 64, 64, 64, False), (2, 2, 37, 150, 32, True),
-                                                  (1, 2, 130, 20, 128, False), (2, 8, 300, 300, 96, True)])
+                                                  (1, 2, 130, 20, 128, False), (2, 8, 300, 300, 96, True),
+                                                  (2, 8, 500, 64, 96, True), (2, 8, 64, 500, 96, False), (3, 4, 300, 128, 64, True)])
 def test_attention_backward_matches_autograd(B, H, Tq, Tk, dh, masked, impl):
     """dq, dk, dv of the encoder attention (packed [Q|K|V] column slices as operands, LSE and O from the forward kernel)
     against torch autograd in float64 on the same bf16 operands.  P and dS are rounded to bf16 before the second GEMMs:
-    element-wise 2e-2 of the tensor's scale, whole-tensor relative error 1e-2.  impl: 0 = ldmatrix form (default), 1 = FMA
-    loops, 2 = first tensor-core form."""
+    element-wise 2e-2 of the tensor's scale, whole-tensor relative error 1e-2.  impl: 0 = the tcgen05 form (default;
+    csrc/attention_bwd_tc.cu), 1 = FMA loops, 2 = first mma.sync form, 4 = ldmatrix mma.sync form."""
     import math
 
     from hriemo import ops
