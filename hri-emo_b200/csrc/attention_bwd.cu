@@ -125,28 +125,34 @@ struct AttnBwdParams {
   float scale;
 };
 
-// dsum[b, h, t] = sum_c dO[b*Tq + t, h*dh + c] * O[b*Tq + t, h*dh + c]: one warp per (row, head)
+// dsum[b, h, t] = sum_c dO[b*Tq + t, h*dh + c] * O[b*Tq + t, h*dh + c]: one THREAD per (row, head), 16-byte loads.
+// Consecutive lanes take consecutive heads of a row (and then the next row), so a warp sweeps one contiguous span of
+// both tensors -- every byte of every 128-byte line it touches is used, within a few iterations -- and all 32 lanes
+// work (the warp-per-(row, head) form had 12 of 32 lanes loading at dh = 96 and five shuffles per 192 bytes).
 __global__ void __launch_bounds__(256)
 attn_bwd_dsum_kernel(const bf* __restrict__ d_out, int64_t lddo, const bf* __restrict__ out, int64_t ldo,
                      float* __restrict__ dsum, int64_t rows, int H, int Tq, int dh) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
-  for (int64_t item = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); item < rows * H;
-       item += warps) {
+  const int64_t n = rows * H;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t item = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; item < n; item += stride) {
     const int64_t row = item / H;
     const int h = static_cast<int>(item - row * H);
-    float acc = 0.0f;
-    for (int c = lane * 2; c < dh; c += 64) {
-      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d_out + row * lddo + h * dh + c));
-      const float2 o = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(out + row * ldo + h * dh + c));
-      acc = fmaf(a.x, o.x, fmaf(a.y, o.y, acc));
-    }
+    const uint4* a4 = reinterpret_cast<const uint4*>(d_out + row * lddo + h * dh);
+    const uint4* o4 = reinterpret_cast<const uint4*>(out + row * ldo + h * dh);
+    float acc0 = 0.0f, acc1 = 0.0f;
+    for (int c = 0; c < dh / 8; ++c) {
+      const uint4 a = __ldg(a4 + c), o = __ldg(o4 + c);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      const int64_t b = row / Tq;
-      dsum[(b * H + h) * Tq + (row - b * Tq)] = acc;
+      for (int i = 0; i < 4; ++i) {
+        const float2 af = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[i]));
+        const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[i]));
+        acc0 = fmaf(af.x, of.x, acc0);
+        acc1 = fmaf(af.y, of.y, acc1);
+      }
     }
+    const int64_t b = row / Tq;
+    dsum[(b * H + h) * Tq + (row - b * Tq)] = acc0 + acc1;
   }
 }
 
@@ -701,7 +707,7 @@ extern "C" int hriemo_attention_backward_bf16(const hriemo_attn_bwd_args* a, voi
     HRIEMO_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, "attention_backward: operands must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t rows = static_cast<int64_t>(a->B) * a->Tq;
-  int64_t gb = (rows * a->H + 7) / 8;
+  int64_t gb = (rows * a->H + 255) / 256;
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
   if (gb > cap) gb = cap;
   attn_bwd_dsum_kernel<<<static_cast<unsigned>(gb), 256, 0, s>>>(static_cast<const bf*>(a->d_out), a->lddo,

@@ -151,8 +151,10 @@ def _decoder_layer_backward(P: dict, tape: dict, dz: torch.Tensor, d_mem: Option
     return dz_in, d_mem, G
 
 
-def decoder_backward(dec, tape: dict, d_logits: torch.Tensor):
-    """d_logits: fp32 [B, N_e].  -> (d_mem bf16 [B*L, d], grads under the names of EmotionDecoder's parameters)."""
+def decoder_backward(dec, tape: dict, d_logits: torch.Tensor, d_z: Optional[torch.Tensor] = None):
+    """d_logits: fp32 [B, N_e]; d_z: fp32 [B, N_e, d] | None, the gradient arriving at the decoder's other output z
+    (a caller that regularises the emotion embeddings).  -> (d_mem bf16 [B*L, d], grads under the names of
+    EmotionDecoder's parameters)."""
     P = dec._prep.get()
     mem, mem_mask = tape["mem"], tape["mem_mask"]
     B, Ne, d = mem.B, dec.num_emotions, dec.d_model
@@ -161,6 +163,8 @@ def decoder_backward(dec, tape: dict, d_logits: torch.Tensor):
     z32 = tape["z"].view(B * Ne, d)
     dz32, G["out_proj.weight"], G["out_proj.bias"] = ops.linear_backward_f32(
         d_logits.contiguous().view(B * Ne, 1), z32, P["w_out"])
+    if d_z is not None:
+        dz32 = dz32 + d_z.to(f32).reshape(B * Ne, d)
     dz = ops.cast_bf16(dz32)
     d_mem = None
     for i in range(len(dec.layers) - 1, -1, -1):
@@ -351,3 +355,39 @@ def loss_and_gradients(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a, mask
     out["grads"].update({f"cross_modal.{k}": v for k, v in g_enc.items()})
     zero_key_bias_gradients(out["grads"])
     return out
+
+
+# --------------------------------------------------------------------------- #
+# forward with tapes / backward from output gradients: the autograd boundary (hriemo/autograd.py)
+# --------------------------------------------------------------------------- #
+def forward_train(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a, mask_t):
+    """The training-mode forward of FusionWithEmotionDecoder (models/fusion_with_emotion_decoder.py:120-197) keeping the
+    tapes of every sub-layer.  -> (logits [B, N_e], beta [B, 1], z [B, N_e, d], ctx) with ctx what backward_from needs."""
+    a, t = E.to_seq(h_a, "h_a"), E.to_seq(h_t, "h_t")
+    mask_a = E.check_mask(mask_a, a.B, a.T, "mask_a")
+    mask_t = E.check_mask(mask_t, t.B, t.T, "mask_t")
+    a_enc, t_enc, enc_tapes = encoder_forward_train(model.cross_modal, a, t, mask_a, mask_t)
+    h, beta, gate_tape = gate_forward_train(model.beta_gate, a_enc, t_enc, mask_a, mask_t)
+    fused_mask = model._build_fused_mask(mask_a, mask_t, h.T)
+    z, logits, dec_tape = decoder_forward_train(model.emotion_decoder, h, fused_mask)
+    return logits, beta, z, dict(enc=enc_tapes, gate=gate_tape, dec=dec_tape)
+
+
+def backward_from(model, ctx: dict, d_logits: Optional[torch.Tensor], d_beta: Optional[torch.Tensor],
+                  d_z: Optional[torch.Tensor] = None, need_dx: bool = False):
+    """What loss.backward() does from the gradients of the model's three outputs (any of them may be None): decoder,
+    gate and encoder backward schedules.  -> (grads under the reference's parameter names, d_a_in, d_t_in) -- the
+    last two (bf16 [B*T, d] gradients of the model's inputs) only with need_dx (the MOSEI wrapper's projections)."""
+    dec = model.emotion_decoder
+    B, Ne = ctx["dec"]["mem"].B, dec.num_emotions
+    dev = ctx["dec"]["z"].device
+    if d_logits is None:
+        d_logits = torch.zeros((B, Ne), dtype=f32, device=dev)
+    d_h, g_dec = decoder_backward(dec, ctx["dec"], d_logits.to(f32).contiguous(), d_z)
+    d_a, d_t, g_gate = gate_backward(model.beta_gate, ctx["gate"], d_h, None if d_beta is None else d_beta.to(f32).contiguous())
+    d_a_in, d_t_in, g_enc = encoder_backward(model.cross_modal, ctx["enc"], d_a, d_t, need_dx=need_dx)
+    grads: Grads = {f"beta_gate.{k}": v for k, v in g_gate.items()}
+    grads.update({f"emotion_decoder.{k}": v for k, v in g_dec.items()})
+    grads.update({f"cross_modal.{k}": v for k, v in g_enc.items()})
+    zero_key_bias_gradients(grads)
+    return grads, d_a_in, d_t_in

@@ -195,9 +195,9 @@ def kv_steps(key_pad: torch.Tensor) -> torch.Tensor:
 @_on_tensor_device
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Optional[torch.Tensor],
               B: int, H: int, Tq: int, Tk: int, dh: int, skip_padded_tiles: bool = True,
-              pair_heads: bool = True, want_lse: bool = False):
+              pair_heads: bool = True, want_lse: bool = False, out: Optional[torch.Tensor] = None):
     """q: [B*Tq, >=H*dh] view, k / v: [B*Tk, >=H*dh] views (column slices of a packed projection are
-    fine).  Returns [B*Tq, H*dh] bf16.  pair_heads=False switches the two-heads-per-work-item form of
+    fine).  Returns [B*Tq, H*dh] bf16 (written into `out` when given: a [B*Tq, >= H*dh] view with 16-byte aligned rows).  pair_heads=False switches the two-heads-per-work-item form of
     short query sequences off (include/hriemo.h: no_head_pairs; same result bit for bit).
     want_lse: also return lse [B, H, Tq] fp32 = ln sum_k exp(scale * q.k) over the unmasked keys."""
     _chk2d(q, bf16, "attention q")
@@ -206,7 +206,12 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Option
     if q.shape[0] != B * Tq or k.shape[0] != B * Tk or v.shape[0] != B * Tk:
         raise _l.HriemoError(f"attention: row counts {q.shape[0]}, {k.shape[0]}, {v.shape[0]} do not match "
                              f"B*Tq={B * Tq}, B*Tk={B * Tk}")
-    out = torch.empty((B * Tq, H * dh), dtype=bf16, device=q.device)
+    if out is None:
+        out = torch.empty((B * Tq, H * dh), dtype=bf16, device=q.device)
+    else:
+        _chk2d(out, bf16, "attention out")
+        if out.shape[0] != B * Tq or out.shape[1] < H * dh:
+            raise _l.HriemoError(f"attention: out shape {tuple(out.shape)} does not hold [{B * Tq}, {H * dh}]")
     m = _mask_u8(key_pad, B, Tk, "attention")
     args = _l.AttnArgs()
     args.q, args.ldq, args.k, args.ldk = q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0)

@@ -95,11 +95,15 @@ class FusionWithEmotionDecoder(nn.Module):
             pack = {"encoder": enc, "decoder": dec}
         return logits, beta, z, pack
 
-    @torch.no_grad()
     def forward(self, h_a, h_t, mask_a=None, mask_t=None, return_attention: bool = False):
         """h_a [B,d] or [B,L_a,d], h_t [B,d] or [B,L_t,d]; masks bool, True = PAD.
         Returns (logits [B,N_e], beta [B,1], z [B,N_e,d]) or, with return_attention, a 4-tuple
-        whose last item is {"encoder": [...per layer dict...], "decoder": [...per layer...]}."""
+        whose last item is {"encoder": [...per layer dict...], "decoder": [...per layer...]}.
+
+        In train() mode with gradients enabled the three outputs carry a grad_fn (hriemo/autograd.py): the reference's
+        training loops -- criterion(logits, y) [+ beta terms], loss.backward(), clip_grad_norm_, optimizer.step()
+        (scripts/fusion/train_fusion_seq_level_decoder.py:310-333) -- run unmodified and fill .grad through the
+        hand-scheduled backward pass (dropout is not applied: the dropout = 0 step is computed)."""
         E.warn_if_training(self, self.p_drop)
         h_a = self._ensure_3d(h_a)
         h_t = self._ensure_3d(h_t)
@@ -107,7 +111,12 @@ class FusionWithEmotionDecoder(nn.Module):
         E.require_cuda(h_t, "h_t")
         mask_a = E.check_mask(mask_a, h_a.shape[0], h_a.shape[1], "mask_a")
         mask_t = E.check_mask(mask_t, h_t.shape[0], h_t.shape[1], "mask_t")
-        logits, beta, z, pack = self.run_slabbed(h_a, h_t, mask_a, mask_t, return_attention)
+        if (self.training and torch.is_grad_enabled() and not return_attention
+                and any(p.requires_grad for p in self.parameters())):
+            from hriemo.autograd import fusion_forward_with_grad
+            return fusion_forward_with_grad(self, h_a, h_t, mask_a, mask_t)
+        with torch.no_grad():
+            logits, beta, z, pack = self.run_slabbed(h_a, h_t, mask_a, mask_t, return_attention)
         if return_attention:
             return logits, beta, z, pack
         return logits, beta, z

@@ -11,6 +11,7 @@ rounding of the forward costs a whole element of that gradient, so its error is 
 reproduces autograd to 1e-9 in float64.  Measured values go to gpurun_out/backward_errors_d*.json when that
 directory exists (copied to profiles/r01_backward_errors.json)."""
 import json
+import math
 import os
 
 import pytest
@@ -366,3 +367,121 @@ def test_trainer_graph_replay_matches_eager_steps():
     m1.eval(), m2.eval()
     la, lb = m1(h_a, h_t, ma, mt)[0], m2(h_a, h_t, ma, mt)[0]
     assert (la - lb).abs().max().item() <= 1e-4
+
+
+# ------------------------------------------------------------------ the autograd boundary (hriemo/autograd.py)
+def test_autograd_boundary_fills_grad_like_the_trainer_path():
+    """model.train(); logits, beta, z = model(...); loss.backward() -- the drop-in contract of the reference's training
+    loops -- must leave in .grad what the Trainer's schedule (backward.loss_and_gradients) computes for the same loss:
+    same kernels, only d_logits / d_beta come from torch's autograd over the loss expression."""
+    from hriemo import backward
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    torch.manual_seed(3)
+    model = FusionWithEmotionDecoder(d_model=256, n_heads=4, num_emotions=6, beta_hidden=64, dropout=0.0).to(DEV).train()
+    B, T_a, T_t = 6, 70, 24
+    h_a, h_t = _rand((B, T_a, 256), 71), _rand((B, T_t, 256), 72)
+    m_a, m_t = _ragged(B, T_a, 73), _ragged(B, T_t, 74)
+    y = (torch.rand((B, 6), device=DEV, generator=torch.Generator(device=DEV).manual_seed(75)) > 0.5).float()
+    logits, beta, z = model(h_a, h_t, m_a, m_t)
+    assert logits.requires_grad and beta.requires_grad and z.requires_grad
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y) - 0.01 * (beta * (1 - beta)).mean()
+    loss.backward()
+    ref = backward.loss_and_gradients(model, h_a, h_t, m_a, m_t, y, 0.01)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref["loss"].item()) <= 1e-5
+    for name, p in model.named_parameters():
+        assert p.grad is not None, name
+        g, r = p.grad, ref["grads"][name].view_as(p)
+        assert (g - r).abs().max().item() <= 1e-3 * max(r.abs().max().item(), 1e-6) + 1e-7, name
+    # eval() / no_grad() keep the inference schedule (no graph)
+    with torch.no_grad():
+        assert not model(h_a, h_t, m_a, m_t)[0].requires_grad
+    assert not model.eval()(h_a, h_t, m_a, m_t)[0].requires_grad
+
+
+def test_reference_training_loop_body_runs_unmodified_against_golden_steps():
+    """The body of the reference's train_one_epoch (scripts/fusion/train_fusion_seq_level_decoder.py:306-333), verbatim:
+    model(...) -> BCEWithLogitsLoss -> beta regulariser -> loss.backward() -> clip_grad_norm_(5.0) -> AdamW.step(), with
+    torch's own optimizer, against the two optimizer steps of the unmodified reference in tests/golden."""
+    import golden_util as G
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    fx = G.load("train_step_default")
+    torch.manual_seed(fx["model_seed"])
+    model = FusionWithEmotionDecoder(dropout=0.0, **fx["ctor"])
+    G.assert_same_weights(model, fx["weights"])
+    model = model.to(DEV)
+    d, n_e = fx["ctor"].get("d_model", 768), fx["ctor"].get("num_emotions", 4)
+    h_a, h_t, m_a, m_t = G.make_inputs(fx["in_seed"], fx["B"], fx["T_a"], fx["T_t"], d, d, True)
+    g = torch.Generator().manual_seed(fx["in_seed"] + 1)
+    labels = torch.eye(n_e)[torch.randint(0, n_e, (fx["B"],), generator=g)]
+    h_a, h_t, m_a, m_t, y = (x.to(DEV) for x in (h_a, h_t, m_a, m_t, labels))
+    optimizer = torch.optim.AdamW(model.parameters(), lr=fx["lr"], weight_decay=fx["weight_decay"])
+    criterion = torch.nn.BCEWithLogitsLoss()
+    model.train()
+    for want in fx["steps"]:
+        before = {k: p.detach().clone() for k, p in model.named_parameters()}
+        optimizer.zero_grad()
+        logits, beta, _ = model(h_a, h_t, m_a, m_t)                       # :310
+        loss = criterion(logits, y)                                       # :318
+        if beta is not None:
+            loss = loss - 0.01 * (beta * (1 - beta)).mean()               # :325-326
+        loss.backward()                                                   # :331
+        total = torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)   # :332
+        optimizer.step()                                                  # :333
+        torch.cuda.synchronize()
+        assert abs(loss.item() - want["loss"]) <= 5e-3
+        assert abs(total.item() - want["grad_norm"]) <= 3e-2 * want["grad_norm"]
+        worst = (0.0, "")
+        for k, p in model.named_parameters():
+            got_u, ref_u = (p.detach() - before[k]).double().norm().item(), want["update_norms"][k]
+            if not k.endswith("in_proj_bias"):
+                worst = max(worst, (abs(got_u - ref_u) / max(ref_u, 1e-7), k))
+        assert worst[0] <= 0.1, worst
+        for k, ref in want["params_full"].items():
+            p = dict(model.named_parameters())[k]
+            assert (p.detach().cpu() - ref).abs().max().item() <= 2.5 * fx["lr"], k
+
+
+def test_mosei_wrapper_trains_through_the_autograd_boundary():
+    """MoseiFusionWithEmotionDecoder in train() mode: pos_weight BCE + beta-entropy regulariser + GradScaler-style loss
+    scaling as in scripts/fusion/train_mosei_fusion_seq_level_decoder.py:380-396; every parameter incl. audio_proj /
+    text_proj receives a gradient that matches autograd over the oracle's float64 forward (bf16 bounds)."""
+    import hriemo_oracle as O
+    from models.mosei_fusion_with_emotion_decoder import MoseiFusionWithEmotionDecoder
+
+    torch.manual_seed(11)
+    model = MoseiFusionWithEmotionDecoder(74, 300, d_model=256, num_emotions=6, n_heads=4, num_layers_fusion=1,
+                                          num_layers_decoder=1, beta_hidden=64, dropout=0.0).to(DEV).train()
+    B, T_a, T_t = 8, 60, 40
+    h_a, h_t = _rand((B, T_a, 74), 81), _rand((B, T_t, 300), 82)
+    m_a, m_t = _ragged(B, T_a, 83), _ragged(B, T_t, 84)
+    y = (torch.rand((B, 6), device=DEV, generator=torch.Generator(device=DEV).manual_seed(85)) > 0.6).float()
+    pos_weight = torch.linspace(1.0, 3.0, 6, device=DEV)
+
+    def objective(logits, beta):
+        bce = torch.nn.functional.binary_cross_entropy_with_logits(logits, y.to(logits.dtype), pos_weight=pos_weight.to(logits.dtype))
+        b = beta.clamp(1e-6, 1 - 1e-6)
+        ent = -(b * b.log() + (1 - b) * (1 - b).log()).mean()
+        return bce + 1e-3 * ent
+
+    logits, beta, _ = model(h_a, h_t, m_a, m_t)
+    scale = 1024.0                                                       # what a GradScaler multiplies the loss by
+    (objective(logits, beta) * scale).backward()
+    torch.cuda.synchronize()
+    sd = {k: v.detach().double().cpu().requires_grad_(True) for k, v in model.state_dict().items()}
+    lo, be, _ = O.mosei_fusion_with_emotion_decoder(sd, h_a.double().cpu(), h_t.double().cpu(), m_a.cpu(), m_t.cpu(), n_heads=4)
+    y, pos_weight = y.double().cpu(), pos_weight.double().cpu()
+    objective(lo, be).backward()
+    total = math.sqrt(sum(float(v.grad.norm()) ** 2 for v in sd.values() if v.grad is not None))
+    for name, p in model.named_parameters():
+        assert p.grad is not None, name
+        got, ref = p.grad.double().cpu() / scale, sd[name].grad
+        if name.endswith("in_proj_bias"):
+            continue          # (key third is exactly zero here, round-off in the reference)
+        err = float((got - ref).norm()) / max(float(ref.norm()), 1e-3 * total)
+        assert err <= 0.1, (name, err)
+    for name in ("audio_proj.weight", "text_proj.weight", "audio_proj.bias", "text_proj.bias"):
+        got, ref = dict(model.named_parameters())[name].grad.double().cpu() / scale, sd[name].grad
+        assert float((got - ref).norm()) / float(ref.norm()) <= 5e-2, name

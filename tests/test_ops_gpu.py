@@ -793,3 +793,57 @@ def test_small_attention_backward_matches_autograd(B, H, Nq, Tk, dh, masked):
     _report("small_attention_backward dq", dq, qr.grad.view(B * Nq, d), atol=2e-2, rtol=2e-2)
     _report("small_attention_backward dk", dk, kr.grad.view(B * Tk, d), atol=2e-2, rtol=2e-2)
     _report("small_attention_backward dv", dv, vr.grad.view(B * Tk, d), atol=2e-2, rtol=2e-2)
+
+
+# ------------------------------------------------------------------ out-of-bounds writes (compute-sanitizer is closed on the pool)
+def _guarded(rows, cols, dtype, pad_rows=3, pad_cols=8):
+    """A [rows, cols] view in the middle of a larger buffer filled with a sentinel; check() asserts the guard band
+    (rows above / below, columns left / right of the view) still holds the sentinel."""
+    sentinel = 12345.0 if dtype == torch.float32 else 1.0e4
+    full = torch.full((rows + 2 * pad_rows, cols + 2 * pad_cols), sentinel, dtype=dtype, device=DEV)
+    view = full[pad_rows:pad_rows + rows, pad_cols:pad_cols + cols]
+
+    def check(name):
+        band = full.clone()
+        band[pad_rows:pad_rows + rows, pad_cols:pad_cols + cols] = sentinel
+        assert bool((band == sentinel).all()), f"{name}: wrote outside its output"
+        assert not bool((view == sentinel).all()), f"{name}: output untouched"
+    return view, check
+
+
+def test_kernels_do_not_write_outside_their_outputs():
+    """Every TMA-store / tcgen05 kernel writes through tensor maps or per-row pointers computed from ragged sizes: outputs
+    are placed inside sentinel-filled buffers (guard rows and guard columns) with row counts that are not multiples of
+    any tile (GEMM one-CTA and pair forms, the four attention forward forms, the tcgen05 attention backward, wgrad)."""
+    from hriemo import lib as L, ops
+
+    g = torch.Generator(device=DEV).manual_seed(9)
+
+    def rnd(*shape):
+        return torch.randn(*shape, device=DEV, generator=g).bfloat16()
+
+    for pair in (1, 2):
+        M, N, K = 389, 264 if pair == 1 else 512, 136
+        out, chk = _guarded(M, N, torch.bfloat16)
+        ops.gemm(rnd(M, K), rnd(N, K), torch.zeros(N, device=DEV), L.EPI_BIAS, out=out, cta_pair=pair)
+        chk(f"gemm cta_pair={pair}")
+    for (B, H, Tq, Tk, dh) in [(3, 2, 301, 299, 96), (3, 2, 301, 61, 96), (3, 2, 63, 301, 96), (3, 2, 61, 63, 64)]:
+        d = H * dh
+        q, k, v = rnd(B * Tq, d), rnd(B * Tk, d), rnd(B * Tk, d)
+        out, chk = _guarded(B * Tq, d, torch.bfloat16)
+        _, lse = ops.attention(q, k, v, None, B, H, Tq, Tk, dh, want_lse=True, out=out)
+        chk(f"attention {Tq}x{Tk}")
+        dq, chq = _guarded(B * Tq, d, torch.bfloat16)
+        dk, chk_ = _guarded(B * Tk, d, torch.bfloat16)
+        dv, chv = _guarded(B * Tk, d, torch.bfloat16)
+        ops.attention_backward(q, k, v, out.contiguous(), rnd(B * Tq, d), lse, None, B, H, Tq, Tk, dh, grads=(dq, dk, dv))
+        chq(f"attention backward dq {Tq}x{Tk}")
+        chk_(f"attention backward dk {Tq}x{Tk}")
+        chv(f"attention backward dv {Tq}x{Tk}")
+    M, N, K = 1301, 264, 136
+    dw, chk = _guarded(N, K, torch.float32, pad_cols=4)
+    try:
+        ops.linear_wgrad(rnd(M, N), rnd(M, K), dw=dw, want_bias=False)
+    except Exception:   # the wrapper may insist on a contiguous dw: then there is nothing to guard here
+        return
+    chk("linear wgrad")
