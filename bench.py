@@ -186,7 +186,9 @@ def parity_and_cpu_leg(model, dev, T_a, T_t, d_a, d_t, n_heads, mosei, n_total, 
     n_chunks = max(2, n_total // chunk)
     half = n_chunks // 2
     fwd = O.mosei_fusion_with_emotion_decoder if mosei else O.fusion_with_emotion_decoder
+    from hriemo import precise
     ref_lo, ref_be, got_lo, got_be, times = [], [], [], [], []
+    x3_lo, x3_be = [], []
     with torch.no_grad():
         for c in range(n_chunks):
             ragged = c >= half
@@ -201,10 +203,15 @@ def parity_and_cpu_leg(model, dev, T_a, T_t, d_a, d_t, n_heads, mosei, n_total, 
             glo, gbe, _ = model(h_a.to(dev), h_t.to(dev), None if m_a is None else m_a.to(dev), None if m_t is None else m_t.to(dev))
             ref_lo.append(lo.double()); ref_be.append(be.double())
             got_lo.append(glo.double().cpu()); got_be.append(gbe.double().cpu())
+            if precise.get_mode() == "bf16":   # the tf32-class mode on the same inputs (north_star: logits <= 1e-4)
+                with precise.mode("tf32x3"):
+                    plo, pbe, _ = model(h_a.to(dev), h_t.to(dev), None if m_a is None else m_a.to(dev), None if m_t is None else m_t.to(dev))
+                x3_lo.append(plo.double().cpu()); x3_be.append(pbe.double().cpu())
     R, G = torch.cat(ref_lo), torch.cat(got_lo)
     Rb, Gb = torch.cat(ref_be).view(-1), torch.cat(got_be).view(-1)
     n = R.shape[0]
-    tol = 1e-2                                  # the logits bar itself: a reference logit closer to 0 than this is undecidable in bf16
+    is_x3 = precise.get_mode() == "tf32x3"
+    tol = 1e-4 if is_x3 else 1e-2               # the logits bar itself: a reference logit closer to 0 than this is undecidable at that precision
     near = R.abs() < tol
     same = (R > 0) == (G > 0)
     top2 = R.topk(2, dim=1).values
@@ -215,7 +222,7 @@ def parity_and_cpu_leg(model, dev, T_a, T_t, d_a, d_t, n_heads, mosei, n_total, 
     parity = {
         "n": n, "n_ragged": (n_chunks - half) * chunk, "decisions": int(R.numel()),
         "reference": "oracle port (fp32, CPU) of the reference forward, same weights (state_dict of the GPU model), same inputs",
-        "logits_max_abs": float((R - G).abs().max()), "logits_bar": 1e-2,
+        "logits_max_abs": float((R - G).abs().max()), "logits_bar": tol, "precision": precise.get_mode(),
         "beta_max_abs": float((Rb - Gb).abs().max()), "beta_bar": 1e-4,
         "thr_agree": float(same[~near].double().mean()) if (~near).any() else None, "thr_excluded": int(near.sum()),
         "thr_excluded_rule": f"|reference logit| < {tol}", "thr_agree_all": float(same.double().mean()),
@@ -229,6 +236,17 @@ def parity_and_cpu_leg(model, dev, T_a, T_t, d_a, d_t, n_heads, mosei, n_total, 
                                   "reported, the per-sample dominance decision beta > 0.5 is the one held to 100 %",
         "beta_range_reference": [float(Rb.min()), float(Rb.max())],
     }
+    if x3_lo:
+        P3, Pb3 = torch.cat(x3_lo), torch.cat(x3_be).view(-1)
+        near3 = R.abs() < 1e-4
+        parity["tf32x3"] = {
+            "mode": "hriemo.precise.mode('tf32x3'): fp32 activations, Linear layers as split-bf16 (hi + lo) tcgen05 GEMMs, fp32 attention / LayerNorm / gate",
+            "n": n, "logits_max_abs": float((R - P3).abs().max()), "logits_bar": 1e-4,
+            "reference_note": "the reference here is the fp32 oracle port (itself ~5e-7 from float64)",
+            "beta_max_abs": float((Rb - Pb3).abs().max()),
+            "thr_agree_all": float(((R > 0) == (P3 > 0)).double().mean()), "thr_within_1e-4_of_zero": int(near3.sum()),
+            "argmax_agree_all": float((R.argmax(1) == P3.argmax(1)).double().mean()),
+            "beta_gt_half_agree_all": float(((Rb > 0.5) == (Pb3 > 0.5)).double().mean())}
     n_timed = chunk * len(times)
     cpu = {"value": n_timed / sum(times), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
            "sample": f"{n_timed} utterances in {len(times)} timed chunks of {chunk} (+1 warm-up chunk) of the same workload "
@@ -559,6 +577,9 @@ def main():
                     help="utterances of the CPU leg (default: 1024 for the in-line parity + cpu_baseline leg = ~30 s of CPU "
                          "work on 16 cores; 96 per step for --impl reference)")
     ap.add_argument("--torch-slab", type=int, default=512, help="utterances per stock-PyTorch forward (torch_gpu arm / gpu_eager_baseline)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32x3"],
+                    help="tf32x3: the tf32-class mode (hriemo/precise.py; logits <= 1e-4) as the measured forward; "
+                         "e2e / ragged / training legs are bf16-path features and are skipped")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU leg (cpu_baseline and parity)")
     ap.add_argument("--no-torch", action="store_true", help="skip gpu_eager_baseline (stock PyTorch on the same GPU)")
@@ -574,8 +595,11 @@ def main():
     if args.impl == "torch_gpu":
         return run_torch_gpu_arm(args, wl)
 
-    from hriemo import lib, ops, pipeline
+    from hriemo import lib, ops, pipeline, precise
 
+    if args.precision == "tf32x3":
+        precise.set_mode("tf32x3")
+        args.no_e2e = args.no_ragged = args.no_train = True
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -634,7 +658,7 @@ def main():
 
     # GEMM launches are tagged by the reference call group they replace: "attn_proj" (MHA in/out
     # projections), "ffn", "gemm" (everything else: decoder, MOSEI input projections)
-    parts = [agg(k) for k in ("gemm", "attn_proj", "ffn")]
+    parts = [agg(k) for k in ("gemm", "attn_proj", "ffn", "precise")]
     g_fl, g_ms, g_n = (sum(p[i] for p in parts) for i in range(3))
     a_fl, a_ms, a_n = agg("attention")
     p_fl, p_ms, p_n = agg("attn_proj")
@@ -668,7 +692,8 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "bf16" if args.precision == "bf16" else "tf32x3 (fp32 activations; bf16 hi + lo split operands on the tcgen05 GEMM, fp32 accumulate)",
+            "data": "synthetic",
             "config": arm_config(wl, world),
             "roofline": roofline, "attention_roofline": attention_roofline,
             "path": {"flops_per_utt": fpu, "achieved_tflops_per_gpu": path_tf, "frac_of_tensor_peak": path_tf / peaks["tf_sust"]},
@@ -688,6 +713,25 @@ def main():
             line["ragged"] = ragged_leg(model, dev, h_a, h_t, 3, world, dist)
         except Exception as e:  # noqa: BLE001
             line["ragged"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    # ---- the tf32-class mode on the head of the same batch (its full line: --precision tf32x3)
+    if rank == 0 and world == 1 and args.precision == "bf16" and not args.no_torch:
+        try:
+            nb = min(B, 1024)
+            with precise.mode("tf32x3"):
+                model(h_a[:nb], h_t[:nb])
+                torch.cuda.synchronize(dev)
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for _ in range(2):
+                    model(h_a[:nb], h_t[:nb])
+                p1.record()
+                torch.cuda.synchronize(dev)
+            line["tf32x3"] = {"value": 2 * nb / (p0.elapsed_time(p1) * 1e-3), "unit": UNIT, "batch": nb, "steps": 2,
+                              "note": "hriemo.precise.mode('tf32x3'); parity of the mode: parity.tf32x3"}
+        except Exception as e:  # noqa: BLE001
+            line["tf32x3"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
 
     # ---- stock PyTorch on the same GPU, same batch (N = 1: the competitor of the kernels; --impl torch_gpu runs it at any N)
     if rank == 0 and world == 1 and not args.no_torch:

@@ -130,6 +130,10 @@ SIGNATURES = {
     "hriemo_gate_blend_backward_w": (C.c_int, [_P, _I64, _P, _I64, _I32, _P, _I64, _P, _P, _I32, _I32, _I32, _P]),
     "hriemo_gate_stream_grad": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P]),
     "hriemo_attention_backward_bf16": (C.c_int, [C.POINTER(AttnBwdArgs), _P]),
+    "hriemo_split3": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _P]),
+    "hriemo_attention_f32": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I32, _I32, _I32, _I32, _I32, _F, _P]),
+    "hriemo_masked_mean_f32": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P]),
+    "hriemo_gate_blend_f32": (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _I32, _I32, _P]),
     "hriemo_host_pack_bf16": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, _I64, _I64, _I64, _I32]),
 }
 

@@ -813,3 +813,63 @@ def gate_stream_grad(dh: torch.Tensor, L: int, w: torch.Tensor, one_minus: bool,
                                                 dpool.data_ptr(), _ptr(m), inv_counts.data_ptr(), dn.data_ptr(), d, B, T, d,
                                                 _stream()), "gate_stream_grad")
     return dn
+
+
+# ------------------------------------------------------------------ "tf32-class" precision mode (hriemo/precise.py)
+@_on_tensor_device
+def split3(x: torch.Tensor, weight: bool = False, relu: bool = False) -> torch.Tensor:
+    """fp32 [rows, K] -> bf16 [rows, 3 * roundup(K, 8)]: activations as [hi | lo | hi], weights as [hi | hi | lo]
+    (hi = bf16(x), lo = bf16(x - hi)); one bf16 GEMM over the tripled K then carries hi.hi + lo.hi + hi.lo."""
+    _chk2d(x, f32, "split3 x")
+    rows, K = x.shape
+    Kp = round_up(K, 8)
+    out = torch.empty((rows, 3 * Kp), dtype=bf16, device=x.device)
+    _l.check(_l.load().hriemo_split3(x.data_ptr(), x.stride(0), out.data_ptr(), 3 * Kp, rows, K, int(weight), int(relu),
+                                      _stream()), "split3")
+    return out
+
+
+@_on_tensor_device
+def attention_f32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Optional[torch.Tensor], B: int, H: int,
+                  Tq: int, Tk: int, dh: int, want_probs: bool = False):
+    """fp32 attention on the CUDA cores; q [B*Tq, >= H*dh], k / v [B*Tk, >= H*dh] views.  Returns (out f32
+    [B*Tq, H*dh], head-averaged probabilities f32 [B, Tq, Tk] | None)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _chk2d(t, f32, f"attention_f32 {n}")
+    if q.shape[0] != B * Tq or k.shape[0] != B * Tk or v.shape[0] != B * Tk:
+        raise _l.HriemoError("attention_f32: row counts do not match B*Tq / B*Tk")
+    out = torch.empty((B * Tq, H * dh), dtype=f32, device=q.device)
+    probs = torch.zeros((B, Tq, Tk), dtype=f32, device=q.device) if want_probs else None
+    m = _mask_u8(key_pad, B, Tk, "attention_f32")
+    _l.check(_l.load().hriemo_attention_f32(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+                                             v.stride(0), _ptr(m), out.data_ptr(), out.stride(0), _ptr(probs), B, H, Tq,
+                                             Tk, dh, 1.0 / math.sqrt(dh), _stream()), "attention_f32")
+    return out, probs
+
+
+@_on_tensor_device
+def masked_mean_f32(x: torch.Tensor, pad: Optional[torch.Tensor], B: int, T: int) -> torch.Tensor:
+    _chk2d(x, f32, "masked_mean_f32 x")
+    if not x.is_contiguous() or x.shape[0] != B * T:
+        raise _l.HriemoError("masked_mean_f32: expected a contiguous [B*T, d] tensor")
+    d = x.shape[1]
+    pooled = torch.empty((B, d), dtype=f32, device=x.device)
+    m = _mask_u8(pad, B, T, "masked_mean_f32")
+    _l.check(_l.load().hriemo_masked_mean_f32(x.data_ptr(), _ptr(m), pooled.data_ptr(), B, T, d, _stream()),
+             "masked_mean_f32")
+    return pooled
+
+
+@_on_tensor_device
+def gate_blend_f32(a: torch.Tensor, T_a: int, t: torch.Tensor, w: torch.Tensor, B: int, L: int):
+    """h = w * a[:, :L] + (1 - w) * t on contiguous f32 [B*T_a, d] / [B*L, d] tensors, w [B, d]; returns (h, beta [B, 1])."""
+    for x, n in ((a, "a"), (t, "t"), (w, "w")):
+        _chk2d(x, f32, f"gate_blend_f32 {n}")
+        if not x.is_contiguous():
+            raise _l.HriemoError(f"gate_blend_f32 {n}: expected a contiguous tensor")
+    d = a.shape[1]
+    h = torch.empty((B * L, d), dtype=f32, device=a.device)
+    beta = torch.empty((B, 1), dtype=f32, device=a.device)
+    _l.check(_l.load().hriemo_gate_blend_f32(a.data_ptr(), T_a, t.data_ptr(), w.data_ptr(), h.data_ptr(), beta.data_ptr(),
+                                              B, L, d, _stream()), "gate_blend_f32")
+    return h, beta

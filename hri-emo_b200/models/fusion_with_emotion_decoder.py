@@ -6,6 +6,7 @@ import torch
 import torch.nn as nn
 
 from hriemo import engine as E
+from hriemo import precise
 
 from .beta_gate_tacfn import BetaGate
 from .cross_modal_block_tacfn import CrossModalTransformer
@@ -111,6 +112,9 @@ class FusionWithEmotionDecoder(nn.Module):
         E.require_cuda(h_t, "h_t")
         mask_a = E.check_mask(mask_a, h_a.shape[0], h_a.shape[1], "mask_a")
         mask_t = E.check_mask(mask_t, h_t.shape[0], h_t.shape[1], "mask_t")
+        if precise.get_mode() == "tf32x3":   # fp32 activations, split-bf16 GEMMs (hriemo/precise.py); inference only
+            logits, beta, z, pack = precise.fusion_forward(self, h_a, h_t, mask_a, mask_t, return_attention)
+            return (logits, beta, z, pack) if return_attention else (logits, beta, z)
         if (self.training and torch.is_grad_enabled() and not return_attention
                 and any(p.requires_grad for p in self.parameters())):
             from hriemo.autograd import fusion_forward_with_grad

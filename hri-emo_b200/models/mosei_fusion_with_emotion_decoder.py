@@ -8,6 +8,7 @@ import torch.nn as nn
 from hriemo import engine as E
 from hriemo import lib as L
 from hriemo import ops
+from hriemo import precise
 
 from .fusion_with_emotion_decoder import FusionWithEmotionDecoder
 
@@ -56,6 +57,9 @@ class MoseiFusionWithEmotionDecoder(nn.Module):
         E.require_cuda(h_t, "h_t")
         mask_a = E.check_mask(mask_a, h_a.shape[0], h_a.shape[1], "mask_a")
         mask_t = E.check_mask(mask_t, h_t.shape[0], h_t.shape[1], "mask_t")
+        if precise.get_mode() == "tf32x3":   # hriemo/precise.py; inference only
+            logits, beta, z, pack = precise.mosei_forward(self, h_a, h_t, mask_a, mask_t, return_attention)
+            return (logits, beta, z, pack) if return_attention else (logits, beta, z)
         if (self.training and torch.is_grad_enabled() and not return_attention
                 and any(p.requires_grad for p in self.parameters())):
             from hriemo.autograd import mosei_forward_with_grad

@@ -411,6 +411,37 @@ typedef struct hriemo_attn_bwd_args {
 } hriemo_attn_bwd_args;
 int hriemo_attention_backward_bf16(const hriemo_attn_bwd_args* args, void* stream);
 
+/* ------------------------------------------------- "tf32-class" precision mode ----
+ * north_star: logits within 1e-4 of the reference's fp32 forward.  The tensor cores multiply bf16 here, so an fp32
+ * operand travels as two bf16 numbers (hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits; TF32 keeps 10) and a product
+ * as three bf16 products accumulated in fp32: x.w ~= hi.hi + lo.hi + hi.lo.  Laid out along K -- activations as
+ * [hi | lo | hi], weights as [hi | hi | lo] -- that is ONE hriemo_gemm_bf16 launch at 3 K with an f32 epilogue
+ * (HRIEMO_EPI_BIAS_F32 / HRIEMO_EPI_BIAS_RESID_F32).  These entry points are the passes around it (f32 in, f32 out);
+ * hriemo/precise.py holds the schedule.  Replaces the same reference lines as the bf16 entry points above. */
+
+/* x f32 [rows, K] (row pitch ldx) -> out bf16 [rows, 3 * Kp], Kp = K rounded up to 8 (zero padded), row pitch ldo.
+ * pattern 0 (activations): [hi | lo | hi]; pattern 1 (weights): [hi | hi | lo].  relu != 0: max(x, 0) first (the
+ * FFN's activation, models/cross_modal_block_tacfn.py:46). */
+int hriemo_split3(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, int64_t rows, int32_t K, int32_t pattern,
+                  int32_t relu, void* stream);
+
+/* softmax(q k^T * scale + key padding) v in fp32 on the CUDA cores; q [B*Tq, >= H*dh], k / v [B*Tk, >= H*dh] (column
+ * slices of a packed projection are fine; dh % 4 == 0, K rows 16-byte aligned), out f32 [B*Tq, H*dh] (pitch ldo).
+ * probs: NULL, or f32 [B, Tq, Tk] ZEROED by the caller, receives the head-averaged probabilities (need_weights of
+ * nn.MultiheadAttention; accumulated with atomics).  A fully masked row gives NaN, as torch.softmax does. */
+int hriemo_attention_f32(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                         const uint8_t* key_pad, float* out, int64_t ldo, float* probs, int32_t B, int32_t H,
+                         int32_t Tq, int32_t Tk, int32_t dh, float scale, void* stream);
+
+/* models/beta_gate_tacfn.py:6-24 on an f32 [B, T, d] tensor: pooled [B, d] = masked mean over time. */
+int hriemo_masked_mean_f32(const float* x, const uint8_t* pad, float* pooled, int32_t B, int32_t T, int32_t d,
+                           void* stream);
+
+/* models/beta_gate_tacfn.py:95-116 on f32 tensors: h [B, L, d] = w * a[:, :L] + (1 - w) * t, beta [B] = mean_d(w);
+ * a holds T_a >= L rows per utterance, t holds L, w is [B, d]. */
+int hriemo_gate_blend_f32(const float* a, int32_t T_a, const float* t, const float* w, float* h, float* beta, int32_t B,
+                          int32_t L, int32_t d, void* stream);
+
 /* Mean over time (UNMASKED) of an f32 [B,L,d] tensor — models/fusion_classifier.py:145. */
 int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d, void* stream);
 

@@ -823,7 +823,7 @@ def test_kernels_do_not_write_outside_their_outputs():
         return torch.randn(*shape, device=DEV, generator=g).bfloat16()
 
     for pair in (1, 2):
-        M, N, K = 389, 264 if pair == 1 else 512, 136
+        M, N, K = 389, 288 if pair == 1 else 512, 136
         out, chk = _guarded(M, N, torch.bfloat16)
         ops.gemm(rnd(M, K), rnd(N, K), torch.zeros(N, device=DEV), L.EPI_BIAS, out=out, cta_pair=pair)
         chk(f"gemm cta_pair={pair}")
@@ -840,7 +840,7 @@ def test_kernels_do_not_write_outside_their_outputs():
         chq(f"attention backward dq {Tq}x{Tk}")
         chk_(f"attention backward dk {Tq}x{Tk}")
         chv(f"attention backward dv {Tq}x{Tk}")
-    M, N, K = 1301, 264, 136
+    M, N, K = 1301, 256, 128
     dw, chk = _guarded(N, K, torch.float32, pad_cols=4)
     try:
         ops.linear_wgrad(rnd(M, N), rnd(M, K), dw=dw, want_bias=False)
