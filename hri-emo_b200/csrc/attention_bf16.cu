@@ -138,6 +138,38 @@ __device__ __forceinline__ void exp_pack(const uint32_t (&v)[32], float sc, floa
   l4[0] = la.x; l4[2] = la.y; l4[1] = lb.x; l4[3] = lb.y;
 }
 
+
+// The two halves of exp_pack for the v5 softmax loop: x = s*sc + neg_m for 32 scores (after which the raw scores are
+// dead and their registers can take the next step's tensor-memory load), and p = 2^x -> 16 packed bf16 pairs + row sums.
+__device__ __forceinline__ void scale32(const uint32_t (&v)[32], float sc, float neg_m, float2 (&x)[16]) {
+  const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(neg_m, neg_m);
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    x[i] = ffma2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
+}
+// (volatile: the exponentials stay between the turn-taking barriers and behind the tensor-memory loads they are to cover;
+// without it the compiler hoists the first chunk's exponentials above the barrier -- HRIEMO_ATTN_V5_LOOSE keeps that form
+// for A/B runs)
+__device__ __forceinline__ float ex2_approx_v(float x) {
+  float y;
+#ifdef HRIEMO_ATTN_V5_LOOSE
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+#else
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+#endif
+  return y;
+}
+__device__ __forceinline__ void exp_pack_x(const float2 (&x)[16], float (&l4)[4], uint32_t (&pk)[16]) {
+  float2 la = make_float2(l4[0], l4[2]), lb = make_float2(l4[1], l4[3]);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 e = make_float2(ex2_approx_v(x[i].x), ex2_approx_v(x[i].y));
+    pk[i] = pack_bf16(e.x, e.y);
+    if (i & 1) lb = fadd2(lb, e); else la = fadd2(la, e);
+  }
+  l4[0] = la.x; l4[2] = la.y; l4[1] = lb.x; l4[3] = lb.y;
+}
+
 template <int DH, bool PAIRED, bool DEFER>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -672,8 +704,8 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if (wg_tid == 0) ATRACE(2 + wg, g + j, 6);
       }
 
-#else
-      // ---- v4 softmax loop.  Against the first form (kept under HRIEMO_ATTN_V3_SOFTMAX for A/B runs):
+#elif !defined(HRIEMO_ATTN_V5_SOFTMAX)
+      // ---- v4 softmax loop (the default).  Against the first form (kept under HRIEMO_ATTN_V3_SOFTMAX for A/B runs):
       //  * the scores of step j+1 are fetched (wait S, tcgen05.ld issued) while the P stores of step j drain, so the
       //    fixed latencies of a step (barrier wait, tensor-memory load, store drain, hand-off) overlap instead of adding up;
       //  * no barrier wait per step for the PV two steps back: S(k) is issued behind PV(k-2) by the same thread, so
@@ -781,6 +813,131 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           tc_fence_after_sync();
           tmem_ld32(t_tile + nbuf * A3_BKV, va);
           if (p.Tk - (j + 1) * A3_BKV > 32) tmem_ld32(t_tile + nbuf * A3_BKV + 32, vb);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 5);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_pfull + (wg * 2 + (pv_issued & 1u)) * 8);
+        ++pv_issued;
+        if (j == 0 && nk > 2) release_q();
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 6);
+      }
+#else
+      // ---- v5 softmax loop (HRIEMO_ATTN_V5_SOFTMAX; an experiment that did NOT pay: 500x500 0.553 ms against v4's 0.525 on
+      // the same box, profiles/r02_attention_issue_notes.txt item 7 -- S(j+1) is issued ~600 cycles behind the hand-off of
+      // P(j-1) and shares the tensor pipe with the other tile, so it has rarely landed in the middle of step j, and the
+      // exact row maximum in front of the exponentials costs what the earlier load saves).  ncu's warp-state samples of v4 (profiles/r02_ncu_attention_v16_summary.txt) put only 34 %
+      // of a softmax warp's time in the exponentials; 15 % went to waiting for the step's tensor-memory load at the top
+      // of the loop and 8 % to the row maximum formed after the exponentials.  Here
+      //  * the row maximum comes FIRST (ALU pipe, ~80 cycles) -- exact, so there is no speculative pass to redo and the
+      //    raw scores are dead as soon as they have been scaled;
+      //  * the second 32-score chunk is scaled before its exponentials start, and the NEXT step's scores are loaded into
+      //    the freed registers right there: wait S(j+1) (issued behind PV(j-1), long done), two tcgen05.ld, and the
+      //    ~250 cycles of their latency pass under the chunk's 32 MUFUs instead of at the top of the next iteration;
+      //  * as in v4: no per-step wait for PV(j-2), one p_full arrival per warp.
+      if (nk <= 2) release_q();   // short items: the producer needs the buffer back sooner (two items ahead)
+      float m_run = -INFINITY;  // running reference maximum, in log2 units (score * scale * log2 e)
+      float l_run = 0.0f;
+      uint32_t va[32], vb[32];
+      {  // the item's first scores
+        const uint32_t sbuf0 = paired ? (g >> 1) & 1u : g & 1u;
+        if (wg_tid == 0) ATRACE(2 + wg, g, 0);
+        mbar_wait(b_sfull + (wg * 2 + sbuf0) * 8, (sbuf0 ? scnt1 : scnt0) & 1u);
+        if (sbuf0) ++scnt1; else ++scnt0;
+        tc_fence_after_sync();
+        if (wg_tid == 0) ATRACE(2 + wg, g, 1);
+        tmem_ld32(t_tile + sbuf0 * A3_BKV, va);
+        if (p.Tk > 32) tmem_ld32(t_tile + sbuf0 * A3_BKV + 32, vb);
+      }
+      for (int j = 0; j < nk; ++j) {
+        // flat step of this tile's j-th key step: g + j, or g + 2 j + wg in paired-head mode (g is even there)
+        const uint32_t sbuf = paired ? ((g >> 1) + static_cast<uint32_t>(j)) & 1u : (g + static_cast<uint32_t>(j)) & 1u;
+        const uint32_t t_s = t_tile + sbuf * A3_BKV;
+        const int rem = p.Tk - j * A3_BKV;
+        const bool two = rem > 32;                   // second 32-key chunk holds a valid key
+        const bool masked = flags[j] != 0;           // warp-uniform
+        const float* cap_j = caps + j * A3_BKV;
+        tmem_ld_wait();
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 2);
+        if (masked) {
+          apply_caps(va, cap_j);
+          if (two) apply_caps(vb, cap_j + 32);
+        }
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        max4(m4, va);
+        if (two) max4(m4, vb);
+        const float tile_max = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;  // sc > 0
+        // ---- lazy running maximum; O / l rescale only when the maximum grew by more than 2^TAU (rare)
+        if (j == 0) {
+          m_run = tile_max;
+        } else {
+          const bool need = tile_max > m_run + A3_LAZY_TAU;
+          if (__any_sync(0xffffffffu, need)) {
+            // every PV of this tile must have retired: the latest one is PV(pv_issued - 1); the one before retired
+            // before this step's S landed (S(j) is issued behind PV(j-2)), so this wait can not see a stale phase
+            const uint32_t kk = pv_issued - 1u;
+            mbar_wait(b_pvdone + (wg * 2 + (kk & 1u)) * 8, (kk >> 1) & 1u);
+            tc_fence_after_sync();
+            const float alpha = need ? ex2_approx(m_run - tile_max) : 1.0f;
+            if (need) m_run = tile_max;
+            l_run *= alpha;
+#pragma unroll 1
+            for (int c = 0; c < DH / 32; ++c) {
+              uint32_t v[32];
+              tmem_ld32(t_o + c * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st32(t_o + c * 32, v);
+            }
+          }
+        }
+        const float neg_m = (m_run == -INFINITY) ? 0.0f : -m_run;
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 3);
+
+        // ---- p = 2^(s*scale - m), row sum, bf16 P into the first 32 columns of this S buffer; the two warpgroups
+        // take turns (named barriers 3 / 4) so that their exponentials do not collide on the quarter-rate XU pipe
+#ifndef HRIEMO_ATTN_NO_PINGPONG
+        asm volatile("bar.sync %0, 256;" ::"r"(3 + wg) : "memory");
+#endif
+        float l4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        uint32_t pk[16];
+        float2 xs[16];
+        scale32(va, sc, neg_m, xs);
+        exp_pack_x(xs, l4, pk);
+        tmem_st16(t_s, pk);
+        if (two) scale32(vb, sc, neg_m, xs);     // vb is dead from here on
+        // ---- the next step's scores, into the registers just freed.  S(j+1) is issued behind PV(j-1) and shares the tensor
+        // pipe with the other tile, so it is often NOT there yet in the middle of this step (a blocking wait here, inside
+        // the exp turn, cost 6 %): one non-blocking test now -- if it has landed its load latency passes under the
+        // exponentials below -- and the blocking wait after them otherwise
+        const bool more = j + 1 < nk;
+        const uint32_t nbuf = sbuf ^ 1u;
+        bool fetched = false;
+        auto fetch_next = [&]() {
+          if (nbuf) ++scnt1; else ++scnt0;
+          tc_fence_after_sync();
+          tmem_ld32(t_tile + nbuf * A3_BKV, va);
+          if (p.Tk - (j + 1) * A3_BKV > 32) tmem_ld32(t_tile + nbuf * A3_BKV + 32, vb);
+          fetched = true;
+        };
+        if (more) {
+          const bool ok = mbar_test_wait(b_sfull + (wg * 2 + nbuf) * 8, (nbuf ? scnt1 : scnt0) & 1u);
+          if (__all_sync(0xffffffffu, ok)) fetch_next();
+        }
+        if (two) {
+          exp_pack_x(xs, l4, pk);
+          tmem_st16(t_s + 16, pk);
+        }
+#ifndef HRIEMO_ATTN_NO_PINGPONG
+        asm volatile("bar.arrive %0, 256;" ::"r"(4 - wg) : "memory");   // the other warpgroup's turn
+#endif
+        l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        if (wg_tid == 0) ATRACE(2 + wg, g + j, 4);
+        if (more && !fetched) {
+          mbar_wait(b_sfull + (wg * 2 + nbuf) * 8, (nbuf ? scnt1 : scnt0) & 1u);
+          fetch_next();
         }
         tmem_st_wait();
         tc_fence_before_sync();

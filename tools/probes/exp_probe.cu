@@ -94,6 +94,48 @@ __device__ __forceinline__ void exp_pack_F(const uint32_t (&v)[32], float sc, fl
   }
 }
 
+
+// H: both 32-score chunks of a step in ONE loop (two independent chains side by side): ptxas keeps every consumer one
+// ITERATION behind its producers, which is now four MUFUs (32 pipe cycles), not two
+__device__ __forceinline__ void exp_pack_H(const uint32_t (&va)[32], const uint32_t (&vb)[32], float sc, float nm, float2& la, float2& lb,
+                                           uint32_t (&pa)[16], uint32_t (&pb)[16]) {
+  const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(nm, nm);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 xa = ffma2(make_float2(__uint_as_float(va[2 * i]), __uint_as_float(va[2 * i + 1])), sc2, nm2);
+    const float2 xb = ffma2(make_float2(__uint_as_float(vb[2 * i]), __uint_as_float(vb[2 * i + 1])), sc2, nm2);
+    const float2 ea = make_float2(ex2a(xa.x), ex2a(xa.y));
+    const float2 eb = make_float2(ex2a(xb.x), ex2a(xb.y));
+    pa[i] = pack_bf16(ea.x, ea.y);
+    pb[i] = pack_bf16(eb.x, eb.y);
+    la = fadd2(la, ea);
+    lb = fadd2(lb, eb);
+  }
+}
+// I: as H with four chains (quarters of 16 scores)
+__device__ __forceinline__ void exp_pack_I(const uint32_t (&va)[32], const uint32_t (&vb)[32], float sc, float nm, float2& la, float2& lb,
+                                           uint32_t (&pa)[16], uint32_t (&pb)[16]) {
+  const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(nm, nm);
+  float2 lc = make_float2(0.f, 0.f), ld = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 x0 = ffma2(make_float2(__uint_as_float(va[2 * i]), __uint_as_float(va[2 * i + 1])), sc2, nm2);
+    const float2 x1 = ffma2(make_float2(__uint_as_float(va[16 + 2 * i]), __uint_as_float(va[16 + 2 * i + 1])), sc2, nm2);
+    const float2 x2 = ffma2(make_float2(__uint_as_float(vb[2 * i]), __uint_as_float(vb[2 * i + 1])), sc2, nm2);
+    const float2 x3 = ffma2(make_float2(__uint_as_float(vb[16 + 2 * i]), __uint_as_float(vb[16 + 2 * i + 1])), sc2, nm2);
+    const float2 e0 = make_float2(ex2a(x0.x), ex2a(x0.y));
+    const float2 e1 = make_float2(ex2a(x1.x), ex2a(x1.y));
+    const float2 e2 = make_float2(ex2a(x2.x), ex2a(x2.y));
+    const float2 e3 = make_float2(ex2a(x3.x), ex2a(x3.y));
+    pa[i] = pack_bf16(e0.x, e0.y);
+    pa[8 + i] = pack_bf16(e1.x, e1.y);
+    pb[i] = pack_bf16(e2.x, e2.y);
+    pb[8 + i] = pack_bf16(e3.x, e3.y);
+    la = fadd2(la, e0); lb = fadd2(lb, e1); lc = fadd2(lc, e2); ld = fadd2(ld, e3);
+  }
+  la = fadd2(la, lc); lb = fadd2(lb, ld);
+}
+
 template <int VAR>
 __global__ void __launch_bounds__(512, 1) probe(const float* in, uint32_t* out, long long* cycles, int iters) {
   uint32_t va[32], vb[32];
@@ -116,12 +158,20 @@ __global__ void __launch_bounds__(512, 1) probe(const float* in, uint32_t* out, 
     else if (VAR == 7) exp_pack_G<3>(V, 0.125f, nm, la, lb, pk);                \
     else if (VAR == 8) exp_pack_G<4>(V, 0.125f, nm, la, lb, pk);                \
     else exp_pack_F(V, 0.125f, nm, la, lb, pk);
+    if (VAR == 9 || VAR == 10) {
+      uint32_t pk2[16];
+      if (VAR == 9) exp_pack_H(va, vb, 0.125f, nm, la, lb, pk, pk2);
+      else exp_pack_I(va, vb, 0.125f, nm, la, lb, pk, pk2);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { acc ^= pk[i]; acc += pk2[i]; }
+    } else {
     RUN(va)
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc ^= pk[i];
     RUN(vb)
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc += pk[i];
+    }
     nm -= 1e-3f;
     // keep the inputs "live and changing" so nothing is hoisted out of the loop
     va[it & 31] ^= acc & 1u;
@@ -161,5 +211,7 @@ int main() {
   run<7>("G consumers depend on pair k+3", in, out, cyc);
   run<8>("G consumers depend on pair k+4", in, out, cyc);
   run<6>("F no row sums", in, out, cyc);
+  run<9>("H two chunks in one loop", in, out, cyc);
+  run<10>("I four quarter-chunks in one loop", in, out, cyc);
   return 0;
 }
