@@ -196,12 +196,23 @@ __device__ __forceinline__ void row_stats(const RowRegs<NV>& r, int d, int lane,
   rstd = rsqrtf(warp_sum(q) / static_cast<float>(d) + eps);
 }
 
-// One CTA per utterance; warp w reduces rows t = w, w+8, ... in registers, then the
-// 8 partial sums are combined through shared memory in a fixed order (deterministic).
-// The parameter vectors are kept off the per-row path (a row is 2 d bytes, each parameter vector 4 d):
-// the pending LayerNorm's (gamma, beta) live in registers for the whole utterance, and the gate's own
-// LayerNorm is linear after the row statistics, so its gamma / beta are applied once to the sum:
-//   mean_t LN(y_t) = gamma * [sum_t (y_t - m_t) rstd_t] / n + beta * count / n.
+// One CTA per utterance; warp w reduces rows t = w, w+8, ... and the 8 partial sums are combined through shared memory in
+// a fixed order (deterministic).
+//  * Rows reach the warp through a warp-PRIVATE ring of LMM stages in shared memory filled with 16-byte cp.async copies:
+//    every lane copies exactly the bytes it later reads, so the ring needs no barrier, and STAGES - 1 rows (not one) are in
+//    flight per warp -- the register-prefetch form kept 24 KB in flight per SM and ran at 0.36 of the HBM roofline.
+//  * The arithmetic is packed fp32 (FFMA2 / FADD2) with one-pass statistics (sum and sum of squares reduced together: one
+//    round of shuffles per row instead of two).  The pending LayerNorm's (gamma, beta) live in registers for the whole
+//    utterance; the gate's own LayerNorm is linear after the row statistics, so its gamma / beta are applied once to the
+//    sum:  mean_t LN(y_t) = gamma * [sum_t (y_t - m_t) rstd_t] / n + beta * count / n,  and the "- m_t rstd_t" term is a
+//    per-row SCALAR accumulated on the side.
+constexpr int LMM_WARPS = 8;
+template <int NV> struct LmmStages { static constexpr int value = NV <= 3 ? 6 : (NV == 4 ? 5 : 3); };
+
+__device__ __forceinline__ void lmm_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
 template <int NV>
 __global__ void __launch_bounds__(256)
 ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
@@ -209,98 +220,159 @@ ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const fl
                       const uint8_t* __restrict__ pad, float* __restrict__ pooled, int64_t ld_pooled,
                       int T, int d, const float* __restrict__ pre_g, const float* __restrict__ pre_b,
                       const float2* __restrict__ pre_stats) {
-  extern __shared__ float part[];  // [8][d]
+  constexpr int STAGES = LmmStages<NV>::value;
+  constexpr int ROW_BYTES = NV * 512;
+  extern __shared__ __align__(16) uint8_t lmm_smem[];   // ring [8 warps][STAGES][NV * 32 lanes][16 B]; later part[8][d]
+  float* part = reinterpret_cast<float*>(lmm_smem);
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  RowRegs<NV> acc, pg, pb;
+  const uint32_t ring = smem_u32(lmm_smem) + warp * (STAGES * ROW_BYTES) + lane * 16;
+  const uint8_t* ring_p = lmm_smem + warp * (STAGES * ROW_BYTES) + lane * 16;
+  float2 acc[NV][4], pg[NV][4], pb[NV][4];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      acc.v[i][k] = 0.0f;
-      pg.v[i][k] = (pre_g != nullptr && c < d) ? __ldg(pre_g + c + k) : 0.0f;
-      pb.v[i][k] = (pre_g != nullptr && c < d) ? __ldg(pre_b + c + k) : 0.0f;
+    for (int k = 0; k < 4; ++k) {
+      acc[i][k] = make_float2(0.0f, 0.0f);
+      const bool on = pre_g != nullptr && c < d;
+      pg[i][k] = on ? make_float2(__ldg(pre_g + c + 2 * k), __ldg(pre_g + c + 2 * k + 1)) : make_float2(0.0f, 0.0f);
+      pb[i][k] = on ? make_float2(__ldg(pre_b + c + 2 * k), __ldg(pre_b + c + 2 * k + 1)) : make_float2(0.0f, 0.0f);
     }
   }
   int count = 0;
-  // the next valid row is already in flight (as raw bf16) while the current one is reduced
+  float side = 0.0f;   // sum over rows of m_t * rstd_t (subtracted from every column at the end)
   auto next_valid = [&](int t) {
-    while (t < T && pad != nullptr && pad[static_cast<int64_t>(b) * T + t] != 0) t += 8;   // warp-uniform
+    while (t < T && pad != nullptr && pad[static_cast<int64_t>(b) * T + t] != 0) t += LMM_WARPS;   // warp-uniform
     return t;
   };
-  uint4 raw[NV];
-  auto fetch = [&](int t) {
-    const __nv_bfloat16* row = x + (static_cast<int64_t>(b) * T + t) * ldx;
+  auto issue = [&](int t, int slot) {   // one commit group per call, also when there is nothing left to copy
+    if (t < T) {
+      const __nv_bfloat16* row = x + (static_cast<int64_t>(b) * T + t) * ldx;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        if (c < d) lmm_cp_async16(ring + slot * ROW_BYTES + i * 512, row + c);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int t = next_valid(warp);
+  int t_iss = t;
+#pragma unroll
+  for (int s0 = 0; s0 < STAGES - 1; ++s0) {
+    issue(t_iss, s0);
+    if (t_iss < T) t_iss = next_valid(t_iss + LMM_WARPS);
+  }
+  const float inv_d = 1.0f / static_cast<float>(d);
+  int slot = 0;
+  while (t < T) {
+    ++count;
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+    float2 r[NV][4];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 8;
-      raw[i] = c < d ? __ldg(reinterpret_cast<const uint4*>(row + c)) : make_uint4(0u, 0u, 0u, 0u);
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (c < d) u = *reinterpret_cast<const uint4*>(ring_p + slot * ROW_BYTES + i * 512);
+      r[i][0] = make_float2(bf16_lo(u.x), bf16_hi(u.x));
+      r[i][1] = make_float2(bf16_lo(u.y), bf16_hi(u.y));
+      r[i][2] = make_float2(bf16_lo(u.z), bf16_hi(u.z));
+      r[i][3] = make_float2(bf16_lo(u.w), bf16_hi(u.w));
     }
-  };
-  int t = next_valid(warp);
-  if (t < T) fetch(t);
-  while (t < T) {
-    ++count;
-    RowRegs<NV> r;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) unpack8(raw[i], r.v[i]);
-    const int t_next = next_valid(t + 8);
-    if (t_next < T) fetch(t_next);
+    // the slot consumed in the PREVIOUS iteration takes the row STAGES - 1 ahead
+    issue(t_iss, slot == 0 ? STAGES - 1 : slot - 1);
+    if (t_iss < T) t_iss = next_valid(t_iss + LMM_WARPS);
     if (pre_g != nullptr) {
       float m1, r1;
       if (pre_stats != nullptr) {
         const float2 st = __ldg(pre_stats + static_cast<int64_t>(b) * T + t);
         m1 = st.x;
         r1 = st.y;
-      } else {
-        row_stats(r, d, lane, eps, m1, r1);
+      } else {   // two-pass statistics of the raw row (only streams whose producer kept no statistics)
+        float s1 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) s1 += r[i][k].x + r[i][k].y;
+        m1 = warp_sum(s1) * inv_d;
+        float q1 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          if ((i * 32 + lane) * 8 < d) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float a0 = r[i][k].x - m1, a1 = r[i][k].y - m1;
+              q1 += a0 * a0 + a1 * a1;
+            }
+          }
+        }
+        r1 = rsqrtf(warp_sum(q1) * inv_d + eps);
       }
+      const float2 u2 = make_float2(r1, r1), k2 = make_float2(-m1 * r1, -m1 * r1);
 #pragma unroll
       for (int i = 0; i < NV; ++i)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r.v[i][k] = (r.v[i][k] - m1) * r1 * pg.v[i][k] + pb.v[i][k];  // 0 past d
+        for (int k = 0; k < 4; ++k) r[i][k] = ffma2(ffma2(r[i][k], u2, k2), pg[i][k], pb[i][k]);   // 0 past d (pg = pb = 0)
     }
     if (apply_ln) {
-      float m2, r2;
-      row_stats(r, d, lane, eps, m2, r2);
+      float2 sy = make_float2(0.0f, 0.0f), sq = make_float2(0.0f, 0.0f);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = (i * 32 + lane) * 8;
-        if (c < d) {
+      for (int i = 0; i < NV; ++i)
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc.v[i][k] += (r.v[i][k] - m2) * r2;
+        for (int k = 0; k < 4; ++k) {
+          sy = fadd2(sy, r[i][k]);
+          sq = ffma2(r[i][k], r[i][k], sq);
         }
+      float s1 = sy.x + sy.y, s2 = sq.x + sq.y;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
       }
+      const float m2 = s1 * inv_d;
+      const float r2 = rsqrtf(fmaxf(s2 * inv_d - m2 * m2, 0.0f) + eps);
+      side = fmaf(m2, r2, side);
+      const float2 r22 = make_float2(r2, r2);
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[i][k] = ffma2(r[i][k], r22, acc[i][k]);
     } else {
 #pragma unroll
       for (int i = 0; i < NV; ++i)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc.v[i][k] += r.v[i][k];
+        for (int k = 0; k < 4; ++k) acc[i][k] = fadd2(acc[i][k], r[i][k]);
     }
-    t = t_next;
+    slot = slot + 1 == STAGES ? 0 : slot + 1;
+    t = next_valid(t + LMM_WARPS);
   }
-  __shared__ int counts[8];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __shared__ int counts[LMM_WARPS];
   if (lane == 0) counts[warp] = count;
+  __syncthreads();   // every warp is done with its ring: the memory becomes part[8][d]
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
     if (c < d) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) part[warp * d + c + k] = acc.v[i][k];
+      for (int k = 0; k < 4; ++k) {
+        part[warp * d + c + 2 * k] = acc[i][k].x - side;
+        part[warp * d + c + 2 * k + 1] = acc[i][k].y - side;
+      }
     }
   }
   __syncthreads();
   int total = 0;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) total += counts[w];
+  for (int w = 0; w < LMM_WARPS; ++w) total += counts[w];
   // mask None -> plain mean over T; else sum / clamp(count, 1)   (beta_gate_tacfn.py:17-24)
   const float denom = pad == nullptr ? static_cast<float>(T) : fmaxf(static_cast<float>(total), 1.0f);
   const float frac = static_cast<float>(total) / denom;   // 1, or 0 when every row is PAD
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     float s = 0.0f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += part[w * d + c];
+    for (int w = 0; w < LMM_WARPS; ++w) s += part[w * d + c];
     s /= denom;
     pooled[static_cast<int64_t>(b) * ld_pooled + c] = apply_ln ? fmaf(__ldg(gamma + c), s, __ldg(beta + c) * frac) : s;
   }
@@ -615,11 +687,19 @@ extern "C" int hriemo_ln_masked_mean(const void* x, int64_t ldx, const float* ga
   HRIEMO_REQUIRE(row_shape_ok(d) && B > 0 && T > 0, "ln_masked_mean: bad shape B=%d T=%d d=%d", B, T, d);
   HRIEMO_REQUIRE(ldx % 8 == 0 && aligned16(x) && aligned16(gamma) && aligned16(beta),
                  "ln_masked_mean: misaligned operand");
-  const size_t smem = static_cast<size_t>(8) * d * sizeof(float);
-  // 8 * d * 4 bytes <= 48 KB for d <= 1536; the d <= 2048 instance (NV = 8) may need 64 KB
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(ln_masked_mean_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4);
-  HRIEMO_DISPATCH_NV(d, (ln_masked_mean_kernel<NV><<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  // warp-private row rings (8 warps x STAGES x NV * 512 bytes; they hold the 8 x d partial sums afterwards): opt-in size
+  static uint64_t lmm_attr_done = 0;
+  if (device_needs_attr(&lmm_attr_done)) {
+    cudaError_t e = cudaSuccess;
+#define HRIEMO_LMM_ATTR(NVV)                                                                                  \
+    if (e == cudaSuccess)                                                                                     \
+      e = cudaFuncSetAttribute(ln_masked_mean_kernel<NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                               LMM_WARPS * LmmStages<NVV>::value * NVV * 512)
+    HRIEMO_LMM_ATTR(1); HRIEMO_LMM_ATTR(2); HRIEMO_LMM_ATTR(3); HRIEMO_LMM_ATTR(4); HRIEMO_LMM_ATTR(8);
+#undef HRIEMO_LMM_ATTR
+    if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "ln_masked_mean: %s", cudaGetErrorString(e));
+  }
+  HRIEMO_DISPATCH_NV(d, (ln_masked_mean_kernel<NV><<<B, 256, LMM_WARPS * LmmStages<NV>::value * NV * 512, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, apply_ln, pad, pooled, ld_pooled, T, d,
       pre_gamma, pre_beta, reinterpret_cast<const float2*>(pre_stats))));
   return check_launch("ln_masked_mean");

@@ -22,6 +22,8 @@ sgemm_f32_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
   const int tx = tid & 15, ty = tid >> 4;
   const int64_t m0 = static_cast<int64_t>(blockIdx.y) * SG_BM;
   const int n0 = blockIdx.x * SG_BN;
+  const bool relu_in = (act & 4) != 0;   // ReLU applied to A as it is read (the hidden layer arrives pre-activation)
+  act &= 3;
   float acc[4][4] = {};
   const int lr = tid >> 2;        // 0..63: row inside the tile
   const int lk = (tid & 3) * 4;   // 0,4,8,12
@@ -30,7 +32,8 @@ sgemm_f32_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
     for (int i = 0; i < 4; ++i) {
       const int k = k0 + lk + i;
       const int64_t am = m0 + lr;
-      As[lk + i][lr] = (am < M && k < K) ? __ldg(A + am * lda + k) : 0.0f;
+      const float av = (am < M && k < K) ? __ldg(A + am * lda + k) : 0.0f;
+      As[lk + i][lr] = relu_in ? fmaxf(av, 0.0f) : av;
       const int wn = n0 + lr;
       Ws[lk + i][lr] = (wn < N && k < K) ? __ldg(W + static_cast<int64_t>(wn) * ldw + k) : 0.0f;
     }
@@ -175,6 +178,119 @@ small_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const _
   }
 }
 
+// ------------------------------------------------------------------ decoder attention (the common case of the above)
+// N_q <= 8 learned queries against T_k <= 128 keys, no attention map requested (models/emotion_decoder.py:42, :48-54 with
+// return_attention False): the work is reading the memory's [K|V] projection once.  One CTA per (utterance, head); the
+// head's K and V tiles ([T_k][dh] bf16, 12 KB each at 64 x 96) are brought into shared memory with 16-byte cp.async
+// copies issued back to back (24 KB in flight per CTA, ~7 CTAs per SM: HBM-bound), rows padded by 16 bytes so that the
+// thread-per-key score loop reads them without bank conflicts.  The general kernel above read each key row with twelve
+// 16-byte loads per THREAD at a 3 KB stride (32 sectors per request, half of each used): 0.23 of the HBM roofline.
+constexpr int DA_THREADS = 128;
+constexpr int DA_MAX_TK = 128;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(DA_THREADS)
+decoder_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k, int64_t ldk,
+                         const __nv_bfloat16* __restrict__ v, int64_t ldv, const uint8_t* __restrict__ key_pad,
+                         __nv_bfloat16* __restrict__ out, int64_t ldo, int Nq, int Tk, int dh, float scale) {
+  extern __shared__ __align__(16) uint8_t da_smem[];
+  const int pitch = (dh + 8) * 2;                            // bytes per staged row
+  uint8_t* Ks = da_smem;                                     // [Tk][dh + 8] bf16
+  uint8_t* Vs = Ks + static_cast<size_t>(Tk) * pitch;
+  float* qs = reinterpret_cast<float*>(Vs + static_cast<size_t>(Tk) * pitch);   // [SA_NQ][dh], pre-scaled
+  float* sc = qs + SA_NQ * dh;                               // [SA_NQ][Tk]
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cpr = dh / 8;                                    // 16-byte chunks per row
+  const __nv_bfloat16* kb = k + static_cast<int64_t>(b) * Tk * ldk + h * dh;
+  const __nv_bfloat16* vb = v + static_cast<int64_t>(b) * Tk * ldv + h * dh;
+  const uint32_t ks_u = smem_u32(Ks), vs_u = smem_u32(Vs);
+  for (int i = tid; i < Tk * cpr; i += DA_THREADS) {
+    const int r = i / cpr, c = i - r * cpr;
+    cp_async16(ks_u + r * pitch + c * 16, kb + static_cast<int64_t>(r) * ldk + c * 8);
+  }
+  for (int i = tid; i < Tk * cpr; i += DA_THREADS) {
+    const int r = i / cpr, c = i - r * cpr;
+    cp_async16(vs_u + r * pitch + c * 16, vb + static_cast<int64_t>(r) * ldv + c * 8);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < Nq * dh; i += DA_THREADS) {
+    const int qi = i / dh, c = i - qi * dh;
+    qs[i] = __bfloat162float(q[(static_cast<int64_t>(b) * Nq + qi) * ldq + h * dh + c]) * scale;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // scores: thread per key, every query
+  for (int j = tid; j < Tk; j += DA_THREADS) {
+    const bool pad = key_pad != nullptr && key_pad[static_cast<int64_t>(b) * Tk + j] != 0;
+    float acc[SA_NQ];
+#pragma unroll
+    for (int qi = 0; qi < SA_NQ; ++qi) acc[qi] = 0.0f;
+    const uint4* kr = reinterpret_cast<const uint4*>(Ks + static_cast<size_t>(j) * pitch);
+    for (int c = 0; c < cpr; ++c) {
+      const uint4 u = kr[c];
+      const float kv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                           bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+      for (int qi = 0; qi < SA_NQ; ++qi) {
+        if (qi < Nq) {
+          const float4 q0 = *reinterpret_cast<const float4*>(qs + qi * dh + c * 8);
+          const float4 q1 = *reinterpret_cast<const float4*>(qs + qi * dh + c * 8 + 4);
+          acc[qi] = fmaf(q0.x, kv[0], fmaf(q0.y, kv[1], fmaf(q0.z, kv[2], fmaf(q0.w, kv[3], acc[qi]))));
+          acc[qi] = fmaf(q1.x, kv[4], fmaf(q1.y, kv[5], fmaf(q1.z, kv[6], fmaf(q1.w, kv[7], acc[qi]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < SA_NQ; ++qi)
+      if (qi < Nq) sc[qi * Tk + j] = pad ? -INFINITY : acc[qi];
+  }
+  __syncthreads();
+  // softmax per query row (a fully masked row gives NaN, like torch.softmax)
+  for (int qi = warp; qi < Nq; qi += DA_THREADS / 32) {
+    float m = -INFINITY;
+    for (int j = lane; j < Tk; j += 32) m = fmaxf(m, sc[qi * Tk + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.0f;
+    for (int j = lane; j < Tk; j += 32) {
+      const float e = expf(sc[qi * Tk + j] - m);
+      sc[qi * Tk + j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < Tk; j += 32) sc[qi * Tk + j] *= inv;
+  }
+  __syncthreads();
+  // P.V: thread per pair of columns
+  for (int c2 = tid; c2 < dh / 2; c2 += DA_THREADS) {
+    float a0[SA_NQ], a1[SA_NQ];
+#pragma unroll
+    for (int qi = 0; qi < SA_NQ; ++qi) a0[qi] = a1[qi] = 0.0f;
+    for (int j = 0; j < Tk; ++j) {
+      const uint32_t vv = *reinterpret_cast<const uint32_t*>(Vs + static_cast<size_t>(j) * pitch + c2 * 4);
+      const float v0 = bf16_lo(vv), v1 = bf16_hi(vv);
+#pragma unroll
+      for (int qi = 0; qi < SA_NQ; ++qi) {
+        if (qi < Nq) {
+          const float pr = sc[qi * Tk + j];
+          a0[qi] = fmaf(pr, v0, a0[qi]);
+          a1[qi] = fmaf(pr, v1, a1[qi]);
+        }
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < SA_NQ; ++qi)
+      if (qi < Nq)
+        *reinterpret_cast<uint32_t*>(out + (static_cast<int64_t>(b) * Nq + qi) * ldo + h * dh + c2 * 2) = pack_bf16(a0[qi], a1[qi]);
+  }
+}
+
 // ------------------------------------------------------------------ small attention, backward (training)
 // Gradients of the decoder attention (models/emotion_decoder.py:42, :48-54; N_q learned queries, T_k keys) for one
 // (utterance, head) per CTA.  P is rebuilt from q, k (exact softmax, as in the forward); then
@@ -298,6 +414,21 @@ __global__ void emotion_outputs_kernel(const float* __restrict__ logits, const f
 static int launch_small_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                                   int64_t ldv, const uint8_t* key_pad, void* out, int64_t ldo, float* probs,
                                   int B, int H, int Nq, int Tk, int dh, float scale, cudaStream_t s) {
+  if (probs == nullptr && out != nullptr && v != nullptr && Nq <= SA_NQ && Tk <= DA_MAX_TK && dh <= 128 && H <= 65535 &&
+      ldv % 8 == 0 && ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(v) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
+    // the decoder's own shapes: K / V staged in shared memory (see decoder_attention_kernel)
+    const size_t sm = static_cast<size_t>(2) * Tk * (dh + 8) * 2 + sizeof(float) * (static_cast<size_t>(SA_NQ) * dh + static_cast<size_t>(SA_NQ) * Tk);
+    static uint64_t da_attr_done = 0;
+    if (sm > 48 * 1024 && device_needs_attr(&da_attr_done)) {
+      cudaError_t e = cudaFuncSetAttribute(decoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "small_attention: %s", cudaGetErrorString(e));
+    }
+    dim3 grid(B, H);
+    decoder_attention_kernel<<<grid, DA_THREADS, sm, s>>>(
+        static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k), ldk,
+        static_cast<const __nv_bfloat16*>(v), ldv, key_pad, static_cast<__nv_bfloat16*>(out), ldo, Nq, Tk, dh, scale);
+    return check_launch("small_attention");
+  }
   const size_t smem = sizeof(float) * (static_cast<size_t>(SA_NQ) * dh + static_cast<size_t>(SA_NQ) * Tk * (probs ? 2 : 1));
   if (smem > 200 * 1024) return set_error(HRIEMO_ERR_INVALID, "small_attention: Tk=%d too long", Tk);
   static uint64_t attr_done = 0;
@@ -323,7 +454,7 @@ extern "C" int hriemo_sgemm_f32(const float* A, int64_t lda, const float* W, int
                                 void* stream) {
   HRIEMO_REQUIRE(A && W && out, "sgemm: null pointer");
   HRIEMO_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ldo >= N, "sgemm: bad shape");
-  HRIEMO_REQUIRE(act >= 0 && act <= 2, "sgemm: unknown activation %d", act);
+  HRIEMO_REQUIRE(act >= 0 && (act & 3) <= 2 && act <= 6, "sgemm: unknown activation %d", act);
   if (M == 0) return HRIEMO_OK;
   HRIEMO_REQUIRE((M + SG_BM - 1) / SG_BM <= 65535, "sgemm: M too large");
   dim3 grid((N + SG_BN - 1) / SG_BN, static_cast<unsigned>((M + SG_BM - 1) / SG_BM));

@@ -261,17 +261,32 @@ def dec_residual_ln(pre32: torch.Tensor, ln) -> Tuple[torch.Tensor, torch.Tensor
     return ops.layernorm(pre32, ln[0], ln[1], want_bf16=True, want_f32=True)
 
 
-def decoder_layer(zb, z32, kv_mem, mem_mask, P: dict, B: int, Ne: int, Lm: int, n_heads: int,
-                  want_attn: bool, tape: Optional[dict] = None):
-    """models/emotion_decoder.py:33-64.  kv_mem = [K|V] projection of the memory for this layer.
-    tape (training): receives the activations the backward pass needs (hriemo/backward.py)."""
+def decoder_self_block(zb, z32, P: dict, B: int, Ne: int, n_heads: int):
+    """LN(z + MHA(z, z, z)) over the N_e queries (models/emotion_decoder.py:42-43) -> (zb1, z32_1, (qkv, sa, pre1))."""
     d = zb.shape[1]
     dh = d // n_heads
-    zb_in = zb
     qkv = ops.gemm(zb, P["self"]["w_qkv"], P["self"]["b_qkv"], L.EPI_BIAS)
     sa, _ = ops.small_attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], None, B, n_heads, Ne, Ne, dh)
     pre1 = ops.gemm(sa, P["self"]["w_o"], P["self"]["b_o"], L.EPI_BIAS_RESID_F32, resid=z32)
     zb1, z32 = dec_residual_ln(pre1, P["norm1"])
+    return zb1, z32, (qkv, sa, pre1)
+
+
+def decoder_layer(zb, z32, kv_mem, mem_mask, P: dict, B: int, Ne: int, Lm: int, n_heads: int,
+                  want_attn: bool, tape: Optional[dict] = None, pre_self=None):
+    """models/emotion_decoder.py:33-64.  kv_mem = [K|V] projection of the memory for this layer.
+    tape (training): receives the activations the backward pass needs (hriemo/backward.py).
+    pre_self = (zb1, z32_1): the self-attention block's output when it is already known -- the first layer's input is
+    the broadcast Parameter (models/emotion_decoder.py:127), so its self-attention block does not depend on the
+    utterance and is computed once per weight set (EmotionDecoder._build)."""
+    d = (zb if pre_self is None else pre_self[0]).shape[1]
+    dh = d // n_heads
+    zb_in = zb
+    if pre_self is None:
+        zb1, z32, (qkv, sa, pre1) = decoder_self_block(zb, z32, P, B, Ne, n_heads)
+    else:
+        zb1, z32 = pre_self
+        qkv = sa = pre1 = None
     q = ops.gemm(zb1, P["cross_wq"], P["cross_bq"], L.EPI_BIAS)
     ca, probs = ops.small_attention(q, kv_mem[:, :d], kv_mem[:, d:], mem_mask, B, n_heads, Ne, Lm, dh,
                                     want_probs=want_attn)

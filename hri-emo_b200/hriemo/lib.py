@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("HRIEMO_LIB_PATH") or os.path.join(_HERE, "libhriemo_b
 
 EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESID, EPI_BIAS_RESID_F32, _EPI_RETIRED, EPI_BIAS_F32 = range(6)
 ACT_NONE, ACT_RELU, ACT_SIGMOID = range(3)
+ACT_RELU_IN = 4   # or-ed in: ReLU on the sgemm's A operand as it is read
 
 
 class HriemoError(RuntimeError):

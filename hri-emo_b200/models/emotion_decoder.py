@@ -50,8 +50,10 @@ class ExplainableDecoderLayer(nn.Module):
         P = self._prep.get()
         return ops.gemm(mem.x, P["cross_wkv"], P["cross_bkv"], L.EPI_BIAS)  # [B*L, 2d] = [K|V]
 
-    def run(self, zb, z32, kv_mem, mem_mask, B: int, Ne: int, Lm: int, want_attn: bool, tape: dict | None = None):
-        return E.decoder_layer(zb, z32, kv_mem, mem_mask, self._prep.get(), B, Ne, Lm, self.nhead, want_attn, tape)
+    def run(self, zb, z32, kv_mem, mem_mask, B: int, Ne: int, Lm: int, want_attn: bool, tape: dict | None = None,
+            pre_self=None):
+        return E.decoder_layer(zb, z32, kv_mem, mem_mask, self._prep.get(), B, Ne, Lm, self.nhead, want_attn, tape,
+                               pre_self)
 
     @torch.no_grad()
     def forward(self, tgt, memory, memory_key_padding_mask=None, return_attention=False):
@@ -85,6 +87,13 @@ class EmotionDecoder(nn.Module):
 
     def _build(self) -> dict:
         p = dict(q32=E.v32(self.emotion_queries))
+        if len(self.layers):
+            # layer 0's self-attention block sees only the learned queries (reference :127 broadcasts the Parameter), so
+            # LN(q + MHA(q, q, q)) is the same [N_e, d] matrix for every utterance: computed here once per weight set
+            q32 = p["q32"]
+            zb1, z32_1, _ = E.decoder_self_block(ops.cast_bf16(q32), q32, self.layers[0]._prep.get(), 1, self.num_emotions,
+                                                 self.layers[0].nhead)
+            p.update(self0_b=zb1, self0_f=z32_1)
         if self.out_proj is not None:
             p.update(w_out=E.v32(self.out_proj.weight), b_out=E.v32(self.out_proj.bias))
         return p
@@ -93,15 +102,23 @@ class EmotionDecoder(nn.Module):
         """tapes (training): a list that receives one dict of saved activations per layer (hriemo/backward.py)."""
         P = self._prep.get()
         B, Ne, d = mem.B, self.num_emotions, self.d_model
-        z32 = P["q32"].unsqueeze(0).expand(B, Ne, d).contiguous().view(B * Ne, d)  # :127 (broadcast copy)
-        zb = ops.cast_bf16(z32)
+        zb = z32 = None
+        if tapes is not None or not len(self.layers):
+            z32 = P["q32"].unsqueeze(0).expand(B, Ne, d).contiguous().view(B * Ne, d)  # :127 (broadcast copy)
+            zb = ops.cast_bf16(z32)
         attn = []
-        for layer in self.layers:
+        for li, layer in enumerate(self.layers):
             tape = None
             if tapes is not None:
                 tape = {}
                 tapes.append(tape)
-            zb, z32, probs = layer.run(zb, z32, layer.project_memory(mem), mem_mask, B, Ne, mem.T, want_attn, tape)
+            pre_self = None
+            if li == 0 and tapes is None:   # inference: the precomputed block, broadcast over the batch (training keeps
+                # the full schedule: the backward pass needs the block's activations for its parameter gradients)
+                pre_self = (P["self0_b"].unsqueeze(0).expand(B, Ne, d).contiguous().view(B * Ne, d),
+                            P["self0_f"].unsqueeze(0).expand(B, Ne, d).contiguous().view(B * Ne, d))
+            zb, z32, probs = layer.run(zb, z32, layer.project_memory(mem), mem_mask, B, Ne, mem.T, want_attn, tape,
+                                       pre_self)
             if want_attn and probs is not None:
                 attn.append(probs)
         logits = None

@@ -201,7 +201,7 @@ int hriemo_gate_input(const float* a_pool, const float* t_pool, float* g, int32_
                       void* stream);
 
 /* Small fp32 GEMM on CUDA cores: out = act(A[M,K] . W[N,K]^T + bias), act in
- * {0 none, 1 relu, 2 sigmoid}.  Used where the reference result feeds a
+ * {0 none, 1 relu, 2 sigmoid}; act | 4: ReLU is applied to A as it is read.  Used where the reference result feeds a
  * bit-sensitive decision (gate MLP models/beta_gate_tacfn.py:62-66,92; emotion
  * head models/emotion_decoder.py:155; classifier models/fusion_classifier.py:74-77). */
 int hriemo_sgemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,

@@ -45,6 +45,12 @@ def gemm(a, w, bias, epilogue=EPI_BIAS, resid=None, out=None, cta_pair=0, a_ln=N
     return y if epilogue in (EPI_BIAS_RESID_F32, EPI_BIAS_F32) else y.to(LO)
 
 
+def split3(x, weight=False, relu=False):
+    """hi + lo split operands of the tf32-class GEMM: the stand-in keeps the value in one piece (only the modules'
+    prepared-operand caches call it on this path)."""
+    return (torch.relu(x) if relu else x).to(LO)
+
+
 def fold_ln_weight(w, bias, gamma, beta, *args, **kwargs):
     """Built by the modules' prepared-operand caches; the training schedule never reads the folded operands."""
     wf = (w * gamma[None, :]).to(LO)
@@ -53,6 +59,8 @@ def fold_ln_weight(w, bias, gamma, beta, *args, **kwargs):
 
 def sgemm(a, w, bias, act=ACT_NONE):
     assert a.dtype == HI and w.dtype == HI
+    if act & 4:
+        a, act = torch.relu(a), act & 3
     y = a @ w.t() + (bias if bias is not None else 0)
     return torch.relu(y) if act == ACT_RELU else (torch.sigmoid(y) if act == ACT_SIGMOID else y)
 
