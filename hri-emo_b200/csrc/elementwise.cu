@@ -534,9 +534,32 @@ layernorm_backward_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, cons
     RowRegs<NV> xr, gr;
     load_row<false, NV>(xr, x + row * ldx, d, lane);
     load_row<false, NV>(gr, dy + row * lddy, d, lane);
-    float mean, rstd;
-    row_stats(xr, d, lane, eps, mean, rstd);
-    float s1 = 0.0f, s2 = 0.0f;
+    // ONE round of warp shuffles per row: sum x, sum x^2, sum g, sum g x (g = dy gamma) are reduced together, and
+    // sum g xhat = rstd (sum g x - mean sum g).  (The two-pass statistics + two more sums cost four dependent rounds.)
+    float sx = 0.0f, sxx = 0.0f, sg = 0.0f, sgx = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {   // columns past d hold zeros (load_row) and gm = 0 there
+        const float xv = xr.v[i][k];
+        const float g = gr.v[i][k] * gm.v[i][k];
+        sx += xv;
+        sxx = fmaf(xv, xv, sxx);
+        sg += g;
+        sgx = fmaf(g, xv, sgx);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sxx += __shfl_xor_sync(0xffffffffu, sxx, o);
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+    }
+    const float mean = sx * inv_d;
+    const float rstd = rsqrtf(fmaxf(sxx * inv_d - mean * mean, 0.0f) + eps);
+    const float s1 = sg * inv_d;
+    const float s2 = rstd * (sgx - mean * sg) * inv_d;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 8;
@@ -545,22 +568,12 @@ layernorm_backward_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, cons
         for (int k = 0; k < 8; ++k) {
           const float xh = (xr.v[i][k] - mean) * rstd;
           const float dyv = gr.v[i][k];
-          g_acc.v[i][k] += dyv * xh;
+          g_acc.v[i][k] = fmaf(dyv, xh, g_acc.v[i][k]);
           b_acc.v[i][k] += dyv;
-          const float g = dyv * gm.v[i][k];
-          xr.v[i][k] = xh;        // keep xhat
-          gr.v[i][k] = g;         // and g = dy * gamma
-          s1 += g;
-          s2 += g * xh;
+          gr.v[i][k] = rstd * (dyv * gm.v[i][k] - s1 - xh * s2);
         }
       }
     }
-    s1 = warp_sum(s1) * inv_d;
-    s2 = warp_sum(s2) * inv_d;
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) gr.v[i][k] = rstd * (gr.v[i][k] - s1 - xr.v[i][k] * s2);
     store_row(gr, dx + row * lddx, nullptr, d, lane);
   }
 #pragma unroll

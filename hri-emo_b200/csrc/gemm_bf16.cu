@@ -228,7 +228,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const bool bf16_out = p.epilogue != HRIEMO_EPI_BIAS_RESID_F32 && p.epilogue != HRIEMO_EPI_BIAS_F32;
     // bf16 residual (pre-LayerNorm epilogue): the [32 x 64] residual box of the NEXT slab is
     // prefetched by TMA into the idle staging buffer and the sum is formed in place.
-    const bool tma_resid = p.epilogue == HRIEMO_EPI_BIAS_RESID;
+    const bool tma_resid = p.epilogue == HRIEMO_EPI_BIAS_RESID || p.epilogue == HRIEMO_EPI_BIAS_MASK;
+    const bool mask_mode = p.epilogue == HRIEMO_EPI_BIAS_MASK;   // the box is the forward's post-ReLU hidden: out = box > 0 ? acc : 0
     const uint32_t my_rbar = bar_resid + static_cast<uint32_t>(ew) * 16;
     auto prefetch_resid = [&](int64_t tile_, int slab_, uint32_t ctr_) {
       const int n_ = static_cast<int>(tile_ % p.num_n_blocks) * BN + slab_ * 64;
@@ -348,8 +349,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 r[2] = ffma2(ffma2(r[2], rs, rh), make_float2(g1.x, g1.y), make_float2(b1.x, b1.y));
                 r[3] = ffma2(ffma2(r[3], rs, rh), make_float2(g1.z, g1.w), make_float2(b1.z, b1.w));
               }
+              if (mask_mode) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) f2[i * 4 + k] = fadd2(f2[i * 4 + k], r[k]);
+                for (int k = 0; k < 4; ++k)
+                  f2[i * 4 + k] = make_float2(r[k].x > 0.0f ? f2[i * 4 + k].x : 0.0f, r[k].y > 0.0f ? f2[i * 4 + k].y : 0.0f);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) f2[i * 4 + k] = fadd2(f2[i * 4 + k], r[k]);
+              }
             }
           } else if (p.epilogue == HRIEMO_EPI_BIAS_RESID_F32 && row_ok) {
             const float4* rp =
@@ -454,7 +461,7 @@ static int launch_gemm(const hriemo_gemm_args& a, cudaStream_t stream) {
     if (rc) return rc;
   }
   tm_r = tm_a;  // only read by the bf16 residual epilogue
-  if (a.epilogue == HRIEMO_EPI_BIAS_RESID) {
+  if (a.epilogue == HRIEMO_EPI_BIAS_RESID || a.epilogue == HRIEMO_EPI_BIAS_MASK) {
     rc = make_tmap_bf16_2d(&tm_r, a.resid, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldr, 64, 32);
     if (rc) return rc;
   }
@@ -510,14 +517,14 @@ extern "C" int hriemo_gemm_bf16(const hriemo_gemm_args* a, void* stream) {
                  "gemm: K=%d, lda=%lld, ldw=%lld must be multiples of 8", a->K, (long long)a->lda,
                  (long long)a->ldw);
   HRIEMO_REQUIRE(a->lda >= a->K && a->ldw >= a->K, "gemm: leading dimension smaller than K");
-  HRIEMO_REQUIRE(a->epilogue >= HRIEMO_EPI_BIAS && a->epilogue <= HRIEMO_EPI_BIAS_F32 && a->epilogue != 4,
+  HRIEMO_REQUIRE(a->epilogue >= HRIEMO_EPI_BIAS && a->epilogue <= HRIEMO_EPI_BIAS_MASK && a->epilogue != 4,
                  "gemm: unknown epilogue %d", a->epilogue);
   HRIEMO_REQUIRE(a->cta_pair >= 0 && a->cta_pair <= 2, "gemm: cta_pair=%d (0 auto, 1 single, 2 pair)", a->cta_pair);
   HRIEMO_REQUIRE(a->cta_pair != 2 || a->N % 256 == 0, "gemm: CTA-pair tiles need N %% 256 == 0 (N=%d)", a->N);
   const bool f32_out = a->epilogue == HRIEMO_EPI_BIAS_RESID_F32 || a->epilogue == HRIEMO_EPI_BIAS_F32;
   HRIEMO_REQUIRE(a->ldo % (f32_out ? 4 : 8) == 0, "gemm: ldo=%lld misaligned", (long long)a->ldo);
   HRIEMO_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15u) == 0, "gemm: out not 16-byte aligned");
-  if (a->epilogue == HRIEMO_EPI_BIAS_RESID || a->epilogue == HRIEMO_EPI_BIAS_RESID_F32) {
+  if (a->epilogue == HRIEMO_EPI_BIAS_RESID || a->epilogue == HRIEMO_EPI_BIAS_RESID_F32 || a->epilogue == HRIEMO_EPI_BIAS_MASK) {
     HRIEMO_REQUIRE(a->resid != nullptr, "gemm: residual epilogue without resid");
     HRIEMO_REQUIRE(a->ldr % (f32_out ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(a->resid) & 15u) == 0,
                    "gemm: resid misaligned");

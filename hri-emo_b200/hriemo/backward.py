@@ -115,8 +115,7 @@ def _decoder_layer_backward(P: dict, tape: dict, dz: torch.Tensor, d_mem: Option
     G: Grads = {}
     # ---- z3 = LN3(z2 + W2 relu(W1 z2 + b1) + b2)                                              :58-59
     d_pre3, G["norm3.weight"], G["norm3.bias"] = ops.layernorm_backward(ops.cast_bf16(tape["pre3"]), dz, P["norm3"][0])
-    d_hpost, G["linear2.weight"], G["linear2.bias"] = ops.linear_backward(d_pre3, tape["h"], _t(P["lin2"]["w"]))
-    d_hid = ops.relu_backward(d_hpost, tape["h"])
+    d_hid, G["linear2.weight"], G["linear2.bias"] = ops.linear_backward(d_pre3, tape["h"], _t(P["lin2"]["w"]), relu_input=True)
     G["linear1.weight"], G["linear1.bias"] = ops.linear_wgrad(d_hid, tape["zb2"])
     dz2 = ops.gemm(d_hid, _t(P["lin1"]["w"]), None, L.EPI_BIAS_RESID, resid=d_pre3, tag="dgrad")
     # ---- z2 = LN2(z1 + MHA(z1, mem, mem))                                                     :48-55
@@ -194,8 +193,8 @@ def _ffn_forward(x: torch.Tensor, P1: dict, P2: dict, ln, tape: dict, key: str) 
 
 def _ffn_backward(dy: torch.Tensor, P1: dict, P2: dict, ln, tp: dict, G: Grads, name: str, norm: str) -> torch.Tensor:
     d_pre, G[f"{norm}.weight"], G[f"{norm}.bias"] = ops.layernorm_backward(tp["pre"], dy, ln[0])
-    d_hpost, G[f"{name}.2.weight"], G[f"{name}.2.bias"] = ops.linear_backward(d_pre, tp["h"], _t(P2["w"]))
-    d_h = ops.relu_backward(d_hpost, tp["h"])
+    # d_h = (d_pre . W2) * (h > 0): the ReLU mask is the epilogue of the input-gradient GEMM
+    d_h, G[f"{name}.2.weight"], G[f"{name}.2.bias"] = ops.linear_backward(d_pre, tp["h"], _t(P2["w"]), relu_input=True)
     G[f"{name}.0.weight"], G[f"{name}.0.bias"] = ops.linear_wgrad(d_h, tp["x"])
     return ops.gemm(d_h, _t(P1["w"]), None, L.EPI_BIAS_RESID, resid=d_pre, tag="dgrad")
 

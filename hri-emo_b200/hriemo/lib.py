@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # HRIEMO_LIB_PATH: an alternative build of the same library (tools/ A/B experiments only)
 LIB_PATH = os.environ.get("HRIEMO_LIB_PATH") or os.path.join(_HERE, "libhriemo_b200.so")
 
-EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESID, EPI_BIAS_RESID_F32, _EPI_RETIRED, EPI_BIAS_F32 = range(6)
+EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESID, EPI_BIAS_RESID_F32, _EPI_RETIRED, EPI_BIAS_F32, EPI_BIAS_MASK = range(7)
 ACT_NONE, ACT_RELU, ACT_SIGMOID = range(3)
 ACT_RELU_IN = 4   # or-ed in: ReLU on the sgemm's A operand as it is read
 

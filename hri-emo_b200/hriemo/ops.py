@@ -565,10 +565,14 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: Optional[torch.Tensor] =
     return dw, db
 
 
-def linear_backward(dy: torch.Tensor, x: torch.Tensor, w_t: torch.Tensor, want_bias: bool = True):
+def linear_backward(dy: torch.Tensor, x: torch.Tensor, w_t: torch.Tensor, want_bias: bool = True, relu_input: bool = False):
     """(dx bf16 [M, K], dW fp32 [N, K], db fp32 [N] | None) of y = x W^T + b given dy [M, N] (bf16), the layer's
-    input x [M, K] (bf16) and the TRANSPOSED weight w_t = transpose_bf16(W) [K, N]."""
-    dx = gemm(dy, _as_gemm_weight(w_t, x.shape[1]), None, _l.EPI_BIAS, tag="dgrad")
+    input x [M, K] (bf16) and the TRANSPOSED weight w_t = transpose_bf16(W) [K, N].  relu_input: x = relu(z) and the
+    gradient wanted is dz = dx * (x > 0) -- the mask is applied in the GEMM's epilogue (EPI_BIAS_MASK)."""
+    if relu_input:
+        dx = gemm(dy, _as_gemm_weight(w_t, x.shape[1]), None, _l.EPI_BIAS_MASK, resid=x, tag="dgrad")
+    else:
+        dx = gemm(dy, _as_gemm_weight(w_t, x.shape[1]), None, _l.EPI_BIAS, tag="dgrad")
     dw, db = linear_wgrad(dy, x, want_bias=want_bias)
     return dx, dw, db
 

@@ -66,7 +66,10 @@ enum {
   HRIEMO_EPI_BIAS_RELU = 1,      /* out bf16 = relu(acc + bias)            (FFN first half) */
   HRIEMO_EPI_BIAS_RESID = 2,     /* out bf16 = acc + bias + resid(bf16)    (pre-LayerNorm)  */
   HRIEMO_EPI_BIAS_RESID_F32 = 3, /* out f32  = acc + bias + resid(f32)     (decoder stream) */
-  HRIEMO_EPI_BIAS_F32 = 5        /* out f32  = acc + bias   (4 is retired: a transposed-V epilogue) */
+  HRIEMO_EPI_BIAS_F32 = 5,       /* out f32  = acc + bias   (4 is retired: a transposed-V epilogue) */
+  HRIEMO_EPI_BIAS_MASK = 6       /* out bf16 = resid(bf16) > 0 ? acc + bias : 0: the input gradient of a Linear whose INPUT
+                                    was relu(.) -- resid is that post-ReLU tensor (models/cross_modal_block_tacfn.py:46
+                                    under loss.backward()) */
 };
 
 typedef struct hriemo_gemm_args {

@@ -17,7 +17,7 @@ bf16, f32 = torch.bfloat16, torch.float32
 # install(..., exact=True) turns every dtype into float64 and every rounding into the identity: the schedule
 # must then agree with autograd to round-off, which separates logic errors from bf16 noise.
 LO, HI = bf16, f32
-EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESID, EPI_BIAS_RESID_F32, _, EPI_BIAS_F32 = range(6)
+EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESID, EPI_BIAS_RESID_F32, _, EPI_BIAS_F32, EPI_BIAS_MASK = range(7)
 ACT_NONE, ACT_RELU, ACT_SIGMOID = range(3)
 EPS = 1e-5
 
@@ -40,6 +40,9 @@ def gemm(a, w, bias, epilogue=EPI_BIAS, resid=None, out=None, cta_pair=0, a_ln=N
         assert resid is not None and resid.dtype == (HI if epilogue == EPI_BIAS_RESID_F32 else LO)
         assert resid.shape == y.shape
         y = y + resid.to(HI)
+    elif epilogue == EPI_BIAS_MASK:
+        assert resid is not None and resid.dtype == LO and resid.shape == y.shape
+        y = y * (resid > 0).to(HI)
     else:
         assert resid is None
     return y if epilogue in (EPI_BIAS_RESID_F32, EPI_BIAS_F32) else y.to(LO)
@@ -181,9 +184,9 @@ def linear_wgrad(dy, x, dw=None, db=None, want_bias=True, accumulate=False):
     return dw, db
 
 
-def linear_backward(dy, x, w_t, want_bias=True):
+def linear_backward(dy, x, w_t, want_bias=True, relu_input=False):
     assert w_t.shape == (x.shape[1], dy.shape[1]), "w_t must be the transposed weight [K, N]"
-    dx = gemm(dy, w_t, None, EPI_BIAS)
+    dx = gemm(dy, w_t, None, EPI_BIAS_MASK, resid=x) if relu_input else gemm(dy, w_t, None, EPI_BIAS)
     dw, db = linear_wgrad(dy, x, want_bias=want_bias)
     return dx, dw, db
 

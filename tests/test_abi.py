@@ -85,6 +85,30 @@ def test_argument_validation_without_gpu(lib):
     assert rc == -1 and b"head dim" in lib.hriemo_last_error()
 
 
+def test_hard_limits_are_reported_not_crashed(lib):
+    """The documented limits of the path come back as error codes with a message: key sequences
+    too long for the shared-memory key caps, rows wider than 2048, unknown GEMM epilogues, fp32 attention key rows."""
+    from hriemo import lib as L
+
+    t = L.AttnArgs()
+    t.q, t.k, t.v, t.out = 16, 16, 16, 16
+    t.B, t.H, t.Tq, t.Tk, t.dh, t.ldq, t.ldk, t.ldv, t.ldo = 1, 8, 64, 40000, 96, 768, 768, 768, 768
+    t.scale = 0.1
+    assert lib.hriemo_attention_bf16(ctypes.byref(t), None) == -1 and b"too long" in lib.hriemo_last_error()
+    rc = lib.hriemo_layernorm(16, 0, 4096, 16, 16, 1e-5, 16, None, 4096, 8, 4096, None)
+    assert rc == -1 and b"<= 2048" in lib.hriemo_last_error()
+    a = L.GemmArgs()
+    a.A, a.W, a.out = 16, 16, 16
+    a.M, a.N, a.K, a.lda, a.ldw, a.ldo, a.epilogue = 128, 128, 64, 64, 64, 128, 4
+    assert lib.hriemo_gemm_bf16(ctypes.byref(a), None) == -1 and b"unknown epilogue" in lib.hriemo_last_error()
+    a.epilogue = L.EPI_BIAS_MASK   # the ReLU-mask epilogue needs the post-ReLU tensor
+    assert lib.hriemo_gemm_bf16(ctypes.byref(a), None) == -1 and b"without resid" in lib.hriemo_last_error()
+    rc = lib.hriemo_attention_f32(16, 768, 16, 768, 16, 768, None, 16, 768, None, 1, 8, 4, 100000, 96, 0.1, None)
+    assert rc == -1 and b"too long" in lib.hriemo_last_error()
+    rc = lib.hriemo_split3(16, 64, 16, 100, 4, 64, 0, 0, None)
+    assert rc == -1 and b"3 * roundup" in lib.hriemo_last_error()
+
+
 def test_ops_refuse_cpu_tensors():
     import torch
     from hriemo import lib as L, ops

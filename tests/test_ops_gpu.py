@@ -847,3 +847,22 @@ def test_kernels_do_not_write_outside_their_outputs():
     except Exception:   # the wrapper may insist on a contiguous dw: then there is nothing to guard here
         return
     chk("linear wgrad")
+
+
+@pytest.mark.parametrize("pair,N", [(1, 288), (2, 512), (0, 3072)])
+def test_gemm_relu_mask_epilogue(pair, N):
+    """EPI_BIAS_MASK: the input gradient of a Linear fed by relu(.) with the mask applied in the epilogue -- equal to the
+    plain GEMM followed by hriemo_relu_backward_bf16."""
+    from hriemo import lib as L, ops
+
+    g = torch.Generator(device=DEV).manual_seed(N)
+    M, K = 389 if N < 1024 else 2048, 136 if N < 1024 else 768
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = torch.randn(N, K, device=DEV, generator=g).bfloat16()
+    h = torch.relu(torch.randn(M, N, device=DEV, generator=g)).bfloat16()
+    got = ops.gemm(a, w, None, L.EPI_BIAS_MASK, resid=h, cta_pair=pair)
+    plain = ops.gemm(a, w, None, L.EPI_BIAS, cta_pair=pair)
+    assert torch.equal(got, ops.relu_backward(plain, h))
+    ref = (a.double() @ w.double().t()) * (h > 0)
+    assert (got.double() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    assert bool((got[h <= 0] == 0).all())
