@@ -33,6 +33,7 @@
 
 #include <type_traits>
 
+#include "dropout.cuh"
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 
@@ -57,8 +58,8 @@ struct Attn3Smem {
   static constexpr int K_OFF = Q_OFF + 4 * Q_TILE;
   static constexpr int V_OFF = K_OFF + KV_STAGES * K_STAGE;
   static constexpr int BAR_OFF = V_OFF + KV_STAGES * V_STAGE;
-  // q_full[2][2] q_empty[2][2] k_full[3] k_empty[3] v_full[3] v_empty[3] s_full[2][2] p_full[2][2] pv_done[2][2]
-  static constexpr int NUM_BARS = 32;
+  // q_full[2][2] q_empty[2][2] k_full[3] k_empty[3] v_full[3] v_empty[3] s_full[2][2] p_full[2][2] pv_done[2][2] s_free[2][2]
+  static constexpr int NUM_BARS = 36;
   static constexpr int TMEM_SLOT_OFF = BAR_OFF + NUM_BARS * 8;
   static constexpr int DYN_OFF = TMEM_SLOT_OFF + 16;   // caps[2][n_kv*64] f32, flags[2][n_kv] i32
   static int dyn_bytes(int n_kv) { return DYN_OFF + 2 * n_kv * A3_BKV * 4 + 2 * n_kv * 4 + 1024; }
@@ -90,6 +91,8 @@ struct Attn3Params {
   int contiguous;   // item -> CTA assignment, see the kernel
   int64_t n_items;
   float scale_log2;
+  uint32_t drop_p8, drop_key;   // dropout on the probabilities (training): 0 = off
+  float drop_scale;             // 1 / (1 - p), folded into the final 1 / l
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -170,15 +173,44 @@ __device__ __forceinline__ void exp_pack_x(const float2 (&x)[16], float (&l4)[4]
   l4[0] = la.x; l4[2] = la.y; l4[1] = lb.x; l4[3] = lb.y;
 }
 
-template <int DH, bool PAIRED, bool DEFER>
+// Dropout on 32 probabilities packed as bf16 pairs (pk[i] = keys 2 i, 2 i + 1 of the chunk whose first hash word is w0):
+// dropped ones become exact zeros; the row sums were taken before (torch normalises first and drops afterwards).
+__device__ __forceinline__ void drop_pk(uint32_t (&pk)[16], uint32_t dbase, uint32_t w0, uint32_t p8) {
+#pragma unroll
+  for (int wi = 0; wi < 8; ++wi) {
+    const uint32_t word = drop_mix(dbase + (w0 + wi) * DROP_C_WORD);
+    pk[2 * wi] &= drop_pair_mask(word, 0, p8);
+    pk[2 * wi + 1] &= drop_pair_mask(word, 1, p8);
+  }
+}
+
+// DROP: the training instances that apply dropout to the probabilities -- a template parameter, not a runtime branch: with
+// the branch in the loop the inference kernels ran 4 - 11 % slower (500x500 0.546 against 0.525 ms) although it was
+// never taken.
+template <int DH, bool PAIRED, bool DEFER, bool DROP = false>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                       const Attn3Params p) {
   using L = Attn3Smem<DH>;
   constexpr uint32_t TMEM_COLS = 512;
-  constexpr uint32_t TILE_COLS = 256;   // per query tile: S0 at +0, S1 at +64, O at +128
-  constexpr uint32_t O_COL = 128;
+  constexpr uint32_t TILE_COLS = 256;   // per query tile: S0 at +0, S1 at +64, O at +128 (PSEP: P at +128, O at +160)
+  // PSEP (long-key general form, dh <= 96): P does NOT overlay the S buffer it was computed from but lives in the 32
+  // columns that are spare next to 2 x 64 (S) + dh (O).  An S buffer is then free again as soon as the warpgroup holds
+  // its scores in registers (s_free), not only after PV has read P out of it: S(g+2) is issued at the START of step g
+  // instead of behind PV(g), so S(j+1) has landed when step j begins and its tensor-memory load can pass under the
+  // exponentials of step j (with P over S the look-ahead was less than one step: r02_attention_issue_notes.txt item 8).
+  // Measured: NOT faster (500x500 0.607 ms against 0.523) -- the load is issued early, but tcgen05.wait::ld, the P-store
+  // drain and the barrier waits each cost their ~200 cycles whether or not the data has long arrived, and the extra
+  // s_free arrive / pv_done wait add two more such instructions per step (r02_attention_issue_notes.txt item 9).  Kept
+  // for A/B runs under HRIEMO_ATTN_PSEP.
+#ifdef HRIEMO_ATTN_PSEP
+  constexpr bool PSEP = !PAIRED && !DEFER && DH <= 96;
+#else
+  constexpr bool PSEP = false;
+#endif
+  constexpr uint32_t P_COL = 128;
+  constexpr uint32_t O_COL = PSEP ? 160 : 128;
   constexpr int KS = L::KV_STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -199,6 +231,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   // steps apart; alternating barriers keep every wait at most one phase behind its barrier.
   const uint32_t b_pfull = bars + 24 * 8;
   const uint32_t b_pvdone = bars + 28 * 8;
+  const uint32_t b_sfree = bars + 32 * 8;    // [tile][S buffer], PSEP form only: the warpgroup has the buffer's scores in registers
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + L::TMEM_SLOT_OFF);
 
   const int warp = threadIdx.x >> 5;
@@ -232,6 +265,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       mbar_init(b_qempty + s * 8, 4);   // released by the 4 warps of the tile's warpgroup (epilogue staging)
       mbar_init(b_sfull + s * 8, 1);
       mbar_init(b_pvdone + s * 8, 1);
+      mbar_init(b_sfree + s * 8, 4);    // one arrival per softmax warp of the tile
     }
     for (int s = 0; s < 3; ++s) {
       mbar_init(b_kfull + s * 8, 1);
@@ -409,6 +443,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       auto sbuf_of = [&](uint32_t g) { return paired ? (g >> 1) & 1u : g & 1u; };
       // ---- S cursor (two flat steps ahead of the PV cursor)
       uint32_t s_g = 0, s_item = item_first, qcnt = 0;
+      [[maybe_unused]] uint32_t s_uses[2] = {0u, 0u};   // PSEP: S tiles of this query tile issued into each buffer so far
       int s_f = 0;
       int s_nk = s_item < item_last ? steps_u(s_item) : 0;
       bool s_act = tile_active(s_item);
@@ -431,6 +466,11 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
         if (leader) ATRACE(t, s_g, 5);
         if (act) {
+          if constexpr (PSEP) {   // the buffer's previous scores must be in the warpgroup's registers
+            const uint32_t sb = sbuf_of(s_g);
+            if (s_uses[sb] > 0) wait_u(b_sfree + (t * 2 + sb) * 8, (s_uses[sb] - 1u) & 1u);
+            ++s_uses[sb];
+          }
           tc_fence_after_sync();
           const uint64_t q_desc = umma_desc_sw128(sQ + qslot * L::Q_TILE);
           const uint64_t k_desc = k_desc0 + ((ks * L::K_STAGE) >> 4);
@@ -500,6 +540,9 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       bool pv_act = tile_active(pv_item);
       for (uint32_t g = 0; pv_item < item_last; ++g) {
         const uint32_t vs = g % KS, vpar = (g / KS) & 1u;
+        if constexpr (PSEP) {
+          if (s_item < item_last) issue_s(true);   // S(g+2) as soon as the warpgroup has loaded S(g): before PV(g), not behind it
+        }
         if (leader) ATRACE(t, g, 0);
         wait_pumping(b_vfull + vs * 8, vpar);   // never wait without moving the S cursor
         if (leader) ATRACE(t, g, 1);
@@ -512,7 +555,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           ++pcnt;
           tc_fence_after_sync();
           const uint64_t v_desc = v_desc0 + ((vs * L::V_STAGE) >> 4);
-          const uint32_t p_tmem = tile_tmem + sbuf_of(g) * A3_BKV;
+          const uint32_t p_tmem = PSEP ? tile_tmem + P_COL : tile_tmem + sbuf_of(g) * A3_BKV;
           {
 #pragma unroll
             for (int st = 0; st < A3_BKV / 16; ++st) {
@@ -530,7 +573,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if constexpr (DEFER) {
           s_allowed = g + 1 + S_LEAD;
           pump(false);
-        } else {
+        } else if constexpr (!PSEP) {
           if (s_item < item_last) issue_s(true);  // general: S(g+2) reuses the S buffer whose P was just consumed
         }
         if (++pv_f == flat_of(pv_nk)) {
@@ -592,6 +635,9 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       const uint32_t in_b = item - static_cast<uint32_t>(b) * static_cast<uint32_t>(p.items_per_b);
       const int h = paired ? static_cast<int>(in_b) * 2 + wg : static_cast<int>(in_b / static_cast<uint32_t>(p.n_qp));
       const int q0 = paired ? 0 : static_cast<int>(in_b % static_cast<uint32_t>(p.n_qp)) * 2 * A3_BQ + wg * A3_BQ;
+      // dropout on the probabilities (training): hash base of this thread's query row in the (utterance, head) stream
+      [[maybe_unused]] const uint32_t dbase =
+          drop_key_bh(p.drop_key, static_cast<uint32_t>(b * p.H + h)) + static_cast<uint32_t>(q0 + quad * 32 + lane) * DROP_C_ROW;
       if (q0 >= p.Tq) {  // this warpgroup's tile does not exist for this item: only keep the exp turn-taking alive
 #ifndef HRIEMO_ATTN_NO_PINGPONG
         for (int j = 0; j < nk; ++j) {
@@ -715,6 +761,102 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       float m_run = -INFINITY;  // running reference maximum, in log2 units (score * scale * log2 e)
       float l_run = 0.0f;
       uint32_t va[32], vb[32];
+      if constexpr (PSEP) {
+        // ---- PSEP loop (see the constant's comment): P in its own 32 columns, S buffers released as soon as their scores
+        // are in registers, exact row maximum first, the next step's scores loaded under this step's exponentials.
+        const uint32_t t_p = t_tile + P_COL;
+        {  // the item's first scores
+          const uint32_t sbuf0 = g & 1u;
+          if (wg_tid == 0) ATRACE(2 + wg, g, 0);
+          mbar_wait(b_sfull + (wg * 2 + sbuf0) * 8, (sbuf0 ? scnt1 : scnt0) & 1u);
+          if (sbuf0) ++scnt1; else ++scnt0;
+          tc_fence_after_sync();
+          if (wg_tid == 0) ATRACE(2 + wg, g, 1);
+          tmem_ld32(t_tile + sbuf0 * A3_BKV, va);
+          if (p.Tk > 32) tmem_ld32(t_tile + sbuf0 * A3_BKV + 32, vb);
+        }
+        for (int j = 0; j < nk; ++j) {
+          const uint32_t sbuf = (g + static_cast<uint32_t>(j)) & 1u;
+          const int rem = p.Tk - j * A3_BKV;
+          const bool two = rem > 32;                   // second 32-key chunk holds a valid key
+          const bool masked = flags[j] != 0;           // warp-uniform
+          const float* cap_j = caps + j * A3_BKV;
+          tmem_ld_wait();
+          // the scores are in registers: the buffer may take S(j+2)
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_sfree + (wg * 2 + sbuf) * 8);
+          if (wg_tid == 0) ATRACE(2 + wg, g + j, 2);
+          if (masked) {
+            apply_caps(va, cap_j);
+            if (two) apply_caps(vb, cap_j + 32);
+          }
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          max4(m4, va);
+          if (two) max4(m4, vb);
+          const float tile_max = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;  // sc > 0
+          // P has ONE buffer: PV(j-1) must have read it before this step's probabilities go in (it was issued a whole
+          // step ago; every PV is awaited in order, so no wait can be answered by a stale phase)
+          consume_pv(pv_issued);
+          if (j == 0) {
+            m_run = tile_max;
+          } else {
+            const bool need = tile_max > m_run + A3_LAZY_TAU;
+            if (__any_sync(0xffffffffu, need)) {   // rare: O / l rescale (every PV of this tile has retired, see above)
+              tc_fence_after_sync();
+              const float alpha = need ? ex2_approx(m_run - tile_max) : 1.0f;
+              if (need) m_run = tile_max;
+              l_run *= alpha;
+#pragma unroll 1
+              for (int c = 0; c < DH / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(t_o + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                tmem_st32(t_o + c * 32, v);
+              }
+            }
+          }
+          const float neg_m = (m_run == -INFINITY) ? 0.0f : -m_run;
+          if (wg_tid == 0) ATRACE(2 + wg, g + j, 3);
+#ifndef HRIEMO_ATTN_NO_PINGPONG
+          asm volatile("bar.sync %0, 256;" ::"r"(3 + wg) : "memory");
+#endif
+          float l4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          uint32_t pk[16];
+          float2 xs[16];
+          scale32(va, sc, neg_m, xs);
+          exp_pack_x(xs, l4, pk);
+          tmem_st16(t_p, pk);
+          if (two) scale32(vb, sc, neg_m, xs);     // va and vb are dead from here on
+          if (j + 1 < nk) {   // S(j+1) was issued at the start of step j-1: it has landed
+            const uint32_t nbuf = sbuf ^ 1u;
+            mbar_wait(b_sfull + (wg * 2 + nbuf) * 8, (nbuf ? scnt1 : scnt0) & 1u);
+            if (nbuf) ++scnt1; else ++scnt0;
+            tc_fence_after_sync();
+            tmem_ld32(t_tile + nbuf * A3_BKV, va);
+            if (p.Tk - (j + 1) * A3_BKV > 32) tmem_ld32(t_tile + nbuf * A3_BKV + 32, vb);
+          }
+          if (two) {
+            exp_pack_x(xs, l4, pk);
+            tmem_st16(t_p + 16, pk);
+          }
+#ifndef HRIEMO_ATTN_NO_PINGPONG
+          asm volatile("bar.arrive %0, 256;" ::"r"(4 - wg) : "memory");   // the other warpgroup's turn
+#endif
+          l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+          if (wg_tid == 0) ATRACE(2 + wg, g + j, 4);
+          tmem_st_wait();
+          tc_fence_before_sync();
+          if (wg_tid == 0) ATRACE(2 + wg, g + j, 5);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_pfull + (wg * 2 + (pv_issued & 1u)) * 8);
+          ++pv_issued;
+          if (j == 0 && nk > 2) release_q();
+          if (wg_tid == 0) ATRACE(2 + wg, g + j, 6);
+        }
+      } else {
       // the item's first scores
       {
         const uint32_t sbuf0 = paired ? (g >> 1) & 1u : g & 1u;
@@ -763,9 +905,11 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         float l4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         uint32_t pk[16];
         exp_pack(va, sc, neg_m, l4, pk);
+        if constexpr (DROP) drop_pk(pk, dbase, static_cast<uint32_t>(j) * 16u, p.drop_p8);
         tmem_st16(t_s, pk);
         if (two) {
           exp_pack(vb, sc, neg_m, l4, pk);
+          if constexpr (DROP) drop_pk(pk, dbase, static_cast<uint32_t>(j) * 16u + 8u, p.drop_p8);
           tmem_st16(t_s + 16, pk);
         }
 #ifndef HRIEMO_ATTN_NO_PINGPONG
@@ -796,9 +940,11 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             neg_m = (m_run == -INFINITY) ? 0.0f : -m_run;
             l4[0] = l4[1] = l4[2] = l4[3] = 0.0f;
             exp_pack(va, sc, neg_m, l4, pk);
+            if constexpr (DROP) drop_pk(pk, dbase, static_cast<uint32_t>(j) * 16u, p.drop_p8);
             tmem_st16(t_s, pk);
             if (two) {
               exp_pack(vb, sc, neg_m, l4, pk);
+              if constexpr (DROP) drop_pk(pk, dbase, static_cast<uint32_t>(j) * 16u + 8u, p.drop_p8);
               tmem_st16(t_s + 16, pk);
             }
           }
@@ -823,6 +969,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if (j == 0 && nk > 2) release_q();
         if (wg_tid == 0) ATRACE(2 + wg, g + j, 6);
       }
+      }   // !PSEP
 #else
       // ---- v5 softmax loop (HRIEMO_ATTN_V5_SOFTMAX; an experiment that did NOT pay: 500x500 0.553 ms against v4's 0.525 on
       // the same box, profiles/r02_attention_issue_notes.txt item 7 -- S(j+1) is issued ~600 cycles behind the hand-off of
@@ -955,13 +1102,16 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 #ifdef HRIEMO_ATTN_V3_SOFTMAX
       consume_pv(pv_issued);
 #else
-      {
+      if constexpr (PSEP) {
+        consume_pv(pv_issued);
+      } else {
         const uint32_t kk = pv_issued - 1u;   // the item's last PV (its predecessor retired before the last S landed)
         mbar_wait(b_pvdone + (wg * 2 + (kk & 1u)) * 8, (kk >> 1) & 1u);
       }
 #endif
       tc_fence_after_sync();
-      const float inv_l = 1.0f / l_run;  // l == 0 (every key masked) -> inf -> NaN like torch.softmax
+      // l == 0 (every key masked) -> inf -> NaN like torch.softmax; DROP: the kept probabilities' 1 / (1 - p)
+      const float inv_l = DROP ? (1.0f / l_run) * p.drop_scale : 1.0f / l_run;
       // what a backward pass needs to rebuild P: ln sum_k exp(s_k * scale); this thread's row is its TMEM lane
       if (p.lse != nullptr && q0 + quad * 32 + lane < p.Tq)
         p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Tq + q0 + quad * 32 + lane] = (m_run + log2f(l_run)) * 0.6931471805599453f;
@@ -1065,14 +1215,19 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
   if (p.n_items * n_kv * (p.paired ? 2 : 1) >= (1ll << 31))
     return set_error(HRIEMO_ERR_INVALID, "attention: too many (item, step) pairs for 32-bit step counters");
   p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.drop_p8 = a.drop_p8; p.drop_key = a.drop_key; p.drop_scale = a.drop_p8 ? a.drop_scale : 1.0f;
   static uint64_t attr_done = 0;
   if (device_needs_attr(&attr_done)) {
     cudaError_t e = cudaSuccess;
-    const void* forms[4] = {reinterpret_cast<const void*>(attention_fwd3_kernel<DH, false, false>),
-                            reinterpret_cast<const void*>(attention_fwd3_kernel<DH, false, true>),
-                            reinterpret_cast<const void*>(attention_fwd3_kernel<DH, true, false>),
-                            reinterpret_cast<const void*>(attention_fwd3_kernel<DH, true, true>)};
-    for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+    const void* forms[8] = {reinterpret_cast<const void*>(attention_fwd3_kernel<DH, false, false, false>),
+                            reinterpret_cast<const void*>(attention_fwd3_kernel<DH, false, true, false>),
+                            reinterpret_cast<const void*>(attention_fwd3_kernel<DH, true, false, false>),
+                            reinterpret_cast<const void*>(attention_fwd3_kernel<DH, true, true, false>),
+                            reinterpret_cast<const void*>(attention_fwd3_kernel<DH, false, false, true>),
+                            reinterpret_cast<const void*>(attention_fwd3_kernel<DH, false, true, true>),
+                            reinterpret_cast<const void*>(attention_fwd3_kernel<DH, true, false, true>),
+                            reinterpret_cast<const void*>(attention_fwd3_kernel<DH, true, true, true>)};
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i)
       e = cudaFuncSetAttribute(forms[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess)
       return set_error(HRIEMO_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -1080,14 +1235,16 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
   const int64_t sms = device_sm_count();
   const unsigned grid = static_cast<unsigned>(p.n_items < sms ? p.n_items : sms);
   const bool defer = n_kv <= 2;   // short items: S look-ahead must not hold up a PV (see the kernel)
-  if (p.paired && defer)
-    attention_fwd3_kernel<DH, true, true><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);
-  else if (p.paired)
-    attention_fwd3_kernel<DH, true, false><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);
-  else if (defer)
-    attention_fwd3_kernel<DH, false, true><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);
-  else
-    attention_fwd3_kernel<DH, false, false><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);
+#define HRIEMO_A3_LAUNCH(PAIRED_, DEFER_)                                                                              \
+  do {                                                                                                                 \
+    if (p.drop_p8) attention_fwd3_kernel<DH, PAIRED_, DEFER_, true><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p); \
+    else attention_fwd3_kernel<DH, PAIRED_, DEFER_, false><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);     \
+  } while (0)
+  if (p.paired && defer) HRIEMO_A3_LAUNCH(true, true);
+  else if (p.paired) HRIEMO_A3_LAUNCH(true, false);
+  else if (defer) HRIEMO_A3_LAUNCH(false, true);
+  else HRIEMO_A3_LAUNCH(false, false);
+#undef HRIEMO_A3_LAUNCH
   return check_launch("attention_bf16");
 }
 
@@ -1133,6 +1290,7 @@ extern "C" int hriemo_attention_bf16(const hriemo_attn_args* a, void* stream) {
   HRIEMO_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15u) == 0, "attention: out misaligned");
   HRIEMO_REQUIRE(a->scale > 0.0f, "attention: scale must be positive");
   HRIEMO_REQUIRE(a->kv_steps == nullptr || a->key_pad != nullptr, "attention: kv_steps comes with key_pad");
+  HRIEMO_REQUIRE(a->drop_p8 <= 255u && (a->drop_p8 == 0u || a->drop_scale > 0.0f), "attention: drop_p8 = round(256 p) <= 255 with drop_scale = 1 / (1 - p)");
   HRIEMO_REQUIRE(a->dh == 32 || a->dh == 64 || a->dh == 96 || a->dh == 128,
                  "attention: head dim %d not in {32,64,96,128}", a->dh);
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -728,6 +728,8 @@ extern "C" int hriemo_attention_backward_bf16(const hriemo_attn_bwd_args* a, voi
   HRIEMO_REQUIRE(a->impl >= 0 && a->impl <= 4,
                  "attention_backward: impl=%d (0 / 3 tcgen05 form, 1 FMA, 2 first mma.sync form, 4 ldmatrix mma.sync form)", a->impl);
   HRIEMO_REQUIRE(a->kv_steps == nullptr || a->key_pad != nullptr, "attention_backward: kv_steps comes with key_pad");
+  HRIEMO_REQUIRE(a->drop_p8 == 0u || ((a->impl == 0 || a->impl == 3) && a->drop_p8 <= 255u && a->drop_scale > 0.0f),
+                 "attention_backward: dropout on the probabilities needs the tcgen05 form (impl 0) and drop_scale = 1 / (1 - p)");
   HRIEMO_REQUIRE(a->dh == 32 || a->dh == 64 || a->dh == 96 || a->dh == 128, "attention_backward: dh=%d not in {32, 64, 96, 128}",
                  a->dh);
   const int64_t lds[] = {a->ldq, a->ldk, a->ldv, a->ldo, a->lddo, a->lddq, a->lddk, a->lddv};

@@ -22,6 +22,7 @@
 // as zero, so a masked probability (exactly 0) never meets a neighbour's NaN.
 #include <math.h>
 
+#include "dropout.cuh"
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 
@@ -69,6 +70,8 @@ struct BwdParams {
   int64_t ld0, ld1;
   int B, H, Tq, Tk, n_tiles;
   float scale, scale_log2;
+  uint32_t drop_p8, drop_key;   // the forward's dropout on the probabilities (0 = off): same hash, csrc/dropout.cuh
+  float drop_scale;
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -77,7 +80,8 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-template <int DH, int PASS>
+// DROP: the instances that recompute the forward's dropout mask (a template parameter: the p = 0 step pays nothing)
+template <int DH, int PASS, bool DROP = false>
 __global__ void __launch_bounds__(BT_THREADS, 1)
 attention_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const BwdParams p) {
   using L = BwdSmem<DH>;
@@ -281,6 +285,15 @@ attention_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const BwdParams p)
       }
       const float rowmask = row_valid ? 1.0f : 0.0f;
       const float2 rmv = make_float2(rowmask, rowmask);
+      // dropout on the probabilities: pass 0 owns key (row0 + row) and walks queries (one hash per query: word k >> 2,
+      // byte k & 3), pass 1 owns query (row0 + row) and walks the words of its row
+      [[maybe_unused]] uint32_t dfix = 0u, dshift = 0u;
+      if constexpr (DROP) {
+        const uint32_t dkey = drop_key_bh(p.drop_key, static_cast<uint32_t>(b * p.H + h));
+        dfix = PASS == 0 ? dkey + (static_cast<uint32_t>(row0 + row) >> 2) * DROP_C_WORD
+                         : dkey + static_cast<uint32_t>(row0 + row) * DROP_C_ROW;
+        dshift = (static_cast<uint32_t>(row0 + row) & 3u) * 8u;   // pass 0: this key's byte
+      }
       // pass 0: LSE / D of a step's 64 queries as per-column vectors in shared memory (lse * log2 e, +inf past Tq so
       // that P = 0 there; D * scale), double-buffered; the NEXT step's values are fetched from global memory while
       // this step computes and only touched (scaled, stored) a whole step later
@@ -336,11 +349,31 @@ attention_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const BwdParams p)
                 if (!((km >> c) & 1ull)) pv.x = 0.0f;
                 if (!((km >> (c + 1)) & 1ull)) pv.y = 0.0f;
               }
-              // dS = scale * P o (dP - D) = P o (dP * scale - D * scale)
-              const float2 t = ffma2(make_float2(__uint_as_float(vd[2 * i]), __uint_as_float(vd[2 * i + 1])), scv, pr ? d23 : d01);
-              const float2 ds = fmul2(pv, t);
-              pp[i] = pack_bf16(pv.x, pv.y);
-              pd[i] = pack_bf16(ds.x, ds.y);
+              if constexpr (DROP) {   // O = (P o M / (1 - p)) V: dV takes P o M c, dP = (dO V^T) o M c; dS keeps the undropped P
+                bool k0, k1;
+                const int c = j * BT_N + half * 32 + 2 * i;     // column of the pair: a query (pass 0) or a key (pass 1)
+                if (PASS == 0) {
+                  k0 = ((drop_mix(dfix + static_cast<uint32_t>(c) * DROP_C_ROW) >> dshift) & 0xffu) >= p.drop_p8;
+                  k1 = ((drop_mix(dfix + static_cast<uint32_t>(c + 1) * DROP_C_ROW) >> dshift) & 0xffu) >= p.drop_p8;
+                } else {
+                  const uint32_t word = drop_mix(dfix + (static_cast<uint32_t>(c) >> 2) * DROP_C_WORD);
+                  k0 = ((word >> ((c & 3) * 8)) & 0xffu) >= p.drop_p8;
+                  k1 = ((word >> ((c & 3) * 8 + 8)) & 0xffu) >= p.drop_p8;
+                }
+                const float2 mc = make_float2(k0 ? p.drop_scale : 0.0f, k1 ? p.drop_scale : 0.0f);
+                const float2 pvm = fmul2(pv, mc);   // what multiplied V in the forward
+                const float2 dp = fmul2(make_float2(__uint_as_float(vd[2 * i]), __uint_as_float(vd[2 * i + 1])), mc);
+                const float2 t = ffma2(dp, scv, pr ? d23 : d01);
+                const float2 ds = fmul2(pv, t);
+                pp[i] = pack_bf16(pvm.x, pvm.y);
+                pd[i] = pack_bf16(ds.x, ds.y);
+              } else {
+                // dS = scale * P o (dP - D) = P o (dP * scale - D * scale)
+                const float2 t = ffma2(make_float2(__uint_as_float(vd[2 * i]), __uint_as_float(vd[2 * i + 1])), scv, pr ? d23 : d01);
+                const float2 ds = fmul2(pv, t);
+                pp[i] = pack_bf16(pv.x, pv.y);
+                pd[i] = pack_bf16(ds.x, ds.y);
+              }
             }
           }
           // bf16 P over S columns [0, 32), bf16 dS over dP columns [0, 32): both halves land inside the first 32
@@ -419,9 +452,14 @@ int launch_attn_bwd_tc(const hriemo_attn_bwd_args& a, cudaStream_t stream) {
   p.lse = a.lse; p.dsum = a.dsum; p.key_pad = a.key_pad; p.kv_steps = a.kv_steps;
   p.B = a.B; p.H = a.H; p.Tq = a.Tq; p.Tk = a.Tk;
   p.scale = a.scale; p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.drop_p8 = a.drop_p8; p.drop_key = a.drop_key; p.drop_scale = a.drop_p8 ? a.drop_scale : 1.0f;
   static uint64_t attr_done = 0;
   if (device_needs_attr(&attr_done)) {
     cudaError_t e = cudaFuncSetAttribute(attention_bwd_tc_kernel<DH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_bwd_tc_kernel<DH, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_bwd_tc_kernel<DH, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attention_bwd_tc_kernel<DH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess)
@@ -441,7 +479,8 @@ int launch_attn_bwd_tc(const hriemo_attn_bwd_args& a, cudaStream_t stream) {
     const int64_t items = static_cast<int64_t>(p.n_tiles) * a.H * a.B;
     if (items >= (1ll << 31)) return set_error(HRIEMO_ERR_INVALID, "attention_backward (tcgen05): too many work items");
     const unsigned grid = static_cast<unsigned>(items < device_sm_count() ? items : device_sm_count());
-    attention_bwd_tc_kernel<DH, 0><<<grid, BT_THREADS, smem, stream>>>(m, p);
+    if (p.drop_p8) attention_bwd_tc_kernel<DH, 0, true><<<grid, BT_THREADS, smem, stream>>>(m, p);
+    else attention_bwd_tc_kernel<DH, 0><<<grid, BT_THREADS, smem, stream>>>(m, p);
     if ((rc = check_launch("attention_backward (tcgen05, dK / dV)"))) return rc;
   }
   {
@@ -457,7 +496,8 @@ int launch_attn_bwd_tc(const hriemo_attn_bwd_args& a, cudaStream_t stream) {
     const int64_t items = static_cast<int64_t>(p.n_tiles) * a.H * a.B;
     if (items >= (1ll << 31)) return set_error(HRIEMO_ERR_INVALID, "attention_backward (tcgen05): too many work items");
     const unsigned grid = static_cast<unsigned>(items < device_sm_count() ? items : device_sm_count());
-    attention_bwd_tc_kernel<DH, 1><<<grid, BT_THREADS, smem, stream>>>(m, p);
+    if (p.drop_p8) attention_bwd_tc_kernel<DH, 1, true><<<grid, BT_THREADS, smem, stream>>>(m, p);
+    else attention_bwd_tc_kernel<DH, 1><<<grid, BT_THREADS, smem, stream>>>(m, p);
     if ((rc = check_launch("attention_backward (tcgen05, dQ)"))) return rc;
   }
   return HRIEMO_OK;

@@ -3,6 +3,7 @@
 //  * small-query attention (emotion decoder) and head-averaged attention maps.
 #include <math.h>
 
+#include "dropout.cuh"
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 
@@ -79,7 +80,8 @@ __global__ void __launch_bounds__(SA_THREADS)
 small_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k,
                        int64_t ldk, const __nv_bfloat16* __restrict__ v, int64_t ldv,
                        const uint8_t* __restrict__ key_pad, __nv_bfloat16* __restrict__ out, int64_t ldo,
-                       float* __restrict__ probs, int H, int Nq, int Tk, int dh, float scale) {
+                       float* __restrict__ probs, int H, int Nq, int Tk, int dh, float scale, uint32_t drop_p8,
+                       uint32_t drop_key, float drop_scale) {
   extern __shared__ float sm[];
   float* qs = sm;                         // [SA_NQ][dh]
   float* sc = qs + SA_NQ * dh;            // [SA_NQ][Tk]  scores -> probabilities
@@ -142,10 +144,14 @@ small_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const _
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       const float inv = 1.0f / s;
+      // training: dropout on the probabilities after the normalisation (csrc/dropout.cuh; the map, if asked for, is
+      // the undropped one)
+      const uint32_t dkey = drop_key_bh(drop_key, static_cast<uint32_t>(b * H + h));
       for (int j = lane; j < Tk; j += 32) {
         const float pr = sc[qi * Tk + j] * inv;
-        sc[qi * Tk + j] = pr;
         if (probs) pavg[qi * Tk + j] += pr * inv_h;
+        sc[qi * Tk + j] = (drop_p8 == 0u || drop_keep(dkey, static_cast<uint32_t>(qb + qi), static_cast<uint32_t>(j), drop_p8))
+                              ? pr * drop_scale : 0.0f;
       }
     }
     __syncthreads();
@@ -303,12 +309,14 @@ small_attention_backward_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq
                                 int64_t ldk, const __nv_bfloat16* __restrict__ v, int64_t ldv,
                                 const __nv_bfloat16* __restrict__ dout, int64_t lddo, const uint8_t* __restrict__ key_pad,
                                 __nv_bfloat16* __restrict__ dq, int64_t lddq, __nv_bfloat16* __restrict__ dk, int64_t lddk,
-                                __nv_bfloat16* __restrict__ dv, int64_t lddv, int H, int Nq, int Tk, int dh, float scale) {
+                                __nv_bfloat16* __restrict__ dv, int64_t lddv, int H, int Nq, int Tk, int dh, float scale,
+                                uint32_t drop_p8, uint32_t drop_key, float drop_scale) {
   extern __shared__ float sm[];
   float* qs = sm;                       // [SA_NQ][dh]  q * scale
   float* dos = qs + SA_NQ * dh;         // [SA_NQ][dh]  dO
   float* ps = dos + SA_NQ * dh;         // [SA_NQ][Tk]  P
   float* dss = ps + SA_NQ * Tk;         // [SA_NQ][Tk]  dP -> dS
+  float* pms = dss + SA_NQ * Tk;        // [SA_NQ][Tk]  P o M / (1 - p): what multiplied V in the forward (= P without dropout)
   const int b = blockIdx.x, h = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < Nq * dh; i += SB_THREADS) {
@@ -360,10 +368,16 @@ small_attention_backward_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float inv = 1.0f / sum;
     float dot = 0.0f;
+    const uint32_t dkey = drop_key_bh(drop_key, static_cast<uint32_t>(b * H + h));
     for (int j = lane; j < Tk; j += 32) {
       const float pr = ps[qi * Tk + j] * inv;
+      // O = (P o M c) V: dV takes P o M c, dP = (dO V^T) o M c, dS = P o (dP - rowsum(dP o P)) with the undropped P
+      const float mc = (drop_p8 == 0u || drop_keep(dkey, static_cast<uint32_t>(qi), static_cast<uint32_t>(j), drop_p8)) ? drop_scale : 0.0f;
+      const float dpm = dss[qi * Tk + j] * mc;
       ps[qi * Tk + j] = pr;
-      dot += pr * dss[qi * Tk + j];
+      pms[qi * Tk + j] = pr * mc;
+      dss[qi * Tk + j] = dpm;
+      dot += pr * dpm;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
@@ -377,7 +391,7 @@ small_attention_backward_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq
 #pragma unroll
     for (int qi = 0; qi < SA_NQ; ++qi) {
       if (qi < Nq) {
-        av = fmaf(ps[qi * Tk + j], dos[qi * dh + c], av);
+        av = fmaf(pms[qi * Tk + j], dos[qi * dh + c], av);
         ak = fmaf(dss[qi * Tk + j], qs[qi * dh + c], ak);
       }
     }
@@ -413,8 +427,9 @@ __global__ void emotion_outputs_kernel(const float* __restrict__ logits, const f
 
 static int launch_small_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                                   int64_t ldv, const uint8_t* key_pad, void* out, int64_t ldo, float* probs,
-                                  int B, int H, int Nq, int Tk, int dh, float scale, cudaStream_t s) {
-  if (probs == nullptr && out != nullptr && v != nullptr && Nq <= SA_NQ && Tk <= DA_MAX_TK && dh <= 128 && H <= 65535 &&
+                                  int B, int H, int Nq, int Tk, int dh, float scale, cudaStream_t s, uint32_t drop_p8 = 0,
+                                  uint32_t drop_key = 0, float drop_scale = 1.0f) {
+  if (drop_p8 == 0u && probs == nullptr && out != nullptr && v != nullptr && Nq <= SA_NQ && Tk <= DA_MAX_TK && dh <= 128 && H <= 65535 &&
       ldv % 8 == 0 && ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(v) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
     // the decoder's own shapes: K / V staged in shared memory (see decoder_attention_kernel)
     const size_t sm = static_cast<size_t>(2) * Tk * (dh + 8) * 2 + sizeof(float) * (static_cast<size_t>(SA_NQ) * dh + static_cast<size_t>(SA_NQ) * Tk);
@@ -441,7 +456,7 @@ static int launch_small_attention(const void* q, int64_t ldq, const void* k, int
   small_attention_kernel<<<grid, SA_THREADS, smem, s>>>(
       static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k), ldk,
       static_cast<const __nv_bfloat16*>(v), ldv, key_pad, static_cast<__nv_bfloat16*>(out), ldo, probs, H, Nq,
-      Tk, dh, scale);
+      Tk, dh, scale, drop_p8, drop_key, drop_p8 ? drop_scale : 1.0f);
   return check_launch("small_attention");
 }
 
@@ -475,6 +490,18 @@ extern "C" int hriemo_small_attention(const void* q, int64_t ldq, const void* k,
                                 static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int hriemo_small_attention_dropout(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                              const uint8_t* key_pad, void* out_bf16, int64_t ldo, int32_t B, int32_t H,
+                                              int32_t Nq, int32_t Tk, int32_t dh, float scale, uint32_t drop_p8,
+                                              uint32_t drop_key, float drop_scale, void* stream) {
+  HRIEMO_REQUIRE(q && k && v && out_bf16, "small_attention_dropout: null pointer");
+  HRIEMO_REQUIRE(B > 0 && H > 0 && Nq > 0 && Tk > 0 && dh > 0 && dh % 8 == 0, "small_attention_dropout: bad shape");
+  HRIEMO_REQUIRE(ldk % 8 == 0 && (reinterpret_cast<uintptr_t>(k) & 15u) == 0, "small_attention_dropout: K misaligned");
+  HRIEMO_REQUIRE(drop_p8 <= 255u && (drop_p8 == 0u || drop_scale > 0.0f), "small_attention_dropout: drop_p8 = round(256 p) <= 255");
+  return launch_small_attention(q, ldq, k, ldk, v, ldv, key_pad, out_bf16, ldo, nullptr, B, H, Nq, Tk, dh, scale,
+                                static_cast<cudaStream_t>(stream), drop_p8, drop_key, drop_scale);
+}
+
 extern "C" int hriemo_emotion_outputs(const float* logits, const float* thresholds, float* probs,
                                       uint8_t* decisions, int64_t B, int32_t n_classes, void* stream) {
   HRIEMO_REQUIRE(logits && (probs || decisions) && B >= 0 && n_classes > 0, "emotion_outputs: bad argument");
@@ -498,15 +525,16 @@ extern "C" int hriemo_attention_probs(const void* q, int64_t ldq, const void* k,
                                 static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int hriemo_small_attention_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
-                                               int64_t ldv, const void* d_out, int64_t lddo, const uint8_t* key_pad,
-                                               void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
-                                               int32_t B, int32_t H, int32_t Nq, int32_t Tk, int32_t dh, float scale,
-                                               void* stream) {
+static int launch_small_attention_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                           const void* d_out, int64_t lddo, const uint8_t* key_pad, void* dq, int64_t lddq,
+                                           void* dk, int64_t lddk, void* dv, int64_t lddv, int32_t B, int32_t H, int32_t Nq,
+                                           int32_t Tk, int32_t dh, float scale, uint32_t drop_p8, uint32_t drop_key,
+                                           float drop_scale, void* stream) {
   HRIEMO_REQUIRE(q && k && v && d_out && dq && dk && dv, "small_attention_backward: null pointer");
   HRIEMO_REQUIRE(B > 0 && H > 0 && H <= 65535 && Nq > 0 && Nq <= SA_NQ && Tk > 0 && dh > 0,
                  "small_attention_backward: bad shape (at most %d queries)", SA_NQ);
-  const size_t smem = sizeof(float) * (2 * static_cast<size_t>(SA_NQ) * dh + 2 * static_cast<size_t>(SA_NQ) * Tk);
+  HRIEMO_REQUIRE(drop_p8 <= 255u && (drop_p8 == 0u || drop_scale > 0.0f), "small_attention_backward: drop_p8 = round(256 p) <= 255");
+  const size_t smem = sizeof(float) * (2 * static_cast<size_t>(SA_NQ) * dh + 3 * static_cast<size_t>(SA_NQ) * Tk);
   HRIEMO_REQUIRE(smem <= 200 * 1024, "small_attention_backward: Tk=%d too long", Tk);
   static uint64_t attr_done = 0;
   if (smem > 48 * 1024 && device_needs_attr(&attr_done)) {
@@ -517,6 +545,24 @@ extern "C" int hriemo_small_attention_backward(const void* q, int64_t ldq, const
   small_attention_backward_kernel<<<dim3(B, H), SB_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf*>(q), ldq, static_cast<const bf*>(k), ldk, static_cast<const bf*>(v), ldv,
       static_cast<const bf*>(d_out), lddo, key_pad, static_cast<bf*>(dq), lddq, static_cast<bf*>(dk), lddk,
-      static_cast<bf*>(dv), lddv, H, Nq, Tk, dh, scale);
+      static_cast<bf*>(dv), lddv, H, Nq, Tk, dh, scale, drop_p8, drop_key, drop_p8 ? drop_scale : 1.0f);
   return check_launch("small_attention_backward");
+}
+
+extern "C" int hriemo_small_attention_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                               int64_t ldv, const void* d_out, int64_t lddo, const uint8_t* key_pad,
+                                               void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                                               int32_t B, int32_t H, int32_t Nq, int32_t Tk, int32_t dh, float scale,
+                                               void* stream) {
+  return launch_small_attention_backward(q, ldq, k, ldk, v, ldv, d_out, lddo, key_pad, dq, lddq, dk, lddk, dv, lddv, B, H, Nq,
+                                         Tk, dh, scale, 0u, 0u, 1.0f, stream);
+}
+
+extern "C" int hriemo_small_attention_backward_dropout(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                                       int64_t ldv, const void* d_out, int64_t lddo, const uint8_t* key_pad,
+                                                       void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                                                       int32_t B, int32_t H, int32_t Nq, int32_t Tk, int32_t dh, float scale,
+                                                       uint32_t drop_p8, uint32_t drop_key, float drop_scale, void* stream) {
+  return launch_small_attention_backward(q, ldq, k, ldk, v, ldv, d_out, lddo, key_pad, dq, lddq, dk, lddk, dv, lddv, B, H, Nq,
+                                         Tk, dh, scale, drop_p8, drop_key, drop_scale, stream);
 }

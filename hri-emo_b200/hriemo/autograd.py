@@ -11,7 +11,8 @@ therefore the CALLER'S torch code, exactly as in the reference; what runs on the
 with tapes and its backward from (d_logits, d_beta, d_z).  Parameters enter the autograd.Function as inputs, which is
 what makes torch accumulate into their `.grad`.
 
-Dropout: the kernels compute the dropout = 0 step (engine.warn_if_training says so once for a model built with p > 0).
+Dropout: applied at every site of the reference when the model was built with p > 0 (hriemo/dropout.py: the forward draws a
+seed from torch's CPU generator, the backward recomputes the masks from the same stream keys).
 hriemo.train.Trainer remains the fast path (flat arenas, fused clip / AdamW, CUDA-graph replay)."""
 from __future__ import annotations
 

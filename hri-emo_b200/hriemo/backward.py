@@ -14,7 +14,11 @@ The gate's training forward differs from the inference schedule in one respect: 
 HBM as bf16 tensors (the backward reads them twice) instead of being applied on the fly inside the pooling and
 blend kernels; streams that arrive with a pending encoder LayerNorm are materialised first.
 
-Dropout: the parity configuration is dropout = 0, which is what this computes.
+Dropout (hriemo/dropout.py, csrc/dropout.cuh): every site of the reference -- the sub-layer outputs, the decoder FFN's
+inner dropout and the attention probabilities of all six MHAs -- is applied in the training forward when the modules were
+built with p > 0 and are in train() mode, with counter-based masks that the backward recomputes from the same stream
+keys (a `Drop` object per forward / backward pair; nothing is stored).  With p = 0 (the parity configuration of SURVEY
+sec. 8d config 5) the schedules below are exactly the round-1 ones.
 """
 from __future__ import annotations
 
@@ -22,6 +26,7 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
+from . import dropout as D
 from . import engine as E
 from . import lib as L
 from . import ops
@@ -94,18 +99,18 @@ def gate_backward(gate, tape: dict, dh: torch.Tensor, dbeta: Optional[torch.Tens
 # --------------------------------------------------------------------------- #
 # emotion decoder
 # --------------------------------------------------------------------------- #
-def decoder_forward_train(dec, mem: E.Seq, mem_mask):
+def decoder_forward_train(dec, mem: E.Seq, mem_mask, drop=None):
     """EmotionDecoder forward (the inference schedule, emotion_decoder.py:117-162) with tapes.
     -> (z [B, N_e, d] fp32, logits [B, N_e] fp32, tape)."""
     if dec.out_proj is None:
         raise L.HriemoError("decoder_forward_train: the training step needs the output layer (use_output_layer=True)")
     tapes: list = []
-    z, logits, _ = dec.run(mem, mem_mask, False, tapes=tapes)
-    return z, logits, dict(layers=tapes, mem=mem, mem_mask=mem_mask, z=z)
+    z, logits, _ = dec.run(mem, mem_mask, False, tapes=tapes, drop=drop)
+    return z, logits, dict(layers=tapes, mem=mem, mem_mask=mem_mask, z=z, drop=drop)
 
 
 def _decoder_layer_backward(P: dict, tape: dict, dz: torch.Tensor, d_mem: Optional[torch.Tensor], mem: E.Seq, mem_mask,
-                            Ne: int, n_heads: int):
+                            Ne: int, n_heads: int, drop=None, site0: int = 0):
     """Reverse of engine.decoder_layer.  dz: bf16 [B*N_e, d] gradient of the layer's output; d_mem: the gradient of
     the memory accumulated so far (the next layer's share) or None.  -> (dz_in, d_mem, grads)."""
     B, Lm = mem.B, mem.T
@@ -113,20 +118,24 @@ def _decoder_layer_backward(P: dict, tape: dict, dz: torch.Tensor, d_mem: Option
     dh = d // n_heads
     dev = dz.device
     G: Grads = {}
-    # ---- z3 = LN3(z2 + W2 relu(W1 z2 + b1) + b2)                                              :58-59
+    ds = (lambda k: drop.site(site0 + k)) if drop else (lambda k: None)
+    dr = (lambda g, k: ops.dropout(g, ds(k))) if drop else (lambda g, k: g)   # the gradient through a dropout site
+    # ---- z3 = LN3(z2 + dropout3(W2 dropout(relu(W1 z2 + b1)) + b2))                           :58-59
     d_pre3, G["norm3.weight"], G["norm3.bias"] = ops.layernorm_backward(ops.cast_bf16(tape["pre3"]), dz, P["norm3"][0])
-    d_hid, G["linear2.weight"], G["linear2.bias"] = ops.linear_backward(d_pre3, tape["h"], _t(P["lin2"]["w"]), relu_input=True)
+    # tape["h"] is the hidden AFTER the inner dropout: it is linear2's input, and its sign pattern is "active and kept"
+    d_hid, G["linear2.weight"], G["linear2.bias"] = ops.linear_backward(dr(d_pre3, 6), tape["h"], _t(P["lin2"]["w"]), relu_input=True)
+    d_hid = dr(d_hid, 5)   # the kept elements' 1 / (1 - p) (the mask itself is idempotent)
     G["linear1.weight"], G["linear1.bias"] = ops.linear_wgrad(d_hid, tape["zb2"])
     dz2 = ops.gemm(d_hid, _t(P["lin1"]["w"]), None, L.EPI_BIAS_RESID, resid=d_pre3, tag="dgrad")
     # ---- z2 = LN2(z1 + MHA(z1, mem, mem))                                                     :48-55
     d_pre2, G["norm2.weight"], G["norm2.bias"] = ops.layernorm_backward(ops.cast_bf16(tape["pre2"]), dz2, P["norm2"][0])
     d_ca, G["cross_attn.out_proj.weight"], G["cross_attn.out_proj.bias"] = ops.linear_backward(
-        d_pre2, tape["ca"], _t(P["cross_wo"]))
+        dr(d_pre2, 4), tape["ca"], _t(P["cross_wo"]))
     kv = tape["kv_mem"]
     dq = torch.empty((B * Ne, d), dtype=bf16, device=dev)
     dkv = torch.empty((B * Lm, 2 * d), dtype=bf16, device=dev)
     ops.small_attention_backward(tape["qc"], kv[:, :d], kv[:, d:], d_ca, mem_mask, B, n_heads, Ne, Lm, dh,
-                                 out=(dq, dkv[:, :d], dkv[:, d:]))
+                                 out=(dq, dkv[:, :d], dkv[:, d:]), drop=ds(3))
     w_in = torch.empty((3 * d, d), dtype=f32, device=dev)
     b_in = torch.empty((3 * d,), dtype=f32, device=dev)
     ops.linear_wgrad(dq, tape["zb1"], dw=w_in[:d], db=b_in[:d])
@@ -140,11 +149,11 @@ def _decoder_layer_backward(P: dict, tape: dict, dz: torch.Tensor, d_mem: Option
     # ---- z1 = LN1(z0 + MHA(z0, z0, z0))                                                       :42-43
     d_pre1, G["norm1.weight"], G["norm1.bias"] = ops.layernorm_backward(ops.cast_bf16(tape["pre1"]), dz1, P["norm1"][0])
     d_sa, G["self_attn.out_proj.weight"], G["self_attn.out_proj.bias"] = ops.linear_backward(
-        d_pre1, tape["sa"], _t(P["self"]["w_o"]))
+        dr(d_pre1, 2), tape["sa"], _t(P["self"]["w_o"]))
     qkv = tape["qkv"]
     dqkv = torch.empty((B * Ne, 3 * d), dtype=bf16, device=dev)
     ops.small_attention_backward(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], d_sa, None, B, n_heads, Ne, Ne, dh,
-                                 out=(dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:]))
+                                 out=(dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:]), drop=ds(1))
     G["self_attn.in_proj_weight"], G["self_attn.in_proj_bias"] = ops.linear_wgrad(dqkv, tape["zb_in"])
     dz_in = ops.gemm(dqkv, _t(P["self"]["w_qkv"]), None, L.EPI_BIAS_RESID, resid=d_pre1, tag="dgrad")
     return dz_in, d_mem, G
@@ -169,7 +178,7 @@ def decoder_backward(dec, tape: dict, d_logits: torch.Tensor, d_z: Optional[torc
     for i in range(len(dec.layers) - 1, -1, -1):
         layer = dec.layers[i]
         dz, d_mem, g = _decoder_layer_backward(layer._prep.get(), tape["layers"][i], dz, d_mem, mem, mem_mask, Ne,
-                                               layer.nhead)
+                                               layer.nhead, tape.get("drop"), 100000 + 100 * i)
         for k, v in g.items():
             G[f"layers.{i}.{k}"] = v
     # the queries are broadcast over the batch (:127): their gradient is the sum over it
@@ -182,24 +191,41 @@ def decoder_backward(dec, tape: dict, d_logits: torch.Tensor, d_z: Optional[torc
 # --------------------------------------------------------------------------- #
 # cross-modal encoder
 # --------------------------------------------------------------------------- #
-def _ffn_forward(x: torch.Tensor, P1: dict, P2: dict, ln, tape: dict, key: str) -> torch.Tensor:
-    """LN(x + W2 relu(W1 x + b1) + b2) on a materialised bf16 stream (cross_modal_block_tacfn.py:106 / :119)."""
+def _out_residual(o: torch.Tensor, w, b, x: torch.Tensor, dk, tag: str) -> torch.Tensor:
+    """x + dropout(o W^T + b): the residual epilogue of the GEMM, or -- with dropout (dk = (p8, scale, key)) -- the plain
+    GEMM followed by the dropout + residual pass."""
+    if dk is None:
+        return ops.gemm(o, w, b, L.EPI_BIAS_RESID, resid=x, tag=tag)
+    return ops.dropout(ops.gemm(o, w, b, L.EPI_BIAS, tag=tag), dk, resid=x)
+
+
+def _ffn_forward(x: torch.Tensor, P1: dict, P2: dict, ln, tape: dict, key: str, dk=None) -> torch.Tensor:
+    """LN(x + dropout(W2 relu(W1 x + b1) + b2)) on a materialised bf16 stream (cross_modal_block_tacfn.py:106 / :119)."""
     h = ops.gemm(x, P1["w"], P1["b"], L.EPI_BIAS_RELU, tag="ffn")
-    pre = ops.gemm(h, P2["w"], P2["b"], L.EPI_BIAS_RESID, resid=x, tag="ffn")
+    pre = _out_residual(h, P2["w"], P2["b"], x, dk, "ffn")
     y, _ = ops.layernorm(pre, *ln)
     tape[key] = dict(x=x, h=h, pre=pre)
     return y
 
 
-def _ffn_backward(dy: torch.Tensor, P1: dict, P2: dict, ln, tp: dict, G: Grads, name: str, norm: str) -> torch.Tensor:
+def _ffn_backward(dy: torch.Tensor, P1: dict, P2: dict, ln, tp: dict, G: Grads, name: str, norm: str, dk=None) -> torch.Tensor:
     d_pre, G[f"{norm}.weight"], G[f"{norm}.bias"] = ops.layernorm_backward(tp["pre"], dy, ln[0])
-    # d_h = (d_pre . W2) * (h > 0): the ReLU mask is the epilogue of the input-gradient GEMM
-    d_h, G[f"{name}.2.weight"], G[f"{name}.2.bias"] = ops.linear_backward(d_pre, tp["h"], _t(P2["w"]), relu_input=True)
+    d_y = d_pre if dk is None else ops.dropout(d_pre, dk)   # through the sub-layer's dropout; the residual takes d_pre itself
+    # d_h = (d_y . W2) * (h > 0): the ReLU mask is the epilogue of the input-gradient GEMM
+    d_h, G[f"{name}.2.weight"], G[f"{name}.2.bias"] = ops.linear_backward(d_y, tp["h"], _t(P2["w"]), relu_input=True)
     G[f"{name}.0.weight"], G[f"{name}.0.bias"] = ops.linear_wgrad(d_h, tp["x"])
     return ops.gemm(d_h, _t(P1["w"]), None, L.EPI_BIAS_RESID, resid=d_pre, tag="dgrad")
 
 
-def encoder_layer_forward_train(block, a: E.Seq, t: E.Seq, mask_a, mask_t):
+# dropout sites of encoder layer i: 1000 (i + 1) + kind
+_ENC_SITES = dict(self_a_p=1, self_a_o=2, self_t_p=3, self_t_o=4, a2t_p=5, a2t_o=6, ffn_a=7, t2a_p=8, t2a_o=9, ffn_t=10)
+
+
+def _enc_site(drop, layer: int, kind: str):
+    return drop.site(1000 * (layer + 1) + _ENC_SITES[kind]) if drop else None
+
+
+def encoder_layer_forward_train(block, a: E.Seq, t: E.Seq, mask_a, mask_t, drop=None, layer: int = 0):
     """CrossModalBlock forward (cross_modal_block_tacfn.py:62-125) on materialised streams: every LayerNorm is
     applied by the stand-alone kernel and every sub-layer keeps its input, its pre-LayerNorm sum, the attention
     output with its log-sum-exp and the FFN hidden.  -> (a_out, t_out, tape)."""
@@ -209,12 +235,14 @@ def encoder_layer_forward_train(block, a: E.Seq, t: E.Seq, mask_a, mask_t):
     d = a.d
     dh = d // H
     B, Ta, Tt = a.B, a.T, t.T
-    tape: dict = dict(B=B, Ta=Ta, Tt=Tt, mask_a=mask_a, mask_t=mask_t)
+    tape: dict = dict(B=B, Ta=Ta, Tt=Tt, mask_a=mask_a, mask_t=mask_t, drop=drop, layer=layer)
+    site = lambda kind: _enc_site(drop, layer, kind)
 
     def self_block(x, Pm, ln, mask, T, key):                                                  # :74-82 / :85-93
         qkv = ops.gemm(x, Pm["w_qkv"], Pm["b_qkv"], L.EPI_BIAS, tag="attn_proj")
-        o, lse = ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], mask, B, H, T, T, dh, want_lse=True)
-        pre = ops.gemm(o, Pm["w_o"], Pm["b_o"], L.EPI_BIAS_RESID, resid=x, tag="attn_proj")
+        o, lse = ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], mask, B, H, T, T, dh, want_lse=True,
+                               drop=site(key + "_p"))
+        pre = _out_residual(o, Pm["w_o"], Pm["b_o"], x, site(key + "_o"), "attn_proj")
         y, _ = ops.layernorm(pre, *ln)
         tape[key] = dict(x=x, qkv=qkv, o=o, lse=lse, pre=pre)
         return y
@@ -227,16 +255,16 @@ def encoder_layer_forward_train(block, a: E.Seq, t: E.Seq, mask_a, mask_t):
     tape.update(a_s=a_s, t_s=t_s, qkv_a=qkv_a, qkv_t=qkv_t)
 
     def cross_block(x, q, k, v, mask_kv, Tq, Tk, Po, ln, key):                                # :98-105 / :111-118
-        o, lse = ops.attention(q, k, v, mask_kv, B, H, Tq, Tk, dh, want_lse=True)
-        pre = ops.gemm(o, Po["w"], Po["b"], L.EPI_BIAS_RESID, resid=x, tag="attn_proj")
+        o, lse = ops.attention(q, k, v, mask_kv, B, H, Tq, Tk, dh, want_lse=True, drop=site(key + "_p"))
+        pre = _out_residual(o, Po["w"], Po["b"], x, site(key + "_o"), "attn_proj")
         y, _ = ops.layernorm(pre, *ln)
         tape[key] = dict(o=o, lse=lse, pre=pre)
         return y
 
     a1 = cross_block(a_s, qkv_a[:, :d], qkv_t[:, d:2 * d], qkv_t[:, 2 * d:], mask_t, Ta, Tt, P["a2t_o"], P["norm_a1"], "a2t")
-    a_o = _ffn_forward(a1, P["ffn_a1"], P["ffn_a2"], P["norm_a2"], tape, "ffn_a")             # :106
+    a_o = _ffn_forward(a1, P["ffn_a1"], P["ffn_a2"], P["norm_a2"], tape, "ffn_a", site("ffn_a"))   # :106
     t1 = cross_block(t_s, qkv_t[:, :d], qkv_a[:, d:2 * d], qkv_a[:, 2 * d:], mask_a, Tt, Ta, P["t2a_o"], P["norm_t1"], "t2a")
-    t_o = _ffn_forward(t1, P["ffn_t1"], P["ffn_t2"], P["norm_t2"], tape, "ffn_t")             # :119
+    t_o = _ffn_forward(t1, P["ffn_t1"], P["ffn_t2"], P["norm_t2"], tape, "ffn_t", site("ffn_t"))   # :119
     return E.Seq(a_o, B, Ta), E.Seq(t_o, B, Tt), tape
 
 
@@ -252,23 +280,26 @@ def encoder_layer_backward(block, tape: dict, d_a: torch.Tensor, d_t: torch.Tens
     dh = d // H
     dev = d_a.device
     G: Grads = {}
+    drop, layer = tape.get("drop"), tape.get("layer", 0)
+    site = lambda kind: _enc_site(drop, layer, kind)
+    dr = (lambda g, kind: ops.dropout(g, site(kind))) if drop else (lambda g, kind: g)   # the gradient through a dropout site
     qkv_a, qkv_t = tape["qkv_a"], tape["qkv_t"]
     dqkv_a = torch.empty((B * Ta, 3 * d), dtype=bf16, device=dev)
     dqkv_t = torch.empty((B * Tt, 3 * d), dtype=bf16, device=dev)
     # ---- audio: FFN (:106), then a_s + MHA_a2t(a_s, t_s, t_s) (:98-105)
-    d_a1 = _ffn_backward(d_a, P["ffn_a1"], P["ffn_a2"], P["norm_a2"], tape["ffn_a"], G, "ffn_a", "norm_a2")
+    d_a1 = _ffn_backward(d_a, P["ffn_a1"], P["ffn_a2"], P["norm_a2"], tape["ffn_a"], G, "ffn_a", "norm_a2", site("ffn_a"))
     tp = tape["a2t"]
     d_pre_a1, G["norm_a1.weight"], G["norm_a1.bias"] = ops.layernorm_backward(tp["pre"], d_a1, P["norm_a1"][0])
-    d_o, G["attn_a2t.out_proj.weight"], G["attn_a2t.out_proj.bias"] = ops.linear_backward(d_pre_a1, tp["o"], _t(P["a2t_o"]["w"]))
+    d_o, G["attn_a2t.out_proj.weight"], G["attn_a2t.out_proj.bias"] = ops.linear_backward(dr(d_pre_a1, "a2t_o"), tp["o"], _t(P["a2t_o"]["w"]))
     ops.attention_backward(qkv_a[:, :d], qkv_t[:, d:2 * d], qkv_t[:, 2 * d:], tp["o"], d_o, tp["lse"], mask_t, B, H, Ta, Tt, dh,
-                           grads=(dqkv_a[:, :d], dqkv_t[:, d:2 * d], dqkv_t[:, 2 * d:]))
+                           grads=(dqkv_a[:, :d], dqkv_t[:, d:2 * d], dqkv_t[:, 2 * d:]), drop=site("a2t_p"))
     # ---- text: FFN (:119), then t_s + MHA_t2a(t_s, a_s, a_s) (:111-118)
-    d_t1 = _ffn_backward(d_t, P["ffn_t1"], P["ffn_t2"], P["norm_t2"], tape["ffn_t"], G, "ffn_t", "norm_t2")
+    d_t1 = _ffn_backward(d_t, P["ffn_t1"], P["ffn_t2"], P["norm_t2"], tape["ffn_t"], G, "ffn_t", "norm_t2", site("ffn_t"))
     tp = tape["t2a"]
     d_pre_t1, G["norm_t1.weight"], G["norm_t1.bias"] = ops.layernorm_backward(tp["pre"], d_t1, P["norm_t1"][0])
-    d_o, G["attn_t2a.out_proj.weight"], G["attn_t2a.out_proj.bias"] = ops.linear_backward(d_pre_t1, tp["o"], _t(P["t2a_o"]["w"]))
+    d_o, G["attn_t2a.out_proj.weight"], G["attn_t2a.out_proj.bias"] = ops.linear_backward(dr(d_pre_t1, "t2a_o"), tp["o"], _t(P["t2a_o"]["w"]))
     ops.attention_backward(qkv_t[:, :d], qkv_a[:, d:2 * d], qkv_a[:, 2 * d:], tp["o"], d_o, tp["lse"], mask_a, B, H, Tt, Ta, dh,
-                           grads=(dqkv_t[:, :d], dqkv_a[:, d:2 * d], dqkv_a[:, 2 * d:]))
+                           grads=(dqkv_t[:, :d], dqkv_a[:, d:2 * d], dqkv_a[:, 2 * d:]), drop=site("t2a_p"))
     # ---- the packed projections: rows [Wq(a2t); Wk(t2a); Wv(t2a)] read a_s, rows [Wq(t2a); Wk(a2t); Wv(a2t)] read t_s
     for n in ("attn_a2t", "attn_t2a"):
         G[f"{n}.in_proj_weight"] = torch.empty((3 * d, d), dtype=f32, device=dev)
@@ -280,28 +311,28 @@ def encoder_layer_backward(block, tape: dict, d_a: torch.Tensor, d_t: torch.Tens
     d_a_s = ops.gemm(dqkv_a, _t(P["cross_a"]["w_qkv"]), None, L.EPI_BIAS_RESID, resid=d_pre_a1, tag="dgrad")
     d_t_s = ops.gemm(dqkv_t, _t(P["cross_t"]["w_qkv"]), None, L.EPI_BIAS_RESID, resid=d_pre_t1, tag="dgrad")
 
-    def self_backward(dy, Pm, ln, mask, T, tp, name, norm, buf):                               # :74-82 / :85-93
+    def self_backward(dy, Pm, ln, mask, T, tp, name, norm, buf, kind):                         # :74-82 / :85-93
         d_pre, G[f"{norm}.weight"], G[f"{norm}.bias"] = ops.layernorm_backward(tp["pre"], dy, ln[0])
-        d_o, G[f"{name}.out_proj.weight"], G[f"{name}.out_proj.bias"] = ops.linear_backward(d_pre, tp["o"], _t(Pm["w_o"]))
+        d_o, G[f"{name}.out_proj.weight"], G[f"{name}.out_proj.bias"] = ops.linear_backward(dr(d_pre, kind + "_o"), tp["o"], _t(Pm["w_o"]))
         qkv = tp["qkv"]
         ops.attention_backward(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], tp["o"], d_o, tp["lse"], mask, B, H, T, T, dh,
-                               grads=(buf[:, :d], buf[:, d:2 * d], buf[:, 2 * d:]))
+                               grads=(buf[:, :d], buf[:, d:2 * d], buf[:, 2 * d:]), drop=site(kind + "_p"))
         G[f"{name}.in_proj_weight"], G[f"{name}.in_proj_bias"] = ops.linear_wgrad(buf, tp["x"])
         if not need_dx:
             return None
         return ops.gemm(buf, _t(Pm["w_qkv"]), None, L.EPI_BIAS_RESID, resid=d_pre, tag="dgrad")
 
     # the packed cross-projection gradients are consumed: their buffers are reused for the self-attention ones
-    d_a_in = self_backward(d_a_s, P["self_a"], P["self_norm_a"], mask_a, Ta, tape["self_a"], "self_attn_a", "self_norm_a", dqkv_a)
-    d_t_in = self_backward(d_t_s, P["self_t"], P["self_norm_t"], mask_t, Tt, tape["self_t"], "self_attn_t", "self_norm_t", dqkv_t)
+    d_a_in = self_backward(d_a_s, P["self_a"], P["self_norm_a"], mask_a, Ta, tape["self_a"], "self_attn_a", "self_norm_a", dqkv_a, "self_a")
+    d_t_in = self_backward(d_t_s, P["self_t"], P["self_norm_t"], mask_t, Tt, tape["self_t"], "self_attn_t", "self_norm_t", dqkv_t, "self_t")
     return d_a_in, d_t_in, G
 
 
-def encoder_forward_train(enc, a: E.Seq, t: E.Seq, mask_a, mask_t):
+def encoder_forward_train(enc, a: E.Seq, t: E.Seq, mask_a, mask_t, drop=None):
     """CrossModalTransformer forward (cross_modal_block_tacfn.py:145-166) with one tape per layer."""
     tapes = []
-    for block in enc.layers:
-        a, t, tape = encoder_layer_forward_train(block, a, t, mask_a, mask_t)
+    for i, block in enumerate(enc.layers):
+        a, t, tape = encoder_layer_forward_train(block, a, t, mask_a, mask_t, drop, i)
         tapes.append(tape)
     return a, t, tapes
 
@@ -319,8 +350,14 @@ def encoder_backward(enc, tapes: list, d_a: torch.Tensor, d_t: torch.Tensor, nee
 # --------------------------------------------------------------------------- #
 # loss -> encoder outputs
 # --------------------------------------------------------------------------- #
+def drop_for(model) -> Optional[D.Drop]:
+    """The dropout of one training pass: the model's own rate while it is in train() mode (a fresh seed per call from
+    torch's CPU generator), None in eval() mode or for p = 0."""
+    return D.make(float(getattr(model, "p_drop", 0.0))) if model.training else None
+
+
 def decode_loss_and_backward(model, a: E.Seq, t: E.Seq, mask_a, mask_t, labels: torch.Tensor,
-                             beta_weight: float = 0.01) -> dict:
+                             beta_weight: float = 0.01, drop=None) -> dict:
     """Gate -> decoder -> loss and back, for a FusionWithEmotionDecoder-like `model` (attributes beta_gate and
     emotion_decoder) given the encoder outputs a / t.  Returns a dict:
       loss [1], logits [B, N_e], beta [B, 1], z [B, N_e, d]  (fp32);
@@ -328,7 +365,7 @@ def decode_loss_and_backward(model, a: E.Seq, t: E.Seq, mask_a, mask_t, labels: 
       d_a [B*T_a, d], d_t [B*T_t, d]: bf16 gradients of the encoder outputs (input of the encoder's backward)."""
     h, beta, gate_tape = gate_forward_train(model.beta_gate, a, t, mask_a, mask_t)
     fused_mask = model._build_fused_mask(mask_a, mask_t, h.T)
-    z, logits, dec_tape = decoder_forward_train(model.emotion_decoder, h, fused_mask)
+    z, logits, dec_tape = decoder_forward_train(model.emotion_decoder, h, fused_mask, drop)
     loss, d_logits, d_beta = ops.bce_beta_loss(logits, labels, beta, beta_weight)
     d_h, g_dec = decoder_backward(model.emotion_decoder, dec_tape, d_logits)
     d_a, d_t, g_gate = gate_backward(model.beta_gate, gate_tape, d_h, d_beta)
@@ -348,8 +385,9 @@ def loss_and_gradients(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a, mask
     a, t = E.to_seq(h_a, "h_a"), E.to_seq(h_t, "h_t")
     mask_a = E.check_mask(mask_a, a.B, a.T, "mask_a")
     mask_t = E.check_mask(mask_t, t.B, t.T, "mask_t")
-    a_enc, t_enc, enc_tapes = encoder_forward_train(model.cross_modal, a, t, mask_a, mask_t)
-    out = decode_loss_and_backward(model, a_enc, t_enc, mask_a, mask_t, labels, beta_weight)
+    drop = drop_for(model)
+    a_enc, t_enc, enc_tapes = encoder_forward_train(model.cross_modal, a, t, mask_a, mask_t, drop)
+    out = decode_loss_and_backward(model, a_enc, t_enc, mask_a, mask_t, labels, beta_weight, drop)
     _, _, g_enc = encoder_backward(model.cross_modal, enc_tapes, out.pop("d_a"), out.pop("d_t"))
     out["grads"].update({f"cross_modal.{k}": v for k, v in g_enc.items()})
     zero_key_bias_gradients(out["grads"])
@@ -365,10 +403,11 @@ def forward_train(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a, mask_t):
     a, t = E.to_seq(h_a, "h_a"), E.to_seq(h_t, "h_t")
     mask_a = E.check_mask(mask_a, a.B, a.T, "mask_a")
     mask_t = E.check_mask(mask_t, t.B, t.T, "mask_t")
-    a_enc, t_enc, enc_tapes = encoder_forward_train(model.cross_modal, a, t, mask_a, mask_t)
+    drop = drop_for(model)
+    a_enc, t_enc, enc_tapes = encoder_forward_train(model.cross_modal, a, t, mask_a, mask_t, drop)
     h, beta, gate_tape = gate_forward_train(model.beta_gate, a_enc, t_enc, mask_a, mask_t)
     fused_mask = model._build_fused_mask(mask_a, mask_t, h.T)
-    z, logits, dec_tape = decoder_forward_train(model.emotion_decoder, h, fused_mask)
+    z, logits, dec_tape = decoder_forward_train(model.emotion_decoder, h, fused_mask, drop)
     return logits, beta, z, dict(enc=enc_tapes, gate=gate_tape, dec=dec_tape)
 
 

@@ -9,7 +9,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(PKG_DIR), "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libhriemo_b200.so")
-SOURCES = ["host_common.cu", "gemm_bf16.cu", "gemm_wgrad.cu", "attention_bf16.cu", "attention_bwd.cu", "attention_bwd_tc.cu", "elementwise.cu", "small_ops.cu", "staging.cu", "train_ops.cu", "train_rows.cu", "precise_ops.cu",
+SOURCES = ["host_common.cu", "gemm_bf16.cu", "gemm_wgrad.cu", "attention_bf16.cu", "attention_bwd.cu", "attention_bwd_tc.cu", "elementwise.cu", "small_ops.cu", "staging.cu", "train_ops.cu", "train_rows.cu", "precise_ops.cu", "dropout_ops.cu",
            "host_pack.cpp", "host_shard.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

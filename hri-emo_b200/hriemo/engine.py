@@ -87,12 +87,16 @@ _warned_train = False
 
 
 def warn_if_training(module: torch.nn.Module, p_drop: float) -> None:
+    """Dropout lives in the TRAINING schedule (hriemo/backward.py, entered through the autograd boundary of the top-level
+    models or hriemo.train.Trainer).  A forward in train() mode that does not go there -- gradients disabled, a sub-module
+    called on its own, return_attention=True -- runs the inference schedule, which applies none: said once."""
     global _warned_train
     if module.training and p_drop > 0 and not _warned_train:
         _warned_train = True
         warnings.warn(
-            "hri-emo_b200: forward() applies no dropout and records no autograd graph even though the module is in "
-            "training mode; call .eval() for inference, hriemo.train.Trainer for training steps.",
+            "hri-emo_b200: this forward runs the inference schedule (no dropout, no autograd graph) although the module is "
+            "in training mode; dropout is applied by the training path: model(...) of FusionWithEmotionDecoder / "
+            "MoseiFusionWithEmotionDecoder with gradients enabled, or hriemo.train.Trainer.  Call .eval() for inference.",
             stacklevel=3)
 
 
@@ -261,39 +265,53 @@ def dec_residual_ln(pre32: torch.Tensor, ln) -> Tuple[torch.Tensor, torch.Tensor
     return ops.layernorm(pre32, ln[0], ln[1], want_bf16=True, want_f32=True)
 
 
-def decoder_self_block(zb, z32, P: dict, B: int, Ne: int, n_heads: int):
-    """LN(z + MHA(z, z, z)) over the N_e queries (models/emotion_decoder.py:42-43) -> (zb1, z32_1, (qkv, sa, pre1))."""
+def _dec_out_residual(x, w, b, z32, dk):
+    """z + dropout(x W^T + b) as fp32 (the decoder's residual stream); dk = (p8, scale, key) | None."""
+    if dk is None:
+        return ops.gemm(x, w, b, L.EPI_BIAS_RESID_F32, resid=z32)
+    return ops.dropout(ops.gemm(x, w, b, L.EPI_BIAS_F32), dk, resid=z32)
+
+
+def decoder_self_block(zb, z32, P: dict, B: int, Ne: int, n_heads: int, drop=None, site0: int = 0):
+    """LN(z + MHA(z, z, z)) over the N_e queries (models/emotion_decoder.py:42-43) -> (zb1, z32_1, (qkv, sa, pre1)).
+    drop (training, hriemo.dropout.Drop): site0 + 1 = the attention probabilities, site0 + 2 = dropout1."""
     d = zb.shape[1]
     dh = d // n_heads
     qkv = ops.gemm(zb, P["self"]["w_qkv"], P["self"]["b_qkv"], L.EPI_BIAS)
-    sa, _ = ops.small_attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], None, B, n_heads, Ne, Ne, dh)
-    pre1 = ops.gemm(sa, P["self"]["w_o"], P["self"]["b_o"], L.EPI_BIAS_RESID_F32, resid=z32)
+    sa, _ = ops.small_attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], None, B, n_heads, Ne, Ne, dh,
+                                drop=drop.site(site0 + 1) if drop else None)
+    pre1 = _dec_out_residual(sa, P["self"]["w_o"], P["self"]["b_o"], z32, drop.site(site0 + 2) if drop else None)
     zb1, z32 = dec_residual_ln(pre1, P["norm1"])
     return zb1, z32, (qkv, sa, pre1)
 
 
 def decoder_layer(zb, z32, kv_mem, mem_mask, P: dict, B: int, Ne: int, Lm: int, n_heads: int,
-                  want_attn: bool, tape: Optional[dict] = None, pre_self=None):
+                  want_attn: bool, tape: Optional[dict] = None, pre_self=None, drop=None, site0: int = 0):
     """models/emotion_decoder.py:33-64.  kv_mem = [K|V] projection of the memory for this layer.
     tape (training): receives the activations the backward pass needs (hriemo/backward.py).
     pre_self = (zb1, z32_1): the self-attention block's output when it is already known -- the first layer's input is
     the broadcast Parameter (models/emotion_decoder.py:127), so its self-attention block does not depend on the
-    utterance and is computed once per weight set (EmotionDecoder._build)."""
+    utterance and is computed once per weight set (EmotionDecoder._build).
+    drop (training, hriemo.dropout.Drop) with the layer's first site id site0: +1 self-attention probabilities, +2 dropout1,
+    +3 cross-attention probabilities, +4 dropout2, +5 the FFN's inner dropout, +6 dropout3 (models/emotion_decoder.py:14-29)."""
     d = (zb if pre_self is None else pre_self[0]).shape[1]
     dh = d // n_heads
     zb_in = zb
     if pre_self is None:
-        zb1, z32, (qkv, sa, pre1) = decoder_self_block(zb, z32, P, B, Ne, n_heads)
+        zb1, z32, (qkv, sa, pre1) = decoder_self_block(zb, z32, P, B, Ne, n_heads, drop, site0)
     else:
         zb1, z32 = pre_self
         qkv = sa = pre1 = None
     q = ops.gemm(zb1, P["cross_wq"], P["cross_bq"], L.EPI_BIAS)
+    ds = (lambda k: drop.site(site0 + k)) if drop else (lambda k: None)
     ca, probs = ops.small_attention(q, kv_mem[:, :d], kv_mem[:, d:], mem_mask, B, n_heads, Ne, Lm, dh,
-                                    want_probs=want_attn)
-    pre2 = ops.gemm(ca, P["cross_wo"], P["cross_bo"], L.EPI_BIAS_RESID_F32, resid=z32)
+                                    want_probs=want_attn, drop=ds(3))
+    pre2 = _dec_out_residual(ca, P["cross_wo"], P["cross_bo"], z32, ds(4))
     zb2, z32 = dec_residual_ln(pre2, P["norm2"])
     h = ops.gemm(zb2, P["lin1"]["w"], P["lin1"]["b"], L.EPI_BIAS_RELU)
-    pre3 = ops.gemm(h, P["lin2"]["w"], P["lin2"]["b"], L.EPI_BIAS_RESID_F32, resid=z32)
+    if drop:
+        h = ops.dropout(h, ds(5))   # the tape keeps the DROPPED hidden: linear2's input, and (h > 0) = kept and active
+    pre3 = _dec_out_residual(h, P["lin2"]["w"], P["lin2"]["b"], z32, ds(6))
     zb, z32 = dec_residual_ln(pre3, P["norm3"])
     if tape is not None:
         tape.update(zb_in=zb_in, qkv=qkv, sa=sa, pre1=pre1, zb1=zb1, qc=q, kv_mem=kv_mem, ca=ca, pre2=pre2, zb2=zb2,

@@ -48,6 +48,7 @@ class AttnArgs(C.Structure):
         ("kv_steps", C.c_void_p),
         ("no_head_pairs", C.c_int32),
         ("lse", C.c_void_p),
+        ("drop_p8", C.c_uint32), ("drop_key", C.c_uint32), ("drop_scale", C.c_float),
     ]
 
 
@@ -67,6 +68,7 @@ class AttnBwdArgs(C.Structure):
         ("scale", C.c_float),
         ("impl", C.c_int32),
         ("kv_steps", C.c_void_p),
+        ("drop_p8", C.c_uint32), ("drop_key", C.c_uint32), ("drop_scale", C.c_float),
     ]
 
 
@@ -135,6 +137,12 @@ SIGNATURES = {
     "hriemo_attention_f32": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I32, _I32, _I32, _I32, _I32, _F, _P]),
     "hriemo_masked_mean_f32": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P]),
     "hriemo_gate_blend_f32": (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _I32, _I32, _P]),
+    "hriemo_small_attention_dropout": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _F,
+                                                  C.c_uint32, C.c_uint32, _F, _P]),
+    "hriemo_small_attention_backward_dropout": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _P, _I64,
+                                                           _I32, _I32, _I32, _I32, _I32, _F, C.c_uint32, C.c_uint32, _F, _P]),
+    "hriemo_dropout": (C.c_int, [_P, _I32, _I64, _P, _I64, _P, _I64, _I64, _I32, C.c_uint32, _F, C.c_uint32, _P]),
+    "hriemo_dropout_mask": (C.c_int, [_P, _I64, _I32, C.c_uint32, C.c_uint32, _I64, _P]),
     "hriemo_host_pack_bf16": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, _I64, _I64, _I64, _I32]),
 }
 

@@ -195,7 +195,7 @@ def kv_steps(key_pad: torch.Tensor) -> torch.Tensor:
 @_on_tensor_device
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Optional[torch.Tensor],
               B: int, H: int, Tq: int, Tk: int, dh: int, skip_padded_tiles: bool = True,
-              pair_heads: bool = True, want_lse: bool = False, out: Optional[torch.Tensor] = None):
+              pair_heads: bool = True, want_lse: bool = False, out: Optional[torch.Tensor] = None, drop=None):
     """q: [B*Tq, >=H*dh] view, k / v: [B*Tk, >=H*dh] views (column slices of a packed projection are
     fine).  Returns [B*Tq, H*dh] bf16 (written into `out` when given: a [B*Tq, >= H*dh] view with 16-byte aligned rows).  pair_heads=False switches the two-heads-per-work-item form of
     short query sequences off (include/hriemo.h: no_head_pairs; same result bit for bit).
@@ -227,6 +227,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Option
     args.no_head_pairs = 0 if pair_heads else 1
     lse = torch.empty((B, H, Tq), dtype=f32, device=q.device) if want_lse else None
     args.lse = _ptr(lse)
+    if drop is not None:   # training: dropout on the probabilities, (p8, scale, key) from hriemo.dropout.Drop.site
+        args.drop_p8, args.drop_scale, args.drop_key = drop
     tok = _prof_begin("attention", 4.0 * B * H * Tq * Tk * dh)
     _l.check(_l.load().hriemo_attention_bf16(C.byref(args), _stream()), "attention_bf16")
     _prof_end(tok)
@@ -249,11 +251,21 @@ def attention_probs(q: torch.Tensor, k: torch.Tensor, key_pad: Optional[torch.Te
 
 @_on_tensor_device
 def small_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Optional[torch.Tensor],
-                    B: int, H: int, Nq: int, Tk: int, dh: int, want_probs: bool = False):
-    """Decoder attention: q [B*Nq, *], k/v [B*Tk, *] row-major views.  Returns (out bf16, probs|None)."""
+                    B: int, H: int, Nq: int, Tk: int, dh: int, want_probs: bool = False, drop=None):
+    """Decoder attention: q [B*Nq, *], k/v [B*Tk, *] row-major views.  Returns (out bf16, probs|None).
+    drop = (p8, scale, key): dropout on the probabilities (training; no attention map then)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _chk2d(t, bf16, f"small_attention {n}")
     out = torch.empty((B * Nq, H * dh), dtype=bf16, device=q.device)
+    if drop is not None:
+        if want_probs:
+            raise _l.HriemoError("small_attention: attention maps are not returned together with dropout")
+        m = _mask_u8(key_pad, B, Tk, "small_attention")
+        _l.check(_l.load().hriemo_small_attention_dropout(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+                                                           v.stride(0), _ptr(m), out.data_ptr(), out.stride(0), B, H, Nq, Tk,
+                                                           dh, 1.0 / math.sqrt(dh), drop[0], drop[2], drop[1], _stream()),
+                 "small_attention_dropout")
+        return out, None
     probs = torch.empty((B, Nq, Tk), dtype=f32, device=q.device) if want_probs else None
     m = _mask_u8(key_pad, B, Tk, "small_attention")
     _l.check(_l.load().hriemo_small_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
@@ -625,8 +637,9 @@ def relu_backward(dy: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
 
 @_on_tensor_device
 def small_attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, d_out: torch.Tensor,
-                             key_pad: Optional[torch.Tensor], B: int, H: int, Nq: int, Tk: int, dh: int, out=None):
+                             key_pad: Optional[torch.Tensor], B: int, H: int, Nq: int, Tk: int, dh: int, out=None, drop=None):
     """Backward of small_attention: (dq [B*Nq, H*dh], dk [B*Tk, H*dh], dv [B*Tk, H*dh]) in bf16.
+    drop = (p8, scale, key): the forward's dropout on the probabilities (the same mask is recomputed).
     out = (dq, dk, dv): existing row-major bf16 views to write (e.g. the columns of one [rows, 3d] / [rows, 2d]
     buffer, so that the projection's backward sees one operand)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (d_out, "d_out")):
@@ -643,6 +656,13 @@ def small_attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, 
             if tuple(t.shape) != (rows, d):
                 raise _l.HriemoError(f"small_attention_backward: {n} must be [{rows}, {d}], got {tuple(t.shape)}")
     m = _mask_u8(key_pad, B, Tk, "small_attention_backward")
+    if drop is not None:
+        _l.check(_l.load().hriemo_small_attention_backward_dropout(
+            q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), d_out.data_ptr(), d_out.stride(0),
+            _ptr(m), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0), B, H, Nq, Tk, dh,
+            1.0 / math.sqrt(dh), drop[0], drop[2], drop[1], _stream()),
+            "small_attention_backward_dropout")
+        return dq, dk, dv
     _l.check(_l.load().hriemo_small_attention_backward(
         q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), d_out.data_ptr(), d_out.stride(0),
         _ptr(m), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0), B, H, Nq, Tk, dh,
@@ -654,7 +674,7 @@ def small_attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, 
 @_on_tensor_device
 def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor,
                        lse: torch.Tensor, key_pad: Optional[torch.Tensor], B: int, H: int, Tq: int, Tk: int, dh: int,
-                       grads=None, impl: int = 0):
+                       grads=None, impl: int = 0, drop=None):
     """Backward of `attention` (the encoder's attention): q / k / v as in the forward (column slices are fine), out
     [B*Tq, H*dh] and lse [B, H, Tq] from attention(..., want_lse=True), d_out [B*Tq, H*dh].
     -> (dq [B*Tq, H*dh], dk [B*Tk, H*dh], dv [B*Tk, H*dh]) bf16; grads = (dq, dk, dv): existing views to write into.
@@ -688,6 +708,8 @@ def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: t
     a.B, a.H, a.Tq, a.Tk, a.dh = B, H, Tq, Tk, dh
     a.scale = 1.0 / math.sqrt(dh)
     a.impl = int(impl)
+    if drop is not None:   # the forward's dropout on the probabilities: (p8, scale, key)
+        a.drop_p8, a.drop_scale, a.drop_key = drop
     steps = None
     if m is not None and Tk > 64:
         steps = kv_steps(m)   # trailing all-PAD key tiles are skipped (ragged batches; exact: a masked key has P = 0)
@@ -877,3 +899,32 @@ def gate_blend_f32(a: torch.Tensor, T_a: int, t: torch.Tensor, w: torch.Tensor, 
     _l.check(_l.load().hriemo_gate_blend_f32(a.data_ptr(), T_a, t.data_ptr(), w.data_ptr(), h.data_ptr(), beta.data_ptr(),
                                               B, L, d, _stream()), "gate_blend_f32")
     return h, beta
+
+
+# ------------------------------------------------------------------ dropout of the training step (hriemo/dropout.py)
+@_on_tensor_device
+def dropout(x: torch.Tensor, drop, resid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = (keep ? x * scale : 0) [+ resid]; x / resid / out all bf16 or all f32 [rows, cols]; drop = (p8, scale, key).
+    Called on a sub-layer's output with the residual in the forward and on the gradient (no residual) in the backward."""
+    if x.dtype not in (bf16, f32):
+        raise _l.HriemoError(f"dropout: unsupported dtype {x.dtype}")
+    _chk2d(x, x.dtype, "dropout x")
+    if resid is not None:
+        _chk2d(resid, x.dtype, "dropout resid")
+        if resid.shape != x.shape:
+            raise _l.HriemoError(f"dropout: residual shape {tuple(resid.shape)} != {tuple(x.shape)}")
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), dtype=x.dtype, device=x.device)
+    p8, scale, key = drop
+    _l.check(_l.load().hriemo_dropout(x.data_ptr(), int(x.dtype == f32), x.stride(0), _ptr(resid),
+                                       resid.stride(0) if resid is not None else 0, out.data_ptr(), out.stride(0), rows, cols,
+                                       p8, scale, key, _stream()), "dropout")
+    return out
+
+
+def dropout_mask(rows: int, cols: int, key: int, p8: int, device, rows_per_stream: int = 0) -> torch.Tensor:
+    """The keep mask as bool [rows, cols] (tests; rows_per_stream > 0: the (utterance, head) streams of an attention)."""
+    out = torch.empty((rows, cols), dtype=torch.uint8, device=device)
+    with torch.cuda.device(out.device):
+        _l.check(_l.load().hriemo_dropout_mask(out.data_ptr(), rows, cols, key, p8, rows_per_stream, _stream()), "dropout_mask")
+    return out.view(torch.bool)

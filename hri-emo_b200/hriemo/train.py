@@ -14,7 +14,8 @@ moments), in `named_parameters()` order with each tensor starting on a 16-byte b
 then one reduction, the update one launch, and the data-parallel exchange (one process per GPU, utterances sharded,
 SURVEY sec. 8e) ONE all-reduce of the gradient arena over NCCL — 218 MB for the default model — instead of 119.
 
-Dropout is not applied (the parity configuration of SURVEY sec. 8d config 5 is dropout = 0).  No autograd graph is
+Dropout is applied when the model was built with p > 0 and is in train() mode (hriemo/dropout.py: counter-based masks
+regenerated in the backward; the parity configuration of SURVEY sec. 8d config 5 is dropout = 0).  No autograd graph is
 involved; torch provides device memory, streams and the process group.
 """
 from __future__ import annotations
@@ -61,9 +62,11 @@ class Trainer:
                  eps: float = 1e-8, max_norm: float = 5.0, beta_weight: float = 0.01, process_group=None,
                  distributed: Optional[bool] = None, graph: bool = False):
         p_drop = max((float(getattr(m, "p_drop", 0.0) or 0.0) for m in model.modules()), default=0.0)
-        if p_drop > 0:
-            warnings.warn(f"hri-emo_b200 Trainer: the model was built with dropout={p_drop}; the B200 training step does not "
-                          "apply dropout (it computes the dropout = 0 step, the configuration parity is defined on)", stacklevel=2)
+        if p_drop > 0 and graph:
+            warnings.warn(f"hri-emo_b200 Trainer: the model was built with dropout={p_drop}; the dropout masks are functions of "
+                          "per-step keys that a captured graph would freeze, so steps taken in train() mode run eagerly "
+                          "instead of through CUDA-graph replay", stacklevel=2)
+        self.p_drop = p_drop
         params = list(model.named_parameters())
         if not params:
             raise L.HriemoError("Trainer: the model has no parameters")
@@ -172,7 +175,8 @@ class Trainer:
         return dict(self._graph_out)
 
     def step(self, h_a: torch.Tensor, h_t: torch.Tensor, mask_a, mask_t, labels: torch.Tensor) -> dict:
-        fb = self._graphed_forward_backward if self.use_graph else self._forward_backward
+        dropping = self.p_drop > 0 and self.model.training   # fresh mask keys every step: not replayable
+        fb = self._graphed_forward_backward if self.use_graph and not dropping else self._forward_backward
         out = fb(h_a, h_t, mask_a, mask_t, labels)
         out.update(self.apply())
         return out

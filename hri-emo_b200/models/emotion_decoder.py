@@ -51,9 +51,9 @@ class ExplainableDecoderLayer(nn.Module):
         return ops.gemm(mem.x, P["cross_wkv"], P["cross_bkv"], L.EPI_BIAS)  # [B*L, 2d] = [K|V]
 
     def run(self, zb, z32, kv_mem, mem_mask, B: int, Ne: int, Lm: int, want_attn: bool, tape: dict | None = None,
-            pre_self=None):
+            pre_self=None, drop=None, site0: int = 0):
         return E.decoder_layer(zb, z32, kv_mem, mem_mask, self._prep.get(), B, Ne, Lm, self.nhead, want_attn, tape,
-                               pre_self)
+                               pre_self, drop, site0)
 
     @torch.no_grad()
     def forward(self, tgt, memory, memory_key_padding_mask=None, return_attention=False):
@@ -98,8 +98,9 @@ class EmotionDecoder(nn.Module):
             p.update(w_out=E.v32(self.out_proj.weight), b_out=E.v32(self.out_proj.bias))
         return p
 
-    def run(self, mem: E.Seq, mem_mask, want_attn: bool = False, tapes: list | None = None):
-        """tapes (training): a list that receives one dict of saved activations per layer (hriemo/backward.py)."""
+    def run(self, mem: E.Seq, mem_mask, want_attn: bool = False, tapes: list | None = None, drop=None):
+        """tapes (training): a list that receives one dict of saved activations per layer (hriemo/backward.py);
+        drop (training): hriemo.dropout.Drop of this step, layer i uses the sites 100000 + 100 i + 1..6."""
         P = self._prep.get()
         B, Ne, d = mem.B, self.num_emotions, self.d_model
         zb = z32 = None
@@ -118,7 +119,7 @@ class EmotionDecoder(nn.Module):
                 pre_self = (P["self0_b"].unsqueeze(0).expand(B, Ne, d).contiguous().view(B * Ne, d),
                             P["self0_f"].unsqueeze(0).expand(B, Ne, d).contiguous().view(B * Ne, d))
             zb, z32, probs = layer.run(zb, z32, layer.project_memory(mem), mem_mask, B, Ne, mem.T, want_attn, tape,
-                                       pre_self)
+                                       pre_self, drop, 100000 + 100 * li)
             if want_attn and probs is not None:
                 attn.append(probs)
         logits = None

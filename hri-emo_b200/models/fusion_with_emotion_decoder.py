@@ -104,8 +104,7 @@ class FusionWithEmotionDecoder(nn.Module):
         In train() mode with gradients enabled the three outputs carry a grad_fn (hriemo/autograd.py): the reference's
         training loops -- criterion(logits, y) [+ beta terms], loss.backward(), clip_grad_norm_, optimizer.step()
         (scripts/fusion/train_fusion_seq_level_decoder.py:310-333) -- run unmodified and fill .grad through the
-        hand-scheduled backward pass (dropout is not applied: the dropout = 0 step is computed)."""
-        E.warn_if_training(self, self.p_drop)
+        hand-scheduled backward pass; dropout (p > 0) is applied at every site of the reference, hriemo/dropout.py)."""
         h_a = self._ensure_3d(h_a)
         h_t = self._ensure_3d(h_t)
         E.require_cuda(h_a, "h_a")
@@ -119,6 +118,7 @@ class FusionWithEmotionDecoder(nn.Module):
                 and any(p.requires_grad for p in self.parameters())):
             from hriemo.autograd import fusion_forward_with_grad
             return fusion_forward_with_grad(self, h_a, h_t, mask_a, mask_t)
+        E.warn_if_training(self, self.p_drop)   # the inference schedule: no dropout even in train() mode
         with torch.no_grad():
             logits, beta, z, pack = self.run_slabbed(h_a, h_t, mask_a, mask_t, return_attention)
         if return_attention:

@@ -52,7 +52,6 @@ class MoseiFusionWithEmotionDecoder(nn.Module):
         whose backward also fills audio_proj / text_proj (hriemo/autograd.py), so the MOSEI training loop
         (scripts/fusion/train_mosei_fusion_seq_level_decoder.py:367-429: autocast, pos_weight BCE, beta entropy,
         GradScaler, gradient accumulation) runs unmodified."""
-        E.warn_if_training(self, self.backbone.p_drop)
         E.require_cuda(h_a, "h_a")
         E.require_cuda(h_t, "h_t")
         mask_a = E.check_mask(mask_a, h_a.shape[0], h_a.shape[1], "mask_a")
@@ -64,6 +63,7 @@ class MoseiFusionWithEmotionDecoder(nn.Module):
                 and any(p.requires_grad for p in self.parameters())):
             from hriemo.autograd import mosei_forward_with_grad
             return mosei_forward_with_grad(self, h_a, h_t, mask_a, mask_t)
+        E.warn_if_training(self, self.backbone.p_drop)   # the inference schedule: no dropout even in train() mode
         with torch.no_grad():
             return self._forward_eval(h_a, h_t, mask_a, mask_t, return_attention)
 

@@ -138,6 +138,13 @@ typedef struct hriemo_attn_args {
   /* Optional: lse[b, h, t_q] = ln sum_k exp(scale * q.k) over the unmasked keys (f32 [B, H, Tq]; -inf when every key
    * is masked) -- the per-row statistic a backward pass needs to rebuild the probabilities. */
   float* lse;
+  /* Training only: dropout on the attention probabilities (nn.MultiheadAttention(dropout=p) of the reference).  drop_p8
+   * = round(256 p) (0 = off), drop_scale = 1 / (1 - drop_p8 / 256), drop_key = the stream key of this attention
+   * (csrc/dropout.cuh: probability (b, h, q, k) is kept iff byte (k & 3) of drop_word(drop_key_bh(key, b * H + h), q,
+   * k >> 2) >= drop_p8).  The row sums (and lse) are those of the undropped probabilities, as in torch. */
+  uint32_t drop_p8;
+  uint32_t drop_key;
+  float drop_scale;
 } hriemo_attn_args;
 
 /* steps[b] = (index of the last valid key of utterance b) / 64 + 1, or 1 when every key is PAD. */
@@ -411,6 +418,10 @@ typedef struct hriemo_attn_bwd_args {
   /* Optional, with key_pad: kv_steps[b] from hriemo_attention_kv_steps -- tiles of trailing PAD keys are neither
    * visited by the dQ pass nor computed by the dK / dV pass (they receive zeros); same result (impl 0 only). */
   const int32_t* kv_steps;
+  /* The forward's dropout on the probabilities (hriemo_attn_args.drop_*): the same mask is recomputed (impl 0 only). */
+  uint32_t drop_p8;
+  uint32_t drop_key;
+  float drop_scale;
 } hriemo_attn_bwd_args;
 int hriemo_attention_backward_bf16(const hriemo_attn_bwd_args* args, void* stream);
 
@@ -444,6 +455,32 @@ int hriemo_masked_mean_f32(const float* x, const uint8_t* pad, float* pooled, in
  * a holds T_a >= L rows per utterance, t holds L, w is [B, d]. */
 int hriemo_gate_blend_f32(const float* a, int32_t T_a, const float* t, const float* w, float* h, float* beta, int32_t B,
                           int32_t L, int32_t d, void* stream);
+
+/* ---- dropout of the training step (csrc/dropout.cuh: counter-based masks, nothing stored).
+ * hriemo_dropout: out = (keep ? x * scale : 0) [+ resid], x / resid / out all f32 (is_f32) or all bf16, [rows, cols] with
+ * cols % 4 == 0; p8 = round(256 p), scale = 1 / (1 - p8 / 256), key = the stream key of the site.  The forward calls it on
+ * a sub-layer's output with the residual (nn.Dropout at models/cross_modal_block_tacfn.py:81-119,
+ * models/emotion_decoder.py:43-59), the backward on the gradient with the same key.
+ * hriemo_dropout_mask: the keep mask itself as bytes (tests; the definition of the mapping): rows_per_stream = 0 -> one
+ * stream of `rows` rows under `key`; > 0 -> consecutive blocks of rows_per_stream rows are the streams drop_key_bh(key, s)
+ * (the probabilities of (utterance, head) s = b * H + h: rows = B * H * Tq, rows_per_stream = Tq, cols = Tk). */
+int hriemo_dropout(const void* x, int32_t is_f32, int64_t ldx, const void* resid, int64_t ldr, void* out, int64_t ldo,
+                   int64_t rows, int32_t cols, uint32_t p8, float scale, uint32_t key, void* stream);
+int hriemo_dropout_mask(uint8_t* out, int64_t rows, int32_t cols, uint32_t key, uint32_t p8, int64_t rows_per_stream,
+                        void* stream);
+
+/* The decoder's attention with dropout on the probabilities (training; nn.MultiheadAttention(dropout=p) at
+ * models/emotion_decoder.py:14, 20): hriemo_small_attention / _backward plus (drop_p8, drop_key, drop_scale) as in
+ * hriemo_attn_args; streams are (utterance, head), rows the queries. */
+int hriemo_small_attention_dropout(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                   const uint8_t* key_pad, void* out_bf16, int64_t ldo, int32_t B, int32_t H, int32_t Nq,
+                                   int32_t Tk, int32_t dh, float scale, uint32_t drop_p8, uint32_t drop_key, float drop_scale,
+                                   void* stream);
+int hriemo_small_attention_backward_dropout(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                            const void* d_out, int64_t lddo, const uint8_t* key_pad, void* dq, int64_t lddq,
+                                            void* dk, int64_t lddk, void* dv, int64_t lddv, int32_t B, int32_t H, int32_t Nq,
+                                            int32_t Tk, int32_t dh, float scale, uint32_t drop_p8, uint32_t drop_key,
+                                            float drop_scale, void* stream);
 
 /* Mean over time (UNMASKED) of an f32 [B,L,d] tensor — models/fusion_classifier.py:145. */
 int hriemo_mean_over_time(const float* x, float* out, int32_t B, int32_t L, int32_t d, void* stream);

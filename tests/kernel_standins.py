@@ -82,21 +82,44 @@ def _heads(x, B, T, H, dh):
     return x.to(HI).reshape(B, T, H, dh).transpose(1, 2)
 
 
-def small_attention(q, k, v, key_pad, B, H, Nq, Tk, dh, want_probs=False):
+def _drop_probs(p, drop, B, H, Tq, Tk):
+    """Dropout on attention probabilities [B, H, Tq, Tk] with the masks of csrc/dropout.cuh (hriemo/dropout.py holds the
+    same arithmetic): stream (b, h) has the key key_bh(key, b * H + h), rows are queries, columns keys."""
+    if drop is None:
+        return p
+    from hriemo import dropout as D
+
+    p8, scale, key = drop
+    keep = torch.stack([D.keep_mask(Tq, Tk, D.key_bh(key, bh), p8) for bh in range(B * H)]).view(B, H, Tq, Tk)
+    return p * keep.to(p.dtype) * scale
+
+
+def dropout(x, drop, resid=None):
+    from hriemo import dropout as D
+
+    p8, scale, key = drop
+    y = x.to(HI) * D.keep_mask(x.shape[0], x.shape[1], key, p8).to(HI) * scale
+    if resid is not None:
+        assert resid.dtype == x.dtype and resid.shape == x.shape
+        y = y + resid.to(HI)
+    return y.to(x.dtype)
+
+
+def small_attention(q, k, v, key_pad, B, H, Nq, Tk, dh, want_probs=False, drop=None):
     s = _heads(q, B, Nq, H, dh) @ _heads(k, B, Tk, H, dh).transpose(-1, -2) / math.sqrt(dh)
     if key_pad is not None:
         s = s.masked_fill(key_pad[:, None, None, :], float("-inf"))
     p = torch.softmax(s, dim=-1)
-    o = (p @ _heads(v, B, Tk, H, dh)).transpose(1, 2).reshape(B * Nq, H * dh)
+    o = (_drop_probs(p, drop, B, H, Nq, Tk) @ _heads(v, B, Tk, H, dh)).transpose(1, 2).reshape(B * Nq, H * dh)
     return o.to(LO), (p.mean(1) if want_probs else None)
 
 
-def small_attention_backward(q, k, v, d_out, key_pad, B, H, Nq, Tk, dh, out=None):
+def small_attention_backward(q, k, v, d_out, key_pad, B, H, Nq, Tk, dh, out=None, drop=None):
     qr, kr, vr = (t.to(HI).clone().requires_grad_(True) for t in (q, k, v))
     s = _heads(qr, B, Nq, H, dh) @ _heads(kr, B, Tk, H, dh).transpose(-1, -2) / math.sqrt(dh)
     if key_pad is not None:
         s = s.masked_fill(key_pad[:, None, None, :], float("-inf"))
-    o = (torch.softmax(s, dim=-1) @ _heads(vr, B, Tk, H, dh)).transpose(1, 2).reshape(B * Nq, H * dh)
+    o = (_drop_probs(torch.softmax(s, dim=-1), drop, B, H, Nq, Tk) @ _heads(vr, B, Tk, H, dh)).transpose(1, 2).reshape(B * Nq, H * dh)
     o.backward(d_out.to(HI))
     res = (qr.grad.to(LO), kr.grad.to(LO), vr.grad.to(LO))
     if out is None:
@@ -107,22 +130,23 @@ def small_attention_backward(q, k, v, d_out, key_pad, B, H, Nq, Tk, dh, out=None
     return out
 
 
-def _attn(qr, kr, vr, key_pad, B, H, Tq, Tk, dh):
+def _attn(qr, kr, vr, key_pad, B, H, Tq, Tk, dh, drop=None):
     s = _heads(qr, B, Tq, H, dh) @ _heads(kr, B, Tk, H, dh).transpose(-1, -2) / math.sqrt(dh)
     if key_pad is not None:
         s = s.masked_fill(key_pad[:, None, None, :], float("-inf"))
-    return (torch.softmax(s, dim=-1) @ _heads(vr, B, Tk, H, dh)).transpose(1, 2).reshape(B * Tq, H * dh), s
+    p = _drop_probs(torch.softmax(s, dim=-1), drop, B, H, Tq, Tk)
+    return (p @ _heads(vr, B, Tk, H, dh)).transpose(1, 2).reshape(B * Tq, H * dh), s
 
 
-def attention(q, k, v, key_pad, B, H, Tq, Tk, dh, skip_padded_tiles=True, pair_heads=True, want_lse=False):
-    o, s = _attn(q, k, v, key_pad, B, H, Tq, Tk, dh)
+def attention(q, k, v, key_pad, B, H, Tq, Tk, dh, skip_padded_tiles=True, pair_heads=True, want_lse=False, out=None, drop=None):
+    o, s = _attn(q, k, v, key_pad, B, H, Tq, Tk, dh, drop)
     return (o.to(LO), torch.logsumexp(s, dim=-1)) if want_lse else o.to(LO)
 
 
-def attention_backward(q, k, v, out, d_out, lse, key_pad, B, H, Tq, Tk, dh, grads=None, impl=0):
+def attention_backward(q, k, v, out, d_out, lse, key_pad, B, H, Tq, Tk, dh, grads=None, impl=0, drop=None):
     assert lse.shape == (B, H, Tq) and out.shape == d_out.shape == (B * Tq, H * dh)
     qr, kr, vr = (t.to(HI).clone().requires_grad_(True) for t in (q, k, v))
-    o, _ = _attn(qr, kr, vr, key_pad, B, H, Tq, Tk, dh)
+    o, _ = _attn(qr, kr, vr, key_pad, B, H, Tq, Tk, dh, drop)
     o.backward(d_out.to(HI))
     res = (qr.grad.to(LO), kr.grad.to(LO), vr.grad.to(LO))
     if grads is None:

@@ -164,9 +164,11 @@ def test_trainer_keeps_the_state_dict_contract(monkeypatch):
     assert all(lo <= p.data_ptr() < hi for p in model.parameters())
     for name, (o, n) in trainer.slots.items():
         assert torch.equal(trainer.params[o:o + n], other[name].reshape(-1)), name
-    with pytest.warns(UserWarning, match="does not.*apply dropout|dropout"):
+    # dropout > 0 is applied by the training step in train() mode; only its combination with CUDA-graph replay (the mask
+    # keys are host scalars baked into a captured graph) is announced and falls back to eager steps
+    with pytest.warns(UserWarning, match="CUDA-graph replay"):
         Trainer(FusionWithEmotionDecoder(d_model=128, num_emotions=4, n_heads=2, num_layers_fusion=1,
-                                         num_layers_decoder=1, beta_hidden=32, dropout=0.1).double(), distributed=False)
+                                         num_layers_decoder=1, beta_hidden=32, dropout=0.1).double(), distributed=False, graph=True)
 
 
 @pytest.mark.parametrize("L_f,L_d,Ne,mask_mode", [(3, 1, 8, "audio"), (1, 3, 1, "text"), (0, 2, 4, "both")])
@@ -234,3 +236,89 @@ def test_trainer_gradient_accumulation_and_lr_schedule(monkeypatch):
         assert abs(info["grad_norm"].item() - want["grad_norm"]) <= 1e-9 * want["grad_norm"]
         for k, p in model.named_parameters():
             assert (p.detach() - sd[k]).abs().max().item() <= 1e-9, k
+
+
+def test_dropout_schedule_is_the_gradient_of_its_forward(monkeypatch):
+    """Dropout > 0 (hriemo/dropout.py): with the mask keys of a step held fixed, the training forward is a smooth
+    function of the parameters and the hand-scheduled backward must be its gradient -- every one of the 16 dropout
+    sites of a layer (sub-layer outputs, the decoder FFN's inner dropout, the probabilities of all six MHAs) has to be
+    re-applied in the backward at the right place with the same stream key.  Exact float64 stand-ins (whose masks are
+    the arithmetic of csrc/dropout.cuh restated in torch); central differences on entries of every parameter family."""
+    kernel_standins.install(monkeypatch, exact=True)
+    from hriemo import backward, dropout as D
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    torch.manual_seed(11)
+    model = FusionWithEmotionDecoder(d_model=128, num_emotions=3, n_heads=2, num_layers_fusion=2, num_layers_decoder=2,
+                                     beta_hidden=32, dropout=0.25).double().train()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "norm" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    g = torch.Generator().manual_seed(12)
+    B, T_a, T_t, d = 3, 10, 6, 128
+    a, t = torch.randn(B, T_a, d, generator=g).double(), torch.randn(B, T_t, d, generator=g).double()
+    ma = torch.arange(T_a)[None, :] >= torch.tensor([10, 7, 4])[:, None]
+    mt = torch.arange(T_t)[None, :] >= torch.tensor([6, 3, 5])[:, None]
+    labels = (torch.rand(B, 3, generator=g) < 0.5).double()
+    monkeypatch.setattr(D, "make", lambda p: D.Drop(p, 20240607) if p > 0 else None)   # the same masks for every call
+    # to_seq casts fp32 features to bf16; in float64 mode hand the streams over as they are
+    monkeypatch.setattr(backward.E, "to_seq", lambda x, what, ld=None: backward.E.Seq(x.reshape(-1, x.shape[-1]), x.shape[0], x.shape[1]))
+
+    from hriemo.train import invalidate_prepared
+
+    def loss_and_grads():
+        invalidate_prepared(model)   # the entries below are perturbed through .data: the operand caches would not notice
+        out = backward.loss_and_gradients(model, a, t, ma, mt, labels)
+        return out["loss"].item(), out["grads"], out["logits"].clone()
+
+    loss0, grads, logits_train = loss_and_grads()
+    # dropout is really on: the eval-mode step differs, and is the p = 0 schedule
+    model.eval()
+    loss_eval, _, logits_eval = loss_and_grads()
+    model.train()
+    assert abs(loss_eval - loss0) > 1e-4 and (logits_eval - logits_train).abs().max().item() > 1e-3
+    params = dict(model.named_parameters())
+    gen = torch.Generator().manual_seed(13)
+    checked = 0
+    for name in ["cross_modal.layers.0.self_attn_a.in_proj_weight", "cross_modal.layers.0.self_attn_t.out_proj.weight",
+                 "cross_modal.layers.0.attn_a2t.in_proj_weight", "cross_modal.layers.1.attn_t2a.out_proj.bias",
+                 "cross_modal.layers.0.ffn_a.0.weight", "cross_modal.layers.1.ffn_t.2.weight", "cross_modal.layers.0.norm_a1.weight",
+                 "cross_modal.layers.1.self_norm_t.bias", "beta_gate.mlp.0.weight", "emotion_decoder.emotion_queries",
+                 "emotion_decoder.layers.0.self_attn.in_proj_weight", "emotion_decoder.layers.0.cross_attn.in_proj_weight",
+                 "emotion_decoder.layers.1.cross_attn.out_proj.weight", "emotion_decoder.layers.0.linear1.weight",
+                 "emotion_decoder.layers.1.linear2.weight", "emotion_decoder.layers.1.norm3.weight", "emotion_decoder.out_proj.weight"]:
+        p = params[name]
+        flat = p.data.view(-1)
+        for idx in torch.randint(0, flat.numel(), (3,), generator=gen).tolist():
+            old = flat[idx].item()
+            eps = 1e-6
+            flat[idx] = old + eps
+            lp = loss_and_grads()[0]
+            flat[idx] = old - eps
+            lm = loss_and_grads()[0]
+            flat[idx] = old
+            num = (lp - lm) / (2 * eps)
+            ana = grads[name].reshape(-1)[idx].item()
+            assert abs(num - ana) <= 1e-6 + 1e-4 * abs(num), (name, idx, num, ana)
+            checked += 1
+    assert checked == 51
+
+
+def test_dropout_mask_arithmetic_and_keys():
+    """hriemo/dropout.py: keep rate of the quantised probability, determinism, distinct streams, p8 = 0 keeps everything."""
+    from hriemo import dropout as D
+
+    drop = D.Drop(0.1, 99)
+    assert drop.p8 == 26 and abs(drop.scale - 1.0 / (1.0 - 26 / 256)) < 1e-12 and drop.on
+    p8, scale, key = drop.site(1005)
+    m = D.keep_mask(512, 768, key, p8)
+    assert abs(m.double().mean().item() - (1 - 26 / 256)) < 3e-3
+    assert torch.equal(m, D.keep_mask(512, 768, key, p8))
+    other = D.keep_mask(512, 768, drop.site(1006)[2], p8)
+    assert abs((m ^ other).double().mean().item() - 2 * (26 / 256) * (1 - 26 / 256)) < 5e-3     # independent streams
+    assert D.keep_mask(8, 8, key, 0).all() and D.Drop(0.0, 1).site(1) is None and D.make(0.0) is None
+    # rows and columns are decorrelated: neighbouring rows share no more than chance
+    same = (m[1:] == m[:-1]).double().mean().item()
+    assert abs(same - (1 - 2 * (26 / 256) * (1 - 26 / 256))) < 5e-3
+    assert D.key_bh(key, 0) != D.key_bh(key, 1) and D.mix(0x12345678) == D.mix(0x12345678 + (1 << 32))

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--ragged", action="store_true", help="trailing-PAD masks, valid lengths uniform in [T/2, T]")
+    ap.add_argument("--dropout", type=float, default=0.0, help="dropout rate of the model (train() mode; > 0 runs eagerly)")
     ap.add_argument("--graph", action="store_true", help="Trainer(graph=True): forward + backward replayed from a CUDA graph (no per-kernel breakdown)")
     ap.add_argument("--attn-bwd-impl", type=int, default=0, help="ops.attention_backward impl (0 ldmatrix, 2 first form)")
     args = ap.parse_args()
@@ -45,7 +46,7 @@ def main():
         dist.init_process_group("nccl")
     dev = torch.device("cuda", local)
     torch.manual_seed(0)
-    model = FusionWithEmotionDecoder(dropout=0.0).to(dev)
+    model = FusionWithEmotionDecoder(dropout=args.dropout).to(dev).train()
     trainer = Trainer(model, graph=args.graph)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     B, d, n_e = args.batch, 768, 4
@@ -89,7 +90,7 @@ def main():
                               n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms, dtype="bf16",
                               data="synthetic", loss=info["loss"].item(), grad_norm=info["grad_norm"].item(),
                               config=dict(workload=f"FusionWithEmotionDecoder BCE training step, B={B}/GPU, T_a={args.T_a}, "
-                                                   f"T_t={args.T_t}, d=768, H=8, N_e=4, 2+2 layers, AdamW, clip 5.0, dropout 0",
+                                                   f"T_t={args.T_t}, d=768, H=8, N_e=4, 2+2 layers, AdamW, clip 5.0, dropout {args.dropout}",
                                           parameters=trainer.numel, cuda_graph=bool(args.graph), ragged=bool(args.ragged), exchange="one all-reduce (AVG) of the fp32 gradient arena"),
                               breakdown=breakdown, peak_mem_gb=torch.cuda.max_memory_allocated() / 2**30)))
     if world > 1:
