@@ -1167,6 +1167,407 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   }
 }
 
+
+// =====================================================================================================================
+// attention_fwd4_kernel: the long-key general form (T_q > 128, more than two key steps) with FOUR softmax warpgroups that
+// split every 64-key step of a tile by COLUMNS.
+//
+// What the profile of the form above says (profiles/r02_attention_issue_notes.txt items 7-9): of the ~2 000 cycles a
+// softmax warp spends per 64-key step only ~690 are exponentials; ~850 are the latencies of the synchronising
+// instructions themselves -- mbarrier try_wait (S full), tcgen05.wait::ld, tcgen05.wait::st + fence, syncwarp + mbarrier
+// arrive -- which cost their ~200 cycles each whether or not the data arrived long ago, block the warp, and with ONE
+// softmax warp per scheduler and tile have nothing to overlap with.  More steps in flight per warp do not help (the waits
+// block it); more warps per scheduler do.  Splitting a tile's key STEPS between two warpgroups lost the S look-ahead
+// (item 5).  Here the two warpgroups of a tile work on the SAME step: warpgroup `half` owns keys [32 half, 32 half + 32)
+// of every step, each thread still owns one query row (its TMEM lane), so S stays double-buffered and issued two steps
+// ahead exactly as above, every warp runs the same chain on half the scores, and four warps per scheduler overlap each
+// other's waits.  The price: the row maximum of a step spans both warpgroups -- the two threads of a row exchange their
+// partial maxima through shared memory behind a 64-thread named barrier (one per tile and lane quadrant) before the
+// exponentials, which also orders the P stores (P overlays S columns [0, 32): half 1's share lands on columns half 0 has
+// to have read first).  Row sums are partial per thread and added in the epilogue; each thread scales and stages half of
+// its row's O columns.  640 threads: warp 0 TMA, warps 1 / 2 the MMA issuers of tiles 0 / 1, warp 3 idle, warps 4..19
+// softmax (tile = (w - 4) >> 3, half = ((w - 4) >> 2) & 1, quadrant = w & 3).  TMA producer and issuers are the general
+// non-DEFER code of the kernel above.
+constexpr int A4_THREADS = 640;
+constexpr bool kFwd4Default = false;   // flipped once the form is measured faster on the B200
+
+template <int DH>
+struct Attn4Smem : Attn3Smem<DH> {
+  // caps[2][n_kv*64] f32, flags[2][n_kv] i32 (one copy per TILE, built by its two warpgroups together), xm[2][2][2][128]
+  // f32 (partial row maxima, double-buffered by step parity), xl[2][2][128] f32 (partial row sums)
+  static int dyn_bytes4(int n_kv) {
+    return Attn3Smem<DH>::DYN_OFF + 2 * n_kv * A3_BKV * 4 + 2 * n_kv * 4 + (2 * 2 * 2 * 128 + 2 * 2 * 128) * 4 + 1024;
+  }
+};
+
+template <int DH, bool DROP = false>
+__global__ void __launch_bounds__(A4_THREADS, 1)
+attention_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
+                      const Attn3Params p) {
+  using L = Attn4Smem<DH>;
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t TILE_COLS = 256;   // per query tile: S0 at +0, S1 at +64, O at +128
+  constexpr uint32_t O_COL = 128;
+  constexpr int KS = L::KV_STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_u32);
+  const uint32_t sQ = base + L::Q_OFF, sK = base + L::K_OFF, sV = base + L::V_OFF;
+  const uint32_t bars = base + L::BAR_OFF;
+  const uint32_t b_qfull = bars + 0 * 8, b_qempty = bars + 4 * 8, b_kfull = bars + 8 * 8, b_kempty = bars + 11 * 8;
+  const uint32_t b_vfull = bars + 14 * 8, b_vempty = bars + 17 * 8, b_sfull = bars + 20 * 8, b_pfull = bars + 24 * 8;
+  const uint32_t b_pvdone = bars + 28 * 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + L::TMEM_SLOT_OFF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_kv = p.n_kv;
+  const uint32_t n_items_all = static_cast<uint32_t>(p.n_items);
+  const uint32_t per_cta = (n_items_all + gridDim.x - 1) / gridDim.x;
+  const uint32_t item_first = p.contiguous ? blockIdx.x * per_cta : blockIdx.x;
+  const uint32_t item_stride = p.contiguous ? 1u : gridDim.x;
+  const uint32_t item_last = p.contiguous ? min(item_first + per_cta, n_items_all) : n_items_all;  // exclusive
+  auto steps_of = [&](uint32_t item) -> int {
+    if (p.kv_steps == nullptr) return n_kv;
+    return __ldg(p.kv_steps + item / static_cast<uint32_t>(p.items_per_b));
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_o);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(b_qfull + s * 8, 1);
+      mbar_init(b_qempty + s * 8, 4);   // released by the four half-0 warps of the tile (they issue the O stores)
+      mbar_init(b_sfull + s * 8, 1);
+      mbar_init(b_pvdone + s * 8, 1);
+      mbar_init(b_pfull + s * 8, 8);    // one arrival per softmax warp of the tile (both halves)
+    }
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(b_kfull + s * 8, 1);
+      mbar_init(b_kempty + s * 8, 2);   // one arrival per MMA issuer
+      mbar_init(b_vfull + s * 8, 1);
+      mbar_init(b_vempty + s * 8, 2);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(base + L::TMEM_SLOT_OFF);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (general mode of attention_fwd3_kernel) =====================
+    if (elect_one()) {
+      uint32_t qcnt[2] = {0, 0};
+      uint32_t g = 0;
+      for (uint32_t item = item_first; item < item_last; item += item_stride) {
+        const uint32_t bh = item / static_cast<uint32_t>(p.n_qp);
+        const int qp = static_cast<int>(item - bh * static_cast<uint32_t>(p.n_qp));
+        const int b = static_cast<int>(bh / static_cast<uint32_t>(p.H));
+        const int h = static_cast<int>(bh - static_cast<uint32_t>(b) * static_cast<uint32_t>(p.H));
+        const int q0 = qp * 2 * A3_BQ;
+        for (int t = 0; t < 2; ++t) {
+          if (q0 + t * A3_BQ >= p.Tq) break;
+          const uint32_t qb = qcnt[t] & 1u, qpar = (qcnt[t] >> 1) & 1u;
+          const uint32_t bar = (t * 2 + qb) * 8;
+          mbar_wait(b_qempty + bar, qpar ^ 1);
+          mbar_arrive_expect_tx(b_qfull + bar, L::Q_TILE);
+          for (int c = 0; c < L::QCH; ++c)
+            tma_load_2d(&tm_q, b_qfull + bar, sQ + (t * 2 + qb) * L::Q_TILE + c * L::Q_CHUNK, h * DH + c * 64,
+                        b * p.Tq + q0 + t * A3_BQ);
+          ++qcnt[t];
+        }
+        const int nk = steps_of(item);
+        for (int j = 0; j < nk; ++j, ++g) {
+          const uint32_t s = g % KS, par = (g / KS) & 1u;
+          mbar_wait(b_kempty + s * 8, par ^ 1);
+          mbar_arrive_expect_tx(b_kfull + s * 8, L::K_STAGE);
+          for (int c = 0; c < L::QCH; ++c)
+            tma_load_2d(&tm_k, b_kfull + s * 8, sK + s * L::K_STAGE + c * L::K_CHUNK, h * DH + c * 64,
+                        b * p.Tk + j * A3_BKV);
+          mbar_wait(b_vempty + s * 8, par ^ 1);
+          mbar_arrive_expect_tx(b_vfull + s * 8, L::V_STAGE);
+          for (int c = 0; c < DH / 32; ++c)
+            tma_load_3d(&tm_v, b_vfull + s * 8, sV + s * L::V_STAGE + c * L::V_GROUP, h * DH + c * 32, j * A3_BKV, b);
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers: warp 1 drives query tile 0, warp 2 query tile 1 (general non-DEFER form) =====
+    auto run_issuer = [&](auto tile_c) {
+      constexpr int t = decltype(tile_c)::value;
+      if (tmem_base != 0u) __trap();   // this CTA owns all 512 columns: the base is the constant 0 (uniform descriptors)
+      constexpr uint32_t idesc_s = umma_idesc_bf16(A3_BQ, A3_BKV);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(A3_BQ, DH) | kUmmaBMajorMN;
+      const uint32_t tile_tmem = t * TILE_COLS;
+      const uint64_t k_desc0 = umma_desc_sw128(sK);
+      const uint64_t v_desc0 = umma_desc_mn_sw64(sV, L::V_GROUP);
+      auto tile_active = [&](uint32_t item) {
+        return t == 0 || static_cast<int>(item % static_cast<uint32_t>(p.n_qp)) * 2 * A3_BQ + A3_BQ < p.Tq;
+      };
+      uint32_t s_g = 0, s_item = item_first, qcnt = 0;
+      int s_f = 0;
+      int s_nk = s_item < item_last ? steps_of(s_item) : 0;
+      bool s_act = tile_active(s_item);
+      auto issue_s = [&]() {
+        const uint32_t ks = s_g % KS, kpar = (s_g / KS) & 1u;
+        const uint32_t qslot = t * 2 + (qcnt & 1u);
+        if (s_act && s_f == 0) mbar_wait(b_qfull + qslot * 8, (qcnt >> 1) & 1u);
+        mbar_wait(b_kfull + ks * 8, kpar);
+        if (s_act) {
+          tc_fence_after_sync();
+          const uint64_t q_desc = umma_desc_sw128(sQ + qslot * L::Q_TILE);
+          const uint64_t k_desc = k_desc0 + ((ks * L::K_STAGE) >> 4);
+          const uint32_t d_tmem = tile_tmem + (s_g & 1u) * A3_BKV;
+#pragma unroll
+          for (int st = 0; st < DH / 16; ++st) {
+            umma_bf16(d_tmem, q_desc + (((st >> 2) * L::Q_CHUNK + (st & 3) * 32) >> 4),
+                      k_desc + (((st >> 2) * L::K_CHUNK + (st & 3) * 32) >> 4), idesc_s, st != 0);
+          }
+          umma_commit(b_sfull + (t * 2 + (s_g & 1u)) * 8);
+          umma_commit(b_kempty + ks * 8);
+          if (s_f == s_nk - 1) ++qcnt;
+        } else {
+          mbar_arrive(b_kempty + ks * 8);
+        }
+        ++s_g;
+        if (++s_f == s_nk) {
+          s_f = 0;
+          s_item += item_stride;
+          s_act = s_item < item_last && tile_active(s_item);
+          s_nk = s_item < item_last ? steps_of(s_item) : 0;
+        }
+      };
+      if (s_item < item_last) issue_s();
+      if (s_item < item_last) issue_s();
+      uint32_t pcnt = 0, pv_item = item_first;
+      int pv_f = 0;
+      int pv_nk = pv_item < item_last ? steps_of(pv_item) : 0;
+      bool pv_act = tile_active(pv_item);
+      for (uint32_t g = 0; pv_item < item_last; ++g) {
+        const uint32_t vs = g % KS, vpar = (g / KS) & 1u;
+        mbar_wait(b_vfull + vs * 8, vpar);
+        if (pv_act) {
+          const int rem = p.Tk - pv_f * A3_BKV;  // keys left from this step on (> 0)
+          const uint32_t slot = t * 2 + (pcnt & 1u);
+          mbar_wait(b_pfull + slot * 8, (pcnt >> 1) & 1u);
+          ++pcnt;
+          tc_fence_after_sync();
+          const uint64_t v_desc = v_desc0 + ((vs * L::V_STAGE) >> 4);
+          const uint32_t p_tmem = tile_tmem + (g & 1u) * A3_BKV;
+#pragma unroll
+          for (int st = 0; st < A3_BKV / 16; ++st) {
+            if (st * 16 < rem)
+              umma_bf16_ts(tile_tmem + O_COL, p_tmem + st * 8, v_desc + ((st * 16 * 64) >> 4), idesc_pv, (pv_f | st) != 0);
+          }
+          umma_commit(b_pvdone + slot * 8);
+          umma_commit(b_vempty + vs * 8);
+        } else {
+          mbar_arrive(b_vempty + vs * 8);
+        }
+        if (s_item < item_last) issue_s();  // S(g+2) reuses the S buffer whose P was just consumed
+        if (++pv_f == pv_nk) {
+          pv_f = 0;
+          pv_item += item_stride;
+          pv_act = pv_item < item_last && tile_active(pv_item);
+          pv_nk = pv_item < item_last ? steps_of(pv_item) : 0;
+        }
+      }
+    };
+    if (elect_one()) {
+      if (warp == 1) run_issuer(std::integral_constant<int, 0>{});
+      else run_issuer(std::integral_constant<int, 1>{});
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax: four warpgroups, (tile, half) = (0,0) (0,1) (1,0) (1,1) =====================
+    const int swg = (warp - 4) >> 2;
+    const int tile = swg >> 1, half = swg & 1;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;                       // query row inside the tile = TMEM lane
+    const int tile_tid = threadIdx.x - 128 - tile * 256;    // thread within the tile's two warpgroups
+    float* dyn = reinterpret_cast<float*>(base_ptr + L::DYN_OFF);
+    float* caps = dyn + tile * n_kv * A3_BKV;
+    int* flags = reinterpret_cast<int*>(dyn + 2 * n_kv * A3_BKV) + tile * n_kv;
+    float* xm = dyn + 2 * n_kv * A3_BKV + 2 * n_kv;         // [2][2][2][128]
+    float* xl = xm + 2 * 2 * 2 * 128;                       // [2][2][128]
+    const uint32_t t_tile = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + tile * TILE_COLS;
+    const uint32_t t_o = t_tile + O_COL;
+    const uint32_t pid = 5 + tile * 4 + quad;               // named barrier of the two warps that share this quadrant of the tile
+    const float sc = p.scale_log2;
+    constexpr int OH = DH / 2;                              // O columns this thread rescales / stages
+    uint32_t scnt0 = 0, scnt1 = 0, pv_issued = 0, xstep = 0;
+    uint32_t g = 0;
+    int pending_qslot = -1;
+    auto release_q = [&]() {   // half-0 warps only (they issue the O stores)
+      if (pending_qslot >= 0) {
+        if (lane == 0) {
+          bulk_wait_read<0>();
+          mbar_arrive(b_qempty + pending_qslot * 8);
+        }
+        pending_qslot = -1;
+      }
+    };
+    uint32_t qcnt_w = 0;
+    int cur_b = -1;
+    int nk = 0;
+    for (uint32_t item = item_first; item < item_last; item += item_stride, g += nk) {
+      nk = steps_of(item);
+      const int b = static_cast<int>(item / static_cast<uint32_t>(p.items_per_b));
+      const uint32_t in_b = item - static_cast<uint32_t>(b) * static_cast<uint32_t>(p.items_per_b);
+      const int h = static_cast<int>(in_b / static_cast<uint32_t>(p.n_qp));
+      const int q0 = static_cast<int>(in_b % static_cast<uint32_t>(p.n_qp)) * 2 * A3_BQ + tile * A3_BQ;
+      if (q0 >= p.Tq) continue;   // this tile does not exist for the item
+      [[maybe_unused]] const uint32_t dbase =
+          drop_key_bh(p.drop_key, static_cast<uint32_t>(b * p.H + h)) + static_cast<uint32_t>(q0 + row) * DROP_C_ROW;
+      if (cur_b < 0 || (b != cur_b && p.key_pad != nullptr)) {   // without a mask the caps only depend on Tk
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + tile) : "memory");   // both warpgroups of the tile are past the old caps
+        for (int j = tile_tid; j < n_kv; j += 256) flags[j] = 0;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + tile) : "memory");
+        for (int kk = tile_tid; kk < n_kv * A3_BKV; kk += 256) {
+          bool pad = kk >= p.Tk;
+          if (!pad && p.key_pad != nullptr) pad = p.key_pad[static_cast<int64_t>(b) * p.Tk + kk] != 0;
+          caps[kk] = pad ? -INFINITY : INFINITY;
+          if (pad) flags[kk / A3_BKV] = 1;
+        }
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + tile) : "memory");
+        cur_b = b;
+      }
+      if (half == 0 && nk <= 2) release_q();
+      float m_run = -INFINITY;   // reference maximum of the row, identical in the two threads that share it
+      float l_run = 0.0f;        // this thread's share of the row sum
+      uint32_t v[32];
+      {  // the item's first scores: this warpgroup's 32 columns of the S buffer
+        const uint32_t sbuf0 = g & 1u;
+        mbar_wait(b_sfull + (tile * 2 + sbuf0) * 8, (sbuf0 ? scnt1 : scnt0) & 1u);
+        if (sbuf0) ++scnt1; else ++scnt0;
+        tc_fence_after_sync();
+        tmem_ld32(t_tile + sbuf0 * A3_BKV + half * 32, v);
+      }
+      for (int j = 0; j < nk; ++j) {
+        const uint32_t sbuf = (g + static_cast<uint32_t>(j)) & 1u;
+        const uint32_t t_s = t_tile + sbuf * A3_BKV;
+        const bool masked = flags[j] != 0;           // warp-uniform
+        tmem_ld_wait();
+        if (masked) apply_caps(v, caps + j * A3_BKV + half * 32);
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        max4(m4, v);
+        const float own_max = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;   // sc > 0
+        // ---- the row maximum spans both halves: exchange, and (the same barrier) both halves hold their scores in
+        // registers, so P may overwrite S columns [0, 32)
+        const uint32_t xb = xstep & 1u;
+        ++xstep;
+        xm[((xb * 2 + tile) * 2 + half) * 128 + row] = own_max;
+        asm volatile("bar.sync %0, 64;" ::"r"(pid) : "memory");
+        const float tile_max = fmaxf(own_max, xm[((xb * 2 + tile) * 2 + (half ^ 1)) * 128 + row]);
+        if (j == 0) {
+          m_run = tile_max;
+        } else {
+          const bool need = tile_max > m_run + A3_LAZY_TAU;
+          if (__any_sync(0xffffffffu, need)) {   // the partner warp holds the same rows: it takes the same branch
+            const uint32_t kk = pv_issued - 1u;  // every PV of this tile must have retired (PV(j-2) did before S(j) landed)
+            mbar_wait(b_pvdone + (tile * 2 + (kk & 1u)) * 8, (kk >> 1) & 1u);
+            tc_fence_after_sync();
+            const float alpha = need ? ex2_approx(m_run - tile_max) : 1.0f;
+            if (need) m_run = tile_max;
+            l_run *= alpha;
+#pragma unroll 1
+            for (int c = 0; c < OH / 16; ++c) {   // this thread's half of the row's O columns
+              uint32_t vo[16];
+              tmem_ld16(t_o + half * OH + c * 16, vo);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) vo[i] = __float_as_uint(__uint_as_float(vo[i]) * alpha);
+              tmem_st16(t_o + half * OH + c * 16, vo);
+            }
+          }
+        }
+        const float neg_m = (m_run == -INFINITY) ? 0.0f : -m_run;
+        // ---- p = 2^(s*scale - m) for this thread's 32 keys; bf16 P into columns [16 half, 16 half + 16) of the S buffer
+        float l4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        uint32_t pk[16];
+        {
+          float2 xs[16];
+          scale32(v, sc, neg_m, xs);
+          exp_pack_x(xs, l4, pk);
+        }
+        if constexpr (DROP) drop_pk(pk, dbase, static_cast<uint32_t>(j) * 16u + static_cast<uint32_t>(half) * 8u, p.drop_p8);
+        tmem_st16(t_s + half * 16, pk);
+        l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        // ---- the next step's scores while the P stores drain
+        if (j + 1 < nk) {
+          const uint32_t nbuf = sbuf ^ 1u;
+          mbar_wait(b_sfull + (tile * 2 + nbuf) * 8, (nbuf ? scnt1 : scnt0) & 1u);
+          if (nbuf) ++scnt1; else ++scnt0;
+          tc_fence_after_sync();
+          tmem_ld32(t_tile + nbuf * A3_BKV + half * 32, v);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_pfull + (tile * 2 + (pv_issued & 1u)) * 8);
+        ++pv_issued;
+        if (half == 0 && j == 0 && nk > 2) release_q();
+      }
+      // ---- epilogue: this thread's half of O / l -> bf16, staged in the item's (now dead) Q buffer; the half-0 warp of a
+      // quadrant issues the TMA store of the 32-row box once both halves have written
+      {
+        const uint32_t kk = pv_issued - 1u;
+        mbar_wait(b_pvdone + (tile * 2 + (kk & 1u)) * 8, (kk >> 1) & 1u);
+      }
+      tc_fence_after_sync();
+      xl[(tile * 2 + half) * 128 + row] = l_run;
+      asm volatile("bar.sync %0, 64;" ::"r"(pid) : "memory");
+      const float l_tot = xl[(tile * 2 + 0) * 128 + row] + xl[(tile * 2 + 1) * 128 + row];   // fixed order in both threads
+      const float inv_l = DROP ? (1.0f / l_tot) * p.drop_scale : 1.0f / l_tot;   // l == 0 -> NaN like torch.softmax
+      if (half == 0 && p.lse != nullptr && q0 + row < p.Tq)
+        p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Tq + q0 + row] = (m_run + log2f(l_tot)) * 0.6931471805599453f;
+      const uint32_t qslot = tile * 2 + (qcnt_w & 1u);
+      const uint32_t stage_warp = sQ + qslot * L::Q_TILE + static_cast<uint32_t>(quad) * (32 * DH * 2);
+      const uint32_t stage_row = stage_warp + static_cast<uint32_t>(lane) * (DH * 2) + static_cast<uint32_t>(half) * (OH * 2);
+#pragma unroll
+      for (int c = 0; c < OH / 16; ++c) {
+        uint32_t vo[16];
+        tmem_ld16(t_o + half * OH + c * 16, vo);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g4 = 0; g4 < 2; ++g4) {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + c * 32 + g4 * 16),
+                       "r"(pack_bf16(__uint_as_float(vo[g4 * 8 + 0]) * inv_l, __uint_as_float(vo[g4 * 8 + 1]) * inv_l)),
+                       "r"(pack_bf16(__uint_as_float(vo[g4 * 8 + 2]) * inv_l, __uint_as_float(vo[g4 * 8 + 3]) * inv_l)),
+                       "r"(pack_bf16(__uint_as_float(vo[g4 * 8 + 4]) * inv_l, __uint_as_float(vo[g4 * 8 + 5]) * inv_l)),
+                       "r"(pack_bf16(__uint_as_float(vo[g4 * 8 + 6]) * inv_l, __uint_as_float(vo[g4 * 8 + 7]) * inv_l))
+                       : "memory");
+        }
+      }
+      tc_fence_before_sync();   // O reads retire before the next item's first p_full lets PV overwrite O
+      fence_proxy_async_smem();
+      asm volatile("bar.sync %0, 64;" ::"r"(pid) : "memory");   // both halves of the 32-row box are staged (and xl is read)
+      if (half == 0) {
+        if (lane == 0 && q0 + quad * 32 < p.Tq) {
+          tma_store_3d(&tm_o, stage_warp, h * DH, q0 + quad * 32, b);
+          bulk_commit();
+        }
+        pending_qslot = static_cast<int>(qslot);
+      }
+      ++qcnt_w;
+    }
+    if (half == 0) release_q();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
 template <int DH>
 static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
   using L = Attn3Smem<DH>;
@@ -1240,7 +1641,26 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
     if (p.drop_p8) attention_fwd3_kernel<DH, PAIRED_, DEFER_, true><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p); \
     else attention_fwd3_kernel<DH, PAIRED_, DEFER_, false><<<grid, A3_THREADS, smem, stream>>>(tq, tk, tv, to, p);     \
   } while (0)
-  if (p.paired && defer) HRIEMO_A3_LAUNCH(true, true);
+  // The long-key general form has a second implementation, attention_fwd4_kernel (four column-split softmax warpgroups).
+  // HRIEMO_ATTN_FWD4 = 0 / 1 selects at run time (A/B measurements in one build); default: see kFwd4Default.
+  static const int fwd4_env = [] {
+    const char* e = getenv("HRIEMO_ATTN_FWD4");
+    return e == nullptr ? -1 : atoi(e);
+  }();
+  const bool use_fwd4 = !p.paired && !defer && (fwd4_env < 0 ? kFwd4Default : fwd4_env != 0) &&
+                        Attn4Smem<DH>::dyn_bytes4(n_kv) <= 227 * 1024;
+  if (use_fwd4) {
+    static uint64_t attr4_done = 0;
+    if (device_needs_attr(&attr4_done)) {
+      cudaError_t e = cudaFuncSetAttribute(attention_fwd4_kernel<DH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attention_fwd4_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    const int smem4 = Attn4Smem<DH>::dyn_bytes4(n_kv);
+    if (p.drop_p8) attention_fwd4_kernel<DH, true><<<grid, A4_THREADS, smem4, stream>>>(tq, tk, tv, to, p);
+    else attention_fwd4_kernel<DH, false><<<grid, A4_THREADS, smem4, stream>>>(tq, tk, tv, to, p);
+  } else if (p.paired && defer) HRIEMO_A3_LAUNCH(true, true);
   else if (p.paired) HRIEMO_A3_LAUNCH(true, false);
   else if (defer) HRIEMO_A3_LAUNCH(false, true);
   else HRIEMO_A3_LAUNCH(false, false);
