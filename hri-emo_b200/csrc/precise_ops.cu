@@ -32,7 +32,7 @@ split3_kernel(const float* __restrict__ x, int64_t ldx, __nv_bfloat16* __restric
     const int64_t r = i / (Kp / 2);
     const int c = static_cast<int>(i - r * (Kp / 2)) * 2;
     float v0 = c < K ? x[r * ldx + c] : 0.0f, v1 = c + 1 < K ? x[r * ldx + c + 1] : 0.0f;
-    if (relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+    if (relu) { v0 = v0 < 0.0f ? 0.0f : v0; v1 = v1 < 0.0f ? 0.0f : v1; }   // keeps NaN, as torch.relu does
     const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
     const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
     const __nv_bfloat162 hi = __halves2bfloat162(h0, h1), lo = __halves2bfloat162(l0, l1);

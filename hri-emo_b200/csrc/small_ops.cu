@@ -34,7 +34,7 @@ sgemm_f32_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
       const int k = k0 + lk + i;
       const int64_t am = m0 + lr;
       const float av = (am < M && k < K) ? __ldg(A + am * lda + k) : 0.0f;
-      As[lk + i][lr] = relu_in ? fmaxf(av, 0.0f) : av;
+      As[lk + i][lr] = (relu_in && av < 0.0f) ? 0.0f : av;   // relu that keeps NaN (fmaxf would turn it into 0; torch.relu does not)
       const int wn = n0 + lr;
       Ws[lk + i][lr] = (wn < N && k < K) ? __ldg(W + static_cast<int64_t>(wn) * ldw + k) : 0.0f;
     }
@@ -62,7 +62,7 @@ sgemm_f32_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.0f);
-      if (act == 1) v = fmaxf(v, 0.0f);
+      if (act == 1) v = v < 0.0f ? 0.0f : v;   // NaN stays NaN, as in torch.relu: the gate of a fully padded utterance must come out NaN
       else if (act == 2) v = 1.0f / (1.0f + expf(-v));
       out[m * ldo + n] = v;
     }

@@ -1,0 +1,143 @@
+"""Shapes the fixed-size tests do not visit (B200): every row-width instance of the HBM-bound row kernels, sequence
+lengths shorter than a warp count, and whole models of random geometry against the float64 oracle -- the reference's own
+tests pin shapes only, so odd geometries are where a tile- or ring-indexed kernel would break first."""
+import math
+
+import pytest
+import torch
+
+import hriemo_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+@pytest.mark.parametrize("d", [64, 264, 512, 1024, 1536, 2048])     # NV = 1, 2, 2, 4, 8, 8 instances
+@pytest.mark.parametrize("T", [3, 41])
+def test_gate_pooling_every_row_width_with_and_without_pending_layernorm(d, T):
+    """ln_masked_mean (warp-private cp.async ring): pooled = masked_mean_t(LN(LN'(x))) with LN' pending (statistics given,
+    or recomputed per row) or absent, for every template instance and for T below the eight rows a CTA handles at once."""
+    from hriemo import ops
+
+    B = 5
+    x = _rand((B * T, d), d + T, dtype=torch.bfloat16)
+    g1, b1 = _rand((d,), 1) * 0.2 + 1.0, _rand((d,), 2) * 0.2
+    g2, b2 = _rand((d,), 3) * 0.2 + 1.0, _rand((d,), 4) * 0.2
+    lens = torch.randint(1, T + 1, (B,), generator=torch.Generator().manual_seed(d))
+    pad = (torch.arange(T)[None, :] >= lens[:, None]).to(DEV)
+    pad[1] = True                                                      # an utterance without a valid row pools to beta-free 0
+    valid = (~pad).double()
+    xd = x.double().view(B, T, d)
+
+    def pooled_ref(y):
+        return (y * valid[..., None]).sum(1) / valid.sum(1, keepdim=True).clamp(min=1.0)
+
+    ln = lambda y, g, b: torch.nn.functional.layer_norm(y, (d,), g.double(), b.double(), 1e-5)
+    # no pending LayerNorm
+    got = ops.ln_masked_mean(x, g2, b2, pad, B, T)
+    assert (got.double() - pooled_ref(ln(xd, g2, b2))).abs().max().item() <= 2e-5
+    # pending LayerNorm, statistics recomputed per row
+    y1 = ln(xd, g1, b1)
+    got = ops.ln_masked_mean(x, g2, b2, pad, B, T, pre_ln=(g1, b1))
+    assert (got.double() - pooled_ref(ln(y1, g2, b2))).abs().max().item() <= 2e-5
+    # pending LayerNorm with the producer's statistics
+    mean = xd.mean(-1)
+    rstd = 1.0 / torch.sqrt(xd.var(-1, unbiased=False) + 1e-5)
+    stats = torch.stack([mean, rstd], dim=-1).view(B * T, 2).float().contiguous()
+    got = ops.ln_masked_mean(x, g2, b2, pad, B, T, pre_ln=(g1, b1, stats))
+    assert (got.double() - pooled_ref(ln(y1, g2, b2))).abs().max().item() <= 2e-5
+    # plain masked mean (models/beta_gate_tacfn.py:6-24)
+    got = ops.ln_masked_mean(x, None, None, pad, B, T, apply_ln=False)
+    assert (got.double() - pooled_ref(xd)).abs().max().item() <= 1e-5
+    assert got[1].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("rows,d", [(1, 64), (7, 264), (33, 1024), (9, 776)])
+def test_layernorm_backward_small_and_wide_rows(rows, d):
+    from hriemo import ops
+
+    x = _rand((rows, d), rows + d, dtype=torch.bfloat16)
+    dy = _rand((rows, d), rows + d + 1, dtype=torch.bfloat16)
+    g = _rand((d,), 5) * 0.2 + 1.0
+    xr = x.double().requires_grad_(True)
+    gr = g.double().requires_grad_(True)
+    br = torch.zeros(d, dtype=torch.float64, device=DEV, requires_grad=True)
+    torch.nn.functional.layer_norm(xr, (d,), gr, br, 1e-5).backward(dy.double())
+    dx, dg, db = ops.layernorm_backward(x, dy, g)
+    assert (dx.double() - xr.grad).abs().max().item() <= 2e-2 * max(1.0, xr.grad.abs().max().item())
+    assert (dg.double() - gr.grad).abs().max().item() <= 1e-3 * max(1.0, gr.grad.abs().max().item())
+    assert (db.double() - br.grad).abs().max().item() <= 1e-3 * max(1.0, br.grad.abs().max().item())
+    if d == 64:   # the documented limit of this kernel comes back as an error, not as a wrong answer
+        from hriemo import lib as L
+
+        with pytest.raises(L.HriemoError, match="<= 1024"):
+            ops.layernorm_backward(_rand((4, 2048), 1, dtype=torch.bfloat16), _rand((4, 2048), 2, dtype=torch.bfloat16), _rand((2048,), 3))
+
+
+@pytest.mark.parametrize("B,H,Nq,Tk,dh", [(3, 1, 1, 1, 32), (2, 3, 8, 127, 64), (4, 2, 5, 50, 96), (2, 2, 3, 129, 128), (1, 8, 9, 64, 96)])
+def test_decoder_attention_every_path(B, H, Nq, Tk, dh):
+    """The staged kernel (N_q <= 8, T_k <= 128) and the general one (anything else) against torch, ragged masks."""
+    from hriemo import ops
+
+    d = H * dh
+    q = _rand((B * Nq, d), 11, dtype=torch.bfloat16)
+    kv = _rand((B * Tk, 2 * d), 12, dtype=torch.bfloat16)
+    lens = torch.randint(1, Tk + 1, (B,), generator=torch.Generator().manual_seed(Tk))
+    pad = (torch.arange(Tk)[None, :] >= lens[:, None]).to(DEV)
+    out, _ = ops.small_attention(q, kv[:, :d], kv[:, d:], pad, B, H, Nq, Tk, dh)
+    qh = q.double().view(B, Nq, H, dh).transpose(1, 2)
+    kh = kv[:, :d].double().view(B, Tk, H, dh).transpose(1, 2)
+    vh = kv[:, d:].double().view(B, Tk, H, dh).transpose(1, 2)
+    s = (qh @ kh.transpose(-1, -2) / math.sqrt(dh)).masked_fill(pad[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B * Nq, d)
+    assert (out.double() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+
+
+GEOMETRIES = [
+    # d, H, beta_hidden, N_e, L_f, L_d, B, T_a, T_t
+    (128, 4, 32, 1, 1, 1, 3, 9, 9),          # head dim 32, one query, equal lengths
+    (192, 2, 64, 8, 2, 1, 5, 131, 17),       # head dim 96, eight queries, a second 128-row tile with 3 rows
+    (256, 4, 128, 6, 1, 3, 4, 300, 128),     # MOSEI-like backbone, three decoder layers
+    (512, 4, 64, 3, 3, 2, 2, 70, 70),        # head dim 128, three encoder layers
+    (256, 2, 32, 4, 2, 2, 6, 1, 1),          # utterance-level inputs ([B, 1, d])
+    (192, 2, 48, 5, 2, 2, 3, 257, 65),       # lengths one past a tile boundary
+]
+
+
+@pytest.mark.parametrize("d,H,bh,Ne,Lf,Ld,B,T_a,T_t", GEOMETRIES)
+def test_models_of_random_geometry_against_the_oracle(d, H, bh, Ne, Lf, Ld, B, T_a, T_t):
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    torch.manual_seed(d + T_a)
+    m = FusionWithEmotionDecoder(d_model=d, n_heads=H, beta_hidden=bh, num_emotions=Ne, num_layers_fusion=Lf,
+                                 num_layers_decoder=Ld).eval()
+    g = torch.Generator().manual_seed(T_a * 7 + T_t)
+    h_a, h_t = torch.randn(B, T_a, d, generator=g), torch.randn(B, T_t, d, generator=g)
+    m_a = m_t = None
+    if T_a > 1:
+        m_a, m_t = O.ragged_masks(B, T_a, g), O.ragged_masks(B, T_t, g)
+        m_t[B - 1] = True                         # every text key of the last utterance is PAD: NaN, like the reference
+    sd = O.cast_state(m.state_dict(), torch.float64)
+    lo_o, be_o, z_o = O.fusion_with_emotion_decoder(sd, h_a.double(), h_t.double(), m_a, m_t, n_heads=H)
+    m = m.to(DEV)
+    dev = lambda x: None if x is None else x.to(DEV)
+    lo, be, z = m(dev(h_a), dev(h_t), dev(m_a), dev(m_t))
+    lo, be, z = lo.cpu(), be.cpu(), z.cpu()
+    assert torch.equal(torch.isnan(lo), torch.isnan(lo_o)), "NaN pattern differs from the reference's"
+    ok = ~torch.isnan(lo_o)
+    assert (lo[ok] - lo_o[ok]).abs().max().item() <= 1e-2
+    okb = ~torch.isnan(be_o)
+    assert torch.equal(torch.isnan(be), torch.isnan(be_o)) and (be[okb] - be_o[okb]).abs().max().item() <= 1e-4
+    okz = ~torch.isnan(z_o)
+    assert (z[okz] - z_o[okz]).abs().max().item() <= 6e-2
+    # and the tf32-class mode on the same geometry
+    from hriemo import precise
+
+    with precise.mode("tf32x3"):
+        lo3 = m(dev(h_a), dev(h_t), dev(m_a), dev(m_t))[0].cpu()
+    assert torch.equal(torch.isnan(lo3), torch.isnan(lo_o)) and (lo3[ok] - lo_o[ok]).abs().max().item() <= 1e-4
