@@ -227,6 +227,15 @@ def forward_bucketed(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Option
 # host staging
 # --------------------------------------------------------------------------- #
 _STAGING = {}   # configuration -> staging buffers + events, reused across calls
+# Pinned bf16 staging sets the converting worker rotates through.  With two, the third conversion of a call waited
+# ~20 ms for the copy of the first to be sent (the copy engine was busy with fp32 slabs in between); three keep the
+# host cores converting back to back (tools/e2e_pack_probe.py).
+HOST_SETS = 3
+# TwoEndedPlan.claim_back: the host side takes another slab while at least PLAN_MIN_LEFT are unclaimed and the copy side
+# has (unclaimed - 1 + PLAN_RESERVE) decisions' worth of other work for the time of one conversion (PLAN_RESERVE: copies
+# already queued in the engine when the decision is made).
+PLAN_MIN_LEFT = 2
+PLAN_RESERVE = 0.0
 # what the host-staged entry points moved, accumulated over calls (bench.py reads and resets it): bytes copied
 # host -> device (counted from the tensors copied), slabs, and how many of them the host cores pre-cast
 STATS = dict(h2d_bytes=0, slabs=0, host_cast_slabs=0, calls=0)
@@ -273,13 +282,13 @@ def _staging(dev, dtype_a, dtype_t, host_dtype, elems_a: int, elems_t: int, rows
         st["direct"] = [mk(dtype_a, dtype_t), mk(dtype_a, dtype_t)]
     if host_sets:
         # slabs prepared by the host cores (bf16 pack of a padded batch, or rows of a shard): pinned staging
-        # on the host (ping-pong) and landing buffers on the device (ping-pong, released when the slab's
-        # forward is done)
+        # on the host (HOST_SETS of them in rotation) and landing buffers on the device (ping-pong, released
+        # when the slab's forward is done)
         def mk_host():
             return dict(a=torch.empty((ea,), dtype=host_dtype).pin_memory(),
                         t=torch.empty((et,), dtype=host_dtype).pin_memory(),
                         sent=torch.cuda.Event())
-        st["host16"] = [mk_host(), mk_host()]
+        st["host16"] = [mk_host() for _ in range(HOST_SETS)]
         st["dev16"] = [mk(host_dtype, host_dtype), mk(host_dtype, host_dtype)]
     _STAGING[key] = st
     return st
@@ -343,11 +352,11 @@ def _run_pipeline(model, dev, B: int, slabs: List[_Slab], d_a: int, d_t: int, dt
     def prepare():
         try:
             for k, i in enumerate(host_ids):
-                hb = st["host16"][k % 2]
-                if k >= 2:
-                    # this host buffer last carried host slab k-2: its copy must have been ENQUEUED (the event
-                    # below is re-recorded per use) before waiting for it to have been READ
-                    enqueued[host_ids[k - 2]].wait()
+                hb = st["host16"][k % HOST_SETS]
+                if k >= HOST_SETS:
+                    # this host buffer last carried host slab k-HOST_SETS: its copy must have been ENQUEUED (the
+                    # event below is re-recorded per use) before waiting for it to have been READ
+                    enqueued[host_ids[k - HOST_SETS]].wait()
                     if failure:
                         return
                 hb["sent"].synchronize()          # the copy that last read this host buffer is done
@@ -372,7 +381,7 @@ def _run_pipeline(model, dev, B: int, slabs: List[_Slab], d_a: int, d_t: int, dt
         if s.host_cast:
             k = n_host[0]
             n_host[0] += 1
-            hb, buf = st["host16"][k % 2], st["dev16"][k % 2]
+            hb, buf = st["host16"][k % HOST_SETS], st["dev16"][k % 2]
             ready[i].wait()
             if failure:
                 raise failure[0]
@@ -502,7 +511,7 @@ class TwoEndedPlan:
     during one conversion (both rates measured as the plan runs), so the batch does not end waiting for the host.
     Thread-safe; no CUDA in here (tests/test_sharding_cpu.py drives it with plain threads)."""
 
-    def __init__(self, n_slabs: int):
+    def __init__(self, n_slabs: int, t_pack: Optional[float] = None, t_step: Optional[float] = None):
         import threading
         from collections import deque
         self.cv = threading.Condition()
@@ -510,20 +519,24 @@ class TwoEndedPlan:
         self.ready = deque()         # (slab, k) converted by the host side, not yet sent
         self.busy = False            # the host side holds a claimed slab it has not published yet
         self.failure = None
-        self.t_pack = None           # seconds per conversion (last)
-        self.t_step = None           # seconds between decisions of the copy side (running mean)
+        self.t_pack = t_pack         # seconds per conversion (last; a stream of calls hands its rates on)
+        self.t_step = t_step         # seconds between PACED decisions of the copy side (running mean)
         self._last = None
 
     def claim_back(self):
         """-> slab index for the host side, or None when it should stop."""
-        import math
         with self.cv:
             left = self.back - self.front
             if self.t_pack is None or self.t_step is None:
-                guard = 2
+                ok = left > 2
             else:
-                guard = max(1, math.ceil(self.t_pack / max(self.t_step, 1e-4)))
-            if left <= guard or self.failure is not None:
+                # worth it while the copy side has enough OTHER slabs to send for (most of) the time one conversion
+                # takes: the slab then crosses PCIe at half the bytes and the engine never waited for it.  (The
+                # earlier rule, left > ceil(t_pack / t_step), stopped one slab early when the two rates are close --
+                # 16 host threads convert a slab in 17 ms while an fp32 slab takes the engine 16 ms -- and left the
+                # copy engine the bound: 1.8 of 8 slabs pre-cast, 6.3 GB per step.)
+                ok = left >= PLAN_MIN_LEFT and (left - 1 + PLAN_RESERVE) * self.t_step >= 0.75 * self.t_pack
+            if not ok or self.failure is not None:
                 return None
             self.back -= 1
             self.busy = True
@@ -543,9 +556,13 @@ class TwoEndedPlan:
             self.busy = False
             self.cv.notify_all()
 
-    def next(self):
+    def next(self, paced: bool = True):
         """-> (slab, k) for the copy side: k >= 0 = the k-th slab the host side converted, k = -1 = send it as it
-        is; None when every slab has been handed out.  Blocks while the host side still holds a slab."""
+        is; None when every slab has been handed out.  Blocks while the host side still holds a slab.
+        paced=False: the caller did not wait for the copy engine before this decision (the first two of a call, which
+        only fill its queue) -- the interval in front of it says nothing about the engine's rate and is not measured.
+        (Measured, it was: 0.2 ms between the first two decisions made every later call of a stream stop converting
+        after one slab.)"""
         import time
         with self.cv:
             while True:
@@ -562,10 +579,10 @@ class TwoEndedPlan:
                     return None
                 self.cv.wait(0.05)
             now = time.perf_counter()
-            if self._last is not None:
+            if paced and self._last is not None:
                 dt = now - self._last
                 self.t_step = dt if self.t_step is None else 0.5 * (self.t_step + dt)
-            self._last = now
+            self._last = now if paced else None
             return item
 
 
@@ -596,7 +613,8 @@ def _run_dense_dynamic(model, dev, h_a, h_t, mask_a, mask_t, slab: int, out_devi
                   True, True, mask_a is not None, mask_t is not None)
     main = torch.cuda.current_stream(dev)
     copy = st["copy"]
-    plan = TwoEndedPlan(n_sl)
+    rates = st.setdefault("rates", {})     # conversion / copy-side rates of the previous call on these staging sets
+    plan = TwoEndedPlan(n_sl, rates.get((n_sl, "pack")), rates.get((n_sl, "step")))
     host_enq = [threading.Event() for _ in range(n_sl)]   # k-th host-prepared slab: its copy has been enqueued
 
     def prepare():
@@ -606,9 +624,9 @@ def _run_dense_dynamic(model, dev, h_a, h_t, mask_a, mask_t, slab: int, out_devi
                 i = plan.claim_back()
                 if i is None:
                     break
-                hb = st["host16"][k % 2]
-                if k >= 2:
-                    host_enq[k - 2].wait()        # the copy that last read this host set has been ENQUEUED ...
+                hb = st["host16"][k % HOST_SETS]
+                if k >= HOST_SETS:
+                    host_enq[k - HOST_SETS].wait()   # the copy that last read this host set has been ENQUEUED ...
                     if plan.failure is not None:
                         break
                 hb["sent"].synchronize()          # ... and is done
@@ -630,9 +648,10 @@ def _run_dense_dynamic(model, dev, h_a, h_t, mask_a, mask_t, slab: int, out_devi
     def next_stage():
         """-> (slab index, device set, host-converted?) of the next slab to compute, its copies enqueued; None when
         every slab is out."""
-        if len(copied_events) >= 2:
+        paced = len(copied_events) >= 2
+        if paced:
             copied_events[-2].synchronize()       # pace the decisions by the copy engine: two copies queued at most
-        item = plan.next()
+        item = plan.next(paced)
         if item is None:
             return None
         i, k = item
@@ -640,7 +659,7 @@ def _run_dense_dynamic(model, dev, h_a, h_t, mask_a, mask_t, slab: int, out_devi
         n = hi - lo
         na, nt = n * T_a, n * T_t
         if k >= 0:
-            hb, buf = st["host16"][k % 2], st["dev16"][n_host[0] % 2]
+            hb, buf = st["host16"][k % HOST_SETS], st["dev16"][n_host[0] % 2]
             n_host[0] += 1
             src_a, src_t = hb["a"][: na * d_a], hb["t"][: nt * d_t]
         else:
@@ -730,6 +749,7 @@ def _run_dense_dynamic(model, dev, h_a, h_t, mask_a, mask_t, slab: int, out_devi
                 pending.append(nxt)
         worker.join()
         STATS["calls"] += 1
+        rates[(n_sl, "pack")], rates[(n_sl, "step")] = plan.t_pack, plan.t_step
     except BaseException as e:
         plan.host_done(e)
         for ev in host_enq:

@@ -210,6 +210,29 @@ def test_two_ended_plan_hands_every_slab_out_once(n_slabs, t_copy, t_pack):
         assert len(packed) <= 2                     # a slow host only what it can finish in time
 
 
+def test_two_ended_plan_ignores_unpaced_decisions_and_keeps_its_rates():
+    """The first two decisions of a call only fill the copy queue (0.2 ms apart): measured as the copy side's rate they
+    made the host side stop after one slab on every later call of a stream.  Unpaced intervals are not measured, and a
+    plan can start from the rates of the previous call."""
+    from hriemo import pipeline
+
+    plan = pipeline.TwoEndedPlan(8)
+    assert plan.claim_back() == 7
+    assert plan.next(paced=False) == (0, -1) and plan.next(paced=False) == (1, -1)
+    assert plan.t_step is None
+    plan.publish(7, 0, 0.017)
+    assert plan.claim_back() == 6                    # rates unknown: keeps going while more than two are left
+    assert plan.next(paced=True) == (7, 0) and plan.t_step is None   # the interval in front of the first paced one: no
+    import time
+    time.sleep(0.01)
+    assert plan.next(paced=True) == (2, -1) and plan.t_step >= 0.01
+
+    plan = pipeline.TwoEndedPlan(8, t_pack=0.017, t_step=0.012)
+    assert [plan.claim_back() for _ in range(3)] == [7, 6, 5]
+    slow = pipeline.TwoEndedPlan(8, t_pack=0.2, t_step=0.012)      # a slow host (2 threads): nothing is worth converting
+    assert slow.claim_back() is None
+
+
 def test_two_ended_plan_surfaces_a_host_failure():
     from hriemo import pipeline
 
