@@ -633,6 +633,7 @@ def main():
         sync_all()
         ops.PROFILE = []
         ops.PROFILE_BYTES = []
+        ops.PROFILE_ATTN = []
         n0 = lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         clk.mark_start()
@@ -645,6 +646,7 @@ def main():
     launches = lib.launch_count() - n0
     prof, ops.PROFILE = ops.PROFILE, None
     prof_bytes, ops.PROFILE_BYTES = ops.PROFILE_BYTES, None
+    prof_attn, ops.PROFILE_ATTN = ops.PROFILE_ATTN, None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -687,6 +689,28 @@ def main():
                           "mha_incl_projections": {"achieved": mha_tf, "frac": mha_tf / peaks["tf_sust"], "unit": "TFLOP/s",
                                                    "launches": a_n + p_n, "share_of_step": (a_ms + p_ms) / ms_total,
                                                    "definition": "SURVEY 8(d): (in-proj + QK^T + PV + out-proj FLOPs) / their kernel time"}}
+    # each attention shape against ITS roofline: the time the launch would take at the sustained tensor peak and at the
+    # measured HBM bandwidth, whichever is larger (the cross shapes of a layer move 3.5 GB for 0.2 TFLOP: HBM work)
+    by_shape, ideal_ms = {}, 0.0
+    for (tq, tk, fl, by, a, b) in prof_attn or []:
+        r = by_shape.setdefault((tq, tk), dict(Tq=tq, Tk=tk, launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        r["launches"] += 1
+        r["ms"] += a.elapsed_time(b)
+        r["flops"] += fl
+        r["bytes"] += by
+    shapes = []
+    for r in by_shape.values():
+        t_tensor, t_hbm = r["flops"] / (peaks["tf_sust"] * 1e12) * 1e3, r["bytes"] / (peaks["hbm"] * 1e9) * 1e3
+        ideal_ms += max(t_tensor, t_hbm)
+        shapes.append({"Tq": r["Tq"], "Tk": r["Tk"], "launches": r["launches"], "avg_launch_ms": r["ms"] / r["launches"],
+                       "tflops": r["flops"] / (r["ms"] * 1e-3) / 1e12, "algorithmic_gbs": r["bytes"] / (r["ms"] * 1e-3) / 1e9,
+                       "bound": "tensor" if t_tensor >= t_hbm else "hbm",
+                       "frac_of_its_roofline": max(t_tensor, t_hbm) / r["ms"]})
+    if shapes:
+        attention_roofline["by_shape"] = sorted(shapes, key=lambda x: -x["avg_launch_ms"] * x["launches"])
+        attention_roofline["frac_of_shape_rooflines"] = ideal_ms / a_ms
+        attention_roofline["by_shape_note"] = ("algorithmic bytes = Q + K + V + O in bf16; frac_of_its_roofline = max(FLOPs / sustained "
+                                               "tensor peak, bytes / measured HBM bandwidth) / measured time")
     fpu = (flops_per_utt(T_a, T_t, d=256, n_e=6, h_beta=128, d_a=74, d_t=300) if mosei else flops_per_utt(T_a, T_t))
     path_tf = fpu * value / world / 1e12
 

@@ -1568,6 +1568,499 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   }
 }
 
+
+// =====================================================================================================================
+// attention_fwd5_kernel: the long-key general form with the O / l epilogue on its OWN warpgroup.
+//
+// What the warp-state samples of the form at the top say (profiles/r02_ncu_attention_v16_summary.txt): a softmax warp
+// spends 22 % of its time per work item NOT producing probabilities -- 6.5 % waiting for the item's last PV, 11 % scaling
+// O by 1 / l, packing it and staging it for the TMA store (with 4-way bank conflicts), 4.5 % setting up the next item --
+// and for all of that time its query tile issues no tensor work beyond the two S tiles of the look-ahead.  Here the
+// softmax warpgroup of a tile ends an item by handing its row sums (l, m) to a fourth warpgroup through shared memory
+// and goes straight on to the next item's first scores (already in tensor memory); the epilogue warpgroup waits for the
+// last PV, pulls O into registers, tells the tile's MMA issuer that O may be overwritten (o_free: the next item's first
+// PV does not accumulate), and only then scales / packs / stages / stores.  By the time the next item's first P is
+// handed over (a whole softmax step) O has long been read.
+//
+// 512 threads = 4 warpgroups (register budget moved between them with setmaxnreg: 56 / 168 / 168 / 120 per thread):
+//   warps 0..3   TMA producer, MMA issuer of tile 0, MMA issuer of tile 1, idle
+//   warps 4..7   softmax of query tile 0 \ the v4 loop of attention_fwd3_kernel, one query row per thread
+//   warps 8..11  softmax of query tile 1 /
+//   warps 12..15 epilogues of both tiles, one query row per thread (TMEM lane quadrant = warp & 3)
+// TMA producer and issuers are the general non-DEFER code of attention_fwd3_kernel.
+//
+// Measured (tools/attn_sweep.py, same build, same box, T_q = T_k = T, dh = 96): correct (the attention and dropout tests pass
+// with HRIEMO_ATTN_FWD5=1, bit-identical to the shipped form) and 2 - 7 % FASTER for short items (T = 200 .. 384, i.e. up to
+// six key steps: 300 x 300 0.96 - 1.00 -> 0.92 - 0.94 ms at B = 1408), equal at T = 448, 3 - 7 % SLOWER from T = 500 up
+// (500 x 500 0.510 - 0.518 -> 0.524 - 0.539 ms): the per-item overhead is gone, but the per-step loop of the softmax warps
+// is slower with four more warps on their schedulers (handing (l, m) over through a named barrier instead of an mbarrier
+// the epilogue warps poll changed nothing measurable).  Not the default; kept behind HRIEMO_ATTN_FWD5=1.
+constexpr int A5_THREADS = 512;
+constexpr bool kFwd5Default = false;   // flipped once the form is measured faster on the B200
+
+template <int DH>
+struct Attn5Smem : Attn3Smem<DH> {
+  // behind the barriers of the base layout: epi_full[2] epi_empty[2] o_free[2] (64 bytes reserved), then caps[2][n_kv*64]
+  // f32, flags[2][n_kv] i32, xl[2][128] f32 (row sums), xm[2][128] f32 (reference maxima, log2 units)
+  static constexpr int BAR5_OFF = Attn3Smem<DH>::DYN_OFF;
+  static constexpr int DYN5_OFF = BAR5_OFF + 64;
+  static int dyn_bytes5(int n_kv) { return DYN5_OFF + 2 * n_kv * A3_BKV * 4 + 2 * n_kv * 4 + 2 * 2 * 128 * 4 + 1024; }
+};
+
+template <int DH, bool DROP = false>
+__global__ void __launch_bounds__(A5_THREADS, 1)
+attention_fwd5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
+                      const Attn3Params p) {
+  using L = Attn5Smem<DH>;
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t TILE_COLS = 256;   // per query tile: S0 at +0, S1 at +64, O at +128
+  constexpr uint32_t O_COL = 128;
+  constexpr int KS = L::KV_STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_u32);
+  const uint32_t sQ = base + L::Q_OFF, sK = base + L::K_OFF, sV = base + L::V_OFF;
+  const uint32_t bars = base + L::BAR_OFF;
+  const uint32_t b_qfull = bars + 0 * 8, b_qempty = bars + 4 * 8, b_kfull = bars + 8 * 8, b_kempty = bars + 11 * 8;
+  const uint32_t b_vfull = bars + 14 * 8, b_vempty = bars + 17 * 8, b_sfull = bars + 20 * 8, b_pfull = bars + 24 * 8;
+  const uint32_t b_pvdone = bars + 28 * 8;
+  const uint32_t b_epifull = base + L::BAR5_OFF;          // [tile] the item's (l, m) are in shared memory
+  const uint32_t b_epiempty = base + L::BAR5_OFF + 16;    // [tile] ... and have been read
+  const uint32_t b_ofree = base + L::BAR5_OFF + 32;       // [tile] the item's O is in the epilogue warps' registers
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + L::TMEM_SLOT_OFF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_kv = p.n_kv;
+  const uint32_t n_items_all = static_cast<uint32_t>(p.n_items);
+  const uint32_t per_cta = (n_items_all + gridDim.x - 1) / gridDim.x;
+  const uint32_t item_first = p.contiguous ? blockIdx.x * per_cta : blockIdx.x;
+  const uint32_t item_stride = p.contiguous ? 1u : gridDim.x;
+  const uint32_t item_last = p.contiguous ? min(item_first + per_cta, n_items_all) : n_items_all;  // exclusive
+  auto steps_of = [&](uint32_t item) -> int {
+    if (p.kv_steps == nullptr) return n_kv;
+    return __ldg(p.kv_steps + item / static_cast<uint32_t>(p.items_per_b));
+  };
+  float* dyn = reinterpret_cast<float*>(base_ptr + L::DYN5_OFF);
+  float* xl = dyn + 2 * n_kv * A3_BKV + 2 * n_kv;   // [2][128]
+  float* xm = xl + 2 * 128;                         // [2][128]
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_o);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(b_qfull + s * 8, 1);
+      mbar_init(b_qempty + s * 8, 4);   // released by the four epilogue warps (each stores its 32 rows)
+      mbar_init(b_sfull + s * 8, 1);
+      mbar_init(b_pvdone + s * 8, 1);
+      mbar_init(b_pfull + s * 8, 4);    // one arrival per softmax warp of the tile
+    }
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(b_kfull + s * 8, 1);
+      mbar_init(b_kempty + s * 8, 2);   // one arrival per MMA issuer
+      mbar_init(b_vfull + s * 8, 1);
+      mbar_init(b_vempty + s * 8, 2);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(b_epifull + s * 8, 4);   // one arrival per softmax warp of the tile
+      mbar_init(b_epiempty + s * 8, 4);  // one arrival per epilogue warp
+      mbar_init(b_ofree + s * 8, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(base + L::TMEM_SLOT_OFF);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int wgrp = warp >> 2;
+
+  if (wgrp == 0) {
+    reg_dealloc<56>();
+    if (warp == 0) {
+      // ===================== TMA producer (general mode of attention_fwd3_kernel) =====================
+      if (elect_one()) {
+        uint32_t qcnt[2] = {0, 0};
+        uint32_t g = 0;
+        for (uint32_t item = item_first; item < item_last; item += item_stride) {
+          const uint32_t bh = item / static_cast<uint32_t>(p.n_qp);
+          const int qp = static_cast<int>(item - bh * static_cast<uint32_t>(p.n_qp));
+          const int b = static_cast<int>(bh / static_cast<uint32_t>(p.H));
+          const int h = static_cast<int>(bh - static_cast<uint32_t>(b) * static_cast<uint32_t>(p.H));
+          const int q0 = qp * 2 * A3_BQ;
+          for (int t = 0; t < 2; ++t) {
+            if (q0 + t * A3_BQ >= p.Tq) break;
+            const uint32_t qb = qcnt[t] & 1u, qpar = (qcnt[t] >> 1) & 1u;
+            const uint32_t bar = (t * 2 + qb) * 8;
+            mbar_wait(b_qempty + bar, qpar ^ 1);
+            mbar_arrive_expect_tx(b_qfull + bar, L::Q_TILE);
+            for (int c = 0; c < L::QCH; ++c)
+              tma_load_2d(&tm_q, b_qfull + bar, sQ + (t * 2 + qb) * L::Q_TILE + c * L::Q_CHUNK, h * DH + c * 64,
+                          b * p.Tq + q0 + t * A3_BQ);
+            ++qcnt[t];
+          }
+          const int nk = steps_of(item);
+          for (int j = 0; j < nk; ++j, ++g) {
+            const uint32_t s = g % KS, par = (g / KS) & 1u;
+            mbar_wait(b_kempty + s * 8, par ^ 1);
+            mbar_arrive_expect_tx(b_kfull + s * 8, L::K_STAGE);
+            for (int c = 0; c < L::QCH; ++c)
+              tma_load_2d(&tm_k, b_kfull + s * 8, sK + s * L::K_STAGE + c * L::K_CHUNK, h * DH + c * 64,
+                          b * p.Tk + j * A3_BKV);
+            mbar_wait(b_vempty + s * 8, par ^ 1);
+            mbar_arrive_expect_tx(b_vfull + s * 8, L::V_STAGE);
+            for (int c = 0; c < DH / 32; ++c)
+              tma_load_3d(&tm_v, b_vfull + s * 8, sV + s * L::V_STAGE + c * L::V_GROUP, h * DH + c * 32, j * A3_BKV, b);
+          }
+        }
+      }
+    } else if (warp == 1 || warp == 2) {
+      // ===================== MMA issuers: warp 1 drives query tile 0, warp 2 query tile 1 (general non-DEFER form) =====
+      auto run_issuer = [&](auto tile_c) {
+        constexpr int t = decltype(tile_c)::value;
+        if (tmem_base != 0u) __trap();   // this CTA owns all 512 columns: the base is the constant 0 (uniform descriptors)
+        constexpr uint32_t idesc_s = umma_idesc_bf16(A3_BQ, A3_BKV);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(A3_BQ, DH) | kUmmaBMajorMN;
+        const uint32_t tile_tmem = t * TILE_COLS;
+        const uint64_t k_desc0 = umma_desc_sw128(sK);
+        const uint64_t v_desc0 = umma_desc_mn_sw64(sV, L::V_GROUP);
+        auto tile_active = [&](uint32_t item) {
+          return t == 0 || static_cast<int>(item % static_cast<uint32_t>(p.n_qp)) * 2 * A3_BQ + A3_BQ < p.Tq;
+        };
+        uint32_t s_g = 0, s_item = item_first, qcnt = 0;
+        int s_f = 0;
+        int s_nk = s_item < item_last ? steps_of(s_item) : 0;
+        bool s_act = tile_active(s_item);
+        auto issue_s = [&]() {
+          const uint32_t ks = s_g % KS, kpar = (s_g / KS) & 1u;
+          const uint32_t qslot = t * 2 + (qcnt & 1u);
+          if (s_act && s_f == 0) mbar_wait(b_qfull + qslot * 8, (qcnt >> 1) & 1u);
+          mbar_wait(b_kfull + ks * 8, kpar);
+          if (s_act) {
+            tc_fence_after_sync();
+            const uint64_t q_desc = umma_desc_sw128(sQ + qslot * L::Q_TILE);
+            const uint64_t k_desc = k_desc0 + ((ks * L::K_STAGE) >> 4);
+            const uint32_t d_tmem = tile_tmem + (s_g & 1u) * A3_BKV;
+#pragma unroll
+            for (int st = 0; st < DH / 16; ++st) {
+              umma_bf16(d_tmem, q_desc + (((st >> 2) * L::Q_CHUNK + (st & 3) * 32) >> 4),
+                        k_desc + (((st >> 2) * L::K_CHUNK + (st & 3) * 32) >> 4), idesc_s, st != 0);
+            }
+            umma_commit(b_sfull + (t * 2 + (s_g & 1u)) * 8);
+            umma_commit(b_kempty + ks * 8);
+            if (s_f == s_nk - 1) ++qcnt;
+          } else {
+            mbar_arrive(b_kempty + ks * 8);
+          }
+          ++s_g;
+          if (++s_f == s_nk) {
+            s_f = 0;
+            s_item += item_stride;
+            s_act = s_item < item_last && tile_active(s_item);
+            s_nk = s_item < item_last ? steps_of(s_item) : 0;
+          }
+        };
+        if (s_item < item_last) issue_s();
+        if (s_item < item_last) issue_s();
+        uint32_t pcnt = 0, pv_item = item_first, ocnt = 0;   // ocnt: items of this tile whose first PV has been issued
+        int pv_f = 0;
+        int pv_nk = pv_item < item_last ? steps_of(pv_item) : 0;
+        bool pv_act = tile_active(pv_item);
+        for (uint32_t g = 0; pv_item < item_last; ++g) {
+          const uint32_t vs = g % KS, vpar = (g / KS) & 1u;
+          mbar_wait(b_vfull + vs * 8, vpar);
+          if (pv_act) {
+            const int rem = p.Tk - pv_f * A3_BKV;  // keys left from this step on (> 0)
+            const uint32_t slot = t * 2 + (pcnt & 1u);
+            mbar_wait(b_pfull + slot * 8, (pcnt >> 1) & 1u);
+            ++pcnt;
+            if (pv_f == 0) {
+              // the item's first PV overwrites O: the previous item's O must be in the epilogue warps' registers
+              if (ocnt > 0) mbar_wait(b_ofree + t * 8, (ocnt - 1u) & 1u);
+              ++ocnt;
+            }
+            tc_fence_after_sync();
+            const uint64_t v_desc = v_desc0 + ((vs * L::V_STAGE) >> 4);
+            const uint32_t p_tmem = tile_tmem + (g & 1u) * A3_BKV;
+#pragma unroll
+            for (int st = 0; st < A3_BKV / 16; ++st) {
+              if (st * 16 < rem)
+                umma_bf16_ts(tile_tmem + O_COL, p_tmem + st * 8, v_desc + ((st * 16 * 64) >> 4), idesc_pv, (pv_f | st) != 0);
+            }
+            umma_commit(b_pvdone + slot * 8);
+            umma_commit(b_vempty + vs * 8);
+          } else {
+            mbar_arrive(b_vempty + vs * 8);
+          }
+          if (s_item < item_last) issue_s();  // S(g+2) reuses the S buffer whose P was just consumed
+          if (++pv_f == pv_nk) {
+            pv_f = 0;
+            pv_item += item_stride;
+            pv_act = pv_item < item_last && tile_active(pv_item);
+            pv_nk = pv_item < item_last ? steps_of(pv_item) : 0;
+          }
+        }
+      };
+      if (elect_one()) {
+        if (warp == 1) run_issuer(std::integral_constant<int, 0>{});
+        else run_issuer(std::integral_constant<int, 1>{});
+      }
+    }
+  } else if (wgrp == 3) {
+    // ===================== epilogue warpgroup: O / l of both tiles =====================
+    reg_dealloc<120>();
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    uint32_t done[2] = {0u, 0u};   // items finished per tile -> (l, m) phase, Q buffer
+    uint32_t pvc[2] = {0u, 0u};    // PVs of the tile up to and including the current item
+    for (uint32_t item = item_first; item < item_last; item += item_stride) {
+      const int nk = steps_of(item);
+      const int b = static_cast<int>(item / static_cast<uint32_t>(p.items_per_b));
+      const uint32_t in_b = item - static_cast<uint32_t>(b) * static_cast<uint32_t>(p.items_per_b);
+      const int h = static_cast<int>(in_b / static_cast<uint32_t>(p.n_qp));
+      const int q_pair = static_cast<int>(in_b % static_cast<uint32_t>(p.n_qp)) * 2 * A3_BQ;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int q0 = q_pair + t * A3_BQ;
+        if (q0 >= p.Tq) continue;
+        const uint32_t t_o = tmem_base + lane_sel + t * TILE_COLS + O_COL;
+        mbar_wait(b_epifull + t * 8, done[t] & 1u);
+        const float l_run = xl[t * 128 + row], m_run = xm[t * 128 + row];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_epiempty + t * 8);
+        // the item's last PV (its predecessors retired before it: one issuer, in order).  Nothing can complete this
+        // barrier's phase twice behind our back: the next PV that lands on it is the next item's SECOND one, and the
+        // next item's first waits for the o_free below.
+        pvc[t] += static_cast<uint32_t>(nk);
+        const uint32_t kk = pvc[t] - 1u;
+        mbar_wait(b_pvdone + (t * 2 + (kk & 1u)) * 8, (kk >> 1) & 1u);
+        tc_fence_after_sync();
+        // l == 0 (every key masked) -> inf -> NaN like torch.softmax; DROP: the kept probabilities' 1 / (1 - p)
+        const float inv_l = DROP ? (1.0f / l_run) * p.drop_scale : 1.0f / l_run;
+        if (p.lse != nullptr && q0 + row < p.Tq)
+          p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Tq + q0 + row] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+        const uint32_t qslot = t * 2 + (done[t] & 1u);
+        const uint32_t stage_warp = sQ + qslot * L::Q_TILE + static_cast<uint32_t>(quad) * (32 * DH * 2);
+        const uint32_t stage_row = stage_warp + static_cast<uint32_t>(lane) * (DH * 2);
+        constexpr int OB = (DH / 32 > 3) ? 2 : DH / 32;   // chunks per batch
+#pragma unroll
+        for (int c0 = 0; c0 < DH / 32; c0 += OB) {
+          uint32_t vo[OB][32];
+#pragma unroll
+          for (int c = 0; c < OB; ++c) tmem_ld32(t_o + (c0 + c) * 32, vo[c]);
+          tmem_ld_wait();
+          if (c0 + OB >= DH / 32) {   // O is in registers: the tile's next item may start accumulating
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_ofree + t * 8);
+          }
+#pragma unroll
+          for (int c = 0; c < OB; ++c) {
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + (c0 + c) * 64 + g4 * 16),
+                           "r"(pack_bf16(__uint_as_float(vo[c][g4 * 8 + 0]) * inv_l, __uint_as_float(vo[c][g4 * 8 + 1]) * inv_l)),
+                           "r"(pack_bf16(__uint_as_float(vo[c][g4 * 8 + 2]) * inv_l, __uint_as_float(vo[c][g4 * 8 + 3]) * inv_l)),
+                           "r"(pack_bf16(__uint_as_float(vo[c][g4 * 8 + 4]) * inv_l, __uint_as_float(vo[c][g4 * 8 + 5]) * inv_l)),
+                           "r"(pack_bf16(__uint_as_float(vo[c][g4 * 8 + 6]) * inv_l, __uint_as_float(vo[c][g4 * 8 + 7]) * inv_l))
+                           : "memory");
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (q0 + quad * 32 < p.Tq) {
+            tma_store_3d(&tm_o, stage_warp, h * DH, q0 + quad * 32, b);
+            bulk_commit();
+          }
+          // this warpgroup is off the critical path: wait for the store to have read the staging bytes and hand the
+          // Q buffer straight back (the producer needs it for the item after next)
+          bulk_wait_read<0>();
+          mbar_arrive(b_qempty + qslot * 8);
+        }
+        __syncwarp();
+        ++done[t];
+      }
+    }
+  } else {
+    // ===================== softmax warpgroups (the v4 loop of attention_fwd3_kernel, general form) =====================
+    reg_alloc<168>();
+    const int wg = wgrp - 1;                 // query tile handled by this warpgroup
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int wg_tid = threadIdx.x - 128 - wg * 128;
+    const int row = quad * 32 + lane;
+    float* caps = dyn + wg * n_kv * A3_BKV;
+    int* flags = reinterpret_cast<int*>(dyn + 2 * n_kv * A3_BKV) + wg * n_kv;
+    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t t_tile = tmem_base + lane_sel + wg * TILE_COLS;
+    const uint32_t t_o = t_tile + O_COL;
+    const float sc = p.scale_log2;
+    uint32_t scnt0 = 0, scnt1 = 0;   // completed uses of each S buffer of this tile
+    uint32_t pv_issued = 0;          // P tiles handed to the MMA warp so far
+    uint32_t items_done = 0;         // items of this tile handed to the epilogue warpgroup
+    uint32_t g = 0;                  // flat step index of this CTA at the start of the current item
+    if (wg == 1) asm volatile("bar.arrive %0, 256;" ::"r"(3) : "memory");   // warpgroup 0 takes the first turn
+    int cur_b = -1;
+    int nk = 0;
+    for (uint32_t item = item_first; item < item_last; item += item_stride, g += nk) {
+      nk = steps_of(item);
+      const int b = static_cast<int>(item / static_cast<uint32_t>(p.items_per_b));
+      const uint32_t in_b = item - static_cast<uint32_t>(b) * static_cast<uint32_t>(p.items_per_b);
+      const int h = static_cast<int>(in_b / static_cast<uint32_t>(p.n_qp));
+      const int q0 = static_cast<int>(in_b % static_cast<uint32_t>(p.n_qp)) * 2 * A3_BQ + wg * A3_BQ;
+      [[maybe_unused]] const uint32_t dbase =
+          drop_key_bh(p.drop_key, static_cast<uint32_t>(b * p.H + h)) + static_cast<uint32_t>(q0 + row) * DROP_C_ROW;
+      if (q0 >= p.Tq) {  // this warpgroup's tile does not exist for this item: only keep the exp turn-taking alive
+        for (int j = 0; j < nk; ++j) {
+          asm volatile("bar.sync %0, 256;" ::"r"(3 + wg) : "memory");
+          asm volatile("bar.arrive %0, 256;" ::"r"(4 - wg) : "memory");
+        }
+        continue;
+      }
+      if (cur_b < 0 || (b != cur_b && p.key_pad != nullptr)) {   // without a mask the caps only depend on Tk
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+        for (int j = wg_tid; j < n_kv; j += 128) flags[j] = 0;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+        for (int kk = wg_tid; kk < n_kv * A3_BKV; kk += 128) {
+          bool pad = kk >= p.Tk;
+          if (!pad && p.key_pad != nullptr) pad = p.key_pad[static_cast<int64_t>(b) * p.Tk + kk] != 0;
+          caps[kk] = pad ? -INFINITY : INFINITY;
+          if (pad) flags[kk / A3_BKV] = 1;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+        cur_b = b;
+      }
+      float m_run = -INFINITY;  // running reference maximum, in log2 units (score * scale * log2 e)
+      float l_run = 0.0f;
+      uint32_t va[32], vb[32];
+      // the item's first scores
+      {
+        const uint32_t sbuf0 = g & 1u;
+        mbar_wait(b_sfull + (wg * 2 + sbuf0) * 8, (sbuf0 ? scnt1 : scnt0) & 1u);
+        if (sbuf0) ++scnt1; else ++scnt0;
+        tc_fence_after_sync();
+        tmem_ld32(t_tile + sbuf0 * A3_BKV, va);
+        if (p.Tk > 32) tmem_ld32(t_tile + sbuf0 * A3_BKV + 32, vb);
+      }
+      for (int j = 0; j < nk; ++j) {
+        const uint32_t sbuf = (g + static_cast<uint32_t>(j)) & 1u;
+        const uint32_t t_s = t_tile + sbuf * A3_BKV;
+        const int rem = p.Tk - j * A3_BKV;
+        const bool two = rem > 32;                   // second 32-key chunk holds a valid key
+        const bool masked = flags[j] != 0;           // warp-uniform
+        const float* cap_j = caps + j * A3_BKV;
+        tmem_ld_wait();
+        if (masked) {
+          apply_caps(va, cap_j);
+          if (two) apply_caps(vb, cap_j + 32);
+        }
+        // ---- row maximum of this step.  Only the item's FIRST step needs it before the exponentials (it sets the
+        // reference maximum).  Later steps keep the reference unless the maximum grew by more than 2^TAU (lazy
+        // rescale), which is rare: they compute p = 2^(s - m_run) with the reference they have (SPECULATIVELY) while
+        // the maximum is formed on the ALU pipe next to the exponentials on the XU pipe, and check afterwards; the
+        // few steps that do need a rescale repair O / l and redo their exponentials before P is handed over.
+        auto row_max = [&]() {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          max4(m4, va);
+          if (two) max4(m4, vb);
+          return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;  // sc > 0
+        };
+        if (j == 0) m_run = row_max();     // (a real branch, j is warp-uniform: later steps must not wait for their maximum)
+        float neg_m = (m_run == -INFINITY) ? 0.0f : -m_run;
+
+        // ---- p = 2^(s*scale - m), row sum, bf16 P into the first 32 columns of this S buffer; the two warpgroups
+        // take turns (named barriers 3 / 4) so that their exponentials do not collide on the quarter-rate XU pipe
+#ifndef HRIEMO_ATTN_NO_PINGPONG
+        asm volatile("bar.sync %0, 256;" ::"r"(3 + wg) : "memory");
+#endif
+        float l4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        uint32_t pk[16];
+        exp_pack(va, sc, neg_m, l4, pk);
+        if constexpr (DROP) drop_pk(pk, dbase, static_cast<uint32_t>(j) * 16u, p.drop_p8);
+        tmem_st16(t_s, pk);
+        if (two) {
+          exp_pack(vb, sc, neg_m, l4, pk);
+          if constexpr (DROP) drop_pk(pk, dbase, static_cast<uint32_t>(j) * 16u + 8u, p.drop_p8);
+          tmem_st16(t_s + 16, pk);
+        }
+#ifndef HRIEMO_ATTN_NO_PINGPONG
+        asm volatile("bar.arrive %0, 256;" ::"r"(4 - wg) : "memory");   // the other warpgroup's turn
+#endif
+        if (j > 0) {
+          const float tile_max = row_max();
+          const bool need = tile_max > m_run + A3_LAZY_TAU;
+          if (__any_sync(0xffffffffu, need)) {
+            // every PV of this tile must have retired: the latest one is PV(pv_issued - 1); the one before retired
+            // before this step's S landed (see above), so this wait can not be answered by a stale phase
+            const uint32_t kk = pv_issued - 1u;
+            mbar_wait(b_pvdone + (wg * 2 + (kk & 1u)) * 8, (kk >> 1) & 1u);
+            tc_fence_after_sync();
+            const float alpha = need ? ex2_approx(m_run - tile_max) : 1.0f;
+            if (need) m_run = tile_max;
+            l_run *= alpha;
+#pragma unroll 1
+            for (int c = 0; c < DH / 32; ++c) {
+              uint32_t v[32];
+              tmem_ld32(t_o + c * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st32(t_o + c * 32, v);
+            }
+            // this step's exponentials again, against the new reference (the scores are still in registers)
+            neg_m = (m_run == -INFINITY) ? 0.0f : -m_run;
+            l4[0] = l4[1] = l4[2] = l4[3] = 0.0f;
+            exp_pack(va, sc, neg_m, l4, pk);
+            if constexpr (DROP) drop_pk(pk, dbase, static_cast<uint32_t>(j) * 16u, p.drop_p8);
+            tmem_st16(t_s, pk);
+            if (two) {
+              exp_pack(vb, sc, neg_m, l4, pk);
+              if constexpr (DROP) drop_pk(pk, dbase, static_cast<uint32_t>(j) * 16u + 8u, p.drop_p8);
+              tmem_st16(t_s + 16, pk);
+            }
+          }
+        }
+        l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        // ---- the next step's scores: wait for S(j+1) and issue its loads while the P stores drain
+        if (j + 1 < nk) {
+          const uint32_t nbuf = sbuf ^ 1u;
+          mbar_wait(b_sfull + (wg * 2 + nbuf) * 8, (nbuf ? scnt1 : scnt0) & 1u);
+          if (nbuf) ++scnt1; else ++scnt0;
+          tc_fence_after_sync();
+          tmem_ld32(t_tile + nbuf * A3_BKV, va);
+          if (p.Tk - (j + 1) * A3_BKV > 32) tmem_ld32(t_tile + nbuf * A3_BKV + 32, vb);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_pfull + (wg * 2 + (pv_issued & 1u)) * 8);
+        ++pv_issued;
+      }
+      // ---- the item's row sums go to the epilogue warpgroup; this one carries straight on with the next item
+      mbar_wait(b_epiempty + wg * 8, (items_done & 1u) ^ 1u);
+      xl[wg * 128 + row] = l_run;
+      xm[wg * 128 + row] = m_run;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_epifull + wg * 8);
+      ++items_done;
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
 template <int DH>
 static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
   using L = Attn3Smem<DH>;
@@ -1649,7 +2142,25 @@ static int launch_attention3(const hriemo_attn_args& a, cudaStream_t stream) {
   }();
   const bool use_fwd4 = !p.paired && !defer && (fwd4_env < 0 ? kFwd4Default : fwd4_env != 0) &&
                         Attn4Smem<DH>::dyn_bytes4(n_kv) <= 227 * 1024;
-  if (use_fwd4) {
+  // ... and a third, attention_fwd5_kernel (the O / l epilogue on its own warpgroup): HRIEMO_ATTN_FWD5 = 0 / 1.
+  static const int fwd5_env = [] {
+    const char* e = getenv("HRIEMO_ATTN_FWD5");
+    return e == nullptr ? -1 : atoi(e);
+  }();
+  const bool use_fwd5 = !p.paired && !defer && !use_fwd4 && (fwd5_env < 0 ? kFwd5Default : fwd5_env != 0) &&
+                        Attn5Smem<DH>::dyn_bytes5(n_kv) <= 227 * 1024;
+  if (use_fwd5) {
+    static uint64_t attr5_done = 0;
+    if (device_needs_attr(&attr5_done)) {
+      cudaError_t e = cudaFuncSetAttribute(attention_fwd5_kernel<DH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attention_fwd5_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    const int smem5 = Attn5Smem<DH>::dyn_bytes5(n_kv);
+    if (p.drop_p8) attention_fwd5_kernel<DH, true><<<grid, A5_THREADS, smem5, stream>>>(tq, tk, tv, to, p);
+    else attention_fwd5_kernel<DH, false><<<grid, A5_THREADS, smem5, stream>>>(tq, tk, tv, to, p);
+  } else if (use_fwd4) {
     static uint64_t attr4_done = 0;
     if (device_needs_attr(&attr4_done)) {
       cudaError_t e = cudaFuncSetAttribute(attention_fwd4_kernel<DH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

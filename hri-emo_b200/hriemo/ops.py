@@ -25,6 +25,10 @@ LN_EPS = 1e-5
 PROFILE = None
 # When set to a list, GEMM launches append (tag, algorithmic bytes = (M*K + N*K + M*N [+ M*N residual]) * 2, None, None).
 PROFILE_BYTES = None
+# When set to a list, attention launches append (Tq, Tk, algorithmic FLOPs, algorithmic bytes = Q + K + V + O in bf16, start,
+# end): the cross shapes of a layer are HBM work, the 500 x 500 self-attention tensor-pipe work (bench.py reports each
+# against its own roofline).
+PROFILE_ATTN = None
 
 
 def _prof_begin(kind: str, work: float):
@@ -232,6 +236,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_pad: Option
     tok = _prof_begin("attention", 4.0 * B * H * Tq * Tk * dh)
     _l.check(_l.load().hriemo_attention_bf16(C.byref(args), _stream()), "attention_bf16")
     _prof_end(tok)
+    if tok is not None and PROFILE_ATTN is not None:
+        PROFILE_ATTN.append((Tq, Tk, tok[1], 2.0 * B * H * dh * (2 * Tq + 2 * Tk), tok[2], tok[3]))
     return (out, lse) if want_lse else out
 
 
