@@ -206,6 +206,29 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   // release at cluster scope would add a full memory barrier per arrival
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// release / acquire at CLUSTER scope: a thread of one CTA passes on to threads of the peer CTA what it has observed
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && (++spins & 0x3fffu) == 0) {   // a pipeline bug traps after ~4 s instead of hanging the box
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
+  }
+}
 // CTA-pair (cta_group::2) variants.  A pair shares one MMA: the leader (cluster rank 0) issues it,
 // each CTA supplies its half of the operands from its own shared memory at the SAME offsets, and
 // each CTA's tensor memory receives its 128 accumulator rows.
