@@ -805,7 +805,7 @@ def main():
             return world * Be * n / float(dt.item()), st
 
         e2e_sequential(1, ha_h, ht_h)
-        n_e2e, n_stream = 3, 5
+        n_e2e, n_stream = 3, 8   # the stream starts cold after a synchronise: ~4 ms per step of ramp at 5 steps, ~2 at 8
         seq, _ = timed(e2e_sequential, n_e2e, ha_h, ht_h)
         e2e_stream(2, ha_h, ht_h)
         stream, st = timed(e2e_stream, n_stream, ha_h, ht_h)

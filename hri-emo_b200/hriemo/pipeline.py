@@ -236,6 +236,7 @@ HOST_SETS = 3
 # already queued in the engine when the decision is made).
 PLAN_MIN_LEFT = 2
 PLAN_RESERVE = 0.0
+HOST_RESERVE = 2
 # what the host-staged entry points moved, accumulated over calls (bench.py reads and resets it): bytes copied
 # host -> device (counted from the tensors copied), slabs, and how many of them the host cores pre-cast
 STATS = dict(h2d_bytes=0, slabs=0, host_cast_slabs=0, calls=0)
@@ -815,7 +816,10 @@ def forward_from_host(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a: Optio
     threads = max(1, torch.get_num_threads())
     if host_cast_every is None or host_cast_every == "auto":
         if early and not bucket and not ramp and (B + slab - 1) // slab >= 3:
-            return _run_dense_dynamic(model, dev, h_a, h_t, mask_a, mask_t, slab, out_device, threads, wait, trace)
+            # the converting threads leave HOST_RESERVE cores to the thread that issues the copies and launches (and to the
+            # CUDA driver's own): with all 16 busy converting, the issuing thread was descheduled between launches
+            conv = threads - HOST_RESERVE if threads >= 8 else threads
+            return _run_dense_dynamic(model, dev, h_a, h_t, mask_a, mask_t, slab, out_device, conv, wait, trace)
         host_cast_every = default_host_cast_every(threads)
     mask_a_dev = mask_t_dev = None
 

@@ -27,10 +27,31 @@ def stream(n):
         if pend is not None: pend.wait()
         pend = nxt
     pend.wait()
+# the device-resident forward of the same batch on this box (what bench.py's `value` times), in slabs of 2048
+def resident(n):
+    for _ in range(n):
+        for lo in range(0, B, 2048):
+            model(xa[lo:lo + 2048], xt[lo:lo + 2048])
+xa, xt = ha.to(dev), ht.to(dev)
+resident(2)
+torch.cuda.synchronize(); t0 = time.perf_counter(); resident(4); torch.cuda.synchronize()
+print(f"device-resident forward: {(time.perf_counter() - t0) / 4 * 1e3:.1f} ms per step")
+del xa, xt
+torch.cuda.empty_cache()
+# bench.py's sequence: one call at a time (3), then two warm-up calls of the stream and 5 timed ones from a synchronise
+for _ in range(1): pipeline.forward_from_host(model, ha, ht, device=dev, slab=512, out_device="cpu")
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(3): pipeline.forward_from_host(model, ha, ht, device=dev, slab=512, out_device="cpu")
+torch.cuda.synchronize(); print(f"one call at a time: {(time.perf_counter() - t0) / 3 * 1e3:.1f} ms per step")
+stream(2)
+for n in (5, 5, 10):
+    pipeline.reset_stats()
+    torch.cuda.synchronize(); t0 = time.perf_counter(); stream(n); torch.cuda.synchronize()
+    print(f"stream of {n} from a synchronise: {(time.perf_counter() - t0) / n * 1e3:.1f} ms per step, host-cast slabs {pipeline.STATS['host_cast_slabs'] / n:.1f}")
 stream(3)
-for rep, (min_left, reserve) in enumerate([(2, 0.0), (1, 1.5), (2, 0.0), (1, 1.5), (1, 0.5)]):
-    pipeline.PLAN_MIN_LEFT, pipeline.PLAN_RESERVE = min_left, reserve
-    print("PLAN_MIN_LEFT", min_left, "PLAN_RESERVE", reserve)
+for rep, host_reserve in enumerate([2, 0]):
+    pipeline.HOST_RESERVE = host_reserve
+    print("HOST_RESERVE", host_reserve)
     packs.clear(); pipeline.reset_stats()
     torch.cuda.synchronize(); t0 = time.perf_counter()
     stream(8)
@@ -51,7 +72,7 @@ def nxt(self, paced=True):
 def pub(self, slab, k, seconds):
     log.append((time.perf_counter() - t00[0], "host done", slab, self.front, self.back, seconds, None)); return op(self, slab, k, seconds)
 pipeline.TwoEndedPlan.claim_back, pipeline.TwoEndedPlan.next, pipeline.TwoEndedPlan.publish = claim_back, nxt, pub
-pipeline.PLAN_MIN_LEFT, pipeline.PLAN_RESERVE = 2, 0.0
+pipeline.HOST_RESERVE = 2
 t00[0] = time.perf_counter()
 stream(4)
 torch.cuda.synchronize()
