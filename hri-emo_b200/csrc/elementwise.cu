@@ -1,6 +1,8 @@
 // HBM-bound passes of the path: feature cast, LayerNorm, the beta-gate pooling
 // and blend.  All are one-warp-per-row kernels with 16-byte vector accesses and
 // fp32 statistics; none needs tensor cores.
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 
@@ -453,6 +455,217 @@ gate_blend_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int T_a,
   }
 }
 
+// The blend, streaming form (default whenever pending LayerNorms come with their row statistics, as in the forward).
+// gate_blend_kernel above gives every row its own short-lived warp: two 1.5 KB loads in flight per warp, then ~1 500
+// instructions (four two-pass LayerNorms with their gamma / beta re-read from L1 for every row, scalar gate loads):
+// 566 MB in 340 us = 0.25 of the HBM roofline (ncu launch list v17).  Here one persistent CTA per SM; a warp owns a
+// contiguous range of rows and a private cp.async ring (STAGES row pairs of a | t in flight per warp), and per row does
+//     x = pending LayerNorm (known statistics; gamma / beta staged once per CTA in lane order in shared memory)
+//     (s, q) = one-pass sums of both streams, reduced together (one round of shuffles for four sums)
+//     h = A o (x_a r_a + k_a) + T o (x_t r_t + k_t) + C,   A = w o gamma_a,  T = (1 - w) o gamma_t,  C = w o beta_a + (1 - w) o beta_t
+// with (A, T, C) folded once per utterance into registers -- all in packed fp32 (FFMA2).  ~700 instructions per row.
+template <int NV> struct GbStages { static constexpr int value = NV <= 3 ? 6 : (NV == 4 ? 4 : 2); };
+
+template <int NV>
+__global__ void __launch_bounds__(256, 1)
+gate_blend_stream_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int T_a,
+                         const __nv_bfloat16* __restrict__ t, int64_t ldt, const float* __restrict__ ga,
+                         const float* __restrict__ ba, const float* __restrict__ gt, const float* __restrict__ bt,
+                         float eps, int apply_ln, const float* __restrict__ w, int w_is_scalar,
+                         __nv_bfloat16* __restrict__ hb, float* __restrict__ hf, int64_t ldh,
+                         float* __restrict__ beta_out, int B, int L, int d, const float* __restrict__ pga,
+                         const float* __restrict__ pba, const float* __restrict__ pgt, const float* __restrict__ pbt,
+                         const float2* __restrict__ psa, const float2* __restrict__ pst) {
+  constexpr int STAGES = GbStages<NV>::value;
+  constexpr int PAIR_BYTES = 2 * NV * 512;
+  extern __shared__ __align__(16) uint8_t gb_smem[];
+  float4* vec = reinterpret_cast<float4*>(gb_smem);   // [4 vectors][NV][2 halves][32 lanes]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const float* srcs[4] = {pga, pba, pgt, pbt};
+    for (int e = threadIdx.x; e < 4 * NV * 64; e += blockDim.x) {
+      const int vsel = e / (NV * 64), rem = e - vsel * (NV * 64);
+      const int i = rem >> 6, half = (rem >> 5) & 1, ln = rem & 31;
+      const int c = (i * 32 + ln) * 8 + half * 4;
+      float4 val = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (srcs[vsel] != nullptr && c < d) val = __ldg(reinterpret_cast<const float4*>(srcs[vsel] + c));
+      vec[e] = val;
+    }
+  }
+  __syncthreads();
+  uint8_t* ring_p = gb_smem + 4 * NV * 64 * 16 + warp * (STAGES * PAIR_BYTES) + lane * 16;
+  const uint32_t ring = smem_u32(ring_p);
+  const int64_t rows = static_cast<int64_t>(B) * L;
+  const int64_t gw = static_cast<int64_t>(blockIdx.x) * 8 + warp, GW = static_cast<int64_t>(gridDim.x) * 8;
+  const int64_t r_begin = rows * gw / GW, r_end = rows * (gw + 1) / GW;
+  auto issue = [&](int64_t r, int slot) {   // one commit group per call, also when there is nothing left to copy
+    if (r < r_end) {
+      const int64_t b = r / L;
+      const int tt = static_cast<int>(r - b * L);
+      const __nv_bfloat16* ar = a + (b * T_a + tt) * lda;
+      const __nv_bfloat16* tr = t + r * ldt;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        if (c < d) {
+          lmm_cp_async16(ring + slot * PAIR_BYTES + i * 512, ar + c);
+          lmm_cp_async16(ring + slot * PAIR_BYTES + (NV + i) * 512, tr + c);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto row_stats_of = [&](int64_t r, float2& sa, float2& st) {   // (mean, rstd) of the pending LayerNorms of row r
+    sa = make_float2(0.0f, 1.0f);
+    st = make_float2(0.0f, 1.0f);
+    if (r < r_end) {
+      const int64_t b = r / L;
+      if (psa != nullptr) sa = __ldg(psa + b * T_a + (r - b * L));
+      if (pst != nullptr) st = __ldg(pst + r);
+    }
+  };
+#pragma unroll
+  for (int s0 = 0; s0 < STAGES - 1; ++s0) issue(r_begin + s0, s0);
+  float2 nsa, nst;
+  row_stats_of(r_begin, nsa, nst);
+  float2 cA[NV][4], cT[NV][4], cC[NV][4];
+  int64_t b_cur = -1;
+  const float inv_d = 1.0f / static_cast<float>(d);
+  int slot = 0;
+  for (int64_t r = r_begin; r < r_end; ++r) {
+    const int64_t b = r / L;
+    const float2 sta = nsa, stt = nst;
+    row_stats_of(r + 1, nsa, nst);   // consumed one row later
+    if (b != b_cur) {
+      b_cur = b;
+      float wsum = 0.0f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        float wv[8], g1[8], b1[8], g2[8], b2[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { wv[k] = 0.0f; g1[k] = g2[k] = 1.0f; b1[k] = b2[k] = 0.0f; }
+        if (c < d) {
+          if (w_is_scalar) {
+            const float ws = __ldg(w + b);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) wv[k] = ws;
+          } else {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + b * d + c)), w1 = __ldg(reinterpret_cast<const float4*>(w + b * d + c + 4));
+            wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w; wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
+          }
+          if (apply_ln) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { g1[k] = __ldg(ga + c + k); b1[k] = __ldg(ba + c + k); g2[k] = __ldg(gt + c + k); b2[k] = __ldg(bt + c + k); }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float w0 = wv[2 * k], w1 = wv[2 * k + 1];
+          wsum += w0 + w1;
+          cA[i][k] = make_float2(w0 * g1[2 * k], w1 * g1[2 * k + 1]);
+          cT[i][k] = make_float2((1.0f - w0) * g2[2 * k], (1.0f - w1) * g2[2 * k + 1]);
+          cC[i][k] = make_float2(w0 * b1[2 * k] + (1.0f - w0) * b2[2 * k], w1 * b1[2 * k + 1] + (1.0f - w1) * b2[2 * k + 1]);
+          if (c >= d) cA[i][k] = cT[i][k] = cC[i][k] = make_float2(0.0f, 0.0f);
+        }
+      }
+      if (beta_out != nullptr && r == b * L) {   // this warp holds the utterance's first row
+        wsum = warp_sum(wsum);
+        if (lane == 0) beta_out[b] = w_is_scalar ? __ldg(w + b) : wsum * inv_d;
+      }
+    }
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+    float2 xa[NV][4], xt[NV][4];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      uint4 u = make_uint4(0u, 0u, 0u, 0u), v = make_uint4(0u, 0u, 0u, 0u);
+      if (c < d) {
+        u = *reinterpret_cast<const uint4*>(ring_p + slot * PAIR_BYTES + i * 512);
+        v = *reinterpret_cast<const uint4*>(ring_p + slot * PAIR_BYTES + (NV + i) * 512);
+      }
+      xa[i][0] = make_float2(bf16_lo(u.x), bf16_hi(u.x)); xa[i][1] = make_float2(bf16_lo(u.y), bf16_hi(u.y));
+      xa[i][2] = make_float2(bf16_lo(u.z), bf16_hi(u.z)); xa[i][3] = make_float2(bf16_lo(u.w), bf16_hi(u.w));
+      xt[i][0] = make_float2(bf16_lo(v.x), bf16_hi(v.x)); xt[i][1] = make_float2(bf16_lo(v.y), bf16_hi(v.y));
+      xt[i][2] = make_float2(bf16_lo(v.z), bf16_hi(v.z)); xt[i][3] = make_float2(bf16_lo(v.w), bf16_hi(v.w));
+    }
+    // the slot consumed in the PREVIOUS iteration takes the row STAGES - 1 ahead
+    issue(r + STAGES - 1, slot == 0 ? STAGES - 1 : slot - 1);
+    if (pga != nullptr) {
+      const float2 u2 = make_float2(sta.y, sta.y), k2 = make_float2(-sta.x * sta.y, -sta.x * sta.y);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 g0 = vec[(0 * NV + i) * 64 + lane], g1 = vec[(0 * NV + i) * 64 + 32 + lane];
+        const float4 b0 = vec[(1 * NV + i) * 64 + lane], b1 = vec[(1 * NV + i) * 64 + 32 + lane];
+        xa[i][0] = ffma2(ffma2(xa[i][0], u2, k2), make_float2(g0.x, g0.y), make_float2(b0.x, b0.y));
+        xa[i][1] = ffma2(ffma2(xa[i][1], u2, k2), make_float2(g0.z, g0.w), make_float2(b0.z, b0.w));
+        xa[i][2] = ffma2(ffma2(xa[i][2], u2, k2), make_float2(g1.x, g1.y), make_float2(b1.x, b1.y));
+        xa[i][3] = ffma2(ffma2(xa[i][3], u2, k2), make_float2(g1.z, g1.w), make_float2(b1.z, b1.w));
+      }
+    }
+    if (pgt != nullptr) {
+      const float2 u2 = make_float2(stt.y, stt.y), k2 = make_float2(-stt.x * stt.y, -stt.x * stt.y);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 g0 = vec[(2 * NV + i) * 64 + lane], g1 = vec[(2 * NV + i) * 64 + 32 + lane];
+        const float4 b0 = vec[(3 * NV + i) * 64 + lane], b1 = vec[(3 * NV + i) * 64 + 32 + lane];
+        xt[i][0] = ffma2(ffma2(xt[i][0], u2, k2), make_float2(g0.x, g0.y), make_float2(b0.x, b0.y));
+        xt[i][1] = ffma2(ffma2(xt[i][1], u2, k2), make_float2(g0.z, g0.w), make_float2(b0.z, b0.w));
+        xt[i][2] = ffma2(ffma2(xt[i][2], u2, k2), make_float2(g1.x, g1.y), make_float2(b1.x, b1.y));
+        xt[i][3] = ffma2(ffma2(xt[i][3], u2, k2), make_float2(g1.z, g1.w), make_float2(b1.z, b1.w));
+      }
+    }
+    float2 ra = make_float2(1.0f, 1.0f), ka = make_float2(0.0f, 0.0f), rt = ra, kt = ka;
+    if (apply_ln) {
+      float2 s1 = make_float2(0.0f, 0.0f), q1 = s1, s2 = s1, q2 = s1;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          s1 = fadd2(s1, xa[i][k]);
+          q1 = ffma2(xa[i][k], xa[i][k], q1);
+          s2 = fadd2(s2, xt[i][k]);
+          q2 = ffma2(xt[i][k], xt[i][k], q2);
+        }
+      float v1 = s1.x + s1.y, v2 = q1.x + q1.y, v3 = s2.x + s2.y, v4 = q2.x + q2.y;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+        v4 += __shfl_xor_sync(0xffffffffu, v4, o);
+      }
+      const float ma = v1 * inv_d, mt = v3 * inv_d;
+      const float rsa = rsqrtf(fmaxf(v2 * inv_d - ma * ma, 0.0f) + eps), rst = rsqrtf(fmaxf(v4 * inv_d - mt * mt, 0.0f) + eps);
+      ra = make_float2(rsa, rsa); ka = make_float2(-ma * rsa, -ma * rsa);
+      rt = make_float2(rst, rst); kt = make_float2(-mt * rst, -mt * rst);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      float2 h[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        h[k] = ffma2(cA[i][k], ffma2(xa[i][k], ra, ka), ffma2(cT[i][k], ffma2(xt[i][k], rt, kt), cC[i][k]));
+      if (c < d) {
+        if (hb != nullptr) {
+          uint4 o;
+          o.x = pack_bf16(h[0].x, h[0].y); o.y = pack_bf16(h[1].x, h[1].y);
+          o.z = pack_bf16(h[2].x, h[2].y); o.w = pack_bf16(h[3].x, h[3].y);
+          *reinterpret_cast<uint4*>(hb + r * ldh + c) = o;
+        }
+        if (hf != nullptr) {
+          float4* p = reinterpret_cast<float4*>(hf + r * ldh + c);
+          p[0] = make_float4(h[0].x, h[0].y, h[1].x, h[1].y);
+          p[1] = make_float4(h[2].x, h[2].y, h[3].x, h[3].y);
+        }
+      }
+    }
+    slot = slot + 1 == STAGES ? 0 : slot + 1;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ fused-LayerNorm helpers
 // partials[slab][row] = (sum, sum of squares) over that slab's columns -> stats[row] = (mean, rstd)
 __global__ void ln_stats_finalize_kernel(const float2* __restrict__ partials, int n_slabs, int64_t rows, int d,
@@ -744,6 +957,32 @@ extern "C" int hriemo_gate_blend(const void* a, int64_t lda, int32_t T_a, const 
                      aligned16(h_bf16) && aligned16(h_f32),
                  "gate_blend: misaligned operand");
   const int64_t rows = static_cast<int64_t>(B) * L;
+  static const bool force_v1 = getenv("HRIEMO_GATE_BLEND_V1") != nullptr;   // the warp-per-row form, for A / B runs
+  if (!force_v1 && d <= 1024 /* wider rows spill in the streaming form */ && (pre_gamma_a == nullptr || pre_stats_a != nullptr) && (pre_gamma_t == nullptr || pre_stats_t != nullptr) &&
+      (w_is_scalar || aligned16(w)) && (!apply_ln || (aligned16(gamma_a) && aligned16(beta_a) && aligned16(gamma_t) && aligned16(beta_t)))) {
+    // streaming form: persistent CTAs, warp-private row rings (gate_blend_stream_kernel)
+    static uint64_t gb_attr_done = 0;
+    if (device_needs_attr(&gb_attr_done)) {
+      cudaError_t e = cudaSuccess;
+#define HRIEMO_GB_ATTR(NVV)                                                                                      \
+      if (e == cudaSuccess)                                                                                      \
+        e = cudaFuncSetAttribute(gate_blend_stream_kernel<NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                 4 * NVV * 1024 + 8 * GbStages<NVV>::value * 2 * NVV * 512)
+      HRIEMO_GB_ATTR(1); HRIEMO_GB_ATTR(2); HRIEMO_GB_ATTR(3); HRIEMO_GB_ATTR(4); HRIEMO_GB_ATTR(8);
+#undef HRIEMO_GB_ATTR
+      if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "gate_blend: %s", cudaGetErrorString(e));
+    }
+    int64_t grid = (rows + 7) / 8;
+    const int64_t resident = static_cast<int64_t>(device_sm_count()) * (d <= 256 ? 2 : 1);   // NV = 1: two CTAs fit an SM (118 registers, 53 KB)
+    if (grid > resident) grid = resident;
+    HRIEMO_DISPATCH_NV(d, (gate_blend_stream_kernel<NV><<<static_cast<unsigned>(grid), 256, 4 * NV * 1024 + 8 * GbStages<NV>::value * 2 * NV * 512,
+                                                         static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(a), lda, T_a, static_cast<const __nv_bfloat16*>(t), ldt, gamma_a,
+        beta_a, gamma_t, beta_t, eps, apply_ln, w, w_is_scalar, static_cast<__nv_bfloat16*>(h_bf16), h_f32,
+        ldh, beta_out, B, L, d, pre_gamma_a, pre_beta_a, pre_gamma_t, pre_beta_t,
+        reinterpret_cast<const float2*>(pre_stats_a), reinterpret_cast<const float2*>(pre_stats_t))));
+    return check_launch("gate_blend");
+  }
   HRIEMO_DISPATCH_NV(d, (gate_blend_kernel<NV><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(a), lda, T_a, static_cast<const __nv_bfloat16*>(t), ldt, gamma_a,
       beta_a, gamma_t, beta_t, eps, apply_ln, w, w_is_scalar, static_cast<__nv_bfloat16*>(h_bf16), h_f32,

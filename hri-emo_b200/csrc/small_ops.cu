@@ -2,6 +2,7 @@
 //  * fp32 GEMM for the beta-gate MLP, the emotion head and the classifier head,
 //  * small-query attention (emotion decoder) and head-averaged attention maps.
 #include <math.h>
+#include <stdlib.h>
 
 #include "dropout.cuh"
 #include "host_common.h"
@@ -297,6 +298,196 @@ decoder_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const
   }
 }
 
+// ------------------------------------------------------------------ decoder attention, warp-private form (default)
+// The CTA-per-(utterance, head) kernel above spends most of a CTA's life in its score / P.V loops with 64 and 48 of its
+// 128 threads busy, so on average few of an SM's bytes are in flight: 0.31 of the HBM roofline (ncu launch list v17:
+// 456 MB in 224 us).  Here a WARP owns a stream of (utterance, head) items and a private two-slot ring in shared memory:
+// while the tensor cores work on slot s (legacy mma.sync m16n8k16 -- the N_q <= 8 query rows fill half of one M = 16
+// tile, which is wasteful and irrelevant: ~100 MMAs per item against a 24 KB tile), the 16-byte cp.async copies of
+// the next item's K | V | Q land in slot s ^ 1.  No __syncthreads, no barrier between warps; every lane copies with
+// a fixed (row mod R, chunk) pattern so the issue loop is one LDGSTS + pointer bumps per chunk.  Fragments come from
+// ldmatrix (K) and ldmatrix.trans (V) over rows padded by 16 bytes (conflict-free); the softmax runs on the accumulator
+// layout (a query row lives in the four lanes of a quad), P goes into P.V as bf16 hi + lo parts.
+// A fully masked row gives NaN, like torch.softmax.  grid = one CTA per SM, persistent.
+template <int DH, int KT>
+struct DecAttn {
+  static constexpr int TKP = KT * 8;                 // staged key rows (rows >= T_k stay zero)
+  static constexpr int PITCH = DH * 2 + 16;          // bytes per staged row
+  static constexpr int CPR = DH / 8;                 // 16-byte chunks per row
+  static constexpr int RPI = 32 / CPR;               // rows copied per warp iteration
+  static constexpr int SLOT = (2 * TKP + 8) * PITCH; // K | V | Q (8 rows)
+  static constexpr int WARPS_FIT = (227 * 1024) / (2 * SLOT);
+  static constexpr int WARPS = WARPS_FIT >= 4 ? 4 : WARPS_FIT;
+  static_assert(DH % 16 == 0 && KT % 2 == 0 && WARPS >= 1, "decoder attention: unsupported tile");
+};
+
+__device__ __forceinline__ void da_ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void da_ldsm_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+// rows 8..15 of the A tile are padding: a1 = a3 = 0
+__device__ __forceinline__ void da_mma(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+
+template <int DH, int KT>
+__global__ void __launch_bounds__(DecAttn<DH, KT>::WARPS * 32, 1)
+decoder_attention_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k, int64_t ldk,
+                             const __nv_bfloat16* __restrict__ v, int64_t ldv, const uint8_t* __restrict__ key_pad,
+                             __nv_bfloat16* __restrict__ out, int64_t ldo, int B, int H, int Nq, int Tk, float scale) {
+  using C = DecAttn<DH, KT>;
+  constexpr int PW = (C::TKP + 31) / 32;   // 32-key mask words
+  extern __shared__ __align__(16) uint8_t dam_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  uint8_t* ring_p = dam_smem + static_cast<size_t>(warp) * 2 * C::SLOT;
+  const uint32_t ring = smem_u32(ring_p);
+  // rows the copies never write (keys >= T_k, queries >= N_q) are zero for the kernel's lifetime
+  for (int s = 0; s < 2; ++s) {
+    for (int i = lane; i < (C::TKP - Tk) * (C::PITCH / 16); i += 32) {
+      reinterpret_cast<uint4*>(ring_p + s * C::SLOT + Tk * C::PITCH)[i] = make_uint4(0u, 0u, 0u, 0u);
+      reinterpret_cast<uint4*>(ring_p + s * C::SLOT + (C::TKP + Tk) * C::PITCH)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int i = lane; i < (8 - Nq) * (C::PITCH / 16); i += 32)
+      reinterpret_cast<uint4*>(ring_p + s * C::SLOT + (2 * C::TKP + Nq) * C::PITCH)[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncwarp();
+  const int64_t items = static_cast<int64_t>(B) * H;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * C::WARPS;
+  // copy pattern of this lane: row (lane / CPR) of every group of RPI rows, chunk lane % CPR
+  const int cr = lane / C::CPR, cc = lane - cr * C::CPR;
+  const bool copier = cr < C::RPI;
+  uint32_t pad_next[PW];
+  auto issue = [&](int64_t item, int slot) {
+#pragma unroll
+    for (int w = 0; w < PW; ++w) pad_next[w] = 1u;
+    if (item < items) {
+      const int b = static_cast<int>(item / H), h = static_cast<int>(item - static_cast<int64_t>(b) * H);
+      if (copier) {
+        const __nv_bfloat16* ks = k + (static_cast<int64_t>(b) * Tk + cr) * ldk + h * DH + cc * 8;
+        const __nv_bfloat16* vs = v + (static_cast<int64_t>(b) * Tk + cr) * ldv + h * DH + cc * 8;
+        uint32_t dst = ring + slot * C::SLOT + cr * C::PITCH + cc * 16;
+        for (int r = cr; r < Tk; r += C::RPI) {
+          cp_async16(dst, ks);
+          cp_async16(dst + C::TKP * C::PITCH, vs);
+          ks += C::RPI * ldk;
+          vs += C::RPI * ldv;
+          dst += C::RPI * C::PITCH;
+        }
+        const __nv_bfloat16* qs = q + (static_cast<int64_t>(b) * Nq + cr) * ldq + h * DH + cc * 8;
+        dst = ring + slot * C::SLOT + (2 * C::TKP + cr) * C::PITCH + cc * 16;
+        for (int r = cr; r < Nq; r += C::RPI) {
+          cp_async16(dst, qs);
+          qs += C::RPI * ldq;
+          dst += C::RPI * C::PITCH;
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < PW; ++w) {
+        const int j = w * 32 + lane;
+        pad_next[w] = j >= Tk ? 1u : (key_pad != nullptr ? static_cast<uint32_t>(__ldg(key_pad + static_cast<int64_t>(b) * Tk + j)) : 0u);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int64_t item = static_cast<int64_t>(blockIdx.x) * C::WARPS + warp;
+  int slot = 0;
+  issue(item, 0);
+  while (item < items) {
+    uint32_t padw[PW];
+#pragma unroll
+    for (int w = 0; w < PW; ++w) padw[w] = __ballot_sync(0xffffffffu, pad_next[w] != 0u);
+    __syncwarp();   // every lane is done reading slot ^ 1 (the previous item)
+    issue(item + stride, slot ^ 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    const int b = static_cast<int>(item / H), h = static_cast<int>(item - static_cast<int64_t>(b) * H);
+    const uint32_t sK = ring + slot * C::SLOT, sV = sK + C::TKP * C::PITCH, sQ = sV + C::TKP * C::PITCH;
+    // ---- S = Q K^T: M = queries (rows g), N = keys, K = dh
+    float s[KT][4];
+#pragma unroll
+    for (int nt = 0; nt < KT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+    const int mi = lane >> 3, mr = lane & 7;
+#pragma unroll
+    for (int ks = 0; ks < DH / 16; ++ks) {
+      uint32_t a0, a2;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(a0) : "r"(sQ + g * C::PITCH + (ks * 16 + 2 * t4) * 2) : "memory");
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(a2) : "r"(sQ + g * C::PITCH + (ks * 16 + 8 + 2 * t4) * 2) : "memory");
+#pragma unroll
+      for (int nt = 0; nt < KT; nt += 2) {
+        uint32_t r0, r1, r2, r3;
+        da_ldsm_x4(r0, r1, r2, r3, sK + ((nt + (mi >> 1)) * 8 + mr) * C::PITCH + (ks * 16 + (mi & 1) * 8) * 2);
+        da_mma(s[nt], a0, a2, r0, r1);
+        da_mma(s[nt + 1], a0, a2, r2, r3);
+      }
+    }
+    // ---- softmax of row g over the keys of this lane's quad (keys nt * 8 + 2 t4 + e)
+    float m = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < KT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = nt * 8 + 2 * t4 + e;
+        const bool masked = (padw[nt >> 2] >> (j & 31)) & 1u;
+        s[nt][e] = masked ? -INFINITY : s[nt][e] * scale;
+        m = fmaxf(m, s[nt][e]);
+      }
+    }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    float sum = 0.0f;
+#pragma unroll
+    for (int nt = 0; nt < KT; ++nt) {
+      s[nt][0] = expf(s[nt][0] - m);
+      s[nt][1] = expf(s[nt][1] - m);
+      sum += s[nt][0] + s[nt][1];
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = 1.0f / sum;
+    // P as bf16 hi + lo (two MMAs per tile: the tensor core is idle anyway, and the decoder's outputs keep the
+    // accuracy of the fp32-probability form this kernel replaces)
+    uint32_t pa[KT], pl[KT];
+#pragma unroll
+    for (int nt = 0; nt < KT; ++nt) {
+      const float p0 = s[nt][0] * inv, p1 = s[nt][1] * inv;
+      pa[nt] = pack_bf16(p0, p1);
+      pl[nt] = pack_bf16(p0 - bf16_lo(pa[nt]), p1 - bf16_hi(pa[nt]));
+    }
+    // ---- O = P V: M = queries, N = dh, K = keys
+    float o[DH / 8][4];
+#pragma unroll
+    for (int ct = 0; ct < DH / 8; ++ct) o[ct][0] = o[ct][1] = o[ct][2] = o[ct][3] = 0.0f;
+#pragma unroll
+    for (int kk = 0; kk < KT / 2; ++kk) {
+#pragma unroll
+      for (int ct = 0; ct < DH / 8; ct += 2) {
+        uint32_t r0, r1, r2, r3;
+        da_ldsm_x4_trans(r0, r1, r2, r3, sV + (kk * 16 + (mi & 1) * 8 + mr) * C::PITCH + (ct + (mi >> 1)) * 16);
+        da_mma(o[ct], pa[2 * kk], pa[2 * kk + 1], r0, r1);
+        da_mma(o[ct + 1], pa[2 * kk], pa[2 * kk + 1], r2, r3);
+        da_mma(o[ct], pl[2 * kk], pl[2 * kk + 1], r0, r1);
+        da_mma(o[ct + 1], pl[2 * kk], pl[2 * kk + 1], r2, r3);
+      }
+    }
+    if (g < Nq) {
+      __nv_bfloat16* orow = out + (static_cast<int64_t>(b) * Nq + g) * ldo + h * DH + 2 * t4;
+#pragma unroll
+      for (int ct = 0; ct < DH / 8; ++ct) *reinterpret_cast<uint32_t*>(orow + ct * 8) = pack_bf16(o[ct][0], o[ct][1]);
+    }
+    item += stride;
+    slot ^= 1;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ small attention, backward (training)
 // Gradients of the decoder attention (models/emotion_decoder.py:42, :48-54; N_q learned queries, T_k keys) for one
 // (utterance, head) per CTA.  P is rebuilt from q, k (exact softmax, as in the forward); then
@@ -429,8 +620,39 @@ static int launch_small_attention(const void* q, int64_t ldq, const void* k, int
                                   int64_t ldv, const uint8_t* key_pad, void* out, int64_t ldo, float* probs,
                                   int B, int H, int Nq, int Tk, int dh, float scale, cudaStream_t s, uint32_t drop_p8 = 0,
                                   uint32_t drop_key = 0, float drop_scale = 1.0f) {
-  if (drop_p8 == 0u && probs == nullptr && out != nullptr && v != nullptr && Nq <= SA_NQ && Tk <= DA_MAX_TK && dh <= 128 && H <= 65535 &&
-      ldv % 8 == 0 && ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(v) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
+  const bool decoder_shape = drop_p8 == 0u && probs == nullptr && out != nullptr && v != nullptr && Nq <= SA_NQ && Tk <= DA_MAX_TK &&
+                             dh <= 128 && ldv % 8 == 0 && ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(v) & 15u) == 0 &&
+                             (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
+  static const bool force_v1 = getenv("HRIEMO_DECODER_ATTN_V1") != nullptr;   // the CTA-per-(utterance, head) form, for A / B runs
+  if (decoder_shape && !force_v1 && (dh == 64 || dh == 96 || dh == 128) && ldq % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(q) & 15u) == 0) {
+    // warp-private ring + mma.sync (decoder_attention_mma_kernel)
+    using bf = __nv_bfloat16;
+    cudaError_t e = cudaSuccess;
+    const int64_t items = static_cast<int64_t>(B) * H;
+#define HRIEMO_DA_LAUNCH(DHV, KTV)                                                                                          \
+    do {                                                                                                                    \
+      using C = DecAttn<DHV, KTV>;                                                                                          \
+      constexpr int smem_bytes = C::WARPS * 2 * C::SLOT;                                                                    \
+      static uint64_t attr_done = 0;                                                                                        \
+      if (device_needs_attr(&attr_done))                                                                                    \
+        e = cudaFuncSetAttribute(decoder_attention_mma_kernel<DHV, KTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
+      if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "small_attention: %s", cudaGetErrorString(e));               \
+      int64_t grid = (items + C::WARPS - 1) / C::WARPS;                                                                     \
+      if (grid > device_sm_count()) grid = device_sm_count();                                                               \
+      decoder_attention_mma_kernel<DHV, KTV><<<static_cast<unsigned>(grid), C::WARPS * 32, smem_bytes, s>>>(                \
+          static_cast<const bf*>(q), ldq, static_cast<const bf*>(k), ldk, static_cast<const bf*>(v), ldv, key_pad,          \
+          static_cast<bf*>(out), ldo, B, H, Nq, Tk, scale);                                                                 \
+    } while (0)
+    if (Tk <= 64) {
+      if (dh == 64) HRIEMO_DA_LAUNCH(64, 8); else if (dh == 96) HRIEMO_DA_LAUNCH(96, 8); else HRIEMO_DA_LAUNCH(128, 8);
+    } else {
+      if (dh == 64) HRIEMO_DA_LAUNCH(64, 16); else if (dh == 96) HRIEMO_DA_LAUNCH(96, 16); else HRIEMO_DA_LAUNCH(128, 16);
+    }
+#undef HRIEMO_DA_LAUNCH
+    return check_launch("small_attention");
+  }
+  if (decoder_shape && H <= 65535) {
     // the decoder's own shapes: K / V staged in shared memory (see decoder_attention_kernel)
     const size_t sm = static_cast<size_t>(2) * Tk * (dh + 8) * 2 + sizeof(float) * (static_cast<size_t>(SA_NQ) * dh + static_cast<size_t>(SA_NQ) * Tk);
     static uint64_t da_attr_done = 0;

@@ -142,14 +142,16 @@ class Trainer:
         grads = out.pop("grads")
         if set(grads) != set(self.slots):
             raise L.HriemoError(f"Trainer: gradient names do not match the parameters: {sorted(set(grads) ^ set(self.slots))[:6]}")
-        for name, (o, n) in self.slots.items():        # device-to-device copies into the arena
-            dst, g = self.grads[o:o + n], grads[name].reshape(-1)
-            if accumulate:
-                dst.add_(g, alpha=scale)
-            elif scale != 1.0:
-                torch.mul(g, scale, out=dst)
-            else:
-                dst.copy_(g)
+        # device-to-device into the arena: ONE multi-tensor launch per dtype group instead of one copy per parameter
+        # (119 launches of a few microseconds each inside the step)
+        dsts = [self.grads[o:o + n] for (o, n) in self.slots.values()]
+        srcs = [grads[name].reshape(-1) for name in self.slots]
+        if accumulate:
+            torch._foreach_add_(dsts, srcs, alpha=scale)
+        else:
+            torch._foreach_copy_(dsts, srcs)
+            if scale != 1.0:
+                torch._foreach_mul_(dsts, scale)
         return out
 
     def _graphed_forward_backward(self, h_a, h_t, mask_a, mask_t, labels) -> dict:
