@@ -810,15 +810,161 @@ layernorm_backward_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, cons
   }
 }
 
+// The same, streaming form (default): one persistent CTA per SM, rows reach a warp through a private cp.async ring of
+// (x | dy) row pairs (STAGES - 1 pairs = 15 KB in flight per warp at d = 768; the kernel above has one pair per warp in
+// flight and nothing to overlap its ~600 instructions per row with: 0.5 of the HBM roofline), arithmetic in packed fp32.
+template <int NV>
+__global__ void __launch_bounds__(256, 1)
+layernorm_backward_ring_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ dy,
+                               int64_t lddy, const float* __restrict__ gamma, float eps, __nv_bfloat16* __restrict__ dx,
+                               int64_t lddx, float* __restrict__ partial, int64_t rows, int d) {
+  constexpr int STAGES = GbStages<NV>::value;
+  constexpr int PAIR_BYTES = 2 * NV * 512;
+  extern __shared__ __align__(16) uint8_t lnb_smem[];   // ring [8 warps][STAGES][x | dy][NV * 32 lanes][16 B]; later part[8][2][d]
+  float* part = reinterpret_cast<float*>(lnb_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* ring_p = lnb_smem + warp * (STAGES * PAIR_BYTES) + lane * 16;
+  const uint32_t ring = smem_u32(ring_p);
+  float2 g_acc[NV][4], b_acc[NV][4], gm[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      g_acc[i][k] = b_acc[i][k] = make_float2(0.0f, 0.0f);
+      gm[i][k] = c < d ? make_float2(__ldg(gamma + c + 2 * k), __ldg(gamma + c + 2 * k + 1)) : make_float2(0.0f, 0.0f);
+    }
+  }
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * 8;
+  auto issue = [&](int64_t row, int slot) {   // one commit group per call, also when there is nothing left to copy
+    if (row < rows) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        if (c < d) {
+          lmm_cp_async16(ring + slot * PAIR_BYTES + i * 512, x + row * ldx + c);
+          lmm_cp_async16(ring + slot * PAIR_BYTES + (NV + i) * 512, dy + row * lddy + c);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+#pragma unroll
+  for (int s0 = 0; s0 < STAGES - 1; ++s0) issue(row0 + s0 * stride, s0);
+  const float inv_d = 1.0f / static_cast<float>(d);
+  int slot = 0;
+  for (int64_t row = row0; row < rows; row += stride) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+    float2 xv[NV][4], gv[NV][4];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      uint4 u = make_uint4(0u, 0u, 0u, 0u), v = make_uint4(0u, 0u, 0u, 0u);
+      if (c < d) {
+        u = *reinterpret_cast<const uint4*>(ring_p + slot * PAIR_BYTES + i * 512);
+        v = *reinterpret_cast<const uint4*>(ring_p + slot * PAIR_BYTES + (NV + i) * 512);
+      }
+      xv[i][0] = make_float2(bf16_lo(u.x), bf16_hi(u.x)); xv[i][1] = make_float2(bf16_lo(u.y), bf16_hi(u.y));
+      xv[i][2] = make_float2(bf16_lo(u.z), bf16_hi(u.z)); xv[i][3] = make_float2(bf16_lo(u.w), bf16_hi(u.w));
+      gv[i][0] = make_float2(bf16_lo(v.x), bf16_hi(v.x)); gv[i][1] = make_float2(bf16_lo(v.y), bf16_hi(v.y));
+      gv[i][2] = make_float2(bf16_lo(v.z), bf16_hi(v.z)); gv[i][3] = make_float2(bf16_lo(v.w), bf16_hi(v.w));
+    }
+    // the slot consumed in the PREVIOUS iteration takes the row STAGES - 1 strides ahead
+    issue(row + (STAGES - 1) * stride, slot == 0 ? STAGES - 1 : slot - 1);
+    // sum x, sum x^2, sum g, sum g x (g = dy gamma) reduced together; columns past d hold zeros and gm = 0 there
+    float2 sx = make_float2(0.0f, 0.0f), sxx = sx, sg = sx, sgx = sx;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 g = fmul2(gv[i][k], gm[i][k]);
+        sx = fadd2(sx, xv[i][k]);
+        sxx = ffma2(xv[i][k], xv[i][k], sxx);
+        sg = fadd2(sg, g);
+        sgx = ffma2(g, xv[i][k], sgx);
+      }
+    float v1 = sx.x + sx.y, v2 = sxx.x + sxx.y, v3 = sg.x + sg.y, v4 = sgx.x + sgx.y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+      v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+      v4 += __shfl_xor_sync(0xffffffffu, v4, o);
+    }
+    const float mean = v1 * inv_d;
+    const float rstd = rsqrtf(fmaxf(v2 * inv_d - mean * mean, 0.0f) + eps);
+    const float s1 = v3 * inv_d;
+    const float s2 = rstd * (v4 - mean * v3) * inv_d;
+    const float2 r2 = make_float2(rstd, rstd), mr = make_float2(-mean * rstd, -mean * rstd);
+    const float2 a1 = make_float2(-s1 * rstd, -s1 * rstd), a2 = make_float2(-s2 * rstd, -s2 * rstd);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      float2 o2[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 xh = ffma2(xv[i][k], r2, mr);
+        g_acc[i][k] = ffma2(gv[i][k], xh, g_acc[i][k]);
+        b_acc[i][k] = fadd2(b_acc[i][k], gv[i][k]);
+        // rstd (dy gamma - s1 - xhat s2)
+        o2[k] = ffma2(xh, a2, ffma2(fmul2(gv[i][k], gm[i][k]), r2, a1));
+      }
+      if (c < d) {
+        uint4 o;
+        o.x = pack_bf16(o2[0].x, o2[0].y); o.y = pack_bf16(o2[1].x, o2[1].y);
+        o.z = pack_bf16(o2[2].x, o2[2].y); o.w = pack_bf16(o2[3].x, o2[3].y);
+        *reinterpret_cast<uint4*>(dx + row * lddx + c) = o;
+      }
+    }
+    slot = slot + 1 == STAGES ? 0 : slot + 1;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();   // every warp is done with its ring: the memory becomes part[8][2][d]
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < d) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        part[(warp * 2 + 0) * d + c + 2 * k] = g_acc[i][k].x;
+        part[(warp * 2 + 0) * d + c + 2 * k + 1] = g_acc[i][k].y;
+        part[(warp * 2 + 1) * d + c + 2 * k] = b_acc[i][k].x;
+        part[(warp * 2 + 1) * d + c + 2 * k + 1] = b_acc[i][k].y;
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) {
+    const int which = c / d, col = c - which * d;
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[(w * 2 + which) * d + col];
+    partial[static_cast<int64_t>(blockIdx.x) * 2 * d + c] = s;
+  }
+}
+
 // out[0..d) = dgamma, out2[0..d) = dbeta: fixed-order sum of the per-CTA partials (optionally on top of the old value)
-__global__ void ln_param_grad_finalize_kernel(const float* __restrict__ partial, int n_ctas, int d, float* __restrict__ dgamma,
-                                              float* __restrict__ dbeta, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * d) return;
+__global__ void __launch_bounds__(256)
+ln_param_grad_finalize_kernel(const float* __restrict__ partial, int n_ctas, int d, float* __restrict__ dgamma,
+                              float* __restrict__ dbeta, int accumulate) {
+  // 32 columns per CTA; the 8 warps each sum every 8th partial (coalesced 128-byte reads), then a fixed-order sum of the
+  // 8 warp sums through shared memory: deterministic, and 1 / 8 of the serial chain of the thread-per-column loop
+  __shared__ float wsum[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 32 + lane;
   float s = 0.0f;
-  for (int i = 0; i < n_ctas; ++i) s += partial[static_cast<int64_t>(i) * 2 * d + c];
-  float* dst = c < d ? dgamma + c : dbeta + (c - d);
-  *dst = (accumulate ? *dst : 0.0f) + s;
+  if (c < 2 * d)
+    for (int i = warp; i < n_ctas; i += 8) s += partial[static_cast<int64_t>(i) * 2 * d + c];
+  wsum[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && c < 2 * d) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += wsum[w][lane];
+    float* dst = c < d ? dgamma + c : dbeta + (c - d);
+    *dst = (accumulate ? *dst : 0.0f) + t;
+  }
 }
 
 // dx = dy where h > 0 else 0 (h = the ReLU's OUTPUT, which is what the forward keeps): 8 elements per thread
@@ -1046,6 +1192,31 @@ extern "C" int hriemo_layernorm_backward(const void* x, int64_t ldx, const void*
   const __nv_bfloat16 *xp = static_cast<const __nv_bfloat16*>(x), *gp = static_cast<const __nv_bfloat16*>(dy);
   __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(dx);
   const int nv = (d + 255) / 256;
+  static const bool force_v1 = getenv("HRIEMO_LN_BWD_V1") != nullptr;   // the one-row-per-warp form, for A / B runs
+  if (!force_v1) {
+    // streaming form: one persistent CTA per SM, warp-private (x | dy) rings (layernorm_backward_ring_kernel)
+    static uint64_t lnb_attr_done = 0;
+    if (device_needs_attr(&lnb_attr_done)) {
+      cudaError_t e = cudaSuccess;
+#define HRIEMO_LNB_ATTR(NVV)                                                                                         \
+      if (e == cudaSuccess)                                                                                          \
+        e = cudaFuncSetAttribute(layernorm_backward_ring_kernel<NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                 8 * GbStages<NVV>::value * 2 * NVV * 512)
+      HRIEMO_LNB_ATTR(1); HRIEMO_LNB_ATTR(2); HRIEMO_LNB_ATTR(3); HRIEMO_LNB_ATTR(4);
+#undef HRIEMO_LNB_ATTR
+      if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "layernorm_backward: %s", cudaGetErrorString(e));
+    }
+    const int rctas = ctas < device_sm_count() ? ctas : device_sm_count();   // the workspace holds ln_backward_ctas(rows) >= rctas partials
+#define HRIEMO_LNB_LAUNCH(NVV)                                                                                       \
+    layernorm_backward_ring_kernel<NVV><<<rctas, 256, 8 * GbStages<NVV>::value * 2 * NVV * 512, s>>>(xp, ldx, gp, lddy, gamma, eps, dp, \
+                                                                                                     lddx, partial, rows, d)
+    if (nv <= 1) HRIEMO_LNB_LAUNCH(1); else if (nv == 2) HRIEMO_LNB_LAUNCH(2); else if (nv == 3) HRIEMO_LNB_LAUNCH(3); else HRIEMO_LNB_LAUNCH(4);
+#undef HRIEMO_LNB_LAUNCH
+    int rc = check_launch("layernorm_backward");
+    if (rc) return rc;
+    ln_param_grad_finalize_kernel<<<(2 * d + 31) / 32, 256, 0, s>>>(partial, rctas, d, dgamma, dbeta, accumulate);
+    return check_launch("layernorm_backward (parameter gradients)");
+  }
   if (smem > 48 * 1024) {
     cudaFuncSetAttribute(layernorm_backward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4);
   }
@@ -1055,7 +1226,7 @@ extern "C" int hriemo_layernorm_backward(const void* x, int64_t ldx, const void*
   else layernorm_backward_kernel<4><<<ctas, 256, smem, s>>>(xp, ldx, gp, lddy, gamma, eps, dp, lddx, partial, rows, d);
   int rc = check_launch("layernorm_backward");
   if (rc) return rc;
-  ln_param_grad_finalize_kernel<<<(2 * d + 255) / 256, 256, 0, s>>>(partial, ctas, d, dgamma, dbeta, accumulate);
+  ln_param_grad_finalize_kernel<<<(2 * d + 31) / 32, 256, 0, s>>>(partial, ctas, d, dgamma, dbeta, accumulate);
   return check_launch("layernorm_backward (parameter gradients)");
 }
 

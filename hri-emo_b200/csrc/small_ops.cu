@@ -599,6 +599,164 @@ small_attention_backward_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq
   }
 }
 
+// The same gradients with the head's K and V tiles staged in shared memory (the decoder's shapes: T_k <= 128).  The kernel
+// above reads each key row element by element from global memory, one row per thread (32 sectors per 2-byte warp load), and
+// runs dQ on N_q * dh threads over all keys: 362 us per 512-utterance cross-attention call for ~200 MB (0.09 of HBM, ncu
+// training launch list v20).  Here: 16-byte cp.async copies of K | V (coalesced, issued back to back), two threads per key
+// for S and dP (halves of dh, combined by one shuffle), 16-byte vector reads of the staged rows, dV / dK written as 16-byte
+// chunks (thread per (key, chunk)), dQ as thread per (query, column pair) over the staged K.
+constexpr int DB_THREADS = 128;
+
+__global__ void __launch_bounds__(DB_THREADS)
+decoder_attention_backward_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k,
+                                  int64_t ldk, const __nv_bfloat16* __restrict__ v, int64_t ldv,
+                                  const __nv_bfloat16* __restrict__ dout, int64_t lddo, const uint8_t* __restrict__ key_pad,
+                                  __nv_bfloat16* __restrict__ dq, int64_t lddq, __nv_bfloat16* __restrict__ dk, int64_t lddk,
+                                  __nv_bfloat16* __restrict__ dv, int64_t lddv, int H, int Nq, int Tk, int dh, float scale,
+                                  uint32_t drop_p8, uint32_t drop_key, float drop_scale) {
+  extern __shared__ __align__(16) uint8_t db_smem[];
+  const int pitch = (dh + 8) * 2;                            // bytes per staged row
+  const int cpr = dh / 8;                                    // 16-byte chunks per row
+  uint8_t* Ks = db_smem;                                     // [Tk][dh + 8] bf16
+  uint8_t* Vs = Ks + static_cast<size_t>(Tk) * pitch;
+  float* qs = reinterpret_cast<float*>(Vs + static_cast<size_t>(Tk) * pitch);   // [SA_NQ][dh]  q * scale
+  float* dos = qs + SA_NQ * dh;         // [SA_NQ][dh]  dO
+  float* ps = dos + SA_NQ * dh;         // [SA_NQ][Tk]  P
+  float* dss = ps + SA_NQ * Tk;         // [SA_NQ][Tk]  dP -> dS
+  float* pms = dss + SA_NQ * Tk;        // [SA_NQ][Tk]  P o M / (1 - p)
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const __nv_bfloat16* kb = k + static_cast<int64_t>(b) * Tk * ldk + h * dh;
+  const __nv_bfloat16* vb = v + static_cast<int64_t>(b) * Tk * ldv + h * dh;
+  const uint32_t ks_u = smem_u32(Ks), vs_u = smem_u32(Vs);
+  for (int i = tid; i < Tk * cpr; i += DB_THREADS) {
+    const int r = i / cpr, c = i - r * cpr;
+    cp_async16(ks_u + r * pitch + c * 16, kb + static_cast<int64_t>(r) * ldk + c * 8);
+    cp_async16(vs_u + r * pitch + c * 16, vb + static_cast<int64_t>(r) * ldv + c * 8);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < SA_NQ * dh; i += DB_THREADS) {
+    const int qi = i / dh, c = i - qi * dh;
+    const bool on = qi < Nq;
+    qs[i] = on ? __bfloat162float(q[(static_cast<int64_t>(b) * Nq + qi) * ldq + h * dh + c]) * scale : 0.0f;
+    dos[i] = on ? __bfloat162float(dout[(static_cast<int64_t>(b) * Nq + qi) * lddo + h * dh + c]) : 0.0f;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // scores and dP = dO . v_j: two threads per key (chunks [0, cpr/2) and [cpr/2, cpr)), combined by one shuffle
+  const int c_half = cpr / 2;
+  for (int j2 = tid; j2 < ((2 * Tk + 31) & ~31); j2 += DB_THREADS) {
+    const int j = j2 >> 1, half = j2 & 1;
+    float s[SA_NQ], dp[SA_NQ];
+#pragma unroll
+    for (int qi = 0; qi < SA_NQ; ++qi) { s[qi] = 0.0f; dp[qi] = 0.0f; }
+    if (j < Tk) {
+      const uint4* kr = reinterpret_cast<const uint4*>(Ks + static_cast<size_t>(j) * pitch);
+      const uint4* vr = reinterpret_cast<const uint4*>(Vs + static_cast<size_t>(j) * pitch);
+      const int c0 = half ? c_half : 0, c1 = half ? cpr : c_half;
+      for (int c = c0; c < c1; ++c) {
+        const uint4 ku = kr[c], vu = vr[c];
+        const float kv[8] = {bf16_lo(ku.x), bf16_hi(ku.x), bf16_lo(ku.y), bf16_hi(ku.y), bf16_lo(ku.z), bf16_hi(ku.z), bf16_lo(ku.w), bf16_hi(ku.w)};
+        const float vv[8] = {bf16_lo(vu.x), bf16_hi(vu.x), bf16_lo(vu.y), bf16_hi(vu.y), bf16_lo(vu.z), bf16_hi(vu.z), bf16_lo(vu.w), bf16_hi(vu.w)};
+#pragma unroll
+        for (int qi = 0; qi < SA_NQ; ++qi) {
+          if (qi < Nq) {
+            const float4 q0 = *reinterpret_cast<const float4*>(qs + qi * dh + c * 8), q1 = *reinterpret_cast<const float4*>(qs + qi * dh + c * 8 + 4);
+            const float4 d0 = *reinterpret_cast<const float4*>(dos + qi * dh + c * 8), d1 = *reinterpret_cast<const float4*>(dos + qi * dh + c * 8 + 4);
+            s[qi] = fmaf(q0.x, kv[0], fmaf(q0.y, kv[1], fmaf(q0.z, kv[2], fmaf(q0.w, kv[3], s[qi]))));
+            s[qi] = fmaf(q1.x, kv[4], fmaf(q1.y, kv[5], fmaf(q1.z, kv[6], fmaf(q1.w, kv[7], s[qi]))));
+            dp[qi] = fmaf(d0.x, vv[0], fmaf(d0.y, vv[1], fmaf(d0.z, vv[2], fmaf(d0.w, vv[3], dp[qi]))));
+            dp[qi] = fmaf(d1.x, vv[4], fmaf(d1.y, vv[5], fmaf(d1.z, vv[6], fmaf(d1.w, vv[7], dp[qi]))));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < SA_NQ; ++qi) {
+      s[qi] += __shfl_xor_sync(0xffffffffu, s[qi], 1);
+      dp[qi] += __shfl_xor_sync(0xffffffffu, dp[qi], 1);
+    }
+    if (j < Tk && half == 0) {
+      const bool pad = key_pad != nullptr && key_pad[static_cast<int64_t>(b) * Tk + j] != 0;
+#pragma unroll
+      for (int qi = 0; qi < SA_NQ; ++qi) {
+        if (qi < Nq) {
+          ps[qi * Tk + j] = pad ? -INFINITY : s[qi];
+          dss[qi * Tk + j] = dp[qi];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // softmax per query row, then dS = P * (dP - sum_j dP_j P_j)  (warp per row)
+  for (int qi = warp; qi < Nq; qi += DB_THREADS / 32) {
+    float m = -INFINITY;
+    for (int j = lane; j < Tk; j += 32) m = fmaxf(m, ps[qi * Tk + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.0f;
+    for (int j = lane; j < Tk; j += 32) {
+      const float e = expf(ps[qi * Tk + j] - m);
+      ps[qi * Tk + j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    float dot = 0.0f;
+    const uint32_t dkey = drop_key_bh(drop_key, static_cast<uint32_t>(b * H + h));
+    for (int j = lane; j < Tk; j += 32) {
+      const float pr = ps[qi * Tk + j] * inv;
+      const float mc = (drop_p8 == 0u || drop_keep(dkey, static_cast<uint32_t>(qi), static_cast<uint32_t>(j), drop_p8)) ? drop_scale : 0.0f;
+      const float dpm = dss[qi * Tk + j] * mc;
+      ps[qi * Tk + j] = pr;
+      pms[qi * Tk + j] = pr * mc;
+      dss[qi * Tk + j] = dpm;
+      dot += pr * dpm;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    for (int j = lane; j < Tk; j += 32) dss[qi * Tk + j] = ps[qi * Tk + j] * (dss[qi * Tk + j] - dot);
+  }
+  __syncthreads();
+  // dV_j = sum_q (P o M c)_qj dO_q ; dK_j = sum_q dS_qj (q_q * scale)   (thread per (key, 8-column chunk), 16-byte stores)
+  for (int i = tid; i < Tk * cpr; i += DB_THREADS) {
+    const int j = i / cpr, c = i - j * cpr;
+    float av[8], ak[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) av[e] = ak[e] = 0.0f;
+#pragma unroll
+    for (int qi = 0; qi < SA_NQ; ++qi) {
+      if (qi < Nq) {
+        const float pm = pms[qi * Tk + j], ds = dss[qi * Tk + j];
+        const float4 d0 = *reinterpret_cast<const float4*>(dos + qi * dh + c * 8), d1 = *reinterpret_cast<const float4*>(dos + qi * dh + c * 8 + 4);
+        const float4 q0 = *reinterpret_cast<const float4*>(qs + qi * dh + c * 8), q1 = *reinterpret_cast<const float4*>(qs + qi * dh + c * 8 + 4);
+        av[0] = fmaf(pm, d0.x, av[0]); av[1] = fmaf(pm, d0.y, av[1]); av[2] = fmaf(pm, d0.z, av[2]); av[3] = fmaf(pm, d0.w, av[3]);
+        av[4] = fmaf(pm, d1.x, av[4]); av[5] = fmaf(pm, d1.y, av[5]); av[6] = fmaf(pm, d1.z, av[6]); av[7] = fmaf(pm, d1.w, av[7]);
+        ak[0] = fmaf(ds, q0.x, ak[0]); ak[1] = fmaf(ds, q0.y, ak[1]); ak[2] = fmaf(ds, q0.z, ak[2]); ak[3] = fmaf(ds, q0.w, ak[3]);
+        ak[4] = fmaf(ds, q1.x, ak[4]); ak[5] = fmaf(ds, q1.y, ak[5]); ak[6] = fmaf(ds, q1.z, ak[6]); ak[7] = fmaf(ds, q1.w, ak[7]);
+      }
+    }
+    uint4 ov, ok;
+    ov.x = pack_bf16(av[0], av[1]); ov.y = pack_bf16(av[2], av[3]); ov.z = pack_bf16(av[4], av[5]); ov.w = pack_bf16(av[6], av[7]);
+    ok.x = pack_bf16(ak[0], ak[1]); ok.y = pack_bf16(ak[2], ak[3]); ok.z = pack_bf16(ak[4], ak[5]); ok.w = pack_bf16(ak[6], ak[7]);
+    *reinterpret_cast<uint4*>(dv + (static_cast<int64_t>(b) * Tk + j) * lddv + h * dh + c * 8) = ov;
+    *reinterpret_cast<uint4*>(dk + (static_cast<int64_t>(b) * Tk + j) * lddk + h * dh + c * 8) = ok;
+  }
+  // dQ_q = scale * sum_j dS_qj k_j   (thread per (query, column pair) over the staged K)
+  for (int i = tid; i < Nq * (dh / 2); i += DB_THREADS) {
+    const int qi = i / (dh / 2), c2 = i - qi * (dh / 2);
+    float a0 = 0.0f, a1 = 0.0f;
+    for (int j = 0; j < Tk; ++j) {
+      const uint32_t kk = *reinterpret_cast<const uint32_t*>(Ks + static_cast<size_t>(j) * pitch + c2 * 4);
+      const float ds = dss[qi * Tk + j];
+      a0 = fmaf(ds, bf16_lo(kk), a0);
+      a1 = fmaf(ds, bf16_hi(kk), a1);
+    }
+    *reinterpret_cast<uint32_t*>(dq + (static_cast<int64_t>(b) * Nq + qi) * lddq + h * dh + c2 * 2) = pack_bf16(a0 * scale, a1 * scale);
+  }
+}
+
 // ------------------------------------------------------------------ post-path outputs
 // probs = sigmoid(logits); decisions = probs >= threshold[class] (per-class calibrated thresholds,
 // or 0.5 when none are given: equivalent to logit > 0 up to the tie at 0).
@@ -764,6 +922,23 @@ static int launch_small_attention_backward(const void* q, int64_t ldq, const voi
     if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "small_attention_backward: %s", cudaGetErrorString(e));
   }
   using bf = __nv_bfloat16;
+  static const bool force_v1 = getenv("HRIEMO_DECODER_ATTN_BWD_V1") != nullptr;   // the unstaged form, for A / B runs
+  auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & m) == 0; };
+  if (!force_v1 && Tk <= DA_MAX_TK && dh % 8 == 0 && dh <= 128 && ldk % 8 == 0 && ldv % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 &&
+      lddq % 2 == 0 && al(k, 15) && al(v, 15) && al(dk, 15) && al(dv, 15) && al(dq, 3)) {
+    // K | V staged in shared memory (decoder_attention_backward_kernel)
+    const size_t sm2 = static_cast<size_t>(2) * Tk * (dh + 8) * 2 + sizeof(float) * (2 * static_cast<size_t>(SA_NQ) * dh + 3 * static_cast<size_t>(SA_NQ) * Tk);
+    static uint64_t db_attr_done = 0;
+    if (device_needs_attr(&db_attr_done)) {
+      cudaError_t e = cudaFuncSetAttribute(decoder_attention_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      if (e != cudaSuccess) return set_error(HRIEMO_ERR_CUDA, "small_attention_backward: %s", cudaGetErrorString(e));
+    }
+    decoder_attention_backward_kernel<<<dim3(B, H), DB_THREADS, sm2, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf*>(q), ldq, static_cast<const bf*>(k), ldk, static_cast<const bf*>(v), ldv,
+        static_cast<const bf*>(d_out), lddo, key_pad, static_cast<bf*>(dq), lddq, static_cast<bf*>(dk), lddk,
+        static_cast<bf*>(dv), lddv, H, Nq, Tk, dh, scale, drop_p8, drop_key, drop_p8 ? drop_scale : 1.0f);
+    return check_launch("small_attention_backward");
+  }
   small_attention_backward_kernel<<<dim3(B, H), SB_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf*>(q), ldq, static_cast<const bf*>(k), ldk, static_cast<const bf*>(v), ldv,
       static_cast<const bf*>(d_out), lddo, key_pad, static_cast<bf*>(dq), lddq, static_cast<bf*>(dk), lddk,

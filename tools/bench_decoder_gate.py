@@ -27,7 +27,7 @@ def timeit(fn, iters=20, warm=3):
 def main():
     dev = "cuda"
     res = []
-    form = "v1" if os.environ.get("HRIEMO_GATE_BLEND_V1") or os.environ.get("HRIEMO_DECODER_ATTN_V1") else "v2"
+    form = "v1" if os.environ.get("HRIEMO_GATE_BLEND_V1") or os.environ.get("HRIEMO_DECODER_ATTN_V1") or os.environ.get("HRIEMO_LN_BWD_V1") or os.environ.get("HRIEMO_DECODER_ATTN_BWD_V1") else "v2"
     # gate blend of the north star: pending LayerNorms with statistics on both streams, bf16 out
     for (B, T_a, L, d) in [(2048, 500, 64, 768), (4096, 300, 128, 256)]:
         g = torch.Generator(device=dev).manual_seed(1)
@@ -49,6 +49,13 @@ def main():
                 gb = B * T_a * d * 2 * frac / 1e9
                 res.append(dict(kernel=name, B=B, T=T_a, d=d, us=ms * 1e3, gbs=gb / ms * 1e3, frac_hbm=gb / ms * 1e3 / PEAK))
                 print(res[-1], flush=True)
+    # LayerNorm backward of one 512-utterance training slab (rows = 512 * 500): x, dy read, dx written
+    for (rows, d) in [(256000, 768), (32768, 768), (614400, 256)]:
+        x = torch.randn(rows, d, device=dev).bfloat16(); dy = torch.randn(rows, d, device=dev).bfloat16(); gam = torch.rand(d, device=dev) + 0.5
+        ms = timeit(lambda: ops.layernorm_backward(x, dy, gam))
+        gb = 3 * rows * d * 2 / 1e9
+        res.append(dict(kernel="layernorm_backward", form="v1" if os.environ.get("HRIEMO_LN_BWD_V1") else "v2", rows=rows, d=d, us=ms * 1e3, gbs=gb / ms * 1e3, frac_hbm=gb / ms * 1e3 / PEAK))
+        print(res[-1], flush=True)
     # decoder attention: cross (4 queries x 64 keys), self (4 x 4), MOSEI (6 x 128, dh 64)
     for (B, H, Nq, Tk, dh) in [(2048, 8, 4, 64, 96), (2048, 8, 4, 4, 96), (4096, 4, 6, 128, 64), (2048, 8, 4, 50, 96)]:
         d = H * dh
@@ -59,6 +66,14 @@ def main():
             gb = (B * Tk * 2 * d * 2 + 2 * B * Nq * d * 2) / 1e9
             res.append(dict(kernel=name, form=form, B=B, H=H, Nq=Nq, Tk=Tk, dh=dh, us=ms * 1e3, gbs=gb / ms * 1e3, frac_hbm=gb / ms * 1e3 / PEAK))
             print(res[-1], flush=True)
+    # decoder attention backward of one 512-utterance training step: cross (4 x 64) and self (4 x 4)
+    for (B, H, Nq, Tk, dh) in [(512, 8, 4, 64, 96), (512, 8, 4, 4, 96)]:
+        d = H * dh
+        q = torch.randn(B * Nq, d, device=dev).bfloat16(); kv = torch.randn(B * Tk, 2 * d, device=dev).bfloat16(); do = torch.randn(B * Nq, d, device=dev).bfloat16()
+        ms = timeit(lambda: ops.small_attention_backward(q, kv[:, :d], kv[:, d:], do, None, B, H, Nq, Tk, dh))
+        gb = (2 * B * Tk * 2 * d * 2 + 3 * B * Nq * d * 2) / 1e9
+        res.append(dict(kernel="decoder_attention_backward", form="v1" if os.environ.get("HRIEMO_DECODER_ATTN_BWD_V1") else "v2", B=B, H=H, Nq=Nq, Tk=Tk, dh=dh, us=ms * 1e3, gbs=gb / ms * 1e3, frac_hbm=gb / ms * 1e3 / PEAK))
+        print(res[-1], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"bench_decoder_gate_{form}.json"), "w"), indent=1)
 
