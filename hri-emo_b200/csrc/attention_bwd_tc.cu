@@ -30,7 +30,8 @@ namespace hriemo {
 
 constexpr int BT_M = 128;        // rows of the CTA's resident tile (UMMA M)
 constexpr int BT_N = 64;         // rows of a step (UMMA N of S / dP, K extent of the accumulating MMAs)
-constexpr int BT_THREADS = 192;  // TMA, MMA, 4 elementwise warps
+constexpr int BT_EW = 8;         // elementwise warps: two per TMEM lane quadrant, each takes 32 of a step's 64 columns
+constexpr int BT_THREADS = 64 + 32 * BT_EW;  // TMA, MMA, the elementwise warps
 
 template <int DH>
 struct BwdSmem {
@@ -138,10 +139,10 @@ attention_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const BwdParams p)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(b_sfull + s * 8, 1);
-      mbar_init(b_edone + s * 8, 4);   // one arrival per elementwise warp
+      mbar_init(b_edone + s * 8, BT_EW);   // one arrival per elementwise warp
     }
     mbar_init(b_accfull, 1);
-    mbar_init(b_accempty, 4);
+    mbar_init(b_accempty, BT_EW);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(base + L::TMEM_SLOT_OFF);
@@ -205,13 +206,17 @@ attention_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const BwdParams p)
         umma_commit(b_sfull + s * 8);
       };
       uint32_t g = 0, ri = 0;
+      bool pre_issued = false;   // the first S | dP of this item went out during the previous item's last step
       for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x, ++ri) {
         int tile, h, b;
         decode(it, tile, h, b);
         const int n_steps = steps_of(b);
-        mbar_wait(b_rfull, ri & 1u);
-        issue_sdp(g);
-        if (n_steps == 1) umma_commit(b_rempty);
+        if (!pre_issued) {
+          mbar_wait(b_rfull, ri & 1u);
+          issue_sdp(g);
+          if (n_steps == 1) umma_commit(b_rempty);
+        }
+        pre_issued = false;
         for (int j = 0; j < n_steps; ++j, ++g) {
           const uint32_t s = g & 1u, par = (g >> 1) & 1u;
           const uint32_t xs = g % L::NSTAGE;
@@ -219,6 +224,17 @@ attention_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const BwdParams p)
           if (j + 1 < n_steps) {
             issue_sdp(g + 1);   // the other accumulator pair: its last readers (step g-1) were issued before
             if (j + 2 == n_steps) umma_commit(b_rempty);   // the item's last S / dP: the resident tiles may be replaced
+          } else if (it + gridDim.x < n_items) {
+            // (v22) last step of the item: look ahead ACROSS the item boundary.  The resident tiles were handed back with
+            // this item's last S | dP, so the producer is already loading the next item's; its first S | dP go into the
+            // other accumulator pair while the elementwise warps are on this step -- the cross-attention shapes have ONE
+            // step per item and ran [S | dP -> elementwise -> accumulate -> drain] strictly one after the other.
+            int tile2, h2, b2;
+            decode(it + gridDim.x, tile2, h2, b2);
+            mbar_wait(b_rfull, (ri + 1u) & 1u);
+            issue_sdp(g + 1);
+            if (steps_of(b2) == 1) umma_commit(b_rempty);
+            pre_issued = true;
           }
           mbar_wait(b_edone + s * 8, par);
           if (j == 0) mbar_wait(b_accempty, (ri & 1u) ^ 1u);   // the previous item's epilogue has read the accumulators
@@ -229,14 +245,14 @@ attention_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const BwdParams p)
             const uint64_t x1_mn = umma_desc_mn_sw128(st + L::X_KM, L::X_CHUNK);
 #pragma unroll
             for (int k = 0; k < BT_N / 16; ++k)    // dV += P^T dO_step
-              umma_bf16_ts(ACC_COL, s * 128u + k * 8, x1_mn + ((k * 16 * 128) >> 4), idesc_acc, (j | k) != 0);
+              umma_bf16_ts(ACC_COL, s * 128u + k * 8 + (k >= 2 ? 16 : 0), x1_mn + ((k * 16 * 128) >> 4), idesc_acc, (j | k) != 0);
 #pragma unroll
             for (int k = 0; k < BT_N / 16; ++k)    // dK += dS^T Q_step
-              umma_bf16_ts(ACC_COL + DH, s * 128u + 64u + k * 8, x0_mn + ((k * 16 * 128) >> 4), idesc_acc, (j | k) != 0);
+              umma_bf16_ts(ACC_COL + DH, s * 128u + 64u + k * 8 + (k >= 2 ? 16 : 0), x0_mn + ((k * 16 * 128) >> 4), idesc_acc, (j | k) != 0);
           } else {
 #pragma unroll
             for (int k = 0; k < BT_N / 16; ++k)    // dQ += dS K_step
-              umma_bf16_ts(ACC_COL, s * 128u + 64u + k * 8, x0_mn + ((k * 16 * 128) >> 4), idesc_acc, (j | k) != 0);
+              umma_bf16_ts(ACC_COL, s * 128u + 64u + k * 8 + (k >= 2 ? 16 : 0), x0_mn + ((k * 16 * 128) >> 4), idesc_acc, (j | k) != 0);
           }
           umma_commit(b_xempty + xs * 8);
         }
@@ -244,7 +260,13 @@ attention_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const BwdParams p)
       }
     }
   } else {
-    // ===================== elementwise warpgroup: one row of the tile per thread =====================
+    // ===================== elementwise warps: one row of the tile per thread, TWO threads per row =====================
+    // (v21) warps 2-5 take columns [0, 32) of every step, warps 6-9 columns [32, 64): with one warp per scheduler a step's
+    // 64 exponentials + dS per thread (~1 800 cycles with the tcgen05.ld / st round trips) were twice the step's ~980
+    // cycles of tensor work.  No exchange is needed between the two (the forward's LSE makes P elementwise); each warp
+    // stores its bf16 P / dS over the first 16 columns of the 32 IT read (columns [0,16) and [32,48) of the accumulator:
+    // the MMA issuer addresses the two K = 32 halves of the A operand separately).
+    const int half = (warp - 2) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int wt = (warp - 2) * 32 + lane;          // thread within the warpgroup
@@ -273,7 +295,7 @@ attention_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const BwdParams p)
         dsc_row = row_valid ? __ldg(dsum_bh + q) * p.scale : 0.0f;
         // (every warp is past the previous item's last step here: its accumulators only completed after all four
         // warps had handed that step over)
-        for (int j = wt; j < n_steps; j += 128) {
+        for (int j = wt; j < n_steps; j += 32 * BT_EW) {
           uint64_t m = 0;
           for (int c = 0; c < BT_N; ++c) {
             const int k = j * BT_N + c;
@@ -281,7 +303,7 @@ attention_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const BwdParams p)
           }
           kmask[j] = m;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * BT_EW) : "memory");
       }
       const float rowmask = row_valid ? 1.0f : 0.0f;
       const float2 rmv = make_float2(rowmask, rowmask);
@@ -301,14 +323,15 @@ attention_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const BwdParams p)
       const float* vsrc = wt < 64 ? lse_bh : dsum_bh;
       const float vmul = wt < 64 ? LOG2E : p.scale;
       auto fetch_vec = [&](int j) {
+        if (wt >= 128) return;   // the first four warps fetch / stash; all eight read
         const int q = j * BT_N + (wt & 63);
         pre = q < p.Tq ? __ldg(vsrc + q) : (wt < 64 ? INFINITY : 0.0f);
       };
-      auto stash_vec = [&](uint32_t gg) { vec[(wt < 64 ? 0 : 128) + (gg & 1u) * 64 + (wt & 63)] = pre * vmul; };
+      auto stash_vec = [&](uint32_t gg) { if (wt < 128) vec[(wt < 64 ? 0 : 128) + (gg & 1u) * 64 + (wt & 63)] = pre * vmul; };
       if (PASS == 0) {
         fetch_vec(0);
         stash_vec(g);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * BT_EW) : "memory");
       }
       for (int j = 0; j < n_steps; ++j, ++g) {
         const uint32_t s = g & 1u, par = (g >> 1) & 1u;
@@ -319,8 +342,7 @@ attention_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const BwdParams p)
         mbar_wait(b_sfull + s * 8, par);
         tc_fence_after_sync();
         const uint32_t t_s = t_row + s * 128u, t_dp = t_s + 64u;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {
           uint32_t vs[32], vd[32];
           tmem_ld32(t_s + half * 32, vs);
           tmem_ld32(t_dp + half * 32, vd);
@@ -376,10 +398,9 @@ attention_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const BwdParams p)
               }
             }
           }
-          // bf16 P over S columns [0, 32), bf16 dS over dP columns [0, 32): both halves land inside the first 32
-          // columns of their accumulator, which are in registers before the first store
-          if (PASS == 0) tmem_st16(t_s + half * 16, pp);
-          tmem_st16(t_dp + half * 16, pd);
+          // bf16 P over the first 16 of the 32 S columns this warp read, bf16 dS likewise over dP: in registers before the store
+          if (PASS == 0) tmem_st16(t_s + half * 32, pp);
+          tmem_st16(t_dp + half * 32, pd);
         }
         tmem_st_wait();
         tc_fence_before_sync();
@@ -387,7 +408,7 @@ attention_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const BwdParams p)
         if (lane == 0) mbar_arrive(b_edone + s * 8);
         if (PASS == 0 && j + 1 < n_steps) {
           stash_vec(g + 1);                                        // (that buffer was last read in step g-1)
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * BT_EW) : "memory");
         }
       }
       // ---- epilogue: accumulators -> registers (then the MMA issuer may start the next item) -> bf16 -> global
@@ -395,33 +416,40 @@ attention_bwd_tc_kernel(const __grid_constant__ BwdMaps maps, const BwdParams p)
       tc_fence_after_sync();
       const int t_out = PASS == 0 ? p.Tk : p.Tq;
       const bool store = row0 + row < t_out;
+      // the two warps of a lane quadrant share the accumulators' columns: 32-column chunks dealt alternately
       constexpr int N_ACC = PASS == 0 ? 2 : 1;
+      constexpr int N_CHUNK = N_ACC * (DH / 32);
+      bool arrived = false;
 #pragma unroll
-      for (int a = 0; a < N_ACC; ++a) {
+      for (int ch = 0; ch < N_CHUNK; ++ch) {
+        if ((ch & 1) != half) continue;
+        const int a = ch / (DH / 32), c0 = (ch % (DH / 32)) * 32;
         __nv_bfloat16* dst = (a == 0 ? p.out0 : p.out1) +
                              (static_cast<int64_t>(b) * t_out + row0 + row) * (a == 0 ? p.ld0 : p.ld1) + h * DH;
+        uint32_t v[32];
+        tmem_ld32(t_row + ACC_COL + a * DH + c0, v);
+        tmem_ld_wait();
+        if (ch + 2 >= N_CHUNK) {     // this warp's last accumulator columns are in registers
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_accempty);
+          arrived = true;
+        }
+        if (store) {
 #pragma unroll
-        for (int c0 = 0; c0 < DH; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_row + ACC_COL + a * DH + c0, v);
-          tmem_ld_wait();
-          if (a == N_ACC - 1 && c0 + 32 >= DH) {     // the last accumulator column is in registers
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(b_accempty);
-          }
-          if (store) {
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-              uint4 o;
-              o.x = pack_bf16(__uint_as_float(v[g4 * 8 + 0]), __uint_as_float(v[g4 * 8 + 1]));
-              o.y = pack_bf16(__uint_as_float(v[g4 * 8 + 2]), __uint_as_float(v[g4 * 8 + 3]));
-              o.z = pack_bf16(__uint_as_float(v[g4 * 8 + 4]), __uint_as_float(v[g4 * 8 + 5]));
-              o.w = pack_bf16(__uint_as_float(v[g4 * 8 + 6]), __uint_as_float(v[g4 * 8 + 7]));
-              *reinterpret_cast<uint4*>(dst + c0 + g4 * 8) = o;
-            }
+          for (int g4 = 0; g4 < 4; ++g4) {
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(v[g4 * 8 + 0]), __uint_as_float(v[g4 * 8 + 1]));
+            o.y = pack_bf16(__uint_as_float(v[g4 * 8 + 2]), __uint_as_float(v[g4 * 8 + 3]));
+            o.z = pack_bf16(__uint_as_float(v[g4 * 8 + 4]), __uint_as_float(v[g4 * 8 + 5]));
+            o.w = pack_bf16(__uint_as_float(v[g4 * 8 + 6]), __uint_as_float(v[g4 * 8 + 7]));
+            *reinterpret_cast<uint4*>(dst + c0 + g4 * 8) = o;
           }
         }
+      }
+      if (!arrived) {                // (a single chunk, dh = 32 in pass 1: the second warp has nothing to read)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_accempty);
       }
     }
   }

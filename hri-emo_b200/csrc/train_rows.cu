@@ -12,6 +12,7 @@
 #include <cuda_bf16.h>
 
 #include "host_common.h"
+#include "sm100_ptx.cuh"
 
 namespace hriemo {
 
@@ -163,40 +164,41 @@ gate_stream_grad_kernel(const __nv_bfloat16* __restrict__ dh, int64_t lddh, int 
                         int one_minus, const float* __restrict__ dpool, const uint8_t* __restrict__ pad,
                         const float* __restrict__ inv_cnt, __nv_bfloat16* __restrict__ dn, int64_t lddn, int64_t B,
                         int T, int d) {
+  // warp per row (one 64-bit division per ROW, 16-byte loads of w / dpool; the thread-per-chunk form spent its time
+  // in two 64-bit divisions and sixteen scalar loads per 16 bytes written: 0.25 of the HBM roofline)
   const int chunks = d / 8;
-  const int64_t total = B * T * chunks;
-  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t row = idx / chunks;
-    const int c = static_cast<int>(idx - row * chunks) * 8;
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = B * T;
+  for (int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+       row += static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5)) {
     const int64_t b = row / T;
     const int l = static_cast<int>(row - b * T);
-    float o[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = 0.0f;
-    if (l < L) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(dh + (b * L + l) * lddh + c));
-      const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 g = __bfloat1622float2(p[k]);
-        float w0 = w[b * d + c + 2 * k], w1 = w[b * d + c + 2 * k + 1];
-        if (one_minus) { w0 = 1.0f - w0; w1 = 1.0f - w1; }
-        o[2 * k] = w0 * g.x;
-        o[2 * k + 1] = w1 * g.y;
-      }
-    }
+    const bool blend = l < L;
     const bool valid = pad == nullptr || pad[b * T + l] == 0;
-    if (valid) {
-      const float s = inv_cnt[b];
+    const float s = valid ? inv_cnt[b] : 0.0f;
+    for (int ci = lane; ci < chunks; ci += 32) {
+      const int c = ci * 8;
+      float o[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = fmaf(dpool[b * d + c + k], s, o[k]);
+      for (int k = 0; k < 8; ++k) o[k] = 0.0f;
+      if (blend) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(dh + (b * L + l) * lddh + c));
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(w + b * d + c)), wb = __ldg(reinterpret_cast<const float4*>(w + b * d + c + 4));
+        float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        const float g[8] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y), bf16_lo(raw.z), bf16_hi(raw.z), bf16_lo(raw.w), bf16_hi(raw.w)};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = (one_minus ? 1.0f - wv[k] : wv[k]) * g[k];
+      }
+      if (valid) {
+        const float4 pa = __ldg(reinterpret_cast<const float4*>(dpool + b * d + c)), pb = __ldg(reinterpret_cast<const float4*>(dpool + b * d + c + 4));
+        const float pv[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(pv[k], s, o[k]);
+      }
+      uint4 outv;
+      outv.x = pack_bf16(o[0], o[1]); outv.y = pack_bf16(o[2], o[3]); outv.z = pack_bf16(o[4], o[5]); outv.w = pack_bf16(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dn + row * lddn + c) = outv;
     }
-    uint4 outv;
-    __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&outv);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) q[k] = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
-    *reinterpret_cast<uint4*>(dn + row * lddn + c) = outv;
   }
 }
 
@@ -295,7 +297,7 @@ extern "C" int hriemo_gate_stream_grad(const void* dh, int64_t lddh, int32_t L, 
                                        int64_t lddn, int32_t B, int32_t T, int32_t d, void* stream) {
   HRIEMO_REQUIRE(dh && w && dpool && inv_counts && dn && B > 0 && T > 0 && L > 0 && L <= T && d > 0 && d % 8 == 0,
                  "gate_stream_grad: bad shape (B=%d, T=%d, L=%d, d=%d)", B, T, L, d);
-  HRIEMO_REQUIRE(lddh % 8 == 0 && lddn % 8 == 0 && al16(dh) && al16(dn), "gate_stream_grad: misaligned operand");
+  HRIEMO_REQUIRE(lddh % 8 == 0 && lddn % 8 == 0 && al16(dh) && al16(dn) && al16(w) && al16(dpool), "gate_stream_grad: misaligned operand");
   using bf = __nv_bfloat16;
   gate_stream_grad_kernel<<<flat_grid_rows(static_cast<int64_t>(B) * T * (d / 8)), 256, 0,
                             static_cast<cudaStream_t>(stream)>>>(static_cast<const bf*>(dh), lddh, L, w, one_minus, dpool,

@@ -67,7 +67,10 @@ def gate_forward_train(gate, a: E.Seq, t: E.Seq, mask_a, mask_t) -> Tuple[E.Seq,
     a_pool = ops.ln_masked_mean(na, None, None, mask_a, a.B, a.T, apply_ln=False)              # :83
     t_pool = ops.ln_masked_mean(nt, None, None, mask_t, t.B, t.T, apply_ln=False)              # :84
     g = ops.gate_input(a_pool, t_pool)                                                         # :87-89
-    hid = ops.sgemm(g, P["w0"], P["b0"], L.ACT_RELU)
+    if "w0_3" in P:   # layer 1 on the split-operand tcgen05 GEMM, as in inference (beta within 1e-7 of the fp32 FMA loop)
+        hid = torch.relu(ops.gemm(ops.split3(g), P["w0_3"], P["b0"], L.EPI_BIAS_F32))          # relu keeps NaN
+    else:
+        hid = ops.sgemm(g, P["w0"], P["b0"], L.ACT_RELU)
     w = ops.sgemm(hid, P["w2"], P["b2"], L.ACT_SIGMOID)                                        # :92
     hb, _, beta = ops.gate_blend(na, a.T, nt, None, None, w, a.B, t.T, apply_ln=False)         # :95-116
     tape = dict(a=a, t=t, na=na, nt=nt, a_pool=a_pool, t_pool=t_pool, g=g, hid=hid, w=w, mask_a=mask_a, mask_t=mask_t)
