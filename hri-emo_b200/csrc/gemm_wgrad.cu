@@ -363,6 +363,29 @@ __global__ void sum_partials_kernel(const float* __restrict__ partials, int spli
   }
 }
 
+// The dW and db sums of one wgrad call in ONE launch: the last ceil(n1 / 256) CTAs take the bias partials (one column per
+// thread), the others walk the dW partials grid-stride.  (Two launches per call were ~50 launches of 7 - 14 us per step.)
+__global__ void sum_partials2_kernel(const float* __restrict__ p0, int splits0, int64_t n0, float* __restrict__ out0,
+                                     const float* __restrict__ p1, int splits1, int n1, float* __restrict__ out1,
+                                     int accumulate) {
+  const int ctas1 = (n1 + static_cast<int>(blockDim.x) - 1) / static_cast<int>(blockDim.x);
+  const int ctas0 = static_cast<int>(gridDim.x) - ctas1;
+  if (static_cast<int>(blockIdx.x) >= ctas0) {
+    const int i = (static_cast<int>(blockIdx.x) - ctas0) * static_cast<int>(blockDim.x) + static_cast<int>(threadIdx.x);
+    if (i >= n1) return;
+    float acc = accumulate ? out1[i] : 0.0f;
+    for (int s = 0; s < splits1; ++s) acc += p1[static_cast<int64_t>(s) * n1 + i];
+    out1[i] = acc;
+    return;
+  }
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n0;
+       i += static_cast<int64_t>(ctas0) * blockDim.x) {
+    float acc = accumulate ? out0[i] : 0.0f;
+    for (int s = 0; s < splits0; ++s) acc += p0[static_cast<int64_t>(s) * n0 + i];
+    out0[i] = acc;
+  }
+}
+
 // out[c][r] = in[r][c] for a bf16 matrix (weights: [N,K] -> [K,N], the operand of dX = dY . W)
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld_in, __nv_bfloat16* __restrict__ out,
@@ -499,11 +522,13 @@ extern "C" int hriemo_linear_wgrad_bf16(const void* dY, int64_t lddy, const void
   int64_t gb = (nk + 255) / 256;
   if (gb > static_cast<int64_t>(device_sm_count()) * 8) gb = static_cast<int64_t>(device_sm_count()) * 8;
   const unsigned g = static_cast<unsigned>(gb);
-  sum_partials_kernel<<<g, 256, 0, s>>>(partials, splits, nk, dW, accumulate);
-  rc = check_launch("linear_wgrad (reduce)");
-  if (rc || db == nullptr) return rc;
-  sum_partials_kernel<<<(N + 255) / 256, 256, 0, s>>>(bpart, static_cast<int>(wgrad_colsum_rows_count(splits, K, bnk)), N, db, accumulate);
-  return check_launch("linear_wgrad (bias reduce)");
+  if (db == nullptr) {
+    sum_partials_kernel<<<g, 256, 0, s>>>(partials, splits, nk, dW, accumulate);
+    return check_launch("linear_wgrad (reduce)");
+  }
+  sum_partials2_kernel<<<g + static_cast<unsigned>((N + 255) / 256), 256, 0, s>>>(
+      partials, splits, nk, dW, bpart, static_cast<int>(wgrad_colsum_rows_count(splits, K, bnk)), N, db, accumulate);
+  return check_launch("linear_wgrad (reduce, with bias)");
 }
 
 extern "C" int hriemo_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int32_t rows, int32_t cols,
