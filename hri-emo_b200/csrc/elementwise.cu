@@ -226,6 +226,9 @@ ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const fl
   constexpr int ROW_BYTES = NV * 512;
   extern __shared__ __align__(16) uint8_t lmm_smem[];   // ring [8 warps][STAGES][NV * 32 lanes][16 B]; later part[8][d]
   float* part = reinterpret_cast<float*>(lmm_smem);
+  // the pending LayerNorm's (mean, rstd) of a row travel with the row: an 8-byte cp.async per stage.  (Fetched with a
+  // plain load at the point of use they were a dependent ~1 000-cycle DRAM round trip in every row's chain: 0.50 of HBM.)
+  __shared__ __align__(8) float2 lmm_stats[LMM_WARPS][8];
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring = smem_u32(lmm_smem) + warp * (STAGES * ROW_BYTES) + lane * 16;
@@ -244,8 +247,20 @@ ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const fl
   }
   int count = 0;
   float side = 0.0f;   // sum over rows of m_t * rstd_t (subtracted from every column at the end)
+  // the utterance's PAD bytes in shared memory (read from global memory they were one dependent L2 round trip per row in
+  // the issue chain of a masked batch); longer sequences keep reading global memory
+  __shared__ uint8_t lmm_pad[2048];
+  const bool pad_smem = pad != nullptr && T <= 2048;
+  if (pad_smem) {
+    for (int i = threadIdx.x; i < T; i += blockDim.x) lmm_pad[i] = pad[static_cast<int64_t>(b) * T + i];
+    __syncthreads();
+  }
   auto next_valid = [&](int t) {
-    while (t < T && pad != nullptr && pad[static_cast<int64_t>(b) * T + t] != 0) t += LMM_WARPS;   // warp-uniform
+    if (pad_smem) {
+      while (t < T && lmm_pad[t] != 0) t += LMM_WARPS;   // warp-uniform
+    } else {
+      while (t < T && pad != nullptr && pad[static_cast<int64_t>(b) * T + t] != 0) t += LMM_WARPS;
+    }
     return t;
   };
   auto issue = [&](int t, int slot) {   // one commit group per call, also when there is nothing left to copy
@@ -256,6 +271,9 @@ ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const fl
         const int c = (i * 32 + lane) * 8;
         if (c < d) lmm_cp_async16(ring + slot * ROW_BYTES + i * 512, row + c);
       }
+      if (pre_stats != nullptr && lane == 0)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&lmm_stats[warp][slot])),
+                     "l"(pre_stats + static_cast<int64_t>(b) * T + t) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -271,6 +289,11 @@ ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const fl
   while (t < T) {
     ++count;
     asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+    float2 st_row = make_float2(0.0f, 1.0f);
+    if (pre_stats != nullptr) {
+      __syncwarp();   // lane 0's copy of the statistics is complete (its wait_group above) and visible to the warp
+      st_row = lmm_stats[warp][slot];
+    }
     float2 r[NV][4];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -288,9 +311,8 @@ ln_masked_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const fl
     if (pre_g != nullptr) {
       float m1, r1;
       if (pre_stats != nullptr) {
-        const float2 st = __ldg(pre_stats + static_cast<int64_t>(b) * T + t);
-        m1 = st.x;
-        r1 = st.y;
+        m1 = st_row.x;
+        r1 = st_row.y;
       } else {   // two-pass statistics of the raw row (only streams whose producer kept no statistics)
         float s1 = 0.0f;
 #pragma unroll
