@@ -379,10 +379,14 @@ def train_leg(dev, world, rank, dist, batch=512, steps=5, warmup=4, T_a=500, T_t
     res = {"metric": "training-step utterances/sec", "value": batch * world / ms * 1e3, "unit": UNIT, "n_gpus": world,
            "ms_per_step": ms, "steps": steps, "warmup": warmup, "dtype": "bf16", "loss": float(info["loss"].item()),
            "allreduce_ms": ar, "allreduce_bytes": trainer.numel * 4, "allreduce_share_of_step": ar / ms,
-           "allreduce_overlapped": False,
+           "allreduce_overlapped": bool(trainer._exchanging()),
            "config": {"workload": f"FusionWithEmotionDecoder BCE training step, B={batch}/GPU, T_a={T_a}, T_t={T_t}, d=768, "
                                   "H=8, N_e=4, 2+2 layers, AdamW, clip 5.0, dropout 0", "cuda_graph": True,
-                      "exchange": "one NCCL all-reduce (AVG) of the fp32 gradient arena per step, after the backward, inside the timed region"},
+                      "exchange": ("NCCL all-reduce (AVG) of the fp32 gradient arena in two parts inside the timed region: decoder, gate and "
+                                   "encoder layers >= 1 (65 % of the bytes) on NCCL's stream under the backward of encoder layer 0, layer 0's "
+                                   "share after it; allreduce_ms is what the step still waits for (events around the second part and the join)")
+                                  if trainer._exchanging() else
+                                  "one NCCL all-reduce (AVG) of the fp32 gradient arena per step, after the backward, inside the timed region"},
            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
     del trainer, model
     torch.cuda.empty_cache()

@@ -340,10 +340,14 @@ def encoder_forward_train(enc, a: E.Seq, t: E.Seq, mask_a, mask_t, drop=None):
     return a, t, tapes
 
 
-def encoder_backward(enc, tapes: list, d_a: torch.Tensor, d_t: torch.Tensor, need_dx: bool = False):
-    """-> (d_a_in | None, d_t_in | None, grads under the names of CrossModalTransformer's parameters)."""
+def encoder_backward(enc, tapes: list, d_a: torch.Tensor, d_t: torch.Tensor, need_dx: bool = False, before_first_layer=None):
+    """-> (d_a_in | None, d_t_in | None, grads under the names of CrossModalTransformer's parameters).
+    before_first_layer(G): called once, just before the backward of layer 0 (the last one to run) starts, with the
+    gradients of layers >= 1 -- the point from which a data-parallel trainer can exchange everything but layer 0."""
     G: Grads = {}
     for i in range(len(enc.layers) - 1, -1, -1):
+        if i == 0 and before_first_layer is not None:
+            before_first_layer(G)
         d_a, d_t, g = encoder_layer_backward(enc.layers[i], tapes[i], d_a, d_t, need_dx=need_dx or i > 0)
         for k, v in g.items():
             G[f"layers.{i}.{k}"] = v
@@ -379,19 +383,29 @@ def decode_loss_and_backward(model, a: E.Seq, t: E.Seq, mask_a, mask_t, labels: 
 
 
 def loss_and_gradients(model, h_a: torch.Tensor, h_t: torch.Tensor, mask_a, mask_t, labels: torch.Tensor,
-                       beta_weight: float = 0.01) -> dict:
+                       beta_weight: float = 0.01, early_hook=None) -> dict:
     """Forward and backward of one training iteration of FusionWithEmotionDecoder
     (scripts/fusion/train_fusion_seq_level_decoder.py:311-332: model(...), BCE + beta regulariser, loss.backward()).
     h_a [B, T_a, d], h_t [B, T_t, d] fp32 / bf16 CUDA features, masks bool True = PAD, labels [B, N_e].
     -> dict(loss, logits, beta, z, grads): grads holds one fp32 tensor per parameter of the model, under the
-    reference's parameter names."""
+    reference's parameter names.
+    early_hook(grads_so_far): called once, before the backward of encoder layer 0 starts, with the final gradients of
+    every other parameter (decoder, gate, encoder layers >= 1) under their full names: Trainer starts their
+    all-reduce there, so that it runs under the last layer's backward."""
     a, t = E.to_seq(h_a, "h_a"), E.to_seq(h_t, "h_t")
     mask_a = E.check_mask(mask_a, a.B, a.T, "mask_a")
     mask_t = E.check_mask(mask_t, t.B, t.T, "mask_t")
     drop = drop_for(model)
     a_enc, t_enc, enc_tapes = encoder_forward_train(model.cross_modal, a, t, mask_a, mask_t, drop)
     out = decode_loss_and_backward(model, a_enc, t_enc, mask_a, mask_t, labels, beta_weight, drop)
-    _, _, g_enc = encoder_backward(model.cross_modal, enc_tapes, out.pop("d_a"), out.pop("d_t"))
+    hook = None
+    if early_hook is not None:
+        def hook(g_layers):
+            early = dict(out["grads"])
+            early.update({f"cross_modal.{k}": v for k, v in g_layers.items()})
+            zero_key_bias_gradients(early)
+            early_hook(early)
+    _, _, g_enc = encoder_backward(model.cross_modal, enc_tapes, out.pop("d_a"), out.pop("d_t"), before_first_layer=hook)
     out["grads"].update({f"cross_modal.{k}": v for k, v in g_enc.items()})
     zero_key_bias_gradients(out["grads"])
     return out
