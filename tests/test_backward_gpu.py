@@ -369,6 +369,52 @@ def test_trainer_graph_replay_matches_eager_steps():
     assert (la - lb).abs().max().item() <= 1e-4
 
 
+def test_trainer_overlapped_exchange_path_matches_plain_steps(tmp_path):
+    """The data-parallel step with the overlapped exchange fills the arena in two parts (everything but encoder layer 0
+    when that layer's backward starts, layer 0 at the end) and, with graph=True, replays the step as TWO CUDA graphs split at
+    that point.  Forced on in a one-rank process group (the collectives are no-ops there; tools/train_overlap_check.py is
+    the 2-GPU check): five steps on changing batches must leave the parameters of five plain eager steps (<= 1e-6 against
+    lr = 1e-4), and the early hook must deliver exactly the final gradients of every parameter outside layer 0."""
+    import copy
+
+    import torch.distributed as dist
+
+    from hriemo import backward
+    from hriemo.train import Trainer
+    from models.fusion_with_emotion_decoder import FusionWithEmotionDecoder
+
+    B, T_a, T_t, d, Ne = 4, 40, 16, 768, 4
+    torch.manual_seed(671)
+    m1 = FusionWithEmotionDecoder(dropout=0.0).to(DEV)
+    m2, m3 = copy.deepcopy(m1), copy.deepcopy(m1)
+    ma, mt = _ragged(B, T_a, 672), _ragged(B, T_t, 673)
+    dist.init_process_group("gloo", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1)
+    try:
+        plain = Trainer(m1, distributed=False)
+        over, over_g = Trainer(m2, overlap=True), Trainer(m3, overlap=True, graph=True)
+        assert over._early_names and over._tail_off == min(over.slots[n][0] for n in over._early_names)
+        assert not any(n.startswith("cross_modal.layers.0.") for n in over._early_names)
+        over._exchanging = lambda: True
+        over_g._exchanging = lambda: True
+        for i in range(5):
+            h_a, h_t = _rand((B, T_a, d), 680 + i), _rand((B, T_t, d), 690 + i)
+            labels = torch.eye(Ne)[torch.randint(0, Ne, (B,), generator=torch.Generator().manual_seed(700 + i))].to(DEV)
+            a = plain.step(h_a, h_t, ma, mt, labels)
+            b = over.step(h_a, h_t, ma, mt, labels)
+            c = over_g.step(h_a, h_t, ma, mt, labels)
+            assert abs(a["loss"].item() - b["loss"].item()) <= 1e-6 and abs(a["loss"].item() - c["loss"].item()) <= 1e-6, i
+        torch.cuda.synchronize()
+        assert isinstance(over_g._graph, tuple) and len(over_g._graph) == 2
+        assert (plain.params - over.params).abs().max().item() <= 1e-6
+        assert (plain.params - over_g.params).abs().max().item() <= 1e-6
+        seen = {}
+        out = backward.loss_and_gradients(m1, h_a, h_t, ma, mt, labels, early_hook=lambda g: seen.update({k: v.clone() for k, v in g.items()}))
+        assert set(seen) == {n for n in out["grads"] if not n.startswith("cross_modal.layers.0.")}
+        assert all(torch.equal(seen[k], out["grads"][k]) for k in seen)
+    finally:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------ the autograd boundary (hriemo/autograd.py)
 def test_autograd_boundary_fills_grad_like_the_trainer_path():
     """model.train(); logits, beta, z = model(...); loss.backward() -- the drop-in contract of the reference's training
