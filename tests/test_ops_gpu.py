@@ -548,7 +548,10 @@ def test_small_attention(B, H, Nq, Tk, dh, masked):
 
 @pytest.mark.parametrize("B,H,Nq,Tk,dh,masked", [(2048, 8, 4, 64, 96, False), (5, 8, 4, 50, 96, True), (3, 4, 6, 128, 64, False),
                                                   (2, 8, 4, 4, 96, False), (3, 2, 8, 37, 128, True), (2, 4, 1, 1, 32, False),
-                                                  (2, 2, 4, 129, 64, True), (2, 2, 9, 40, 64, False)])
+                                                  (2, 2, 4, 129, 64, True), (2, 2, 9, 40, 64, False),
+                                                  # every instance of the warp-private form: dh x {<= 64, <= 128 keys}
+                                                  (3, 2, 8, 128, 128, True), (3, 4, 5, 100, 96, True), (2, 3, 7, 65, 64, False),
+                                                  (4, 3, 1, 64, 64, True), (2, 5, 8, 1, 128, False), (300, 8, 4, 64, 96, True)])
 def test_small_attention_without_probabilities(B, H, Nq, Tk, dh, masked):
     """The decoder's own call (no probability map: one CTA per (utterance, head)) against the fp64 reference and
     against the probability-map form (one CTA per utterance looping over heads), incl. NaN for a fully padded
