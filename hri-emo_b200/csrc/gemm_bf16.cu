@@ -50,6 +50,7 @@ struct GemmKernelParams {
   float2* stats_out;
   int num_n_blocks, num_k_blocks;
   int64_t num_tiles;
+  int contiguous_walk;
 };
 
 template <int BN, int STAGES, int CTAS, int EW>
@@ -93,8 +94,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   // tiles are owned by a CTA (CTAS = 1) or a CTA pair (CTAS = 2) and are BM*CTAS rows tall
-  const int64_t tile_first = blockIdx.x / CTAS;
-  const int64_t tile_step = gridDim.x / CTAS;
+  // tile walk of an owner (CTA or CTA pair): strided (owner, owner + owners, ...: the N tiles of an M block run on
+  // neighbouring owners at about the same time and share its A rows through L2 -- when they stay in step) or, with
+  // p.contiguous_walk, a contiguous range of the M-major tile order (an owner visits the N tiles of an M block one after the
+  // other and re-reads its A rows from L2 by itself).
+  const int64_t owners = gridDim.x / CTAS, owner = blockIdx.x / CTAS;
+  const int64_t tile_first = p.contiguous_walk ? p.num_tiles * owner / owners : owner;
+  const int64_t tile_end = p.contiguous_walk ? p.num_tiles * (owner + 1) / owners : p.num_tiles;
+  const int64_t tile_step = p.contiguous_walk ? 1 : owners;
   constexpr int TILE_M = BM * CTAS;
 
   extern __shared__ uint8_t smem_raw[];
@@ -162,7 +169,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // each of them in an ELECT / R2UR.BROADCAST / branch-back loop (see csrc/attention_bf16.cu)
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
-      for (int64_t tile = tile_first; tile < p.num_tiles; tile += tile_step) {
+      for (int64_t tile = tile_first; tile < tile_end; tile += tile_step) {
         const int m0 = static_cast<int>(tile / p.num_n_blocks) * TILE_M + static_cast<int>(rank) * BM;
         const int n0 = static_cast<int>(tile % p.num_n_blocks) * BN + static_cast<int>(rank) * (BN / CTAS);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -186,7 +193,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
       uint32_t stage = 0, phase = 0;
       uint32_t it = 0;
-      for (int64_t tile = tile_first; tile < p.num_tiles; tile += tile_step, ++it) {
+      for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
         const uint32_t as = it & 1u;
         const uint32_t aphase = (it >> 1) & 1u;
         mbar_wait(bar_tempty + as * 8, aphase ^ 1);  // epilogue drained this accumulator
@@ -255,10 +262,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     };
     uint32_t it = 0, slab_ctr = 0;
     const uint32_t tempty_leader = CTAS == 2 ? mapa_shared(bar_tempty, 0) : bar_tempty;
-    if (tma_resid && tile_first < p.num_tiles && has_slab(tile_first, slab0)) {
+    if (tma_resid && tile_first < tile_end && has_slab(tile_first, slab0)) {
       if (elect_one()) prefetch_resid(tile_first, slab0, 0);
     }
-    for (int64_t tile = tile_first; tile < p.num_tiles; tile += tile_step, ++it) {
+    for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
       const uint32_t as = it & 1u;
       const uint32_t aphase = (it >> 1) & 1u;
       const int64_t m_tile = (tile / p.num_n_blocks) * TILE_M + static_cast<int64_t>(rank) * BM;
@@ -386,7 +393,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             int64_t nt_ = tile;
             int ns_ = s + 1;
             if (sl + 1 >= SLABS || n0 + ns_ * 64 >= p.N) { nt_ = tile + tile_step; ns_ = slab0; }
-            if (nt_ < p.num_tiles && has_slab(nt_, ns_)) {
+            if (nt_ < tile_end && has_slab(nt_, ns_)) {
               bulk_wait_read<0>();
               prefetch_resid(nt_, ns_, slab_ctr + 1);
             }
@@ -477,6 +484,9 @@ static int launch_gemm(const hriemo_gemm_args& a, cudaStream_t stream) {
   p.num_k_blocks = (a.K + BK - 1) / BK;
   const int64_t num_m_blocks = (a.M + BM * CTAS - 1) / (BM * CTAS);
   p.num_tiles = num_m_blocks * p.num_n_blocks;
+  // HRIEMO_GEMM_WALK=contiguous | strided (default strided; read once per process: an A / B switch)
+  static const int walk_env = [] { const char* e = getenv("HRIEMO_GEMM_WALK"); return e && e[0] == 'c' ? 1 : 0; }();
+  p.contiguous_walk = walk_env;
 
   static uint64_t attr_done = 0;
   if (device_needs_attr(&attr_done)) {
