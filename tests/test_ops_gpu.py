@@ -852,6 +852,60 @@ def test_kernels_do_not_write_outside_their_outputs():
     chk("linear wgrad")
 
 
+def test_row_kernels_do_not_write_outside_their_outputs():
+    """The round-2 closing row kernels compute their store addresses from (utterance, head, row) arithmetic of their own
+    (warp-private rings, contiguous row ranges per warp): decoder attention, its backward, the streaming gate blend and the
+    LayerNorm backward ring write into sentinel-guarded views through the C ABI (compute-sanitizer is closed on this pool)."""
+    import math
+
+    from hriemo import lib as L, ops
+
+    g = torch.Generator(device=DEV).manual_seed(19)
+
+    def rnd(*shape):
+        return torch.randn(*shape, device=DEV, generator=g).bfloat16()
+
+    lib, st = L.load(), ops._stream()
+    for (B, H, Nq, Tk, dh) in [(7, 8, 4, 50, 96), (5, 4, 6, 128, 64), (3, 2, 8, 1, 128)]:
+        d = H * dh
+        q, kv = rnd(B * Nq, d), rnd(B * Tk, 2 * d)
+        k, v = kv[:, :d], kv[:, d:]
+        out, chk = _guarded(B * Nq, d, torch.bfloat16)
+        L.check(lib.hriemo_small_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), None,
+                                           out.data_ptr(), out.stride(0), None, B, H, Nq, Tk, dh, 1.0 / math.sqrt(dh), st), "small_attention")
+        chk(f"decoder attention {Nq}x{Tk}x{dh}")
+        dq, chq = _guarded(B * Nq, d, torch.bfloat16)
+        dk, chk_ = _guarded(B * Tk, d, torch.bfloat16)
+        dv, chv = _guarded(B * Tk, d, torch.bfloat16)
+        ops.small_attention_backward(q, k, v, rnd(B * Nq, d), None, B, H, Nq, Tk, dh, out=(dq, dk, dv))
+        chq(f"decoder attention backward dq {Nq}x{Tk}x{dh}")
+        chk_(f"decoder attention backward dk {Nq}x{Tk}x{dh}")
+        chv(f"decoder attention backward dv {Nq}x{Tk}x{dh}")
+    for (B, Ta, Lf, d) in [(5, 37, 13, 768), (9, 20, 20, 256), (3, 9, 7, 1024)]:
+        xa, xt = rnd(B * Ta, d), rnd(B * Lf, d)
+        vec = [torch.rand(d, device=DEV, generator=g) + 0.5 for _ in range(8)]
+        sa = torch.stack([xa.float().mean(1), torch.rsqrt(xa.float().var(1, unbiased=False) + 1e-5)], 1).contiguous()
+        stt = torch.stack([xt.float().mean(1), torch.rsqrt(xt.float().var(1, unbiased=False) + 1e-5)], 1).contiguous()
+        w = torch.sigmoid(torch.randn(B, d, device=DEV, generator=g))
+        hb, chk = _guarded(B * Lf, d, torch.bfloat16)
+        beta = torch.empty(B, 1, device=DEV)
+        L.check(lib.hriemo_gate_blend(xa.data_ptr(), xa.stride(0), Ta, xt.data_ptr(), xt.stride(0), vec[0].data_ptr(), vec[1].data_ptr(),
+                                      vec[2].data_ptr(), vec[3].data_ptr(), 1e-5, 1, w.data_ptr(), 0, hb.data_ptr(), None, hb.stride(0),
+                                      beta.data_ptr(), B, Lf, d, vec[4].data_ptr(), vec[5].data_ptr(), vec[6].data_ptr(), vec[7].data_ptr(),
+                                      sa.data_ptr(), stt.data_ptr(), st), "gate_blend")
+        chk(f"gate blend (streaming) d={d}")
+        rows = B * Ta
+        dx, chk = _guarded(rows, d, torch.bfloat16)
+        dg, db = torch.empty(d, device=DEV), torch.empty(d, device=DEV)
+        ws = torch.empty(int(lib.hriemo_layernorm_backward_workspace_bytes(rows, d)) // 4, device=DEV)
+        dy = rnd(rows, d)
+        L.check(lib.hriemo_layernorm_backward(xa.data_ptr(), xa.stride(0), dy.data_ptr(), dy.stride(0), vec[0].data_ptr(), 1e-5,
+                                              dx.data_ptr(), dx.stride(0), dg.data_ptr(), db.data_ptr(), 0, ws.data_ptr(), rows, d, st),
+                "layernorm_backward")
+        chk(f"layernorm backward ring d={d}")
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("pair,N", [(1, 288), (2, 512), (0, 3072)])
 def test_gemm_relu_mask_epilogue(pair, N):
     """EPI_BIAS_MASK: the input gradient of a Linear fed by relu(.) with the mask applied in the epilogue -- equal to the
