@@ -13,8 +13,11 @@ from .cross_modal_block_tacfn import CrossModalTransformer
 from .emotion_decoder import EmotionDecoder
 
 # Utterances are processed in slabs so that the widest intermediate (the 4d FFN hidden,
-# bf16) stays below ~8 GB whatever the batch size; every kernel still sees >= 148 tiles.
-MAX_ROWS_PER_SLAB = 1 << 20
+# bf16) stays bounded whatever the batch size; every kernel still sees >= 148 tiles.
+# HRIEMO_MAX_ROWS_PER_SLAB overrides the row budget (an A / B switch of the benchmark).
+import os as _os
+
+MAX_ROWS_PER_SLAB = int(_os.environ.get("HRIEMO_MAX_ROWS_PER_SLAB", 1 << 20))
 
 
 class FusionWithEmotionDecoder(nn.Module):
